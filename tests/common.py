@@ -1,0 +1,66 @@
+"""Shared helpers for the parity tests: golden cases, oracle construction, error metrics."""
+import os
+
+import numpy as np
+import torch
+
+from oracle.tdnet_oracle import TDOracle, state_dict_template
+from tdnet_b200.synth import synth_clip, synth_state_dict
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CH_STRIDE = 4  # tests/golden/make_golden.py stores every 4th channel of the wide taps
+
+# name -> (arch, backbone)
+GOLDEN_CASES = {
+    "td4_r18_97x161": ("td4_psp18", "resnet18"),
+    "td4_r18_128x256": ("td4_psp18", "resnet18"),
+    "td2_r50_64x128": ("td2_psp50", "resnet50"),
+    "td2_r34_80x112": ("td2_psp50", "resnet34"),
+    "td4_r50_64x64_n2": ("td4_psp18", "resnet50"),
+    "td4_r18_769x1537_chk": ("td4_psp18", "resnet18"),
+}
+
+
+def load_golden(name):
+    g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    H, W, batch, n_frames, h8, w8 = (int(v) for v in g["meta"])
+    return g, dict(H=H, W=W, batch=batch, n_frames=n_frames, h8=h8, w8=w8)
+
+
+def feat_hw(h, w):
+    for _ in range(3):
+        h, w = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    return h, w
+
+
+def make_weights(arch, backbone, h8, w8, seed=0):
+    return synth_state_dict(state_dict_template(arch, backbone, ln_shape=(h8, w8)), seed=seed)
+
+
+def make_oracle(arch, backbone, H, W, seed=0):
+    h8, w8 = feat_hw(H, W)
+    sd = make_weights(arch, backbone, h8, w8, seed)
+    return TDOracle(arch, sd, backbone), sd
+
+
+def max_abs(a, b):
+    return float((torch.as_tensor(a).double() - torch.as_tensor(b).double()).abs().max())
+
+
+def rel_l2(a, b):
+    a, b = torch.as_tensor(a).double(), torch.as_tensor(b).double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def argmax_report(test_logits, ref_logits, err):
+    """Argmax agreement the way SURVEY.md 8(c) states the gate: labels must be equal on every pixel
+    whose reference top-1/top-2 margin exceeds 2*err (err = measured max-abs logit error); pixels
+    inside that band are near-ties that even fp64-vs-fp32 runs of the reference flip."""
+    ref = torch.as_tensor(ref_logits)
+    tst = torch.as_tensor(test_logits)
+    top2 = ref.topk(2, dim=1).values
+    margin = top2[:, 0] - top2[:, 1]
+    same = tst.argmax(1) == ref.argmax(1)
+    decided = margin > 2.0 * err
+    return dict(mismatch_total=int((~same).sum()), mismatch_decided=int((~same & decided).sum()),
+                near_ties=int((~decided).sum()), pixels=int(same.numel()))

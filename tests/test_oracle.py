@@ -1,0 +1,92 @@
+"""CPU: the oracle restatement vs. what the unmodified reference produced (tests/golden/*.npz)."""
+import numpy as np
+import pytest
+import torch
+
+from common import CH_STRIDE, GOLDEN_CASES, load_golden, make_oracle, max_abs
+from oracle.tdnet_oracle import stage_plan, state_dict_template
+from tdnet_b200.synth import synth_clip
+
+# Same machine + same torch primitives in the same order: expected bit-equal; the tolerance only
+# absorbs oneDNN choosing a different kernel when the thread count differs from generation time.
+TOL = 2e-5
+
+
+@pytest.mark.parametrize("name", [n for n in GOLDEN_CASES if not n.endswith("_chk")])
+def test_oracle_matches_reference_outputs(name):
+    arch, backbone = GOLDEN_CASES[name]
+    g, m = load_golden(name)
+    oracle, _ = make_oracle(arch, backbone, m["H"], m["W"])
+    frames = synth_clip(m["n_frames"], m["H"], m["W"], batch=m["batch"], clip_id=0)
+    paths = oracle.paths
+    for i, f in enumerate(frames):
+        out = oracle(f, pos_id=i % paths)
+        assert max_abs(oracle.taps["head"], g[f"head_{i}"]) <= TOL, (name, i)
+        if f"logits_{i}" in g:
+            assert out.shape == g[f"logits_{i}"].shape
+            assert max_abs(out, g[f"logits_{i}"]) <= TOL
+            assert (out.argmax(1).numpy() == g[f"logits_{i}"].argmax(1)).mean() > 0.9999
+    t = oracle.taps
+    s = CH_STRIDE
+    assert max_abs(t["c4"][:, ::s], g["tap_c4"]) <= 5 * TOL
+    assert max_abs(t["z"][:, ::s], g["tap_z"]) <= 5 * TOL
+    assert max_abs(t["q_cur"], g["tap_q_cur"]) <= 5 * TOL
+    assert max_abs(t["v_cur"][:, ::s], g["tap_v_cur"]) <= 5 * TOL
+    assert max_abs(t["q_sub"], g["tap_q_sub"]) <= 5 * TOL
+    assert max_abs(t["k_sub"], g["tap_k_sub"]) <= 5 * TOL
+    assert max_abs(t["v_sub"], g["tap_v_sub"]) <= 5 * TOL
+    assert max_abs(t["v_prop"][:, ::s], g["tap_v_prop"]) <= 5 * TOL
+    assert max_abs(t["normed"][:, ::s], g["tap_normed"]) <= 5 * TOL
+    if arch == "td4_psp18":
+        assert max_abs(t["v2"], g["tap_hop0"]) <= 5 * TOL
+        assert max_abs(t["v3"], g["tap_hop1"]) <= 5 * TOL
+    # FIFO semantics of buffer_contral (td4_psp18.py:123-134 / td2_psp50.py:98-109)
+    assert len(oracle.Q_queue) == len(oracle.K_queue) == len(oracle.V_queue) == oracle.depth
+
+
+def test_oracle_native_size_checksums():
+    """769x1537 (the only size the unpatched reference accepts, LayerNorm([97,193]))."""
+    name = "td4_r18_769x1537_chk"
+    arch, backbone = GOLDEN_CASES[name]
+    g, m = load_golden(name)
+    assert (m["h8"], m["w8"]) == (97, 193)
+    oracle, _ = make_oracle(arch, backbone, m["H"], m["W"])
+    frames = synth_clip(m["n_frames"], m["H"], m["W"], batch=m["batch"], clip_id=0)
+    for i, f in enumerate(frames):
+        out = oracle(f, pos_id=i % 4)
+        head = oracle.taps["head"]
+        assert max_abs(head[:, :, ::8, ::16], g[f"head_sub_{i}"]) <= TOL
+        assert max_abs(out[:, :, ::64, ::128], g[f"logits_sub_{i}"]) <= TOL
+        assert abs(head.double().mean().item() - float(g[f"head_mean_{i}"])) <= 1e-6
+    assert oracle.Q_queue[0].shape == (1, 25 * 49, 64)  # P' = 1225 keys
+
+
+def test_warmup_frames_skip_attention():
+    """While the FIFO is not full the output is head(LN(v_cur)) (td4_psp18.py:142-143)."""
+    oracle, _ = make_oracle("td4_psp18", "resnet18", 64, 64)
+    frames = synth_clip(4, 64, 64)
+    for i in range(3):
+        oracle(frames[i], pos_id=i)
+        assert "v_prop" not in oracle.taps
+    oracle(frames[3], pos_id=3)
+    assert "v_prop" in oracle.taps
+
+
+def test_dilation_plan_matches_reference_table():
+    """layer3 block0 conv1 d1 / conv2 d2, rest d2; layer4 conv1 d=[4,8,16][i], conv2 d4."""
+    kind, plan = stage_plan("resnet18")
+    assert kind == "basic"
+    assert [(b["d1"], b["d2"]) for b in plan[2]] == [(1, 2), (2, 2)]
+    assert [(b["d1"], b["d2"]) for b in plan[3]] == [(4, 4), (8, 4)]
+    assert plan[1][0]["stride"] == 2 and plan[1][0]["downsample"]
+    kind, plan = stage_plan("resnet50")
+    assert kind == "bottleneck" and plan[0][0]["downsample"] and not plan[0][1]["downsample"]
+    assert [b["d1"] for b in plan[3]] == [4, 8, 16]
+
+
+def test_state_dict_template_sizes():
+    """728 tensors / 54.9 M elements for td4-psp18, 776 / 65.5 M for td2-psp50."""
+    sd = state_dict_template("td4_psp18")
+    assert len(sd) == 728 and abs(sum(v.numel() for v in sd.values()) / 1e6 - 54.9) < 0.1
+    sd = state_dict_template("td2_psp50")
+    assert len(sd) == 776 and abs(sum(v.numel() for v in sd.values()) / 1e6 - 65.5) < 0.1
