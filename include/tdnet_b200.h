@@ -1,0 +1,157 @@
+/*
+ * tdnet_b200 C-ABI: the drop-in boundary of the B200-native TDNet inference hot path.
+ *
+ * The reference (feinanshan/TDNet, /root/reference) is pure Python/PyTorch and has no FFI of its
+ * own: on its hot path every numeric step is a torch library call.  The entry
+ * points below are what a maintainer would bind in place of those calls; each one names the
+ * reference call site (file:line under /root/reference/Testing/model/pspnet/) it replaces.
+ * INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions
+ *   - Plain C: POD structs, raw device pointers, sizes.  No torch types, no exceptions.
+ *   - Every function returns 0 on success or a negative tdn_status; tdn_strerror() names it and
+ *     tdn_last_error() returns a thread-local detail string.
+ *   - Work is enqueued on `stream` (a cudaStream_t passed as void*); nothing synchronises, nothing
+ *     allocates: the caller owns every buffer including workspaces, so a whole frame can be
+ *     captured in a CUDA graph.
+ *   - Activations are NHWC ("pixel-major": channels contiguous), described by tdn_tensor with
+ *     explicit element strides so that channel slices, stride-4 sub-sampled views
+ *     (transformer.py:26 MaxPool2d(kernel 1, stride 4)) and token matrices [P, C] are all views.
+ *   - There is no CPU path.  On a device that is not sm_100 the tensor-core entry points fail with
+ *     TDN_ERR_ARCH; nothing falls back silently.
+ */
+#ifndef TDNET_B200_H_
+#define TDNET_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TDN_ABI_VERSION 1
+
+typedef enum tdn_status {
+  TDN_OK = 0,
+  TDN_ERR_INVALID = -1,   /* bad argument (null pointer, misaligned, inconsistent dims) */
+  TDN_ERR_UNSUPPORTED = -2, /* shape / option outside what the kernels implement */
+  TDN_ERR_CUDA = -3,      /* a CUDA runtime/driver call failed; see tdn_last_error() */
+  TDN_ERR_ARCH = -4,      /* device is not sm_100 (Blackwell B200) */
+  TDN_ERR_WORKSPACE = -5  /* caller-provided workspace too small */
+} tdn_status;
+
+typedef enum tdn_dtype {
+  TDN_F32 = 0,    /* one fp32 plane */
+  TDN_SPLIT16 = 1 /* two fp16 planes hi/lo with value = hi + lo: the fp32-faithful operand format of
+                     the tcgen05 kernels (22+ significant bits, see DESIGN.md "exact mode") */
+} tdn_dtype;
+
+typedef enum tdn_act {
+  TDN_ACT_NONE = 0,
+  TDN_ACT_RELU = 1,
+  TDN_ACT_LEAKY_RELU = 2 /* slope in tdn_conv2d_desc.leaky_slope (reference: nn.LeakyReLU() = 0.01) */
+} tdn_act;
+
+/* NHWC view.  Element (n,y,x,ch) lives at data[n*stride_n + y*stride_h + x*stride_w + ch].
+ * Strides are in elements.  For TDN_SPLIT16 `data` is the hi plane and `data_lo` the lo plane,
+ * both with the same strides. */
+typedef struct tdn_tensor {
+  void* data;
+  void* data_lo;
+  int32_t dtype; /* tdn_dtype */
+  int32_t n, h, w, c;
+  int64_t stride_n, stride_h, stride_w;
+} tdn_tensor;
+
+/* ------------------------------------------------------------------------------------------------
+ * tdn_conv2d: out = act( conv(in, weight) * scale[co] + bias[co] + residual )
+ *
+ * Replaces, with eval-mode BatchNorm folded into (scale, bias) by the host:
+ *   resnet.py:43-59   BasicBlock  conv3x3 -> BN -> ReLU -> conv3x3 -> BN -> (+residual) -> ReLU
+ *   resnet.py:91-111  Bottleneck  conv1x1/3x3/1x1 with BN/ReLU and the residual add
+ *   resnet.py:122-137 stem convs (input first converted by tdn_image_to_nhwc)
+ *   resnet.py:172-178 downsample conv1x1 + BN
+ *   td4_psp18.py:255-266  PSP branch conv1x1 + BN + ReLU on the pooled bins
+ *   transformer.py:18-24,142-161  Encoding w_qs / w_ks / w_vs 1x1 convs (+bias, BN+LeakyReLU)
+ *   transformer.py:84-86  Attention.fc applied per token
+ *   td4_psp18.py:295-299  FCNHead conv3x3 + BN + ReLU and the 1x1 classifier
+ *   transformer.py:128,137  torch.bmm(q, k^T) and torch.bmm(attn, v) in the SIMT attention path
+ *     (a GEMM is a 1x1 convolution over a [1,1,rows,K] view; `batch` handles the bmm batch).
+ *
+ * weight: fp32, "K-major" [cout][kh][kw][cin] when weight_kn == 0, or [kh*kw*cin][cout] when
+ *         weight_kn == 1 (used for attn @ v where v is [P', d_v]).
+ * scale/bias: fp32 [cout] or NULL (scale -> 1, bias -> 0).  residual: optional, same dims as out.
+ * batch > 1: in/out/residual/weight advance by their *_batch_stride (elements) per batch entry.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct tdn_conv2d_desc {
+  tdn_tensor in;
+  tdn_tensor out;
+  tdn_tensor residual; /* residual.data == NULL -> none */
+  const float* weight;
+  const float* scale;
+  const float* bias;
+  int32_t cout;
+  int32_t kh, kw;
+  int32_t stride, pad, dilation;
+  int32_t act;         /* tdn_act */
+  float leaky_slope;
+  int32_t weight_kn;
+  int32_t batch;       /* >= 1 */
+  int64_t in_batch_stride, out_batch_stride, residual_batch_stride, weight_batch_stride;
+} tdn_conv2d_desc;
+
+int tdn_conv2d(const tdn_conv2d_desc* desc, void* stream);
+
+/* NCHW fp32 image [n,3,H,W] (Testing/dataloader.py:69-71) -> NHWC fp32 with channels zero-padded to
+ * out.c (4), the layout every later kernel reads.  Replaces nothing numeric; it is the layout edge. */
+int tdn_image_to_nhwc(const float* nchw, int32_t n, int32_t c, int32_t h, int32_t w,
+                      const tdn_tensor* out, void* stream);
+
+/* F.max_pool2d(kernel 3, stride 2, padding 1) of the stem (resnet.py:137,208), NHWC fp32. */
+int tdn_maxpool3x3s2(const tdn_tensor* in, const tdn_tensor* out, void* stream);
+
+/* The four nn.AdaptiveAvgPool2d(1,2,3,6) of PyramidPooling (td4_psp18.py:249-252,273-276) in one
+ * pass: out is [n, 1, 50, c] with bins ordered 1x1, 2x2, 3x3, 6x6 (row-major inside each grid);
+ * bin i of size o covers rows [floor(i*H/o), ceil((i+1)*H/o)). */
+int tdn_psp_pool(const tdn_tensor* in, const tdn_tensor* out, void* workspace, uint64_t workspace_bytes,
+                 void* stream);
+/* Workspace the call above needs: n*h*12*c floats. */
+uint64_t tdn_psp_pool_workspace_bytes(int32_t n, int32_t h, int32_t c);
+
+/* F.interpolate(mode='bilinear', align_corners=True) of a small NHWC map into a (channel-slice)
+ * view of a larger one (td4_psp18.py:273-276 + the slice/cat of :278-284). */
+int tdn_bilinear_nhwc(const tdn_tensor* in, const tdn_tensor* out, void* stream);
+
+/* Strided copy between NHWC fp32 views with equal dims (the x[:, pid*c/2:...] part of the cat in
+ * td4_psp18.py:278-284, and the FIFO snapshots of buffer_contral :123-134). */
+int tdn_copy_nhwc(const tdn_tensor* in, const tdn_tensor* out, void* stream);
+
+/* In-place softmax over the last dim of a [rows, cols] fp32 matrix after multiplying by `scale`
+ * (transformer.py:128-134: attn / temperature, nn.Softmax(dim=2)).  ld = row pitch in elements. */
+int tdn_softmax_rows(float* s, int64_t rows, int32_t cols, int64_t ld, float scale, void* stream);
+
+/* Layer_Norm over the (H8,W8) map of every (n, channel) (td4_psp18.py:306-312, nn.LayerNorm([H8,W8]),
+ * biased variance, eps 1e-5) in two steps: statistics (mean/rstd are [n, c]; fixed-order fp64
+ * two-stage reduction, so results are bit-reproducible), then normalise + affine gamma/beta[h*w]. */
+int tdn_layernorm_hw_stats(const tdn_tensor* x, float* mean, float* rstd, float eps, void* workspace,
+                           uint64_t workspace_bytes, void* stream);
+uint64_t tdn_layernorm_hw_workspace_bytes(int32_t n, int32_t h, int32_t w, int32_t c);
+int tdn_layernorm_hw_apply(const tdn_tensor* x, const float* mean, const float* rstd,
+                           const float* gamma, const float* beta, const tdn_tensor* out, void* stream);
+
+/* Final F.interpolate(output, (H, W), bilinear, align_corners=True) (td4_psp18.py:227): NHWC fp32
+ * low-resolution logits -> NCHW fp32 [n, c, H, W], the tensor test.py:53,61 consumes. */
+int tdn_upsample_logits(const tdn_tensor* in, float* out_nchw, int32_t out_h, int32_t out_w,
+                        void* stream);
+
+/* Library info / errors. */
+int tdn_abi_version(void);
+const char* tdn_strerror(int status);
+const char* tdn_last_error(void);
+/* Compute capability of the current device as major*10+minor, or a negative tdn_status. */
+int tdn_device_arch(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TDNET_B200_H_ */

@@ -1,0 +1,2 @@
+"""tdnet_b200: B200-native (sm_100a) implementation of the TDNet per-frame inference hot path."""
+__version__ = "0.1.0"

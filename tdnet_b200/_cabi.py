@@ -1,0 +1,83 @@
+"""ctypes binding of libtdnet_b200.so (the C-ABI declared in include/tdnet_b200.h).
+
+The library is built in-tree by __graft_entry__.build() (nvcc, sm_100a).  There is no fallback: if
+the shared object is missing or a call fails, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libtdnet_b200.so")
+
+TDN_F32, TDN_SPLIT16 = 0, 1
+ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
+
+
+class Tensor(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("data_lo", C.c_void_p), ("dtype", C.c_int32),
+                ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("c", C.c_int32),
+                ("stride_n", C.c_int64), ("stride_h", C.c_int64), ("stride_w", C.c_int64)]
+
+
+class Conv2dDesc(C.Structure):
+    _fields_ = [("in_", Tensor), ("out", Tensor), ("residual", Tensor),
+                ("weight", C.c_void_p), ("scale", C.c_void_p), ("bias", C.c_void_p),
+                ("cout", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32),
+                ("stride", C.c_int32), ("pad", C.c_int32), ("dilation", C.c_int32),
+                ("act", C.c_int32), ("leaky_slope", C.c_float), ("weight_kn", C.c_int32),
+                ("batch", C.c_int32),
+                ("in_batch_stride", C.c_int64), ("out_batch_stride", C.c_int64),
+                ("residual_batch_stride", C.c_int64), ("weight_batch_stride", C.c_int64)]
+
+
+# symbol -> (restype, argtypes); tests/test_cabi.py checks this list against include/tdnet_b200.h
+_TP = C.POINTER(Tensor)
+SIGNATURES = {
+    "tdn_abi_version": (C.c_int, []),
+    "tdn_strerror": (C.c_char_p, [C.c_int]),
+    "tdn_last_error": (C.c_char_p, []),
+    "tdn_device_arch": (C.c_int, []),
+    "tdn_conv2d": (C.c_int, [C.POINTER(Conv2dDesc), C.c_void_p]),
+    "tdn_image_to_nhwc": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _TP, C.c_void_p]),
+    "tdn_maxpool3x3s2": (C.c_int, [_TP, _TP, C.c_void_p]),
+    "tdn_psp_pool": (C.c_int, [_TP, _TP, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "tdn_psp_pool_workspace_bytes": (C.c_uint64, [C.c_int32, C.c_int32, C.c_int32]),
+    "tdn_bilinear_nhwc": (C.c_int, [_TP, _TP, C.c_void_p]),
+    "tdn_copy_nhwc": (C.c_int, [_TP, _TP, C.c_void_p]),
+    "tdn_softmax_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_float, C.c_void_p]),
+    "tdn_layernorm_hw_stats": (C.c_int, [_TP, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "tdn_layernorm_hw_workspace_bytes": (C.c_uint64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "tdn_layernorm_hw_apply": (C.c_int, [_TP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _TP, C.c_void_p]),
+    "tdn_upsample_logits": (C.c_int, [_TP, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+}
+
+_lib = None
+
+
+def load():
+    """dlopen the in-tree library and declare every prototype.  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise RuntimeError(
+            f"tdnet_b200: CUDA library not built ({LIB_PATH} missing). Run "
+            "`python -c 'import __graft_entry__ as g; g.build()'` in the repo root. "
+            "There is no CPU or PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here = header/library drift
+        fn.restype, fn.argtypes = res, args
+    if lib.tdn_abi_version() != 1:
+        raise RuntimeError("tdnet_b200: ABI version mismatch between _cabi.py and the library")
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        lib = load()
+        raise RuntimeError(f"tdnet_b200 {what}: {lib.tdn_strerror(rc).decode()} ({rc}): "
+                           f"{lib.tdn_last_error().decode()}")

@@ -1,0 +1,128 @@
+// extern "C" surface of libtdnet_b200.so (see include/tdnet_b200.h).  Argument validation and
+// kernel selection live here; no function throws or synchronises.
+#include "common.cuh"
+
+#include <string.h>
+
+namespace tdn {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+int check_f32_tensor(const tdn_tensor* t, const char* what) {
+  TDN_REQUIRE(t != nullptr && t->data != nullptr, TDN_ERR_INVALID, "%s: null tensor", what);
+  TDN_REQUIRE(t->dtype == TDN_F32, TDN_ERR_UNSUPPORTED, "%s: expected an fp32 plane", what);
+  TDN_REQUIRE(t->n > 0 && t->h > 0 && t->w > 0 && t->c > 0, TDN_ERR_INVALID, "%s: empty dims [%d,%d,%d,%d]",
+              what, t->n, t->h, t->w, t->c);
+  return TDN_OK;
+}
+
+int conv2d_simt(const tdn_conv2d_desc* d, cudaStream_t stream);
+int image_to_nhwc(const float*, int, int, int, int, const tdn_tensor*, cudaStream_t);
+int maxpool3x3s2(const tdn_tensor*, const tdn_tensor*, cudaStream_t);
+int psp_pool(const tdn_tensor*, const tdn_tensor*, float*, size_t, cudaStream_t);
+int bilinear_nhwc(const tdn_tensor*, const tdn_tensor*, cudaStream_t);
+int copy_nhwc(const tdn_tensor*, const tdn_tensor*, cudaStream_t);
+int softmax_rows(float*, long long, int, long long, float, cudaStream_t);
+int layernorm_hw_stats(const tdn_tensor*, float*, float*, float, void*, size_t, cudaStream_t);
+int layernorm_hw_apply(const tdn_tensor*, const float*, const float*, const float*, const float*,
+                       const tdn_tensor*, cudaStream_t);
+int upsample_logits(const tdn_tensor*, float*, int, int, cudaStream_t);
+
+}  // namespace tdn
+
+using namespace tdn;
+
+extern "C" {
+
+int tdn_abi_version(void) { return TDN_ABI_VERSION; }
+
+const char* tdn_strerror(int status) {
+  switch (status) {
+    case TDN_OK: return "ok";
+    case TDN_ERR_INVALID: return "invalid argument";
+    case TDN_ERR_UNSUPPORTED: return "unsupported shape or option";
+    case TDN_ERR_CUDA: return "CUDA error";
+    case TDN_ERR_ARCH: return "device is not sm_100 (B200)";
+    case TDN_ERR_WORKSPACE: return "workspace too small";
+    default: return "unknown status";
+  }
+}
+
+const char* tdn_last_error(void) { return get_error(); }
+
+int tdn_device_arch(void) {
+  int dev = 0, major = 0, minor = 0;
+  TDN_CUDA_OK(cudaGetDevice(&dev));
+  TDN_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  TDN_CUDA_OK(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  return major * 10 + minor;
+}
+
+int tdn_conv2d(const tdn_conv2d_desc* d, void* stream) {
+  TDN_REQUIRE(d != nullptr, TDN_ERR_INVALID, "conv2d: null descriptor");
+  TDN_REQUIRE(d->in.data && d->out.data && d->weight, TDN_ERR_INVALID, "conv2d: null data pointer");
+  TDN_REQUIRE(d->kh > 0 && d->kw > 0 && d->stride > 0 && d->dilation > 0 && d->pad >= 0 && d->cout > 0 &&
+                  d->batch >= 1, TDN_ERR_INVALID, "conv2d: bad geometry");
+  TDN_REQUIRE(d->in.n > 0 && d->in.h > 0 && d->in.w > 0 && d->in.c > 0, TDN_ERR_INVALID,
+              "conv2d: empty input");
+  return conv2d_simt(d, (cudaStream_t)stream);
+}
+
+int tdn_image_to_nhwc(const float* nchw, int32_t n, int32_t c, int32_t h, int32_t w, const tdn_tensor* out,
+                      void* stream) {
+  return image_to_nhwc(nchw, n, c, h, w, out, (cudaStream_t)stream);
+}
+
+int tdn_maxpool3x3s2(const tdn_tensor* in, const tdn_tensor* out, void* stream) {
+  return maxpool3x3s2(in, out, (cudaStream_t)stream);
+}
+
+uint64_t tdn_psp_pool_workspace_bytes(int32_t n, int32_t h, int32_t c) {
+  return (uint64_t)n * h * 12 * c * sizeof(float);
+}
+
+int tdn_psp_pool(const tdn_tensor* in, const tdn_tensor* out, void* workspace, uint64_t workspace_bytes,
+                 void* stream) {
+  return psp_pool(in, out, (float*)workspace, (size_t)workspace_bytes, (cudaStream_t)stream);
+}
+
+int tdn_bilinear_nhwc(const tdn_tensor* in, const tdn_tensor* out, void* stream) {
+  return bilinear_nhwc(in, out, (cudaStream_t)stream);
+}
+
+int tdn_copy_nhwc(const tdn_tensor* in, const tdn_tensor* out, void* stream) {
+  return copy_nhwc(in, out, (cudaStream_t)stream);
+}
+
+int tdn_softmax_rows(float* s, int64_t rows, int32_t cols, int64_t ld, float scale, void* stream) {
+  return softmax_rows(s, rows, cols, ld, scale, (cudaStream_t)stream);
+}
+
+uint64_t tdn_layernorm_hw_workspace_bytes(int32_t n, int32_t h, int32_t w, int32_t c) {
+  uint64_t chunks = ((uint64_t)h * w + 63) / 64;
+  return (uint64_t)n * chunks * c * 16;
+}
+
+int tdn_layernorm_hw_stats(const tdn_tensor* x, float* mean, float* rstd, float eps, void* workspace,
+                           uint64_t workspace_bytes, void* stream) {
+  return layernorm_hw_stats(x, mean, rstd, eps, workspace, (size_t)workspace_bytes, (cudaStream_t)stream);
+}
+
+int tdn_layernorm_hw_apply(const tdn_tensor* x, const float* mean, const float* rstd, const float* gamma,
+                           const float* beta, const tdn_tensor* out, void* stream) {
+  return layernorm_hw_apply(x, mean, rstd, gamma, beta, out, (cudaStream_t)stream);
+}
+
+int tdn_upsample_logits(const tdn_tensor* in, float* out_nchw, int32_t out_h, int32_t out_w, void* stream) {
+  return upsample_logits(in, out_nchw, out_h, out_w, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,438 @@
+// HBM-bound layout / pooling / normalisation / resampling kernels of the frame (fp32, NHWC).
+// None of these has data reuse worth tensor cores; the rules that matter are coalesced, vectorised
+// access and enough CTAs to fill 148 SMs.
+#include "common.cuh"
+
+namespace tdn {
+
+// ---------------------------------------------------------------------------------------------
+// NCHW image -> NHWC, channels padded with zeros to 4 (one float4 store per pixel).
+// ---------------------------------------------------------------------------------------------
+__global__ void image_to_nhwc_kernel(const float* __restrict__ src, int n, int c, int h, int w,
+                                     View out) {
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long total = (long long)n * h * w;
+  if (idx >= total) return;
+  int x = idx % w;
+  long long t = idx / w;
+  int y = t % h;
+  int b = t / h;
+  const long long plane = (long long)h * w;
+  const float* s = src + (long long)b * c * plane + (long long)y * w + x;
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int ch = 0; ch < c && ch < 4; ++ch) v[ch] = __ldg(s + ch * plane);
+  float* d = out.p + b * out.sn + y * out.sh + x * out.sw;
+  *reinterpret_cast<float4*>(d) = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+int image_to_nhwc(const float* nchw, int n, int c, int h, int w, const tdn_tensor* out,
+                  cudaStream_t stream) {
+  TDN_REQUIRE(nchw && out && out->data, TDN_ERR_INVALID, "image_to_nhwc: null pointer");
+  TDN_REQUIRE(c <= 4 && out->c == 4 && out->n == n && out->h == h && out->w == w && vec4_ok(*out),
+              TDN_ERR_INVALID, "image_to_nhwc: expects c<=4 and a float4-aligned [n,h,w,4] output");
+  long long total = (long long)n * h * w;
+  image_to_nhwc_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(nchw, n, c, h, w, make_view(*out));
+  TDN_LAUNCH_OK();
+  return TDN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// 3x3 stride-2 pad-1 max pool (padding acts as -inf), float4 over channels.
+// ---------------------------------------------------------------------------------------------
+__global__ void maxpool3x3s2_kernel(View in, View out) {
+  const int c4 = out.c >> 2;
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long total = (long long)out.n * out.h * out.w * c4;
+  if (idx >= total) return;
+  int cq = idx % c4;
+  long long t = idx / c4;
+  int ox = t % out.w; t /= out.w;
+  int oy = t % out.h;
+  int b = t / out.h;
+  float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy) {
+    int iy = oy * 2 - 1 + dy;
+    if (iy < 0 || iy >= in.h) continue;
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) {
+      int ix = ox * 2 - 1 + dx;
+      if (ix < 0 || ix >= in.w) continue;
+      float4 v = *reinterpret_cast<const float4*>(in.p + b * in.sn + iy * in.sh + ix * in.sw + cq * 4);
+      m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+    }
+  }
+  *reinterpret_cast<float4*>(out.p + b * out.sn + oy * out.sh + ox * out.sw + cq * 4) = m;
+}
+
+int maxpool3x3s2(const tdn_tensor* in, const tdn_tensor* out, cudaStream_t stream) {
+  int rc;
+  if ((rc = check_f32_tensor(in, "maxpool.in"))) return rc;
+  if ((rc = check_f32_tensor(out, "maxpool.out"))) return rc;
+  TDN_REQUIRE(vec4_ok(*in) && vec4_ok(*out), TDN_ERR_INVALID, "maxpool: float4-aligned views required");
+  TDN_REQUIRE(out->h == (in->h - 1) / 2 + 1 && out->w == (in->w - 1) / 2 + 1 && out->c == in->c &&
+                  out->n == in->n, TDN_ERR_INVALID, "maxpool: output dims mismatch");
+  long long total = (long long)out->n * out->h * out->w * (out->c / 4);
+  maxpool3x3s2_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(make_view(*in), make_view(*out));
+  TDN_LAUNCH_OK();
+  return TDN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pyramid pooling, 50 bins (1x1, 2x2, 3x3, 6x6) in two separable passes.
+// Pass 1: per image row, the sums over the 12 column ranges -> rowsum[n][H][12][C]   (reads x once
+//         from HBM; the 4 pyramid levels re-read the row from L1/L2).
+// Pass 2: per bin, sum its rows of the matching column range and divide by the bin area.
+// Bin i of o covers [floor(i*L/o), ceil((i+1)*L/o)) (AdaptiveAvgPool2d; bins overlap when o !| L).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int bin_start(int i, int o, int len) { return (i * len) / o; }
+__device__ __forceinline__ int bin_end(int i, int o, int len) { return ((i + 1) * len + o - 1) / o; }
+
+__global__ void psp_rowsum_kernel(View in, float* __restrict__ rowsum) {
+  const int y = blockIdx.x, b = blockIdx.y;
+  const float* row = in.p + b * in.sn + y * in.sh;
+  float* dst = rowsum + ((long long)(b * in.h + y) * 12) * in.c;
+  for (int c = threadIdx.x; c < in.c; c += blockDim.x) {
+    int r = 0;
+#pragma unroll
+    for (int lv = 0; lv < 4; ++lv) {
+      const int o = lv == 0 ? 1 : lv == 1 ? 2 : lv == 2 ? 3 : 6;
+      for (int j = 0; j < o; ++j, ++r) {
+        int x0 = bin_start(j, o, in.w), x1 = bin_end(j, o, in.w);
+        float s = 0.f;
+        for (int x = x0; x < x1; ++x) s += row[x * in.sw + c];
+        dst[(long long)r * in.c + c] = s;
+      }
+    }
+  }
+}
+
+__global__ void psp_binsum_kernel(const float* __restrict__ rowsum, View out, int H, int W) {
+  const int bin = blockIdx.x, b = blockIdx.y;
+  int o, local, roff;
+  if (bin < 1) { o = 1; local = bin; roff = 0; }
+  else if (bin < 5) { o = 2; local = bin - 1; roff = 1; }
+  else if (bin < 14) { o = 3; local = bin - 5; roff = 3; }
+  else { o = 6; local = bin - 14; roff = 6; }
+  const int i = local / o, j = local % o;
+  const int y0 = bin_start(i, o, H), y1 = bin_end(i, o, H);
+  const int x0 = bin_start(j, o, W), x1 = bin_end(j, o, W);
+  const float inv = 1.f / (float)((y1 - y0) * (x1 - x0));
+  for (int c = threadIdx.x; c < out.c; c += blockDim.x) {
+    float s = 0.f;
+    for (int y = y0; y < y1; ++y)
+      s += rowsum[((long long)(b * H + y) * 12 + roff + j) * out.c + c];
+    out.p[b * out.sn + bin * out.sw + c] = s * inv;
+  }
+}
+
+int psp_pool(const tdn_tensor* in, const tdn_tensor* out, float* workspace, size_t workspace_bytes,
+             cudaStream_t stream) {
+  int rc;
+  if ((rc = check_f32_tensor(in, "psp_pool.in"))) return rc;
+  if ((rc = check_f32_tensor(out, "psp_pool.out"))) return rc;
+  TDN_REQUIRE(out->n == in->n && out->h == 1 && out->w == 50 && out->c == in->c, TDN_ERR_INVALID,
+              "psp_pool: out must be [n,1,50,c]");
+  size_t need = (size_t)in->n * in->h * 12 * in->c * sizeof(float);
+  TDN_REQUIRE(workspace && workspace_bytes >= need, TDN_ERR_WORKSPACE,
+              "psp_pool: workspace %zu < %zu bytes", workspace_bytes, need);
+  int threads = in->c >= 512 ? 512 : (in->c >= 256 ? 256 : 128);
+  psp_rowsum_kernel<<<dim3(in->h, in->n), threads, 0, stream>>>(make_view(*in), workspace);
+  TDN_LAUNCH_OK();
+  psp_binsum_kernel<<<dim3(50, in->n), threads, 0, stream>>>(workspace, make_view(*out), in->h, in->w);
+  TDN_LAUNCH_OK();
+  return TDN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Bilinear resize, align_corners=True, NHWC -> NHWC (channel-slice views allowed).
+// src = dst * (in-1)/(out-1); index0 = floor, lambda = frac (ATen upsample semantics).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void src_index(int dst, float scale, int in_size, int& i0, int& i1, float& l1) {
+  float s = scale * (float)dst;
+  i0 = min((int)s, in_size - 1);
+  i1 = min(i0 + 1, in_size - 1);
+  l1 = fminf(fmaxf(s - (float)i0, 0.f), 1.f);
+}
+
+__global__ void bilinear_nhwc_kernel(View in, View out, float sy, float sx) {
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long total = (long long)out.n * out.h * out.w * out.c;
+  if (idx >= total) return;
+  int c = idx % out.c;
+  long long t = idx / out.c;
+  int x = t % out.w; t /= out.w;
+  int y = t % out.h;
+  int b = t / out.h;
+  int y0, y1, x0, x1; float ly, lx;
+  src_index(y, sy, in.h, y0, y1, ly);
+  src_index(x, sx, in.w, x0, x1, lx);
+  const float* base = in.p + b * in.sn + c;
+  float v00 = base[y0 * in.sh + x0 * in.sw], v01 = base[y0 * in.sh + x1 * in.sw];
+  float v10 = base[y1 * in.sh + x0 * in.sw], v11 = base[y1 * in.sh + x1 * in.sw];
+  float top = v00 * (1.f - lx) + v01 * lx;
+  float bot = v10 * (1.f - lx) + v11 * lx;
+  out.p[b * out.sn + y * out.sh + x * out.sw + c] = top * (1.f - ly) + bot * ly;
+}
+
+static inline float ac_scale(int in_size, int out_size) {
+  return out_size > 1 ? (float)(in_size - 1) / (float)(out_size - 1) : 0.f;
+}
+
+int bilinear_nhwc(const tdn_tensor* in, const tdn_tensor* out, cudaStream_t stream) {
+  int rc;
+  if ((rc = check_f32_tensor(in, "bilinear.in"))) return rc;
+  if ((rc = check_f32_tensor(out, "bilinear.out"))) return rc;
+  TDN_REQUIRE(in->n == out->n && in->c == out->c, TDN_ERR_INVALID, "bilinear: n/c mismatch");
+  long long total = (long long)out->n * out->h * out->w * out->c;
+  bilinear_nhwc_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(
+      make_view(*in), make_view(*out), ac_scale(in->h, out->h), ac_scale(in->w, out->w));
+  TDN_LAUNCH_OK();
+  return TDN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Strided NHWC copy (float4 when possible).
+// ---------------------------------------------------------------------------------------------
+template <int VEC>
+__global__ void copy_nhwc_kernel(View in, View out) {
+  const int cv = out.c / VEC;
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long total = (long long)out.n * out.h * out.w * cv;
+  if (idx >= total) return;
+  int c = (idx % cv) * VEC;
+  long long t = idx / cv;
+  int x = t % out.w; t /= out.w;
+  int y = t % out.h;
+  int b = t / out.h;
+  const float* s = in.p + b * in.sn + y * in.sh + x * in.sw + c;
+  float* d = out.p + b * out.sn + y * out.sh + x * out.sw + c;
+  if (VEC == 4) *reinterpret_cast<float4*>(d) = *reinterpret_cast<const float4*>(s);
+  else *d = *s;
+}
+
+int copy_nhwc(const tdn_tensor* in, const tdn_tensor* out, cudaStream_t stream) {
+  int rc;
+  if ((rc = check_f32_tensor(in, "copy.in"))) return rc;
+  if ((rc = check_f32_tensor(out, "copy.out"))) return rc;
+  TDN_REQUIRE(in->n == out->n && in->h == out->h && in->w == out->w && in->c == out->c,
+              TDN_ERR_INVALID, "copy_nhwc: dims mismatch");
+  if (vec4_ok(*in) && vec4_ok(*out)) {
+    long long total = (long long)out->n * out->h * out->w * (out->c / 4);
+    copy_nhwc_kernel<4><<<ceil_div(total, 256), 256, 0, stream>>>(make_view(*in), make_view(*out));
+  } else {
+    long long total = (long long)out->n * out->h * out->w * out->c;
+    copy_nhwc_kernel<1><<<ceil_div(total, 256), 256, 0, stream>>>(make_view(*in), make_view(*out));
+  }
+  TDN_LAUNCH_OK();
+  return TDN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Row softmax with pre-scale (one CTA per row; three passes over a row that stays in L1/L2).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ s, int cols,
+                                                           long long ld, float scale) {
+  __shared__ float red[8];
+  float* row = s + blockIdx.x * ld;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  float m = -INFINITY;
+  for (int c = threadIdx.x; c < cols; c += 256) m = fmaxf(m, row[c] * scale);
+  m = warp_max(m);
+  if (lane == 0) red[wid] = m;
+  __syncthreads();
+  m = red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int c = threadIdx.x; c < cols; c += 256) {
+    float e = expf(row[c] * scale - m);
+    row[c] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) red[wid] = sum;
+  __syncthreads();
+  sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sum += red[i];
+  const float inv = 1.f / sum;
+  for (int c = threadIdx.x; c < cols; c += 256) row[c] *= inv;
+}
+
+int softmax_rows(float* s, long long rows, int cols, long long ld, float scale, cudaStream_t stream) {
+  TDN_REQUIRE(s && rows > 0 && cols > 0 && ld >= cols, TDN_ERR_INVALID, "softmax_rows: bad arguments");
+  TDN_REQUIRE(rows < (1ll << 31), TDN_ERR_UNSUPPORTED, "softmax_rows: too many rows");
+  softmax_rows_kernel<<<(unsigned)rows, 256, 0, stream>>>(s, cols, ld, scale);
+  TDN_LAUNCH_OK();
+  return TDN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm over the (H, W) map per (n, channel): fixed-order two-stage reduction in fp64 (bit
+// reproducible run to run; no atomics), then a fused normalise + spatial affine.
+// ---------------------------------------------------------------------------------------------
+constexpr int LN_CHUNK = 64;  // pixels per partial
+
+__global__ void ln_partial_kernel(View x, double2* __restrict__ part, int chunks) {
+  const int chunk = blockIdx.x, b = blockIdx.y;
+  const int P = x.h * x.w;
+  const int p0 = chunk * LN_CHUNK, p1 = min(p0 + LN_CHUNK, P);
+  for (int c = threadIdx.x; c < x.c; c += blockDim.x) {
+    double s = 0.0, q = 0.0;
+    for (int p = p0; p < p1; ++p) {
+      int y = p / x.w, xx = p - y * x.w;
+      double v = (double)x.p[b * x.sn + y * x.sh + xx * x.sw + c];
+      s += v; q += v * v;
+    }
+    part[((long long)b * chunks + chunk) * x.c + c] = make_double2(s, q);
+  }
+}
+
+__global__ void ln_final_kernel(const double2* __restrict__ part, int chunks, int C, int P, float eps,
+                                float* __restrict__ mean, float* __restrict__ rstd) {
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int k = 0; k < chunks; ++k) {
+    double2 v = part[((long long)b * chunks + k) * C + c];
+    s += v.x; q += v.y;
+  }
+  double mu = s / P;
+  double var = q / P - mu * mu;
+  if (var < 0.0) var = 0.0;
+  mean[b * C + c] = (float)mu;
+  rstd[b * C + c] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+int layernorm_hw_stats(const tdn_tensor* x, float* mean, float* rstd, float eps, void* workspace,
+                       size_t workspace_bytes, cudaStream_t stream) {
+  int rc;
+  if ((rc = check_f32_tensor(x, "layernorm.x"))) return rc;
+  TDN_REQUIRE(mean && rstd, TDN_ERR_INVALID, "layernorm_hw_stats: null output");
+  const int P = x->h * x->w;
+  const int chunks = ceil_div(P, LN_CHUNK);
+  size_t need = (size_t)x->n * chunks * x->c * sizeof(double2);
+  TDN_REQUIRE(workspace && workspace_bytes >= need && aligned16(workspace), TDN_ERR_WORKSPACE,
+              "layernorm_hw_stats: workspace %zu < %zu bytes", workspace_bytes, need);
+  int threads = x->c >= 256 ? 256 : 128;
+  ln_partial_kernel<<<dim3(chunks, x->n), threads, 0, stream>>>(make_view(*x), (double2*)workspace, chunks);
+  TDN_LAUNCH_OK();
+  ln_final_kernel<<<dim3(ceil_div(x->c, 128), x->n), 128, 0, stream>>>((const double2*)workspace, chunks,
+                                                                      x->c, P, eps, mean, rstd);
+  TDN_LAUNCH_OK();
+  return TDN_OK;
+}
+
+__global__ void ln_apply_kernel(View x, View out, const float* __restrict__ mean,
+                                const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                const float* __restrict__ beta) {
+  const int c4 = x.c >> 2;
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long total = (long long)x.n * x.h * x.w * c4;
+  if (idx >= total) return;
+  int c = (idx % c4) * 4;
+  long long t = idx / c4;
+  int xx = t % x.w; t /= x.w;
+  int y = t % x.h;
+  int b = t / x.h;
+  const float g = gamma[y * x.w + xx], be = beta[y * x.w + xx];
+  float4 v = *reinterpret_cast<const float4*>(x.p + b * x.sn + y * x.sh + xx * x.sw + c);
+  float4 mu = *reinterpret_cast<const float4*>(mean + b * x.c + c);
+  float4 rs = *reinterpret_cast<const float4*>(rstd + b * x.c + c);
+  float4 o;
+  o.x = (v.x - mu.x) * rs.x * g + be;
+  o.y = (v.y - mu.y) * rs.y * g + be;
+  o.z = (v.z - mu.z) * rs.z * g + be;
+  o.w = (v.w - mu.w) * rs.w * g + be;
+  *reinterpret_cast<float4*>(out.p + b * out.sn + y * out.sh + xx * out.sw + c) = o;
+}
+
+int layernorm_hw_apply(const tdn_tensor* x, const float* mean, const float* rstd, const float* gamma,
+                       const float* beta, const tdn_tensor* out, cudaStream_t stream) {
+  int rc;
+  if ((rc = check_f32_tensor(x, "layernorm.x"))) return rc;
+  if ((rc = check_f32_tensor(out, "layernorm.out"))) return rc;
+  TDN_REQUIRE(mean && rstd && gamma && beta, TDN_ERR_INVALID, "layernorm_hw_apply: null pointer");
+  TDN_REQUIRE(vec4_ok(*x) && vec4_ok(*out) && aligned16(mean) && aligned16(rstd), TDN_ERR_INVALID,
+              "layernorm_hw_apply: float4-aligned views required");
+  TDN_REQUIRE(x->n == out->n && x->h == out->h && x->w == out->w && x->c == out->c, TDN_ERR_INVALID,
+              "layernorm_hw_apply: dims mismatch");
+  long long total = (long long)x->n * x->h * x->w * (x->c / 4);
+  ln_apply_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(make_view(*x), make_view(*out), mean, rstd,
+                                                            gamma, beta);
+  TDN_LAUNCH_OK();
+  return TDN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Final x8 bilinear upsample (align_corners) NHWC low-res logits -> NCHW fp32.
+// One thread produces 4 consecutive x of one (n, y) for all classes: float4 streaming stores that are
+// contiguous across the warp (the 159 MB/frame output write is the whole cost; the 2.5 MB input
+// stays in L1/L2).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) upsample_logits_kernel(View in, float* __restrict__ out, int H,
+                                                              int W, float sy, float sx) {
+  const int W4 = (W + 3) >> 2;
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long total = (long long)in.n * H * W4;
+  if (idx >= total) return;
+  int xq = idx % W4;
+  long long t = idx / W4;
+  int y = t % H;
+  int b = t / H;
+  int y0, y1; float ly;
+  src_index(y, sy, in.h, y0, y1, ly);
+  int x0[4], x1[4]; float lx[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) src_index(min(xq * 4 + j, W - 1), sx, in.w, x0[j], x1[j], lx[j]);
+  const float* r0 = in.p + b * in.sn + y0 * in.sh;
+  const float* r1 = in.p + b * in.sn + y1 * in.sh;
+  const long long plane = (long long)H * W;
+  float* o = out + (long long)b * in.c * plane + (long long)y * W + xq * 4;
+  const bool full = (xq * 4 + 3 < W) && ((W & 3) == 0);
+  for (int c = 0; c < in.c; ++c) {
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float top = r0[x0[j] * in.sw + c] * (1.f - lx[j]) + r0[x1[j] * in.sw + c] * lx[j];
+      float bot = r1[x0[j] * in.sw + c] * (1.f - lx[j]) + r1[x1[j] * in.sw + c] * lx[j];
+      v[j] = top * (1.f - ly) + bot * ly;
+    }
+    float* oc = o + c * plane;
+    if (full) {
+      __stcs(reinterpret_cast<float4*>(oc), make_float4(v[0], v[1], v[2], v[3]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (xq * 4 + j < W) oc[j] = v[j];
+    }
+  }
+}
+
+int upsample_logits(const tdn_tensor* in, float* out_nchw, int out_h, int out_w, cudaStream_t stream) {
+  int rc;
+  if ((rc = check_f32_tensor(in, "upsample.in"))) return rc;
+  TDN_REQUIRE(out_nchw && out_h > 0 && out_w > 0, TDN_ERR_INVALID, "upsample_logits: bad output");
+  TDN_REQUIRE(aligned16(out_nchw), TDN_ERR_INVALID, "upsample_logits: output must be 16-byte aligned");
+  long long total = (long long)in->n * out_h * ((out_w + 3) / 4);
+  upsample_logits_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(
+      make_view(*in), out_nchw, out_h, out_w, ac_scale(in->h, out_h), ac_scale(in->w, out_w));
+  TDN_LAUNCH_OK();
+  return TDN_OK;
+}
+
+}  // namespace tdn

@@ -1,0 +1,159 @@
+"""Shared implementation of the two TD models: parameter containers with the reference's state-dict
+layout, the Q/K/V FIFO, and `forward(img, pos_id)` dispatching to the CUDA frame engine.
+
+API kept from the reference (Testing/model/pspnet/td4_psp18.py:29-240, td2_psp50.py:29-166):
+constructor kwargs, `eval()/to()`, `state_dict()` keys and shapes (checkpoints load with
+strict=True), `forward(img, pos_id) -> fp32 [n, nclass, H, W]` on the input's device, the observable
+`Q_queue / K_queue / V_queue` lists, `pretrained_mp_load()`.
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict
+
+import torch
+import torch.nn as nn
+
+from . import arch as A
+
+
+class _Group(nn.Module):
+    """Pure parameter container; never called."""
+
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError("parameter container; the computation runs in the CUDA engine")
+
+
+def _attach(root: nn.Module, key: str, shape, kind: str):
+    *parents, leaf = key.split(".")
+    mod = root
+    for p in parents:
+        if not hasattr(mod, p):
+            mod.add_module(p, _Group())
+        mod = getattr(mod, p)
+    if kind == "param":
+        t = torch.zeros(shape)
+        if leaf == "weight" and len(shape) <= 2 and not key.endswith("fc.weight"):
+            t.fill_(1.0)  # norm gammas default to 1 as in the reference constructors
+        mod.register_parameter(leaf, nn.Parameter(t, requires_grad=False))
+    elif kind == "buffer":
+        mod.register_buffer(leaf, torch.ones(shape) if leaf == "running_var" else torch.zeros(shape))
+    else:
+        mod.register_buffer(leaf, torch.zeros(shape, dtype=torch.long))
+
+
+def _default_init_(module: nn.Module, seed=0):
+    """Random init for the no-checkpoint case (the reference also runs with random weights when the
+    file is missing, td4_psp18.py:239-240).  He-normal on conv kernels (resnet.py:162-165)."""
+    g = torch.Generator().manual_seed(seed)
+    for name, p in module.named_parameters():
+        if p.dim() == 4:
+            fan = p.shape[0] * p.shape[2] * p.shape[3]
+            p.data.copy_(torch.randn(p.shape, generator=g) * (2.0 / fan) ** 0.5)
+        elif p.dim() == 2 and name.endswith("fc.weight"):
+            p.data.copy_(torch.randn(p.shape, generator=g) * 0.01)
+
+
+class TDModel(nn.Module):
+    ARCH = None          # 'td4_psp18' | 'td2_psp50'
+    PATHS = None
+
+    def __init__(self, nclass=21, norm_layer=None, backbone=None, dilated=True, aux=True, multi_grid=True,
+                 path_num=None, model_path=None, ln_shape=(97, 193)):
+        super().__init__()
+        assert backbone in ("resnet50", "resnet34", "resnet18")
+        assert path_num == self.PATHS
+        if not (dilated and multi_grid):
+            raise RuntimeError("tdnet_b200 implements the dilated, multi-grid backbone the reference tests ship")
+        self.psp_path = model_path
+        self.path_num = path_num
+        self.nclass = nclass
+        self.backbone = backbone
+        self.norm_layer = norm_layer
+        self.arch = A.build_arch(self.ARCH, backbone, nclass)
+        self.expansion = self.arch.c4 // 512
+        self.ln_shape = tuple(ln_shape)
+        for key, (shape, kind) in A.parameter_table(self.arch, self.ln_shape).items():
+            _attach(self, key, shape, kind)
+        _default_init_(self)
+        self.pretrained_mp_load()
+        self.Q_queue, self.K_queue, self.V_queue = [], [], []
+        self._engines: Dict[tuple, object] = {}
+        self._frames_seen = 0
+
+    # ---- reference API ---------------------------------------------------------------------
+    def pretrained_mp_load(self):
+        if self.psp_path is not None:
+            if os.path.isfile(self.psp_path):
+                print("Loading pretrained model from '{}'".format(self.psp_path))
+                self.load_state_dict(torch.load(self.psp_path, map_location="cpu"), strict=True)
+            else:
+                print("No pretrained found at '{}'".format(self.psp_path))
+
+    def set_ln_shape(self, h8, w8):
+        """Re-create the LayerNorm affine for another feature-map size (the reference hard-codes
+        [97,193], td4_psp18.py:107-110, i.e. 769x1537 inputs; tests patch it the same way)."""
+        self.ln_shape = (h8, w8)
+        dev = next(self.parameters()).device
+        for p in range(1, self.PATHS + 1):
+            ln = getattr(self, f"layer_norm{p}").ln
+            ln.weight = nn.Parameter(torch.ones(h8, w8, device=dev), requires_grad=False)
+            ln.bias = nn.Parameter(torch.zeros(h8, w8, device=dev), requires_grad=False)
+        self._engines.clear()
+
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        out = super().load_state_dict(state_dict, strict=strict, **kw)
+        self._engines.clear()  # packed device weights are rebuilt lazily
+        return out
+
+    def reset(self):
+        """Start a new clip (the reference needs a new model instance for that)."""
+        self.Q_queue, self.K_queue, self.V_queue = [], [], []
+
+    def buffer_contral(self, q, k, v):
+        assert len(self.Q_queue) == len(self.V_queue)
+        assert len(self.Q_queue) == len(self.K_queue)
+        self.Q_queue.append(q), self.V_queue.append(v), self.K_queue.append(k)
+        if len(self.Q_queue) > self.arch.depth:
+            self.Q_queue.pop(0), self.V_queue.pop(0), self.K_queue.pop(0)
+
+    # ---- engine ----------------------------------------------------------------------------
+    def _engine(self, img: torch.Tensor):
+        from ..engine import Engine
+        n, c, h, w = img.shape
+        key = (n, h, w, img.device.index)
+        eng = self._engines.get(key)
+        if eng is None:
+            if self._engines:  # a different input shape starts a new clip: the FIFO lives in the engine
+                self._engines.clear()
+                self.reset()
+            sd = {k: v.detach().cpu() for k, v in self.state_dict().items()}
+            eng = Engine(self.arch, sd, n, h, w, img.device, self.ln_shape)
+            self._engines[key] = eng
+        return eng
+
+    @torch.no_grad()
+    def forward(self, img, pos_id=0):
+        if not img.is_cuda:
+            raise RuntimeError("tdnet_b200 runs on a CUDA (sm_100) device only; there is no CPU path. "
+                               "Move the model and the input with .to('cuda').")
+        if img.dtype != torch.float32 or img.dim() != 4 or img.shape[1] != 3:
+            raise RuntimeError("expected an fp32 NCHW image batch [n,3,H,W] (Testing/dataloader.py:69-71)")
+        if not (0 <= pos_id < self.PATHS):
+            raise RuntimeError(f"pos_id must be in [0,{self.PATHS})")
+        img = img.contiguous()
+        n, _, h, w = img.shape
+        eng = self._engine(img)
+        steady = len(self.Q_queue) >= self.arch.depth
+        plan = eng.plan(pos_id + 1, steady)
+        out = torch.empty((n, self.nclass, h, w), dtype=torch.float32, device=img.device)
+        eng.run(plan, img.data_ptr(), out.data_ptr(), torch.cuda.current_stream(img.device).cuda_stream)
+        # FIFO bookkeeping mirrors buffer_contral; the tensors are views of the engine's device slots
+        # (slot j = j-th oldest frame once the FIFO is full).
+        depth = self.arch.depth
+        fill = min(len(self.Q_queue) + 1, depth)
+        self.Q_queue = [eng.q_slots[depth - fill + j].torch().view(n, -1, self.arch.d_k) for j in range(fill)]
+        self.K_queue = [eng.k_slots[depth - fill + j].torch().view(n, -1, self.arch.d_k) for j in range(fill)]
+        self.V_queue = [eng.v_slots[depth - fill + j].torch().view(n, -1, self.arch.d_v) for j in range(fill)]
+        self._last = (eng, plan)
+        return out

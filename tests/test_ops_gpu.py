@@ -1,0 +1,235 @@
+"""GPU: every C-ABI operator against the torch CPU primitive the reference calls at that site."""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from common import max_abs
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def env():
+    from tdnet_b200 import _cabi
+    from tdnet_b200.engine import View
+    lib = _cabi.load()
+    return lib, _cabi, View, torch.device("cuda:0")
+
+
+def nhwc(x):  # NCHW cpu -> NHWC cuda contiguous
+    return x.permute(0, 2, 3, 1).contiguous().cuda()
+
+
+def run_conv(env, x, w, scale=None, bias=None, residual=None, stride=1, dilation=1, act=0):
+    lib, cabi, View, dev = env
+    n, cin, h, wd = x.shape
+    cout, _, k, _ = w.shape
+    pad = dilation * (k - 1) // 2
+    cin4 = (cin + 3) // 4 * 4
+    xin = F.pad(x, (0, 0, 0, 0, 0, cin4 - cin))
+    wk = F.pad(w.permute(0, 2, 3, 1), (0, cin4 - cin)).contiguous().cuda()
+    xd = nhwc(xin)
+    ref = F.conv2d(x, w, None, stride, pad, dilation)
+    oh, ow = ref.shape[2:]
+    out = torch.empty(n, oh, ow, cout, device=dev)
+    d = cabi.Conv2dDesc()
+    d.in_ = View(xd.view(-1), n, h, wd, cin4).ct()
+    d.out = View(out.view(-1), n, oh, ow, cout).ct()
+    keep = [xd, wk, out]
+    if residual is not None:
+        rd = nhwc(residual)
+        keep.append(rd)
+        d.residual = View(rd.view(-1), n, oh, ow, cout).ct()
+        ref = None
+    d.weight = wk.data_ptr()
+    if scale is not None:
+        sd_, bd_ = scale.cuda(), bias.cuda()
+        keep += [sd_, bd_]
+        d.scale, d.bias = sd_.data_ptr(), bd_.data_ptr()
+    d.cout, d.kh, d.kw, d.stride, d.pad, d.dilation = cout, k, k, stride, pad, dilation
+    d.act, d.leaky_slope, d.batch = act, 0.01, 1
+    cabi.check(lib.tdn_conv2d(C.byref(d), None), "conv2d")
+    torch.cuda.synchronize()
+    return out.permute(0, 3, 1, 2).cpu()
+
+
+CONV_CASES = [
+    # cin, cout, k, stride, dil, h, w
+    (3, 64, 7, 2, 1, 37, 53),     # stem (resnet.py:133)
+    (64, 64, 3, 1, 1, 19, 27),
+    (64, 128, 3, 2, 1, 19, 27),   # layer2.0.conv1
+    (64, 128, 1, 2, 1, 19, 27),   # downsample
+    (128, 256, 3, 1, 2, 13, 21),  # dilation 2
+    (256, 96, 3, 1, 4, 13, 21),   # dilation 4 (wider than the map: mostly padding)
+    (96, 40, 3, 1, 8, 13, 21),
+    (128, 19, 1, 1, 1, 13, 21),   # classifier: cout not a multiple of 4
+]
+
+
+@pytest.mark.parametrize("cin,cout,k,stride,dil,h,w", CONV_CASES)
+def test_conv2d_geometries(env, cin, cout, k, stride, dil, h, w):
+    g = torch.Generator().manual_seed(cin * 1000 + cout + k)
+    x = torch.randn(2, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5
+    got = run_conv(env, x, wt, stride=stride, dilation=dil)
+    ref = F.conv2d(x, wt, None, stride, dil * (k - 1) // 2, dil)
+    assert got.shape == ref.shape
+    assert max_abs(got, ref) < 2e-5
+
+
+def test_conv2d_bn_residual_relu_epilogue(env):
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(1, 64, 17, 23, generator=g)
+    wt = torch.randn(64, 64, 3, 3, generator=g) / 24
+    s, b = torch.rand(64, generator=g) + 0.5, torch.randn(64, generator=g)
+    r = torch.randn(1, 64, 17, 23, generator=g)
+    got = run_conv(env, x, wt, scale=s, bias=b, residual=r, act=1)
+    ref = F.relu(F.conv2d(x, wt, None, 1, 1) * s.view(1, -1, 1, 1) + b.view(1, -1, 1, 1) + r)
+    assert max_abs(got, ref) < 2e-5
+    got = run_conv(env, x, wt, scale=s, bias=b, act=2)
+    ref = F.leaky_relu(F.conv2d(x, wt, None, 1, 1) * s.view(1, -1, 1, 1) + b.view(1, -1, 1, 1), 0.01)
+    assert max_abs(got, ref) < 2e-5
+
+
+def test_batched_gemm_both_weight_layouts(env):
+    """bmm(q, k^T) and bmm(attn, v) (transformer.py:128,137) through tdn_conv2d with batch=2."""
+    lib, cabi, View, dev = env
+    g = torch.Generator().manual_seed(3)
+    q, k = torch.randn(2, 70, 64, generator=g), torch.randn(2, 30, 64, generator=g)
+    qd, kd = q.cuda(), k.cuda()
+    s = torch.zeros(2, 70, 32, device=dev)  # row pitch 32 (30 padded to a multiple of 4)
+    d = cabi.Conv2dDesc()
+    d.in_ = View(qd.view(-1), 1, 1, 70, 64).ct()
+    d.out = View(s.view(-1), 1, 1, 70, 30, 70 * 32, 70 * 32, 32).ct()
+    d.weight, d.cout, d.kh, d.kw, d.stride, d.dilation, d.batch = kd.data_ptr(), 30, 1, 1, 1, 1, 2
+    d.in_batch_stride, d.out_batch_stride, d.weight_batch_stride = 70 * 64, 70 * 32, 30 * 64
+    cabi.check(lib.tdn_conv2d(C.byref(d), None))
+    torch.cuda.synchronize()
+    assert max_abs(s[:, :, :30].cpu(), torch.bmm(q, k.transpose(1, 2))) < 2e-5
+    assert float(s[:, :, 30:].abs().max()) == 0.0
+    cabi.check(lib.tdn_softmax_rows(s.data_ptr(), 140, 30, 32, C.c_float(0.125), None))
+    torch.cuda.synchronize()
+    attn = torch.softmax(torch.bmm(q, k.transpose(1, 2)) / 8.0, dim=2)
+    assert max_abs(s[:, :, :30].cpu(), attn) < 1e-6
+    v = torch.randn(2, 30, 48, generator=g)
+    vd = torch.zeros(2, 32, 48, device=dev)
+    vd[:, :30] = v.cuda()
+    res = torch.randn(2, 70, 48, generator=g)
+    rd = res.cuda()
+    o = torch.empty(2, 70, 48, device=dev)
+    d = cabi.Conv2dDesc()
+    d.in_ = View(s.view(-1), 1, 1, 70, 32).ct()
+    d.out = View(o.view(-1), 1, 1, 70, 48).ct()
+    d.residual = View(rd.view(-1), 1, 1, 70, 48).ct()
+    d.weight, d.cout, d.kh, d.kw, d.stride, d.dilation, d.batch = vd.data_ptr(), 48, 1, 1, 1, 1, 2
+    d.weight_kn = 1
+    d.in_batch_stride, d.out_batch_stride, d.weight_batch_stride = 70 * 32, 70 * 48, 32 * 48
+    d.residual_batch_stride = 70 * 48
+    cabi.check(lib.tdn_conv2d(C.byref(d), None))
+    torch.cuda.synchronize()
+    assert max_abs(o.cpu(), torch.bmm(attn, v) + res) < 2e-5
+
+
+def test_image_layout_and_maxpool(env):
+    lib, cabi, View, dev = env
+    g = torch.Generator().manual_seed(5)
+    img = torch.randn(2, 3, 21, 34, generator=g)
+    imgd = img.cuda()
+    o = torch.empty(2, 21, 34, 4, device=dev)
+    t = View(o.view(-1), 2, 21, 34, 4).ct()
+    cabi.check(lib.tdn_image_to_nhwc(imgd.data_ptr(), 2, 3, 21, 34, C.byref(t), None))
+    torch.cuda.synchronize()
+    assert torch.equal(o[..., :3].cpu(), img.permute(0, 2, 3, 1)) and float(o[..., 3].abs().max()) == 0
+    x = torch.randn(2, 64, 21, 34, generator=g)
+    xd = nhwc(x)
+    y = torch.empty(2, 11, 17, 64, device=dev)
+    ti, to = View(xd.view(-1), 2, 21, 34, 64).ct(), View(y.view(-1), 2, 11, 17, 64).ct()
+    cabi.check(lib.tdn_maxpool3x3s2(C.byref(ti), C.byref(to), None))
+    torch.cuda.synchronize()
+    assert torch.equal(y.permute(0, 3, 1, 2).cpu(), F.max_pool2d(x, 3, 2, 1))
+
+
+@pytest.mark.parametrize("h,w", [(13, 21), (16, 32), (6, 6), (97, 193)])
+def test_psp_pool_matches_adaptive_avg_pool(env, h, w):
+    lib, cabi, View, dev = env
+    g = torch.Generator().manual_seed(h * w)
+    x = torch.randn(2, 128, h, w, generator=g)
+    xd = nhwc(x)
+    out = torch.empty(2, 50, 128, device=dev)
+    nbytes = int(lib.tdn_psp_pool_workspace_bytes(2, h, 128))
+    ws = torch.empty(nbytes // 4, device=dev)
+    ti, to = View(xd.view(-1), 2, h, w, 128).ct(), View(out.view(-1), 2, 1, 50, 128).ct()
+    cabi.check(lib.tdn_psp_pool(C.byref(ti), C.byref(to), ws.data_ptr(), nbytes, None))
+    assert lib.tdn_psp_pool(C.byref(ti), C.byref(to), ws.data_ptr(), nbytes - 4, None) == -5
+    torch.cuda.synchronize()
+    off = 0
+    for bins in (1, 2, 3, 6):
+        ref = F.adaptive_avg_pool2d(x, bins).permute(0, 2, 3, 1).reshape(2, bins * bins, 128)
+        assert max_abs(out[:, off:off + bins * bins].cpu(), ref) < 2e-6
+        off += bins * bins
+
+
+@pytest.mark.parametrize("hs,ws", [(1, 1), (2, 2), (3, 3), (6, 6)])
+def test_bilinear_align_corners_into_channel_slice(env, hs, ws):
+    lib, cabi, View, dev = env
+    g = torch.Generator().manual_seed(hs)
+    x = torch.randn(2, 16, hs, ws, generator=g)
+    xd = nhwc(x)
+    big = torch.full((2, 13, 21, 40), -7.0, device=dev)
+    ti = View(xd.view(-1), 2, hs, ws, 16).ct()
+    to = View(big.view(-1), 2, 13, 21, 40).channels(8, 24).ct()
+    cabi.check(lib.tdn_bilinear_nhwc(C.byref(ti), C.byref(to), None))
+    torch.cuda.synchronize()
+    ref = F.interpolate(x, (13, 21), mode="bilinear", align_corners=True)
+    assert max_abs(big[..., 8:24].permute(0, 3, 1, 2).cpu(), ref) < 2e-6
+    assert float((big[..., :8] + 7).abs().max()) == 0 and float((big[..., 24:] + 7).abs().max()) == 0
+
+
+def test_layernorm_hw(env):
+    lib, cabi, View, dev = env
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(2, 64, 13, 21, generator=g) * 3 + 1.5
+    gamma, beta = torch.rand(13, 21, generator=g) + 0.5, torch.randn(13, 21, generator=g)
+    xd = nhwc(x)
+    mean, rstd = torch.empty(128, device=dev), torch.empty(128, device=dev)
+    nbytes = int(lib.tdn_layernorm_hw_workspace_bytes(2, 13, 21, 64))
+    ws = torch.empty(nbytes // 4, device=dev)
+    tx = View(xd.view(-1), 2, 13, 21, 64).ct()
+    cabi.check(lib.tdn_layernorm_hw_stats(C.byref(tx), mean.data_ptr(), rstd.data_ptr(), C.c_float(1e-5),
+                                          ws.data_ptr(), nbytes, None))
+    y = torch.empty(2, 13, 21, 64, device=dev)
+    gd, bd = gamma.cuda().view(-1), beta.cuda().view(-1)
+    ty = View(y.view(-1), 2, 13, 21, 64).ct()
+    cabi.check(lib.tdn_layernorm_hw_apply(C.byref(tx), mean.data_ptr(), rstd.data_ptr(), gd.data_ptr(),
+                                          bd.data_ptr(), C.byref(ty), None))
+    torch.cuda.synchronize()
+    ref = F.layer_norm(x, (13, 21), gamma, beta, 1e-5)
+    assert max_abs(y.permute(0, 3, 1, 2).cpu(), ref) < 5e-6
+
+
+@pytest.mark.parametrize("h,w,H,W", [(13, 21, 97, 161), (16, 32, 128, 256), (8, 8, 64, 64)])
+def test_upsample_logits_nchw(env, h, w, H, W):
+    lib, cabi, View, dev = env
+    g = torch.Generator().manual_seed(H)
+    x = torch.randn(2, 19, h, w, generator=g)
+    xd = nhwc(x)
+    out = torch.empty(2, 19, H, W, device=dev)
+    t = View(xd.view(-1), 2, h, w, 19).ct()
+    cabi.check(lib.tdn_upsample_logits(C.byref(t), out.data_ptr(), H, W, None))
+    torch.cuda.synchronize()
+    ref = F.interpolate(x, (H, W), mode="bilinear", align_corners=True)
+    assert max_abs(out.cpu(), ref) < 2e-6
+
+
+def test_errors_are_reported_not_swallowed(env):
+    lib, cabi, View, dev = env
+    x = torch.zeros(1, 5, 5, 6, device=dev)
+    d = cabi.Conv2dDesc()
+    d.in_ = View(x.view(-1), 1, 5, 5, 6).ct()          # cin = 6: not a multiple of 4
+    d.out = View(x.view(-1), 1, 5, 5, 6).ct()
+    d.weight, d.cout, d.kh, d.kw, d.stride, d.dilation, d.batch = x.data_ptr(), 6, 1, 1, 1, 1, 1
+    assert lib.tdn_conv2d(C.byref(d), None) == -2
+    with pytest.raises(RuntimeError, match="multiple of 4"):
+        cabi.check(lib.tdn_conv2d(C.byref(d), None), "conv2d")
