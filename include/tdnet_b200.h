@@ -102,6 +102,48 @@ typedef struct tdn_conv2d_desc {
 
 int tdn_conv2d(const tdn_conv2d_desc* desc, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * tdn_conv2d_tc: the tcgen05 (5th-gen tensor core) implementation of the same operator for the
+ * shapes that dominate the frame: stride-1 "same" convolutions (1x1 / 3x3, any dilation) and plain
+ * GEMMs with cin %% 64 == 0, on SPLIT16 operands.  fp32-faithful: three fp16 tensor-core products per
+ * K step (hi*lo, lo*hi, hi*hi) accumulate into one fp32 TMEM accumulator ("exact mode").
+ * Same call sites as tdn_conv2d; additionally transformer.py:128,137 (q k^T, attn v) where the
+ * "weight" operand is itself an activation (weight_batched = 1: one [cout][K] matrix per image).
+ *
+ * weight_hi/lo: fp16 [cout][kh*kw*cin] K-major with row pitch weight_ld (elements).
+ * bias_along_m: bias is indexed by the output pixel (row of the GEMM) instead of the channel; used to
+ *   produce V'^T = W_fc V^T + b directly in the K-major layout the next GEMM wants.
+ * out: SPLIT16 or F32; out_f32_copy (optional) additionally receives fp32 with out's strides.
+ * range_flag (optional, device int): set to 1 if a SPLIT16 output exceeded the fp16 range guard.
+ * Fails with TDN_ERR_ARCH on anything but sm_100.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct tdn_tc_conv_desc {
+  tdn_tensor in;
+  tdn_tensor out;
+  tdn_tensor residual; /* residual.data == NULL -> none; SPLIT16 or F32 */
+  float* out_f32_copy;
+  const void* weight_hi;
+  const void* weight_lo;
+  int64_t weight_ld;
+  int64_t weight_batch_stride;
+  int32_t weight_batched;
+  int32_t bias_along_m;
+  const float* scale;
+  const float* bias;
+  int32_t cout;
+  int32_t kh, kw;
+  int32_t dilation;
+  int32_t act;
+  float leaky_slope;
+  int32_t* range_flag;
+} tdn_tc_conv_desc;
+
+int tdn_conv2d_tc(const tdn_tc_conv_desc* desc, void* stream);
+
+/* fp32 plane <-> SPLIT16 planes (hi = fp16(x), lo = fp16(x - hi)); views must have equal dims. */
+int tdn_split16(const tdn_tensor* in_f32, const tdn_tensor* out_split16, void* stream);
+int tdn_merge16(const tdn_tensor* in_split16, const tdn_tensor* out_f32, void* stream);
+
 /* NCHW fp32 image [n,3,H,W] (Testing/dataloader.py:69-71) -> NHWC fp32 with channels zero-padded to
  * out.c (4), the layout every later kernel reads.  Replaces nothing numeric; it is the layout edge. */
 int tdn_image_to_nhwc(const float* nchw, int32_t n, int32_t c, int32_t h, int32_t w,

@@ -32,6 +32,16 @@ class Conv2dDesc(C.Structure):
                 ("residual_batch_stride", C.c_int64), ("weight_batch_stride", C.c_int64)]
 
 
+class TcConvDesc(C.Structure):
+    _fields_ = [("in_", Tensor), ("out", Tensor), ("residual", Tensor),
+                ("out_f32_copy", C.c_void_p), ("weight_hi", C.c_void_p), ("weight_lo", C.c_void_p),
+                ("weight_ld", C.c_int64), ("weight_batch_stride", C.c_int64),
+                ("weight_batched", C.c_int32), ("bias_along_m", C.c_int32),
+                ("scale", C.c_void_p), ("bias", C.c_void_p),
+                ("cout", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32), ("dilation", C.c_int32),
+                ("act", C.c_int32), ("leaky_slope", C.c_float), ("range_flag", C.c_void_p)]
+
+
 # symbol -> (restype, argtypes); tests/test_cabi.py checks this list against include/tdnet_b200.h
 _TP = C.POINTER(Tensor)
 SIGNATURES = {
@@ -40,6 +50,9 @@ SIGNATURES = {
     "tdn_last_error": (C.c_char_p, []),
     "tdn_device_arch": (C.c_int, []),
     "tdn_conv2d": (C.c_int, [C.POINTER(Conv2dDesc), C.c_void_p]),
+    "tdn_conv2d_tc": (C.c_int, [C.POINTER(TcConvDesc), C.c_void_p]),
+    "tdn_split16": (C.c_int, [_TP, _TP, C.c_void_p]),
+    "tdn_merge16": (C.c_int, [_TP, _TP, C.c_void_p]),
     "tdn_image_to_nhwc": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _TP, C.c_void_p]),
     "tdn_maxpool3x3s2": (C.c_int, [_TP, _TP, C.c_void_p]),
     "tdn_psp_pool": (C.c_int, [_TP, _TP, C.c_void_p, C.c_uint64, C.c_void_p]),

@@ -35,6 +35,9 @@ int layernorm_hw_stats(const tdn_tensor*, float*, float*, float, void*, size_t, 
 int layernorm_hw_apply(const tdn_tensor*, const float*, const float*, const float*, const float*,
                        const tdn_tensor*, cudaStream_t);
 int upsample_logits(const tdn_tensor*, float*, int, int, cudaStream_t);
+int conv2d_tc(const tdn_tc_conv_desc*, cudaStream_t);
+int split16(const tdn_tensor*, const tdn_tensor*, cudaStream_t);
+int merge16(const tdn_tensor*, const tdn_tensor*, cudaStream_t);
 
 }  // namespace tdn
 
@@ -74,6 +77,24 @@ int tdn_conv2d(const tdn_conv2d_desc* d, void* stream) {
   TDN_REQUIRE(d->in.n > 0 && d->in.h > 0 && d->in.w > 0 && d->in.c > 0, TDN_ERR_INVALID,
               "conv2d: empty input");
   return conv2d_simt(d, (cudaStream_t)stream);
+}
+
+int tdn_conv2d_tc(const tdn_tc_conv_desc* d, void* stream) {
+  TDN_REQUIRE(d != nullptr, TDN_ERR_INVALID, "conv2d_tc: null descriptor");
+  static thread_local int arch = 0;
+  if (arch == 0) arch = tdn_device_arch();
+  if (arch < 0) return arch;
+  TDN_REQUIRE(arch / 10 == 10, TDN_ERR_ARCH, "conv2d_tc: tcgen05 kernels need sm_100, device is sm_%d", arch);
+  TDN_REQUIRE(d->cout > 0 && d->kh > 0 && d->kw > 0 && d->dilation > 0, TDN_ERR_INVALID, "conv2d_tc: bad geometry");
+  return conv2d_tc(d, (cudaStream_t)stream);
+}
+
+int tdn_split16(const tdn_tensor* in, const tdn_tensor* out, void* stream) {
+  return split16(in, out, (cudaStream_t)stream);
+}
+
+int tdn_merge16(const tdn_tensor* in, const tdn_tensor* out, void* stream) {
+  return merge16(in, out, (cudaStream_t)stream);
 }
 
 int tdn_image_to_nhwc(const float* nchw, int32_t n, int32_t c, int32_t h, int32_t w, const tdn_tensor* out,

@@ -229,6 +229,85 @@ int copy_nhwc(const tdn_tensor* in, const tdn_tensor* out, cudaStream_t stream) 
 }
 
 // ---------------------------------------------------------------------------------------------
+// fp32 <-> SPLIT16 (hi = fp16(x), lo = fp16(x - hi)), 4 channels per thread.
+// ---------------------------------------------------------------------------------------------
+__global__ void split16_kernel(View in, __half* __restrict__ hi, __half* __restrict__ lo, long long sn,
+                               long long sh, long long sw) {
+  const int c4 = in.c >> 2;
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long total = (long long)in.n * in.h * in.w * c4;
+  if (idx >= total) return;
+  int c = (idx % c4) * 4;
+  long long t = idx / c4;
+  int x = t % in.w; t /= in.w;
+  int y = t % in.h;
+  int b = t / in.h;
+  float4 v = *reinterpret_cast<const float4*>(in.p + b * in.sn + y * in.sh + x * in.sw + c);
+  float f[4] = {v.x, v.y, v.z, v.w};
+  __half h[4], l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    h[j] = __float2half_rn(f[j]);
+    l[j] = __float2half_rn(f[j] - __half2float(h[j]));
+  }
+  long long o = b * sn + y * sh + x * sw + c;
+  *reinterpret_cast<uint2*>(hi + o) = *reinterpret_cast<const uint2*>(h);
+  *reinterpret_cast<uint2*>(lo + o) = *reinterpret_cast<const uint2*>(l);
+}
+
+__global__ void merge16_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, long long sn,
+                               long long sh, long long sw, View out) {
+  const int c4 = out.c >> 2;
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long total = (long long)out.n * out.h * out.w * c4;
+  if (idx >= total) return;
+  int c = (idx % c4) * 4;
+  long long t = idx / c4;
+  int x = t % out.w; t /= out.w;
+  int y = t % out.h;
+  int b = t / out.h;
+  long long i = b * sn + y * sh + x * sw + c;
+  uint2 hv = *reinterpret_cast<const uint2*>(hi + i);
+  uint2 lv = *reinterpret_cast<const uint2*>(lo + i);
+  const __half* h = reinterpret_cast<const __half*>(&hv);
+  const __half* l = reinterpret_cast<const __half*>(&lv);
+  float4 v = make_float4(__half2float(h[0]) + __half2float(l[0]), __half2float(h[1]) + __half2float(l[1]),
+                         __half2float(h[2]) + __half2float(l[2]), __half2float(h[3]) + __half2float(l[3]));
+  *reinterpret_cast<float4*>(out.p + b * out.sn + y * out.sh + x * out.sw + c) = v;
+}
+
+static int check_split_pair(const tdn_tensor* f, const tdn_tensor* s, const char* what) {
+  int rc;
+  if ((rc = check_f32_tensor(f, what))) return rc;
+  TDN_REQUIRE(s && s->data && s->data_lo && s->dtype == TDN_SPLIT16, TDN_ERR_INVALID, "%s: SPLIT16 view expected", what);
+  TDN_REQUIRE(f->n == s->n && f->h == s->h && f->w == s->w && f->c == s->c, TDN_ERR_INVALID, "%s: dims mismatch", what);
+  TDN_REQUIRE(vec4_ok(*f) && (((uintptr_t)s->data) & 7) == 0 && (((uintptr_t)s->data_lo) & 7) == 0 &&
+                  s->stride_w % 4 == 0 && s->stride_h % 4 == 0 && s->stride_n % 4 == 0,
+              TDN_ERR_INVALID, "%s: views must be vector aligned (c %% 4 == 0)", what);
+  return TDN_OK;
+}
+
+int split16(const tdn_tensor* in, const tdn_tensor* out, cudaStream_t stream) {
+  int rc;
+  if ((rc = check_split_pair(in, out, "split16"))) return rc;
+  long long total = (long long)in->n * in->h * in->w * (in->c / 4);
+  split16_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(make_view(*in), (__half*)out->data, (__half*)out->data_lo,
+                                                           out->stride_n, out->stride_h, out->stride_w);
+  TDN_LAUNCH_OK();
+  return TDN_OK;
+}
+
+int merge16(const tdn_tensor* in, const tdn_tensor* out, cudaStream_t stream) {
+  int rc;
+  if ((rc = check_split_pair(out, in, "merge16"))) return rc;
+  long long total = (long long)out->n * out->h * out->w * (out->c / 4);
+  merge16_kernel<<<ceil_div(total, 256), 256, 0, stream>>>((const __half*)in->data, (const __half*)in->data_lo,
+                                                           in->stride_n, in->stride_h, in->stride_w, make_view(*out));
+  TDN_LAUNCH_OK();
+  return TDN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Row softmax with pre-scale (one CTA per row; three passes over a row that stays in L1/L2).
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_max(float v) {

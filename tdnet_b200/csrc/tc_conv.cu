@@ -1,0 +1,468 @@
+// tcgen05 implicit-GEMM convolution / GEMM for sm_100a, fp32-faithful ("exact mode").
+//
+//   out[pixel, co] = act( (sum_{tap, ci} A[pixel + tap*dil, ci] * W[co, tap, ci]) * scale[co] + bias + residual )
+//
+// Operands are SPLIT16: every fp32 value x is carried as two fp16 planes, hi = fp16(x) and
+// lo = fp16(x - hi), so hi + lo reproduces x to >= 22 significant bits.  Three tensor-core products
+// per K step -- Ah*Bl, Al*Bh, Ah*Bh -- accumulate in ONE fp32 TMEM accumulator (fp16 x fp16 products
+// are exact in fp32; the dropped Al*Bl term is below 2^-22 relative).  This is what makes the
+// tensor-core path match the reference's fp32 arithmetic instead of being a bf16/tf32 approximation.
+//
+// Structure (one persistent CTA per SM, 192 threads):
+//   warp 0      TMA producer: per K block (one filter tap x 64 input channels) four bulk-tensor loads
+//               -- A hi/lo as a [BH x BW pixels] x 64ch box of the NHWC map, shifted by the tap offset
+//               (out-of-bounds rows/cols are zero-filled by TMA = the convolution padding), B hi/lo as
+//               [BLOCK_N couts] x 64 -- into a STAGES-deep shared-memory ring (128B swizzle).
+//   warp 1      MMA issuer: one elected lane issues 12 tcgen05.mma (4 K16 steps x 3 products) per
+//               stage into a double-buffered TMEM accumulator; tcgen05.commit releases the stage.
+//   warps 2-5   epilogue: tcgen05.ld the 128 x BLOCK_N fp32 tile (one pixel row per thread), apply
+//               scale/bias/residual/activation, re-split to hi/lo (and/or write fp32), 16-byte stores.
+// The TMEM double buffer lets the epilogue of tile i overlap the main loop of tile i+1.
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+#include <string.h>
+#include <cuda.h>  // CUtensorMap types only; the encode entry point is resolved at run time
+
+namespace tdn {
+
+using namespace ptx;
+
+constexpr int TC_BLOCK_M = 128;
+constexpr int TC_BLOCK_K = 64;                       // fp16 elements = 128 bytes = one swizzle row
+constexpr int TC_A_PLANE = TC_BLOCK_M * TC_BLOCK_K * 2;  // 16 KiB per hi or lo plane
+constexpr int TC_THREADS = 192;
+
+struct TcParams {
+  int n_img, Ho, Wo;
+  int tiles_h, tiles_w, BH, BW;
+  int Cout, Cin;
+  int taps_h, taps_w, dil;
+  int n_tiles_n, num_tiles;
+  int w_batched;
+  const float* scale;
+  const float* bias;
+  int bias_along_m;
+  int act;
+  float slope;
+  __half* out_hi;
+  __half* out_lo;
+  float* out_f32;
+  long long osn, osh, osw;
+  const __half* res_hi;
+  const __half* res_lo;
+  const float* res_f32;
+  long long rsn, rsh, rsw;
+  int* range_flag;
+};
+
+template <int BLOCK_N>
+struct TcCfg {
+  static constexpr int B_PLANE = BLOCK_N * TC_BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = 2 * TC_A_PLANE + 2 * B_PLANE;
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES;
+  static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ float tc_act(float v, int act, float slope) {
+  if (act == TDN_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == TDN_ACT_LEAKY_RELU) return v > 0.f ? v : v * slope;
+  return v;
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+               const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+               const TcParams p) {
+  using Cfg = TcCfg<BLOCK_N>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int kc_per_tap = p.Cin / TC_BLOCK_K;
+  const int num_kb = p.taps_h * p.taps_w * kc_per_tap;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmA_hi);
+    prefetch_tensormap(&tmA_lo);
+    prefetch_tensormap(&tmB_hi);
+    prefetch_tensormap(&tmB_lo);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ======================= TMA producer =======================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles_n;
+        int mt = tile / p.n_tiles_n;
+        const int tx = mt % p.tiles_w;
+        mt /= p.tiles_w;
+        const int ty = mt % p.tiles_h;
+        const int img = mt / p.tiles_h;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int tap = kb / kc_per_tap;
+          const int kc = kb - tap * kc_per_tap;
+          const int ky = tap / p.taps_w;
+          const int kx = tap - ky * p.taps_w;
+          const int x0 = tx * p.BW + (kx - (p.taps_w - 1) / 2) * p.dil;
+          const int y0 = ty * p.BH + (ky - (p.taps_h - 1) / 2) * p.dil;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + 2 * TC_A_PLANE;
+          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          tma_load_4d(sa, &tmA_hi, &full_bar[stage], kc * TC_BLOCK_K, x0, y0, img);
+          tma_load_4d(sa + TC_A_PLANE, &tmA_lo, &full_bar[stage], kc * TC_BLOCK_K, x0, y0, img);
+          const int kcol = tap * p.Cin + kc * TC_BLOCK_K;
+          const int bz = p.w_batched ? img : 0;
+          tma_load_3d(sb, &tmB_hi, &full_bar[stage], kcol, nt * BLOCK_N, bz);
+          tma_load_3d(sb + Cfg::B_PLANE, &tmB_lo, &full_bar[stage], kcol, nt * BLOCK_N, bz);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer =======================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(TC_BLOCK_M, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + 2 * TC_A_PLANE;
+#pragma unroll
+          for (int k = 0; k < TC_BLOCK_K / 16; ++k) {
+            const uint64_t a_hi = umma_desc_k_sw128(sa + k * 32);
+            const uint64_t a_lo = umma_desc_k_sw128(sa + TC_A_PLANE + k * 32);
+            const uint64_t b_hi = umma_desc_k_sw128(sb + k * 32);
+            const uint64_t b_lo = umma_desc_k_sw128(sb + Cfg::B_PLANE + k * 32);
+            umma_f16(d_tmem, a_hi, b_lo, idesc, (kb | k) != 0);
+            umma_f16(d_tmem, a_lo, b_hi, idesc, 1);
+            umma_f16(d_tmem, a_hi, b_hi, idesc, 1);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[as]);
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else {
+    // ======================= epilogue (warps 2..5) =======================
+    const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;          // pixel row of the tile
+    const int h_local = row / p.BW;
+    const int w_local = row - h_local * p.BW;
+    int as = 0;
+    uint32_t aphase = 0;
+    bool out_of_range = false;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int nt = tile % p.n_tiles_n;
+      int mt = tile / p.n_tiles_n;
+      const int tx = mt % p.tiles_w;
+      mt /= p.tiles_w;
+      const int ty = mt % p.tiles_h;
+      const int img = mt / p.tiles_h;
+      const int oh = ty * p.BH + h_local;
+      const int ow = tx * p.BW + w_local;
+      const bool valid = oh < p.Ho && ow < p.Wo;
+      const long long ooff = (long long)img * p.osn + (long long)oh * p.osh + (long long)ow * p.osw;
+      const long long roff = (long long)img * p.rsn + (long long)oh * p.rsh + (long long)ow * p.rsw;
+      const float bias_m = (p.bias && p.bias_along_m && valid) ? __ldg(p.bias + oh * p.Wo + ow) : 0.f;
+
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BLOCK_N;
+#pragma unroll 1
+      for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + chunk * 32, r);
+        tmem_ld_wait();
+        const int c0 = nt * BLOCK_N + chunk * 32;
+        if (valid && c0 < p.Cout) {
+          float v[32];
+          const bool full = (c0 + 32 <= p.Cout);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int c = c0 + j;
+            float acc = __uint_as_float(r[j]);
+            float s = 1.f, b = bias_m;
+            if (full || c < p.Cout) {
+              if (p.scale) s = __ldg(p.scale + c);
+              if (p.bias && !p.bias_along_m) b = __ldg(p.bias + c);
+            }
+            v[j] = fmaf(acc, s, b);
+          }
+          if (p.res_hi) {
+            if (full) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                uint4 h4 = *reinterpret_cast<const uint4*>(p.res_hi + roff + c0 + q * 8);
+                uint4 l4 = *reinterpret_cast<const uint4*>(p.res_lo + roff + c0 + q * 8);
+                const __half2* hh = reinterpret_cast<const __half2*>(&h4);
+                const __half2* ll = reinterpret_cast<const __half2*>(&l4);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  float2 a = __half22float2(hh[e]), b2 = __half22float2(ll[e]);
+                  v[q * 8 + e * 2 + 0] += a.x + b2.x;
+                  v[q * 8 + e * 2 + 1] += a.y + b2.y;
+                }
+              }
+            } else {
+              for (int j = 0; j < 32 && c0 + j < p.Cout; ++j)
+                v[j] += __half2float(p.res_hi[roff + c0 + j]) + __half2float(p.res_lo[roff + c0 + j]);
+            }
+          } else if (p.res_f32) {
+            if (full) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                float4 f = *reinterpret_cast<const float4*>(p.res_f32 + roff + c0 + q * 4);
+                v[q * 4 + 0] += f.x; v[q * 4 + 1] += f.y; v[q * 4 + 2] += f.z; v[q * 4 + 3] += f.w;
+              }
+            } else {
+              for (int j = 0; j < 32 && c0 + j < p.Cout; ++j) v[j] += p.res_f32[roff + c0 + j];
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = tc_act(v[j], p.act, p.slope);
+
+          if (p.out_f32) {
+            if (full) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                *reinterpret_cast<float4*>(p.out_f32 + ooff + c0 + q * 4) =
+                    make_float4(v[q * 4 + 0], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+            } else {
+              for (int j = 0; j < 32 && c0 + j < p.Cout; ++j) p.out_f32[ooff + c0 + j] = v[j];
+            }
+          }
+          if (p.out_hi) {
+            __half hi[32], lo[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              out_of_range |= fabsf(v[j]) > 60000.f;
+              hi[j] = __float2half_rn(v[j]);
+              lo[j] = __float2half_rn(v[j] - __half2float(hi[j]));
+            }
+            if (full) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                *reinterpret_cast<uint4*>(p.out_hi + ooff + c0 + q * 8) = *reinterpret_cast<const uint4*>(&hi[q * 8]);
+                *reinterpret_cast<uint4*>(p.out_lo + ooff + c0 + q * 8) = *reinterpret_cast<const uint4*>(&lo[q * 8]);
+              }
+            } else {
+              for (int j = 0; j < 32 && c0 + j < p.Cout; ++j) {
+                p.out_hi[ooff + c0 + j] = hi[j];
+                p.out_lo[ooff + c0 + j] = lo[j];
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[as]);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+    if (out_of_range && p.range_flag) atomicOr(p.range_flag, 1);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims,
+                      const cuuint64_t* strides_bytes, const cuuint32_t* box, const char* what) {
+  EncodeTiledFn fn = get_encode_fn();
+  TDN_REQUIRE(fn != nullptr, TDN_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TDN_REQUIRE(r == CUDA_SUCCESS, TDN_ERR_CUDA, "cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
+  return TDN_OK;
+}
+
+static void pick_tile(int H, int W, int* BH, int* BW) {
+  // 128 pixels as BH x BW; minimise the padded area, prefer wide tiles (longer contiguous runs) on ties.
+  const int cand[5][2] = {{1, 128}, {2, 64}, {4, 32}, {8, 16}, {16, 8}};
+  long long best = -1;
+  for (int i = 0; i < 5; ++i) {
+    int bh = cand[i][0], bw = cand[i][1];
+    long long area = (long long)ceil_div(H, bh) * bh * ceil_div(W, bw) * bw;
+    if (best < 0 || area < best) { best = area; *BH = bh; *BW = bw; }
+  }
+}
+
+static int g_num_sms = 0;
+
+template <int BLOCK_N>
+static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
+                     const CUtensorMap& b_lo, const TcParams& p, cudaStream_t stream) {
+  using Cfg = TcCfg<BLOCK_N>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TDN_CUDA_OK(cudaFuncSetAttribute(tc_conv_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  if (g_num_sms == 0) {
+    int dev = 0;
+    TDN_CUDA_OK(cudaGetDevice(&dev));
+    TDN_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
+  tc_conv_kernel<BLOCK_N><<<grid, TC_THREADS, Cfg::SMEM_BYTES, stream>>>(a_hi, a_lo, b_hi, b_lo, p);
+  TDN_LAUNCH_OK();
+  return TDN_OK;
+}
+
+int conv2d_tc(const tdn_tc_conv_desc* d, cudaStream_t stream) {
+  const tdn_tensor& in = d->in;
+  const tdn_tensor& out = d->out;
+  TDN_REQUIRE(in.dtype == TDN_SPLIT16 && in.data && in.data_lo, TDN_ERR_INVALID, "conv2d_tc: input must be SPLIT16");
+  TDN_REQUIRE(d->weight_hi && d->weight_lo, TDN_ERR_INVALID, "conv2d_tc: null weights");
+  TDN_REQUIRE(in.c % TC_BLOCK_K == 0, TDN_ERR_UNSUPPORTED, "conv2d_tc: cin=%d must be a multiple of 64", in.c);
+  TDN_REQUIRE(d->kh % 2 == 1 && d->kw % 2 == 1 && d->kh * d->kw <= 49, TDN_ERR_UNSUPPORTED, "conv2d_tc: odd kernels only");
+  TDN_REQUIRE(out.n == in.n && out.h == in.h && out.w == in.w && out.c == d->cout, TDN_ERR_INVALID,
+              "conv2d_tc: stride-1 'same' convolution expects out dims == in dims");
+  TDN_REQUIRE(aligned16(in.data) && aligned16(in.data_lo) && in.stride_w % 8 == 0 && in.stride_h % 8 == 0 &&
+                  in.stride_n % 8 == 0, TDN_ERR_INVALID, "conv2d_tc: input planes must be 16-byte aligned");
+  TDN_REQUIRE(aligned16(d->weight_hi) && aligned16(d->weight_lo) && d->weight_ld % 8 == 0 &&
+                  d->weight_batch_stride % 8 == 0, TDN_ERR_INVALID, "conv2d_tc: weights must be 16-byte aligned");
+  const bool out16 = out.dtype == TDN_SPLIT16;
+  TDN_REQUIRE(out.data != nullptr && (out16 ? out.data_lo != nullptr : true), TDN_ERR_INVALID, "conv2d_tc: null output");
+  const int taps = d->kh * d->kw;
+  TDN_REQUIRE(d->weight_ld >= (long long)taps * in.c, TDN_ERR_INVALID, "conv2d_tc: weight_ld < K");
+
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.n_img = in.n; p.Ho = in.h; p.Wo = in.w;
+  pick_tile(in.h, in.w, &p.BH, &p.BW);
+  p.tiles_h = ceil_div(in.h, p.BH);
+  p.tiles_w = ceil_div(in.w, p.BW);
+  p.Cout = d->cout; p.Cin = in.c;
+  p.taps_h = d->kh; p.taps_w = d->kw; p.dil = d->dilation;
+  const int block_n = d->cout <= 64 ? 64 : 128;
+  p.n_tiles_n = ceil_div(d->cout, block_n);
+  long long num_tiles = (long long)in.n * p.tiles_h * p.tiles_w * p.n_tiles_n;
+  TDN_REQUIRE(num_tiles < (1ll << 31), TDN_ERR_UNSUPPORTED, "conv2d_tc: too many tiles");
+  p.num_tiles = (int)num_tiles;
+  p.w_batched = d->weight_batched;
+  p.scale = d->scale; p.bias = d->bias; p.bias_along_m = d->bias_along_m;
+  p.act = d->act; p.slope = d->leaky_slope;
+  // 16-byte vector stores/loads in the epilogue need channel-aligned rows
+  const bool vec_ok = (d->cout % 8 == 0);
+  if (out16) {
+    p.out_hi = (__half*)out.data; p.out_lo = (__half*)out.data_lo;
+    TDN_REQUIRE(aligned16(out.data) && aligned16(out.data_lo) && out.stride_w % 8 == 0 && out.stride_h % 8 == 0 &&
+                    out.stride_n % 8 == 0 && vec_ok, TDN_ERR_INVALID, "conv2d_tc: SPLIT16 output must be 16-byte aligned, cout %% 8 == 0");
+  } else {
+    p.out_f32 = (float*)out.data;
+    TDN_REQUIRE(aligned16(out.data) && out.stride_w % 4 == 0 && out.stride_h % 4 == 0 && out.stride_n % 4 == 0 &&
+                    d->cout % 4 == 0, TDN_ERR_INVALID, "conv2d_tc: fp32 output must be 16-byte aligned, cout %% 4 == 0");
+  }
+  if (d->out_f32_copy) {
+    TDN_REQUIRE(out16 && aligned16(d->out_f32_copy), TDN_ERR_INVALID, "conv2d_tc: out_f32_copy needs a SPLIT16 primary output");
+    p.out_f32 = d->out_f32_copy;  // same element strides as `out`
+  }
+  p.osn = out.stride_n; p.osh = out.stride_h; p.osw = out.stride_w;
+  if (d->residual.data) {
+    const tdn_tensor& r = d->residual;
+    TDN_REQUIRE(r.n == out.n && r.h == out.h && r.w == out.w && r.c == out.c, TDN_ERR_INVALID,
+                "conv2d_tc: residual dims must equal output dims");
+    if (r.dtype == TDN_SPLIT16) {
+      TDN_REQUIRE(r.data_lo && aligned16(r.data) && aligned16(r.data_lo) && r.stride_w % 8 == 0 &&
+                      r.stride_h % 8 == 0 && r.stride_n % 8 == 0, TDN_ERR_INVALID, "conv2d_tc: misaligned residual");
+      p.res_hi = (const __half*)r.data; p.res_lo = (const __half*)r.data_lo;
+    } else {
+      TDN_REQUIRE(aligned16(r.data) && r.stride_w % 4 == 0 && r.stride_h % 4 == 0 && r.stride_n % 4 == 0,
+                  TDN_ERR_INVALID, "conv2d_tc: misaligned residual");
+      p.res_f32 = (const float*)r.data;
+    }
+    p.rsn = r.stride_n; p.rsh = r.stride_h; p.rsw = r.stride_w;
+  }
+  p.range_flag = d->range_flag;
+
+  CUtensorMap a_hi, a_lo, b_hi, b_lo;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)in.c, (cuuint64_t)in.w, (cuuint64_t)in.h, (cuuint64_t)in.n};
+    cuuint64_t str[3] = {(cuuint64_t)in.stride_w * 2, (cuuint64_t)in.stride_h * 2, (cuuint64_t)in.stride_n * 2};
+    cuuint32_t box[4] = {(cuuint32_t)TC_BLOCK_K, (cuuint32_t)p.BW, (cuuint32_t)p.BH, 1};
+    int rc;
+    if ((rc = encode_map(&a_hi, in.data, 4, dims, str, box, "A.hi"))) return rc;
+    if ((rc = encode_map(&a_lo, in.data_lo, 4, dims, str, box, "A.lo"))) return rc;
+  }
+  {
+    const int nb = d->weight_batched ? in.n : 1;
+    cuuint64_t bstride = d->weight_batched ? (cuuint64_t)d->weight_batch_stride * 2
+                                           : (cuuint64_t)d->weight_ld * 2 * (cuuint64_t)d->cout;
+    cuuint64_t dims[3] = {(cuuint64_t)taps * in.c, (cuuint64_t)d->cout, (cuuint64_t)nb};
+    cuuint64_t str[2] = {(cuuint64_t)d->weight_ld * 2, bstride};
+    cuuint32_t box[3] = {(cuuint32_t)TC_BLOCK_K, (cuuint32_t)block_n, 1};
+    int rc;
+    if ((rc = encode_map(&b_hi, d->weight_hi, 3, dims, str, box, "B.hi"))) return rc;
+    if ((rc = encode_map(&b_lo, d->weight_lo, 3, dims, str, box, "B.lo"))) return rc;
+  }
+  if (block_n == 64) return launch_tc<64>(a_hi, a_lo, b_hi, b_lo, p, stream);
+  return launch_tc<128>(a_hi, a_lo, b_hi, b_lo, p, stream);
+}
+
+}  // namespace tdn
