@@ -1,0 +1,198 @@
+"""Bring-up probe for the tcgen05 conv/GEMM kernel (run on the B200 box via gpurun).
+
+Each experiment runs in its own subprocess with a timeout so that a trap or a hang in one kernel
+variant cannot take the rest of the report (or the box) with it.  Writes gpurun_out/tc_probe.txt.
+"""
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def split(x):
+    hi = x.half()
+    lo = (x - hi.float()).half()
+    return hi.contiguous(), lo.contiguous()
+
+
+def tensor(cabi, hi, lo, n, h, w, c, dtype=1):
+    return cabi.Tensor(hi.data_ptr(), lo.data_ptr() if lo is not None else None, dtype, n, h, w, c, h * w * c, w * c, c)
+
+
+def run_tc(x, wt, dil=1, scale=None, bias=None, residual=None, act=0, out_split=False, bias_along_m=False,
+           batched_w=None, reps=0):
+    """x: [n,h,w,cin] fp32 cuda; wt: [cout,kh,kw,cin] fp32 cuda (or batched [n,cout,cin]). Returns fp32 out."""
+    import torch
+    from tdnet_b200 import _cabi as cabi
+    lib = cabi.load()
+    n, h, w, cin = x.shape
+    xh, xl = split(x)
+    if batched_w is not None:
+        wt = batched_w
+        cout, K = wt.shape[1], wt.shape[2]
+        kh = kw = 1
+    else:
+        cout, kh, kw, _ = wt.shape
+        K = kh * kw * cin
+    wh, wl = split(wt.reshape(-1, K) if batched_w is None else wt)
+    d = cabi.TcConvDesc()
+    d.in_ = tensor(cabi, xh, xl, n, h, w, cin)
+    keep = [xh, xl, wh, wl]
+    if out_split:
+        oh_ = torch.empty(n, h, w, cout, dtype=torch.half, device="cuda")
+        ol_ = torch.empty_like(oh_)
+        d.out = tensor(cabi, oh_, ol_, n, h, w, cout)
+    else:
+        of = torch.empty(n, h, w, cout, dtype=torch.float32, device="cuda")
+        d.out = tensor(cabi, of, None, n, h, w, cout, dtype=0)
+    if residual is not None:
+        rh, rl = split(residual)
+        keep += [rh, rl]
+        d.residual = tensor(cabi, rh, rl, n, h, w, cout)
+    d.weight_hi, d.weight_lo, d.weight_ld = wh.data_ptr(), wl.data_ptr(), K
+    if batched_w is not None:
+        d.weight_batched, d.weight_batch_stride = 1, cout * K
+    if scale is not None:
+        d.scale = scale.data_ptr()
+    if bias is not None:
+        d.bias = bias.data_ptr()
+    d.bias_along_m = int(bias_along_m)
+    flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+    d.range_flag = flag.data_ptr()
+    d.cout, d.kh, d.kw, d.dilation, d.act, d.leaky_slope = cout, kh, kw, dil, act, 0.01
+    cabi.check(lib.tdn_conv2d_tc(C.byref(d), None), "conv2d_tc")
+    torch.cuda.synchronize()
+    ms = None
+    if reps:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(3):
+            lib.tdn_conv2d_tc(C.byref(d), None)
+        e0.record()
+        for _ in range(reps):
+            lib.tdn_conv2d_tc(C.byref(d), None)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+    out = (oh_.float() + ol_.float()) if out_split else of
+    return out, ms, int(flag.item())
+
+
+def ref_conv(x, wt, dil=1):
+    import torch
+    import torch.nn.functional as F
+    xd = x.permute(0, 3, 1, 2).double()
+    wd = wt.permute(0, 3, 1, 2).double()
+    k = wt.shape[1]
+    return F.conv2d(xd, wd, None, 1, dil * (k - 1) // 2, dil).permute(0, 2, 3, 1)
+
+
+def stats(out, ref):
+    d = (out.double() - ref)
+    return dict(max_abs=float(d.abs().max()), rel_l2=float(d.norm() / ref.norm()),
+                mean_signed_rel=float((d / ref.abs().clamp_min(1e-3)).mean()), ref_absmax=float(ref.abs().max()))
+
+
+def experiment(name):
+    import torch
+    torch.manual_seed(0)
+    dev = "cuda"
+    if name == "gemm_k64":
+        x = torch.randn(1, 1, 256, 64, device=dev)
+        w = torch.randn(128, 1, 1, 64, device=dev)
+        out, _, _ = run_tc(x, w)
+        return stats(out, ref_conv(x, w))
+    if name == "gemm_k512_ragged":
+        x = torch.randn(1, 1, 1000, 512, device=dev)
+        w = torch.randn(256, 1, 1, 512, device=dev) / 22
+        out, _, _ = run_tc(x, w)
+        return stats(out, ref_conv(x, w))
+    if name == "gemm_n64":
+        x = torch.randn(1, 1, 384, 128, device=dev)
+        w = torch.randn(64, 1, 1, 128, device=dev) / 11
+        out, _, _ = run_tc(x, w)
+        return stats(out, ref_conv(x, w))
+    if name == "conv3x3_d2_ragged":
+        x = torch.randn(2, 24, 40, 64, device=dev)
+        w = torch.randn(128, 3, 3, 64, device=dev) / 24
+        out, _, _ = run_tc(x, w, dil=2)
+        return stats(out, ref_conv(x, w, 2))
+    if name == "conv3x3_d8_97x193":
+        x = torch.randn(1, 97, 193, 128, device=dev)
+        w = torch.randn(96, 3, 3, 128, device=dev) / 34
+        out, _, _ = run_tc(x, w, dil=8)
+        return stats(out, ref_conv(x, w, 8))
+    if name == "epilogue":
+        x = torch.randn(1, 16, 32, 64, device=dev)
+        w = torch.randn(128, 3, 3, 64, device=dev) / 24
+        s, b = torch.rand(128, device=dev) + 0.5, torch.randn(128, device=dev)
+        r = torch.randn(1, 16, 32, 128, device=dev)
+        out, _, flag = run_tc(x, w, scale=s, bias=b, residual=r, act=1, out_split=True)
+        ref = torch.relu(ref_conv(x, w) * s.double() + b.double() + r.double())
+        st = stats(out, ref)
+        st["range_flag"] = flag
+        out2, _, _ = run_tc(x, w, bias=torch.randn(512, device=dev), bias_along_m=True)
+        return st
+    if name == "batched_qk":
+        q = torch.randn(2, 1, 300, 64, device=dev)
+        k = torch.randn(2, 100, 64, device=dev)
+        out, _, _ = run_tc(q, None, batched_w=k)
+        ref = torch.bmm(q.view(2, 300, 64).double(), k.double().transpose(1, 2)).view(2, 1, 300, 100)
+        return stats(out, ref)
+    if name == "layer4_perf":
+        x = torch.randn(1, 128, 256, 512, device=dev).relu()
+        w = torch.randn(512, 3, 3, 512, device=dev) / 68
+        out, ms, _ = run_tc(x, w, dil=4, reps=10)
+        st = stats(out, ref_conv(x, w, 4))
+        flop = 2 * 128 * 256 * 512 * 512 * 9
+        st.update(ms=ms, algorithmic_tflops=flop / ms / 1e9, executed_tflops=3 * flop / ms / 1e9)
+        return st
+    if name == "layer1_perf":
+        x = torch.randn(1, 256, 512, 64, device=dev).relu()
+        w = torch.randn(64, 3, 3, 64, device=dev) / 24
+        out, ms, _ = run_tc(x, w, dil=1, reps=10)
+        st = stats(out, ref_conv(x, w, 1))
+        flop = 2 * 256 * 512 * 64 * 64 * 9
+        st.update(ms=ms, algorithmic_tflops=flop / ms / 1e9)
+        return st
+    if name == "accum_bias_positive":
+        # all-positive operands: truncating accumulation would show up as a negative mean signed error
+        x = torch.rand(1, 1, 2048, 4608, device=dev) + 0.5
+        w = torch.rand(128, 1, 1, 4608, device=dev) + 0.5
+        out, _, _ = run_tc(x, w)
+        xs = (x.half().float() + (x - x.half().float()).half().float()).double()
+        ws = (w.half().float() + (w - w.half().float()).half().float()).double()
+        ref_split = torch.matmul(xs.view(2048, 4608), ws.view(128, 4608).t()).view(1, 1, 2048, 128)
+        ref_true = torch.matmul(x.double().view(2048, 4608), w.double().view(128, 4608).t()).view(1, 1, 2048, 128)
+        torch.backends.cuda.matmul.allow_tf32 = False
+        f32 = torch.matmul(x.view(2048, 4608), w.view(128, 4608).t()).view(1, 1, 2048, 128)
+        return dict(tc_vs_split_inputs=stats(out, ref_split), tc_vs_true=stats(out, ref_true),
+                    cublas_fp32_vs_true=stats(f32, ref_true))
+    raise KeyError(name)
+
+
+EXPERIMENTS = ["gemm_k64", "gemm_k512_ragged", "gemm_n64", "conv3x3_d2_ragged", "conv3x3_d8_97x193", "epilogue",
+               "batched_qk", "accum_bias_positive", "layer1_perf", "layer4_perf"]
+
+if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "--one":
+        print("RESULT " + json.dumps(experiment(sys.argv[2])))
+        sys.exit(0)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    lines = []
+    for name in (sys.argv[1:] or EXPERIMENTS):
+        t0 = time.time()
+        try:
+            r = subprocess.run([sys.executable, __file__, "--one", name], capture_output=True, text=True, timeout=150)
+            res = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")]
+            msg = res[0][7:] if res else f"FAILED rc={r.returncode} stdout={r.stdout[-600:]!r} stderr={r.stderr[-900:]!r}"
+        except subprocess.TimeoutExpired:
+            msg = "TIMEOUT (150 s)"
+        line = f"{name}: {msg}  [{time.time() - t0:.1f}s]"
+        print(line, flush=True)
+        lines.append(line)
+    open(os.path.join(ROOT, "gpurun_out", "tc_probe.txt"), "w").write("\n".join(lines) + "\n")

@@ -118,12 +118,14 @@ class PackedConv:
 class FramePlan:
     def __init__(self):
         self.ops: List[Callable] = []
+        self.names: List[str] = []   # per op: state-dict prefix of the conv it runs ('' for the rest)
         self.keep = []           # ctypes objects / tensors referenced by raw pointer
         self.kernel_launches = 0
 
-    def add(self, fn, *args, launches=1):
+    def add(self, fn, *args, launches=1, name=""):
         self.keep.append(args)
         self.ops.append((fn, args))
+        self.names.append(name)
         self.kernel_launches += launches
 
 
@@ -204,7 +206,7 @@ class Engine:
         d.weight_kn, d.batch = weight_kn, batch
         d.in_batch_stride, d.out_batch_stride = in_bs, out_bs
         d.residual_batch_stride, d.weight_batch_stride = res_bs, w_bs
-        plan.add(self.lib.tdn_conv2d, C.byref(d), "stream")
+        plan.add(self.lib.tdn_conv2d, C.byref(d), "stream", name=spec.name if spec else "")
         plan.keep.append((d, pc, x, out, residual))
 
     def _out_hw(self, h, w, c: A.Conv):
@@ -380,9 +382,16 @@ class Engine:
         return carry
 
     # ------------------------------------------------------------------ execution
-    def run(self, plan: FramePlan, img_ptr: int, out_ptr: int, stream: int):
+    def run(self, plan: FramePlan, img_ptr: int, out_ptr: int, stream: int, probe=None):
+        """Enqueue the frame.  probe = (op_name, event_before, event_after) brackets one op with CUDA
+        events (bench.py times the dominant kernel live this way)."""
         subst = {"img": img_ptr, "out": out_ptr, "stream": stream}
-        for fn, args in plan.ops:
+        for i, (fn, args) in enumerate(plan.ops):
+            hit = probe is not None and plan.names[i] == probe[0]
+            if hit:
+                probe[1].record()
             rc = fn(*[subst[a] if isinstance(a, str) else a for a in args])
+            if hit:
+                probe[2].record()
             if rc != 0:
                 _cabi.check(rc, fn.__name__)

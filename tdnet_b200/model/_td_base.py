@@ -132,8 +132,21 @@ class TDModel(nn.Module):
             self._engines[key] = eng
         return eng
 
+    def time_dominant_op(self, frames, step, reps=8):
+        """Average device time (ms) of the frame's dominant kernel -- the last 3x3 conv of layer4, 154.6
+        GFLOP at 1024x2048 for td4-psp18 -- bracketed by CUDA events while whole frames run."""
+        total = 0.0
+        for r in range(reps):
+            pos = (step + r) % self.PATHS
+            self.dominant_op_name = f"pretrained{pos + 1}.layer4.1.conv2"
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.forward(frames[(step + r) % len(frames)], pos_id=pos, _probe=(self.dominant_op_name, e0, e1))
+            torch.cuda.synchronize()
+            total += e0.elapsed_time(e1)
+        return total / reps
+
     @torch.no_grad()
-    def forward(self, img, pos_id=0):
+    def forward(self, img, pos_id=0, _probe=None):
         if not img.is_cuda:
             raise RuntimeError("tdnet_b200 runs on a CUDA (sm_100) device only; there is no CPU path. "
                                "Move the model and the input with .to('cuda').")
@@ -147,7 +160,7 @@ class TDModel(nn.Module):
         steady = len(self.Q_queue) >= self.arch.depth
         plan = eng.plan(pos_id + 1, steady)
         out = torch.empty((n, self.nclass, h, w), dtype=torch.float32, device=img.device)
-        eng.run(plan, img.data_ptr(), out.data_ptr(), torch.cuda.current_stream(img.device).cuda_stream)
+        eng.run(plan, img.data_ptr(), out.data_ptr(), torch.cuda.current_stream(img.device).cuda_stream, _probe)
         # FIFO bookkeeping mirrors buffer_contral; the tensors are views of the engine's device slots
         # (slot j = j-th oldest frame once the FIFO is full).
         depth = self.arch.depth
