@@ -164,13 +164,20 @@ uint64_t tdn_psp_pool_workspace_bytes(int32_t n, int32_t h, int32_t c);
  * view of a larger one (td4_psp18.py:273-276 + the slice/cat of :278-284). */
 int tdn_bilinear_nhwc(const tdn_tensor* in, const tdn_tensor* out, void* stream);
 
-/* Strided copy between NHWC fp32 views with equal dims (the x[:, pid*c/2:...] part of the cat in
+/* Strided copy between NHWC views with equal dims; the two views may differ in dtype, which makes
+ * this the F32 <-> SPLIT16 converter as well (the x[:, pid*c/2:...] part of the cat in
  * td4_psp18.py:278-284, and the FIFO snapshots of buffer_contral :123-134). */
 int tdn_copy_nhwc(const tdn_tensor* in, const tdn_tensor* out, void* stream);
 
 /* In-place softmax over the last dim of a [rows, cols] fp32 matrix after multiplying by `scale`
  * (transformer.py:128-134: attn / temperature, nn.Softmax(dim=2)).  ld = row pitch in elements. */
 int tdn_softmax_rows(float* s, int64_t rows, int32_t cols, int64_t ld, float scale, void* stream);
+
+/* Same softmax with the probabilities written as SPLIT16 fp16 planes (row pitch ld_out >= cols, the
+ * pad columns are zeroed) multiplied by out_scale (a power of two), ready to be the K-major A operand
+ * of tdn_conv2d_tc for attn @ v. */
+int tdn_softmax_rows_split16(const float* s, int64_t rows, int32_t cols, int64_t ld, float scale, void* p_hi,
+                             void* p_lo, int64_t ld_out, float out_scale, void* stream);
 
 /* Layer_Norm over the (H8,W8) map of every (n, channel) (td4_psp18.py:306-312, nn.LayerNorm([H8,W8]),
  * biased variance, eps 1e-5) in two steps: statistics (mean/rstd are [n, c]; fixed-order fp64

@@ -16,11 +16,19 @@ void set_error(const char* fmt, ...) {
 }
 const char* get_error() { return g_err; }
 
-int check_f32_tensor(const tdn_tensor* t, const char* what) {
+int check_tensor(const tdn_tensor* t, const char* what) {
   TDN_REQUIRE(t != nullptr && t->data != nullptr, TDN_ERR_INVALID, "%s: null tensor", what);
-  TDN_REQUIRE(t->dtype == TDN_F32, TDN_ERR_UNSUPPORTED, "%s: expected an fp32 plane", what);
+  TDN_REQUIRE(t->dtype == TDN_F32 || (t->dtype == TDN_SPLIT16 && t->data_lo != nullptr), TDN_ERR_INVALID,
+              "%s: dtype must be F32 or SPLIT16 (with a lo plane)", what);
   TDN_REQUIRE(t->n > 0 && t->h > 0 && t->w > 0 && t->c > 0, TDN_ERR_INVALID, "%s: empty dims [%d,%d,%d,%d]",
               what, t->n, t->h, t->w, t->c);
+  return TDN_OK;
+}
+
+int check_f32_tensor(const tdn_tensor* t, const char* what) {
+  int rc = check_tensor(t, what);
+  if (rc) return rc;
+  TDN_REQUIRE(t->dtype == TDN_F32, TDN_ERR_UNSUPPORTED, "%s: expected an fp32 plane", what);
   return TDN_OK;
 }
 
@@ -31,6 +39,7 @@ int psp_pool(const tdn_tensor*, const tdn_tensor*, float*, size_t, cudaStream_t)
 int bilinear_nhwc(const tdn_tensor*, const tdn_tensor*, cudaStream_t);
 int copy_nhwc(const tdn_tensor*, const tdn_tensor*, cudaStream_t);
 int softmax_rows(float*, long long, int, long long, float, cudaStream_t);
+int softmax_rows_split16(const float*, long long, int, long long, float, void*, void*, long long, float, cudaStream_t);
 int layernorm_hw_stats(const tdn_tensor*, float*, float*, float, void*, size_t, cudaStream_t);
 int layernorm_hw_apply(const tdn_tensor*, const float*, const float*, const float*, const float*,
                        const tdn_tensor*, cudaStream_t);
@@ -125,6 +134,11 @@ int tdn_copy_nhwc(const tdn_tensor* in, const tdn_tensor* out, void* stream) {
 
 int tdn_softmax_rows(float* s, int64_t rows, int32_t cols, int64_t ld, float scale, void* stream) {
   return softmax_rows(s, rows, cols, ld, scale, (cudaStream_t)stream);
+}
+
+int tdn_softmax_rows_split16(const float* s, int64_t rows, int32_t cols, int64_t ld, float scale, void* p_hi,
+                             void* p_lo, int64_t ld_out, float out_scale, void* stream) {
+  return softmax_rows_split16(s, rows, cols, ld, scale, p_hi, p_lo, ld_out, out_scale, (cudaStream_t)stream);
 }
 
 uint64_t tdn_layernorm_hw_workspace_bytes(int32_t n, int32_t h, int32_t w, int32_t c) {

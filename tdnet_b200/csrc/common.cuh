@@ -37,29 +37,78 @@ const char* get_error();
 
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
-// Device-side NHWC view (fp32 plane).
+// Device-side NHWC view: one fp32 plane (p) or two fp16 planes hi/lo with value = hi + lo
+// (TDN_SPLIT16).  Every layout kernel goes through ld4/st4/ld1/st1, so it accepts either format.
 struct View {
   float* p;
+  __half* hi;
+  __half* lo;
+  int split;
   int n, h, w, c;
   long long sn, sh, sw;
 };
 
 static inline View make_view(const tdn_tensor& t) {
   View v;
-  v.p = (float*)t.data;
+  v.split = t.dtype == TDN_SPLIT16;
+  v.p = v.split ? nullptr : (float*)t.data;
+  v.hi = v.split ? (__half*)t.data : nullptr;
+  v.lo = v.split ? (__half*)t.data_lo : nullptr;
   v.n = t.n; v.h = t.h; v.w = t.w; v.c = t.c;
   v.sn = t.stride_n; v.sh = t.stride_h; v.sw = t.stride_w;
   return v;
 }
 
-static inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
-
-// A float4-friendly view: 16-byte aligned base, channel count and all strides multiples of 4.
-static inline bool vec4_ok(const tdn_tensor& t) {
-  return aligned16(t.data) && (t.c % 4 == 0) && (t.stride_n % 4 == 0) && (t.stride_h % 4 == 0) &&
-         (t.stride_w % 4 == 0);
+__device__ __forceinline__ void split_f32(float x, __half& hi, __half& lo) {
+  hi = __float2half_rn(x);
+  lo = __float2half_rn(x - __half2float(hi));
 }
 
+// Four consecutive channels at element offset `off` (off % 4 == 0, planes suitably aligned).
+__device__ __forceinline__ float4 ld4(const View& v, long long off) {
+  if (!v.split) return *reinterpret_cast<const float4*>(v.p + off);
+  uint2 hv = *reinterpret_cast<const uint2*>(v.hi + off);
+  uint2 lv = *reinterpret_cast<const uint2*>(v.lo + off);
+  const __half2* h = reinterpret_cast<const __half2*>(&hv);
+  const __half2* l = reinterpret_cast<const __half2*>(&lv);
+  float2 h0 = __half22float2(h[0]), h1 = __half22float2(h[1]);
+  float2 l0 = __half22float2(l[0]), l1 = __half22float2(l[1]);
+  return make_float4(h0.x + l0.x, h0.y + l0.y, h1.x + l1.x, h1.y + l1.y);
+}
+__device__ __forceinline__ void st4(const View& v, long long off, float4 x) {
+  if (!v.split) {
+    *reinterpret_cast<float4*>(v.p + off) = x;
+    return;
+  }
+  __half h[4], l[4];
+  split_f32(x.x, h[0], l[0]); split_f32(x.y, h[1], l[1]);
+  split_f32(x.z, h[2], l[2]); split_f32(x.w, h[3], l[3]);
+  *reinterpret_cast<uint2*>(v.hi + off) = *reinterpret_cast<const uint2*>(h);
+  *reinterpret_cast<uint2*>(v.lo + off) = *reinterpret_cast<const uint2*>(l);
+}
+__device__ __forceinline__ float ld1(const View& v, long long off) {
+  if (!v.split) return v.p[off];
+  return __half2float(v.hi[off]) + __half2float(v.lo[off]);
+}
+__device__ __forceinline__ void st1(const View& v, long long off, float x) {
+  if (!v.split) { v.p[off] = x; return; }
+  __half h, l;
+  split_f32(x, h, l);
+  v.hi[off] = h; v.lo[off] = l;
+}
+
+static inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
+static inline bool aligned8(const void* p) { return (((uintptr_t)p) & 7u) == 0; }
+
+// A 4-channel-vector friendly view: aligned base(s), channel count and all strides multiples of 4.
+static inline bool vec4_ok(const tdn_tensor& t) {
+  bool base = t.dtype == TDN_SPLIT16 ? (aligned8(t.data) && aligned8(t.data_lo)) : aligned16(t.data);
+  return base && (t.c % 4 == 0) && (t.stride_n % 4 == 0) && (t.stride_h % 4 == 0) && (t.stride_w % 4 == 0);
+}
+
+// Validates a view of either dtype (non-null planes, positive dims).
+int check_tensor(const tdn_tensor* t, const char* what);
+// Same, and requires an fp32 plane.
 int check_f32_tensor(const tdn_tensor* t, const char* what);
 
 }  // namespace tdn

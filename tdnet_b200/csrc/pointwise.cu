@@ -21,13 +21,14 @@ __global__ void image_to_nhwc_kernel(const float* __restrict__ src, int n, int c
   const float* s = src + (long long)b * c * plane + (long long)y * w + x;
   float v[4] = {0.f, 0.f, 0.f, 0.f};
   for (int ch = 0; ch < c && ch < 4; ++ch) v[ch] = __ldg(s + ch * plane);
-  float* d = out.p + b * out.sn + y * out.sh + x * out.sw;
-  *reinterpret_cast<float4*>(d) = make_float4(v[0], v[1], v[2], v[3]);
+  st4(out, b * out.sn + y * out.sh + x * out.sw, make_float4(v[0], v[1], v[2], v[3]));
 }
 
 int image_to_nhwc(const float* nchw, int n, int c, int h, int w, const tdn_tensor* out,
                   cudaStream_t stream) {
-  TDN_REQUIRE(nchw && out && out->data, TDN_ERR_INVALID, "image_to_nhwc: null pointer");
+  TDN_REQUIRE(nchw != nullptr, TDN_ERR_INVALID, "image_to_nhwc: null pointer");
+  int rc;
+  if ((rc = check_tensor(out, "image_to_nhwc.out"))) return rc;
   TDN_REQUIRE(c <= 4 && out->c == 4 && out->n == n && out->h == h && out->w == w && vec4_ok(*out),
               TDN_ERR_INVALID, "image_to_nhwc: expects c<=4 and a float4-aligned [n,h,w,4] output");
   long long total = (long long)n * h * w;
@@ -58,17 +59,17 @@ __global__ void maxpool3x3s2_kernel(View in, View out) {
     for (int dx = 0; dx < 3; ++dx) {
       int ix = ox * 2 - 1 + dx;
       if (ix < 0 || ix >= in.w) continue;
-      float4 v = *reinterpret_cast<const float4*>(in.p + b * in.sn + iy * in.sh + ix * in.sw + cq * 4);
+      float4 v = ld4(in, b * in.sn + iy * in.sh + ix * in.sw + cq * 4);
       m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
     }
   }
-  *reinterpret_cast<float4*>(out.p + b * out.sn + oy * out.sh + ox * out.sw + cq * 4) = m;
+  st4(out, b * out.sn + oy * out.sh + ox * out.sw + cq * 4, m);
 }
 
 int maxpool3x3s2(const tdn_tensor* in, const tdn_tensor* out, cudaStream_t stream) {
   int rc;
-  if ((rc = check_f32_tensor(in, "maxpool.in"))) return rc;
-  if ((rc = check_f32_tensor(out, "maxpool.out"))) return rc;
+  if ((rc = check_tensor(in, "maxpool.in"))) return rc;
+  if ((rc = check_tensor(out, "maxpool.out"))) return rc;
   TDN_REQUIRE(vec4_ok(*in) && vec4_ok(*out), TDN_ERR_INVALID, "maxpool: float4-aligned views required");
   TDN_REQUIRE(out->h == (in->h - 1) / 2 + 1 && out->w == (in->w - 1) / 2 + 1 && out->c == in->c &&
                   out->n == in->n, TDN_ERR_INVALID, "maxpool: output dims mismatch");
@@ -90,7 +91,7 @@ __device__ __forceinline__ int bin_end(int i, int o, int len) { return ((i + 1) 
 
 __global__ void psp_rowsum_kernel(View in, float* __restrict__ rowsum) {
   const int y = blockIdx.x, b = blockIdx.y;
-  const float* row = in.p + b * in.sn + y * in.sh;
+  const long long row = b * in.sn + y * in.sh;
   float* dst = rowsum + ((long long)(b * in.h + y) * 12) * in.c;
   for (int c = threadIdx.x; c < in.c; c += blockDim.x) {
     int r = 0;
@@ -100,7 +101,7 @@ __global__ void psp_rowsum_kernel(View in, float* __restrict__ rowsum) {
       for (int j = 0; j < o; ++j, ++r) {
         int x0 = bin_start(j, o, in.w), x1 = bin_end(j, o, in.w);
         float s = 0.f;
-        for (int x = x0; x < x1; ++x) s += row[x * in.sw + c];
+        for (int x = x0; x < x1; ++x) s += ld1(in, row + x * in.sw + c);
         dst[(long long)r * in.c + c] = s;
       }
     }
@@ -129,7 +130,7 @@ __global__ void psp_binsum_kernel(const float* __restrict__ rowsum, View out, in
 int psp_pool(const tdn_tensor* in, const tdn_tensor* out, float* workspace, size_t workspace_bytes,
              cudaStream_t stream) {
   int rc;
-  if ((rc = check_f32_tensor(in, "psp_pool.in"))) return rc;
+  if ((rc = check_tensor(in, "psp_pool.in"))) return rc;
   if ((rc = check_f32_tensor(out, "psp_pool.out"))) return rc;
   TDN_REQUIRE(out->n == in->n && out->h == 1 && out->w == 50 && out->c == in->c, TDN_ERR_INVALID,
               "psp_pool: out must be [n,1,50,c]");
@@ -167,12 +168,12 @@ __global__ void bilinear_nhwc_kernel(View in, View out, float sy, float sx) {
   int y0, y1, x0, x1; float ly, lx;
   src_index(y, sy, in.h, y0, y1, ly);
   src_index(x, sx, in.w, x0, x1, lx);
-  const float* base = in.p + b * in.sn + c;
-  float v00 = base[y0 * in.sh + x0 * in.sw], v01 = base[y0 * in.sh + x1 * in.sw];
-  float v10 = base[y1 * in.sh + x0 * in.sw], v11 = base[y1 * in.sh + x1 * in.sw];
+  const long long base = b * in.sn + c;
+  float v00 = ld1(in, base + y0 * in.sh + x0 * in.sw), v01 = ld1(in, base + y0 * in.sh + x1 * in.sw);
+  float v10 = ld1(in, base + y1 * in.sh + x0 * in.sw), v11 = ld1(in, base + y1 * in.sh + x1 * in.sw);
   float top = v00 * (1.f - lx) + v01 * lx;
   float bot = v10 * (1.f - lx) + v11 * lx;
-  out.p[b * out.sn + y * out.sh + x * out.sw + c] = top * (1.f - ly) + bot * ly;
+  st1(out, b * out.sn + y * out.sh + x * out.sw + c, top * (1.f - ly) + bot * ly);
 }
 
 static inline float ac_scale(int in_size, int out_size) {
@@ -181,8 +182,8 @@ static inline float ac_scale(int in_size, int out_size) {
 
 int bilinear_nhwc(const tdn_tensor* in, const tdn_tensor* out, cudaStream_t stream) {
   int rc;
-  if ((rc = check_f32_tensor(in, "bilinear.in"))) return rc;
-  if ((rc = check_f32_tensor(out, "bilinear.out"))) return rc;
+  if ((rc = check_tensor(in, "bilinear.in"))) return rc;
+  if ((rc = check_tensor(out, "bilinear.out"))) return rc;
   TDN_REQUIRE(in->n == out->n && in->c == out->c, TDN_ERR_INVALID, "bilinear: n/c mismatch");
   long long total = (long long)out->n * out->h * out->w * out->c;
   bilinear_nhwc_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(
@@ -205,16 +206,16 @@ __global__ void copy_nhwc_kernel(View in, View out) {
   int x = t % out.w; t /= out.w;
   int y = t % out.h;
   int b = t / out.h;
-  const float* s = in.p + b * in.sn + y * in.sh + x * in.sw + c;
-  float* d = out.p + b * out.sn + y * out.sh + x * out.sw + c;
-  if (VEC == 4) *reinterpret_cast<float4*>(d) = *reinterpret_cast<const float4*>(s);
-  else *d = *s;
+  const long long so = b * in.sn + y * in.sh + x * in.sw + c;
+  const long long dof = b * out.sn + y * out.sh + x * out.sw + c;
+  if (VEC == 4) st4(out, dof, ld4(in, so));
+  else st1(out, dof, ld1(in, so));
 }
 
 int copy_nhwc(const tdn_tensor* in, const tdn_tensor* out, cudaStream_t stream) {
   int rc;
-  if ((rc = check_f32_tensor(in, "copy.in"))) return rc;
-  if ((rc = check_f32_tensor(out, "copy.out"))) return rc;
+  if ((rc = check_tensor(in, "copy.in"))) return rc;
+  if ((rc = check_tensor(out, "copy.out"))) return rc;
   TDN_REQUIRE(in->n == out->n && in->h == out->h && in->w == out->w && in->c == out->c,
               TDN_ERR_INVALID, "copy_nhwc: dims mismatch");
   if (vec4_ok(*in) && vec4_ok(*out)) {
@@ -228,83 +229,16 @@ int copy_nhwc(const tdn_tensor* in, const tdn_tensor* out, cudaStream_t stream) 
   return TDN_OK;
 }
 
-// ---------------------------------------------------------------------------------------------
-// fp32 <-> SPLIT16 (hi = fp16(x), lo = fp16(x - hi)), 4 channels per thread.
-// ---------------------------------------------------------------------------------------------
-__global__ void split16_kernel(View in, __half* __restrict__ hi, __half* __restrict__ lo, long long sn,
-                               long long sh, long long sw) {
-  const int c4 = in.c >> 2;
-  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  long long total = (long long)in.n * in.h * in.w * c4;
-  if (idx >= total) return;
-  int c = (idx % c4) * 4;
-  long long t = idx / c4;
-  int x = t % in.w; t /= in.w;
-  int y = t % in.h;
-  int b = t / in.h;
-  float4 v = *reinterpret_cast<const float4*>(in.p + b * in.sn + y * in.sh + x * in.sw + c);
-  float f[4] = {v.x, v.y, v.z, v.w};
-  __half h[4], l[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    h[j] = __float2half_rn(f[j]);
-    l[j] = __float2half_rn(f[j] - __half2float(h[j]));
-  }
-  long long o = b * sn + y * sh + x * sw + c;
-  *reinterpret_cast<uint2*>(hi + o) = *reinterpret_cast<const uint2*>(h);
-  *reinterpret_cast<uint2*>(lo + o) = *reinterpret_cast<const uint2*>(l);
-}
-
-__global__ void merge16_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, long long sn,
-                               long long sh, long long sw, View out) {
-  const int c4 = out.c >> 2;
-  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  long long total = (long long)out.n * out.h * out.w * c4;
-  if (idx >= total) return;
-  int c = (idx % c4) * 4;
-  long long t = idx / c4;
-  int x = t % out.w; t /= out.w;
-  int y = t % out.h;
-  int b = t / out.h;
-  long long i = b * sn + y * sh + x * sw + c;
-  uint2 hv = *reinterpret_cast<const uint2*>(hi + i);
-  uint2 lv = *reinterpret_cast<const uint2*>(lo + i);
-  const __half* h = reinterpret_cast<const __half*>(&hv);
-  const __half* l = reinterpret_cast<const __half*>(&lv);
-  float4 v = make_float4(__half2float(h[0]) + __half2float(l[0]), __half2float(h[1]) + __half2float(l[1]),
-                         __half2float(h[2]) + __half2float(l[2]), __half2float(h[3]) + __half2float(l[3]));
-  *reinterpret_cast<float4*>(out.p + b * out.sn + y * out.sh + x * out.sw + c) = v;
-}
-
-static int check_split_pair(const tdn_tensor* f, const tdn_tensor* s, const char* what) {
-  int rc;
-  if ((rc = check_f32_tensor(f, what))) return rc;
-  TDN_REQUIRE(s && s->data && s->data_lo && s->dtype == TDN_SPLIT16, TDN_ERR_INVALID, "%s: SPLIT16 view expected", what);
-  TDN_REQUIRE(f->n == s->n && f->h == s->h && f->w == s->w && f->c == s->c, TDN_ERR_INVALID, "%s: dims mismatch", what);
-  TDN_REQUIRE(vec4_ok(*f) && (((uintptr_t)s->data) & 7) == 0 && (((uintptr_t)s->data_lo) & 7) == 0 &&
-                  s->stride_w % 4 == 0 && s->stride_h % 4 == 0 && s->stride_n % 4 == 0,
-              TDN_ERR_INVALID, "%s: views must be vector aligned (c %% 4 == 0)", what);
-  return TDN_OK;
-}
-
+// fp32 <-> SPLIT16 conversions are copies between views of different dtype.
 int split16(const tdn_tensor* in, const tdn_tensor* out, cudaStream_t stream) {
-  int rc;
-  if ((rc = check_split_pair(in, out, "split16"))) return rc;
-  long long total = (long long)in->n * in->h * in->w * (in->c / 4);
-  split16_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(make_view(*in), (__half*)out->data, (__half*)out->data_lo,
-                                                           out->stride_n, out->stride_h, out->stride_w);
-  TDN_LAUNCH_OK();
-  return TDN_OK;
+  TDN_REQUIRE(in && out && in->dtype == TDN_F32 && out->dtype == TDN_SPLIT16, TDN_ERR_INVALID,
+              "split16: expects an F32 input and a SPLIT16 output");
+  return copy_nhwc(in, out, stream);
 }
-
 int merge16(const tdn_tensor* in, const tdn_tensor* out, cudaStream_t stream) {
-  int rc;
-  if ((rc = check_split_pair(out, in, "merge16"))) return rc;
-  long long total = (long long)out->n * out->h * out->w * (out->c / 4);
-  merge16_kernel<<<ceil_div(total, 256), 256, 0, stream>>>((const __half*)in->data, (const __half*)in->data_lo,
-                                                           in->stride_n, in->stride_h, in->stride_w, make_view(*out));
-  TDN_LAUNCH_OK();
-  return TDN_OK;
+  TDN_REQUIRE(in && out && in->dtype == TDN_SPLIT16 && out->dtype == TDN_F32, TDN_ERR_INVALID,
+              "merge16: expects a SPLIT16 input and an F32 output");
+  return copy_nhwc(in, out, stream);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -351,6 +285,57 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ s
   for (int c = threadIdx.x; c < cols; c += 256) row[c] *= inv;
 }
 
+// Same softmax, but the probabilities leave as SPLIT16 (times `out_scale`, a power of two that keeps the
+// lo plane in the normal fp16 range; the consumer GEMM undoes it in its epilogue scale).  Columns
+// [cols, ld_out) are written as zeros so that the row can be used as a K operand padded to 64.
+__global__ void __launch_bounds__(256) softmax_rows_split16_kernel(const float* __restrict__ s, int cols,
+                                                                   long long ld, float scale,
+                                                                   __half* __restrict__ p_hi,
+                                                                   __half* __restrict__ p_lo, long long ld_out,
+                                                                   float out_scale) {
+  __shared__ float red[8];
+  const float* row = s + blockIdx.x * ld;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  float m = -INFINITY;
+  for (int c = threadIdx.x; c < cols; c += 256) m = fmaxf(m, row[c] * scale);
+  m = warp_max(m);
+  if (lane == 0) red[wid] = m;
+  __syncthreads();
+  m = red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int c = threadIdx.x; c < cols; c += 256) sum += expf(row[c] * scale - m);
+  sum = warp_sum(sum);
+  if (lane == 0) red[wid] = sum;
+  __syncthreads();
+  sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sum += red[i];
+  const float inv = out_scale / sum;
+  __half* oh = p_hi + blockIdx.x * ld_out;
+  __half* ol = p_lo + blockIdx.x * ld_out;
+  for (int c = threadIdx.x; c < ld_out; c += 256) {
+    float v = c < cols ? expf(row[c] * scale - m) * inv : 0.f;
+    __half h, l;
+    split_f32(v, h, l);
+    oh[c] = h;
+    ol[c] = l;
+  }
+}
+
+int softmax_rows_split16(const float* s, long long rows, int cols, long long ld, float scale, void* p_hi,
+                         void* p_lo, long long ld_out, float out_scale, cudaStream_t stream) {
+  TDN_REQUIRE(s && p_hi && p_lo && rows > 0 && cols > 0 && ld >= cols && ld_out >= cols, TDN_ERR_INVALID,
+              "softmax_rows_split16: bad arguments");
+  TDN_REQUIRE(rows < (1ll << 31), TDN_ERR_UNSUPPORTED, "softmax_rows_split16: too many rows");
+  softmax_rows_split16_kernel<<<(unsigned)rows, 256, 0, stream>>>(s, cols, ld, scale, (__half*)p_hi, (__half*)p_lo,
+                                                                  ld_out, out_scale);
+  TDN_LAUNCH_OK();
+  return TDN_OK;
+}
+
 int softmax_rows(float* s, long long rows, int cols, long long ld, float scale, cudaStream_t stream) {
   TDN_REQUIRE(s && rows > 0 && cols > 0 && ld >= cols, TDN_ERR_INVALID, "softmax_rows: bad arguments");
   TDN_REQUIRE(rows < (1ll << 31), TDN_ERR_UNSUPPORTED, "softmax_rows: too many rows");
@@ -373,7 +358,7 @@ __global__ void ln_partial_kernel(View x, double2* __restrict__ part, int chunks
     double s = 0.0, q = 0.0;
     for (int p = p0; p < p1; ++p) {
       int y = p / x.w, xx = p - y * x.w;
-      double v = (double)x.p[b * x.sn + y * x.sh + xx * x.sw + c];
+      double v = (double)ld1(x, b * x.sn + y * x.sh + xx * x.sw + c);
       s += v; q += v * v;
     }
     part[((long long)b * chunks + chunk) * x.c + c] = make_double2(s, q);
@@ -400,7 +385,7 @@ __global__ void ln_final_kernel(const double2* __restrict__ part, int chunks, in
 int layernorm_hw_stats(const tdn_tensor* x, float* mean, float* rstd, float eps, void* workspace,
                        size_t workspace_bytes, cudaStream_t stream) {
   int rc;
-  if ((rc = check_f32_tensor(x, "layernorm.x"))) return rc;
+  if ((rc = check_tensor(x, "layernorm.x"))) return rc;
   TDN_REQUIRE(mean && rstd, TDN_ERR_INVALID, "layernorm_hw_stats: null output");
   const int P = x->h * x->w;
   const int chunks = ceil_div(P, LN_CHUNK);
@@ -429,7 +414,7 @@ __global__ void ln_apply_kernel(View x, View out, const float* __restrict__ mean
   int y = t % x.h;
   int b = t / x.h;
   const float g = gamma[y * x.w + xx], be = beta[y * x.w + xx];
-  float4 v = *reinterpret_cast<const float4*>(x.p + b * x.sn + y * x.sh + xx * x.sw + c);
+  float4 v = ld4(x, b * x.sn + y * x.sh + xx * x.sw + c);
   float4 mu = *reinterpret_cast<const float4*>(mean + b * x.c + c);
   float4 rs = *reinterpret_cast<const float4*>(rstd + b * x.c + c);
   float4 o;
@@ -437,14 +422,14 @@ __global__ void ln_apply_kernel(View x, View out, const float* __restrict__ mean
   o.y = (v.y - mu.y) * rs.y * g + be;
   o.z = (v.z - mu.z) * rs.z * g + be;
   o.w = (v.w - mu.w) * rs.w * g + be;
-  *reinterpret_cast<float4*>(out.p + b * out.sn + y * out.sh + xx * out.sw + c) = o;
+  st4(out, b * out.sn + y * out.sh + xx * out.sw + c, o);
 }
 
 int layernorm_hw_apply(const tdn_tensor* x, const float* mean, const float* rstd, const float* gamma,
                        const float* beta, const tdn_tensor* out, cudaStream_t stream) {
   int rc;
-  if ((rc = check_f32_tensor(x, "layernorm.x"))) return rc;
-  if ((rc = check_f32_tensor(out, "layernorm.out"))) return rc;
+  if ((rc = check_tensor(x, "layernorm.x"))) return rc;
+  if ((rc = check_tensor(out, "layernorm.out"))) return rc;
   TDN_REQUIRE(mean && rstd && gamma && beta, TDN_ERR_INVALID, "layernorm_hw_apply: null pointer");
   TDN_REQUIRE(vec4_ok(*x) && vec4_ok(*out) && aligned16(mean) && aligned16(rstd), TDN_ERR_INVALID,
               "layernorm_hw_apply: float4-aligned views required");

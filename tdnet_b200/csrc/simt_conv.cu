@@ -11,9 +11,10 @@
 namespace tdn {
 
 struct ConvParams {
-  const float* in;
-  float* out;
-  const float* res;
+  View in;    // dims unused; planes + format only (strides below)
+  View out;
+  View res;
+  int has_res;
   const float* w;
   const float* scale;
   const float* bias;
@@ -49,7 +50,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvParams p) {
   const int m0 = blockIdx.x * BM;
   const int n0 = blockIdx.y * BN;
   const int b = blockIdx.z;
-  const float* __restrict__ in = p.in + (long long)b * p.in_bs;
+  const long long in_b = (long long)b * p.in_bs;
   const float* __restrict__ w = p.w + (long long)b * p.w_bs;
 
   // ---- A-load mapping: two rows (r, r+64), one float4 of K each ----
@@ -92,8 +93,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvParams p) {
       int iw = a_iw0[i] + kx * p.dil;
       bool ok = kvalid && a_ok[i] && ih >= 0 && ih < p.Hin && iw >= 0 && iw < p.Win;
       if (ok) {
-        a_reg[i] = *reinterpret_cast<const float4*>(in + a_base[i] + (long long)ih * p.ish +
-                                                    (long long)iw * p.isw + c);
+        a_reg[i] = ld4(p.in, in_b + a_base[i] + (long long)ih * p.ish + (long long)iw * p.isw + c);
       } else {
         a_reg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
@@ -178,8 +178,9 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvParams p) {
   }
 
   // ---- epilogue: rows ty*4+{0..3} and 64+ty*4+{0..3}, cols n0+tx*4+{0..3} ----
-  float* __restrict__ out = p.out + (long long)b * p.out_bs;
-  const float* __restrict__ res = p.res ? p.res + (long long)b * p.res_bs : nullptr;
+  const long long out_b = (long long)b * p.out_bs;
+  const long long res_b = (long long)b * p.res_bs;
+  const bool res = p.has_res != 0;
   const int nb = n0 + tx * 4;
   float sc[TN], bi[TN];
 #pragma unroll
@@ -196,36 +197,36 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvParams p) {
     int t = m / p.Wo;
     int oh = t % p.Ho;
     int n = t / p.Ho;
-    long long ooff = (long long)n * p.osn + (long long)oh * p.osh + (long long)ow * p.osw + nb;
-    long long roff = (long long)n * p.rsn + (long long)oh * p.rsh + (long long)ow * p.rsw + nb;
+    long long ooff = out_b + (long long)n * p.osn + (long long)oh * p.osh + (long long)ow * p.osw + nb;
+    long long roff = res_b + (long long)n * p.rsn + (long long)oh * p.rsh + (long long)ow * p.rsw + nb;
     float v[TN];
 #pragma unroll
     for (int j = 0; j < TN; ++j) v[j] = fmaf(acc[i][j], sc[j], bi[j]);
     if (nb + 3 < p.Cout) {
       if (res) {
         if (p.res_vec4) {
-          float4 r = *reinterpret_cast<const float4*>(res + roff);
+          float4 r = ld4(p.res, roff);
           v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w;
         } else {
 #pragma unroll
-          for (int j = 0; j < TN; ++j) v[j] += res[roff + j];
+          for (int j = 0; j < TN; ++j) v[j] += ld1(p.res, roff + j);
         }
       }
 #pragma unroll
       for (int j = 0; j < TN; ++j) v[j] = apply_act(v[j], p.act, p.slope);
       if (p.out_vec4) {
-        *reinterpret_cast<float4*>(out + ooff) = make_float4(v[0], v[1], v[2], v[3]);
+        st4(p.out, ooff, make_float4(v[0], v[1], v[2], v[3]));
       } else {
 #pragma unroll
-        for (int j = 0; j < TN; ++j) out[ooff + j] = v[j];
+        for (int j = 0; j < TN; ++j) st1(p.out, ooff + j, v[j]);
       }
     } else {
 #pragma unroll
       for (int j = 0; j < TN; ++j) {
         if (nb + j < p.Cout) {
           float x = v[j];
-          if (res) x += res[roff + j];
-          out[ooff + j] = apply_act(x, p.act, p.slope);
+          if (res) x += ld1(p.res, roff + j);
+          st1(p.out, ooff + j, apply_act(x, p.act, p.slope));
         }
       }
     }
@@ -235,11 +236,12 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvParams p) {
 int conv2d_simt(const tdn_conv2d_desc* d, cudaStream_t stream) {
   const tdn_tensor& in = d->in;
   const tdn_tensor& out = d->out;
-  TDN_REQUIRE(in.dtype == TDN_F32 && out.dtype == TDN_F32, TDN_ERR_UNSUPPORTED,
-              "conv2d_simt: fp32 planes only");
+  int rc0;
+  if ((rc0 = check_tensor(&in, "conv2d.in"))) return rc0;
+  if ((rc0 = check_tensor(&out, "conv2d.out"))) return rc0;
   TDN_REQUIRE(in.c % 4 == 0, TDN_ERR_UNSUPPORTED, "conv2d_simt: cin=%d must be a multiple of 4", in.c);
-  TDN_REQUIRE(aligned16(in.data) && in.stride_n % 4 == 0 && in.stride_h % 4 == 0 && in.stride_w % 4 == 0,
-              TDN_ERR_INVALID, "conv2d_simt: input view must be 16-byte aligned with strides %% 4 == 0");
+  TDN_REQUIRE(vec4_ok(in) && d->in_batch_stride % 4 == 0,
+              TDN_ERR_INVALID, "conv2d_simt: input view must be vector aligned with strides %% 4 == 0");
   TDN_REQUIRE(aligned16(d->weight), TDN_ERR_INVALID, "conv2d_simt: weight must be 16-byte aligned");
   const int Ho = (in.h + 2 * d->pad - d->dilation * (d->kh - 1) - 1) / d->stride + 1;
   const int Wo = (in.w + 2 * d->pad - d->dilation * (d->kw - 1) - 1) / d->stride + 1;
@@ -247,9 +249,10 @@ int conv2d_simt(const tdn_conv2d_desc* d, cudaStream_t stream) {
               "conv2d: output dims [%d,%d,%d,%d] do not match computed [%d,%d,%d,%d]", out.n, out.h,
               out.w, out.c, in.n, Ho, Wo, d->cout);
   ConvParams p;
-  p.in = (const float*)in.data;
-  p.out = (float*)out.data;
-  p.res = (const float*)d->residual.data;
+  p.in = make_view(in);
+  p.out = make_view(out);
+  p.has_res = d->residual.data != nullptr;
+  p.res = p.has_res ? make_view(d->residual) : make_view(out);
   p.w = d->weight; p.scale = d->scale; p.bias = d->bias;
   p.isn = in.stride_n; p.ish = in.stride_h; p.isw = in.stride_w;
   p.osn = out.stride_n; p.osh = out.stride_h; p.osw = out.stride_w;
@@ -266,11 +269,11 @@ int conv2d_simt(const tdn_conv2d_desc* d, cudaStream_t stream) {
   p.act = d->act; p.slope = d->leaky_slope;
   p.w_kn = d->weight_kn;
   p.out_vec4 = vec4_ok(out) && (d->out_batch_stride % 4 == 0);
-  p.res_vec4 = p.res ? (vec4_ok(d->residual) && (d->residual_batch_stride % 4 == 0)) : 0;
-  if (p.res) {
-    TDN_REQUIRE(d->residual.dtype == TDN_F32 && d->residual.n == out.n && d->residual.h == out.h &&
-                    d->residual.w == out.w && d->residual.c == out.c,
-                TDN_ERR_INVALID, "conv2d: residual dims must equal output dims");
+  p.res_vec4 = p.has_res ? (vec4_ok(d->residual) && (d->residual_batch_stride % 4 == 0)) : 0;
+  if (p.has_res) {
+    if ((rc0 = check_tensor(&d->residual, "conv2d.residual"))) return rc0;
+    TDN_REQUIRE(d->residual.n == out.n && d->residual.h == out.h && d->residual.w == out.w &&
+                    d->residual.c == out.c, TDN_ERR_INVALID, "conv2d: residual dims must equal output dims");
   }
   if (p.w_kn) {
     // float4 weight loads along cout need cout % 4 == 0 alignment of each K row

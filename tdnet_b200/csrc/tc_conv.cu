@@ -408,16 +408,16 @@ int conv2d_tc(const tdn_tc_conv_desc* d, cudaStream_t stream) {
   p.w_batched = d->weight_batched;
   p.scale = d->scale; p.bias = d->bias; p.bias_along_m = d->bias_along_m;
   p.act = d->act; p.slope = d->leaky_slope;
-  // 16-byte vector stores/loads in the epilogue need channel-aligned rows
-  const bool vec_ok = (d->cout % 8 == 0);
+  // The epilogue stores 32-channel chunks with 16-byte vectors (a ragged last chunk falls back to scalar
+  // stores), so pixel rows must start 16-byte aligned: pitch % 8 (fp16 planes) / % 4 (fp32).
   if (out16) {
     p.out_hi = (__half*)out.data; p.out_lo = (__half*)out.data_lo;
     TDN_REQUIRE(aligned16(out.data) && aligned16(out.data_lo) && out.stride_w % 8 == 0 && out.stride_h % 8 == 0 &&
-                    out.stride_n % 8 == 0 && vec_ok, TDN_ERR_INVALID, "conv2d_tc: SPLIT16 output must be 16-byte aligned, cout %% 8 == 0");
+                    out.stride_n % 8 == 0, TDN_ERR_INVALID, "conv2d_tc: SPLIT16 output rows must be 16-byte aligned");
   } else {
     p.out_f32 = (float*)out.data;
-    TDN_REQUIRE(aligned16(out.data) && out.stride_w % 4 == 0 && out.stride_h % 4 == 0 && out.stride_n % 4 == 0 &&
-                    d->cout % 4 == 0, TDN_ERR_INVALID, "conv2d_tc: fp32 output must be 16-byte aligned, cout %% 4 == 0");
+    TDN_REQUIRE(aligned16(out.data) && out.stride_w % 4 == 0 && out.stride_h % 4 == 0 && out.stride_n % 4 == 0,
+                TDN_ERR_INVALID, "conv2d_tc: fp32 output rows must be 16-byte aligned");
   }
   if (d->out_f32_copy) {
     TDN_REQUIRE(out16 && aligned16(d->out_f32_copy), TDN_ERR_INVALID, "conv2d_tc: out_f32_copy needs a SPLIT16 primary output");

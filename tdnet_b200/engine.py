@@ -40,47 +40,79 @@ PSP_OFFSETS = (0, 1, 5, 14)
 
 
 class View:
-    """NHWC fp32 view over a torch buffer (element strides), convertible to a C `tdn_tensor`."""
+    """NHWC view over torch storage (element strides), convertible to a C `tdn_tensor`.
+    fp32: one float32 buffer.  SPLIT16: two float16 buffers (`base` = hi plane, `lo` = lo plane)."""
 
-    def __init__(self, base: torch.Tensor, n, h, w, c, sn=None, sh=None, sw=None, offset=0):
-        self.base, self.n, self.h, self.w, self.c = base, n, h, w, c
+    def __init__(self, base: torch.Tensor, n, h, w, c, sn=None, sh=None, sw=None, offset=0, lo=None):
+        self.base, self.lo, self.n, self.h, self.w, self.c = base, lo, n, h, w, c
         self.sw = c if sw is None else sw
         self.sh = w * self.sw if sh is None else sh
         self.sn = h * self.sh if sn is None else sn
         self.offset = offset
 
+    @property
+    def split(self):
+        return self.lo is not None
+
     @staticmethod
-    def alloc(n, h, w, c, device, zero=False):
+    def alloc(n, h, w, c, device, zero=False, split=False):
         fn = torch.zeros if zero else torch.empty
+        if split:
+            return View(fn(n * h * w * c, dtype=torch.float16, device=device), n, h, w, c,
+                        lo=fn(n * h * w * c, dtype=torch.float16, device=device))
         return View(fn(n * h * w * c, dtype=torch.float32, device=device), n, h, w, c)
 
     @property
     def ptr(self):
-        return self.base.data_ptr() + 4 * self.offset
+        return self.base.data_ptr() + self.base.element_size() * self.offset
+
+    @property
+    def ptr_lo(self):
+        return None if self.lo is None else self.lo.data_ptr() + 2 * self.offset
 
     def ct(self) -> Tensor:
-        return Tensor(self.ptr, None, _cabi.TDN_F32, self.n, self.h, self.w, self.c, self.sn, self.sh, self.sw)
+        return Tensor(self.ptr, self.ptr_lo, _cabi.TDN_SPLIT16 if self.split else _cabi.TDN_F32, self.n, self.h,
+                      self.w, self.c, self.sn, self.sh, self.sw)
+
+    def _like(self, n, h, w, c, sn, sh, sw, offset):
+        return View(self.base, n, h, w, c, sn, sh, sw, offset, lo=self.lo)
 
     def channels(self, lo, hi):
-        return View(self.base, self.n, self.h, self.w, hi - lo, self.sn, self.sh, self.sw, self.offset + lo)
+        return self._like(self.n, self.h, self.w, hi - lo, self.sn, self.sh, self.sw, self.offset + lo)
 
     def subsample(self, s):
-        return View(self.base, self.n, (self.h - 1) // s + 1, (self.w - 1) // s + 1, self.c, self.sn,
-                    self.sh * s, self.sw * s, self.offset)
+        return self._like(self.n, (self.h - 1) // s + 1, (self.w - 1) // s + 1, self.c, self.sn, self.sh * s,
+                          self.sw * s, self.offset)
 
     def rows(self, lo, hi, h, w):
         """Rows [lo, hi) of a [n,1,R,c] matrix view, reshaped to an h x w grid (PSP bins)."""
         assert self.h == 1 and (hi - lo) == h * w
-        return View(self.base, self.n, h, w, self.c, self.sn, w * self.sw, self.sw, self.offset + lo * self.sw)
+        return self._like(self.n, h, w, self.c, self.sn, w * self.sw, self.sw, self.offset + lo * self.sw)
 
     def tokens(self):
         """[n,h,w,c] dense map -> per-image token matrix [1,1,h*w,c] (+ batch stride)."""
         assert self.sh == self.w * self.sw
-        return View(self.base, 1, 1, self.h * self.w, self.c, self.sn, self.h * self.w * self.sw, self.sw, self.offset)
+        return self._like(1, 1, self.h * self.w, self.c, self.sn, self.h * self.w * self.sw, self.sw, self.offset)
+
+    def image(self, i):
+        """Image i of the batch as an n=1 view."""
+        return self._like(1, self.h, self.w, self.c, self.sn, self.sh, self.sw, self.offset + i * self.sn)
+
+    def narrow_c(self, c):
+        """First c channels (columns of a token matrix) with the row pitch unchanged."""
+        return self._like(self.n, self.h, self.w, c, self.sn, self.sh, self.sw, self.offset)
+
+    def narrow_w(self, w):
+        """First w columns (token rows) of each row."""
+        return self._like(self.n, self.h, w, self.c, self.sn, self.sh, self.sw, self.offset)
 
     def torch(self):
-        """Dense torch view [n,h,w,c] (tests / FIFO introspection)."""
-        return torch.as_strided(self.base, (self.n, self.h, self.w, self.c), (self.sn, self.sh, self.sw, 1), self.offset)
+        """Dense fp32 torch tensor [n,h,w,c] (tests / FIFO introspection); SPLIT16 views are merged."""
+        shape, strides = (self.n, self.h, self.w, self.c), (self.sn, self.sh, self.sw, 1)
+        t = torch.as_strided(self.base, shape, strides, self.offset)
+        if self.split:
+            return t.float() + torch.as_strided(self.lo, shape, strides, self.offset).float()
+        return t
 
 
 class PackedConv:
@@ -113,6 +145,29 @@ class PackedConv:
         self.weight = w.to(device)
         self.scale = None if scale is None else scale.contiguous().to(device)
         self.bias = None if shift is None else shift.contiguous().to(device)
+        self._tc = None
+
+    def tc(self):
+        """SPLIT16 form for the tcgen05 kernel: rows scaled by an exact power of two so that the lo
+        plane stays in the normal fp16 range (max |w| of a row lands in [2^13, 2^14)), hi = fp16(w),
+        lo = fp16(w - hi); the epilogue scale absorbs 2^-k.  Returns (hi, lo, scale[cout], K)."""
+        if self._tc is None:
+            w = self.weight.reshape(self.cout, -1).float()
+            hi, lo, inv = split_rows_pow2(w)
+            scale = inv if self.scale is None else self.scale * inv
+            self._tc = (hi, lo, scale.contiguous(), w.shape[1])
+        return self._tc
+
+
+def split_rows_pow2(w: torch.Tensor):
+    """w [rows, K] fp32 -> (hi fp16, lo fp16, inv_scale fp32[rows]) with w = (hi + lo) * inv_scale."""
+    amax = w.abs().amax(dim=1).clamp_min(1e-30)
+    k = torch.floor(torch.log2(16000.0 / amax)).clamp_(-24, 40)
+    mult = torch.exp2(k)
+    ws = w * mult[:, None]
+    hi = ws.half()
+    lo = (ws - hi.float()).half()
+    return hi.contiguous(), lo.contiguous(), torch.exp2(-k).contiguous()
 
 
 class FramePlan:
@@ -132,8 +187,12 @@ class FramePlan:
 class Engine:
     """Static buffers + plans for one (batch, H, W).  `weights` is the model's state dict."""
 
-    def __init__(self, arch: A.ModelArch, state_dict, n, H, W, device, ln_shape):
+    def __init__(self, arch: A.ModelArch, state_dict, n, H, W, device, ln_shape, mode="tc"):
+        """mode 'tc': tcgen05 exact-mode kernels on SPLIT16 activations wherever the shape allows (the
+        product path on B200); mode 'simt': everything on the fp32 CUDA-core kernels (yardstick)."""
+        assert mode in ("tc", "simt")
         self.lib = _cabi.load()
+        self.tc = mode == "tc"
         self.m, self.n, self.H, self.W, self.device = arch, n, H, W, device
         self.h8, self.w8 = A.feature_hw(H, W)
         if tuple(ln_shape) != (self.h8, self.w8):
@@ -143,7 +202,7 @@ class Engine:
                                f"[{n}, {arch.d_v}, {self.h8}, {self.w8}]")
         self.hs, self.ws = (self.h8 - 1) // 4 + 1, (self.w8 - 1) // 4 + 1
         self.pk = self.hs * self.ws                       # keys per frame (P')
-        self.pk_pad = (self.pk + 3) // 4 * 4
+        self.pk_pad = (self.pk + 63) // 64 * 64 if self.tc else (self.pk + 3) // 4 * 4
         self.sd = state_dict
         self._packed: Dict[str, PackedConv] = {}
         self._plans: Dict[tuple, FramePlan] = {}
@@ -152,9 +211,11 @@ class Engine:
         m = arch
         dev = device
         # FIFO slots: token matrices [n, P'(padded rows for V'), c]
-        self.q_slots = [View.alloc(n, 1, self.pk, m.d_k, dev, zero=True) for _ in range(m.depth)]
-        self.k_slots = [View.alloc(n, 1, self.pk, m.d_k, dev, zero=True) for _ in range(m.depth)]
-        self.v_slots = [View.alloc(n, 1, self.pk, m.d_v, dev, zero=True) for _ in range(m.depth)]
+        self.q_slots = [View.alloc(n, 1, self.pk, m.d_k, dev, zero=True, split=self.tc) for _ in range(m.depth)]
+        self.k_slots = [View.alloc(n, 1, self.pk, m.d_k, dev, zero=True, split=self.tc) for _ in range(m.depth)]
+        self.v_slots = [View.alloc(n, 1, self.pk, m.d_v, dev, zero=True, split=self.tc) for _ in range(m.depth)]
+        self.range_flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._consts: Dict[tuple, torch.Tensor] = {}
         self.ln_gamma = {p: state_dict[f"layer_norm{p}.ln.weight"].detach().float().reshape(-1).contiguous().to(dev)
                          for p in range(1, m.paths + 1)}
         self.ln_beta = {p: state_dict[f"layer_norm{p}.ln.bias"].detach().float().reshape(-1).contiguous().to(dev)
@@ -167,23 +228,72 @@ class Engine:
             self._packed[key] = PackedConv(spec, self.sd, self.device, row_slice)
         return self._packed[key]
 
-    def buf(self, n, h, w, c, zero=False) -> View:
+    def const_vec(self, value: float, length: int) -> torch.Tensor:
+        key = (value, length)
+        if key not in self._consts:
+            self._consts[key] = torch.full((length,), value, dtype=torch.float32, device=self.device)
+        return self._consts[key]
+
+    def buf(self, n, h, w, c, zero=False, split=None) -> View:
         """Scratch buffer for the plan being built.  Plans never run concurrently and nothing but the
         FIFO slots survives a frame, so all plans of an engine share one pool: the i-th request of a
         given size in every plan maps to the same storage.  `zero` buffers (padded S / V' matrices whose
         pad columns must stay 0) live in their own pool and are only ever reused at identical shape."""
-        key = (n * h * w * c, (n, h, w, c) if zero else None)
+        split = self.tc if split is None else split
+        key = (n * h * w * c, (n, h, w, c) if zero else None, split)
         idx = self._cursor.get(key, 0)
         self._cursor[key] = idx + 1
         pool = self._pool.setdefault(key, [])
         if idx == len(pool):
             fn = torch.zeros if zero else torch.empty
-            pool.append(fn(n * h * w * c, dtype=torch.float32, device=self.device))
-        return View(pool[idx], n, h, w, c)
+            if split:
+                pool.append((fn(n * h * w * c, dtype=torch.float16, device=self.device),
+                             fn(n * h * w * c, dtype=torch.float16, device=self.device)))
+            else:
+                pool.append((fn(n * h * w * c, dtype=torch.float32, device=self.device), None))
+        hi, lo = pool[idx]
+        return View(hi, n, h, w, c, lo=lo)
 
-    def _conv(self, plan: FramePlan, pc: PackedConv, x: View, out: View, residual: Optional[View] = None,
-              act=None, stride=None, batch=1, weight_ptr=None, weight_kn=0, in_bs=0, out_bs=0, res_bs=0, w_bs=0,
-              k=None, dilation=None, cout=None, scale_ptr="auto", bias_ptr="auto"):
+    def _conv(self, plan: FramePlan, pc: PackedConv, x: View, out: View, residual: Optional[View] = None, **kw):
+        """Folded conv+BN+act(+residual).  Takes the tcgen05 kernel when the engine runs in 'tc' mode and
+        the geometry fits it (stride 1, cin % 64 == 0, SPLIT16 input); the fp32 CUDA-core kernel otherwise
+        (3-channel stem, stride-2 convs, pooled PSP convs, the 19-class classifier)."""
+        spec = pc.spec if pc is not None else None
+        if (self.tc and spec is not None and not kw and spec.stride == 1 and x.split and x.c % 64 == 0
+                and x.n * x.h * x.w >= 64):
+            return self._conv_tc(plan, x, out, pc=pc, residual=residual)
+        return self._conv_simt(plan, pc, x, out, residual, **kw)
+
+    def _conv_tc(self, plan: FramePlan, x: View, out: View, pc: PackedConv = None, residual: Optional[View] = None,
+                 w_hi=None, w_lo=None, w_ld=None, w_bs=0, batched=False, cout=None, k=1, dilation=1, act="none",
+                 scale=None, bias=None, bias_along_m=False, name=""):
+        d = _cabi.TcConvDesc()
+        d.in_, d.out = x.ct(), out.ct()
+        if residual is not None:
+            d.residual = residual.ct()
+        if pc is not None:
+            hi, lo, sc, K = pc.tc()
+            d.weight_hi, d.weight_lo, d.weight_ld = hi.data_ptr(), lo.data_ptr(), K
+            d.scale = sc.data_ptr()
+            d.bias = pc.bias.data_ptr() if pc.bias is not None else None
+            d.cout, d.kh, d.kw, d.dilation = pc.cout, pc.spec.k, pc.spec.k, pc.spec.dilation
+            d.act = _ACT[pc.spec.act]
+            name = pc.spec.name
+        else:
+            d.weight_hi, d.weight_lo, d.weight_ld = w_hi, w_lo, w_ld
+            d.weight_batched, d.weight_batch_stride = int(batched), w_bs
+            d.scale = scale.data_ptr() if scale is not None else None
+            d.bias = bias.data_ptr() if bias is not None else None
+            d.bias_along_m = int(bias_along_m)
+            d.cout, d.kh, d.kw, d.dilation, d.act = cout, k, k, dilation, _ACT[act]
+        d.leaky_slope = 0.01
+        d.range_flag = self.range_flag.data_ptr()
+        plan.add(self.lib.tdn_conv2d_tc, C.byref(d), "stream", name=name)
+        plan.keep.append((d, pc, x, out, residual, scale, bias))
+
+    def _conv_simt(self, plan: FramePlan, pc: PackedConv, x: View, out: View, residual: Optional[View] = None,
+                   act=None, stride=None, batch=1, weight_ptr=None, weight_kn=0, in_bs=0, out_bs=0, res_bs=0, w_bs=0,
+                   k=None, dilation=None, cout=None, scale_ptr="auto", bias_ptr="auto"):
         spec = pc.spec if pc is not None else None
         d = Conv2dDesc()
         d.in_, d.out = x.ct(), out.ct()
@@ -228,7 +338,7 @@ class Engine:
         H, W, h8, w8 = self.H, self.W, self.h8, self.w8
 
         # --- stem: NCHW image -> NHWC(4) -> conv(s) -> maxpool
-        img = self.buf(n, H, W, 4)
+        img = self.buf(n, H, W, 4, split=False)
         plan.add(lib.tdn_image_to_nhwc, "img", n, 3, H, W, C.byref(self._ct(plan, img)), "stream")
         x = img
         for c in m.stems[path]:
@@ -264,7 +374,7 @@ class Engine:
         z = self.buf(n, h8, w8, m.c4)
         plan.add(lib.tdn_copy_nhwc, C.byref(self._ct(plan, c4.channels(pid * half, (pid + 1) * half))),
                  C.byref(self._ct(plan, z.channels(0, half))), "stream")
-        pooled = self.buf(n, 1, 50, m.c4)
+        pooled = self.buf(n, 1, 50, m.c4, split=False)
         ws_bytes = int(lib.tdn_psp_pool_workspace_bytes(n, h8, m.c4))
         ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=self.device)
         plan.add(lib.tdn_psp_pool, C.byref(self._ct(plan, c4)), C.byref(self._ct(plan, pooled)), ws.data_ptr(),
@@ -272,7 +382,7 @@ class Engine:
         plan.keep.append(ws)
         for i, (bins, off, c) in enumerate(zip(PSP_BINS, PSP_OFFSETS, A.psp_convs(m, path))):
             pc = self.packed(c, row_slice=(pid * eighth, (pid + 1) * eighth))
-            small = self.buf(n, bins, bins, eighth)
+            small = self.buf(n, bins, bins, eighth, split=False)
             self._conv(plan, pc, pooled.rows(off, off + bins * bins, bins, bins), small)
             plan.add(lib.tdn_bilinear_nhwc, C.byref(self._ct(plan, small)),
                      C.byref(self._ct(plan, z.channels(half + i * eighth, half + (i + 1) * eighth))), "stream")
@@ -288,7 +398,8 @@ class Engine:
 
         # --- attention propagation over the FIFO
         if steady:
-            fused = self._attention_chain(plan, path, q_cur, v_cur)
+            chain = self._attention_chain_tc if self.tc else self._attention_chain
+            fused = chain(plan, path, q_cur, v_cur)
         else:
             fused = v_cur  # td4_psp18.py:142-143: head(layer_norm(v_cur)) while the FIFO fills
 
@@ -307,7 +418,7 @@ class Engine:
         hc = A.head_convs(m, path)
         mid = self.buf(n, h8, w8, m.head_mid)
         self._conv(plan, self.packed(hc[0]), normed, mid)
-        low = self.buf(n, h8, w8, m.nclass)
+        low = self.buf(n, h8, w8, m.nclass, split=False)
         self._conv(plan, self.packed(hc[1]), mid, low)
         plan.add(lib.tdn_upsample_logits, C.byref(self._ct(plan, low)), "out", H, W, "stream")
 
@@ -331,7 +442,7 @@ class Engine:
 
     def _grid_view(self, slot: View) -> View:
         """FIFO slot [n,1,P',c] seen as the [n,hs,ws,c] grid it was sampled from."""
-        return View(slot.base, slot.n, self.hs, self.ws, slot.c, slot.sn, self.ws * slot.sw, slot.sw, slot.offset)
+        return slot._like(slot.n, self.hs, self.ws, slot.c, slot.sn, self.ws * slot.sw, slot.sw, slot.offset)
 
     def _ct(self, plan: FramePlan, v: View) -> Tensor:
         t = v.ct()
@@ -380,6 +491,72 @@ class Engine:
                        bias_ptr=None)
             carry = out
         return carry
+
+    def _attention_chain_tc(self, plan: FramePlan, path: int, q_cur: View, v_cur: View) -> View:
+        """Same chain on the tensor cores (SPLIT16 operands, exact mode).  Per hop and image:
+             V'^T [d_v, P'] = W_fc @ v_src^T + b      (bias along rows; written K-major for the last GEMM)
+             S    [Pq, P']  = q @ k^T                 (fp32)
+             P    = softmax(S / 8) * 2^10             (SPLIT16; 2^10 keeps the lo plane normal)
+             out  [Pq, d_v] = P @ V' * 2^-10 + residual
+        The fused single-kernel version replaces the middle three steps (tc_attn.cu)."""
+        m, n, lib = self.m, self.n, self.lib
+        hops = m.hop_modules(path)
+        pk, pkp, pq_full = self.pk, self.pk_pad, self.h8 * self.w8
+        P_SCALE = 1024.0
+        carry = None
+        for j, name in enumerate(hops):
+            last = j == len(hops) - 1
+            v_src = self.v_slots[j] if carry is None else carry          # [n,1,P',d_v] SPLIT16
+            fc = self.packed(A.fc_conv(m, name))
+            wfc = self._fc_as_activation(fc)                              # [1,1,d_v,d_v] SPLIT16 + scale
+            vpt = self.buf(n, 1, m.d_v, pkp, zero=True)                   # V'^T, K (=P') padded to 64
+            if last:
+                q, pq = q_cur.tokens(), pq_full                           # per image [1,1,P,64]
+                out = self.buf(n, self.h8, self.w8, m.d_v)
+                res_all, out_tok = v_cur, out._like(n, 1, pq_full, m.d_v, out.sn, out.sn, m.d_v, out.offset)
+                res_tok = v_cur._like(n, 1, pq_full, m.d_v, v_cur.sn, v_cur.sn, m.d_v, v_cur.offset)
+            else:
+                pq = pk
+                out = self.buf(n, 1, pk, m.d_v)
+                out_tok, res_tok = out, self.v_slots[j + 1]
+            q_all = (q_cur._like(n, 1, pq_full, m.d_k, q_cur.sn, q_cur.sn, m.d_k, q_cur.offset) if last
+                     else self.q_slots[j + 1])
+            s_buf = self.buf(n, 1, pq, pkp, split=False)
+            p_buf = self.buf(n, 1, pq, pkp)
+            for i in range(n):
+                # V'^T_i = W_fc @ v_src_i^T + b  -> rows d_v, cols P'
+                self._conv_tc(plan, wfc["view"], vpt.image(i).narrow_c(pk), w_hi=v_src.image(i).ptr,
+                              w_lo=v_src.image(i).ptr_lo, w_ld=v_src.sw, cout=pk,
+                              scale=self.const_vec(wfc["inv_scale"], pkp), bias=fc.bias,
+                              bias_along_m=True, name=name + ".fc")
+            # S = q k^T (all images in one launch: weights batched per image)
+            k_slot = self.k_slots[j]
+            self._conv_tc(plan, q_all, s_buf.narrow_c(pk), w_hi=k_slot.ptr, w_lo=k_slot.ptr_lo, w_ld=k_slot.sw,
+                          w_bs=k_slot.sn, batched=True, cout=pk, name=name + ".qk")
+            plan.add(lib.tdn_softmax_rows_split16, s_buf.ptr, n * pq, pk, pkp, C.c_float(1.0 / float(m.d_k) ** 0.5),
+                     p_buf.ptr, p_buf.ptr_lo, pkp, C.c_float(P_SCALE), "stream", name=name + ".softmax")
+            plan.keep.append((s_buf, p_buf))
+            self._conv_tc(plan, p_buf, out_tok, residual=res_tok, w_hi=vpt.ptr, w_lo=vpt.ptr_lo, w_ld=pkp,
+                          w_bs=vpt.sn, batched=True, cout=m.d_v, scale=self.const_vec(1.0 / P_SCALE, m.d_v),
+                          name=name + ".pv")
+            carry = out
+        return carry
+
+    def _fc_as_activation(self, fc: PackedConv):
+        """Attention.fc weight [d_v, d_v] as a SPLIT16 'activation' [1,1,d_v,d_v] (A operand of the
+        V'^T GEMM), scaled by one exact power of two; returns the view and the per-column inverse scale."""
+        key = "fcact:" + fc.spec.name
+        if key not in self._packed:
+            w = fc.weight.reshape(fc.cout, -1).float()
+            amax = float(w.abs().max().clamp_min(1e-30))
+            import math
+            kexp = max(-24, min(40, math.floor(math.log2(16000.0 / amax))))
+            ws = w * (2.0 ** kexp)
+            hi = ws.half().contiguous()
+            lo = (ws - hi.float()).half().contiguous()
+            view = View(hi.view(-1), 1, 1, fc.cout, w.shape[1], lo=lo.view(-1))
+            self._packed[key] = dict(view=view, inv_scale=2.0 ** (-kexp), hi=hi, lo=lo)
+        return self._packed[key]
 
     # ------------------------------------------------------------------ execution
     def run(self, plan: FramePlan, img_ptr: int, out_ptr: int, stream: int, probe=None):

@@ -79,7 +79,8 @@ class TDModel(nn.Module):
         self.pretrained_mp_load()
         self.Q_queue, self.K_queue, self.V_queue = [], [], []
         self._engines: Dict[tuple, object] = {}
-        self._frames_seen = 0
+        # 'tc': tcgen05 exact-mode kernels (product path on B200); 'simt': fp32 CUDA-core kernels only.
+        self.engine_mode = os.environ.get("TDNET_B200_ENGINE", "tc")
 
     # ---- reference API ---------------------------------------------------------------------
     def pretrained_mp_load(self):
@@ -121,14 +122,14 @@ class TDModel(nn.Module):
     def _engine(self, img: torch.Tensor):
         from ..engine import Engine
         n, c, h, w = img.shape
-        key = (n, h, w, img.device.index)
+        key = (n, h, w, img.device.index, self.engine_mode)
         eng = self._engines.get(key)
         if eng is None:
             if self._engines:  # a different input shape starts a new clip: the FIFO lives in the engine
                 self._engines.clear()
                 self.reset()
             sd = {k: v.detach().cpu() for k, v in self.state_dict().items()}
-            eng = Engine(self.arch, sd, n, h, w, img.device, self.ln_shape)
+            eng = Engine(self.arch, sd, n, h, w, img.device, self.ln_shape, mode=self.engine_mode)
             self._engines[key] = eng
         return eng
 

@@ -20,13 +20,14 @@ LOGIT_TOL = 2e-4
 TAP_TOL = 1e-3   # backbone maps reach |x| ~ 40
 
 
-def build_model(arch, backbone, h8, w8, sd):
+def build_model(arch, backbone, h8, w8, sd, mode="tc"):
     from tdnet_b200.model import td2_psp50, td4_psp18
     if arch == "td4_psp18":
         net = td4_psp18.td4_psp18(nclass=19, path_num=4, backbone=backbone, ln_shape=(h8, w8))
     else:
         net = td2_psp50.td2_psp50(nclass=19, path_num=2, backbone=backbone, ln_shape=(h8, w8))
     net.load_state_dict(sd, strict=True)
+    net.engine_mode = mode   # 'tc': tcgen05 exact-mode kernels (product path); 'simt': fp32 CUDA-core yardstick
     return net.eval().to("cuda:0")
 
 
@@ -34,12 +35,13 @@ def tap(view):  # engine NHWC view -> NCHW cpu tensor
     return view.torch().permute(0, 3, 1, 2).contiguous().cpu()
 
 
+@pytest.mark.parametrize("mode", ["tc", "simt"])
 @pytest.mark.parametrize("name", [n for n in GOLDEN_CASES if not n.endswith("_chk")])
-def test_model_matches_reference_golden(name):
+def test_model_matches_reference_golden(name, mode):
     arch, backbone = GOLDEN_CASES[name]
     g, m = load_golden(name)
     sd = make_weights(arch, backbone, m["h8"], m["w8"])
-    net = build_model(arch, backbone, m["h8"], m["w8"], sd)
+    net = build_model(arch, backbone, m["h8"], m["w8"], sd, mode)
     frames = synth_clip(m["n_frames"], m["H"], m["W"], batch=m["batch"], clip_id=0)
     for i, f in enumerate(frames):
         out = net(f.cuda(), pos_id=i % net.path_num)

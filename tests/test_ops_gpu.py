@@ -233,3 +233,145 @@ def test_errors_are_reported_not_swallowed(env):
     assert lib.tdn_conv2d(C.byref(d), None) == -2
     with pytest.raises(RuntimeError, match="multiple of 4"):
         cabi.check(lib.tdn_conv2d(C.byref(d), None), "conv2d")
+
+
+# ------------------------------------------------------------------------------------------------
+# SPLIT16 (hi/lo fp16 planes) views through the same operators
+# ------------------------------------------------------------------------------------------------
+def split_planes(x):
+    hi = x.half()
+    return hi.contiguous(), (x - hi.float()).half().contiguous()
+
+
+def test_split16_roundtrip_precision(env):
+    """copy F32 -> SPLIT16 -> F32 keeps >= 22 significant bits (and is exact for small magnitudes)."""
+    lib, cabi, View, dev = env
+    g = torch.Generator().manual_seed(21)
+    x = (torch.randn(2, 9, 11, 64, generator=g) * 10).cuda()
+    s = View.alloc(2, 9, 11, 64, dev, split=True)
+    y = torch.empty_like(x)
+    tx, ty, ts = View(x.view(-1), 2, 9, 11, 64).ct(), View(y.view(-1), 2, 9, 11, 64).ct(), s.ct()
+    cabi.check(lib.tdn_split16(C.byref(tx), C.byref(ts), None))
+    cabi.check(lib.tdn_merge16(C.byref(ts), C.byref(ty), None))
+    torch.cuda.synchronize()
+    rel = ((y - x).abs() / x.abs().clamp_min(0.25)).max().item()
+    assert rel < 2.0 ** -21, rel
+    hi, lo = split_planes(x)
+    assert torch.equal(s.base.view_as(x), hi) and torch.equal(s.lo.view_as(x), lo)
+
+
+def test_simt_conv_with_split16_views(env):
+    lib, cabi, View, dev = env
+    g = torch.Generator().manual_seed(22)
+    x = torch.randn(1, 64, 15, 22, generator=g)
+    wt = torch.randn(128, 64, 3, 3, generator=g) / 24
+    r = torch.randn(1, 128, 8, 11, generator=g)
+    xs = View.alloc(1, 15, 22, 64, dev, split=True)
+    hi, lo = split_planes(nhwc(x))
+    xs.base.copy_(hi.view(-1)); xs.lo.copy_(lo.view(-1))
+    rs = View.alloc(1, 8, 11, 128, dev, split=True)
+    hi, lo = split_planes(nhwc(r))
+    rs.base.copy_(hi.view(-1)); rs.lo.copy_(lo.view(-1))
+    out = View.alloc(1, 8, 11, 128, dev, split=True)
+    wk = wt.permute(0, 2, 3, 1).contiguous().cuda()
+    d = cabi.Conv2dDesc()
+    d.in_, d.out, d.residual = xs.ct(), out.ct(), rs.ct()
+    d.weight, d.cout, d.kh, d.kw, d.stride, d.pad, d.dilation, d.act, d.batch = wk.data_ptr(), 128, 3, 3, 2, 1, 1, 1, 1
+    cabi.check(lib.tdn_conv2d(C.byref(d), None))
+    torch.cuda.synchronize()
+    xr, rr = xs.torch().permute(0, 3, 1, 2).cpu(), rs.torch().permute(0, 3, 1, 2).cpu()
+    ref = F.relu(F.conv2d(xr, wt, None, 2, 1) + rr)
+    assert max_abs(out.torch().permute(0, 3, 1, 2).cpu(), ref) < 2e-5
+
+
+def test_softmax_rows_split16(env):
+    lib, cabi, View, dev = env
+    g = torch.Generator().manual_seed(23)
+    s = torch.randn(37, 128, generator=g).cuda() * 20
+    p_hi = torch.full((37, 128), 7.0, dtype=torch.half, device=dev)
+    p_lo = torch.full((37, 128), 7.0, dtype=torch.half, device=dev)
+    cabi.check(lib.tdn_softmax_rows_split16(s.data_ptr(), 37, 100, 128, C.c_float(0.125), p_hi.data_ptr(),
+                                            p_lo.data_ptr(), 128, C.c_float(1024.0), None))
+    torch.cuda.synchronize()
+    ref = torch.softmax(s[:, :100].cpu() / 8.0, dim=1)
+    got = (p_hi.float() + p_lo.float()).cpu() / 1024.0
+    assert max_abs(got[:, :100], ref) < 2e-7
+    assert float(got[:, 100:].abs().max()) == 0.0
+
+
+TC_CASES = [
+    # n, h, w, cin, cout, k, dil
+    (1, 1, 256, 64, 128, 1, 1),      # plain GEMM, one K block
+    (1, 1, 1000, 512, 256, 1, 1),    # ragged M, 8 K blocks (ring wraps), two N tiles
+    (1, 1, 384, 128, 64, 1, 1),      # BLOCK_N = 64 variant
+    (2, 24, 40, 64, 128, 3, 2),      # 3x3 dilated, 8x16 pixel tiles, batch 2
+    (1, 97, 193, 128, 96, 3, 8),     # ragged map (reference-native 97x193), cout not a multiple of 32... 96
+    (1, 23, 30, 64, 40, 3, 4),       # cout = 40: partial 32-channel chunk in the epilogue
+]
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,k,dil", TC_CASES)
+def test_tc_conv_exact_mode(env, n, h, w, cin, cout, k, dil):
+    """tcgen05 SPLIT16 conv against an fp64 convolution of the same fp32 inputs: fp32-level error."""
+    lib, cabi, View, dev = env
+    g = torch.Generator().manual_seed(n * h + w + cin + cout)
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5
+    xs = View.alloc(n, h, w, cin, dev, split=True)
+    hi, lo = split_planes(nhwc(x))
+    xs.base.copy_(hi.view(-1)); xs.lo.copy_(lo.view(-1))
+    wh, wl = split_planes(wt.permute(0, 2, 3, 1).reshape(cout, -1).cuda())
+    out = View.alloc(n, h, w, cout, dev)
+    d = cabi.TcConvDesc()
+    d.in_, d.out = xs.ct(), out.ct()
+    d.weight_hi, d.weight_lo, d.weight_ld = wh.data_ptr(), wl.data_ptr(), k * k * cin
+    d.cout, d.kh, d.kw, d.dilation = cout, k, k, dil
+    cabi.check(lib.tdn_conv2d_tc(C.byref(d), None), "conv2d_tc")
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.double(), wt.double(), None, 1, dil * (k - 1) // 2, dil)
+    got = out.torch().permute(0, 3, 1, 2).cpu()
+    err = max_abs(got, ref)
+    assert err < 3e-6 * max(1.0, float(ref.abs().max())), err
+
+
+def test_tc_conv_epilogue_and_batched_weights(env):
+    lib, cabi, View, dev = env
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(1, 64, 16, 32, generator=g)
+    wt = torch.randn(128, 64, 3, 3, generator=g) / 24
+    sc, bi = torch.rand(128, generator=g) + 0.5, torch.randn(128, generator=g)
+    r = torch.randn(1, 128, 16, 32, generator=g)
+    xs, rs = View.alloc(1, 16, 32, 64, dev, split=True), View.alloc(1, 16, 32, 128, dev, split=True)
+    for v, t in ((xs, x), (rs, r)):
+        hi, lo = split_planes(nhwc(t))
+        v.base.copy_(hi.view(-1)); v.lo.copy_(lo.view(-1))
+    wh, wl = split_planes(wt.permute(0, 2, 3, 1).reshape(128, -1).cuda())
+    out = View.alloc(1, 16, 32, 128, dev, split=True)
+    scd, bid = sc.cuda(), bi.cuda()
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    d = cabi.TcConvDesc()
+    d.in_, d.out, d.residual = xs.ct(), out.ct(), rs.ct()
+    d.weight_hi, d.weight_lo, d.weight_ld = wh.data_ptr(), wl.data_ptr(), 576
+    d.scale, d.bias, d.cout, d.kh, d.kw, d.dilation, d.act = scd.data_ptr(), bid.data_ptr(), 128, 3, 3, 1, 1
+    d.range_flag = flag.data_ptr()
+    cabi.check(lib.tdn_conv2d_tc(C.byref(d), None), "conv2d_tc")
+    torch.cuda.synchronize()
+    ref = F.relu(F.conv2d(x.double(), wt.double(), None, 1, 1) * sc.double().view(1, -1, 1, 1)
+                 + bi.double().view(1, -1, 1, 1) + rs.torch().permute(0, 3, 1, 2).cpu().double())
+    assert max_abs(out.torch().permute(0, 3, 1, 2).cpu(), ref) < 5e-6
+    assert int(flag.item()) == 0
+    # q k^T with one key matrix per image (transformer.py:128)
+    q, k = torch.randn(2, 300, 64, generator=g), torch.randn(2, 100, 64, generator=g)
+    qs = View.alloc(2, 1, 300, 64, dev, split=True)
+    hi, lo = split_planes(q.cuda())
+    qs.base.copy_(hi.view(-1)); qs.lo.copy_(lo.view(-1))
+    kh, kl = split_planes(k.cuda())
+    s = View.alloc(2, 1, 300, 128, dev)
+    d = cabi.TcConvDesc()
+    d.in_, d.out = qs.ct(), s.narrow_c(100).ct()
+    d.weight_hi, d.weight_lo, d.weight_ld, d.weight_batched, d.weight_batch_stride = kh.data_ptr(), kl.data_ptr(), 64, 1, 6400
+    d.cout, d.kh, d.kw, d.dilation = 100, 1, 1, 1
+    cabi.check(lib.tdn_conv2d_tc(C.byref(d), None), "conv2d_tc")
+    torch.cuda.synchronize()
+    ref = torch.bmm(q.double(), k.double().transpose(1, 2))
+    assert max_abs(s.torch()[:, 0, :, :100].cpu(), ref) < 5e-6

@@ -101,6 +101,22 @@ def experiment(name):
     import torch
     torch.manual_seed(0)
     dev = "cuda"
+    if name == "layout_debug":
+        # one-hot A rows and index-coded B: out[m, n] must equal B[n, m % 64] = n * 64 + m % 64 exactly;
+        # any swizzle / descriptor / lane-mapping mistake shows up as a permutation in the dump.
+        import numpy as np
+        m_idx = torch.arange(256, device=dev)
+        x = torch.zeros(1, 1, 256, 64, device=dev)
+        x[0, 0, m_idx, m_idx % 64] = 1.0
+        w = (torch.arange(128, device=dev)[:, None] * 64 + torch.arange(64, device=dev)[None, :]).float().view(128, 1, 1, 64)
+        out, _, _ = run_tc(x, w)
+        ref = ref_conv(x, w)
+        np.save(os.path.join(ROOT, "gpurun_out", "tc_layout_debug.npy"), out.cpu().numpy())
+        bad = (out.double() != ref)
+        st = stats(out, ref)
+        st["mismatches"] = int(bad.sum())
+        st["first_rows"] = out[0, 0, :3, :6].tolist()
+        return st
     if name == "gemm_k64":
         x = torch.randn(1, 1, 256, 64, device=dev)
         w = torch.randn(128, 1, 1, 64, device=dev)
@@ -175,7 +191,7 @@ def experiment(name):
     raise KeyError(name)
 
 
-EXPERIMENTS = ["gemm_k64", "gemm_k512_ragged", "gemm_n64", "conv3x3_d2_ragged", "conv3x3_d8_97x193", "epilogue",
+EXPERIMENTS = ["layout_debug", "gemm_k64", "gemm_k512_ragged", "gemm_n64", "conv3x3_d2_ragged", "conv3x3_d8_97x193", "epilogue",
                "batched_qk", "accum_bias_positive", "layer1_perf", "layer4_perf"]
 
 if __name__ == "__main__":
