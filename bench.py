@@ -168,7 +168,9 @@ def run_ours(args, rank, world):
     net = td4_psp18.td4_psp18(nclass=19, path_num=4, backbone=BACKBONE, ln_shape=(h8, w8)).eval()
     net.load_state_dict(_weights(h8, w8), strict=True)
     net.to(dev)
-    host_frames = [f.pin_memory() for f in synth_clip(N_DISTINCT_FRAMES, H, W, batch=BATCH, clip_id=rank)]
+    from tdnet_b200.streams import clips_for_rank, whole_job_throughput
+    clip = clips_for_rank(rank, world, world)[0]   # one independent clip per GPU
+    host_frames = [f.pin_memory() for f in synth_clip(N_DISTINCT_FRAMES, H, W, batch=BATCH, clip_id=clip)]
     dev_frames = [f.to(dev) for f in host_frames]
     stream = torch.cuda.current_stream(dev)
 
@@ -217,15 +219,10 @@ def run_ours(args, rank, world):
     # ---- dominant kernel, timed live with CUDA events around its launch inside running frames
     dom_ms = net.time_dominant_op(dev_frames, step, reps=min(args.steps, 12)) if hasattr(net, "time_dominant_op") else None
 
-    if world > 1:
-        t = torch.tensor([ms_dev, ms_e2e], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_dev, ms_e2e = float(t[0]), float(t[1])
+    total_frames, ms_dev, fps = whole_job_throughput(args.steps, ms_dev, device=dev)
+    _, ms_e2e, fps_e2e = whole_job_throughput(args.steps, ms_e2e, device=dev)
     if rank == 0:
         peaks = _peaks()
-        total_frames = args.steps * world
-        fps = total_frames / (ms_dev / 1e3)
-        fps_e2e = total_frames / (ms_e2e / 1e3)
         roof = None
         if dom_ms:
             achieved = DOMINANT_GFLOP / dom_ms  # GFLOP / ms = TFLOP/s

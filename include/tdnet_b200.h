@@ -140,6 +140,37 @@ typedef struct tdn_tc_conv_desc {
 
 int tdn_conv2d_tc(const tdn_tc_conv_desc* desc, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * tdn_attention_tc: the fused attention-propagation kernel (tcgen05/TMEM/TMA, exact mode).
+ *   out[b, q, :] = softmax_k( Q[b,q,:] . K[b,k,:] / sqrt(d_k) ) @ V'[b,k,:]  + residual[b,q,:]
+ * Replaces ScaledDotProductAttention.forward (transformer.py:126-139: bmm, /temperature, softmax,
+ * bmm) and -- with Attention.fc (transformer.py:84-86) folded into V' by the caller, which is exact
+ * because softmax rows sum to one -- the whole of Attention.forward (transformer.py:71-92) plus the
+ * `v + V_queue[j]` / `v_4_ + v_cur` adds of td4_psp18.py:146-151.  The [pq x pk] attention matrix is
+ * never written to memory.
+ *   q  : SPLIT16 token matrix [n][pq][64]   (row pitch q_ld, batch stride q_batch_stride; elements)
+ *   k  : SPLIT16 token matrix [n][pk][64]
+ *   vt : SPLIT16 V'^T [n][d_v][pk padded to 64] (keys contiguous; pad columns must be zero/finite)
+ *   out / residual : [n,1,pq,d_v] token views, SPLIT16 or F32.  d_k must be 64, d_v % 128 == 0.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct tdn_attention_desc {
+  const void* q_hi;
+  const void* q_lo;
+  int64_t q_ld, q_batch_stride;
+  const void* k_hi;
+  const void* k_lo;
+  int64_t k_ld, k_batch_stride;
+  const void* vt_hi;
+  const void* vt_lo;
+  int64_t vt_ld, vt_batch_stride;
+  tdn_tensor out;
+  tdn_tensor residual; /* residual.data == NULL -> none */
+  int32_t n, pq, pk, d_k, d_v;
+  int32_t* range_flag;
+} tdn_attention_desc;
+
+int tdn_attention_tc(const tdn_attention_desc* desc, void* stream);
+
 /* fp32 plane <-> SPLIT16 planes (hi = fp16(x), lo = fp16(x - hi)); views must have equal dims. */
 int tdn_split16(const tdn_tensor* in_f32, const tdn_tensor* out_split16, void* stream);
 int tdn_merge16(const tdn_tensor* in_split16, const tdn_tensor* out_f32, void* stream);

@@ -42,6 +42,15 @@ class TcConvDesc(C.Structure):
                 ("act", C.c_int32), ("leaky_slope", C.c_float), ("range_flag", C.c_void_p)]
 
 
+class AttentionDesc(C.Structure):
+    _fields_ = [("q_hi", C.c_void_p), ("q_lo", C.c_void_p), ("q_ld", C.c_int64), ("q_batch_stride", C.c_int64),
+                ("k_hi", C.c_void_p), ("k_lo", C.c_void_p), ("k_ld", C.c_int64), ("k_batch_stride", C.c_int64),
+                ("vt_hi", C.c_void_p), ("vt_lo", C.c_void_p), ("vt_ld", C.c_int64), ("vt_batch_stride", C.c_int64),
+                ("out", Tensor), ("residual", Tensor),
+                ("n", C.c_int32), ("pq", C.c_int32), ("pk", C.c_int32), ("d_k", C.c_int32), ("d_v", C.c_int32),
+                ("range_flag", C.c_void_p)]
+
+
 # symbol -> (restype, argtypes); tests/test_cabi.py checks this list against include/tdnet_b200.h
 _TP = C.POINTER(Tensor)
 SIGNATURES = {
@@ -51,6 +60,7 @@ SIGNATURES = {
     "tdn_device_arch": (C.c_int, []),
     "tdn_conv2d": (C.c_int, [C.POINTER(Conv2dDesc), C.c_void_p]),
     "tdn_conv2d_tc": (C.c_int, [C.POINTER(TcConvDesc), C.c_void_p]),
+    "tdn_attention_tc": (C.c_int, [C.POINTER(AttentionDesc), C.c_void_p]),
     "tdn_split16": (C.c_int, [_TP, _TP, C.c_void_p]),
     "tdn_merge16": (C.c_int, [_TP, _TP, C.c_void_p]),
     "tdn_image_to_nhwc": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _TP, C.c_void_p]),

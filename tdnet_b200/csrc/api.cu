@@ -45,6 +45,7 @@ int layernorm_hw_apply(const tdn_tensor*, const float*, const float*, const floa
                        const tdn_tensor*, cudaStream_t);
 int upsample_logits(const tdn_tensor*, float*, int, int, cudaStream_t);
 int conv2d_tc(const tdn_tc_conv_desc*, cudaStream_t);
+int attention_tc(const tdn_attention_desc*, cudaStream_t);
 int split16(const tdn_tensor*, const tdn_tensor*, cudaStream_t);
 int merge16(const tdn_tensor*, const tdn_tensor*, cudaStream_t);
 
@@ -96,6 +97,15 @@ int tdn_conv2d_tc(const tdn_tc_conv_desc* d, void* stream) {
   TDN_REQUIRE(arch / 10 == 10, TDN_ERR_ARCH, "conv2d_tc: tcgen05 kernels need sm_100, device is sm_%d", arch);
   TDN_REQUIRE(d->cout > 0 && d->kh > 0 && d->kw > 0 && d->dilation > 0, TDN_ERR_INVALID, "conv2d_tc: bad geometry");
   return conv2d_tc(d, (cudaStream_t)stream);
+}
+
+int tdn_attention_tc(const tdn_attention_desc* d, void* stream) {
+  TDN_REQUIRE(d != nullptr, TDN_ERR_INVALID, "attention_tc: null descriptor");
+  static thread_local int arch = 0;
+  if (arch == 0) arch = tdn_device_arch();
+  if (arch < 0) return arch;
+  TDN_REQUIRE(arch / 10 == 10, TDN_ERR_ARCH, "attention_tc: tcgen05 kernels need sm_100, device is sm_%d", arch);
+  return attention_tc(d, (cudaStream_t)stream);
 }
 
 int tdn_split16(const tdn_tensor* in, const tdn_tensor* out, void* stream) {

@@ -1,0 +1,473 @@
+// Fused attention-propagation kernel for sm_100a (tcgen05 + TMEM + TMA), fp32-faithful exact mode.
+//
+//   out[q, :] = softmax_k( Q[q,:] . K[k,:] / sqrt(d_k) ) @ V'[k, :]  (+ residual[q, :])
+//
+// replaces transformer.py:126-139 (ScaledDotProductAttention: bmm -> /temperature -> softmax -> bmm)
+// and, with the fc folded into V' by the host (softmax rows sum to 1), Attention.forward :71-92.
+// The [Pq x P'] attention matrix never exists in memory.
+//
+// Work item = (image, 128-query tile, 128-channel slice of d_v); persistent CTAs loop over items.
+// Per item, two passes over the P' keys in tiles of 64:
+//   pass 1  S~ = Qhi.Khi^T (one fp16 MMA per K step) -> running row maximum m.  The maximum is only a
+//           stabiliser, so the cheap single-product S~ is enough (it is within ~1e-3*|S| of S).
+//   pass 2  S  = Q.K^T in exact mode (hi*lo + lo*hi + hi*hi, fp32 TMEM accumulator);
+//           p  = exp(S/sqrt(d_k) - m) (fp32, per query row in registers, row sum l accumulated);
+//           P  = p * 2^10 split to fp16 hi/lo, written to shared memory in the UMMA K-major 128B-swizzled
+//                layout; O += P.V'^T in exact mode (fp32 TMEM accumulator, 128 columns).
+//   epilogue out = O / (l * 2^10) + residual, re-split to hi/lo (and/or fp32).
+// Because m is fixed before pass 2 there is no running rescale of O: the MMA warp never waits on a
+// correction step and the result does not depend on tile order.
+//
+// Warp roles (192 threads): warp 0 TMA producer (Q tile, K ring, V ring), warp 1 MMA issuer,
+// warps 2-5 softmax + epilogue (one query row per thread; TMEM lane quarter = warp % 4).
+// TMEM: S double-buffered 2 x 64 columns, O 128 columns.  Shared memory: Q 32 KB, K ring 2 x 16 KB,
+// V ring 2 x 32 KB, P double buffer 2 x 32 KB (hi+lo planes each).
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+#include <string.h>
+#include <cuda.h>
+
+namespace tdn {
+
+using namespace ptx;
+
+constexpr int AT_BQ = 128;       // queries per item
+constexpr int AT_BK = 64;        // keys per tile (= one 128-byte swizzle row of fp16)
+constexpr int AT_DK = 64;        // d_k (fixed by the model: Encoding(d_model, 64, d_v))
+constexpr int AT_DV = 128;       // d_v slice per item
+constexpr int AT_THREADS = 192;
+constexpr int AT_Q_PLANE = AT_BQ * AT_DK * 2;   // 16 KB
+constexpr int AT_K_PLANE = AT_BK * AT_DK * 2;   // 8 KB
+constexpr int AT_V_PLANE = AT_DV * AT_BK * 2;   // 16 KB
+constexpr int AT_P_PLANE = AT_BQ * AT_BK * 2;   // 16 KB
+constexpr int AT_KSTAGES = 2, AT_VSTAGES = 2;
+constexpr int AT_SMEM_DATA = 2 * AT_Q_PLANE + AT_KSTAGES * 2 * AT_K_PLANE + AT_VSTAGES * 2 * AT_V_PLANE + 2 * 2 * AT_P_PLANE;
+constexpr int AT_SMEM_BYTES = AT_SMEM_DATA + 1024 + 512;
+constexpr int AT_TMEM_COLS = 256;   // S: 2 x 64, O: 128
+constexpr float AT_P_SCALE = 1024.f;
+
+struct AttnParams {
+  int n_img, Pq, Pk;
+  int q_tiles, dv_tiles, k_tiles, num_items;
+  float scale_log2;         // log2(e) / sqrt(d_k)
+  __half* out_hi;
+  __half* out_lo;
+  float* out_f32;
+  long long o_bs, o_ld;     // batch stride / row pitch (elements)
+  const __half* res_hi;
+  const __half* res_lo;
+  const float* res_f32;
+  long long r_bs, r_ld;
+  int* range_flag;
+};
+
+struct AttnBars {
+  uint64_t q_full, q_empty;
+  uint64_t k_full[AT_KSTAGES], k_empty[AT_KSTAGES];
+  uint64_t v_full[AT_VSTAGES], v_empty[AT_VSTAGES];
+  uint64_t s_full[2], s_empty[2];
+  uint64_t p_full[2], p_empty[2];
+  uint64_t o_full, o_empty;
+  uint32_t tmem_ptr;
+};
+
+__global__ void __launch_bounds__(AT_THREADS, 1)
+tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ CUtensorMap tmQ_lo,
+               const __grid_constant__ CUtensorMap tmK_hi, const __grid_constant__ CUtensorMap tmK_lo,
+               const __grid_constant__ CUtensorMap tmV_hi, const __grid_constant__ CUtensorMap tmV_lo,
+               const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem;                                            // hi | lo
+  uint8_t* sK = sQ + 2 * AT_Q_PLANE;                             // stages x (hi | lo)
+  uint8_t* sV = sK + AT_KSTAGES * 2 * AT_K_PLANE;
+  uint8_t* sP = sV + AT_VSTAGES * 2 * AT_V_PLANE;                // 2 buffers x (hi | lo)
+  AttnBars* bars = reinterpret_cast<AttnBars*>(sP + 2 * 2 * AT_P_PLANE);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmQ_hi); prefetch_tensormap(&tmQ_lo);
+    prefetch_tensormap(&tmK_hi); prefetch_tensormap(&tmK_lo);
+    prefetch_tensormap(&tmV_hi); prefetch_tensormap(&tmV_lo);
+    mbar_init(&bars->q_full, 1);
+    mbar_init(&bars->q_empty, 1);
+    for (int s = 0; s < AT_KSTAGES; ++s) { mbar_init(&bars->k_full[s], 1); mbar_init(&bars->k_empty[s], 1); }
+    for (int s = 0; s < AT_VSTAGES; ++s) { mbar_init(&bars->v_full[s], 1); mbar_init(&bars->v_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bars->s_full[s], 1);
+      mbar_init(&bars->s_empty[s], 128);
+      mbar_init(&bars->p_full[s], 128);
+      mbar_init(&bars->p_empty[s], 1);
+    }
+    mbar_init(&bars->o_full, 1);
+    mbar_init(&bars->o_empty, 128);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&bars->tmem_ptr, AT_TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_ptr;
+  const uint32_t tmem_S = tmem_base;            // + buf * 64
+  const uint32_t tmem_O = tmem_base + 128;
+  const int T = p.k_tiles;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int ks = 0, vs = 0;
+      uint32_t kph = 0, vph = 0, qph = 0;
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        const int dvt = item % p.dv_tiles;
+        int t = item / p.dv_tiles;
+        const int qt = t % p.q_tiles;
+        const int img = t / p.q_tiles;
+        mbar_wait(&bars->q_empty, qph ^ 1);
+        mbar_expect_tx(&bars->q_full, 2 * AT_Q_PLANE);
+        tma_load_3d(sQ, &tmQ_hi, &bars->q_full, 0, qt * AT_BQ, img);
+        tma_load_3d(sQ + AT_Q_PLANE, &tmQ_lo, &bars->q_full, 0, qt * AT_BQ, img);
+        qph ^= 1;
+        // pass 1: the hi plane of the keys only (S~ = Qhi.Khi^T)
+        for (int kt = 0; kt < T; ++kt) {
+          mbar_wait(&bars->k_empty[ks], kph ^ 1);
+          uint8_t* dst = sK + ks * 2 * AT_K_PLANE;
+          mbar_expect_tx(&bars->k_full[ks], AT_K_PLANE);
+          tma_load_3d(dst, &tmK_hi, &bars->k_full[ks], 0, kt * AT_BK, img);
+          if (++ks == AT_KSTAGES) { ks = 0; kph ^= 1; }
+        }
+        // pass 2: keys (hi+lo) and the V'^T slice (hi+lo)
+        for (int kt = 0; kt < T; ++kt) {
+          mbar_wait(&bars->k_empty[ks], kph ^ 1);
+          uint8_t* dk = sK + ks * 2 * AT_K_PLANE;
+          mbar_expect_tx(&bars->k_full[ks], 2 * AT_K_PLANE);
+          tma_load_3d(dk, &tmK_hi, &bars->k_full[ks], 0, kt * AT_BK, img);
+          tma_load_3d(dk + AT_K_PLANE, &tmK_lo, &bars->k_full[ks], 0, kt * AT_BK, img);
+          if (++ks == AT_KSTAGES) { ks = 0; kph ^= 1; }
+          mbar_wait(&bars->v_empty[vs], vph ^ 1);
+          uint8_t* dv = sV + vs * 2 * AT_V_PLANE;
+          mbar_expect_tx(&bars->v_full[vs], 2 * AT_V_PLANE);
+          tma_load_3d(dv, &tmV_hi, &bars->v_full[vs], kt * AT_BK, dvt * AT_DV, img);
+          tma_load_3d(dv + AT_V_PLANE, &tmV_lo, &bars->v_full[vs], kt * AT_BK, dvt * AT_DV, img);
+          if (++vs == AT_VSTAGES) { vs = 0; vph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_f16(AT_BQ, AT_BK);   // 128 x 64
+      constexpr uint32_t idesc_o = umma_idesc_f16(AT_BQ, AT_DV);   // 128 x 128
+      int ks = 0, vs = 0, sb = 0, pb = 0;
+      uint32_t kph = 0, vph = 0, sph = 0, pph = 0, qph = 0, oph = 0;
+      const uint32_t q_hi = smem_u32(sQ), q_lo = q_hi + AT_Q_PLANE;
+
+      auto issue_s = [&](bool exact) {
+        mbar_wait(&bars->k_full[ks], kph);
+        mbar_wait(&bars->s_empty[sb], sph ^ 1);
+        tc_fence_after();
+        const uint32_t k_hi = smem_u32(sK + ks * 2 * AT_K_PLANE), k_lo = k_hi + AT_K_PLANE;
+        const uint32_t d = tmem_S + sb * AT_BK;
+#pragma unroll
+        for (int k = 0; k < AT_DK / 16; ++k) {
+          const uint64_t a_h = umma_desc_k_sw128(q_hi + k * 32), b_h = umma_desc_k_sw128(k_hi + k * 32);
+          if (exact) {
+            const uint64_t a_l = umma_desc_k_sw128(q_lo + k * 32), b_l = umma_desc_k_sw128(k_lo + k * 32);
+            umma_f16(d, a_h, b_l, idesc_s, k != 0);
+            umma_f16(d, a_l, b_h, idesc_s, 1);
+            umma_f16(d, a_h, b_h, idesc_s, 1);
+          } else {
+            umma_f16(d, a_h, b_h, idesc_s, k != 0);
+          }
+        }
+        umma_commit(&bars->s_full[sb]);
+        umma_commit(&bars->k_empty[ks]);
+        if (++ks == AT_KSTAGES) { ks = 0; kph ^= 1; }
+        if (++sb == 2) { sb = 0; sph ^= 1; }
+      };
+
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        mbar_wait(&bars->q_full, qph);
+        tc_fence_after();
+        for (int kt = 0; kt < T; ++kt) issue_s(false);       // pass 1
+        issue_s(true);                                        // S(0) of pass 2
+        for (int kt = 0; kt < T; ++kt) {
+          if (kt + 1 < T) issue_s(true);                      // S(kt+1) overlaps softmax(kt)
+          mbar_wait(&bars->v_full[vs], vph);
+          mbar_wait(&bars->p_full[pb], pph);
+          if (kt == 0) mbar_wait(&bars->o_empty, oph ^ 1);
+          tc_fence_after();
+          const uint32_t p_hi = smem_u32(sP + pb * 2 * AT_P_PLANE), p_lo = p_hi + AT_P_PLANE;
+          const uint32_t v_hi = smem_u32(sV + vs * 2 * AT_V_PLANE), v_lo = v_hi + AT_V_PLANE;
+#pragma unroll
+          for (int k = 0; k < AT_BK / 16; ++k) {
+            const uint64_t a_h = umma_desc_k_sw128(p_hi + k * 32), a_l = umma_desc_k_sw128(p_lo + k * 32);
+            const uint64_t b_h = umma_desc_k_sw128(v_hi + k * 32), b_l = umma_desc_k_sw128(v_lo + k * 32);
+            umma_f16(tmem_O, a_h, b_l, idesc_o, (kt | k) != 0);
+            umma_f16(tmem_O, a_l, b_h, idesc_o, 1);
+            umma_f16(tmem_O, a_h, b_h, idesc_o, 1);
+          }
+          umma_commit(&bars->p_empty[pb]);
+          umma_commit(&bars->v_empty[vs]);
+          if (++vs == AT_VSTAGES) { vs = 0; vph ^= 1; }
+          if (++pb == 2) { pb = 0; pph ^= 1; }
+        }
+        umma_commit(&bars->o_full);
+        umma_commit(&bars->q_empty);
+        qph ^= 1;
+        oph ^= 1;
+      }
+    }
+  } else {
+    // ================================ softmax + epilogue warps ================================
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;                      // query row inside the tile = TMEM lane
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    int sb = 0, pb = 0;
+    uint32_t sph = 0, pph = 0, oph = 0;
+    bool out_of_range = false;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      const int dvt = item % p.dv_tiles;
+      int t = item / p.dv_tiles;
+      const int qt = t % p.q_tiles;
+      const int img = t / p.q_tiles;
+      const int q_idx = qt * AT_BQ + row;
+      const bool valid = q_idx < p.Pq;
+
+      // ---- pass 1: row maximum of S~ * scale (in log2 units)
+      float m = -INFINITY;
+      for (int kt = 0; kt < T; ++kt) {
+        mbar_wait(&bars->s_full[sb], sph);
+        tc_fence_after();
+        uint32_t r[32];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          tmem_ld_32x32(tmem_S + lane_addr + sb * AT_BK + half * 32, r);
+          tmem_ld_wait();
+          const int kbase = kt * AT_BK + half * 32;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (kbase + j < p.Pk) m = fmaxf(m, __uint_as_float(r[j]));
+        }
+        tc_fence_before();
+        mbar_arrive(&bars->s_empty[sb]);
+        if (++sb == 2) { sb = 0; sph ^= 1; }
+      }
+      const float m_scaled = m * p.scale_log2;
+
+      // ---- pass 2: probabilities -> shared memory (UMMA K-major, 128B swizzle), row sum
+      float l = 0.f;
+      for (int kt = 0; kt < T; ++kt) {
+        mbar_wait(&bars->s_full[sb], sph);
+        tc_fence_after();
+        float pr[AT_BK];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_S + lane_addr + sb * AT_BK + half * 32, r);
+          tmem_ld_wait();
+          const int kbase = kt * AT_BK + half * 32;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float e = exp2f(fmaf(__uint_as_float(r[j]), p.scale_log2, -m_scaled));
+            e = (kbase + j < p.Pk) ? e : 0.f;
+            l += e;
+            pr[half * 32 + j] = e * AT_P_SCALE;
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&bars->s_empty[sb]);
+        if (++sb == 2) { sb = 0; sph ^= 1; }
+
+        mbar_wait(&bars->p_empty[pb], pph ^ 1);
+        uint8_t* ph = sP + pb * 2 * AT_P_PLANE + row * 128;
+        uint8_t* pl = ph + AT_P_PLANE;
+#pragma unroll
+        for (int c16 = 0; c16 < 8; ++c16) {
+          __half hi[8], lo[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) split_f32(pr[c16 * 8 + e], hi[e], lo[e]);
+          const int phys = (c16 ^ (row & 7)) << 4;
+          *reinterpret_cast<uint4*>(ph + phys) = *reinterpret_cast<const uint4*>(hi);
+          *reinterpret_cast<uint4*>(pl + phys) = *reinterpret_cast<const uint4*>(lo);
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&bars->p_full[pb]);
+        if (++pb == 2) { pb = 0; pph ^= 1; }
+      }
+
+      // ---- epilogue: out = O / (l * 2^10) + residual
+      mbar_wait(&bars->o_full, oph);
+      tc_fence_after();
+      oph ^= 1;
+      const float inv = 1.f / (l * AT_P_SCALE);
+      const long long obase = (long long)img * p.o_bs + (long long)q_idx * p.o_ld + dvt * AT_DV;
+      const long long rbase = (long long)img * p.r_bs + (long long)q_idx * p.r_ld + dvt * AT_DV;
+#pragma unroll 1
+      for (int chunk = 0; chunk < AT_DV / 32; ++chunk) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_O + lane_addr + chunk * 32, r);
+        tmem_ld_wait();
+        if (valid) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * inv;
+          const int c0 = chunk * 32;
+          if (p.res_hi) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 h4 = *reinterpret_cast<const uint4*>(p.res_hi + rbase + c0 + q * 8);
+              uint4 l4 = *reinterpret_cast<const uint4*>(p.res_lo + rbase + c0 + q * 8);
+              const __half2* hh = reinterpret_cast<const __half2*>(&h4);
+              const __half2* ll = reinterpret_cast<const __half2*>(&l4);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float2 a = __half22float2(hh[e]), b2 = __half22float2(ll[e]);
+                v[q * 8 + e * 2 + 0] += a.x + b2.x;
+                v[q * 8 + e * 2 + 1] += a.y + b2.y;
+              }
+            }
+          } else if (p.res_f32) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              float4 f = *reinterpret_cast<const float4*>(p.res_f32 + rbase + c0 + q * 4);
+              v[q * 4 + 0] += f.x; v[q * 4 + 1] += f.y; v[q * 4 + 2] += f.z; v[q * 4 + 3] += f.w;
+            }
+          }
+          if (p.out_f32) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              *reinterpret_cast<float4*>(p.out_f32 + obase + c0 + q * 4) =
+                  make_float4(v[q * 4 + 0], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+          }
+          if (p.out_hi) {
+            __half hi[32], lo[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              out_of_range |= fabsf(v[j]) > 60000.f;
+              split_f32(v[j], hi[j], lo[j]);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              *reinterpret_cast<uint4*>(p.out_hi + obase + c0 + q * 8) = *reinterpret_cast<const uint4*>(&hi[q * 8]);
+              *reinterpret_cast<uint4*>(p.out_lo + obase + c0 + q * 8) = *reinterpret_cast<const uint4*>(&lo[q * 8]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&bars->o_empty);
+    }
+    if (out_of_range && p.range_flag) atomicOr(p.range_flag, 1);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, AT_TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+int encode_map_f16(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims,
+                   const cuuint64_t* strides_bytes, const cuuint32_t* box, const char* what);
+
+int attention_tc(const tdn_attention_desc* d, cudaStream_t stream) {
+  TDN_REQUIRE(d->q_hi && d->q_lo && d->k_hi && d->k_lo && d->vt_hi && d->vt_lo, TDN_ERR_INVALID,
+              "attention_tc: null operand");
+  TDN_REQUIRE(d->d_k == AT_DK, TDN_ERR_UNSUPPORTED, "attention_tc: d_k must be 64 (got %d)", d->d_k);
+  TDN_REQUIRE(d->d_v % AT_DV == 0, TDN_ERR_UNSUPPORTED, "attention_tc: d_v=%d must be a multiple of 128", d->d_v);
+  TDN_REQUIRE(d->n > 0 && d->pq > 0 && d->pk > 0, TDN_ERR_INVALID, "attention_tc: empty problem");
+  TDN_REQUIRE(d->vt_ld % 8 == 0 && d->vt_ld >= ((d->pk + 63) / 64) * 64, TDN_ERR_INVALID,
+              "attention_tc: V'^T row pitch must cover the keys padded to 64 (zero-filled) and be 16-byte aligned");
+  TDN_REQUIRE(d->q_ld % 8 == 0 && d->k_ld % 8 == 0 && d->q_batch_stride % 8 == 0 && d->k_batch_stride % 8 == 0 &&
+                  d->vt_batch_stride % 8 == 0, TDN_ERR_INVALID, "attention_tc: operand pitches must be 16-byte aligned");
+  const tdn_tensor& out = d->out;
+  TDN_REQUIRE(out.data && out.n == d->n && out.h == 1 && out.w == d->pq && out.c == d->d_v, TDN_ERR_INVALID,
+              "attention_tc: out must be a [n,1,pq,d_v] token view");
+  AttnParams p;
+  memset(&p, 0, sizeof(p));
+  p.n_img = d->n; p.Pq = d->pq; p.Pk = d->pk;
+  p.q_tiles = ceil_div(d->pq, AT_BQ);
+  p.dv_tiles = d->d_v / AT_DV;
+  p.k_tiles = ceil_div(d->pk, AT_BK);
+  long long items = (long long)d->n * p.q_tiles * p.dv_tiles;
+  TDN_REQUIRE(items < (1ll << 31), TDN_ERR_UNSUPPORTED, "attention_tc: too many work items");
+  p.num_items = (int)items;
+  p.scale_log2 = 1.4426950408889634f / sqrtf((float)d->d_k);
+  if (out.dtype == TDN_SPLIT16) {
+    TDN_REQUIRE(out.data_lo && aligned16(out.data) && aligned16(out.data_lo) && out.stride_w % 8 == 0 &&
+                    out.stride_n % 8 == 0, TDN_ERR_INVALID, "attention_tc: misaligned SPLIT16 output");
+    p.out_hi = (__half*)out.data; p.out_lo = (__half*)out.data_lo;
+  } else {
+    TDN_REQUIRE(aligned16(out.data) && out.stride_w % 4 == 0 && out.stride_n % 4 == 0, TDN_ERR_INVALID,
+                "attention_tc: misaligned fp32 output");
+    p.out_f32 = (float*)out.data;
+  }
+  p.o_bs = out.stride_n; p.o_ld = out.stride_w;
+  if (d->residual.data) {
+    const tdn_tensor& r = d->residual;
+    TDN_REQUIRE(r.n == out.n && r.h == 1 && r.w == out.w && r.c == out.c, TDN_ERR_INVALID,
+                "attention_tc: residual dims must equal output dims");
+    if (r.dtype == TDN_SPLIT16) {
+      TDN_REQUIRE(r.data_lo && aligned16(r.data) && aligned16(r.data_lo) && r.stride_w % 8 == 0 && r.stride_n % 8 == 0,
+                  TDN_ERR_INVALID, "attention_tc: misaligned residual");
+      p.res_hi = (const __half*)r.data; p.res_lo = (const __half*)r.data_lo;
+    } else {
+      TDN_REQUIRE(aligned16(r.data) && r.stride_w % 4 == 0 && r.stride_n % 4 == 0, TDN_ERR_INVALID,
+                  "attention_tc: misaligned residual");
+      p.res_f32 = (const float*)r.data;
+    }
+    p.r_bs = r.stride_n; p.r_ld = r.stride_w;
+  }
+  p.range_flag = d->range_flag;
+
+  CUtensorMap mq_h, mq_l, mk_h, mk_l, mv_h, mv_l;
+  int rc;
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)AT_DK, (cuuint64_t)d->pq, (cuuint64_t)d->n};
+    cuuint64_t str[2] = {(cuuint64_t)d->q_ld * 2, (cuuint64_t)(d->n > 1 ? d->q_batch_stride : d->q_ld * (long long)d->pq) * 2};
+    cuuint32_t box[3] = {(cuuint32_t)AT_DK, (cuuint32_t)AT_BQ, 1};
+    if ((rc = encode_map_f16(&mq_h, d->q_hi, 3, dims, str, box, "Q.hi"))) return rc;
+    if ((rc = encode_map_f16(&mq_l, d->q_lo, 3, dims, str, box, "Q.lo"))) return rc;
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)AT_DK, (cuuint64_t)d->pk, (cuuint64_t)d->n};
+    cuuint64_t str[2] = {(cuuint64_t)d->k_ld * 2, (cuuint64_t)(d->n > 1 ? d->k_batch_stride : d->k_ld * (long long)d->pk) * 2};
+    cuuint32_t box[3] = {(cuuint32_t)AT_DK, (cuuint32_t)AT_BK, 1};
+    if ((rc = encode_map_f16(&mk_h, d->k_hi, 3, dims, str, box, "K.hi"))) return rc;
+    if ((rc = encode_map_f16(&mk_l, d->k_lo, 3, dims, str, box, "K.lo"))) return rc;
+  }
+  {
+    // V'^T: [d_v rows][keys], keys contiguous; the key extent is the padded pitch so that the pad
+    // columns (zeros written by the producer) are read rather than treated as out of bounds.
+    cuuint64_t dims[3] = {(cuuint64_t)(((d->pk + 63) / 64) * 64), (cuuint64_t)d->d_v, (cuuint64_t)d->n};
+    cuuint64_t str[2] = {(cuuint64_t)d->vt_ld * 2, (cuuint64_t)(d->n > 1 ? d->vt_batch_stride : d->vt_ld * (long long)d->d_v) * 2};
+    cuuint32_t box[3] = {(cuuint32_t)AT_BK, (cuuint32_t)AT_DV, 1};
+    if ((rc = encode_map_f16(&mv_h, d->vt_hi, 3, dims, str, box, "Vt.hi"))) return rc;
+    if ((rc = encode_map_f16(&mv_l, d->vt_lo, 3, dims, str, box, "Vt.lo"))) return rc;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    TDN_CUDA_OK(cudaFuncSetAttribute(tc_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES));
+    attr_set = true;
+  }
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    TDN_CUDA_OK(cudaGetDevice(&dev));
+    TDN_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  int grid = p.num_items < num_sms ? p.num_items : num_sms;
+  tc_attn_kernel<<<grid, AT_THREADS, AT_SMEM_BYTES, stream>>>(mq_h, mq_l, mk_h, mk_l, mv_h, mv_l, p);
+  TDN_LAUNCH_OK();
+  return TDN_OK;
+}
+
+}  // namespace tdn

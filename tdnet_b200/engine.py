@@ -193,6 +193,8 @@ class Engine:
         assert mode in ("tc", "simt")
         self.lib = _cabi.load()
         self.tc = mode == "tc"
+        import os
+        self.fused_attn = os.environ.get("TDNET_B200_FUSED_ATTN", "1") != "0"
         self.m, self.n, self.H, self.W, self.device = arch, n, H, W, device
         self.h8, self.w8 = A.feature_hw(H, W)
         if tuple(ln_shape) != (self.h8, self.w8):
@@ -260,7 +262,7 @@ class Engine:
         (3-channel stem, stride-2 convs, pooled PSP convs, the 19-class classifier)."""
         spec = pc.spec if pc is not None else None
         if (self.tc and spec is not None and not kw and spec.stride == 1 and x.split and x.c % 64 == 0
-                and x.n * x.h * x.w >= 64):
+                and x.n * x.h * x.w >= 64 and out.sw % (8 if out.split else 4) == 0 and pc.cout % 8 == 0):
             return self._conv_tc(plan, x, out, pc=pc, residual=residual)
         return self._conv_simt(plan, pc, x, out, residual, **kw)
 
@@ -521,16 +523,30 @@ class Engine:
                 out_tok, res_tok = out, self.v_slots[j + 1]
             q_all = (q_cur._like(n, 1, pq_full, m.d_k, q_cur.sn, q_cur.sn, m.d_k, q_cur.offset) if last
                      else self.q_slots[j + 1])
-            s_buf = self.buf(n, 1, pq, pkp, split=False)
-            p_buf = self.buf(n, 1, pq, pkp)
             for i in range(n):
                 # V'^T_i = W_fc @ v_src_i^T + b  -> rows d_v, cols P'
                 self._conv_tc(plan, wfc["view"], vpt.image(i).narrow_c(pk), w_hi=v_src.image(i).ptr,
                               w_lo=v_src.image(i).ptr_lo, w_ld=v_src.sw, cout=pk,
                               scale=self.const_vec(wfc["inv_scale"], pkp), bias=fc.bias,
                               bias_along_m=True, name=name + ".fc")
-            # S = q k^T (all images in one launch: weights batched per image)
             k_slot = self.k_slots[j]
+            if self.fused_attn:
+                # one kernel: QK^T -> softmax -> PV (+ residual); the attention matrix stays on chip
+                d = _cabi.AttentionDesc()
+                d.q_hi, d.q_lo, d.q_ld, d.q_batch_stride = q_all.ptr, q_all.ptr_lo, q_all.sw, q_all.sn
+                d.k_hi, d.k_lo, d.k_ld, d.k_batch_stride = k_slot.ptr, k_slot.ptr_lo, k_slot.sw, k_slot.sn
+                d.vt_hi, d.vt_lo, d.vt_ld, d.vt_batch_stride = vpt.ptr, vpt.ptr_lo, pkp, vpt.sn
+                d.out, d.residual = out_tok.ct(), res_tok.ct()
+                d.n, d.pq, d.pk, d.d_k, d.d_v = n, pq, pk, m.d_k, m.d_v
+                d.range_flag = self.range_flag.data_ptr()
+                plan.add(lib.tdn_attention_tc, C.byref(d), "stream", name=name + ".attention")
+                plan.keep.append((d, q_all, k_slot, vpt, out_tok, res_tok))
+                carry = out
+                continue
+            # unfused tensor-core chain (kept as the cross-check of the fused kernel)
+            s_buf = self.buf(n, 1, pq, pkp, split=False)
+            p_buf = self.buf(n, 1, pq, pkp)
+            # S = q k^T (all images in one launch: weights batched per image)
             self._conv_tc(plan, q_all, s_buf.narrow_c(pk), w_hi=k_slot.ptr, w_lo=k_slot.ptr_lo, w_ld=k_slot.sw,
                           w_bs=k_slot.sn, batched=True, cout=pk, name=name + ".qk")
             plan.add(lib.tdn_softmax_rows_split16, s_buf.ptr, n * pq, pk, pkp, C.c_float(1.0 / float(m.d_k) ** 0.5),

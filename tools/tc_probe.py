@@ -188,11 +188,69 @@ def experiment(name):
         f32 = torch.matmul(x.view(2048, 4608), w.view(128, 4608).t()).view(1, 1, 2048, 128)
         return dict(tc_vs_split_inputs=stats(out, ref_split), tc_vs_true=stats(out, ref_true),
                     cublas_fp32_vs_true=stats(f32, ref_true))
+    if name.startswith("attention"):
+        return attention_experiment(name)
     raise KeyError(name)
 
 
-EXPERIMENTS = ["layout_debug", "gemm_k64", "gemm_k512_ragged", "gemm_n64", "conv3x3_d2_ragged", "conv3x3_d8_97x193", "epilogue",
-               "batched_qk", "accum_bias_positive", "layer1_perf", "layer4_perf"]
+def attention_experiment(name):
+    """Fused attention kernel vs an fp64 softmax(QK^T/8)V + R reference."""
+    import torch
+    from tdnet_b200 import _cabi as cabi
+    lib = cabi.load()
+    dev = "cuda"
+    torch.manual_seed(1)
+    n, pq, pk, dv, reps = {"attention_small": (2, 300, 100, 128, 0), "attention_ragged": (1, 18721, 1225, 512, 3),
+                           "attention_big": (1, 32768, 2048, 512, 10)}[name]
+    pkp = (pk + 63) // 64 * 64
+    q = torch.randn(n, pq, 64, device=dev) * 1.3
+    k = torch.randn(n, pk, 64, device=dev) * 1.4
+    v = torch.randn(n, pk, dv, device=dev) * 3
+    r = torch.randn(n, pq, dv, device=dev)
+    qh, ql = split(q)
+    kh, kl = split(k)
+    vt = torch.zeros(n, dv, pkp, device=dev)
+    vt[:, :, :pk] = v.transpose(1, 2)
+    vh, vl = split(vt)
+    rh, rl = split(r)
+    out = torch.empty(n, pq, dv, device=dev)
+    d = cabi.AttentionDesc()
+    d.q_hi, d.q_lo, d.q_ld, d.q_batch_stride = qh.data_ptr(), ql.data_ptr(), 64, pq * 64
+    d.k_hi, d.k_lo, d.k_ld, d.k_batch_stride = kh.data_ptr(), kl.data_ptr(), 64, pk * 64
+    d.vt_hi, d.vt_lo, d.vt_ld, d.vt_batch_stride = vh.data_ptr(), vl.data_ptr(), pkp, dv * pkp
+    d.out = cabi.Tensor(out.data_ptr(), None, 0, n, 1, pq, dv, pq * dv, pq * dv, dv)
+    d.residual = cabi.Tensor(rh.data_ptr(), rl.data_ptr(), 1, n, 1, pq, dv, pq * dv, pq * dv, dv)
+    d.n, d.pq, d.pk, d.d_k, d.d_v = n, pq, pk, 64, dv
+    cabi.check(lib.tdn_attention_tc(C.byref(d), None), "attention_tc")
+    torch.cuda.synchronize()
+    ms = None
+    if reps:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(2):
+            lib.tdn_attention_tc(C.byref(d), None)
+        e0.record()
+        for _ in range(reps):
+            lib.tdn_attention_tc(C.byref(d), None)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+    # reference in fp64, chunked over queries to bound memory
+    ref = torch.empty(n, pq, dv, dtype=torch.float64, device=dev)
+    for s0 in range(0, pq, 4096):
+        a = torch.softmax(torch.bmm(q[:, s0:s0 + 4096].double(), k.double().transpose(1, 2)) / 8.0, dim=2)
+        ref[:, s0:s0 + 4096] = torch.bmm(a, v.double()) + r[:, s0:s0 + 4096].double()
+    st = stats(out, ref)
+    if ms:
+        flop = 2.0 * n * pq * pk * (64 + dv)
+        st.update(ms=ms, algorithmic_tflops=flop / ms / 1e9)
+    return st
+
+
+EXPERIMENTS = ["layout_debug", "gemm_k512_ragged", "conv3x3_d8_97x193", "epilogue", "accum_bias_positive",
+               "layer1_perf", "layer4_perf", "attention_small", "attention_ragged", "attention_big"]
+# (experiment, TDNET_TC_CHUNK_KB) pairs run after the default set
+CHUNK_SWEEP = [("layer4_perf", 1), ("layer4_perf", 4), ("layer4_perf", 100000), ("accum_bias_positive", 1),
+               ("accum_bias_positive", 4)]
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "--one":
@@ -200,15 +258,20 @@ if __name__ == "__main__":
         sys.exit(0)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     lines = []
-    for name in (sys.argv[1:] or EXPERIMENTS):
+    todo = [(n, None) for n in (sys.argv[1:] or EXPERIMENTS)] + ([] if sys.argv[1:] else CHUNK_SWEEP)
+    for name, chunk in todo:
         t0 = time.time()
+        env = dict(os.environ)
+        if chunk is not None:
+            env["TDNET_TC_CHUNK_KB"] = str(chunk)
         try:
-            r = subprocess.run([sys.executable, __file__, "--one", name], capture_output=True, text=True, timeout=150)
+            r = subprocess.run([sys.executable, __file__, "--one", name], capture_output=True, text=True, timeout=150,
+                               env=env)
             res = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")]
             msg = res[0][7:] if res else f"FAILED rc={r.returncode} stdout={r.stdout[-600:]!r} stderr={r.stderr[-900:]!r}"
         except subprocess.TimeoutExpired:
             msg = "TIMEOUT (150 s)"
-        line = f"{name}: {msg}  [{time.time() - t0:.1f}s]"
+        line = f"{name}{'' if chunk is None else f' [chunk_kb={chunk}]'}: {msg}  [{time.time() - t0:.1f}s]"
         print(line, flush=True)
         lines.append(line)
     open(os.path.join(ROOT, "gpurun_out", "tc_probe.txt"), "w").write("\n".join(lines) + "\n")
