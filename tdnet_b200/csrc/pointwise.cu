@@ -90,6 +90,35 @@ __device__ __forceinline__ int bin_start(int i, int o, int len) { return (i * le
 __device__ __forceinline__ int bin_end(int i, int o, int len) { return ((i + 1) * len + o - 1) / o; }
 
 __global__ void psp_rowsum_kernel(View in, float* __restrict__ rowsum) {
+  // One pass over the row: every pyramid level keeps the running sum of its current column range.
+  // Adjacent ranges of a level overlap by at most one column (ceil vs floor), which seeds the next sum.
+  const int y = blockIdx.x, b = blockIdx.z;
+  const int c = blockIdx.y * blockDim.x + threadIdx.x;
+  if (c >= in.c) return;
+  const long long row = b * in.sn + y * in.sh + c;
+  float* dst = rowsum + ((long long)(b * in.h + y) * 12) * in.c + c;
+  const int W = in.w;
+  const int lv_o[4] = {1, 2, 3, 6};
+  const int lv_off[4] = {0, 1, 3, 6};
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  int cur[4] = {0, 0, 0, 0};
+  for (int x = 0; x < W; ++x) {
+    const float v = ld1(in, row + x * in.sw);
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      acc[l] += v;
+      if (x + 1 == bin_end(cur[l], lv_o[l], W)) {
+        dst[(long long)(lv_off[l] + cur[l]) * in.c] = acc[l];
+        ++cur[l];
+        acc[l] = (cur[l] < lv_o[l] && bin_start(cur[l], lv_o[l], W) <= x) ? v : 0.f;
+      }
+    }
+  }
+}
+
+// Generic fallback (any width, re-reads the row once per level): used when the map is narrower than the
+// finest pyramid level, where ranges overlap by more than one column.
+__global__ void psp_rowsum_generic_kernel(View in, float* __restrict__ rowsum) {
   const int y = blockIdx.x, b = blockIdx.y;
   const long long row = b * in.sn + y * in.sh;
   float* dst = rowsum + ((long long)(b * in.h + y) * 12) * in.c;
@@ -138,7 +167,11 @@ int psp_pool(const tdn_tensor* in, const tdn_tensor* out, float* workspace, size
   TDN_REQUIRE(workspace && workspace_bytes >= need, TDN_ERR_WORKSPACE,
               "psp_pool: workspace %zu < %zu bytes", workspace_bytes, need);
   int threads = in->c >= 512 ? 512 : (in->c >= 256 ? 256 : 128);
-  psp_rowsum_kernel<<<dim3(in->h, in->n), threads, 0, stream>>>(make_view(*in), workspace);
+  if (in->w >= 6) {
+    psp_rowsum_kernel<<<dim3(in->h, ceil_div(in->c, 128), in->n), 128, 0, stream>>>(make_view(*in), workspace);
+  } else {
+    psp_rowsum_generic_kernel<<<dim3(in->h, in->n), threads, 0, stream>>>(make_view(*in), workspace);
+  }
   TDN_LAUNCH_OK();
   psp_binsum_kernel<<<dim3(50, in->n), threads, 0, stream>>>(workspace, make_view(*out), in->h, in->w);
   TDN_LAUNCH_OK();
@@ -365,21 +398,32 @@ __global__ void ln_partial_kernel(View x, double2* __restrict__ part, int chunks
   }
 }
 
-__global__ void ln_final_kernel(const double2* __restrict__ part, int chunks, int C, int P, float eps,
-                                float* __restrict__ mean, float* __restrict__ rstd) {
+__global__ void __launch_bounds__(256) ln_final_kernel(const double2* __restrict__ part, int chunks, int C, int P,
+                                                       float eps, float* __restrict__ mean,
+                                                       float* __restrict__ rstd) {
+  // block = 32 channels x 8 chunk groups; fixed summation order -> bit-reproducible
+  __shared__ double ss[8][32], sq[8][32];
   const int b = blockIdx.y;
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+  const int cl = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
   double s = 0.0, q = 0.0;
-  for (int k = 0; k < chunks; ++k) {
-    double2 v = part[((long long)b * chunks + k) * C + c];
-    s += v.x; q += v.y;
+  if (c < C) {
+    for (int k = grp; k < chunks; k += 8) {
+      double2 v = part[((long long)b * chunks + k) * C + c];
+      s += v.x; q += v.y;
+    }
   }
-  double mu = s / P;
-  double var = q / P - mu * mu;
-  if (var < 0.0) var = 0.0;
-  mean[b * C + c] = (float)mu;
-  rstd[b * C + c] = (float)(1.0 / sqrt(var + (double)eps));
+  ss[grp][cl] = s; sq[grp][cl] = q;
+  __syncthreads();
+  if (grp == 0 && c < C) {
+#pragma unroll
+    for (int g = 1; g < 8; ++g) { s += ss[g][cl]; q += sq[g][cl]; }
+    double mu = s / P;
+    double var = q / P - mu * mu;
+    if (var < 0.0) var = 0.0;
+    mean[b * C + c] = (float)mu;
+    rstd[b * C + c] = (float)(1.0 / sqrt(var + (double)eps));
+  }
 }
 
 int layernorm_hw_stats(const tdn_tensor* x, float* mean, float* rstd, float eps, void* workspace,
@@ -395,8 +439,8 @@ int layernorm_hw_stats(const tdn_tensor* x, float* mean, float* rstd, float eps,
   int threads = x->c >= 256 ? 256 : 128;
   ln_partial_kernel<<<dim3(chunks, x->n), threads, 0, stream>>>(make_view(*x), (double2*)workspace, chunks);
   TDN_LAUNCH_OK();
-  ln_final_kernel<<<dim3(ceil_div(x->c, 128), x->n), 128, 0, stream>>>((const double2*)workspace, chunks,
-                                                                      x->c, P, eps, mean, rstd);
+  ln_final_kernel<<<dim3(ceil_div(x->c, 32), x->n), 256, 0, stream>>>((const double2*)workspace, chunks, x->c, P,
+                                                                     eps, mean, rstd);
   TDN_LAUNCH_OK();
   return TDN_OK;
 }

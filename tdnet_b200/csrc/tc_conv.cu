@@ -19,10 +19,10 @@
 //               scale/bias/residual/activation, re-split to hi/lo (and/or write fp32), 16-byte stores.
 // Accumulation is CHUNKED: the tensor core adds into its fp32 TMEM accumulator with truncation (measured
 // on B200: -3.8e-5 mean relative error after 864 chained MMAs on positive data), so a TMEM accumulator
-// only ever holds `chunk_kb` K blocks (default 2 = 24 MMAs); the epilogue warps pull each finished chunk
-// out of TMEM and add it to per-thread fp32 registers with round-to-nearest.  Two TMEM buffers ping-pong
-// at chunk granularity, so the MMA warp keeps issuing while the previous chunk is being drained, and the
-// final scale/bias/store of tile i overlaps the first chunks of tile i+1.
+// only ever holds `chunk_kb` K blocks (default 4 = 48 MMAs); the epilogue warps pull each finished chunk
+// out of TMEM and add it to per-thread fp32 registers with round-to-nearest.  The 512 TMEM columns form
+// a ring of 4 (BLOCK_N=128) or 8 (BLOCK_N=64) chunk accumulators, so the MMA warp keeps issuing while
+// earlier chunks are drained and while the scale/bias/store phase of the previous tile runs.
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -68,8 +68,12 @@ struct TcCfg {
   static constexpr int B_PLANE = BLOCK_N * TC_BLOCK_K * 2;
   static constexpr int STAGE_BYTES = 2 * TC_A_PLANE + 2 * B_PLANE;
   static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES;
-  static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  // All 512 TMEM columns as a ring of chunk accumulators (4 x 128 or 8 x 64 columns): the MMA warp can
+  // run several chunks ahead of the warps that drain them, so the per-tile store phase of the epilogue
+  // (scale/bias/residual/split/store) overlaps the MMAs of the next tile instead of stalling them.
+  static constexpr int NUM_ACC = 512 / BLOCK_N;
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
 };
 
 __device__ __forceinline__ float tc_act(float v, int act, float slope) {
@@ -89,9 +93,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
+  constexpr int NUM_ACC = Cfg::NUM_ACC;
   uint64_t* tmem_full = empty_bar + STAGES;
-  uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* tmem_empty = tmem_full + NUM_ACC;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + NUM_ACC);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -107,7 +112,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < NUM_ACC; ++s) {
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], 128);
     }
@@ -188,7 +193,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
           umma_commit(&tmem_full[as]);
-          if (++as == 2) { as = 0; aphase ^= 1; }
+          if (++as == NUM_ACC) { as = 0; aphase ^= 1; }
         }
       }
     }
@@ -232,7 +237,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         }
         tc_fence_before();
         mbar_arrive(&tmem_empty[as]);
-        if (++as == 2) { as = 0; aphase ^= 1; }
+        if (++as == NUM_ACC) { as = 0; aphase ^= 1; }
       }
 #pragma unroll
       for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
@@ -240,15 +245,30 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         if (valid && c0 < p.Cout) {
           float v[32];
           const bool full = (c0 + 32 <= p.Cout);
+          if (full) {
+            // warp-uniform 16-byte loads of the per-channel scale / bias (L1 broadcast)
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int c = c0 + j;
-            float s = 1.f, b = bias_m;
-            if (full || c < p.Cout) {
-              if (p.scale) s = __ldg(p.scale + c);
-              if (p.bias && !p.bias_along_m) b = __ldg(p.bias + c);
+            for (int q = 0; q < 8; ++q) {
+              float4 s4 = p.scale ? __ldg(reinterpret_cast<const float4*>(p.scale + c0) + q)
+                                  : make_float4(1.f, 1.f, 1.f, 1.f);
+              float4 b4 = (p.bias && !p.bias_along_m) ? __ldg(reinterpret_cast<const float4*>(p.bias + c0) + q)
+                                                      : make_float4(bias_m, bias_m, bias_m, bias_m);
+              v[q * 4 + 0] = fmaf(acc[chunk * 32 + q * 4 + 0], s4.x, b4.x);
+              v[q * 4 + 1] = fmaf(acc[chunk * 32 + q * 4 + 1], s4.y, b4.y);
+              v[q * 4 + 2] = fmaf(acc[chunk * 32 + q * 4 + 2], s4.z, b4.z);
+              v[q * 4 + 3] = fmaf(acc[chunk * 32 + q * 4 + 3], s4.w, b4.w);
             }
-            v[j] = fmaf(acc[chunk * 32 + j], s, b);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int c = c0 + j;
+              float s = 1.f, b = bias_m;
+              if (c < p.Cout) {
+                if (p.scale) s = __ldg(p.scale + c);
+                if (p.bias && !p.bias_along_m) b = __ldg(p.bias + c);
+              }
+              v[j] = fmaf(acc[chunk * 32 + j], s, b);
+            }
           }
           if (p.res_hi) {
             if (full) {
@@ -404,6 +424,8 @@ int conv2d_tc(const tdn_tc_conv_desc* d, cudaStream_t stream) {
               "conv2d_tc: stride-1 'same' convolution expects out dims == in dims");
   TDN_REQUIRE(aligned16(in.data) && aligned16(in.data_lo) && in.stride_w % 8 == 0 && in.stride_h % 8 == 0 &&
                   in.stride_n % 8 == 0, TDN_ERR_INVALID, "conv2d_tc: input planes must be 16-byte aligned");
+  TDN_REQUIRE((!d->scale || aligned16(d->scale)) && (!d->bias || aligned16(d->bias)), TDN_ERR_INVALID,
+              "conv2d_tc: scale/bias must be 16-byte aligned");
   TDN_REQUIRE(aligned16(d->weight_hi) && aligned16(d->weight_lo) && d->weight_ld % 8 == 0 &&
                   d->weight_batch_stride % 8 == 0, TDN_ERR_INVALID, "conv2d_tc: weights must be 16-byte aligned");
   const bool out16 = out.dtype == TDN_SPLIT16;
@@ -425,13 +447,13 @@ int conv2d_tc(const tdn_tc_conv_desc* d, cudaStream_t stream) {
   TDN_REQUIRE(num_tiles < (1ll << 31), TDN_ERR_UNSUPPORTED, "conv2d_tc: too many tiles");
   p.num_tiles = (int)num_tiles;
   {
-    // K blocks per TMEM accumulation chunk (see the header comment).  2 is the measured sweet spot;
+    // K blocks per TMEM accumulation chunk (see the header comment).  4 is the measured sweet spot;
     // TDNET_TC_CHUNK_KB overrides it for experiments (a huge value = plain in-TMEM accumulation).
     static int chunk_kb = 0;
     if (chunk_kb == 0) {
       const char* e = getenv("TDNET_TC_CHUNK_KB");
-      chunk_kb = e ? atoi(e) : 2;
-      if (chunk_kb < 1) chunk_kb = 2;
+      chunk_kb = e ? atoi(e) : 4;
+      if (chunk_kb < 1) chunk_kb = 4;
     }
     p.chunk_kb = chunk_kb;
   }

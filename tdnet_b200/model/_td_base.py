@@ -76,9 +76,9 @@ class TDModel(nn.Module):
         for key, (shape, kind) in A.parameter_table(self.arch, self.ln_shape).items():
             _attach(self, key, shape, kind)
         _default_init_(self)
+        self._engines: Dict[tuple, object] = {}
         self.pretrained_mp_load()
         self.Q_queue, self.K_queue, self.V_queue = [], [], []
-        self._engines: Dict[tuple, object] = {}
         # 'tc': tcgen05 exact-mode kernels (product path on B200); 'simt': fp32 CUDA-core kernels only.
         self.engine_mode = os.environ.get("TDNET_B200_ENGINE", "tc")
 

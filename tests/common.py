@@ -64,3 +64,16 @@ def argmax_report(test_logits, ref_logits, err):
     decided = margin > 2.0 * err
     return dict(mismatch_total=int((~same).sum()), mismatch_decided=int((~same & decided).sum()),
                 near_ties=int((~decided).sum()), pixels=int(same.numel()))
+
+
+def record(name, **metrics):
+    """Append measured parity numbers to gpurun_out/parity_metrics.jsonl (copied into profiles/ and cited
+    in DESIGN.md); never fails a test."""
+    import json
+    try:
+        out = os.path.join(os.path.dirname(GOLDEN_DIR), "..", "gpurun_out")
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_metrics.jsonl"), "a") as f:
+            f.write(json.dumps(dict(name=name, **metrics)) + "\n")
+    except OSError:
+        pass

@@ -1,0 +1,67 @@
+"""CPU: the drop-in `model` package exposes the reference's import surface (Testing/test.py:9)."""
+import importlib
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_dropin_import_surface():
+    sys.path.insert(0, os.path.join(ROOT, "tdnet_b200", "dropin"))
+    try:
+        sys.modules.pop("model", None)
+        model = importlib.import_module("model")
+        from model import pspnet, td2_psp50, td4_psp18  # noqa: F401  (the line in Testing/test.py:9)
+        net = model.td4_psp18.td4_psp18(nclass=19, path_num=4, model_path="/nonexistent.pth")  # test.py:26
+        assert isinstance(net, torch.nn.Module) and net.path_num == 4
+        net.eval()
+        assert len(net.state_dict()) == 728
+        net2 = model.td2_psp50.td2_psp50(nclass=19, path_num=2)
+        assert len(net2.state_dict()) == 776 and net2.Q_queue == []
+        with pytest.raises(NotImplementedError):
+            model.pspnet.pspnet(nclass=19)
+    finally:
+        sys.path.pop(0)
+        sys.modules.pop("model", None)
+
+
+def test_checkpoint_roundtrip_strict(tmp_path):
+    """pretrained_mp_load: torch.load + load_state_dict(strict=True) (td4_psp18.py:232-240)."""
+    from tdnet_b200.model import td2_psp50
+    from tdnet_b200.synth import synth_state_dict
+    a = td2_psp50.td2_psp50(nclass=19, path_num=2, backbone="resnet18")
+    sd = synth_state_dict(a.state_dict(), seed=3)
+    path = tmp_path / "ckpt.pth"
+    torch.save(sd, path)
+    b = td2_psp50.td2_psp50(nclass=19, path_num=2, backbone="resnet18", model_path=str(path))
+    for k, v in b.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        b(torch.zeros(1, 3, 32, 32), pos_id=0)
+
+
+def test_engine_plans_build_without_gpu():
+    """Host logic only: plan construction (buffer pool, descriptors, op order) for both engine modes."""
+    from collections import Counter
+    from tdnet_b200.engine import Engine
+    from tdnet_b200.model import arch as A
+    m = A.build_arch("td4_psp18", "resnet18", 19)
+    h8, w8 = A.feature_hw(97, 161)
+    sd = {k: torch.full(shape, 0.01) if kind != "long_buffer" else torch.zeros(shape, dtype=torch.long)
+          for k, (shape, kind) in A.parameter_table(m, (h8, w8)).items()}
+    for k in sd:
+        if k.endswith("running_var"):
+            sd[k].fill_(1.0)
+    for mode, tc_ops in (("simt", 0), ("tc", 24)):
+        eng = Engine(m, sd, 1, 97, 161, torch.device("cpu"), (h8, w8), mode=mode)
+        warm, steady = eng.plan(1, False), eng.plan(1, True)
+        c = Counter(fn.__name__ for fn, _ in steady.ops)
+        assert c["tdn_conv2d_tc"] == tc_ops and c["tdn_upsample_logits"] == 1
+        assert (c["tdn_attention_tc"] == 3) == (mode == "tc")
+        assert len(steady.ops) > len(warm.ops)           # warm-up frames skip the attention hops
+        assert eng.pk == 4 * 6 and len(eng.k_slots) == 3  # P' = ceil(13/4) x ceil(21/4), FIFO depth 3
+    with pytest.raises(RuntimeError, match="normalized_shape"):
+        Engine(m, sd, 1, 64, 64, torch.device("cpu"), (h8, w8))

@@ -11,7 +11,8 @@ import numpy as np
 import pytest
 import torch
 
-from common import CH_STRIDE, GOLDEN_CASES, argmax_report, load_golden, make_oracle, make_weights, max_abs
+from common import (CH_STRIDE, GOLDEN_CASES, argmax_report, load_golden, make_oracle, make_weights, max_abs,
+                    record, rel_l2)
 from tdnet_b200.synth import synth_clip
 
 pytestmark = pytest.mark.gpu
@@ -55,6 +56,7 @@ def test_model_matches_reference_golden(name, mode):
             e = max_abs(out.cpu(), ref)
             assert e <= LOGIT_TOL, (name, i, e)
             rep = argmax_report(out.cpu(), ref, max(e, 1e-6))
+            record(f"golden/{name}/{mode}/frame{i}", max_abs=e, rel_l2=rel_l2(out.cpu(), ref), **rep)
             assert rep["mismatch_decided"] == 0, rep
             assert rep["near_ties"] <= 0.001 * rep["pixels"] + 2, rep
         assert len(net.Q_queue) == len(net.K_queue) == len(net.V_queue) == min(i + 1, net.arch.depth)
@@ -99,6 +101,7 @@ def test_td4_512x1024_against_oracle_two_cycles():
         e = max_abs(out, ref)
         worst = max(worst, e)
         rep = argmax_report(out, ref, max(e, 1e-6))
+        record(f"oracle/td4_512x1024/frame{i}", max_abs=e, rel_l2=rel_l2(out, ref), **rep)
         assert rep["mismatch_decided"] == 0, (i, rep)
         flips += rep["mismatch_total"]
         near += rep["near_ties"]
@@ -120,8 +123,9 @@ def test_full_size_1024x2048_properties():
         outs.append(out.cpu())
         if i >= 3:
             e = max_abs(outs[-1], ref)
-            assert e <= LOGIT_TOL, (i, e)
             rep = argmax_report(outs[-1], ref, max(e, 1e-6))
+            record(f"oracle/td4_1024x2048/frame{i}", max_abs=e, rel_l2=rel_l2(outs[-1], ref), **rep)
+            assert e <= LOGIT_TOL, (i, e)
             assert rep["mismatch_decided"] == 0, rep
     assert net.K_queue[0].shape == (1, 2048, 64) and net.V_queue[0].shape == (1, 2048, 512)
     assert all(torch.isfinite(o).all() for o in outs)

@@ -151,7 +151,7 @@ def test_image_layout_and_maxpool(env):
     assert torch.equal(y.permute(0, 3, 1, 2).cpu(), F.max_pool2d(x, 3, 2, 1))
 
 
-@pytest.mark.parametrize("h,w", [(13, 21), (16, 32), (6, 6), (97, 193)])
+@pytest.mark.parametrize("h,w", [(13, 21), (16, 32), (6, 6), (97, 193), (4, 4), (7, 5), (23, 30)])
 def test_psp_pool_matches_adaptive_avg_pool(env, h, w):
     lib, cabi, View, dev = env
     g = torch.Generator().manual_seed(h * w)
@@ -358,7 +358,7 @@ def test_tc_conv_epilogue_and_batched_weights(env):
     torch.cuda.synchronize()
     ref = F.relu(F.conv2d(x.double(), wt.double(), None, 1, 1) * sc.double().view(1, -1, 1, 1)
                  + bi.double().view(1, -1, 1, 1) + rs.torch().permute(0, 3, 1, 2).cpu().double())
-    assert max_abs(out.torch().permute(0, 3, 1, 2).cpu(), ref) < 5e-6
+    assert max_abs(out.torch().permute(0, 3, 1, 2).cpu(), ref) < 2e-6 * float(ref.abs().max())
     assert int(flag.item()) == 0
     # q k^T with one key matrix per image (transformer.py:128)
     q, k = torch.randn(2, 300, 64, generator=g), torch.randn(2, 100, 64, generator=g)
@@ -374,7 +374,7 @@ def test_tc_conv_epilogue_and_batched_weights(env):
     cabi.check(lib.tdn_conv2d_tc(C.byref(d), None), "conv2d_tc")
     torch.cuda.synchronize()
     ref = torch.bmm(q.double(), k.double().transpose(1, 2))
-    assert max_abs(s.torch()[:, 0, :, :100].cpu(), ref) < 5e-6
+    assert max_abs(s.torch()[:, 0, :, :100].cpu(), ref) < 2e-6 * float(ref.abs().max())
 
 
 @pytest.mark.parametrize("n,pq,pk,dv", [(2, 300, 100, 128), (1, 2048, 2048, 512), (1, 1000, 690, 256)])
@@ -402,4 +402,6 @@ def test_fused_attention_tc(env, n, pq, pk, dv):
     torch.cuda.synchronize()
     a = torch.softmax(torch.bmm(q.double(), k.double().transpose(1, 2)) / 8.0, dim=2)
     ref = torch.bmm(a, v.double()) + r.double()
-    assert max_abs(out.cpu(), ref) < 2e-5
+    # the O accumulator chains up to 12 * ceil(pk / 64) tensor-core adds (truncating), hence the looser bound
+    assert max_abs(out.cpu(), ref) < 1.5e-5 * float(ref.abs().max())
+    assert float((out.cpu().double() - ref).norm() / ref.norm()) < 5e-6
