@@ -32,6 +32,7 @@ ARCH, BACKBONE = "td4_psp18", "resnet18"
 WORKLOAD = "td4-psp18 1024x2048 synthetic Cityscapes stream, batch 1 (BASELINE.json configs[1])"
 FRAME_GFLOP = 936.2            # algorithmic FLOPs of one frame (2*MAC of the reference's operators)
 DOMINANT_GFLOP = 154.62        # layer4 3x3 512->512 dilated conv at 128x256
+DOMINANT_TRAFFIC_BYTES = 110.4e6   # ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum (profiles/r01_*)
 N_DISTINCT_FRAMES = 8
 
 
@@ -98,33 +99,56 @@ def _weights(h8, w8):
             .to(torch.long if kind == "long_buffer" else torch.float32) for k, (shape, kind) in table.items()}
 
 
-def run_reference(args, rank):
-    """The reference's own CPU implementation of the path: the oracle port (kind 'port'; the reference
-    is Python and /root/reference does not exist on the GPU box), all host threads."""
-    if rank != 0:
-        return
+def _cpu_oracle_fps(n_timed, warm=3):
+    """Oracle port of the reference on the host cores.  torch's intra-op pool does not scale to every
+    core of a 128-thread box for these convolutions, so a few thread counts are tried on one frame each
+    and the best one is used for the timed frames ('cores' = the threads actually used)."""
     import torch
     from oracle.tdnet_oracle import TDOracle
     from tdnet_b200.model.arch import feature_hw
     from tdnet_b200.synth import synth_clip
-    cores = os.cpu_count()
-    torch.set_num_threads(cores)
+    ncpu = os.cpu_count() or 1
     h8, w8 = feature_hw(H, W)
     oracle = TDOracle(ARCH, _weights(h8, w8), BACKBONE)
-    steps, warm = min(args.steps, args.ref_max_steps), min(max(args.warmup, 3), 4)
-    frames = synth_clip(min(steps + warm, N_DISTINCT_FRAMES), H, W, batch=BATCH)
-    for i in range(warm):
-        oracle(frames[i % len(frames)], pos_id=i % 4)
-    t0 = time.perf_counter()
-    for i in range(warm, warm + steps):
-        out = oracle(frames[i % len(frames)], pos_id=i % 4)
+    frames = synth_clip(N_DISTINCT_FRAMES, H, W, batch=BATCH)
+    step = 0
+
+    def one():
+        nonlocal step
+        t0 = time.perf_counter()
+        out = oracle(frames[step % len(frames)], pos_id=step % 4)
         _ = out.max(1)[1]
-    dt = time.perf_counter() - t0
-    fps = steps / dt
-    sample = f"{steps} steady-state frames after {warm} warm-up frames, torch {torch.__version__} CPU fp32, {cores} threads"
+        step += 1
+        return time.perf_counter() - t0
+
+    cands = sorted({c for c in (ncpu, 64, 32, 16) if c <= ncpu}, reverse=True)
+    torch.set_num_threads(min(32, ncpu))
+    for _ in range(warm):
+        one()
+    best, best_t = cands[0], None
+    for c in cands:
+        torch.set_num_threads(c)
+        t = one()
+        if best_t is None or t < best_t:
+            best, best_t = c, t
+    torch.set_num_threads(best)
+    dt = sum(one() for _ in range(n_timed))
+    tried = ", ".join(str(c) for c in cands)
+    sample = (f"{n_timed} steady-state 1024x2048 frames after {warm}+{len(cands)} warm-up frames, oracle port of the "
+              f"reference on torch {torch.__version__} CPU fp32, best of {{{tried}}} threads on a {ncpu}-thread host")
+    return n_timed / dt, best, sample, dt
+
+
+def run_reference(args, rank):
+    """The reference's own CPU implementation of the path: the oracle port (kind 'port'; the reference
+    is Python and /root/reference does not exist on the GPU box)."""
+    if rank != 0:
+        return
+    steps = min(args.steps, args.ref_max_steps)
+    fps, cores, sample, dt = _cpu_oracle_fps(steps)
     print(json.dumps({
         "impl": "reference", "metric": "frames/sec at 1024x2048 (td4-psp18)", "value": fps, "unit": "frames/s",
-        "n_gpus": args.gpus, "steps": steps, "steps_requested": args.steps, "warmup": warm,
+        "n_gpus": args.gpus, "steps": steps, "steps_requested": args.steps, "warmup": 3,
         "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
@@ -133,23 +157,8 @@ def run_reference(args, rank):
 
 
 def cpu_baseline(n_frames=3):
-    import torch
-    from oracle.tdnet_oracle import TDOracle
-    from tdnet_b200.model.arch import feature_hw
-    from tdnet_b200.synth import synth_clip
-    cores = os.cpu_count()
-    torch.set_num_threads(cores)
-    h8, w8 = feature_hw(H, W)
-    oracle = TDOracle(ARCH, _weights(h8, w8), BACKBONE)
-    frames = synth_clip(4, H, W, batch=BATCH)
-    for i in range(3):
-        oracle(frames[i], pos_id=i)
-    t0 = time.perf_counter()
-    for i in range(3, 3 + n_frames):
-        oracle(frames[i % 4], pos_id=i % 4)
-    dt = time.perf_counter() - t0
-    return {"value": n_frames / dt, "unit": "frames/s", "cores": cores, "kind": "port",
-            "sample": f"{n_frames} steady-state 1024x2048 frames after 3 warm-up frames, oracle port on torch CPU fp32"}
+    fps, cores, sample, _ = _cpu_oracle_fps(n_frames)
+    return {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample}
 
 
 def run_ours(args, rank, world):
@@ -226,10 +235,14 @@ def run_ours(args, rank, world):
         roof = None
         if dom_ms:
             achieved = DOMINANT_GFLOP / dom_ms  # GFLOP / ms = TFLOP/s
-            roof = {"bound": "tensor", "kernel": dom_ms_name(net), "achieved": achieved, "peak": peaks["tflops"],
-                    "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "traffic": None,
-                    "peak_source": peaks["source"], "ms_per_launch": dom_ms,
-                    "note": "algorithmic FLOPs (2*MAC of the reference conv); exact mode executes 3 fp16 MMAs per product"}
+            roof = {"bound": "tensor", "kernel": f"tc_conv_kernel<128> ({dom_ms_name(net)}: 3x3 512->512 dilated, 128x256 map)",
+                    "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
+                    "traffic": DOMINANT_TRAFFIC_BYTES, "peak_source": peaks["source"], "ms_per_launch": dom_ms,
+                    "executed_tflops": 3 * achieved, "executed_frac": 3 * achieved / peaks["tflops"],
+                    "note": "achieved = algorithmic FLOPs (2*MAC of the reference conv, 154.62 GFLOP) / live CUDA-event "
+                            "time of that launch inside running frames; the fp32-faithful exact mode executes 3 fp16 "
+                            "tensor-core products per algorithmic product, so the ceiling of `frac` is 1/3; traffic = "
+                            "dram read+write bytes of one launch from profiles/r01_prof_conv_summary.txt"}
         line = {
             "metric": "frames/sec at 1024x2048 (td4-psp18)", "value": fps, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": warm, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
