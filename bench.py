@@ -211,16 +211,47 @@ def run_ours(args, rank, world):
     ms_dev = e0.elapsed_time(e1)
     clocks = sampler.stop() if sampler else None
 
-    # ---- timed region B: end to end through the public API: pinned host frame -> H2D -> forward -> argmax -> D2H
-    labels_host = torch.empty((BATCH, H, W), dtype=torch.int64).pin_memory()
+    # ---- timed region B: end to end through the public API, the way a streaming caller drives it:
+    #      pinned host frame -> H2D (copy stream, double-buffered) -> model(image, pos_id) -> argmax
+    #      (Testing/test.py:53,61) -> D2H of the label map (second copy stream).  Every frame's input crosses
+    #      PCIe inside the timed region and every frame's labels land in pinned host memory.
+    copy_s, d2h_s = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    dev_in = [torch.empty_like(dev_frames[0]) for _ in range(2)]
+    labels_host = [torch.empty((BATCH, H, W), dtype=torch.int64).pin_memory() for _ in range(2)]
+    ev_in = [torch.cuda.Event() for _ in range(2)]
+    ev_consumed = [torch.cuda.Event() for _ in range(2)]
+    ev_done = [torch.cuda.Event() for _ in range(2)]
+    ev_d2h = [torch.cuda.Event() for _ in range(2)]
+
+    def prefetch(i, slot, first=False):
+        with torch.cuda.stream(copy_s):
+            if not first:
+                copy_s.wait_event(ev_consumed[slot])       # the frame that used this slot has read it
+            dev_in[slot].copy_(host_frames[i % N_DISTINCT_FRAMES], non_blocking=True)
+            ev_in[slot].record(copy_s)
+
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record(stream)
-    for _ in range(args.steps):
-        img = host_frames[step % N_DISTINCT_FRAMES].to(dev, non_blocking=True)
-        out = net(img, pos_id=step % 4)
-        labels_host.copy_(out.max(1)[1], non_blocking=True)   # Testing/test.py:61
+    copy_s.wait_event(e2)
+    d2h_s.wait_event(e2)
+    prefetch(step, 0, first=True)
+    for i in range(args.steps):
+        slot = i % 2
+        stream.wait_event(ev_in[slot])
+        out = net(dev_in[slot], pos_id=step % 4)
+        ev_consumed[slot].record(stream)
+        labels = out.max(1)[1]                              # Testing/test.py:61
+        ev_done[slot].record(stream)
+        if i + 1 < args.steps:
+            prefetch(step + 1, slot ^ 1, first=(i == 0))
+        with torch.cuda.stream(d2h_s):
+            d2h_s.wait_event(ev_done[slot])
+            labels_host[slot].copy_(labels, non_blocking=True)
+            labels.record_stream(d2h_s)
+            ev_d2h[slot].record(d2h_s)
         step += 1
+    stream.wait_stream(d2h_s)
     e3.record(stream)
     barrier()
     ms_e2e = e2.elapsed_time(e3)
@@ -252,7 +283,8 @@ def run_ours(args, rank, world):
                        "frame_gflop": FRAME_GFLOP},
             "frame_tflops": FRAME_GFLOP * fps / 1e3 / world,
             "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": BATCH * 3 * H * W * 4,
-                    "d2h_bytes_per_step": BATCH * H * W * 8, "ms_per_step": ms_e2e / args.steps},
+                    "d2h_bytes_per_step": BATCH * H * W * 8, "ms_per_step": ms_e2e / args.steps,
+                    "pipeline": "H2D of frame i+1 and D2H of labels i-1 overlap compute of frame i (3 streams)"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof,
             "cpu_baseline": cpu_baseline() if (world == 1 and not args.no_cpu_baseline) else None,
         }

@@ -6,22 +6,24 @@
 // and, with the fc folded into V' by the host (softmax rows sum to 1), Attention.forward :71-92.
 // The [Pq x P'] attention matrix never exists in memory.
 //
-// Work item = (image, 128-query tile, 128-channel slice of d_v); persistent CTAs loop over items.
+// Work item = (image, 128-query tile, DVT-channel slice of d_v, DVT = 256 when d_v % 256 == 0 else 128);
+// persistent CTAs loop over items.
 // Per item, two passes over the P' keys in tiles of 64:
 //   pass 1  S~ = Qhi.Khi^T (one fp16 MMA per K step) -> running row maximum m.  The maximum is only a
 //           stabiliser, so the cheap single-product S~ is enough (it is within ~1e-3*|S| of S).
 //   pass 2  S  = Q.K^T in exact mode (hi*lo + lo*hi + hi*hi, fp32 TMEM accumulator);
 //           p  = exp(S/sqrt(d_k) - m) (fp32, per query row in registers, row sum l accumulated);
 //           P  = p * 2^10 split to fp16 hi/lo, written to shared memory in the UMMA K-major 128B-swizzled
-//                layout; O += P.V'^T in exact mode (fp32 TMEM accumulator, 128 columns).
+//                layout; O += P.V'^T in exact mode (fp32 TMEM accumulator, DVT columns, N=128 MMAs).
 //   epilogue out = O / (l * 2^10) + residual, re-split to hi/lo (and/or fp32).
 // Because m is fixed before pass 2 there is no running rescale of O: the MMA warp never waits on a
 // correction step and the result does not depend on tile order.
 //
-// Warp roles (192 threads): warp 0 TMA producer (Q tile, K ring, V ring), warp 1 MMA issuer,
-// warps 2-5 softmax + epilogue (one query row per thread; TMEM lane quarter = warp % 4).
-// TMEM: S double-buffered 2 x 64 columns, O 128 columns.  Shared memory: Q 32 KB, K ring 2 x 16 KB,
-// V ring 2 x 32 KB, P double buffer 2 x 32 KB (hi+lo planes each).
+// Warp roles (320 threads): warp 0 TMA producer (Q tile, K ring, V ring), warp 1 MMA issuer,
+// warps 2-9 softmax + epilogue: two warps per TMEM lane quarter, each owning half of the key columns of
+// a tile and half of the output channels (row max / sum exchanged through shared memory).
+// TMEM: S double-buffered 2 x 64 columns, O DVT columns.  Shared memory: Q 32 KB, K ring 2 x 16 KB,
+// V ring 3 x 32 KB (128-row halves of the V'^T tile), P double buffer 2 x 32 KB (hi+lo planes each).
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -35,16 +37,16 @@ using namespace ptx;
 constexpr int AT_BQ = 128;       // queries per item
 constexpr int AT_BK = 64;        // keys per tile (= one 128-byte swizzle row of fp16)
 constexpr int AT_DK = 64;        // d_k (fixed by the model: Encoding(d_model, 64, d_v))
-constexpr int AT_DV = 128;       // d_v slice per item
-constexpr int AT_THREADS = 192;
+constexpr int AT_DVH = 128;      // V'^T rows per shared-memory stage / per PV MMA (N = 128)
+constexpr int AT_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 softmax + epilogue (two per TMEM lane quarter)
+constexpr int AT_SOFTMAX_THREADS = 256;
 constexpr int AT_Q_PLANE = AT_BQ * AT_DK * 2;   // 16 KB
 constexpr int AT_K_PLANE = AT_BK * AT_DK * 2;   // 8 KB
-constexpr int AT_V_PLANE = AT_DV * AT_BK * 2;   // 16 KB
+constexpr int AT_V_PLANE = AT_DVH * AT_BK * 2;  // 16 KB
 constexpr int AT_P_PLANE = AT_BQ * AT_BK * 2;   // 16 KB
-constexpr int AT_KSTAGES = 2, AT_VSTAGES = 2;
+constexpr int AT_KSTAGES = 2, AT_VSTAGES = 3;
 constexpr int AT_SMEM_DATA = 2 * AT_Q_PLANE + AT_KSTAGES * 2 * AT_K_PLANE + AT_VSTAGES * 2 * AT_V_PLANE + 2 * 2 * AT_P_PLANE;
-constexpr int AT_SMEM_BYTES = AT_SMEM_DATA + 1024 + 512;
-constexpr int AT_TMEM_COLS = 256;   // S: 2 x 64, O: 128
+constexpr int AT_TMEM_COLS = 512;   // S: 2 x 64 columns, O: up to 256 columns
 constexpr float AT_P_SCALE = 1024.f;
 
 struct AttnParams {
@@ -70,8 +72,13 @@ struct AttnBars {
   uint64_t p_full[2], p_empty[2];
   uint64_t o_full, o_empty;
   uint32_t tmem_ptr;
+  float xch[2][AT_BQ];     // row max / row sum exchange between the two softmax warp groups
 };
 
+constexpr int AT_SMEM_BYTES = AT_SMEM_DATA + 1024 /*alignment slack*/ + ((int)sizeof(AttnBars) + 127) / 128 * 128;
+static_assert(AT_SMEM_BYTES <= 232448, "attention kernel exceeds the 227 KB shared-memory limit");
+
+template <int DVT>   // d_v slice per work item: 128 or 256 (one or two 128-row V'^T halves per key tile)
 __global__ void __launch_bounds__(AT_THREADS, 1)
 tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ CUtensorMap tmQ_lo,
                const __grid_constant__ CUtensorMap tmK_hi, const __grid_constant__ CUtensorMap tmK_lo,
@@ -98,12 +105,12 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant
     for (int s = 0; s < AT_VSTAGES; ++s) { mbar_init(&bars->v_full[s], 1); mbar_init(&bars->v_empty[s], 1); }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&bars->s_full[s], 1);
-      mbar_init(&bars->s_empty[s], 128);
-      mbar_init(&bars->p_full[s], 128);
+      mbar_init(&bars->s_empty[s], AT_SOFTMAX_THREADS);
+      mbar_init(&bars->p_full[s], AT_SOFTMAX_THREADS);
       mbar_init(&bars->p_empty[s], 1);
     }
     mbar_init(&bars->o_full, 1);
-    mbar_init(&bars->o_empty, 128);
+    mbar_init(&bars->o_empty, AT_SOFTMAX_THREADS);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -117,6 +124,7 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant
   const uint32_t tmem_S = tmem_base;            // + buf * 64
   const uint32_t tmem_O = tmem_base + 128;
   const int T = p.k_tiles;
+  constexpr int HALVES = DVT / AT_DVH;
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -149,12 +157,14 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant
           tma_load_3d(dk, &tmK_hi, &bars->k_full[ks], 0, kt * AT_BK, img);
           tma_load_3d(dk + AT_K_PLANE, &tmK_lo, &bars->k_full[ks], 0, kt * AT_BK, img);
           if (++ks == AT_KSTAGES) { ks = 0; kph ^= 1; }
-          mbar_wait(&bars->v_empty[vs], vph ^ 1);
-          uint8_t* dv = sV + vs * 2 * AT_V_PLANE;
-          mbar_expect_tx(&bars->v_full[vs], 2 * AT_V_PLANE);
-          tma_load_3d(dv, &tmV_hi, &bars->v_full[vs], kt * AT_BK, dvt * AT_DV, img);
-          tma_load_3d(dv + AT_V_PLANE, &tmV_lo, &bars->v_full[vs], kt * AT_BK, dvt * AT_DV, img);
-          if (++vs == AT_VSTAGES) { vs = 0; vph ^= 1; }
+          for (int h = 0; h < HALVES; ++h) {
+            mbar_wait(&bars->v_empty[vs], vph ^ 1);
+            uint8_t* dv = sV + vs * 2 * AT_V_PLANE;
+            mbar_expect_tx(&bars->v_full[vs], 2 * AT_V_PLANE);
+            tma_load_3d(dv, &tmV_hi, &bars->v_full[vs], kt * AT_BK, dvt * DVT + h * AT_DVH, img);
+            tma_load_3d(dv + AT_V_PLANE, &tmV_lo, &bars->v_full[vs], kt * AT_BK, dvt * DVT + h * AT_DVH, img);
+            if (++vs == AT_VSTAGES) { vs = 0; vph ^= 1; }
+          }
         }
       }
     }
@@ -162,7 +172,7 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant
     // ================================ MMA issuer ================================
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_f16(AT_BQ, AT_BK);   // 128 x 64
-      constexpr uint32_t idesc_o = umma_idesc_f16(AT_BQ, AT_DV);   // 128 x 128
+      constexpr uint32_t idesc_o = umma_idesc_f16(AT_BQ, AT_DVH);  // 128 x 128
       int ks = 0, vs = 0, sb = 0, pb = 0;
       uint32_t kph = 0, vph = 0, sph = 0, pph = 0, qph = 0, oph = 0;
       const uint32_t q_hi = smem_u32(sQ), q_lo = q_hi + AT_Q_PLANE;
@@ -198,23 +208,26 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant
         issue_s(true);                                        // S(0) of pass 2
         for (int kt = 0; kt < T; ++kt) {
           if (kt + 1 < T) issue_s(true);                      // S(kt+1) overlaps softmax(kt)
-          mbar_wait(&bars->v_full[vs], vph);
           mbar_wait(&bars->p_full[pb], pph);
           if (kt == 0) mbar_wait(&bars->o_empty, oph ^ 1);
-          tc_fence_after();
           const uint32_t p_hi = smem_u32(sP + pb * 2 * AT_P_PLANE), p_lo = p_hi + AT_P_PLANE;
-          const uint32_t v_hi = smem_u32(sV + vs * 2 * AT_V_PLANE), v_lo = v_hi + AT_V_PLANE;
+          for (int h = 0; h < HALVES; ++h) {
+            mbar_wait(&bars->v_full[vs], vph);
+            tc_fence_after();
+            const uint32_t v_hi = smem_u32(sV + vs * 2 * AT_V_PLANE), v_lo = v_hi + AT_V_PLANE;
+            const uint32_t d = tmem_O + h * AT_DVH;
 #pragma unroll
-          for (int k = 0; k < AT_BK / 16; ++k) {
-            const uint64_t a_h = umma_desc_k_sw128(p_hi + k * 32), a_l = umma_desc_k_sw128(p_lo + k * 32);
-            const uint64_t b_h = umma_desc_k_sw128(v_hi + k * 32), b_l = umma_desc_k_sw128(v_lo + k * 32);
-            umma_f16(tmem_O, a_h, b_l, idesc_o, (kt | k) != 0);
-            umma_f16(tmem_O, a_l, b_h, idesc_o, 1);
-            umma_f16(tmem_O, a_h, b_h, idesc_o, 1);
+            for (int k = 0; k < AT_BK / 16; ++k) {
+              const uint64_t a_h = umma_desc_k_sw128(p_hi + k * 32), a_l = umma_desc_k_sw128(p_lo + k * 32);
+              const uint64_t b_h = umma_desc_k_sw128(v_hi + k * 32), b_l = umma_desc_k_sw128(v_lo + k * 32);
+              umma_f16(d, a_h, b_l, idesc_o, (kt | k) != 0);
+              umma_f16(d, a_l, b_h, idesc_o, 1);
+              umma_f16(d, a_h, b_h, idesc_o, 1);
+            }
+            umma_commit(&bars->v_empty[vs]);
+            if (++vs == AT_VSTAGES) { vs = 0; vph ^= 1; }
           }
           umma_commit(&bars->p_empty[pb]);
-          umma_commit(&bars->v_empty[vs]);
-          if (++vs == AT_VSTAGES) { vs = 0; vph ^= 1; }
           if (++pb == 2) { pb = 0; pph ^= 1; }
         }
         umma_commit(&bars->o_full);
@@ -225,12 +238,17 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant
     }
   } else {
     // ================================ softmax + epilogue warps ================================
+    // Two warps per TMEM lane quarter: group g (warps 2-5 / 6-9) owns key columns [32g, 32g+32) of every
+    // 64-key tile and output channels [g*DVT/2, (g+1)*DVT/2) of the O tile.  Row max and row sum are
+    // exchanged through shared memory (named barrier 1 over the 256 softmax threads).
     const int quarter = warp & 3;
+    const int group = (warp - 2) >> 2;
     const int row = quarter * 32 + lane;                      // query row inside the tile = TMEM lane
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     int sb = 0, pb = 0;
     uint32_t sph = 0, pph = 0, oph = 0;
     bool out_of_range = false;
+    auto group_sync = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       const int dvt = item % p.dv_tiles;
       int t = item / p.dv_tiles;
@@ -239,45 +257,45 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant
       const int q_idx = qt * AT_BQ + row;
       const bool valid = q_idx < p.Pq;
 
-      // ---- pass 1: row maximum of S~ * scale (in log2 units)
+      // ---- pass 1: row maximum of S~ (this group's 32 key columns per tile)
       float m = -INFINITY;
       for (int kt = 0; kt < T; ++kt) {
         mbar_wait(&bars->s_full[sb], sph);
         tc_fence_after();
         uint32_t r[32];
+        tmem_ld_32x32(tmem_S + lane_addr + sb * AT_BK + group * 32, r);
+        tmem_ld_wait();
+        const int kbase = kt * AT_BK + group * 32;
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          tmem_ld_32x32(tmem_S + lane_addr + sb * AT_BK + half * 32, r);
-          tmem_ld_wait();
-          const int kbase = kt * AT_BK + half * 32;
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (kbase + j < p.Pk) m = fmaxf(m, __uint_as_float(r[j]));
-        }
+        for (int j = 0; j < 32; ++j)
+          if (kbase + j < p.Pk) m = fmaxf(m, __uint_as_float(r[j]));
         tc_fence_before();
         mbar_arrive(&bars->s_empty[sb]);
         if (++sb == 2) { sb = 0; sph ^= 1; }
       }
+      bars->xch[group][row] = m;
+      group_sync();
+      m = fmaxf(m, bars->xch[group ^ 1][row]);
+      group_sync();                                           // xch is reused for the row sums below
       const float m_scaled = m * p.scale_log2;
 
-      // ---- pass 2: probabilities -> shared memory (UMMA K-major, 128B swizzle), row sum
+      // ---- pass 2: probabilities -> shared memory (UMMA K-major, 128B swizzle), partial row sum
       float l = 0.f;
       for (int kt = 0; kt < T; ++kt) {
         mbar_wait(&bars->s_full[sb], sph);
         tc_fence_after();
-        float pr[AT_BK];
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
+        float pr[32];
+        {
           uint32_t r[32];
-          tmem_ld_32x32(tmem_S + lane_addr + sb * AT_BK + half * 32, r);
+          tmem_ld_32x32(tmem_S + lane_addr + sb * AT_BK + group * 32, r);
           tmem_ld_wait();
-          const int kbase = kt * AT_BK + half * 32;
+          const int kbase = kt * AT_BK + group * 32;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             float e = exp2f(fmaf(__uint_as_float(r[j]), p.scale_log2, -m_scaled));
             e = (kbase + j < p.Pk) ? e : 0.f;
             l += e;
-            pr[half * 32 + j] = e * AT_P_SCALE;
+            pr[j] = e * AT_P_SCALE;
           }
         }
         tc_fence_before();
@@ -288,11 +306,11 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant
         uint8_t* ph = sP + pb * 2 * AT_P_PLANE + row * 128;
         uint8_t* pl = ph + AT_P_PLANE;
 #pragma unroll
-        for (int c16 = 0; c16 < 8; ++c16) {
+        for (int c = 0; c < 4; ++c) {
           __half hi[8], lo[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) split_f32(pr[c16 * 8 + e], hi[e], lo[e]);
-          const int phys = (c16 ^ (row & 7)) << 4;
+          for (int e = 0; e < 8; ++e) split_f32(pr[c * 8 + e], hi[e], lo[e]);
+          const int phys = ((group * 4 + c) ^ (row & 7)) << 4;
           *reinterpret_cast<uint4*>(ph + phys) = *reinterpret_cast<const uint4*>(hi);
           *reinterpret_cast<uint4*>(pl + phys) = *reinterpret_cast<const uint4*>(lo);
         }
@@ -300,18 +318,24 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant
         mbar_arrive(&bars->p_full[pb]);
         if (++pb == 2) { pb = 0; pph ^= 1; }
       }
+      bars->xch[group][row] = l;
+      group_sync();
+      l += bars->xch[group ^ 1][row];
+      group_sync();
 
-      // ---- epilogue: out = O / (l * 2^10) + residual
+      // ---- epilogue: out = O / (l * 2^10) + residual; this group's half of the channel slice
       mbar_wait(&bars->o_full, oph);
       tc_fence_after();
       oph ^= 1;
       const float inv = 1.f / (l * AT_P_SCALE);
-      const long long obase = (long long)img * p.o_bs + (long long)q_idx * p.o_ld + dvt * AT_DV;
-      const long long rbase = (long long)img * p.r_bs + (long long)q_idx * p.r_ld + dvt * AT_DV;
+      constexpr int COLS = DVT / 2;
+      const int cbase = dvt * DVT + group * COLS;
+      const long long obase = (long long)img * p.o_bs + (long long)q_idx * p.o_ld + cbase;
+      const long long rbase = (long long)img * p.r_bs + (long long)q_idx * p.r_ld + cbase;
 #pragma unroll 1
-      for (int chunk = 0; chunk < AT_DV / 32; ++chunk) {
+      for (int chunk = 0; chunk < COLS / 32; ++chunk) {
         uint32_t r[32];
-        tmem_ld_32x32(tmem_O + lane_addr + chunk * 32, r);
+        tmem_ld_32x32(tmem_O + lane_addr + group * COLS + chunk * 32, r);
         tmem_ld_wait();
         if (valid) {
           float v[32];
@@ -382,7 +406,8 @@ int attention_tc(const tdn_attention_desc* d, cudaStream_t stream) {
   TDN_REQUIRE(d->q_hi && d->q_lo && d->k_hi && d->k_lo && d->vt_hi && d->vt_lo, TDN_ERR_INVALID,
               "attention_tc: null operand");
   TDN_REQUIRE(d->d_k == AT_DK, TDN_ERR_UNSUPPORTED, "attention_tc: d_k must be 64 (got %d)", d->d_k);
-  TDN_REQUIRE(d->d_v % AT_DV == 0, TDN_ERR_UNSUPPORTED, "attention_tc: d_v=%d must be a multiple of 128", d->d_v);
+  TDN_REQUIRE(d->d_v % AT_DVH == 0, TDN_ERR_UNSUPPORTED, "attention_tc: d_v=%d must be a multiple of 128", d->d_v);
+  const int dvt_size = (d->d_v % 256 == 0) ? 256 : 128;
   TDN_REQUIRE(d->n > 0 && d->pq > 0 && d->pk > 0, TDN_ERR_INVALID, "attention_tc: empty problem");
   TDN_REQUIRE(d->vt_ld % 8 == 0 && d->vt_ld >= ((d->pk + 63) / 64) * 64, TDN_ERR_INVALID,
               "attention_tc: V'^T row pitch must cover the keys padded to 64 (zero-filled) and be 16-byte aligned");
@@ -395,7 +420,7 @@ int attention_tc(const tdn_attention_desc* d, cudaStream_t stream) {
   memset(&p, 0, sizeof(p));
   p.n_img = d->n; p.Pq = d->pq; p.Pk = d->pk;
   p.q_tiles = ceil_div(d->pq, AT_BQ);
-  p.dv_tiles = d->d_v / AT_DV;
+  p.dv_tiles = d->d_v / dvt_size;
   p.k_tiles = ceil_div(d->pk, AT_BK);
   long long items = (long long)d->n * p.q_tiles * p.dv_tiles;
   TDN_REQUIRE(items < (1ll << 31), TDN_ERR_UNSUPPORTED, "attention_tc: too many work items");
@@ -449,13 +474,14 @@ int attention_tc(const tdn_attention_desc* d, cudaStream_t stream) {
     // columns (zeros written by the producer) are read rather than treated as out of bounds.
     cuuint64_t dims[3] = {(cuuint64_t)(((d->pk + 63) / 64) * 64), (cuuint64_t)d->d_v, (cuuint64_t)d->n};
     cuuint64_t str[2] = {(cuuint64_t)d->vt_ld * 2, (cuuint64_t)(d->n > 1 ? d->vt_batch_stride : d->vt_ld * (long long)d->d_v) * 2};
-    cuuint32_t box[3] = {(cuuint32_t)AT_BK, (cuuint32_t)AT_DV, 1};
+    cuuint32_t box[3] = {(cuuint32_t)AT_BK, (cuuint32_t)AT_DVH, 1};
     if ((rc = encode_map_f16(&mv_h, d->vt_hi, 3, dims, str, box, "Vt.hi"))) return rc;
     if ((rc = encode_map_f16(&mv_l, d->vt_lo, 3, dims, str, box, "Vt.lo"))) return rc;
   }
   static bool attr_set = false;
   if (!attr_set) {
-    TDN_CUDA_OK(cudaFuncSetAttribute(tc_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES));
+    TDN_CUDA_OK(cudaFuncSetAttribute(tc_attn_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES));
+    TDN_CUDA_OK(cudaFuncSetAttribute(tc_attn_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES));
     attr_set = true;
   }
   static int num_sms = 0;
@@ -465,7 +491,10 @@ int attention_tc(const tdn_attention_desc* d, cudaStream_t stream) {
     TDN_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   int grid = p.num_items < num_sms ? p.num_items : num_sms;
-  tc_attn_kernel<<<grid, AT_THREADS, AT_SMEM_BYTES, stream>>>(mq_h, mq_l, mk_h, mk_l, mv_h, mv_l, p);
+  if (dvt_size == 256)
+    tc_attn_kernel<256><<<grid, AT_THREADS, AT_SMEM_BYTES, stream>>>(mq_h, mq_l, mk_h, mk_l, mv_h, mv_l, p);
+  else
+    tc_attn_kernel<128><<<grid, AT_THREADS, AT_SMEM_BYTES, stream>>>(mq_h, mq_l, mk_h, mk_l, mv_h, mv_l, p);
   TDN_LAUNCH_OK();
   return TDN_OK;
 }

@@ -167,6 +167,37 @@ def experiment(name):
         flop = 2 * 128 * 256 * 512 * 512 * 9
         st.update(ms=ms, algorithmic_tflops=flop / ms / 1e9, executed_tflops=3 * flop / ms / 1e9)
         return st
+    if name == "layer4_sustained":
+        # same conv, 300 launches back to back over 4 rotating input/output sets (268 MB each > L2 share):
+        # separates the power/clock and L2-residency effects from the single-launch number
+        from tdnet_b200 import _cabi as cabi
+        lib = cabi.load()
+        w = torch.randn(512, 3, 3, 512, device=dev) / 68
+        wh, wl = split(w.reshape(512, -1))
+        descs, keep = [], []
+        for i in range(4):
+            x = torch.randn(1, 128, 256, 512, device=dev).relu()
+            xh, xl = split(x)
+            oh_, ol_ = torch.empty_like(xh), torch.empty_like(xh)
+            d = cabi.TcConvDesc()
+            d.in_ = tensor(cabi, xh, xl, 1, 128, 256, 512)
+            d.out = tensor(cabi, oh_, ol_, 1, 128, 256, 512)
+            d.weight_hi, d.weight_lo, d.weight_ld = wh.data_ptr(), wl.data_ptr(), 4608
+            d.cout, d.kh, d.kw, d.dilation = 512, 3, 3, 4
+            descs.append(d); keep += [xh, xl, oh_, ol_]
+        for d in descs:
+            cabi.check(lib.tdn_conv2d_tc(C.byref(d), None))
+        torch.cuda.synchronize()
+        res = {}
+        for reps in (8, 300):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for r in range(reps):
+                lib.tdn_conv2d_tc(C.byref(descs[r % 4]), None)
+            e1.record()
+            torch.cuda.synchronize()
+            res[f"ms_per_launch_{reps}"] = e0.elapsed_time(e1) / reps
+        return res
     if name == "layer1_perf":
         x = torch.randn(1, 256, 512, 64, device=dev).relu()
         w = torch.randn(64, 3, 3, 64, device=dev) / 24
@@ -247,10 +278,9 @@ def attention_experiment(name):
 
 
 EXPERIMENTS = ["layout_debug", "gemm_k512_ragged", "conv3x3_d8_97x193", "epilogue", "accum_bias_positive",
-               "layer1_perf", "layer4_perf", "attention_small", "attention_ragged", "attention_big"]
+               "layer1_perf", "layer4_perf", "layer4_sustained", "attention_small", "attention_ragged", "attention_big"]
 # (experiment, TDNET_TC_CHUNK_KB) pairs run after the default set
-CHUNK_SWEEP = [("layer4_perf", 1), ("layer4_perf", 4), ("layer4_perf", 100000), ("accum_bias_positive", 1),
-               ("accum_bias_positive", 4)]
+CHUNK_SWEEP = [("layer4_perf", 2), ("layer4_perf", 8), ("layer4_perf", 100000), ("accum_bias_positive", 8)]
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "--one":
