@@ -104,8 +104,8 @@ int tdn_conv2d(const tdn_conv2d_desc* desc, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * tdn_conv2d_tc: the tcgen05 (5th-gen tensor core) implementation of the same operator for the
- * shapes that dominate the frame: stride-1 "same" convolutions (1x1 / 3x3, any dilation) and plain
- * GEMMs with cin %% 64 == 0, on SPLIT16 operands.  fp32-faithful: three fp16 tensor-core products per
+ * shapes that dominate the frame: "same"-padded convolutions (1x1 / 3x3, any dilation, stride 1 or 2) and
+ * plain GEMMs with cin %% 64 == 0, on SPLIT16 operands.  fp32-faithful: three fp16 tensor-core products per
  * K step (hi*lo, lo*hi, hi*hi) accumulate into one fp32 TMEM accumulator ("exact mode").
  * Same call sites as tdn_conv2d; additionally transformer.py:128,137 (q k^T, attn v) where the
  * "weight" operand is itself an activation (weight_batched = 1: one [cout][K] matrix per image).
@@ -136,6 +136,7 @@ typedef struct tdn_tc_conv_desc {
   int32_t act;
   float leaky_slope;
   int32_t* range_flag;
+  int32_t stride; /* 0 or 1: stride 1; 2: stride-2 conv (TMA element strides), out = ceil(in / 2) */
 } tdn_tc_conv_desc;
 
 int tdn_conv2d_tc(const tdn_tc_conv_desc* desc, void* stream);
@@ -179,6 +180,12 @@ int tdn_merge16(const tdn_tensor* in_split16, const tdn_tensor* out_f32, void* s
  * out.c (4), the layout every later kernel reads.  Replaces nothing numeric; it is the layout edge. */
 int tdn_image_to_nhwc(const float* nchw, int32_t n, int32_t c, int32_t h, int32_t w,
                       const tdn_tensor* out, void* stream);
+
+/* Fused ResNet-18/34 stem (resnet.py:133-137,205-208): conv 7x7 stride 2 pad 3 (3->64) + folded BatchNorm +
+ * ReLU + max_pool2d(3, 2, 1), from the caller's NCHW fp32 image [n,3,h,w] straight to the pooled NHWC map
+ * `out` [n, Hp, Wp, 64] (F32 or SPLIT16).  weight is fp32 [147][64] with k = (c*7 + ky)*7 + kx. */
+int tdn_stem_conv_pool(const float* nchw, int32_t n, int32_t h, int32_t w, const float* weight,
+                       const float* scale, const float* bias, const tdn_tensor* out, void* stream);
 
 /* F.max_pool2d(kernel 3, stride 2, padding 1) of the stem (resnet.py:137,208), NHWC fp32. */
 int tdn_maxpool3x3s2(const tdn_tensor* in, const tdn_tensor* out, void* stream);

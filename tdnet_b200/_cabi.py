@@ -39,7 +39,8 @@ class TcConvDesc(C.Structure):
                 ("weight_batched", C.c_int32), ("bias_along_m", C.c_int32),
                 ("scale", C.c_void_p), ("bias", C.c_void_p),
                 ("cout", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32), ("dilation", C.c_int32),
-                ("act", C.c_int32), ("leaky_slope", C.c_float), ("range_flag", C.c_void_p)]
+                ("act", C.c_int32), ("leaky_slope", C.c_float), ("range_flag", C.c_void_p),
+                ("stride", C.c_int32)]
 
 
 class AttentionDesc(C.Structure):
@@ -64,6 +65,8 @@ SIGNATURES = {
     "tdn_split16": (C.c_int, [_TP, _TP, C.c_void_p]),
     "tdn_merge16": (C.c_int, [_TP, _TP, C.c_void_p]),
     "tdn_image_to_nhwc": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _TP, C.c_void_p]),
+    "tdn_stem_conv_pool": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     _TP, C.c_void_p]),
     "tdn_maxpool3x3s2": (C.c_int, [_TP, _TP, C.c_void_p]),
     "tdn_psp_pool": (C.c_int, [_TP, _TP, C.c_void_p, C.c_uint64, C.c_void_p]),
     "tdn_psp_pool_workspace_bytes": (C.c_uint64, [C.c_int32, C.c_int32, C.c_int32]),

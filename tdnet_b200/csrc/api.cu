@@ -45,6 +45,7 @@ int layernorm_hw_apply(const tdn_tensor*, const float*, const float*, const floa
                        const tdn_tensor*, cudaStream_t);
 int upsample_logits(const tdn_tensor*, float*, int, int, cudaStream_t);
 int conv2d_tc(const tdn_tc_conv_desc*, cudaStream_t);
+int stem_conv_pool(const float*, int, int, int, const float*, const float*, const float*, const tdn_tensor*, cudaStream_t);
 int attention_tc(const tdn_attention_desc*, cudaStream_t);
 int split16(const tdn_tensor*, const tdn_tensor*, cudaStream_t);
 int merge16(const tdn_tensor*, const tdn_tensor*, cudaStream_t);
@@ -119,6 +120,11 @@ int tdn_merge16(const tdn_tensor* in, const tdn_tensor* out, void* stream) {
 int tdn_image_to_nhwc(const float* nchw, int32_t n, int32_t c, int32_t h, int32_t w, const tdn_tensor* out,
                       void* stream) {
   return image_to_nhwc(nchw, n, c, h, w, out, (cudaStream_t)stream);
+}
+
+int tdn_stem_conv_pool(const float* nchw, int32_t n, int32_t h, int32_t w, const float* weight, const float* scale,
+                       const float* bias, const tdn_tensor* out, void* stream) {
+  return stem_conv_pool(nchw, n, h, w, weight, scale, bias, out, (cudaStream_t)stream);
 }
 
 int tdn_maxpool3x3s2(const tdn_tensor* in, const tdn_tensor* out, void* stream) {

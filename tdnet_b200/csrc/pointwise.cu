@@ -102,15 +102,28 @@ __global__ void psp_rowsum_kernel(View in, float* __restrict__ rowsum) {
   const int lv_off[4] = {0, 1, 3, 6};
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   int cur[4] = {0, 0, 0, 0};
-  for (int x = 0; x < W; ++x) {
-    const float v = ld1(in, row + x * in.sw);
+  int nend[4];
 #pragma unroll
-    for (int l = 0; l < 4; ++l) {
-      acc[l] += v;
-      if (x + 1 == bin_end(cur[l], lv_o[l], W)) {
-        dst[(long long)(lv_off[l] + cur[l]) * in.c] = acc[l];
-        ++cur[l];
-        acc[l] = (cur[l] < lv_o[l] && bin_start(cur[l], lv_o[l], W) <= x) ? v : 0.f;
+  for (int l = 0; l < 4; ++l) nend[l] = bin_end(0, lv_o[l], W);
+  constexpr int UN = 8;   // loads issued ahead of the (serial) range bookkeeping
+  for (int x0 = 0; x0 < W; x0 += UN) {
+    float vbuf[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) vbuf[u] = (x0 + u < W) ? ld1(in, row + (long long)(x0 + u) * in.sw) : 0.f;
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int x = x0 + u;
+      if (x >= W) break;
+      const float v = vbuf[u];
+#pragma unroll
+      for (int l = 0; l < 4; ++l) {
+        acc[l] += v;
+        if (x + 1 == nend[l]) {
+          dst[(long long)(lv_off[l] + cur[l]) * in.c] = acc[l];
+          ++cur[l];
+          nend[l] = bin_end(cur[l], lv_o[l], W);
+          acc[l] = (cur[l] < lv_o[l] && bin_start(cur[l], lv_o[l], W) <= x) ? v : 0.f;
+        }
       }
     }
   }

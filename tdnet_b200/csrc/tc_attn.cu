@@ -400,7 +400,8 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant
 
 // ------------------------------------------------------------------------------------------------
 int encode_map_f16(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims,
-                   const cuuint64_t* strides_bytes, const cuuint32_t* box, const char* what);
+                   const cuuint64_t* strides_bytes, const cuuint32_t* box, const char* what,
+                   const cuuint32_t* elem_strides);
 
 int attention_tc(const tdn_attention_desc* d, cudaStream_t stream) {
   TDN_REQUIRE(d->q_hi && d->q_lo && d->k_hi && d->k_lo && d->vt_hi && d->vt_lo, TDN_ERR_INVALID,
@@ -459,15 +460,15 @@ int attention_tc(const tdn_attention_desc* d, cudaStream_t stream) {
     cuuint64_t dims[3] = {(cuuint64_t)AT_DK, (cuuint64_t)d->pq, (cuuint64_t)d->n};
     cuuint64_t str[2] = {(cuuint64_t)d->q_ld * 2, (cuuint64_t)(d->n > 1 ? d->q_batch_stride : d->q_ld * (long long)d->pq) * 2};
     cuuint32_t box[3] = {(cuuint32_t)AT_DK, (cuuint32_t)AT_BQ, 1};
-    if ((rc = encode_map_f16(&mq_h, d->q_hi, 3, dims, str, box, "Q.hi"))) return rc;
-    if ((rc = encode_map_f16(&mq_l, d->q_lo, 3, dims, str, box, "Q.lo"))) return rc;
+    if ((rc = encode_map_f16(&mq_h, d->q_hi, 3, dims, str, box, "Q.hi", nullptr))) return rc;
+    if ((rc = encode_map_f16(&mq_l, d->q_lo, 3, dims, str, box, "Q.lo", nullptr))) return rc;
   }
   {
     cuuint64_t dims[3] = {(cuuint64_t)AT_DK, (cuuint64_t)d->pk, (cuuint64_t)d->n};
     cuuint64_t str[2] = {(cuuint64_t)d->k_ld * 2, (cuuint64_t)(d->n > 1 ? d->k_batch_stride : d->k_ld * (long long)d->pk) * 2};
     cuuint32_t box[3] = {(cuuint32_t)AT_DK, (cuuint32_t)AT_BK, 1};
-    if ((rc = encode_map_f16(&mk_h, d->k_hi, 3, dims, str, box, "K.hi"))) return rc;
-    if ((rc = encode_map_f16(&mk_l, d->k_lo, 3, dims, str, box, "K.lo"))) return rc;
+    if ((rc = encode_map_f16(&mk_h, d->k_hi, 3, dims, str, box, "K.hi", nullptr))) return rc;
+    if ((rc = encode_map_f16(&mk_l, d->k_lo, 3, dims, str, box, "K.lo", nullptr))) return rc;
   }
   {
     // V'^T: [d_v rows][keys], keys contiguous; the key extent is the padded pitch so that the pad
@@ -475,8 +476,8 @@ int attention_tc(const tdn_attention_desc* d, cudaStream_t stream) {
     cuuint64_t dims[3] = {(cuuint64_t)(((d->pk + 63) / 64) * 64), (cuuint64_t)d->d_v, (cuuint64_t)d->n};
     cuuint64_t str[2] = {(cuuint64_t)d->vt_ld * 2, (cuuint64_t)(d->n > 1 ? d->vt_batch_stride : d->vt_ld * (long long)d->d_v) * 2};
     cuuint32_t box[3] = {(cuuint32_t)AT_BK, (cuuint32_t)AT_DVH, 1};
-    if ((rc = encode_map_f16(&mv_h, d->vt_hi, 3, dims, str, box, "Vt.hi"))) return rc;
-    if ((rc = encode_map_f16(&mv_l, d->vt_lo, 3, dims, str, box, "Vt.lo"))) return rc;
+    if ((rc = encode_map_f16(&mv_h, d->vt_hi, 3, dims, str, box, "Vt.hi", nullptr))) return rc;
+    if ((rc = encode_map_f16(&mv_l, d->vt_lo, 3, dims, str, box, "Vt.lo", nullptr))) return rc;
   }
   static bool attr_set = false;
   if (!attr_set) {

@@ -43,7 +43,7 @@ struct TcParams {
   int n_img, Ho, Wo;
   int tiles_h, tiles_w, BH, BW;
   int Cout, Cin;
-  int taps_h, taps_w, dil;
+  int taps_h, taps_w, dil, conv_stride;
   int n_tiles_n, num_tiles;
   int chunk_kb;          // K blocks accumulated inside TMEM before the fp32 register accumulation
   int w_batched;
@@ -144,8 +144,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           const int kc = kb - tap * kc_per_tap;
           const int ky = tap / p.taps_w;
           const int kx = tap - ky * p.taps_w;
-          const int x0 = tx * p.BW + (kx - (p.taps_w - 1) / 2) * p.dil;
-          const int y0 = ty * p.BH + (ky - (p.taps_h - 1) / 2) * p.dil;
+          // top-left input pixel of the tap's box; with conv_stride 2 the tensor map picks every second
+          // pixel (TMA elementStrides), so the box still lands as BH x BW pixel rows in shared memory
+          const int x0 = tx * p.BW * p.conv_stride + (kx - (p.taps_w - 1) / 2) * p.dil;
+          const int y0 = ty * p.BH * p.conv_stride + (ky - (p.taps_h - 1) / 2) * p.dil;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + 2 * TC_A_PLANE;
@@ -368,10 +370,13 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 int encode_map_f16(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims,
-                   const cuuint64_t* strides_bytes, const cuuint32_t* box, const char* what) {
+                   const cuuint64_t* strides_bytes, const cuuint32_t* box, const char* what,
+                   const cuuint32_t* elem_strides) {
   EncodeTiledFn fn = get_encode_fn();
   TDN_REQUIRE(fn != nullptr, TDN_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  if (elem_strides)
+    for (int i = 0; i < rank; ++i) estr[i] = elem_strides[i];
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -420,8 +425,10 @@ int conv2d_tc(const tdn_tc_conv_desc* d, cudaStream_t stream) {
   TDN_REQUIRE(d->weight_hi && d->weight_lo, TDN_ERR_INVALID, "conv2d_tc: null weights");
   TDN_REQUIRE(in.c % TC_BLOCK_K == 0, TDN_ERR_UNSUPPORTED, "conv2d_tc: cin=%d must be a multiple of 64", in.c);
   TDN_REQUIRE(d->kh % 2 == 1 && d->kw % 2 == 1 && d->kh * d->kw <= 49, TDN_ERR_UNSUPPORTED, "conv2d_tc: odd kernels only");
-  TDN_REQUIRE(out.n == in.n && out.h == in.h && out.w == in.w && out.c == d->cout, TDN_ERR_INVALID,
-              "conv2d_tc: stride-1 'same' convolution expects out dims == in dims");
+  const int cs = d->stride <= 1 ? 1 : d->stride;
+  TDN_REQUIRE(cs == 1 || cs == 2, TDN_ERR_UNSUPPORTED, "conv2d_tc: stride must be 1 or 2");
+  TDN_REQUIRE(out.n == in.n && out.h == (in.h - 1) / cs + 1 && out.w == (in.w - 1) / cs + 1 && out.c == d->cout,
+              TDN_ERR_INVALID, "conv2d_tc: 'same'-padded convolution expects out dims == ceil(in dims / stride)");
   TDN_REQUIRE(aligned16(in.data) && aligned16(in.data_lo) && in.stride_w % 8 == 0 && in.stride_h % 8 == 0 &&
                   in.stride_n % 8 == 0, TDN_ERR_INVALID, "conv2d_tc: input planes must be 16-byte aligned");
   TDN_REQUIRE((!d->scale || aligned16(d->scale)) && (!d->bias || aligned16(d->bias)), TDN_ERR_INVALID,
@@ -435,10 +442,11 @@ int conv2d_tc(const tdn_tc_conv_desc* d, cudaStream_t stream) {
 
   TcParams p;
   memset(&p, 0, sizeof(p));
-  p.n_img = in.n; p.Ho = in.h; p.Wo = in.w;
-  pick_tile(in.h, in.w, &p.BH, &p.BW);
-  p.tiles_h = ceil_div(in.h, p.BH);
-  p.tiles_w = ceil_div(in.w, p.BW);
+  p.n_img = in.n; p.Ho = out.h; p.Wo = out.w;
+  pick_tile(out.h, out.w, &p.BH, &p.BW);
+  p.tiles_h = ceil_div(out.h, p.BH);
+  p.tiles_w = ceil_div(out.w, p.BW);
+  p.conv_stride = cs;
   p.Cout = d->cout; p.Cin = in.c;
   p.taps_h = d->kh; p.taps_w = d->kw; p.dil = d->dilation;
   const int block_n = d->cout <= 64 ? 64 : 128;
@@ -497,10 +505,13 @@ int conv2d_tc(const tdn_tc_conv_desc* d, cudaStream_t stream) {
   {
     cuuint64_t dims[4] = {(cuuint64_t)in.c, (cuuint64_t)in.w, (cuuint64_t)in.h, (cuuint64_t)in.n};
     cuuint64_t str[3] = {(cuuint64_t)in.stride_w * 2, (cuuint64_t)in.stride_h * 2, (cuuint64_t)in.stride_n * 2};
-    cuuint32_t box[4] = {(cuuint32_t)TC_BLOCK_K, (cuuint32_t)p.BW, (cuuint32_t)p.BH, 1};
+    // box extents are in source pixels; elementStrides picks every cs-th one, so BW*cs x BH*cs source
+    // pixels deliver BW x BH rows of 128 bytes
+    cuuint32_t box[4] = {(cuuint32_t)TC_BLOCK_K, (cuuint32_t)(p.BW * cs), (cuuint32_t)(p.BH * cs), 1};
+    cuuint32_t est[4] = {1, (cuuint32_t)cs, (cuuint32_t)cs, 1};
     int rc;
-    if ((rc = encode_map_f16(&a_hi, in.data, 4, dims, str, box, "A.hi"))) return rc;
-    if ((rc = encode_map_f16(&a_lo, in.data_lo, 4, dims, str, box, "A.lo"))) return rc;
+    if ((rc = encode_map_f16(&a_hi, in.data, 4, dims, str, box, "A.hi", est))) return rc;
+    if ((rc = encode_map_f16(&a_lo, in.data_lo, 4, dims, str, box, "A.lo", est))) return rc;
   }
   {
     const int nb = d->weight_batched ? in.n : 1;
@@ -510,8 +521,8 @@ int conv2d_tc(const tdn_tc_conv_desc* d, cudaStream_t stream) {
     cuuint64_t str[2] = {(cuuint64_t)d->weight_ld * 2, bstride};
     cuuint32_t box[3] = {(cuuint32_t)TC_BLOCK_K, (cuuint32_t)block_n, 1};
     int rc;
-    if ((rc = encode_map_f16(&b_hi, d->weight_hi, 3, dims, str, box, "B.hi"))) return rc;
-    if ((rc = encode_map_f16(&b_lo, d->weight_lo, 3, dims, str, box, "B.lo"))) return rc;
+    if ((rc = encode_map_f16(&b_hi, d->weight_hi, 3, dims, str, box, "B.hi", nullptr))) return rc;
+    if ((rc = encode_map_f16(&b_lo, d->weight_lo, 3, dims, str, box, "B.lo", nullptr))) return rc;
   }
   if (block_n == 64) return launch_tc<64>(a_hi, a_lo, b_hi, b_lo, p, stream);
   return launch_tc<128>(a_hi, a_lo, b_hi, b_lo, p, stream);

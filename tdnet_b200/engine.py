@@ -195,6 +195,8 @@ class Engine:
         self.tc = mode == "tc"
         import os
         self.fused_attn = os.environ.get("TDNET_B200_FUSED_ATTN", "1") != "0"
+        self.tc_stride2 = os.environ.get("TDNET_B200_TC_STRIDE2", "1") != "0"
+        self.fused_stem = os.environ.get("TDNET_B200_FUSED_STEM", "1") != "0"
         self.m, self.n, self.H, self.W, self.device = arch, n, H, W, device
         self.h8, self.w8 = A.feature_hw(H, W)
         if tuple(ln_shape) != (self.h8, self.w8):
@@ -230,6 +232,16 @@ class Engine:
             self._packed[key] = PackedConv(spec, self.sd, self.device, row_slice)
         return self._packed[key]
 
+    def stem_packed(self, spec: A.Conv):
+        """7x7x3 stem weights as [147][64] (k = (c*7+ky)*7+kx) + folded BN, for tdn_stem_conv_pool."""
+        key = "stem:" + spec.name
+        if key not in self._packed:
+            pc = self.packed(spec)
+            w = self.sd[spec.name + ".weight"].detach().float()          # [64,3,7,7]
+            wk = w.permute(1, 2, 3, 0).reshape(147, 64).contiguous().to(self.device)
+            self._packed[key] = dict(w=wk, scale=pc.scale, bias=pc.bias)
+        return self._packed[key]
+
     def const_vec(self, value: float, length: int) -> torch.Tensor:
         key = (value, length)
         if key not in self._consts:
@@ -261,8 +273,8 @@ class Engine:
         the geometry fits it (stride 1, cin % 64 == 0, SPLIT16 input); the fp32 CUDA-core kernel otherwise
         (3-channel stem, stride-2 convs, pooled PSP convs, the 19-class classifier)."""
         spec = pc.spec if pc is not None else None
-        if (self.tc and spec is not None and not kw and spec.stride == 1 and x.split and x.c % 64 == 0
-                and x.n * x.h * x.w >= 64 and out.sw % (8 if out.split else 4) == 0 and pc.cout % 8 == 0):
+        if (self.tc and spec is not None and not kw and spec.stride in (1, 2) and x.split and x.c % 64 == 0
+                and (spec.stride == 1 or self.tc_stride2) and x.n * x.h * x.w >= 64 and out.sw % (8 if out.split else 4) == 0 and pc.cout % 8 == 0):
             return self._conv_tc(plan, x, out, pc=pc, residual=residual)
         return self._conv_simt(plan, pc, x, out, residual, **kw)
 
@@ -280,6 +292,12 @@ class Engine:
             d.bias = pc.bias.data_ptr() if pc.bias is not None else None
             d.cout, d.kh, d.kw, d.dilation = pc.cout, pc.spec.k, pc.spec.k, pc.spec.dilation
             d.act = _ACT[pc.spec.act]
+            if pc.spec.stride == 2:
+                if pc.spec.k == 1:
+                    # a strided 1x1 conv is a 1x1 conv on the stride-2 view of its input (no TMA striding needed)
+                    d.in_ = x.subsample(2).ct()
+                else:
+                    d.stride = 2
             name = pc.spec.name
         else:
             d.weight_hi, d.weight_lo, d.weight_ld = w_hi, w_lo, w_ld
@@ -339,18 +357,28 @@ class Engine:
         self._cursor = {}
         H, W, h8, w8 = self.H, self.W, self.h8, self.w8
 
-        # --- stem: NCHW image -> NHWC(4) -> conv(s) -> maxpool
-        img = self.buf(n, H, W, 4, split=False)
-        plan.add(lib.tdn_image_to_nhwc, "img", n, 3, H, W, C.byref(self._ct(plan, img)), "stream")
-        x = img
-        for c in m.stems[path]:
-            oh, ow = self._out_hw(x.h, x.w, c)
-            y = self.buf(n, oh, ow, c.cout)
-            self._conv(plan, self.packed(c), x, y)
+        # --- stem
+        if len(m.stems[path]) == 1 and self.fused_stem:
+            # ResNet-18/34: conv7x7 s2 + BN + ReLU + maxpool in one kernel, straight from the NCHW image
+            c = m.stems[path][0]
+            pk = self.stem_packed(c)
+            hc, wc = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+            x = self.buf(n, (hc - 1) // 2 + 1, (wc - 1) // 2 + 1, c.cout)
+            plan.add(lib.tdn_stem_conv_pool, "img", n, H, W, pk["w"].data_ptr(), pk["scale"].data_ptr(),
+                     pk["bias"].data_ptr(), C.byref(self._ct(plan, x)), "stream", name=c.name)
+        else:
+            # deep stem (ResNet-50) or unfused path: NCHW image -> NHWC(4) -> conv(s) -> maxpool
+            img = self.buf(n, H, W, 4, split=False)
+            plan.add(lib.tdn_image_to_nhwc, "img", n, 3, H, W, C.byref(self._ct(plan, img)), "stream")
+            x = img
+            for c in m.stems[path]:
+                oh, ow = self._out_hw(x.h, x.w, c)
+                y = self.buf(n, oh, ow, c.cout)
+                self._conv(plan, self.packed(c), x, y)
+                x = y
+            y = self.buf(n, (x.h - 1) // 2 + 1, (x.w - 1) // 2 + 1, x.c)
+            plan.add(lib.tdn_maxpool3x3s2, C.byref(self._ct(plan, x)), C.byref(self._ct(plan, y)), "stream")
             x = y
-        y = self.buf(n, (x.h - 1) // 2 + 1, (x.w - 1) // 2 + 1, x.c)
-        plan.add(lib.tdn_maxpool3x3s2, C.byref(self._ct(plan, x)), C.byref(self._ct(plan, y)), "stream")
-        x = y
 
         # --- residual stages
         for blk in m.stages[path]:

@@ -405,3 +405,50 @@ def test_fused_attention_tc(env, n, pq, pk, dv):
     # the O accumulator chains up to 12 * ceil(pk / 64) tensor-core adds (truncating), hence the looser bound
     assert max_abs(out.cpu(), ref) < 1.5e-5 * float(ref.abs().max())
     assert float((out.cpu().double() - ref).norm() / ref.norm()) < 5e-6
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,k", [(1, 64, 96, 64, 128, 3), (2, 25, 41, 64, 128, 3), (1, 193, 385, 64, 64, 3),
+                                               (1, 25, 41, 128, 256, 1)])
+def test_tc_conv_stride2(env, n, h, w, cin, cout, k):
+    """Stride-2 'same'-padded conv on the tensor cores (layer2.0.conv1 / downsample, resnet.py:170-178):
+    TMA element strides pick every second pixel; odd map sizes exercise the zero fill."""
+    lib, cabi, View, dev = env
+    g = torch.Generator().manual_seed(h * w + cout)
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5
+    xs = View.alloc(n, h, w, cin, dev, split=True)
+    hi, lo = split_planes(nhwc(x))
+    xs.base.copy_(hi.view(-1)); xs.lo.copy_(lo.view(-1))
+    wh, wl = split_planes(wt.permute(0, 2, 3, 1).reshape(cout, -1).cuda())
+    oh, ow = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    out = View.alloc(n, oh, ow, cout, dev)
+    d = cabi.TcConvDesc()
+    d.in_, d.out = (xs.subsample(2).ct() if k == 1 else xs.ct()), out.ct()
+    d.weight_hi, d.weight_lo, d.weight_ld = wh.data_ptr(), wl.data_ptr(), k * k * cin
+    d.cout, d.kh, d.kw, d.dilation, d.stride = cout, k, k, 1, (0 if k == 1 else 2)
+    cabi.check(lib.tdn_conv2d_tc(C.byref(d), None), "conv2d_tc")
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.double(), wt.double(), None, 2, (k - 1) // 2, 1)
+    got = out.torch().permute(0, 3, 1, 2).cpu()
+    assert got.shape == ref.shape
+    assert max_abs(got, ref) < 2e-6 * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("h,w,split", [(64, 96, False), (97, 161, True), (130, 70, True)])
+def test_fused_stem_conv_bn_relu_maxpool(env, h, w, split):
+    """tdn_stem_conv_pool vs conv2d(7,2,3) -> BN(eval) -> ReLU -> max_pool2d(3,2,1) (resnet.py:205-208)."""
+    lib, cabi, View, dev = env
+    g = torch.Generator().manual_seed(h + w)
+    img = torch.randn(2, 3, h, w, generator=g)
+    wt = torch.randn(64, 3, 7, 7, generator=g) / 12
+    sc, bi = torch.rand(64, generator=g) + 0.5, torch.randn(64, generator=g) * 0.3
+    ref = F.max_pool2d(F.relu(F.conv2d(img, wt, None, 2, 3) * sc.view(1, -1, 1, 1) + bi.view(1, -1, 1, 1)), 3, 2, 1)
+    hp, wp = ref.shape[2:]
+    out = View.alloc(2, hp, wp, 64, dev, split=split)
+    imgd, wk = img.cuda(), wt.permute(1, 2, 3, 0).reshape(147, 64).contiguous().cuda()
+    scd, bid = sc.cuda(), bi.cuda()
+    t = out.ct()
+    cabi.check(lib.tdn_stem_conv_pool(imgd.data_ptr(), 2, h, w, wk.data_ptr(), scd.data_ptr(), bid.data_ptr(),
+                                      C.byref(t), None), "stem")
+    torch.cuda.synchronize()
+    assert max_abs(out.torch().permute(0, 3, 1, 2).cpu(), ref) < 1e-5
