@@ -49,6 +49,14 @@ constexpr int AT_SMEM_DATA = 2 * AT_Q_PLANE + AT_KSTAGES * 2 * AT_K_PLANE + AT_V
 constexpr int AT_TMEM_COLS = 512;   // S: 2 x 64 columns, O: up to 256 columns
 constexpr float AT_P_SCALE = 1024.f;
 
+// 2^x through one MUFU.EX2 (2 ulp; results below the normal range flush to zero, which is what a
+// probability that small should do).  The libm exp2f spends ~6 more instructions on range handling.
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 struct AttnParams {
   int n_img, Pq, Pk;
   int q_tiles, dv_tiles, k_tiles, num_items;
@@ -292,7 +300,7 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant
           const int kbase = kt * AT_BK + group * 32;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            float e = exp2f(fmaf(__uint_as_float(r[j]), p.scale_log2, -m_scaled));
+            float e = fast_exp2(fmaf(__uint_as_float(r[j]), p.scale_log2, -m_scaled));
             e = (kbase + j < p.Pk) ? e : 0.f;
             l += e;
             pr[j] = e * AT_P_SCALE;
@@ -307,9 +315,9 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant
         uint8_t* pl = ph + AT_P_PLANE;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          __half hi[8], lo[8];
+          __half2 hi[4], lo[4];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) split_f32(pr[c * 8 + e], hi[e], lo[e]);
+          for (int e = 0; e < 4; ++e) split_f32x2(pr[c * 8 + 2 * e], pr[c * 8 + 2 * e + 1], hi[e], lo[e]);
           const int phys = ((group * 4 + c) ^ (row & 7)) << 4;
           *reinterpret_cast<uint4*>(ph + phys) = *reinterpret_cast<const uint4*>(hi);
           *reinterpret_cast<uint4*>(pl + phys) = *reinterpret_cast<const uint4*>(lo);
@@ -370,16 +378,16 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant
                   make_float4(v[q * 4 + 0], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
           }
           if (p.out_hi) {
-            __half hi[32], lo[32];
+            __half2 hi[16], lo[16];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              out_of_range |= fabsf(v[j]) > 60000.f;
-              split_f32(v[j], hi[j], lo[j]);
+            for (int j = 0; j < 16; ++j) {
+              out_of_range |= fmaxf(fabsf(v[2 * j]), fabsf(v[2 * j + 1])) > 60000.f;
+              split_f32x2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              *reinterpret_cast<uint4*>(p.out_hi + obase + c0 + q * 8) = *reinterpret_cast<const uint4*>(&hi[q * 8]);
-              *reinterpret_cast<uint4*>(p.out_lo + obase + c0 + q * 8) = *reinterpret_cast<const uint4*>(&lo[q * 8]);
+              *reinterpret_cast<uint4*>(p.out_hi + obase + c0 + q * 8) = *reinterpret_cast<const uint4*>(&hi[q * 4]);
+              *reinterpret_cast<uint4*>(p.out_lo + obase + c0 + q * 8) = *reinterpret_cast<const uint4*>(&lo[q * 4]);
             }
           }
         }

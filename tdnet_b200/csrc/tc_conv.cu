@@ -316,13 +316,14 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             }
           }
           if (p.out_hi) {
-            __half hi[32], lo[32];
+            __half2 hi2[16], lo2[16];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              out_of_range |= fabsf(v[j]) > 60000.f;
-              hi[j] = __float2half_rn(v[j]);
-              lo[j] = __float2half_rn(v[j] - __half2float(hi[j]));
+            for (int j = 0; j < 16; ++j) {
+              out_of_range |= fmaxf(fabsf(v[2 * j]), fabsf(v[2 * j + 1])) > 60000.f;
+              split_f32x2(v[2 * j], v[2 * j + 1], hi2[j], lo2[j]);
             }
+            const __half* hi = reinterpret_cast<const __half*>(hi2);
+            const __half* lo = reinterpret_cast<const __half*>(lo2);
             if (full) {
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
