@@ -202,6 +202,12 @@ uint64_t tdn_psp_pool_workspace_bytes(int32_t n, int32_t h, int32_t c);
  * view of a larger one (td4_psp18.py:273-276 + the slice/cat of :278-284). */
 int tdn_bilinear_nhwc(const tdn_tensor* in, const tdn_tensor* out, void* stream);
 
+/* The whole PyramidPooling output in one pass (td4_psp18.py:273-284): z = cat(x, up(b1), up(b2), up(b3), up(b6))
+ * where x is the (already sliced) channel view of c4 and small[i] are the four branch maps, dense fp32
+ * [n, bins_i, bins_i, eighth] with bins = 1, 2, 3, 6, resized bilinearly (align_corners=True) on the fly. */
+int tdn_psp_concat(const tdn_tensor* x, const float* const* small, int32_t eighth, const tdn_tensor* z,
+                   void* stream);
+
 /* Strided copy between NHWC views with equal dims; the two views may differ in dtype, which makes
  * this the F32 <-> SPLIT16 converter as well (the x[:, pid*c/2:...] part of the cat in
  * td4_psp18.py:278-284, and the FIFO snapshots of buffer_contral :123-134). */

@@ -38,6 +38,7 @@ int maxpool3x3s2(const tdn_tensor*, const tdn_tensor*, cudaStream_t);
 int psp_pool(const tdn_tensor*, const tdn_tensor*, float*, size_t, cudaStream_t);
 int bilinear_nhwc(const tdn_tensor*, const tdn_tensor*, cudaStream_t);
 int copy_nhwc(const tdn_tensor*, const tdn_tensor*, cudaStream_t);
+int psp_concat(const tdn_tensor*, const float* const*, int, const tdn_tensor*, cudaStream_t);
 int softmax_rows(float*, long long, int, long long, float, cudaStream_t);
 int softmax_rows_split16(const float*, long long, int, long long, float, void*, void*, long long, float, cudaStream_t);
 int layernorm_hw_stats(const tdn_tensor*, float*, float*, float, void*, size_t, cudaStream_t);
@@ -142,6 +143,10 @@ int tdn_psp_pool(const tdn_tensor* in, const tdn_tensor* out, void* workspace, u
 
 int tdn_bilinear_nhwc(const tdn_tensor* in, const tdn_tensor* out, void* stream) {
   return bilinear_nhwc(in, out, (cudaStream_t)stream);
+}
+
+int tdn_psp_concat(const tdn_tensor* x, const float* const* small, int32_t eighth, const tdn_tensor* z, void* stream) {
+  return psp_concat(x, small, eighth, z, (cudaStream_t)stream);
 }
 
 int tdn_copy_nhwc(const tdn_tensor* in, const tdn_tensor* out, void* stream) {

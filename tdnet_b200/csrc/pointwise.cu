@@ -239,6 +239,64 @@ int bilinear_nhwc(const tdn_tensor* in, const tdn_tensor* out, cudaStream_t stre
 }
 
 // ---------------------------------------------------------------------------------------------
+// PyramidPooling output in one pass (td4_psp18.py:273-284): z = cat(x[:, slice], up(feat1..4)[:, slice]).
+// `x` is already the channel-slice view of c4; the four branch maps are the (sliced) conv+BN+ReLU
+// outputs on the 1/2/3/6 grids and are bilinearly resized (align_corners) on the fly.
+// ---------------------------------------------------------------------------------------------
+struct PspSmall { const float* p[4]; };
+
+__global__ void psp_concat_kernel(View x, PspSmall small, int eighth, View z) {
+  const int c4 = z.c >> 2;
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long total = (long long)z.n * z.h * z.w * c4;
+  if (idx >= total) return;
+  const int c = (idx % c4) * 4;
+  long long t = idx / c4;
+  const int xx = t % z.w; t /= z.w;
+  const int y = t % z.h;
+  const int b = t / z.h;
+  const long long zo = b * z.sn + y * z.sh + xx * z.sw + c;
+  if (c < x.c) {
+    st4(z, zo, ld4(x, b * x.sn + y * x.sh + xx * x.sw + c));
+    return;
+  }
+  const int lv = (c - x.c) / eighth;
+  const int cc = (c - x.c) - lv * eighth;
+  const int bins = lv == 0 ? 1 : lv == 1 ? 2 : lv == 2 ? 3 : 6;
+  int y0, y1, x0, x1; float ly, lx;
+  src_index(y, z.h > 1 ? (float)(bins - 1) / (float)(z.h - 1) : 0.f, bins, y0, y1, ly);
+  src_index(xx, z.w > 1 ? (float)(bins - 1) / (float)(z.w - 1) : 0.f, bins, x0, x1, lx);
+  const float* base = small.p[lv] + ((long long)b * bins * bins) * eighth + cc;
+  const float4 v00 = *reinterpret_cast<const float4*>(base + (y0 * bins + x0) * eighth);
+  const float4 v01 = *reinterpret_cast<const float4*>(base + (y0 * bins + x1) * eighth);
+  const float4 v10 = *reinterpret_cast<const float4*>(base + (y1 * bins + x0) * eighth);
+  const float4 v11 = *reinterpret_cast<const float4*>(base + (y1 * bins + x1) * eighth);
+  float4 o;
+  o.x = (v00.x * (1.f - lx) + v01.x * lx) * (1.f - ly) + (v10.x * (1.f - lx) + v11.x * lx) * ly;
+  o.y = (v00.y * (1.f - lx) + v01.y * lx) * (1.f - ly) + (v10.y * (1.f - lx) + v11.y * lx) * ly;
+  o.z = (v00.z * (1.f - lx) + v01.z * lx) * (1.f - ly) + (v10.z * (1.f - lx) + v11.z * lx) * ly;
+  o.w = (v00.w * (1.f - lx) + v01.w * lx) * (1.f - ly) + (v10.w * (1.f - lx) + v11.w * lx) * ly;
+  st4(z, zo, o);
+}
+
+int psp_concat(const tdn_tensor* x, const float* const* small, int eighth, const tdn_tensor* z, cudaStream_t stream) {
+  int rc;
+  if ((rc = check_tensor(x, "psp_concat.x"))) return rc;
+  if ((rc = check_tensor(z, "psp_concat.z"))) return rc;
+  TDN_REQUIRE(small && small[0] && small[1] && small[2] && small[3], TDN_ERR_INVALID, "psp_concat: null branch map");
+  TDN_REQUIRE(eighth > 0 && eighth % 4 == 0 && z->c == x->c + 4 * eighth && x->n == z->n && x->h == z->h &&
+                  x->w == z->w && vec4_ok(*x) && vec4_ok(*z), TDN_ERR_INVALID,
+              "psp_concat: z must be [n,h,w,x.c + 4*eighth] with vector-aligned views");
+  for (int i = 0; i < 4; ++i) TDN_REQUIRE(aligned16(small[i]), TDN_ERR_INVALID, "psp_concat: misaligned branch map");
+  PspSmall sm;
+  for (int i = 0; i < 4; ++i) sm.p[i] = small[i];
+  long long total = (long long)z->n * z->h * z->w * (z->c / 4);
+  psp_concat_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(make_view(*x), sm, eighth, make_view(*z));
+  TDN_LAUNCH_OK();
+  return TDN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Strided NHWC copy (float4 when possible).
 // ---------------------------------------------------------------------------------------------
 template <int VEC>

@@ -21,7 +21,8 @@ constexpr int ST_IW = 2 * ST_CWP + 5;                // 73 input cols (covers th
 constexpr int ST_K = 147;                            // 3 * 7 * 7
 constexpr int ST_PAIRS = ST_CH * (ST_CWP / 2);       // 153 pixel pairs
 constexpr int ST_THREADS = 320;
-constexpr int ST_SMEM_FLOATS = 3 * ST_IH * ST_IW + ST_K * 64 + ST_CH * ST_CWP * 64 + 128;
+constexpr int ST_IN_FLOATS = (3 * ST_IH * ST_IW + 3) / 4 * 4;   // keep the float4 regions behind it 16-byte aligned
+constexpr int ST_SMEM_FLOATS = ST_IN_FLOATS + ST_K * 64 + ST_CH * ST_CWP * 64 + 128;
 
 struct StemParams {
   const float* img;      // [n,3,H,W]
@@ -33,9 +34,9 @@ struct StemParams {
 };
 
 __global__ void __launch_bounds__(ST_THREADS, 1) stem_conv_pool_kernel(const StemParams p) {
-  extern __shared__ float st_smem[];
+  extern __shared__ __align__(16) float st_smem[];
   float* s_in = st_smem;                               // [3][ST_IH][ST_IW]
-  float* s_w = s_in + 3 * ST_IH * ST_IW;               // [147][64]
+  float* s_w = s_in + ST_IN_FLOATS;                    // [147][64]
   float* s_conv = s_w + ST_K * 64;                     // [ST_CH][ST_CWP][64]
   float* s_sb = s_conv + ST_CH * ST_CWP * 64;          // scale[64] | bias[64]
 

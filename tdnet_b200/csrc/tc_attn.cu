@@ -157,14 +157,20 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant
           tma_load_3d(dst, &tmK_hi, &bars->k_full[ks], 0, kt * AT_BK, img);
           if (++ks == AT_KSTAGES) { ks = 0; kph ^= 1; }
         }
-        // pass 2: keys (hi+lo) and the V'^T slice (hi+lo)
-        for (int kt = 0; kt < T; ++kt) {
+        // pass 2: keys (hi+lo) and the V'^T slice (hi+lo).  The key tile is fetched ONE TILE AHEAD of the
+        // values: S(kt+1) is issued before P.V(kt), and a V stage only frees up when P.V(kt-1) retires, so a
+        // K load queued behind the V loads would arrive a TMA latency too late and stall the tensor pipe.
+        auto load_k = [&](int kt) {
           mbar_wait(&bars->k_empty[ks], kph ^ 1);
           uint8_t* dk = sK + ks * 2 * AT_K_PLANE;
           mbar_expect_tx(&bars->k_full[ks], 2 * AT_K_PLANE);
           tma_load_3d(dk, &tmK_hi, &bars->k_full[ks], 0, kt * AT_BK, img);
           tma_load_3d(dk + AT_K_PLANE, &tmK_lo, &bars->k_full[ks], 0, kt * AT_BK, img);
           if (++ks == AT_KSTAGES) { ks = 0; kph ^= 1; }
+        };
+        load_k(0);
+        for (int kt = 0; kt < T; ++kt) {
+          if (kt + 1 < T) load_k(kt + 1);
           for (int h = 0; h < HALVES; ++h) {
             mbar_wait(&bars->v_empty[vs], vph ^ 1);
             uint8_t* dv = sV + vs * 2 * AT_V_PLANE;

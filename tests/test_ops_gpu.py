@@ -452,3 +452,27 @@ def test_fused_stem_conv_bn_relu_maxpool(env, h, w, split):
                                       C.byref(t), None), "stem")
     torch.cuda.synchronize()
     assert max_abs(out.torch().permute(0, 3, 1, 2).cpu(), ref) < 1e-5
+
+
+@pytest.mark.parametrize("h,w,split", [(13, 21, False), (16, 32, True)])
+def test_psp_concat_matches_interpolate_and_cat(env, h, w, split):
+    lib, cabi, View, dev = env
+    g = torch.Generator().manual_seed(h)
+    x = torch.randn(2, 32, h, w, generator=g)
+    feats = [torch.randn(2, 8, b, b, generator=g) for b in (1, 2, 3, 6)]
+    xd = View.alloc(2, h, w, 32, dev, split=split)
+    src = nhwc(x)
+    if split:
+        hi, lo = split_planes(src)
+        xd.base.copy_(hi.view(-1)); xd.lo.copy_(lo.view(-1))
+    else:
+        xd.base.copy_(src.view(-1))
+    smalls = [nhwc(f) for f in feats]
+    ptrs = (C.c_void_p * 4)(*[t.data_ptr() for t in smalls])
+    z = View.alloc(2, h, w, 64, dev, split=split)
+    tx, tz = xd.ct(), z.ct()
+    cabi.check(lib.tdn_psp_concat(C.byref(tx), ptrs, 8, C.byref(tz), None), "psp_concat")
+    torch.cuda.synchronize()
+    ref = torch.cat([xd.torch().permute(0, 3, 1, 2).cpu()] +
+                    [F.interpolate(f, (h, w), mode="bilinear", align_corners=True) for f in feats], 1)
+    assert max_abs(z.torch().permute(0, 3, 1, 2).cpu(), ref) < 2e-6
