@@ -202,6 +202,13 @@ uint64_t tdn_psp_pool_workspace_bytes(int32_t n, int32_t h, int32_t c);
  * view of a larger one (td4_psp18.py:273-276 + the slice/cat of :278-284). */
 int tdn_bilinear_nhwc(const tdn_tensor* in, const tdn_tensor* out, void* stream);
 
+/* The four PSP branch convolutions on the pooled bins in one launch (td4_psp18.py:255-266: conv1x1 without
+ * bias -> BatchNorm -> ReLU, here only this path's output-channel slice): pooled is the dense [n,1,50,c4]
+ * output of tdn_psp_pool; w[i] fp32 [eighth][c4], scale[i]/bias[i] the folded BN, out[i] dense fp32
+ * [n, bins_i, bins_i, eighth] for bins = 1, 2, 3, 6. */
+int tdn_psp_branch_convs(const tdn_tensor* pooled, const float* const* w, const float* const* scale,
+                         const float* const* bias, int32_t eighth, float* const* out, void* stream);
+
 /* The whole PyramidPooling output in one pass (td4_psp18.py:273-284): z = cat(x, up(b1), up(b2), up(b3), up(b6))
  * where x is the (already sliced) channel view of c4 and small[i] are the four branch maps, dense fp32
  * [n, bins_i, bins_i, eighth] with bins = 1, 2, 3, 6, resized bilinearly (align_corners=True) on the fly. */

@@ -71,6 +71,8 @@ SIGNATURES = {
     "tdn_psp_pool": (C.c_int, [_TP, _TP, C.c_void_p, C.c_uint64, C.c_void_p]),
     "tdn_psp_pool_workspace_bytes": (C.c_uint64, [C.c_int32, C.c_int32, C.c_int32]),
     "tdn_bilinear_nhwc": (C.c_int, [_TP, _TP, C.c_void_p]),
+    "tdn_psp_branch_convs": (C.c_int, [_TP, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                       C.c_int32, C.POINTER(C.c_void_p), C.c_void_p]),
     "tdn_psp_concat": (C.c_int, [_TP, C.POINTER(C.c_void_p), C.c_int32, _TP, C.c_void_p]),
     "tdn_copy_nhwc": (C.c_int, [_TP, _TP, C.c_void_p]),
     "tdn_softmax_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_float, C.c_void_p]),

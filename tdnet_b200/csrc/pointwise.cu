@@ -5,6 +5,12 @@
 
 namespace tdn {
 
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
 // ---------------------------------------------------------------------------------------------
 // NCHW image -> NHWC, channels padded with zeros to 4 (one float4 store per pixel).
 // ---------------------------------------------------------------------------------------------
@@ -234,6 +240,66 @@ int bilinear_nhwc(const tdn_tensor* in, const tdn_tensor* out, cudaStream_t stre
   long long total = (long long)out->n * out->h * out->w * out->c;
   bilinear_nhwc_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(
       make_view(*in), make_view(*out), ac_scale(in->h, out->h), ac_scale(in->w, out->w));
+  TDN_LAUNCH_OK();
+  return TDN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The four PSP branch convolutions (conv1x1 c4 -> slice of c4/4, folded BN, ReLU; td4_psp18.py:255-266)
+// on the 50 pooled bins in ONE launch: a block per (bin, image) keeps the pooled vector in shared memory,
+// each warp produces output channels with a coalesced dot product over K and a shuffle reduction.
+// (As four generic conv launches these were single-CTA, latency-bound ~45 us each.)
+// ---------------------------------------------------------------------------------------------
+struct PspBranch {
+  const float* w[4];      // [eighth][c4] fp32, K-major
+  const float* scale[4];
+  const float* bias[4];
+  float* out[4];          // [n, bins, bins, eighth]
+};
+
+__global__ void __launch_bounds__(256) psp_branch_kernel(const float* __restrict__ pooled, int c4, int eighth,
+                                                         PspBranch br) {
+  extern __shared__ float xs[];
+  const int bin = blockIdx.x, b = blockIdx.y;
+  int lv, local, bins;
+  if (bin < 1) { lv = 0; local = bin; bins = 1; }
+  else if (bin < 5) { lv = 1; local = bin - 1; bins = 2; }
+  else if (bin < 14) { lv = 2; local = bin - 5; bins = 3; }
+  else { lv = 3; local = bin - 14; bins = 6; }
+  const float* x = pooled + ((long long)b * 50 + bin) * c4;
+  for (int k = threadIdx.x; k < c4; k += 256) xs[k] = x[k];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* w = br.w[lv];
+  float* out = br.out[lv] + ((long long)b * bins * bins + local) * eighth;
+  for (int co = warp; co < eighth; co += 8) {
+    const float* wr = w + (long long)co * c4;
+    float acc = 0.f;
+    for (int k = lane * 4; k < c4; k += 128) {
+      const float4 wv = *reinterpret_cast<const float4*>(wr + k);
+      const float4 xv = *reinterpret_cast<const float4*>(xs + k);
+      acc = fmaf(wv.x, xv.x, acc); acc = fmaf(wv.y, xv.y, acc);
+      acc = fmaf(wv.z, xv.z, acc); acc = fmaf(wv.w, xv.w, acc);
+    }
+    acc = warp_sum_f(acc);
+    if (lane == 0) out[co] = fmaxf(fmaf(acc, br.scale[lv][co], br.bias[lv][co]), 0.f);
+  }
+}
+
+int psp_branch_convs(const tdn_tensor* pooled, const float* const* w, const float* const* scale,
+                     const float* const* bias, int eighth, float* const* out, cudaStream_t stream) {
+  int rc;
+  if ((rc = check_f32_tensor(pooled, "psp_branch.pooled"))) return rc;
+  TDN_REQUIRE(pooled->h == 1 && pooled->w == 50 && pooled->stride_w == pooled->c && pooled->stride_n == 50ll * pooled->c &&
+                  pooled->c % 4 == 0 && aligned16(pooled->data), TDN_ERR_INVALID, "psp_branch: pooled must be dense [n,1,50,c4]");
+  PspBranch br;
+  for (int i = 0; i < 4; ++i) {
+    TDN_REQUIRE(w && scale && bias && out && w[i] && scale[i] && bias[i] && out[i] && aligned16(w[i]), TDN_ERR_INVALID,
+                "psp_branch: null or misaligned branch %d", i);
+    br.w[i] = w[i]; br.scale[i] = scale[i]; br.bias[i] = bias[i]; br.out[i] = out[i];
+  }
+  psp_branch_kernel<<<dim3(50, pooled->n), 256, pooled->c * sizeof(float), stream>>>((const float*)pooled->data,
+                                                                                     pooled->c, eighth, br);
   TDN_LAUNCH_OK();
   return TDN_OK;
 }

@@ -19,9 +19,11 @@
 // Because m is fixed before pass 2 there is no running rescale of O: the MMA warp never waits on a
 // correction step and the result does not depend on tile order.
 //
-// Warp roles (320 threads): warp 0 TMA producer (Q tile, K ring, V ring), warp 1 MMA issuer,
-// warps 2-9 softmax + epilogue: two warps per TMEM lane quarter, each owning half of the key columns of
-// a tile and half of the output channels (row max / sum exchanged through shared memory).
+// Warp roles (352 threads): warp 0 TMA producer (Q tile, K ring, V ring); warp 1 issues the S = Q.K^T MMAs
+// and warp 10 the O += P.V'^T MMAs (two independent issue streams: a single issuing thread that also has to
+// poll five barriers per key tile was the measured bottleneck); warps 2-9 softmax + epilogue, two warps
+// per TMEM lane quarter, each owning half of the key columns of a tile and half of the output channels
+// (row max / sum exchanged through shared memory).
 // TMEM: S double-buffered 2 x 64 columns, O DVT columns.  Shared memory: Q 32 KB, K ring 2 x 16 KB,
 // V ring 3 x 32 KB (128-row halves of the V'^T tile), P double buffer 2 x 32 KB (hi+lo planes each).
 #include "common.cuh"
@@ -38,7 +40,8 @@ constexpr int AT_BQ = 128;       // queries per item
 constexpr int AT_BK = 64;        // keys per tile (= one 128-byte swizzle row of fp16)
 constexpr int AT_DK = 64;        // d_k (fixed by the model: Encoding(d_model, 64, d_v))
 constexpr int AT_DVH = 128;      // V'^T rows per shared-memory stage / per PV MMA (N = 128)
-constexpr int AT_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 softmax + epilogue (two per TMEM lane quarter)
+constexpr int AT_THREADS = 352;  // warp 0 TMA, warp 1 S-MMA issuer, warps 2-9 softmax + epilogue, warp 10 PV-MMA issuer
+constexpr int AT_PV_WARP = 10;
 constexpr int AT_SOFTMAX_THREADS = 256;
 constexpr int AT_Q_PLANE = AT_BQ * AT_DK * 2;   // 16 KB
 constexpr int AT_K_PLANE = AT_BK * AT_DK * 2;   // 8 KB
@@ -183,53 +186,61 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    // ================================ MMA issuer ================================
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_f16(AT_BQ, AT_BK);   // 128 x 64
-      constexpr uint32_t idesc_o = umma_idesc_f16(AT_BQ, AT_DVH);  // 128 x 128
-      int ks = 0, vs = 0, sb = 0, pb = 0;
-      uint32_t kph = 0, vph = 0, sph = 0, pph = 0, qph = 0, oph = 0;
-      const uint32_t q_hi = smem_u32(sQ), q_lo = q_hi + AT_Q_PLANE;
-
-      auto issue_s = [&](bool exact) {
+    // ================================ MMA issuer 1: S = Q.K^T (both passes) ================================
+    // The whole warp runs the loop and the barrier waits so that stage indices, phases and descriptors
+    // stay warp-uniform (uniform registers feed tcgen05.mma directly); one elected lane issues.
+    constexpr uint32_t idesc_s = umma_idesc_f16(AT_BQ, AT_BK);   // 128 x 64
+    int ks = 0, sb = 0;
+    uint32_t kph = 0, sph = 0, qph = 0;
+    const uint32_t q_hi = smem_u32(sQ), q_lo = q_hi + AT_Q_PLANE;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      mbar_wait(&bars->q_full, qph);
+      for (int it = 0; it < 2 * T; ++it) {
+        const bool exact = it >= T;                              // pass 1: hi x hi only
         mbar_wait(&bars->k_full[ks], kph);
         mbar_wait(&bars->s_empty[sb], sph ^ 1);
         tc_fence_after();
         const uint32_t k_hi = smem_u32(sK + ks * 2 * AT_K_PLANE), k_lo = k_hi + AT_K_PLANE;
         const uint32_t d = tmem_S + sb * AT_BK;
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < AT_DK / 16; ++k) {
-          const uint64_t a_h = umma_desc_k_sw128(q_hi + k * 32), b_h = umma_desc_k_sw128(k_hi + k * 32);
-          if (exact) {
-            const uint64_t a_l = umma_desc_k_sw128(q_lo + k * 32), b_l = umma_desc_k_sw128(k_lo + k * 32);
-            umma_f16(d, a_h, b_l, idesc_s, k != 0);
-            umma_f16(d, a_l, b_h, idesc_s, 1);
-            umma_f16(d, a_h, b_h, idesc_s, 1);
-          } else {
-            umma_f16(d, a_h, b_h, idesc_s, k != 0);
+          for (int k = 0; k < AT_DK / 16; ++k) {
+            const uint64_t a_h = umma_desc_k_sw128(q_hi + k * 32), b_h = umma_desc_k_sw128(k_hi + k * 32);
+            if (exact) {
+              const uint64_t a_l = umma_desc_k_sw128(q_lo + k * 32), b_l = umma_desc_k_sw128(k_lo + k * 32);
+              umma_f16(d, a_h, b_l, idesc_s, k != 0);
+              umma_f16(d, a_l, b_h, idesc_s, 1);
+              umma_f16(d, a_h, b_h, idesc_s, 1);
+            } else {
+              umma_f16(d, a_h, b_h, idesc_s, k != 0);
+            }
           }
+          umma_commit(&bars->s_full[sb]);
+          umma_commit(&bars->k_empty[ks]);
+          if (it == 2 * T - 1) umma_commit(&bars->q_empty);      // Q tile free once the last S has retired
         }
-        umma_commit(&bars->s_full[sb]);
-        umma_commit(&bars->k_empty[ks]);
+        __syncwarp();
         if (++ks == AT_KSTAGES) { ks = 0; kph ^= 1; }
         if (++sb == 2) { sb = 0; sph ^= 1; }
-      };
-
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-        mbar_wait(&bars->q_full, qph);
-        tc_fence_after();
-        for (int kt = 0; kt < T; ++kt) issue_s(false);       // pass 1
-        issue_s(true);                                        // S(0) of pass 2
-        for (int kt = 0; kt < T; ++kt) {
-          if (kt + 1 < T) issue_s(true);                      // S(kt+1) overlaps softmax(kt)
-          mbar_wait(&bars->p_full[pb], pph);
-          if (kt == 0) mbar_wait(&bars->o_empty, oph ^ 1);
-          const uint32_t p_hi = smem_u32(sP + pb * 2 * AT_P_PLANE), p_lo = p_hi + AT_P_PLANE;
-          for (int h = 0; h < HALVES; ++h) {
-            mbar_wait(&bars->v_full[vs], vph);
-            tc_fence_after();
-            const uint32_t v_hi = smem_u32(sV + vs * 2 * AT_V_PLANE), v_lo = v_hi + AT_V_PLANE;
-            const uint32_t d = tmem_O + h * AT_DVH;
+      }
+      qph ^= 1;
+    }
+  } else if (warp == AT_PV_WARP) {
+    // ================================ MMA issuer 2: O += P.V'^T ================================
+    constexpr uint32_t idesc_o = umma_idesc_f16(AT_BQ, AT_DVH);  // 128 x 128
+    int vs = 0, pb = 0;
+    uint32_t vph = 0, pph = 0, oph = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      mbar_wait(&bars->o_empty, oph ^ 1);                        // epilogue of the previous item has read O
+      for (int kt = 0; kt < T; ++kt) {
+        mbar_wait(&bars->p_full[pb], pph);
+        const uint32_t p_hi = smem_u32(sP + pb * 2 * AT_P_PLANE), p_lo = p_hi + AT_P_PLANE;
+        for (int h = 0; h < HALVES; ++h) {
+          mbar_wait(&bars->v_full[vs], vph);
+          tc_fence_after();
+          const uint32_t v_hi = smem_u32(sV + vs * 2 * AT_V_PLANE), v_lo = v_hi + AT_V_PLANE;
+          const uint32_t d = tmem_O + h * AT_DVH;
+          if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < AT_BK / 16; ++k) {
               const uint64_t a_h = umma_desc_k_sw128(p_hi + k * 32), a_l = umma_desc_k_sw128(p_lo + k * 32);
@@ -239,16 +250,17 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant
               umma_f16(d, a_h, b_h, idesc_o, 1);
             }
             umma_commit(&bars->v_empty[vs]);
-            if (++vs == AT_VSTAGES) { vs = 0; vph ^= 1; }
+            if (h == HALVES - 1) {
+              umma_commit(&bars->p_empty[pb]);
+              if (kt == T - 1) umma_commit(&bars->o_full);
+            }
           }
-          umma_commit(&bars->p_empty[pb]);
-          if (++pb == 2) { pb = 0; pph ^= 1; }
+          __syncwarp();
+          if (++vs == AT_VSTAGES) { vs = 0; vph ^= 1; }
         }
-        umma_commit(&bars->o_full);
-        umma_commit(&bars->q_empty);
-        qph ^= 1;
-        oph ^= 1;
+        if (++pb == 2) { pb = 0; pph ^= 1; }
       }
+      oph ^= 1;
     }
   } else {
     // ================================ softmax + epilogue warps ================================
@@ -422,7 +434,16 @@ int attention_tc(const tdn_attention_desc* d, cudaStream_t stream) {
               "attention_tc: null operand");
   TDN_REQUIRE(d->d_k == AT_DK, TDN_ERR_UNSUPPORTED, "attention_tc: d_k must be 64 (got %d)", d->d_k);
   TDN_REQUIRE(d->d_v % AT_DVH == 0, TDN_ERR_UNSUPPORTED, "attention_tc: d_v=%d must be a multiple of 128", d->d_v);
-  const int dvt_size = (d->d_v % 256 == 0) ? 256 : 128;
+  // 256-wide slices halve the QK^T / softmax recompute; small problems (the FIFO hops with P' queries) would
+  // not fill the SMs with them, so they take 128-wide slices = twice as many work items.
+  static int num_sms_cached = 0;
+  if (num_sms_cached == 0) {
+    int dev = 0;
+    TDN_CUDA_OK(cudaGetDevice(&dev));
+    TDN_CUDA_OK(cudaDeviceGetAttribute(&num_sms_cached, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const long long items256 = (long long)d->n * ceil_div(d->pq, AT_BQ) * (d->d_v / 256);
+  const int dvt_size = (d->d_v % 256 == 0 && items256 >= num_sms_cached) ? 256 : 128;
   TDN_REQUIRE(d->n > 0 && d->pq > 0 && d->pk > 0, TDN_ERR_INVALID, "attention_tc: empty problem");
   TDN_REQUIRE(d->vt_ld % 8 == 0 && d->vt_ld >= ((d->pk + 63) / 64) * 64, TDN_ERR_INVALID,
               "attention_tc: V'^T row pitch must cover the keys padded to 64 (zero-filled) and be 16-byte aligned");

@@ -164,23 +164,24 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     }
   } else if (warp == 1) {
     // ======================= MMA issuer =======================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(TC_BLOCK_M, BLOCK_N);
-      int stage = 0;
-      uint32_t phase = 0;
-      int as = 0;
-      uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        for (int kb0 = 0; kb0 < num_kb; kb0 += p.chunk_kb) {
-          const int kb1 = min(kb0 + p.chunk_kb, num_kb);
-          mbar_wait(&tmem_empty[as], aphase ^ 1);
+    // All 32 lanes run the loop and the barrier waits (keeps stage / phase / descriptors warp-uniform, i.e.
+    // in uniform registers); one elected lane issues the tcgen05 instructions.
+    constexpr uint32_t idesc = umma_idesc_f16(TC_BLOCK_M, BLOCK_N);
+    int stage = 0;
+    uint32_t phase = 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int kb0 = 0; kb0 < num_kb; kb0 += p.chunk_kb) {
+        const int kb1 = min(kb0 + p.chunk_kb, num_kb);
+        mbar_wait(&tmem_empty[as], aphase ^ 1);
+        const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + as * BLOCK_N;
-          for (int kb = kb0; kb < kb1; ++kb) {
-            mbar_wait(&full_bar[stage], phase);
-            tc_fence_after();
-            const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-            const uint32_t sb = sa + 2 * TC_A_PLANE;
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + 2 * TC_A_PLANE;
+          if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < TC_BLOCK_K / 16; ++k) {
               const uint64_t a_hi = umma_desc_k_sw128(sa + k * 32);
@@ -192,11 +193,12 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               umma_f16(d_tmem, a_hi, b_hi, idesc, 1);
             }
             umma_commit(&empty_bar[stage]);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            if (kb == kb1 - 1) umma_commit(&tmem_full[as]);
           }
-          umma_commit(&tmem_full[as]);
-          if (++as == NUM_ACC) { as = 0; aphase ^= 1; }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        if (++as == NUM_ACC) { as = 0; aphase ^= 1; }
       }
     }
   } else {

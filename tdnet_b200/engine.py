@@ -408,12 +408,16 @@ class Engine:
         plan.add(lib.tdn_psp_pool, C.byref(self._ct(plan, c4)), C.byref(self._ct(plan, pooled)), ws.data_ptr(),
                  ws_bytes, "stream", launches=2)
         plan.keep.append(ws)
-        smalls = []
+        smalls, pcs = [], []
         for i, (bins, off, c) in enumerate(zip(PSP_BINS, PSP_OFFSETS, A.psp_convs(m, path))):
-            pc = self.packed(c, row_slice=(pid * eighth, (pid + 1) * eighth))
-            small = self.buf(n, bins, bins, eighth, split=False)
-            self._conv(plan, pc, pooled.rows(off, off + bins * bins, bins, bins), small)
-            smalls.append(small)
+            pcs.append(self.packed(c, row_slice=(pid * eighth, (pid + 1) * eighth)))
+            smalls.append(self.buf(n, bins, bins, eighth, split=False))
+        arr = lambda xs: (C.c_void_p * 4)(*xs)  # noqa: E731
+        wp, sp, bp = arr([p_.weight.data_ptr() for p_ in pcs]), arr([p_.scale.data_ptr() for p_ in pcs]), \
+            arr([p_.bias.data_ptr() for p_ in pcs])
+        op = arr([sm.ptr for sm in smalls])
+        plan.add(lib.tdn_psp_branch_convs, C.byref(self._ct(plan, pooled)), wp, sp, bp, eighth, op, "stream")
+        plan.keep.append((wp, sp, bp, op, pcs))
         ptrs = (C.c_void_p * 4)(*[sm.ptr for sm in smalls])
         plan.add(lib.tdn_psp_concat, C.byref(self._ct(plan, c4.channels(pid * half, (pid + 1) * half))), ptrs, eighth,
                  C.byref(self._ct(plan, z)), "stream")

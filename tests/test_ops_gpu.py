@@ -476,3 +476,25 @@ def test_psp_concat_matches_interpolate_and_cat(env, h, w, split):
     ref = torch.cat([xd.torch().permute(0, 3, 1, 2).cpu()] +
                     [F.interpolate(f, (h, w), mode="bilinear", align_corners=True) for f in feats], 1)
     assert max_abs(z.torch().permute(0, 3, 1, 2).cpu(), ref) < 2e-6
+
+
+def test_psp_branch_convs_one_launch(env):
+    lib, cabi, View, dev = env
+    g = torch.Generator().manual_seed(77)
+    c4, eighth, n = 512, 64, 2
+    pooled = torch.randn(n, 50, c4, generator=g)
+    ws = [torch.randn(eighth, c4, generator=g) / 22 for _ in range(4)]
+    scs = [torch.rand(eighth, generator=g) + 0.5 for _ in range(4)]
+    bis = [torch.randn(eighth, generator=g) * 0.2 for _ in range(4)]
+    pd = pooled.cuda()
+    wd, sd_, bd = [w.cuda() for w in ws], [s.cuda() for s in scs], [b.cuda() for b in bis]
+    outs = [torch.empty(n, b * b, eighth, device=dev) for b in (1, 2, 3, 6)]
+    arr = lambda xs: (C.c_void_p * 4)(*[t.data_ptr() for t in xs])  # noqa: E731
+    t = View(pd.view(-1), n, 1, 50, c4).ct()
+    cabi.check(lib.tdn_psp_branch_convs(C.byref(t), arr(wd), arr(sd_), arr(bd), eighth, arr(outs), None), "psp_branch")
+    torch.cuda.synchronize()
+    off = 0
+    for i, b in enumerate((1, 2, 3, 6)):
+        ref = F.relu(pooled[:, off:off + b * b] @ ws[i].t() * scs[i] + bis[i])
+        assert max_abs(outs[i].cpu(), ref) < 5e-6
+        off += b * b

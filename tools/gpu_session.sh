@@ -10,7 +10,7 @@ echo "== ops"; timeout 400 python -m pytest tests/test_ops_gpu.py -m gpu -q 2>&1
 echo "== model (tc fused + simt)"; timeout 900 python -m pytest tests/test_model_gpu.py -m gpu -q 2>&1 | tail -25 | tee gpurun_out/t_model.log
 echo "== model tc, unfused attention chain"; TDNET_B200_FUSED_ATTN=0 timeout 400 python -m pytest tests/test_model_gpu.py -m gpu -q -k "golden and tc" 2>&1 | tail -8 | tee gpurun_out/t_model_unfused.log
 echo "== bench tc"; timeout 300 python bench.py --steps 40 --warmup 8 2>&1 | tail -1 | tee gpurun_out/bench_tc.json | cut -c1-1500
-echo "== ncu launch list"; timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:^(tc_|conv_simt|bilinear|copy_nhwc|maxpool|psp_|ln_|upsample|softmax|image_to)' -s 560 -c 420 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1; tail -1 gpurun_out/ncu_bench.log | cut -c1-200
+echo "== ncu launch list"; timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:^(tc_|stem_|conv_simt|bilinear|copy_nhwc|maxpool|psp_|ln_|upsample|softmax|image_to)' -s 450 -c 360 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1; tail -1 gpurun_out/ncu_bench.log | cut -c1-200
 echo "== ncu full: conv"; timeout 300 ncu --set full --clock-control none --import-source on -k regex:tc_conv_kernel -s 3 -c 1 -f -o gpurun_out/prof_conv python tools/tc_probe.py --one layer4_perf > gpurun_out/ncu_conv.log 2>&1; tail -2 gpurun_out/ncu_conv.log | cut -c1-200
 echo "== ncu full: attention"; timeout 300 ncu --set full --clock-control none --import-source on -k regex:tc_attn_kernel -s 2 -c 1 -f -o gpurun_out/prof_attn python tools/tc_probe.py --one attention_big > gpurun_out/ncu_attn.log 2>&1; tail -2 gpurun_out/ncu_attn.log | cut -c1-200
 ls -la gpurun_out | head -30
