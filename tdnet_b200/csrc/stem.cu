@@ -4,25 +4,24 @@
 // path and the op is ~1 % of the frame's FLOPs); what the fusion buys is memory traffic: the 512x1024x64
 // pre-pool map (134 MB at 1024x2048) never leaves shared memory.
 //
-// One CTA = 4 x 16 pooled pixels.  It stages the 23 x 71 x 3 input patch and the 147 x 64 weights in
-// shared memory, computes the 9 x 33 conv pixels the pooling windows touch (each thread: 2 adjacent
-// pixels x 32 channels = 64 fp32 accumulators, weights broadcast from shared memory), applies
-// scale/bias/ReLU into a shared conv tile, then max-pools it and stores 4 channels per thread.
+// One CTA = 8 x 8 pooled pixels = 17 x 17 conv pixels.  Warp r owns conv row r: its 32 lanes hold two
+// output channels each (lane, lane+32) for all 17 pixels of the row (34 fp32 accumulators).  For every
+// (channel, filter row) the warp reads the 39 input floats of that row segment with ten 16-byte broadcast
+// loads and its 14 weights with conflict-free 4-byte loads, then does 7 x 17 x 2 FMAs per lane: 24
+// shared-memory wavefronts per 238 FMA instructions, i.e. FMA-bound, not load/store-bound.
 #include "common.cuh"
 
 namespace tdn {
 
-constexpr int ST_PH = 4, ST_PW = 16;                 // pooled tile
-constexpr int ST_CH = 2 * ST_PH + 1;                 // 9 conv rows
-constexpr int ST_CW = 2 * ST_PW + 1;                 // 33 conv cols
-constexpr int ST_CWP = ST_CW + 1;                    // padded to a pair count (34)
-constexpr int ST_IH = 2 * ST_CH + 5;                 // 23 input rows
-constexpr int ST_IW = 2 * ST_CWP + 5;                // 73 input cols (covers the padded pair)
+constexpr int ST_P = 8;                              // pooled tile edge
+constexpr int ST_C = 2 * ST_P + 1;                   // 17 conv rows / cols
+constexpr int ST_IH = 2 * ST_C + 5;                  // 39 input rows
+constexpr int ST_IW = 40;                            // 39 input cols, padded to a multiple of 4
 constexpr int ST_K = 147;                            // 3 * 7 * 7
-constexpr int ST_PAIRS = ST_CH * (ST_CWP / 2);       // 153 pixel pairs
-constexpr int ST_THREADS = 320;
-constexpr int ST_IN_FLOATS = (3 * ST_IH * ST_IW + 3) / 4 * 4;   // keep the float4 regions behind it 16-byte aligned
-constexpr int ST_SMEM_FLOATS = ST_IN_FLOATS + ST_K * 64 + ST_CH * ST_CWP * 64 + 128;
+constexpr int ST_THREADS = 32 * ST_C;                // 544: one warp per conv row
+constexpr int ST_IN_FLOATS = 3 * ST_IH * ST_IW;      // 4680 (multiple of 4)
+constexpr int ST_CONV_PITCH = 66;                    // floats per conv pixel in smem (64 + 2: conflict-free float2 rows)
+constexpr int ST_SMEM_FLOATS = ST_IN_FLOATS + ST_K * 64 + ST_C * ST_C * ST_CONV_PITCH + 128;
 
 struct StemParams {
   const float* img;      // [n,3,H,W]
@@ -37,19 +36,19 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_conv_pool_kernel(const Ste
   extern __shared__ __align__(16) float st_smem[];
   float* s_in = st_smem;                               // [3][ST_IH][ST_IW]
   float* s_w = s_in + ST_IN_FLOATS;                    // [147][64]
-  float* s_conv = s_w + ST_K * 64;                     // [ST_CH][ST_CWP][64]
-  float* s_sb = s_conv + ST_CH * ST_CWP * 64;          // scale[64] | bias[64]
+  float* s_conv = s_w + ST_K * 64;                     // [17][17][ST_CONV_PITCH]
+  float* s_sb = s_conv + ST_C * ST_C * ST_CONV_PITCH;  // scale[64] | bias[64]
 
   const int tid = threadIdx.x;
   const int b = blockIdx.z;
-  const int py0 = blockIdx.y * ST_PH, px0 = blockIdx.x * ST_PW;
+  const int py0 = blockIdx.y * ST_P, px0 = blockIdx.x * ST_P;
   const int cy0 = 2 * py0 - 1, cx0 = 2 * px0 - 1;      // first conv pixel of the tile (may be -1)
   const int iy0 = 2 * cy0 - 3, ix0 = 2 * cx0 - 3;      // first input pixel of the patch
 
   for (int i = tid; i < ST_K * 64; i += ST_THREADS) s_w[i] = __ldg(p.w + i);
   if (tid < 64) { s_sb[tid] = __ldg(p.scale + tid); s_sb[64 + tid] = __ldg(p.bias + tid); }
   const float* img = p.img + (long long)b * 3 * p.H * p.W;
-  for (int i = tid; i < 3 * ST_IH * ST_IW; i += ST_THREADS) {
+  for (int i = tid; i < ST_IN_FLOATS; i += ST_THREADS) {
     const int x = i % ST_IW;
     const int t = i / ST_IW;
     const int y = t % ST_IH;
@@ -61,65 +60,53 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_conv_pool_kernel(const Ste
   }
   __syncthreads();
 
-  if (tid < 2 * ST_PAIRS) {
-    const int half = tid / ST_PAIRS;                   // channels [32*half, 32*half+32)
-    const int pair = tid - half * ST_PAIRS;
-    const int prow = pair / (ST_CWP / 2);
-    const int pcol = pair - prow * (ST_CWP / 2);
-    float acc0[32], acc1[32];
+  {
+    const int r = tid >> 5;                            // conv row of the tile (one warp each)
+    const int lane = tid & 31;
+    float acc0[ST_C], acc1[ST_C];                      // channels lane and lane + 32
 #pragma unroll
-    for (int j = 0; j < 32; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; }
-    const float* in_base = s_in + (2 * prow) * ST_IW + 4 * pcol;   // pixel 2*pcol -> input col 2*(2*pcol)
-    const float* w_base = s_w + half * 32;
-    for (int c = 0; c < 3; ++c) {
+    for (int j = 0; j < ST_C; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; }
 #pragma unroll 1
-      for (int ky = 0; ky < 7; ++ky) {
-        const float* row = in_base + (c * ST_IH + ky) * ST_IW;
+    for (int cky = 0; cky < 21; ++cky) {               // (input channel, filter row)
+      const int c = cky / 7, ky = cky - c * 7;
+      const float4* row4 = reinterpret_cast<const float4*>(s_in + (c * ST_IH + 2 * r + ky) * ST_IW);
+      float in[ST_IW];
 #pragma unroll
-        for (int kx = 0; kx < 7; ++kx) {
-          const float a0 = row[kx], a1 = row[kx + 2];
-          const float4* wv = reinterpret_cast<const float4*>(w_base + ((c * 7 + ky) * 7 + kx) * 64);
+      for (int q = 0; q < ST_IW / 4; ++q) {
+        const float4 v = row4[q];                      // same address in every lane: broadcast
+        in[4 * q + 0] = v.x; in[4 * q + 1] = v.y; in[4 * q + 2] = v.z; in[4 * q + 3] = v.w;
+      }
+      const float* wk = s_w + (cky * 7) * 64 + lane;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 w4 = wv[q];
-            acc0[q * 4 + 0] = fmaf(a0, w4.x, acc0[q * 4 + 0]); acc1[q * 4 + 0] = fmaf(a1, w4.x, acc1[q * 4 + 0]);
-            acc0[q * 4 + 1] = fmaf(a0, w4.y, acc0[q * 4 + 1]); acc1[q * 4 + 1] = fmaf(a1, w4.y, acc1[q * 4 + 1]);
-            acc0[q * 4 + 2] = fmaf(a0, w4.z, acc0[q * 4 + 2]); acc1[q * 4 + 2] = fmaf(a1, w4.z, acc1[q * 4 + 2]);
-            acc0[q * 4 + 3] = fmaf(a0, w4.w, acc0[q * 4 + 3]); acc1[q * 4 + 3] = fmaf(a1, w4.w, acc1[q * 4 + 3]);
-          }
+      for (int kx = 0; kx < 7; ++kx) {
+        const float w0 = wk[kx * 64], w1 = wk[kx * 64 + 32];
+#pragma unroll
+        for (int j = 0; j < ST_C; ++j) {
+          acc0[j] = fmaf(in[2 * j + kx], w0, acc0[j]);
+          acc1[j] = fmaf(in[2 * j + kx], w1, acc1[j]);
         }
       }
     }
     // BN + ReLU; conv pixels outside the conv map become 0, which cannot change a max over ReLU outputs
-    const int cy = cy0 + prow, cxa = cx0 + 2 * pcol, cxb = cxa + 1;
+    const int cy = cy0 + r;
     const bool rowok = cy >= 0 && cy < p.Hc;
-    const bool oka = rowok && cxa >= 0 && cxa < p.Wc, okb = rowok && cxb >= 0 && cxb < p.Wc;
-    float* da = s_conv + (prow * ST_CWP + 2 * pcol) * 64 + half * 32;
-    float* db = da + 64;
+    const float sc0 = s_sb[lane], sc1 = s_sb[lane + 32], bi0 = s_sb[64 + lane], bi1 = s_sb[96 + lane];
+    float* dst = s_conv + (r * ST_C) * ST_CONV_PITCH;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      float4 ra, rb;
-      const float* sc = s_sb + half * 32 + q * 4;
-      const float* bi = sc + 64;
-      ra.x = oka ? fmaxf(fmaf(acc0[q * 4 + 0], sc[0], bi[0]), 0.f) : 0.f;
-      ra.y = oka ? fmaxf(fmaf(acc0[q * 4 + 1], sc[1], bi[1]), 0.f) : 0.f;
-      ra.z = oka ? fmaxf(fmaf(acc0[q * 4 + 2], sc[2], bi[2]), 0.f) : 0.f;
-      ra.w = oka ? fmaxf(fmaf(acc0[q * 4 + 3], sc[3], bi[3]), 0.f) : 0.f;
-      rb.x = okb ? fmaxf(fmaf(acc1[q * 4 + 0], sc[0], bi[0]), 0.f) : 0.f;
-      rb.y = okb ? fmaxf(fmaf(acc1[q * 4 + 1], sc[1], bi[1]), 0.f) : 0.f;
-      rb.z = okb ? fmaxf(fmaf(acc1[q * 4 + 2], sc[2], bi[2]), 0.f) : 0.f;
-      rb.w = okb ? fmaxf(fmaf(acc1[q * 4 + 3], sc[3], bi[3]), 0.f) : 0.f;
-      *reinterpret_cast<float4*>(da + q * 4) = ra;
-      *reinterpret_cast<float4*>(db + q * 4) = rb;
+    for (int j = 0; j < ST_C; ++j) {
+      const int cx = cx0 + j;
+      const bool ok = rowok && cx >= 0 && cx < p.Wc;
+      dst[j * ST_CONV_PITCH + lane] = ok ? fmaxf(fmaf(acc0[j], sc0, bi0), 0.f) : 0.f;
+      dst[j * ST_CONV_PITCH + lane + 32] = ok ? fmaxf(fmaf(acc1[j], sc1, bi1), 0.f) : 0.f;
     }
   }
   __syncthreads();
 
-  // 3x3 stride-2 max pool over the shared conv tile: pooled (py, px) covers conv rows 2py..2py+2 of the tile
-  for (int u = tid; u < ST_PH * ST_PW * 16; u += ST_THREADS) {
+  // 3x3 stride-2 max pool over the shared conv tile: pooled (py, px) covers conv rows/cols 2p .. 2p+2 of the tile
+  for (int u = tid; u < ST_P * ST_P * 16; u += ST_THREADS) {
     const int cq = u & 15;
     const int pp = u >> 4;
-    const int px = pp % ST_PW, py = pp / ST_PW;
+    const int px = pp % ST_P, py = pp / ST_P;
     const int gy = py0 + py, gx = px0 + px;
     if (gy >= p.Hp || gx >= p.Wp) continue;
     float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -127,8 +114,9 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_conv_pool_kernel(const Ste
     for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
       for (int dx = 0; dx < 3; ++dx) {
-        const float4 v = *reinterpret_cast<const float4*>(s_conv + ((2 * py + dy) * ST_CWP + 2 * px + dx) * 64 + cq * 4);
-        m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+        const float* v = s_conv + ((2 * py + dy) * ST_C + 2 * px + dx) * ST_CONV_PITCH + cq * 4;
+        const float2 v0 = *reinterpret_cast<const float2*>(v), v1 = *reinterpret_cast<const float2*>(v + 2);
+        m.x = fmaxf(m.x, v0.x); m.y = fmaxf(m.y, v0.y); m.z = fmaxf(m.z, v1.x); m.w = fmaxf(m.w, v1.y);
       }
     st4(p.out, b * p.out.sn + gy * p.out.sh + gx * p.out.sw + cq * 4, m);
   }
@@ -153,7 +141,7 @@ int stem_conv_pool(const float* nchw, int n, int h, int w, const float* weight, 
     TDN_CUDA_OK(cudaFuncSetAttribute(stem_conv_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  dim3 grid(ceil_div(p.Wp, ST_PW), ceil_div(p.Hp, ST_PH), n);
+  dim3 grid(ceil_div(p.Wp, ST_P), ceil_div(p.Hp, ST_P), n);
   stem_conv_pool_kernel<<<grid, ST_THREADS, smem, stream>>>(p);
   TDN_LAUNCH_OK();
   return TDN_OK;

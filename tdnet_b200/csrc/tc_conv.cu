@@ -8,15 +8,16 @@
 // are exact in fp32; the dropped Al*Bl term is below 2^-22 relative).  This is what makes the
 // tensor-core path match the reference's fp32 arithmetic instead of being a bf16/tf32 approximation.
 //
-// Structure (one persistent CTA per SM, 192 threads):
+// Structure (one persistent CTA per SM, 320 threads):
 //   warp 0      TMA producer: per K block (one filter tap x 64 input channels) four bulk-tensor loads
 //               -- A hi/lo as a [BH x BW pixels] x 64ch box of the NHWC map, shifted by the tap offset
 //               (out-of-bounds rows/cols are zero-filled by TMA = the convolution padding), B hi/lo as
 //               [BLOCK_N couts] x 64 -- into a STAGES-deep shared-memory ring (128B swizzle).
 //   warp 1      MMA issuer: one elected lane issues 12 tcgen05.mma (4 K16 steps x 3 products) per
 //               stage into a double-buffered TMEM accumulator; tcgen05.commit releases the stage.
-//   warps 2-5   epilogue: tcgen05.ld the 128 x BLOCK_N fp32 tile (one pixel row per thread), apply
-//               scale/bias/residual/activation, re-split to hi/lo (and/or write fp32), 16-byte stores.
+//   warps 2-9   epilogue: tcgen05.ld the 128 x BLOCK_N fp32 tile (one pixel row x half the columns per
+//               thread), apply scale/bias/residual/activation, re-split to hi/lo (and/or write fp32),
+//               16-byte stores.
 // Accumulation is CHUNKED: the tensor core adds into its fp32 TMEM accumulator with truncation (measured
 // on B200: -3.8e-5 mean relative error after 864 chained MMAs on positive data), so a TMEM accumulator
 // only ever holds `chunk_kb` K blocks (default 4 = 48 MMAs); the epilogue warps pull each finished chunk
@@ -37,7 +38,8 @@ using namespace ptx;
 constexpr int TC_BLOCK_M = 128;
 constexpr int TC_BLOCK_K = 64;                       // fp16 elements = 128 bytes = one swizzle row
 constexpr int TC_A_PLANE = TC_BLOCK_M * TC_BLOCK_K * 2;  // 16 KiB per hi or lo plane
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 8;                      // two per TMEM lane quarter, each owning half of the N columns
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
 
 struct TcParams {
   int n_img, Ho, Wo;
@@ -114,7 +116,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     }
     for (int s = 0; s < NUM_ACC; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 128);
+      mbar_init(&tmem_empty[s], 32 * TC_EPI_WARPS);
     }
     fence_mbar_init();
   }
@@ -202,7 +204,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       }
     }
   } else {
-    // ======================= epilogue (warps 2..5) =======================
+    // ======================= epilogue (warps 2..9) =======================
+    // Warp w may only touch TMEM lanes 32*(w%4)..+31, so the 8 epilogue warps pair up per lane quarter:
+    // group 0 (warps 2-5) owns accumulator columns [0, N/2), group 1 (warps 6-9) columns [N/2, N).
+    constexpr int COLS = BLOCK_N / 2;
+    const int group = (warp - 2) >> 2;
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;          // pixel row of the tile
     const int h_local = row / p.BW;
@@ -224,15 +230,15 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       const long long roff = (long long)img * p.rsn + (long long)oh * p.rsh + (long long)ow * p.rsw;
       const float bias_m = (p.bias && p.bias_along_m && valid) ? __ldg(p.bias + oh * p.Wo + ow) : 0.f;
 
-      float acc[BLOCK_N];
+      float acc[COLS];
 #pragma unroll
-      for (int j = 0; j < BLOCK_N; ++j) acc[j] = 0.f;
+      for (int j = 0; j < COLS; ++j) acc[j] = 0.f;
       for (int kb0 = 0; kb0 < num_kb; kb0 += p.chunk_kb) {
         mbar_wait(&tmem_full[as], aphase);
         tc_fence_after();
-        const uint32_t taddr_c = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BLOCK_N;
+        const uint32_t taddr_c = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BLOCK_N + group * COLS;
 #pragma unroll
-        for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
+        for (int chunk = 0; chunk < COLS / 32; ++chunk) {
           uint32_t r[32];
           tmem_ld_32x32(taddr_c + chunk * 32, r);
           tmem_ld_wait();
@@ -244,8 +250,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         if (++as == NUM_ACC) { as = 0; aphase ^= 1; }
       }
 #pragma unroll
-      for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
-        const int c0 = nt * BLOCK_N + chunk * 32;
+      for (int chunk = 0; chunk < COLS / 32; ++chunk) {
+        const int c0 = nt * BLOCK_N + group * COLS + chunk * 32;
         if (valid && c0 < p.Cout) {
           float v[32];
           const bool full = (c0 + 32 <= p.Cout);
