@@ -95,31 +95,42 @@ int maxpool3x3s2(const tdn_tensor* in, const tdn_tensor* out, cudaStream_t strea
 __device__ __forceinline__ int bin_start(int i, int o, int len) { return (i * len) / o; }
 __device__ __forceinline__ int bin_end(int i, int o, int len) { return ((i + 1) * len + o - 1) / o; }
 
+constexpr int PSP_PARTS = 4;   // x-segments per row (more CTAs in flight; partial sums are added in pass 2)
+
 __global__ void psp_rowsum_kernel(View in, float* __restrict__ rowsum) {
-  // One pass over the row: every pyramid level keeps the running sum of its current column range.
-  // Adjacent ranges of a level overlap by at most one column (ceil vs floor), which seeds the next sum.
-  const int y = blockIdx.x, b = blockIdx.z;
+  // One pass over a quarter of the row: every pyramid level keeps the running sum of its current column
+  // range.  Adjacent ranges of a level overlap by at most one column (ceil vs floor), which seeds the next
+  // sum.  Ranges cut by the segment boundary leave partial sums; untouched ranges stay zero.
+  const int y = blockIdx.x;
+  const int part = blockIdx.z % PSP_PARTS, b = blockIdx.z / PSP_PARTS;
   const int c = blockIdx.y * blockDim.x + threadIdx.x;
   if (c >= in.c) return;
   const long long row = b * in.sn + y * in.sh + c;
-  float* dst = rowsum + ((long long)(b * in.h + y) * 12) * in.c + c;
+  float* dst = rowsum + (((long long)(b * in.h + y) * PSP_PARTS + part) * 12) * in.c + c;
   const int W = in.w;
+  const int x_lo = (part * W) / PSP_PARTS, x_hi = ((part + 1) * W) / PSP_PARTS;
   const int lv_o[4] = {1, 2, 3, 6};
   const int lv_off[4] = {0, 1, 3, 6};
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  int cur[4] = {0, 0, 0, 0};
-  int nend[4];
 #pragma unroll
-  for (int l = 0; l < 4; ++l) nend[l] = bin_end(0, lv_o[l], W);
+  for (int r = 0; r < 12; ++r) dst[(long long)r * in.c] = 0.f;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  int cur[4], nend[4];
+#pragma unroll
+  for (int l = 0; l < 4; ++l) {
+    int j = 0;
+    while (j < lv_o[l] && bin_end(j, lv_o[l], W) <= x_lo) ++j;   // first range that reaches into the segment
+    cur[l] = j;
+    nend[l] = bin_end(j, lv_o[l], W);
+  }
   constexpr int UN = 8;   // loads issued ahead of the (serial) range bookkeeping
-  for (int x0 = 0; x0 < W; x0 += UN) {
+  for (int x0 = x_lo; x0 < x_hi; x0 += UN) {
     float vbuf[UN];
 #pragma unroll
-    for (int u = 0; u < UN; ++u) vbuf[u] = (x0 + u < W) ? ld1(in, row + (long long)(x0 + u) * in.sw) : 0.f;
+    for (int u = 0; u < UN; ++u) vbuf[u] = (x0 + u < x_hi) ? ld1(in, row + (long long)(x0 + u) * in.sw) : 0.f;
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
       const int x = x0 + u;
-      if (x >= W) break;
+      if (x >= x_hi) break;
       const float v = vbuf[u];
 #pragma unroll
       for (int l = 0; l < 4; ++l) {
@@ -133,6 +144,9 @@ __global__ void psp_rowsum_kernel(View in, float* __restrict__ rowsum) {
       }
     }
   }
+#pragma unroll
+  for (int l = 0; l < 4; ++l)      // ranges still open at the segment end keep their partial sum
+    if (cur[l] < lv_o[l] && bin_start(cur[l], lv_o[l], W) < x_hi) dst[(long long)(lv_off[l] + cur[l]) * in.c] = acc[l];
 }
 
 // Generic fallback (any width, re-reads the row once per level): used when the map is narrower than the
@@ -140,8 +154,9 @@ __global__ void psp_rowsum_kernel(View in, float* __restrict__ rowsum) {
 __global__ void psp_rowsum_generic_kernel(View in, float* __restrict__ rowsum) {
   const int y = blockIdx.x, b = blockIdx.y;
   const long long row = b * in.sn + y * in.sh;
-  float* dst = rowsum + ((long long)(b * in.h + y) * 12) * in.c;
+  float* dst = rowsum + ((long long)(b * in.h + y) * PSP_PARTS * 12) * in.c;   // everything goes to part 0
   for (int c = threadIdx.x; c < in.c; c += blockDim.x) {
+    for (int r = 12; r < 12 * PSP_PARTS; ++r) dst[(long long)r * in.c + c] = 0.f;
     int r = 0;
 #pragma unroll
     for (int lv = 0; lv < 4; ++lv) {
@@ -170,7 +185,9 @@ __global__ void psp_binsum_kernel(const float* __restrict__ rowsum, View out, in
   for (int c = threadIdx.x; c < out.c; c += blockDim.x) {
     float s = 0.f;
     for (int y = y0; y < y1; ++y)
-      s += rowsum[((long long)(b * H + y) * 12 + roff + j) * out.c + c];
+#pragma unroll
+      for (int part = 0; part < PSP_PARTS; ++part)
+        s += rowsum[(((long long)(b * H + y) * PSP_PARTS + part) * 12 + roff + j) * out.c + c];
     out.p[b * out.sn + bin * out.sw + c] = s * inv;
   }
 }
@@ -182,12 +199,13 @@ int psp_pool(const tdn_tensor* in, const tdn_tensor* out, float* workspace, size
   if ((rc = check_f32_tensor(out, "psp_pool.out"))) return rc;
   TDN_REQUIRE(out->n == in->n && out->h == 1 && out->w == 50 && out->c == in->c, TDN_ERR_INVALID,
               "psp_pool: out must be [n,1,50,c]");
-  size_t need = (size_t)in->n * in->h * 12 * in->c * sizeof(float);
+  size_t need = (size_t)in->n * in->h * PSP_PARTS * 12 * in->c * sizeof(float);
   TDN_REQUIRE(workspace && workspace_bytes >= need, TDN_ERR_WORKSPACE,
               "psp_pool: workspace %zu < %zu bytes", workspace_bytes, need);
   int threads = in->c >= 512 ? 512 : (in->c >= 256 ? 256 : 128);
   if (in->w >= 6) {
-    psp_rowsum_kernel<<<dim3(in->h, ceil_div(in->c, 128), in->n), 128, 0, stream>>>(make_view(*in), workspace);
+    psp_rowsum_kernel<<<dim3(in->h, ceil_div(in->c, 128), in->n * PSP_PARTS), 128, 0, stream>>>(make_view(*in),
+                                                                                              workspace);
   } else {
     psp_rowsum_generic_kernel<<<dim3(in->h, in->n), threads, 0, stream>>>(make_view(*in), workspace);
   }
@@ -649,13 +667,32 @@ __global__ void __launch_bounds__(256) upsample_logits_kernel(View in, float* __
   const long long plane = (long long)H * W;
   float* o = out + (long long)b * in.c * plane + (long long)y * W + xq * 4;
   const bool full = (xq * 4 + 3 < W) && ((W & 3) == 0);
+  // 4 consecutive outputs of a >= 3x upsample touch at most 3 consecutive low-res columns: load
+  // those once per channel instead of 16 scalar loads
+  const int xa = x0[0];
+  const bool compact = sx <= (1.f / 3.f);   // then x0[3] - x0[0] <= 1 and x1[3] - x0[0] <= 2
+  const int xb = min(xa + 1, in.w - 1), xc = min(xa + 2, in.w - 1);
   for (int c = 0; c < in.c; ++c) {
     float v[4];
+    if (compact) {
+      const float t0 = r0[xa * in.sw + c], t1 = r0[xb * in.sw + c], t2 = r0[xc * in.sw + c];
+      const float u0 = r1[xa * in.sw + c], u1 = r1[xb * in.sw + c], u2 = r1[xc * in.sw + c];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float top = r0[x0[j] * in.sw + c] * (1.f - lx[j]) + r0[x1[j] * in.sw + c] * lx[j];
-      float bot = r1[x0[j] * in.sw + c] * (1.f - lx[j]) + r1[x1[j] * in.sw + c] * lx[j];
-      v[j] = top * (1.f - ly) + bot * ly;
+      for (int j = 0; j < 4; ++j) {
+        const int d0 = x0[j] - xa, d1 = x1[j] - xa;            // 0..1 and 0..2
+        const float ta = d0 == 0 ? t0 : t1, tb = d1 == 0 ? t0 : (d1 == 1 ? t1 : t2);
+        const float ua = d0 == 0 ? u0 : u1, ub = d1 == 0 ? u0 : (d1 == 1 ? u1 : u2);
+        const float top = ta * (1.f - lx[j]) + tb * lx[j];
+        const float bot = ua * (1.f - lx[j]) + ub * lx[j];
+        v[j] = top * (1.f - ly) + bot * ly;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float top = r0[x0[j] * in.sw + c] * (1.f - lx[j]) + r0[x1[j] * in.sw + c] * lx[j];
+        float bot = r1[x0[j] * in.sw + c] * (1.f - lx[j]) + r1[x1[j] * in.sw + c] * lx[j];
+        v[j] = top * (1.f - ly) + bot * ly;
+      }
     }
     float* oc = o + c * plane;
     if (full) {

@@ -176,12 +176,19 @@ class FramePlan:
         self.names: List[str] = []   # per op: state-dict prefix of the conv it runs ('' for the rest)
         self.keep = []           # ctypes objects / tensors referenced by raw pointer
         self.kernel_launches = 0
+        self.side = False        # ops added while True are enqueued on the engine's side stream
 
     def add(self, fn, *args, launches=1, name=""):
         self.keep.append(args)
+        args = tuple("side" if (self.side and a == "stream") else a for a in args)
         self.ops.append((fn, args))
         self.names.append(name)
         self.kernel_launches += launches
+
+    def mark(self, what):
+        """'fork': side stream waits for the main stream; 'join': main stream waits for the side stream."""
+        self.ops.append((what, ()))
+        self.names.append(what)
 
 
 class Engine:
@@ -197,6 +204,8 @@ class Engine:
         self.fused_attn = os.environ.get("TDNET_B200_FUSED_ATTN", "1") != "0"
         self.tc_stride2 = os.environ.get("TDNET_B200_TC_STRIDE2", "1") != "0"
         self.fused_stem = os.environ.get("TDNET_B200_FUSED_STEM", "1") != "0"
+        use_side = os.environ.get("TDNET_B200_SIDE_STREAM", "1") != "0"
+        self.side_stream = torch.cuda.Stream(device) if (use_side and device.type == "cuda") else None
         self.m, self.n, self.H, self.W, self.device = arch, n, H, W, device
         self.h8, self.w8 = A.feature_hw(H, W)
         if tuple(ln_shape) != (self.h8, self.w8):
@@ -380,6 +389,15 @@ class Engine:
             plan.add(lib.tdn_maxpool3x3s2, C.byref(self._ct(plan, x)), C.byref(self._ct(plan, y)), "stream")
             x = y
 
+        # --- attention prelude on the side stream: the FIFO hops and the fc of the last hop depend only on the
+        #     FIFO (td4_psp18.py:145-146), so they overlap the backbone instead of serialising behind it
+        pre = None
+        if steady and self.tc and self.fused_attn and self.side_stream is not None:
+            plan.mark("fork")
+            plan.side = True
+            pre = self._attention_chain_tc(plan, path, None, None, stage="prelude")
+            plan.side = False
+
         # --- residual stages
         for blk in m.stages[path]:
             identity = x
@@ -434,8 +452,12 @@ class Engine:
 
         # --- attention propagation over the FIFO
         if steady:
-            chain = self._attention_chain_tc if self.tc else self._attention_chain
-            fused = chain(plan, path, q_cur, v_cur)
+            if pre is not None:
+                plan.mark("join")
+                fused = self._attention_chain_tc(plan, path, q_cur, v_cur, stage="final", pre=pre)
+            else:
+                chain = self._attention_chain_tc if self.tc else self._attention_chain
+                fused = chain(plan, path, q_cur, v_cur)
         else:
             fused = v_cur  # td4_psp18.py:142-143: head(layer_norm(v_cur)) while the FIFO fills
 
@@ -529,7 +551,7 @@ class Engine:
             carry = out
         return carry
 
-    def _attention_chain_tc(self, plan: FramePlan, path: int, q_cur: View, v_cur: View) -> View:
+    def _attention_chain_tc(self, plan: FramePlan, path: int, q_cur: View, v_cur: View, stage="all", pre=None):
         """Same chain on the tensor cores (SPLIT16 operands, exact mode).  Per hop and image:
              V'^T [d_v, P'] = W_fc @ v_src^T + b      (bias along rows; written K-major for the last GEMM)
              S    [Pq, P']  = q @ k^T                 (fp32)
@@ -543,10 +565,23 @@ class Engine:
         carry = None
         for j, name in enumerate(hops):
             last = j == len(hops) - 1
+            if stage == "final" and not last:
+                continue                                                  # emitted by the prelude
             v_src = self.v_slots[j] if carry is None else carry          # [n,1,P',d_v] SPLIT16
-            fc = self.packed(A.fc_conv(m, name))
-            wfc = self._fc_as_activation(fc)                              # [1,1,d_v,d_v] SPLIT16 + scale
-            vpt = self.buf(n, 1, m.d_v, pkp, zero=True)                   # V'^T, K (=P') padded to 64
+            if stage == "final":
+                vpt = pre["vpt"]
+            else:
+                fc = self.packed(A.fc_conv(m, name))
+                wfc = self._fc_as_activation(fc)                          # [1,1,d_v,d_v] SPLIT16 + scale
+                vpt = self.buf(n, 1, m.d_v, pkp, zero=True)               # V'^T, K (=P') padded to 64
+                for i in range(n):
+                    # V'^T_i = W_fc @ v_src_i^T + b  -> rows d_v, cols P'
+                    self._conv_tc(plan, wfc["view"], vpt.image(i).narrow_c(pk), w_hi=v_src.image(i).ptr,
+                                  w_lo=v_src.image(i).ptr_lo, w_ld=v_src.sw, cout=pk,
+                                  scale=self.const_vec(wfc["inv_scale"], pkp), bias=fc.bias,
+                                  bias_along_m=True, name=name + ".fc")
+                if stage == "prelude" and last:
+                    return dict(vpt=vpt)
             if last:
                 q, pq = q_cur.tokens(), pq_full                           # per image [1,1,P,64]
                 out = self.buf(n, self.h8, self.w8, m.d_v)
@@ -558,12 +593,6 @@ class Engine:
                 out_tok, res_tok = out, self.v_slots[j + 1]
             q_all = (q_cur._like(n, 1, pq_full, m.d_k, q_cur.sn, q_cur.sn, m.d_k, q_cur.offset) if last
                      else self.q_slots[j + 1])
-            for i in range(n):
-                # V'^T_i = W_fc @ v_src_i^T + b  -> rows d_v, cols P'
-                self._conv_tc(plan, wfc["view"], vpt.image(i).narrow_c(pk), w_hi=v_src.image(i).ptr,
-                              w_lo=v_src.image(i).ptr_lo, w_ld=v_src.sw, cout=pk,
-                              scale=self.const_vec(wfc["inv_scale"], pkp), bias=fc.bias,
-                              bias_along_m=True, name=name + ".fc")
             k_slot = self.k_slots[j]
             if self.fused_attn:
                 # one kernel: QK^T -> softmax -> PV (+ residual); the attention matrix stays on chip
@@ -620,8 +649,14 @@ class Engine:
             a in ("img", "out") for _, args in plan.ops[1:-1] for a in args if isinstance(a, str))
         subst = {"img": img_ptr, "out": out_ptr, "stream": stream.cuda_stream}
 
-        def call(op, sub):
+        def call(op, sub, main=None):
             fn, args = op
+            if fn == "fork":
+                self.side_stream.wait_stream(main)
+                return
+            if fn == "join":
+                main.wait_stream(self.side_stream)
+                return
             rc = fn(*[sub[a] if isinstance(a, str) else a for a in args])
             if rc != 0:
                 _cabi.check(rc, fn.__name__)
@@ -629,9 +664,11 @@ class Engine:
         if getattr(plan, "graph", None) is None:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                cap = {"stream": torch.cuda.current_stream(self.device).cuda_stream}
+                cap_main = torch.cuda.current_stream(self.device)
+                cap = {"stream": cap_main.cuda_stream,
+                       "side": self.side_stream.cuda_stream if self.side_stream is not None else None}
                 for op in plan.ops[1:-1]:
-                    call(op, cap)
+                    call(op, cap, cap_main)
             plan.graph = g
         call(first, subst)
         plan.graph.replay()
@@ -640,8 +677,16 @@ class Engine:
     def run(self, plan: FramePlan, img_ptr: int, out_ptr: int, stream: int, probe=None):
         """Enqueue the frame.  probe = (op_name, event_before, event_after) brackets one op with CUDA
         events (bench.py times the dominant kernel live this way)."""
-        subst = {"img": img_ptr, "out": out_ptr, "stream": stream}
+        subst = {"img": img_ptr, "out": out_ptr, "stream": stream,
+                 "side": self.side_stream.cuda_stream if self.side_stream is not None else None}
+        main = torch.cuda.current_stream(self.device) if self.side_stream is not None else None
         for i, (fn, args) in enumerate(plan.ops):
+            if fn == "fork":
+                self.side_stream.wait_stream(main)
+                continue
+            if fn == "join":
+                main.wait_stream(self.side_stream)
+                continue
             hit = probe is not None and plan.names[i] == probe[0]
             if hit:
                 probe[1].record()

@@ -109,6 +109,26 @@ def test_td4_512x1024_against_oracle_two_cycles():
     assert worst <= LOGIT_TOL
 
 
+@pytest.mark.parametrize("arch,backbone,H,W,frames", [
+    ("td2_psp50", "resnet50", 512, 1024, 3),   # BASELINE configs[0]: td2-psp50 frame pair(s) at 512x1024
+    ("td2_psp50", "resnet34", 720, 960, 3),    # BASELINE configs[3] stand-in ('td2-bise34'): 90x120 map, P'=690
+])
+def test_baseline_td2_configs_against_oracle(arch, backbone, H, W, frames):
+    from tdnet_b200.model.arch import feature_hw
+    oracle, sd = make_oracle(arch, backbone, H, W)
+    h8, w8 = feature_hw(H, W)
+    net = build_model(arch, backbone, h8, w8, sd)
+    for i, f in enumerate(synth_clip(frames, H, W, clip_id=5)):
+        ref = oracle(f, pos_id=i % 2)
+        out = net(f.cuda(), pos_id=i % 2).cpu()
+        e = max_abs(out, ref)
+        rep = argmax_report(out, ref, max(e, 1e-6))
+        record(f"oracle/{arch}_{backbone}_{H}x{W}/frame{i}", max_abs=e, rel_l2=rel_l2(out, ref), **rep)
+        assert e <= LOGIT_TOL, (i, e)
+        assert rep["mismatch_decided"] == 0, rep
+    assert net.K_queue[0].shape[1] == ((h8 - 1) // 4 + 1) * ((w8 - 1) // 4 + 1)
+
+
 def test_full_size_1024x2048_properties():
     """BASELINE config 2 at full size: determinism, FIFO shapes, finite logits, oracle parity on one
     steady-state frame (the oracle needs ~3 s/frame on the host, so five frames only)."""
