@@ -218,6 +218,7 @@ def run_ours(args, rank, world):
     copy_s, d2h_s = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
     dev_in = [torch.empty_like(dev_frames[0]) for _ in range(2)]
     labels_host = [torch.empty((BATCH, H, W), dtype=torch.int64).pin_memory() for _ in range(2)]
+    labels_host_u8 = [torch.empty((BATCH, H, W), dtype=torch.uint8).pin_memory() for _ in range(2)]
     ev_in = [torch.cuda.Event() for _ in range(2)]
     ev_consumed = [torch.cuda.Event() for _ in range(2)]
     ev_done = [torch.cuda.Event() for _ in range(2)]
@@ -236,31 +237,52 @@ def run_ours(args, rank, world):
     copy_s.wait_event(e2)
     d2h_s.wait_event(e2)
     prefetch(step, 0, first=True)
-    for i in range(args.steps):
-        slot = i % 2
-        stream.wait_event(ev_in[slot])
-        out = net(dev_in[slot], pos_id=step % 4)
-        ev_consumed[slot].record(stream)
-        labels = out.max(1)[1]                              # Testing/test.py:61
-        ev_done[slot].record(stream)
-        if i + 1 < args.steps:
-            prefetch(step + 1, slot ^ 1, first=(i == 0))
-        with torch.cuda.stream(d2h_s):
-            d2h_s.wait_event(ev_done[slot])
-            labels_host[slot].copy_(labels, non_blocking=True)
-            labels.record_stream(d2h_s)
-            ev_d2h[slot].record(d2h_s)
-        step += 1
-    stream.wait_stream(d2h_s)
+
+    def e2e_loop(use_label_kernel):
+        nonlocal step
+        for i in range(args.steps):
+            slot = i % 2
+            stream.wait_event(ev_in[slot])
+            if use_label_kernel:
+                labels = net.forward_labels(dev_in[slot], pos_id=step % 4)   # fused upsample + arg-max, uint8
+            else:
+                out = net(dev_in[slot], pos_id=step % 4)
+                labels = out.max(1)[1]                          # Testing/test.py:61
+            ev_consumed[slot].record(stream)
+            ev_done[slot].record(stream)
+            if i + 1 < args.steps:
+                prefetch(step + 1, slot ^ 1, first=(i == 0))
+            with torch.cuda.stream(d2h_s):
+                d2h_s.wait_event(ev_done[slot])
+                (labels_host_u8 if use_label_kernel else labels_host)[slot].copy_(labels, non_blocking=True)
+                labels.record_stream(d2h_s)
+                ev_d2h[slot].record(d2h_s)
+            step += 1
+        stream.wait_stream(d2h_s)
+
+    e2e_loop(False)
     e3.record(stream)
     barrier()
     ms_e2e = e2.elapsed_time(e3)
+
+    # variant: labels straight from the fused upsample+arg-max kernel, uint8 D2H
+    barrier()
+    e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e4.record(stream)
+    copy_s.wait_event(e4)
+    d2h_s.wait_event(e4)
+    prefetch(step, 0, first=True)
+    e2e_loop(True)
+    e5.record(stream)
+    barrier()
+    ms_e2e_labels = e4.elapsed_time(e5)
 
     # ---- dominant kernel, timed live with CUDA events around its launch inside running frames
     dom_ms = net.time_dominant_op(dev_frames, step, reps=min(args.steps, 12)) if hasattr(net, "time_dominant_op") else None
 
     total_frames, ms_dev, fps = whole_job_throughput(args.steps, ms_dev, device=dev)
     _, ms_e2e, fps_e2e = whole_job_throughput(args.steps, ms_e2e, device=dev)
+    _, ms_e2e_labels, fps_e2e_labels = whole_job_throughput(args.steps, ms_e2e_labels, device=dev)
     if rank == 0:
         peaks = _peaks()
         roof = None
@@ -285,6 +307,9 @@ def run_ours(args, rank, world):
             "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": BATCH * 3 * H * W * 4,
                     "d2h_bytes_per_step": BATCH * H * W * 8, "ms_per_step": ms_e2e / args.steps,
                     "pipeline": "H2D of frame i+1 and D2H of labels i-1 overlap compute of frame i (3 streams)"},
+            "e2e_labels": {"value": fps_e2e_labels, "unit": "frames/s", "h2d_bytes_per_step": BATCH * 3 * H * W * 4,
+                           "d2h_bytes_per_step": BATCH * H * W, "ms_per_step": ms_e2e_labels / args.steps,
+                           "api": "model.forward_labels(image, pos_id): fused upsample+arg-max, uint8 label map"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof,
             "cpu_baseline": cpu_baseline() if (world == 1 and not args.no_cpu_baseline) else None,
         }

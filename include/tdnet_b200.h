@@ -187,6 +187,13 @@ int tdn_image_to_nhwc(const float* nchw, int32_t n, int32_t c, int32_t h, int32_
 int tdn_stem_conv_pool(const float* nchw, int32_t n, int32_t h, int32_t w, const float* weight,
                        const float* scale, const float* bias, const tdn_tensor* out, void* stream);
 
+/* Device-side frame ingest: the same fused stem reading the camera frame as uint8 HWC
+ * [n,h,w,3] and normalising on the fly through a host-built table lut[3][256] with
+ * lut[c][v] = (float)((v / 255.0 - mean[c]) / std[c]) evaluated in fp64 -- bit-identical to
+ * Testing/dataloader.py:66-71 ((img/255.0 - mean)/std, then .float()); H2D shrinks from 12 to 3 bytes/pixel. */
+int tdn_stem_conv_pool_u8(const uint8_t* hwc, const float* lut, int32_t n, int32_t h, int32_t w, const float* weight,
+                          const float* scale, const float* bias, const tdn_tensor* out, void* stream);
+
 /* F.max_pool2d(kernel 3, stride 2, padding 1) of the stem (resnet.py:137,208), NHWC fp32. */
 int tdn_maxpool3x3s2(const tdn_tensor* in, const tdn_tensor* out, void* stream);
 
@@ -243,6 +250,11 @@ int tdn_layernorm_hw_apply(const tdn_tensor* x, const float* mean, const float* 
  * low-resolution logits -> NCHW fp32 [n, c, H, W], the tensor test.py:53,61 consumes. */
 int tdn_upsample_logits(const tdn_tensor* in, float* out_nchw, int32_t out_h, int32_t out_w,
                         void* stream);
+
+/* Same interpolation with the arg-max over classes fused in (Testing/test.py:61: output.max(1)[1]; lowest
+ * index wins ties): NHWC fp32 low-resolution logits -> uint8 labels [n, H, W].  Bit-consistent with
+ * tdn_upsample_logits (labels == argmax of the logits that call would write).  SURVEY.md 8f rank 1. */
+int tdn_upsample_argmax(const tdn_tensor* in, uint8_t* labels, int32_t out_h, int32_t out_w, void* stream);
 
 /* Library info / errors. */
 int tdn_abi_version(void);

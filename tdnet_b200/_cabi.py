@@ -67,6 +67,8 @@ SIGNATURES = {
     "tdn_image_to_nhwc": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _TP, C.c_void_p]),
     "tdn_stem_conv_pool": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                      _TP, C.c_void_p]),
+    "tdn_stem_conv_pool_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, _TP, C.c_void_p]),
     "tdn_maxpool3x3s2": (C.c_int, [_TP, _TP, C.c_void_p]),
     "tdn_psp_pool": (C.c_int, [_TP, _TP, C.c_void_p, C.c_uint64, C.c_void_p]),
     "tdn_psp_pool_workspace_bytes": (C.c_uint64, [C.c_int32, C.c_int32, C.c_int32]),
@@ -81,6 +83,7 @@ SIGNATURES = {
     "tdn_layernorm_hw_stats": (C.c_int, [_TP, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_uint64, C.c_void_p]),
     "tdn_layernorm_hw_workspace_bytes": (C.c_uint64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "tdn_layernorm_hw_apply": (C.c_int, [_TP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _TP, C.c_void_p]),
+    "tdn_upsample_argmax": (C.c_int, [_TP, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "tdn_upsample_logits": (C.c_int, [_TP, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
 }
 

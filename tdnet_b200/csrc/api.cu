@@ -47,8 +47,10 @@ int layernorm_hw_stats(const tdn_tensor*, float*, float*, float, void*, size_t, 
 int layernorm_hw_apply(const tdn_tensor*, const float*, const float*, const float*, const float*,
                        const tdn_tensor*, cudaStream_t);
 int upsample_logits(const tdn_tensor*, float*, int, int, cudaStream_t);
+int upsample_argmax(const tdn_tensor*, uint8_t*, int, int, cudaStream_t);
 int conv2d_tc(const tdn_tc_conv_desc*, cudaStream_t);
-int stem_conv_pool(const float*, int, int, int, const float*, const float*, const float*, const tdn_tensor*, cudaStream_t);
+int stem_conv_pool(const float*, const uint8_t*, const float*, int, int, int, const float*, const float*, const float*,
+                   const tdn_tensor*, cudaStream_t);
 int attention_tc(const tdn_attention_desc*, cudaStream_t);
 int split16(const tdn_tensor*, const tdn_tensor*, cudaStream_t);
 int merge16(const tdn_tensor*, const tdn_tensor*, cudaStream_t);
@@ -127,7 +129,13 @@ int tdn_image_to_nhwc(const float* nchw, int32_t n, int32_t c, int32_t h, int32_
 
 int tdn_stem_conv_pool(const float* nchw, int32_t n, int32_t h, int32_t w, const float* weight, const float* scale,
                        const float* bias, const tdn_tensor* out, void* stream) {
-  return stem_conv_pool(nchw, n, h, w, weight, scale, bias, out, (cudaStream_t)stream);
+  return stem_conv_pool(nchw, nullptr, nullptr, n, h, w, weight, scale, bias, out, (cudaStream_t)stream);
+}
+
+int tdn_stem_conv_pool_u8(const uint8_t* hwc, const float* lut, int32_t n, int32_t h, int32_t w, const float* weight,
+                          const float* scale, const float* bias, const tdn_tensor* out, void* stream) {
+  TDN_REQUIRE(hwc && lut, TDN_ERR_INVALID, "stem_u8: null image / lut");
+  return stem_conv_pool(nullptr, hwc, lut, n, h, w, weight, scale, bias, out, (cudaStream_t)stream);
 }
 
 int tdn_maxpool3x3s2(const tdn_tensor* in, const tdn_tensor* out, void* stream) {
@@ -186,6 +194,10 @@ int tdn_layernorm_hw_apply(const tdn_tensor* x, const float* mean, const float* 
 
 int tdn_upsample_logits(const tdn_tensor* in, float* out_nchw, int32_t out_h, int32_t out_w, void* stream) {
   return upsample_logits(in, out_nchw, out_h, out_w, (cudaStream_t)stream);
+}
+
+int tdn_upsample_argmax(const tdn_tensor* in, uint8_t* labels, int32_t out_h, int32_t out_w, void* stream) {
+  return upsample_argmax(in, labels, out_h, out_w, (cudaStream_t)stream);
 }
 
 }  // extern "C"

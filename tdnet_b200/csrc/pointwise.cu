@@ -95,7 +95,7 @@ int maxpool3x3s2(const tdn_tensor* in, const tdn_tensor* out, cudaStream_t strea
 __device__ __forceinline__ int bin_start(int i, int o, int len) { return (i * len) / o; }
 __device__ __forceinline__ int bin_end(int i, int o, int len) { return ((i + 1) * len + o - 1) / o; }
 
-constexpr int PSP_PARTS = 4;   // x-segments per row (more CTAs in flight; partial sums are added in pass 2)
+constexpr int PSP_PARTS = 1;   // x-segments per row; splitting rows (tried 4) only added pass-2 reads, the pass is not occupancy-bound
 
 __global__ void psp_rowsum_kernel(View in, float* __restrict__ rowsum) {
   // One pass over a quarter of the row: every pyramid level keeps the running sum of its current column
@@ -641,6 +641,15 @@ int layernorm_hw_apply(const tdn_tensor* x, const float* mean, const float* rstd
   return TDN_OK;
 }
 
+// Bilinear blend with explicitly rounded products and sums (no FMA contraction), shared by the logits and the
+// arg-max upsamplers so that both produce bit-identical interpolated values.
+__device__ __forceinline__ float bilerp(float t0, float t1, float u0, float u1, float lx, float ly) {
+  const float wx0 = 1.f - lx, wy0 = 1.f - ly;
+  const float top = __fadd_rn(__fmul_rn(t0, wx0), __fmul_rn(t1, lx));
+  const float bot = __fadd_rn(__fmul_rn(u0, wx0), __fmul_rn(u1, lx));
+  return __fadd_rn(__fmul_rn(top, wy0), __fmul_rn(bot, ly));
+}
+
 // ---------------------------------------------------------------------------------------------
 // Final x8 bilinear upsample (align_corners) NHWC low-res logits -> NCHW fp32.
 // One thread produces 4 consecutive x of one (n, y) for all classes: float4 streaming stores that are
@@ -682,16 +691,13 @@ __global__ void __launch_bounds__(256) upsample_logits_kernel(View in, float* __
         const int d0 = x0[j] - xa, d1 = x1[j] - xa;            // 0..1 and 0..2
         const float ta = d0 == 0 ? t0 : t1, tb = d1 == 0 ? t0 : (d1 == 1 ? t1 : t2);
         const float ua = d0 == 0 ? u0 : u1, ub = d1 == 0 ? u0 : (d1 == 1 ? u1 : u2);
-        const float top = ta * (1.f - lx[j]) + tb * lx[j];
-        const float bot = ua * (1.f - lx[j]) + ub * lx[j];
-        v[j] = top * (1.f - ly) + bot * ly;
+        v[j] = bilerp(ta, tb, ua, ub, lx[j], ly);
       }
     } else {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        float top = r0[x0[j] * in.sw + c] * (1.f - lx[j]) + r0[x1[j] * in.sw + c] * lx[j];
-        float bot = r1[x0[j] * in.sw + c] * (1.f - lx[j]) + r1[x1[j] * in.sw + c] * lx[j];
-        v[j] = top * (1.f - ly) + bot * ly;
+        v[j] = bilerp(r0[x0[j] * in.sw + c], r0[x1[j] * in.sw + c], r1[x0[j] * in.sw + c], r1[x1[j] * in.sw + c],
+                      lx[j], ly);
       }
     }
     float* oc = o + c * plane;
@@ -703,6 +709,59 @@ __global__ void __launch_bounds__(256) upsample_logits_kernel(View in, float* __
         if (xq * 4 + j < W) oc[j] = v[j];
     }
   }
+}
+
+// Same interpolation, but only the arg-max class leaves the chip: uint8 label map [n, H, W]
+// (Testing/test.py:61 takes output.max(1)[1] right after the forward; lowest index wins ties, like torch).
+// Saves the 159 MB fp32 logits write and turns a 16.8 MB int64 D2H into 2 MB.
+__global__ void __launch_bounds__(256) upsample_argmax_kernel(View in, uint8_t* __restrict__ labels, int H, int W,
+                                                              float sy, float sx) {
+  const int W4 = (W + 3) >> 2;
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long total = (long long)in.n * H * W4;
+  if (idx >= total) return;
+  int xq = idx % W4;
+  long long t = idx / W4;
+  int y = t % H;
+  int b = t / H;
+  int y0, y1; float ly;
+  src_index(y, sy, in.h, y0, y1, ly);
+  int x0[4], x1[4]; float lx[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) src_index(min(xq * 4 + j, W - 1), sx, in.w, x0[j], x1[j], lx[j]);
+  const float* r0 = in.p + b * in.sn + y0 * in.sh;
+  const float* r1 = in.p + b * in.sn + y1 * in.sh;
+  float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  int arg[4] = {0, 0, 0, 0};
+  for (int c = 0; c < in.c; ++c) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      // identical arithmetic to upsample_logits_kernel, so labels == argmax of the logits it would write
+      const float v = bilerp(r0[x0[j] * in.sw + c], r0[x1[j] * in.sw + c], r1[x0[j] * in.sw + c],
+                             r1[x1[j] * in.sw + c], lx[j], ly);
+      if (v > best[j]) { best[j] = v; arg[j] = c; }
+    }
+  }
+  uint8_t* o = labels + ((long long)b * H + y) * W + xq * 4;
+  if ((xq * 4 + 3 < W) && ((W & 3) == 0)) {
+    *reinterpret_cast<uchar4*>(o) = make_uchar4((uint8_t)arg[0], (uint8_t)arg[1], (uint8_t)arg[2], (uint8_t)arg[3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (xq * 4 + j < W) o[j] = (uint8_t)arg[j];
+  }
+}
+
+int upsample_argmax(const tdn_tensor* in, uint8_t* labels, int out_h, int out_w, cudaStream_t stream) {
+  int rc;
+  if ((rc = check_f32_tensor(in, "upsample_argmax.in"))) return rc;
+  TDN_REQUIRE(labels && out_h > 0 && out_w > 0 && in->c <= 256, TDN_ERR_INVALID, "upsample_argmax: bad output / > 256 classes");
+  TDN_REQUIRE((((uintptr_t)labels) & 3u) == 0, TDN_ERR_INVALID, "upsample_argmax: labels must be 4-byte aligned");
+  long long total = (long long)in->n * out_h * ((out_w + 3) / 4);
+  upsample_argmax_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(make_view(*in), labels, out_h, out_w,
+                                                                   ac_scale(in->h, out_h), ac_scale(in->w, out_w));
+  TDN_LAUNCH_OK();
+  return TDN_OK;
 }
 
 int upsample_logits(const tdn_tensor* in, float* out_nchw, int out_h, int out_w, cudaStream_t stream) {

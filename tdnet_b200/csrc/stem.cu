@@ -24,7 +24,9 @@ constexpr int ST_CONV_PITCH = 66;                    // floats per conv pixel in
 constexpr int ST_SMEM_FLOATS = ST_IN_FLOATS + ST_K * 64 + ST_C * ST_C * ST_CONV_PITCH + 128;
 
 struct StemParams {
-  const float* img;      // [n,3,H,W]
+  const float* img;      // [n,3,H,W] fp32 NCHW ...
+  const uint8_t* img_u8; // ... or [n,H,W,3] uint8 HWC with `lut` (device-side frame ingest)
+  const float* lut;      // [3][256]: lut[c][v] = float((v/255.0 - mean[c]) / std[c]) computed in fp64 on the host
   const float* w;        // [147][64]  (k = (c*7 + ky)*7 + kx)
   const float* scale;    // [64]
   const float* bias;     // [64]
@@ -32,6 +34,7 @@ struct StemParams {
   int H, W, Hc, Wc, Hp, Wp;
 };
 
+template <bool U8>
 __global__ void __launch_bounds__(ST_THREADS, 1) stem_conv_pool_kernel(const StemParams p) {
   extern __shared__ __align__(16) float st_smem[];
   float* s_in = st_smem;                               // [3][ST_IH][ST_IW]
@@ -48,14 +51,18 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_conv_pool_kernel(const Ste
   for (int i = tid; i < ST_K * 64; i += ST_THREADS) s_w[i] = __ldg(p.w + i);
   if (tid < 64) { s_sb[tid] = __ldg(p.scale + tid); s_sb[64 + tid] = __ldg(p.bias + tid); }
   const float* img = p.img + (long long)b * 3 * p.H * p.W;
+  const uint8_t* img8 = p.img_u8 + (long long)b * 3 * p.H * p.W;
   for (int i = tid; i < ST_IN_FLOATS; i += ST_THREADS) {
     const int x = i % ST_IW;
     const int t = i / ST_IW;
     const int y = t % ST_IH;
     const int c = t / ST_IH;
     const int iy = iy0 + y, ix = ix0 + x;
-    float v = 0.f;
-    if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) v = __ldg(img + ((long long)c * p.H + iy) * p.W + ix);
+    float v = 0.f;   // zero padding applies to the normalised tensor
+    if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
+      if (U8) v = __ldg(p.lut + c * 256 + __ldg(img8 + ((long long)iy * p.W + ix) * 3 + c));
+      else v = __ldg(img + ((long long)c * p.H + iy) * p.W + ix);
+    }
     s_in[i] = v;
   }
   __syncthreads();
@@ -122,13 +129,14 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_conv_pool_kernel(const Ste
   }
 }
 
-int stem_conv_pool(const float* nchw, int n, int h, int w, const float* weight, const float* scale,
-                   const float* bias, const tdn_tensor* out, cudaStream_t stream) {
-  TDN_REQUIRE(nchw && weight && scale && bias, TDN_ERR_INVALID, "stem: null pointer");
+int stem_conv_pool(const float* nchw, const uint8_t* hwc_u8, const float* lut, int n, int h, int w,
+                   const float* weight, const float* scale, const float* bias, const tdn_tensor* out,
+                   cudaStream_t stream) {
+  TDN_REQUIRE((nchw || (hwc_u8 && lut)) && weight && scale && bias, TDN_ERR_INVALID, "stem: null pointer");
   int rc;
   if ((rc = check_tensor(out, "stem.out"))) return rc;
   StemParams p;
-  p.img = nchw; p.w = weight; p.scale = scale; p.bias = bias;
+  p.img = nchw; p.img_u8 = hwc_u8; p.lut = lut; p.w = weight; p.scale = scale; p.bias = bias;
   p.out = make_view(*out);
   p.H = h; p.W = w;
   p.Hc = (h - 1) / 2 + 1; p.Wc = (w - 1) / 2 + 1;
@@ -138,11 +146,13 @@ int stem_conv_pool(const float* nchw, int n, int h, int w, const float* weight, 
   const int smem = ST_SMEM_FLOATS * (int)sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
-    TDN_CUDA_OK(cudaFuncSetAttribute(stem_conv_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    TDN_CUDA_OK(cudaFuncSetAttribute(stem_conv_pool_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    TDN_CUDA_OK(cudaFuncSetAttribute(stem_conv_pool_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
   dim3 grid(ceil_div(p.Wp, ST_P), ceil_div(p.Hp, ST_P), n);
-  stem_conv_pool_kernel<<<grid, ST_THREADS, smem, stream>>>(p);
+  if (nchw) stem_conv_pool_kernel<false><<<grid, ST_THREADS, smem, stream>>>(p);
+  else stem_conv_pool_kernel<true><<<grid, ST_THREADS, smem, stream>>>(p);
   TDN_LAUNCH_OK();
   return TDN_OK;
 }

@@ -251,6 +251,15 @@ class Engine:
             self._packed[key] = dict(w=wk, scale=pc.scale, bias=pc.bias)
         return self._packed[key]
 
+    def norm_lut(self) -> torch.Tensor:
+        """lut[c][v] = float((v/255.0 - mean[c]) / std[c]) in fp64, the arithmetic of Testing/dataloader.py:52-53,66-67."""
+        if "lut" not in self._consts:
+            v = torch.arange(256, dtype=torch.float64)[None, :] / 255.0
+            mean = torch.tensor([.485, .456, .406], dtype=torch.float64)[:, None]
+            std = torch.tensor([.229, .224, .225], dtype=torch.float64)[:, None]
+            self._consts["lut"] = ((v - mean) / std).float().contiguous().to(self.device)
+        return self._consts["lut"]
+
     def const_vec(self, value: float, length: int) -> torch.Tensor:
         key = (value, length)
         if key not in self._consts:
@@ -375,6 +384,10 @@ class Engine:
             x = self.buf(n, (hc - 1) // 2 + 1, (wc - 1) // 2 + 1, c.cout)
             plan.add(lib.tdn_stem_conv_pool, "img", n, H, W, pk["w"].data_ptr(), pk["scale"].data_ptr(),
                      pk["bias"].data_ptr(), C.byref(self._ct(plan, x)), "stream", name=c.name)
+            # alternative first op: uint8 HWC frame + normalisation table (forward_u8)
+            plan.u8_op = (lib.tdn_stem_conv_pool_u8, ("img", self.norm_lut().data_ptr(), n, H, W, pk["w"].data_ptr(),
+                                                       pk["scale"].data_ptr(), pk["bias"].data_ptr(),
+                                                       plan.ops[-1][1][7], "stream"))
         else:
             # deep stem (ResNet-50) or unfused path: NCHW image -> NHWC(4) -> conv(s) -> maxpool
             img = self.buf(n, H, W, 4, split=False)
@@ -496,6 +509,8 @@ class Engine:
         # --- final x8 bilinear upsample into the caller's output tensor (last op: it is the only one besides
         #     the first that touches a per-call pointer, which keeps everything in between graph-capturable)
         plan.add(lib.tdn_upsample_logits, C.byref(self._ct(plan, low)), "out", H, W, "stream")
+        # alternative last op: fused upsample + arg-max -> uint8 labels (forward_labels)
+        plan.labels_op = (lib.tdn_upsample_argmax, (C.byref(self._ct(plan, low)), "out", H, W, "stream"))
         plan.taps = dict(c4=c4, z=z, q_cur=q_cur, v_cur=v_cur, fused=fused, normed=normed, head=low)
         return plan
 
@@ -639,12 +654,12 @@ class Engine:
         return self._packed[key]
 
     # ------------------------------------------------------------------ execution
-    def run_graphed(self, plan: FramePlan, img_ptr: int, out_ptr: int):
+    def run_graphed(self, plan: FramePlan, img_ptr: int, out_ptr: int, labels=False, u8=False):
         """Frame through a CUDA graph: the first and last op take the per-call image / output pointers and
         are launched directly; everything in between (static buffers only) is captured once and replayed.
         The plan must have run eagerly once before (kernel attributes, lazy packing)."""
         stream = torch.cuda.current_stream(self.device)
-        first, last = plan.ops[0], plan.ops[-1]
+        first, last = (plan.u8_op if u8 else plan.ops[0]), (plan.labels_op if labels else plan.ops[-1])
         assert "img" in first[1] and "out" in last[1] and not any(
             a in ("img", "out") for _, args in plan.ops[1:-1] for a in args if isinstance(a, str))
         subst = {"img": img_ptr, "out": out_ptr, "stream": stream.cuda_stream}
@@ -674,13 +689,16 @@ class Engine:
         plan.graph.replay()
         call(last, subst)
 
-    def run(self, plan: FramePlan, img_ptr: int, out_ptr: int, stream: int, probe=None):
+    def run(self, plan: FramePlan, img_ptr: int, out_ptr: int, stream: int, probe=None, labels=False, u8=False):
         """Enqueue the frame.  probe = (op_name, event_before, event_after) brackets one op with CUDA
         events (bench.py times the dominant kernel live this way)."""
         subst = {"img": img_ptr, "out": out_ptr, "stream": stream,
                  "side": self.side_stream.cuda_stream if self.side_stream is not None else None}
         main = torch.cuda.current_stream(self.device) if self.side_stream is not None else None
-        for i, (fn, args) in enumerate(plan.ops):
+        ops = plan.ops[:-1] + [plan.labels_op] if labels else plan.ops
+        if u8:
+            ops = [plan.u8_op] + list(ops[1:])
+        for i, (fn, args) in enumerate(ops):
             if fn == "fork":
                 self.side_stream.wait_stream(main)
                 continue

@@ -121,9 +121,9 @@ class TDModel(nn.Module):
             self.Q_queue.pop(0), self.V_queue.pop(0), self.K_queue.pop(0)
 
     # ---- engine ----------------------------------------------------------------------------
-    def _engine(self, img: torch.Tensor):
+    def _engine(self, img: torch.Tensor, shape):
         from ..engine import Engine
-        n, c, h, w = img.shape
+        n, c, h, w = shape
         key = (n, h, w, img.device.index, self.engine_mode)
         eng = self._engines.get(key)
         if eng is None:
@@ -148,26 +148,56 @@ class TDModel(nn.Module):
             total += e0.elapsed_time(e1)
         return total / reps
 
+    def forward_labels(self, img, pos_id=0):
+        """Same frame step as forward(), but returns the uint8 label map [n, H, W] =
+        forward(img, pos_id).max(1)[1] (Testing/test.py:61) computed by a fused upsample + arg-max kernel:
+        the 159 MB fp32 logits tensor is never written."""
+        return self.forward(img, pos_id, _labels=True)
+
+    def forward_u8(self, frame_u8, pos_id=0, labels=False):
+        """Device-side frame ingest: `frame_u8` is the RGB camera frame as uint8 HWC
+        [n,H,W,3] on the GPU; (x/255 - mean)/std of Testing/dataloader.py:52-53,66-67 is applied inside the
+        stem kernel through an fp64-built table, bit-identical to feeding the normalised fp32 NCHW tensor."""
+        return self.forward(frame_u8, pos_id, _labels=labels, _u8=True)
+
+    def check_numeric_range(self):
+        """Raise if any SPLIT16 activation ever exceeded the fp16 range guard (|x| > 6e4) since the
+        engine was created.  Synchronises; meant for validation runs, not the frame loop."""
+        for eng in self._engines.values():
+            if int(eng.range_flag.item()) != 0:
+                raise RuntimeError("tdnet_b200: an activation exceeded the SPLIT16 range (|x| > 6e4); use "
+                                   "engine_mode='simt' (fp32 planes) for this checkpoint")
+
     @torch.no_grad()
-    def forward(self, img, pos_id=0, _probe=None):
+    def forward(self, img, pos_id=0, _probe=None, _labels=False, _u8=False):
         if not img.is_cuda:
             raise RuntimeError("tdnet_b200 runs on a CUDA (sm_100) device only; there is no CPU path. "
                                "Move the model and the input with .to('cuda').")
-        if img.dtype != torch.float32 or img.dim() != 4 or img.shape[1] != 3:
+        if _u8:
+            if img.dtype != torch.uint8 or img.dim() != 4 or img.shape[3] != 3:
+                raise RuntimeError("forward_u8 expects a uint8 HWC frame batch [n,H,W,3]")
+            if len(self.arch.stems[1]) != 1:
+                raise NotImplementedError("forward_u8 needs the single-conv stem (ResNet-18/34 backbones)")
+            shape_nchw = (img.shape[0], 3, img.shape[1], img.shape[2])
+        elif img.dtype != torch.float32 or img.dim() != 4 or img.shape[1] != 3:
             raise RuntimeError("expected an fp32 NCHW image batch [n,3,H,W] (Testing/dataloader.py:69-71)")
         if not (0 <= pos_id < self.PATHS):
             raise RuntimeError(f"pos_id must be in [0,{self.PATHS})")
         img = img.contiguous()
-        n, _, h, w = img.shape
-        eng = self._engine(img)
+        n, _, h, w = shape_nchw if _u8 else img.shape
+        eng = self._engine(img, (n, 3, h, w))
         steady = len(self.Q_queue) >= self.arch.depth
         plan = eng.plan(pos_id + 1, steady)
-        out = torch.empty((n, self.nclass, h, w), dtype=torch.float32, device=img.device)
+        if _labels:
+            out = torch.empty((n, h, w), dtype=torch.uint8, device=img.device)
+        else:
+            out = torch.empty((n, self.nclass, h, w), dtype=torch.float32, device=img.device)
         plan.uses = getattr(plan, "uses", 0) + 1
         if self.use_cuda_graph and _probe is None and plan.uses > 1:
-            eng.run_graphed(plan, img.data_ptr(), out.data_ptr())
+            eng.run_graphed(plan, img.data_ptr(), out.data_ptr(), labels=_labels, u8=_u8)
         else:
-            eng.run(plan, img.data_ptr(), out.data_ptr(), torch.cuda.current_stream(img.device).cuda_stream, _probe)
+            eng.run(plan, img.data_ptr(), out.data_ptr(), torch.cuda.current_stream(img.device).cuda_stream, _probe,
+                    labels=_labels, u8=_u8)
         # FIFO bookkeeping mirrors buffer_contral; the tensors are views of the engine's device slots
         # (slot j = j-th oldest frame once the FIFO is full).
         depth = self.arch.depth

@@ -172,3 +172,37 @@ def test_api_errors_match_reference_behaviour():
     sd.pop("head1.conv5.4.bias")
     with pytest.raises(RuntimeError):                                    # strict=True, td4_psp18.py:237
         net.load_state_dict(sd, strict=True)
+
+
+def test_forward_labels_equals_argmax_of_logits():
+    """forward_labels (fused upsample + arg-max) == forward().max(1)[1] (test.py:61)."""
+    H, W = 128, 256
+    sd = make_weights("td4_psp18", "resnet18", 16, 32)
+    a = build_model("td4_psp18", "resnet18", 16, 32, sd)
+    b = build_model("td4_psp18", "resnet18", 16, 32, sd)
+    for i, f in enumerate(synth_clip(7, H, W, clip_id=9)):
+        logits = a(f.cuda(), pos_id=i % 4)
+        labels = b.forward_labels(f.cuda(), pos_id=i % 4)
+        assert labels.dtype == torch.uint8 and labels.shape == (1, H, W)
+        assert torch.equal(labels.long(), logits.max(1)[1]), i
+    a.check_numeric_range()
+
+
+def test_forward_u8_is_bit_identical_to_normalised_fp32_input():
+    """Device-side ingest: uint8 HWC frames through the stem's normalisation table ==
+    the dataloader arithmetic of Testing/dataloader.py:66-71 done on the host in fp64."""
+    import numpy as np
+    H, W = 96, 160
+    sd = make_weights("td2_psp50", "resnet18", 12, 20)
+    a = build_model("td2_psp50", "resnet18", 12, 20, sd)
+    b = build_model("td2_psp50", "resnet18", 12, 20, sd)
+    rng = np.random.default_rng(0)
+    mean, std = np.array([.485, .456, .406]), np.array([.229, .224, .225])
+    for i in range(4):
+        u8 = rng.integers(0, 256, (1, H, W, 3), dtype=np.uint8)
+        ref_in = torch.from_numpy(((u8 / 255.0 - mean) / std).transpose(0, 3, 1, 2)).float().contiguous()
+        out_ref = a(ref_in.cuda(), pos_id=i % 2)
+        out_u8 = b.forward_u8(torch.from_numpy(u8).cuda(), pos_id=i % 2)
+        assert torch.equal(out_ref, out_u8), i
+    lab = b.forward_u8(torch.from_numpy(u8).cuda(), pos_id=0, labels=True)
+    assert lab.dtype == torch.uint8 and lab.shape == (1, H, W)
