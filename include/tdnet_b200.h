@@ -202,7 +202,7 @@ int tdn_maxpool3x3s2(const tdn_tensor* in, const tdn_tensor* out, void* stream);
  * bin i of size o covers rows [floor(i*H/o), ceil((i+1)*H/o)). */
 int tdn_psp_pool(const tdn_tensor* in, const tdn_tensor* out, void* workspace, uint64_t workspace_bytes,
                  void* stream);
-/* Workspace the call above needs (n*h*4*12*c floats: per row, 4 column segments x 12 column ranges). */
+/* Workspace the call above needs: n*h*12*c floats (per row, the sums over the 12 column ranges). */
 uint64_t tdn_psp_pool_workspace_bytes(int32_t n, int32_t h, int32_t c);
 
 /* F.interpolate(mode='bilinear', align_corners=True) of a small NHWC map into a (channel-slice)

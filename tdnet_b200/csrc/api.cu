@@ -143,7 +143,7 @@ int tdn_maxpool3x3s2(const tdn_tensor* in, const tdn_tensor* out, void* stream) 
 }
 
 uint64_t tdn_psp_pool_workspace_bytes(int32_t n, int32_t h, int32_t c) {
-  return (uint64_t)n * h * 4 /*x-segments*/ * 12 * c * sizeof(float);
+  return (uint64_t)n * h * 12 * c * sizeof(float);
 }
 
 int tdn_psp_pool(const tdn_tensor* in, const tdn_tensor* out, void* workspace, uint64_t workspace_bytes,

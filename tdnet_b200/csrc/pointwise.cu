@@ -95,7 +95,8 @@ int maxpool3x3s2(const tdn_tensor* in, const tdn_tensor* out, cudaStream_t strea
 __device__ __forceinline__ int bin_start(int i, int o, int len) { return (i * len) / o; }
 __device__ __forceinline__ int bin_end(int i, int o, int len) { return ((i + 1) * len + o - 1) / o; }
 
-constexpr int PSP_PARTS = 1;   // x-segments per row; splitting rows (tried 4) only added pass-2 reads, the pass is not occupancy-bound
+constexpr int PSP_PARTS = 1;   // x-segments per row (tdn_psp_pool_workspace_bytes assumes 1); splitting rows into 4 was
+                               // measured slower: it only adds pass-2 reads, the pass is not occupancy-bound
 
 __global__ void psp_rowsum_kernel(View in, float* __restrict__ rowsum) {
   // One pass over a quarter of the row: every pyramid level keeps the running sum of its current column

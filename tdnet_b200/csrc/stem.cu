@@ -5,10 +5,11 @@
 // pre-pool map (134 MB at 1024x2048) never leaves shared memory.
 //
 // One CTA = 8 x 8 pooled pixels = 17 x 17 conv pixels.  Warp r owns conv row r: its 32 lanes hold two
-// output channels each (lane, lane+32) for all 17 pixels of the row (34 fp32 accumulators).  For every
-// (channel, filter row) the warp reads the 39 input floats of that row segment with ten 16-byte broadcast
-// loads and its 14 weights with conflict-free 4-byte loads, then does 7 x 17 x 2 FMAs per lane: 24
-// shared-memory wavefronts per 238 FMA instructions, i.e. FMA-bound, not load/store-bound.
+// output channels each (lane, lane+32) for all 17 pixels of the row, as 17 packed fp32x2 accumulators.
+// The arithmetic is FFMA2 (fma.rn.f32x2: two IEEE fp32 FMAs per instruction): plain 3-operand FFMA issues
+// at half rate on this part (measured: the scalar version of this kernel and conv_simt both sit at ~37 of
+// the nominal 75 TFLOP/s), so operands are laid out as pairs: inputs are stored duplicated ({v, v}) and
+// weights interleaved ({w[ch], w[ch+32]}) in shared memory, accumulators are the channel pair.
 #include "common.cuh"
 
 namespace tdn {
@@ -19,9 +20,17 @@ constexpr int ST_IH = 2 * ST_C + 5;                  // 39 input rows
 constexpr int ST_IW = 40;                            // 39 input cols, padded to a multiple of 4
 constexpr int ST_K = 147;                            // 3 * 7 * 7
 constexpr int ST_THREADS = 32 * ST_C;                // 544: one warp per conv row
-constexpr int ST_IN_FLOATS = 3 * ST_IH * ST_IW;      // 4680 (multiple of 4)
+constexpr int ST_IN_FLOATS = 2 * 3 * ST_IH * ST_IW;  // 9360: every input value is stored twice ({v, v}) so that a
+                                                     // shared-memory load lands directly as an FFMA2 operand pair
 constexpr int ST_CONV_PITCH = 66;                    // floats per conv pixel in smem (64 + 2: conflict-free float2 rows)
 constexpr int ST_SMEM_FLOATS = ST_IN_FLOATS + ST_K * 64 + ST_C * ST_C * ST_CONV_PITCH + 128;
+
+__device__ __forceinline__ void ffma2(uint64_t& c, uint64_t a, uint64_t b) {   // c.{lo,hi} += a.{lo,hi} * b.{lo,hi}
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
 
 struct StemParams {
   const float* img;      // [n,3,H,W] fp32 NCHW ...
@@ -48,11 +57,15 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_conv_pool_kernel(const Ste
   const int cy0 = 2 * py0 - 1, cx0 = 2 * px0 - 1;      // first conv pixel of the tile (may be -1)
   const int iy0 = 2 * cy0 - 3, ix0 = 2 * cx0 - 3;      // first input pixel of the patch
 
-  for (int i = tid; i < ST_K * 64; i += ST_THREADS) s_w[i] = __ldg(p.w + i);
+  // weights -> [k][lane][2] = {w[k][lane], w[k][lane + 32]}
+  for (int i = tid; i < ST_K * 64; i += ST_THREADS) {
+    const int k = i >> 6, r = i & 63;
+    s_w[i] = __ldg(p.w + k * 64 + (r >> 1) + (r & 1) * 32);
+  }
   if (tid < 64) { s_sb[tid] = __ldg(p.scale + tid); s_sb[64 + tid] = __ldg(p.bias + tid); }
   const float* img = p.img + (long long)b * 3 * p.H * p.W;
   const uint8_t* img8 = p.img_u8 + (long long)b * 3 * p.H * p.W;
-  for (int i = tid; i < ST_IN_FLOATS; i += ST_THREADS) {
+  for (int i = tid; i < 3 * ST_IH * ST_IW; i += ST_THREADS) {
     const int x = i % ST_IW;
     const int t = i / ST_IW;
     const int y = t % ST_IH;
@@ -63,35 +76,42 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_conv_pool_kernel(const Ste
       if (U8) v = __ldg(p.lut + c * 256 + __ldg(img8 + ((long long)iy * p.W + ix) * 3 + c));
       else v = __ldg(img + ((long long)c * p.H + iy) * p.W + ix);
     }
-    s_in[i] = v;
+    reinterpret_cast<float2*>(s_in)[i] = make_float2(v, v);
   }
   __syncthreads();
 
   {
     const int r = tid >> 5;                            // conv row of the tile (one warp each)
     const int lane = tid & 31;
-    float acc0[ST_C], acc1[ST_C];                      // channels lane and lane + 32
+    uint64_t acc[ST_C];                                // packed {channel lane, channel lane + 32}
 #pragma unroll
-    for (int j = 0; j < ST_C; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; }
+    for (int j = 0; j < ST_C; ++j) acc[j] = 0ull;
 #pragma unroll 1
     for (int cky = 0; cky < 21; ++cky) {               // (input channel, filter row)
       const int c = cky / 7, ky = cky - c * 7;
-      const float4* row4 = reinterpret_cast<const float4*>(s_in + (c * ST_IH + 2 * r + ky) * ST_IW);
-      float in[ST_IW];
+      const ulonglong2* row = reinterpret_cast<const ulonglong2*>(
+          reinterpret_cast<const float2*>(s_in) + (c * ST_IH + 2 * r + ky) * ST_IW);   // 2 duplicated inputs / load
+      const uint64_t* wk = reinterpret_cast<const uint64_t*>(s_w) + (cky * 7) * 32 + lane;
+      uint64_t wp[7];
 #pragma unroll
-      for (int q = 0; q < ST_IW / 4; ++q) {
-        const float4 v = row4[q];                      // same address in every lane: broadcast
-        in[4 * q + 0] = v.x; in[4 * q + 1] = v.y; in[4 * q + 2] = v.z; in[4 * q + 3] = v.w;
+      for (int kx = 0; kx < 7; ++kx) wp[kx] = wk[kx * 32];
+      {  // pixels 0..8 use input columns 0..22
+        uint64_t in[24];
+#pragma unroll
+        for (int q = 0; q < 12; ++q) { const ulonglong2 v = row[q]; in[2 * q] = v.x; in[2 * q + 1] = v.y; }
+#pragma unroll
+        for (int kx = 0; kx < 7; ++kx)
+#pragma unroll
+          for (int j = 0; j < 9; ++j) ffma2(acc[j], in[2 * j + kx], wp[kx]);
       }
-      const float* wk = s_w + (cky * 7) * 64 + lane;
+      {  // pixels 9..16 use input columns 18..38
+        uint64_t in[22];
 #pragma unroll
-      for (int kx = 0; kx < 7; ++kx) {
-        const float w0 = wk[kx * 64], w1 = wk[kx * 64 + 32];
+        for (int q = 0; q < 11; ++q) { const ulonglong2 v = row[9 + q]; in[2 * q] = v.x; in[2 * q + 1] = v.y; }
 #pragma unroll
-        for (int j = 0; j < ST_C; ++j) {
-          acc0[j] = fmaf(in[2 * j + kx], w0, acc0[j]);
-          acc1[j] = fmaf(in[2 * j + kx], w1, acc1[j]);
-        }
+        for (int kx = 0; kx < 7; ++kx)
+#pragma unroll
+          for (int j = 9; j < ST_C; ++j) ffma2(acc[j], in[2 * j + kx - 18], wp[kx]);
       }
     }
     // BN + ReLU; conv pixels outside the conv map become 0, which cannot change a max over ReLU outputs
@@ -103,8 +123,10 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_conv_pool_kernel(const Ste
     for (int j = 0; j < ST_C; ++j) {
       const int cx = cx0 + j;
       const bool ok = rowok && cx >= 0 && cx < p.Wc;
-      dst[j * ST_CONV_PITCH + lane] = ok ? fmaxf(fmaf(acc0[j], sc0, bi0), 0.f) : 0.f;
-      dst[j * ST_CONV_PITCH + lane + 32] = ok ? fmaxf(fmaf(acc1[j], sc1, bi1), 0.f) : 0.f;
+      float a0, a1;
+      unpack2(acc[j], a0, a1);
+      dst[j * ST_CONV_PITCH + lane] = ok ? fmaxf(fmaf(a0, sc0, bi0), 0.f) : 0.f;
+      dst[j * ST_CONV_PITCH + lane + 32] = ok ? fmaxf(fmaf(a1, sc1, bi1), 0.f) : 0.f;
     }
   }
   __syncthreads();

@@ -39,7 +39,7 @@ def test_info_calls_without_gpu(lib):
     assert lib.tdn_abi_version() == 1
     assert lib.tdn_strerror(0) == b"ok"
     assert b"sm_100" in lib.tdn_strerror(-4)
-    assert lib.tdn_psp_pool_workspace_bytes(1, 128, 512) == 128 * 4 * 12 * 512 * 4
+    assert lib.tdn_psp_pool_workspace_bytes(1, 128, 512) == 128 * 12 * 512 * 4
     # argument validation happens before any CUDA call, so it is checkable on a CPU-only box
     assert lib.tdn_conv2d(None, None) == -1
     assert b"null descriptor" in lib.tdn_last_error()

@@ -129,6 +129,24 @@ def test_baseline_td2_configs_against_oracle(arch, backbone, H, W, frames):
     assert net.K_queue[0].shape[1] == ((h8 - 1) // 4 + 1) * ((w8 - 1) // 4 + 1)
 
 
+def test_td4_resnet50_two_streams_512x1024_against_oracle():
+    """BASELINE configs[4] family ('td4-psp50', batch of lock-step streams per GPU; SURVEY.md 0.5 maps it to
+    td4_psp18(backbone='resnet50')): n=2 streams at 512x1024, d_v = 2048, through warm-up into steady state."""
+    H, W, n = 512, 1024, 2
+    oracle, sd = make_oracle("td4_psp18", "resnet50", H, W)
+    net = build_model("td4_psp18", "resnet50", 64, 128, sd)
+    for i, f in enumerate(synth_clip(5, H, W, batch=n, clip_id=11)):
+        ref = oracle(f, pos_id=i % 4)
+        out = net(f.cuda(), pos_id=i % 4).cpu()
+        e = max_abs(out, ref)
+        rep = argmax_report(out, ref, max(e, 1e-6))
+        record(f"oracle/td4_resnet50_n2_{H}x{W}/frame{i}", max_abs=e, rel_l2=rel_l2(out, ref), **rep)
+        assert e <= LOGIT_TOL, (i, e)
+        assert rep["mismatch_decided"] == 0, rep
+    assert net.V_queue[0].shape == (n, 16 * 32, 2048)
+    net.check_numeric_range()
+
+
 def test_full_size_1024x2048_properties():
     """BASELINE config 2 at full size: determinism, FIFO shapes, finite logits, oracle parity on one
     steady-state frame (the oracle needs ~3 s/frame on the host, so five frames only)."""
