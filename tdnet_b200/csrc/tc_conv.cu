@@ -459,14 +459,16 @@ int conv2d_tc(const tdn_tc_conv_desc* d, cudaStream_t stream) {
   p.Cout = d->cout; p.Cin = in.c;
   p.taps_h = d->kh; p.taps_w = d->kw; p.dil = d->dilation;
   // N tile: 128 columns unless the problem is so small that 128-wide tiles would leave the 148 SMs with fewer
-  // than two waves of work (wave quantisation costs more than the lower per-tile efficiency of N = 64).
+  // than two waves of work AND the K loop is short (measured: the fc GEMMs with 8 K blocks gain 25 % from
+  // N = 64, the head conv with 72 K blocks loses 35 % because the A tile is then fetched twice as often).
   if (g_num_sms == 0) {
     int dev = 0;
     TDN_CUDA_OK(cudaGetDevice(&dev));
     TDN_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const long long tiles128 = (long long)in.n * p.tiles_h * p.tiles_w * ceil_div(d->cout, 128);
-  const int block_n = (d->cout <= 64 || tiles128 < 2ll * g_num_sms) ? 64 : 128;
+  const int num_kb_host = taps * (in.c / TC_BLOCK_K);
+  const int block_n = (d->cout <= 64 || (tiles128 < 2ll * g_num_sms && num_kb_host <= 24)) ? 64 : 128;
   p.n_tiles_n = ceil_div(d->cout, block_n);
   long long num_tiles = (long long)in.n * p.tiles_h * p.tiles_w * p.n_tiles_n;
   TDN_REQUIRE(num_tiles < (1ll << 31), TDN_ERR_UNSUPPORTED, "conv2d_tc: too many tiles");
