@@ -32,6 +32,8 @@ ARCH, BACKBONE = "td4_psp18", "resnet18"
 WORKLOAD = "td4-psp18 1024x2048 synthetic Cityscapes stream, batch 1 (BASELINE.json configs[1])"
 FRAME_GFLOP = 936.2            # algorithmic FLOPs of one frame (2*MAC of the reference's operators)
 DOMINANT_GFLOP = 154.62        # layer4 3x3 512->512 dilated conv at 128x256
+ATTN_GFLOP = 77.31             # fused attention-propagation kernel, big hop: 2*32768*2048*(64+512)
+ATTN_EXECUTED_GFLOP = 3 * (68.72 + 2 * 8.59) + 2 * 8.59
 DOMINANT_TRAFFIC_BYTES = 110.4e6   # ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum (profiles/r01_*)
 N_DISTINCT_FRAMES = 8
 
@@ -278,7 +280,8 @@ def run_ours(args, rank, world):
     ms_e2e_labels = e4.elapsed_time(e5)
 
     # ---- dominant kernel, timed live with CUDA events around its launch inside running frames
-    dom_ms = net.time_dominant_op(dev_frames, step, reps=min(args.steps, 12)) if hasattr(net, "time_dominant_op") else None
+    dom_ms = net.time_dominant_op(dev_frames, step, reps=min(args.steps, 12))
+    attn_ms = net.time_attention_op(dev_frames, step, reps=min(args.steps, 12))
 
     total_frames, ms_dev, fps = whole_job_throughput(args.steps, ms_dev, device=dev)
     _, ms_e2e, fps_e2e = whole_job_throughput(args.steps, ms_e2e, device=dev)
@@ -311,6 +314,14 @@ def run_ours(args, rank, world):
                            "d2h_bytes_per_step": BATCH * H * W, "ms_per_step": ms_e2e_labels / args.steps,
                            "api": "model.forward_labels(image, pos_id): fused upsample+arg-max, uint8 label map"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof,
+            "roofline_attention": {
+                "bound": "tensor", "kernel": "tc_attn_kernel<256> (big hop: 32768 queries x 2048 keys, d_k 64, d_v 512)",
+                "achieved": ATTN_GFLOP / attn_ms, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                "frac": ATTN_GFLOP / attn_ms / peaks["tflops"], "ms_per_launch": attn_ms,
+                "executed_tflops": ATTN_EXECUTED_GFLOP / attn_ms,
+                "executed_frac": ATTN_EXECUTED_GFLOP / attn_ms / peaks["tflops"],
+                "note": "algorithmic = 2*Pq*P'*(d_k+d_v) = 77.31 GFLOP (SURVEY.md 8d); executed = 3 products x "
+                        "(PV + 2 d_v-slices x QK^T) + the single-product max pass = 275 GFLOP"},
             "cpu_baseline": cpu_baseline() if (world == 1 and not args.no_cpu_baseline) else None,
         }
         print(json.dumps(line), flush=True)

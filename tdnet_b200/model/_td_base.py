@@ -135,6 +135,19 @@ class TDModel(nn.Module):
             self._engines[key] = eng
         return eng
 
+    def time_attention_op(self, frames, step, reps=8):
+        """Average device time (ms) of the fused attention-propagation kernel of the big hop (the last hop of
+        the path: all P queries against the P' keys of the newest FIFO entry), timed like time_dominant_op."""
+        total = 0.0
+        for r in range(reps):
+            pos = (step + r) % self.PATHS
+            name = self.arch.hop_modules(pos + 1)[-1] + ".attention"
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.forward(frames[(step + r) % len(frames)], pos_id=pos, _probe=(name, e0, e1))
+            torch.cuda.synchronize()
+            total += e0.elapsed_time(e1)
+        return total / reps
+
     def time_dominant_op(self, frames, step, reps=8):
         """Average device time (ms) of the frame's dominant kernel -- the last 3x3 conv of layer4, 154.6
         GFLOP at 1024x2048 for td4-psp18 -- bracketed by CUDA events while whole frames run."""
