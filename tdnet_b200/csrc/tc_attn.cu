@@ -427,7 +427,7 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant
 // ------------------------------------------------------------------------------------------------
 int encode_map_f16(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims,
                    const cuuint64_t* strides_bytes, const cuuint32_t* box, const char* what,
-                   const cuuint32_t* elem_strides);
+                   const cuuint32_t* elem_strides, int swizzle128 = 1);
 
 int attention_tc(const tdn_attention_desc* d, cudaStream_t stream) {
   TDN_REQUIRE(d->q_hi && d->q_lo && d->k_hi && d->k_lo && d->vt_hi && d->vt_lo, TDN_ERR_INVALID,

@@ -24,46 +24,13 @@
 // out of TMEM and add it to per-thread fp32 registers with round-to-nearest.  The 512 TMEM columns form
 // a ring of 4 (BLOCK_N=128) or 8 (BLOCK_N=64) chunk accumulators, so the MMA warp keeps issuing while
 // earlier chunks are drained and while the scale/bias/store phase of the previous tile runs.
-#include "common.cuh"
-#include "tc_ptx.cuh"
+#include "tc_common.cuh"
 
 #include <stdlib.h>
 #include <string.h>
 #include <cuda.h>  // CUtensorMap types only; the encode entry point is resolved at run time
 
 namespace tdn {
-
-using namespace ptx;
-
-constexpr int TC_BLOCK_M = 128;
-constexpr int TC_BLOCK_K = 64;                       // fp16 elements = 128 bytes = one swizzle row
-constexpr int TC_A_PLANE = TC_BLOCK_M * TC_BLOCK_K * 2;  // 16 KiB per hi or lo plane
-constexpr int TC_EPI_WARPS = 8;                      // two per TMEM lane quarter, each owning half of the N columns
-constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
-
-struct TcParams {
-  int n_img, Ho, Wo;
-  int tiles_h, tiles_w, BH, BW;
-  int Cout, Cin;
-  int taps_h, taps_w, dil, conv_stride;
-  int n_tiles_n, num_tiles;
-  int chunk_kb;          // K blocks accumulated inside TMEM before the fp32 register accumulation
-  int w_batched;
-  const float* scale;
-  const float* bias;
-  int bias_along_m;
-  int act;
-  float slope;
-  __half* out_hi;
-  __half* out_lo;
-  float* out_f32;
-  long long osn, osh, osw;
-  const __half* res_hi;
-  const __half* res_lo;
-  const float* res_f32;
-  long long rsn, rsh, rsw;
-  int* range_flag;
-};
 
 template <int BLOCK_N>
 struct TcCfg {
@@ -77,12 +44,6 @@ struct TcCfg {
   static constexpr int TMEM_COLS = 512;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
 };
-
-__device__ __forceinline__ float tc_act(float v, int act, float slope) {
-  if (act == TDN_ACT_RELU) return fmaxf(v, 0.f);
-  if (act == TDN_ACT_LEAKY_RELU) return v > 0.f ? v : v * slope;
-  return v;
-}
 
 template <int BLOCK_N>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -204,151 +165,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       }
     }
   } else {
-    // ======================= epilogue (warps 2..9) =======================
-    // Warp w may only touch TMEM lanes 32*(w%4)..+31, so the 8 epilogue warps pair up per lane quarter:
-    // group 0 (warps 2-5) owns accumulator columns [0, N/2), group 1 (warps 6-9) columns [N/2, N).
-    constexpr int COLS = BLOCK_N / 2;
-    const int group = (warp - 2) >> 2;
-    const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
-    const int row = quarter * 32 + lane;          // pixel row of the tile
-    const int h_local = row / p.BW;
-    const int w_local = row - h_local * p.BW;
-    int as = 0;
-    uint32_t aphase = 0;
-    bool out_of_range = false;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const int nt = tile % p.n_tiles_n;
-      int mt = tile / p.n_tiles_n;
-      const int tx = mt % p.tiles_w;
-      mt /= p.tiles_w;
-      const int ty = mt % p.tiles_h;
-      const int img = mt / p.tiles_h;
-      const int oh = ty * p.BH + h_local;
-      const int ow = tx * p.BW + w_local;
-      const bool valid = oh < p.Ho && ow < p.Wo;
-      const long long ooff = (long long)img * p.osn + (long long)oh * p.osh + (long long)ow * p.osw;
-      const long long roff = (long long)img * p.rsn + (long long)oh * p.rsh + (long long)ow * p.rsw;
-      const float bias_m = (p.bias && p.bias_along_m && valid) ? __ldg(p.bias + oh * p.Wo + ow) : 0.f;
-
-      float acc[COLS];
-#pragma unroll
-      for (int j = 0; j < COLS; ++j) acc[j] = 0.f;
-      for (int kb0 = 0; kb0 < num_kb; kb0 += p.chunk_kb) {
-        mbar_wait(&tmem_full[as], aphase);
-        tc_fence_after();
-        const uint32_t taddr_c = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BLOCK_N + group * COLS;
-#pragma unroll
-        for (int chunk = 0; chunk < COLS / 32; ++chunk) {
-          uint32_t r[32];
-          tmem_ld_32x32(taddr_c + chunk * 32, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) acc[chunk * 32 + j] += __uint_as_float(r[j]);
-        }
-        tc_fence_before();
-        mbar_arrive(&tmem_empty[as]);
-        if (++as == NUM_ACC) { as = 0; aphase ^= 1; }
-      }
-#pragma unroll
-      for (int chunk = 0; chunk < COLS / 32; ++chunk) {
-        const int c0 = nt * BLOCK_N + group * COLS + chunk * 32;
-        if (valid && c0 < p.Cout) {
-          float v[32];
-          const bool full = (c0 + 32 <= p.Cout);
-          if (full) {
-            // warp-uniform 16-byte loads of the per-channel scale / bias (L1 broadcast)
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              float4 s4 = p.scale ? __ldg(reinterpret_cast<const float4*>(p.scale + c0) + q)
-                                  : make_float4(1.f, 1.f, 1.f, 1.f);
-              float4 b4 = (p.bias && !p.bias_along_m) ? __ldg(reinterpret_cast<const float4*>(p.bias + c0) + q)
-                                                      : make_float4(bias_m, bias_m, bias_m, bias_m);
-              v[q * 4 + 0] = fmaf(acc[chunk * 32 + q * 4 + 0], s4.x, b4.x);
-              v[q * 4 + 1] = fmaf(acc[chunk * 32 + q * 4 + 1], s4.y, b4.y);
-              v[q * 4 + 2] = fmaf(acc[chunk * 32 + q * 4 + 2], s4.z, b4.z);
-              v[q * 4 + 3] = fmaf(acc[chunk * 32 + q * 4 + 3], s4.w, b4.w);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int c = c0 + j;
-              float s = 1.f, b = bias_m;
-              if (c < p.Cout) {
-                if (p.scale) s = __ldg(p.scale + c);
-                if (p.bias && !p.bias_along_m) b = __ldg(p.bias + c);
-              }
-              v[j] = fmaf(acc[chunk * 32 + j], s, b);
-            }
-          }
-          if (p.res_hi) {
-            if (full) {
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                uint4 h4 = *reinterpret_cast<const uint4*>(p.res_hi + roff + c0 + q * 8);
-                uint4 l4 = *reinterpret_cast<const uint4*>(p.res_lo + roff + c0 + q * 8);
-                const __half2* hh = reinterpret_cast<const __half2*>(&h4);
-                const __half2* ll = reinterpret_cast<const __half2*>(&l4);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  float2 a = __half22float2(hh[e]), b2 = __half22float2(ll[e]);
-                  v[q * 8 + e * 2 + 0] += a.x + b2.x;
-                  v[q * 8 + e * 2 + 1] += a.y + b2.y;
-                }
-              }
-            } else {
-              for (int j = 0; j < 32 && c0 + j < p.Cout; ++j)
-                v[j] += __half2float(p.res_hi[roff + c0 + j]) + __half2float(p.res_lo[roff + c0 + j]);
-            }
-          } else if (p.res_f32) {
-            if (full) {
-#pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                float4 f = *reinterpret_cast<const float4*>(p.res_f32 + roff + c0 + q * 4);
-                v[q * 4 + 0] += f.x; v[q * 4 + 1] += f.y; v[q * 4 + 2] += f.z; v[q * 4 + 3] += f.w;
-              }
-            } else {
-              for (int j = 0; j < 32 && c0 + j < p.Cout; ++j) v[j] += p.res_f32[roff + c0 + j];
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = tc_act(v[j], p.act, p.slope);
-
-          if (p.out_f32) {
-            if (full) {
-#pragma unroll
-              for (int q = 0; q < 8; ++q)
-                *reinterpret_cast<float4*>(p.out_f32 + ooff + c0 + q * 4) =
-                    make_float4(v[q * 4 + 0], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-            } else {
-              for (int j = 0; j < 32 && c0 + j < p.Cout; ++j) p.out_f32[ooff + c0 + j] = v[j];
-            }
-          }
-          if (p.out_hi) {
-            __half2 hi2[16], lo2[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              out_of_range |= fmaxf(fabsf(v[2 * j]), fabsf(v[2 * j + 1])) > 60000.f;
-              split_f32x2(v[2 * j], v[2 * j + 1], hi2[j], lo2[j]);
-            }
-            const __half* hi = reinterpret_cast<const __half*>(hi2);
-            const __half* lo = reinterpret_cast<const __half*>(lo2);
-            if (full) {
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                *reinterpret_cast<uint4*>(p.out_hi + ooff + c0 + q * 8) = *reinterpret_cast<const uint4*>(&hi[q * 8]);
-                *reinterpret_cast<uint4*>(p.out_lo + ooff + c0 + q * 8) = *reinterpret_cast<const uint4*>(&lo[q * 8]);
-              }
-            } else {
-              for (int j = 0; j < 32 && c0 + j < p.Cout; ++j) {
-                p.out_hi[ooff + c0 + j] = hi[j];
-                p.out_lo[ooff + c0 + j] = lo[j];
-              }
-            }
-          }
-        }
-      }
-    }
-    if (out_of_range && p.range_flag) atomicOr(p.range_flag, 1);
+    tc_epilogue_role<BLOCK_N, NUM_ACC>(p, tmem_base, tmem_full, tmem_empty, warp, lane, num_kb);
   }
 
   tc_fence_before();
@@ -380,14 +197,15 @@ static EncodeTiledFn get_encode_fn() {
 
 int encode_map_f16(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims,
                    const cuuint64_t* strides_bytes, const cuuint32_t* box, const char* what,
-                   const cuuint32_t* elem_strides) {
+                   const cuuint32_t* elem_strides, int swizzle128) {
   EncodeTiledFn fn = get_encode_fn();
   TDN_REQUIRE(fn != nullptr, TDN_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   if (elem_strides)
     for (int i = 0; i < rank; ++i) estr[i] = elem_strides[i];
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   TDN_REQUIRE(r == CUDA_SUCCESS, TDN_ERR_CUDA, "cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
   return TDN_OK;
@@ -426,6 +244,8 @@ static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUt
   TDN_LAUNCH_OK();
   return TDN_OK;
 }
+
+int conv2d_tc_halo(const tdn_tc_conv_desc* d, TcParams p, int num_sms, int chunk_kb, cudaStream_t stream);
 
 int conv2d_tc(const tdn_tc_conv_desc* d, cudaStream_t stream) {
   const tdn_tensor& in = d->in;
@@ -520,6 +340,17 @@ int conv2d_tc(const tdn_tc_conv_desc* d, cudaStream_t stream) {
   }
   p.range_flag = d->range_flag;
 
+  {
+    // 3x3 / stride 1 / dilation <= 2: one halo-region load per channel block instead of nine tap loads
+    static int halo = -1;
+    if (halo < 0) {
+      const char* e = getenv("TDNET_TC_HALO");
+      halo = e ? atoi(e) : 0;
+    }
+    if (halo && d->kh == 3 && d->kw == 3 && cs == 1 && d->dilation <= 2 && !d->weight_batched && in.w >= 8)
+      return conv2d_tc_halo(d, p, g_num_sms, p.chunk_kb, stream);
+  }
+
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
   {
     cuuint64_t dims[4] = {(cuuint64_t)in.c, (cuuint64_t)in.w, (cuuint64_t)in.h, (cuuint64_t)in.n};
@@ -529,8 +360,8 @@ int conv2d_tc(const tdn_tc_conv_desc* d, cudaStream_t stream) {
     cuuint32_t box[4] = {(cuuint32_t)TC_BLOCK_K, (cuuint32_t)(p.BW * cs), (cuuint32_t)(p.BH * cs), 1};
     cuuint32_t est[4] = {1, (cuuint32_t)cs, (cuuint32_t)cs, 1};
     int rc;
-    if ((rc = encode_map_f16(&a_hi, in.data, 4, dims, str, box, "A.hi", est))) return rc;
-    if ((rc = encode_map_f16(&a_lo, in.data_lo, 4, dims, str, box, "A.lo", est))) return rc;
+    if ((rc = encode_map_f16(&a_hi, in.data, 4, dims, str, box, "A.hi", est, 1))) return rc;
+    if ((rc = encode_map_f16(&a_lo, in.data_lo, 4, dims, str, box, "A.lo", est, 1))) return rc;
   }
   {
     const int nb = d->weight_batched ? in.n : 1;
@@ -540,8 +371,8 @@ int conv2d_tc(const tdn_tc_conv_desc* d, cudaStream_t stream) {
     cuuint64_t str[2] = {(cuuint64_t)d->weight_ld * 2, bstride};
     cuuint32_t box[3] = {(cuuint32_t)TC_BLOCK_K, (cuuint32_t)block_n, 1};
     int rc;
-    if ((rc = encode_map_f16(&b_hi, d->weight_hi, 3, dims, str, box, "B.hi", nullptr))) return rc;
-    if ((rc = encode_map_f16(&b_lo, d->weight_lo, 3, dims, str, box, "B.lo", nullptr))) return rc;
+    if ((rc = encode_map_f16(&b_hi, d->weight_hi, 3, dims, str, box, "B.hi", nullptr, 1))) return rc;
+    if ((rc = encode_map_f16(&b_lo, d->weight_lo, 3, dims, str, box, "B.lo", nullptr, 1))) return rc;
   }
   if (block_n == 64) return launch_tc<64>(a_hi, a_lo, b_hi, b_lo, p, stream);
   return launch_tc<128>(a_hi, a_lo, b_hi, b_lo, p, stream);

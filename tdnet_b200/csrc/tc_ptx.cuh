@@ -163,6 +163,18 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                           // layout type SWIZZLE_128B, bits [61,64)
   return d;
 }
+// K-major operand without swizzle ("interleave"): 8-row x 16-byte core matrices stored contiguously (128 B);
+// lbo = distance between the two 8-element K chunks of a K16 step, sbo = distance between consecutive 8-row
+// groups, both in 16-byte units.  The start address only needs 16-byte alignment, which is what lets a filter
+// tap be a byte offset into a shared halo region (tc_conv_halo.cu).
+__device__ __forceinline__ uint64_t umma_desc_k_noswz(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)(lbo & 0x3FFF) << 16;
+  d |= (uint64_t)(sbo & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;                           // descriptor version 1 (sm_100)
+  return d;                                         // layout type 0 = SWIZZLE_NONE
+}
 // Instruction descriptor for kind::f16: fp16 A/B (format 0), fp32 D (1), both K-major, M x N tile.
 __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
   return (1u << 4)                      // c_format = F32

@@ -198,6 +198,33 @@ def experiment(name):
             torch.cuda.synchronize()
             res[f"ms_per_launch_{reps}"] = e0.elapsed_time(e1) / reps
         return res
+    if name == "halo_ragged":
+        x = torch.randn(2, 23, 30, 64, device=dev)
+        w = torch.randn(40, 3, 3, 64, device=dev) / 24
+        out, _, _ = run_tc(x, w, dil=2)
+        return stats(out, ref_conv(x, w, 2))
+    if name == "halo_epilogue":
+        x = torch.randn(1, 40, 24, 128, device=dev)
+        w = torch.randn(128, 3, 3, 128, device=dev) / 34
+        s_, b_ = torch.rand(128, device=dev) + 0.5, torch.randn(128, device=dev)
+        r = torch.randn(1, 40, 24, 128, device=dev)
+        out, _, flag = run_tc(x, w, scale=s_, bias=b_, residual=r, act=1, out_split=True)
+        ref = torch.relu(ref_conv(x, w) * s_.double() + b_.double() + r.double())
+        return stats(out, ref)
+    if name == "layer2_perf":
+        x = torch.randn(1, 128, 256, 128, device=dev).relu()
+        w = torch.randn(128, 3, 3, 128, device=dev) / 34
+        out, ms, _ = run_tc(x, w, dil=1, reps=10)
+        st = stats(out, ref_conv(x, w, 1))
+        st.update(ms=ms, algorithmic_tflops=2 * 128 * 256 * 128 * 128 * 9 / ms / 1e9)
+        return st
+    if name == "layer3_perf":
+        x = torch.randn(1, 128, 256, 256, device=dev).relu()
+        w = torch.randn(256, 3, 3, 256, device=dev) / 48
+        out, ms, _ = run_tc(x, w, dil=2, reps=10)
+        st = stats(out, ref_conv(x, w, 2))
+        st.update(ms=ms, algorithmic_tflops=2 * 128 * 256 * 256 * 256 * 9 / ms / 1e9)
+        return st
     if name == "layer1_perf":
         x = torch.randn(1, 256, 512, 64, device=dev).relu()
         w = torch.randn(64, 3, 3, 64, device=dev) / 24
@@ -277,10 +304,15 @@ def attention_experiment(name):
     return st
 
 
-EXPERIMENTS = ["layout_debug", "gemm_k512_ragged", "conv3x3_d8_97x193", "epilogue", "accum_bias_positive",
-               "layer1_perf", "layer4_perf", "layer4_sustained", "attention_small", "attention_ragged", "attention_big"]
+EXPERIMENTS = ["layout_debug", "conv3x3_d2_ragged", "layer1_perf", "layer4_perf", "attention_big"]
 # (experiment, TDNET_TC_CHUNK_KB) pairs run after the default set
-CHUNK_SWEEP = [("layer4_perf", 2), ("layer4_perf", 8), ("layer4_perf", 100000), ("accum_bias_positive", 8)]
+CHUNK_SWEEP = []
+# (experiment, extra environment) pairs: the halo-region variant of the 3x3 kernel against the per-tap one
+ENV_SWEEP = [("halo_ragged", {"TDNET_TC_HALO": "1"}), ("halo_epilogue", {"TDNET_TC_HALO": "1"}),
+             ("conv3x3_d2_ragged", {"TDNET_TC_HALO": "1"}),
+             ("layer1_perf", {"TDNET_TC_HALO": "1"}), ("layer2_perf", {"TDNET_TC_HALO": "0"}),
+             ("layer2_perf", {"TDNET_TC_HALO": "1"}), ("layer3_perf", {"TDNET_TC_HALO": "0"}),
+             ("layer3_perf", {"TDNET_TC_HALO": "1"})]
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "--one":
@@ -288,11 +320,13 @@ if __name__ == "__main__":
         sys.exit(0)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     lines = []
-    todo = [(n, None) for n in (sys.argv[1:] or EXPERIMENTS)] + ([] if sys.argv[1:] else CHUNK_SWEEP)
+    todo = [(n, None) for n in (sys.argv[1:] or EXPERIMENTS)] + ([] if sys.argv[1:] else CHUNK_SWEEP + ENV_SWEEP)
     for name, chunk in todo:
         t0 = time.time()
         env = dict(os.environ)
-        if chunk is not None:
+        if isinstance(chunk, dict):
+            env.update(chunk)
+        elif chunk is not None:
             env["TDNET_TC_CHUNK_KB"] = str(chunk)
         try:
             r = subprocess.run([sys.executable, __file__, "--one", name], capture_output=True, text=True, timeout=150,
@@ -301,7 +335,8 @@ if __name__ == "__main__":
             msg = res[0][7:] if res else f"FAILED rc={r.returncode} stdout={r.stdout[-600:]!r} stderr={r.stderr[-900:]!r}"
         except subprocess.TimeoutExpired:
             msg = "TIMEOUT (150 s)"
-        line = f"{name}{'' if chunk is None else f' [chunk_kb={chunk}]'}: {msg}  [{time.time() - t0:.1f}s]"
+        tag = "" if chunk is None else (f" {chunk}" if isinstance(chunk, dict) else f" [chunk_kb={chunk}]")
+        line = f"{name}{tag}: {msg}  [{time.time() - t0:.1f}s]"
         print(line, flush=True)
         lines.append(line)
     open(os.path.join(ROOT, "gpurun_out", "tc_probe.txt"), "w").write("\n".join(lines) + "\n")
