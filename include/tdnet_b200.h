@@ -194,6 +194,16 @@ int tdn_stem_conv_pool(const float* nchw, int32_t n, int32_t h, int32_t w, const
 int tdn_stem_conv_pool_u8(const uint8_t* hwc, const float* lut, int32_t n, int32_t h, int32_t w, const float* weight,
                           const float* scale, const float* bias, const tdn_tensor* out, void* stream);
 
+/* The same fused stem on the tensor cores (tcgen05, exact mode: split-fp16 operands, fp32 accumulation), reading
+ * either the fp32 NCHW image (`nchw`, hwc_u8 = lut = NULL) or the uint8 HWC frame with its table (`hwc_u8`, `lut`,
+ * nchw = NULL).  weight_tc is fp16 [2 planes (hi, lo)][7 ky][4 kx pairs][64 cout][2 kx][4 c] holding
+ * w[cout][c][ky][kx] * 2^e(cout) (zero for kx = 7 and c = 3); `scale` is the folded BatchNorm scale times
+ * 2^-e(cout).  Image magnitudes must stay below 65504 (fp16 operand range); *range_flag is OR-ed with 1 otherwise
+ * (may be NULL).  Returns TDN_ERR_ARCH on a device that is not sm_100. */
+int tdn_stem_conv_pool_tc(const float* nchw, const uint8_t* hwc_u8, const float* lut, int32_t n, int32_t h, int32_t w,
+                          const void* weight_tc, const float* scale, const float* bias, const tdn_tensor* out,
+                          int32_t* range_flag, void* stream);
+
 /* F.max_pool2d(kernel 3, stride 2, padding 1) of the stem (resnet.py:137,208), NHWC fp32. */
 int tdn_maxpool3x3s2(const tdn_tensor* in, const tdn_tensor* out, void* stream);
 

@@ -52,6 +52,8 @@ int conv2d_tc(const tdn_tc_conv_desc*, cudaStream_t);
 int stem_conv_pool(const float*, const uint8_t*, const float*, int, int, int, const float*, const float*, const float*,
                    const tdn_tensor*, cudaStream_t);
 int attention_tc(const tdn_attention_desc*, cudaStream_t);
+int stem_conv_pool_tc(const float*, const uint8_t*, const float*, int, int, int, const void*, const float*, const float*,
+                      const tdn_tensor*, int*, cudaStream_t);
 int split16(const tdn_tensor*, const tdn_tensor*, cudaStream_t);
 int merge16(const tdn_tensor*, const tdn_tensor*, cudaStream_t);
 
@@ -130,6 +132,16 @@ int tdn_image_to_nhwc(const float* nchw, int32_t n, int32_t c, int32_t h, int32_
 int tdn_stem_conv_pool(const float* nchw, int32_t n, int32_t h, int32_t w, const float* weight, const float* scale,
                        const float* bias, const tdn_tensor* out, void* stream) {
   return stem_conv_pool(nchw, nullptr, nullptr, n, h, w, weight, scale, bias, out, (cudaStream_t)stream);
+}
+
+int tdn_stem_conv_pool_tc(const float* nchw, const uint8_t* hwc_u8, const float* lut, int32_t n, int32_t h, int32_t w,
+                          const void* weight_tc, const float* scale, const float* bias, const tdn_tensor* out,
+                          int32_t* range_flag, void* stream) {
+  static thread_local int arch = 0;
+  if (arch == 0) arch = tdn_device_arch();
+  if (arch < 0) return arch;
+  TDN_REQUIRE(arch / 10 == 10, TDN_ERR_ARCH, "stem_conv_pool_tc: tcgen05 kernels need sm_100, device is sm_%d", arch);
+  return stem_conv_pool_tc(nchw, hwc_u8, lut, n, h, w, weight_tc, scale, bias, out, range_flag, (cudaStream_t)stream);
 }
 
 int tdn_stem_conv_pool_u8(const uint8_t* hwc, const float* lut, int32_t n, int32_t h, int32_t w, const float* weight,

@@ -170,6 +170,18 @@ def split_rows_pow2(w: torch.Tensor):
     return hi.contiguous(), lo.contiguous(), torch.exp2(-k).contiguous()
 
 
+def pack_stem_tc(w: torch.Tensor):
+    """Stem weights [64,3,7,7] fp32 -> (fp16 [2 planes][7 ky][4 kx pairs][64 cout][2 kx][4 c], inv_scale [64]) for
+    tdn_stem_conv_pool_tc: w = (hi + lo) * inv_scale per output channel, zero for the padding taps kx = 7, c = 3."""
+    hi, lo, inv = split_rows_pow2(w.reshape(64, 147).float())
+    planes = []
+    for t in (hi, lo):
+        t4 = torch.zeros(64, 4, 7, 8, dtype=torch.float16, device=w.device)     # [cout][c][ky][kx]
+        t4[:, :3, :, :7] = t.reshape(64, 3, 7, 7)
+        planes.append(t4.reshape(64, 4, 7, 4, 2).permute(2, 3, 0, 4, 1))       # [ky][pair][cout][kx in pair][c]
+    return torch.stack(planes).contiguous(), inv
+
+
 class FramePlan:
     def __init__(self):
         self.ops: List[Callable] = []
@@ -204,6 +216,7 @@ class Engine:
         self.fused_attn = os.environ.get("TDNET_B200_FUSED_ATTN", "1") != "0"
         self.tc_stride2 = os.environ.get("TDNET_B200_TC_STRIDE2", "1") != "0"
         self.fused_stem = os.environ.get("TDNET_B200_FUSED_STEM", "1") != "0"
+        self.tc_stem = os.environ.get("TDNET_B200_TC_STEM", "0") != "0"
         use_side = os.environ.get("TDNET_B200_SIDE_STREAM", "1") != "0"
         self.side_stream = torch.cuda.Stream(device) if (use_side and device.type == "cuda") else None
         self.m, self.n, self.H, self.W, self.device = arch, n, H, W, device
@@ -249,6 +262,16 @@ class Engine:
             w = self.sd[spec.name + ".weight"].detach().float()          # [64,3,7,7]
             wk = w.permute(1, 2, 3, 0).reshape(147, 64).contiguous().to(self.device)
             self._packed[key] = dict(w=wk, scale=pc.scale, bias=pc.bias)
+        return self._packed[key]
+
+    def stem_packed_tc(self, spec: A.Conv):
+        """Stem weights in the split-fp16 chunk layout of tdn_stem_conv_pool_tc + folded BN (x weight row scale)."""
+        key = "stem_tc:" + spec.name
+        if key not in self._packed:
+            pc = self.packed(spec)
+            w, inv = pack_stem_tc(self.sd[spec.name + ".weight"].detach().float().to(self.device))
+            scale = inv if pc.scale is None else pc.scale * inv
+            self._packed[key] = dict(w=w, scale=scale.contiguous(), bias=pc.bias)
         return self._packed[key]
 
     def norm_lut(self) -> torch.Tensor:
@@ -382,12 +405,23 @@ class Engine:
             pk = self.stem_packed(c)
             hc, wc = (H - 1) // 2 + 1, (W - 1) // 2 + 1
             x = self.buf(n, (hc - 1) // 2 + 1, (wc - 1) // 2 + 1, c.cout)
-            plan.add(lib.tdn_stem_conv_pool, "img", n, H, W, pk["w"].data_ptr(), pk["scale"].data_ptr(),
-                     pk["bias"].data_ptr(), C.byref(self._ct(plan, x)), "stream", name=c.name)
-            # alternative first op: uint8 HWC frame + normalisation table (forward_u8)
-            plan.u8_op = (lib.tdn_stem_conv_pool_u8, ("img", self.norm_lut().data_ptr(), n, H, W, pk["w"].data_ptr(),
-                                                       pk["scale"].data_ptr(), pk["bias"].data_ptr(),
-                                                       plan.ops[-1][1][7], "stream"))
+            if self.tc and self.tc_stem:
+                # tcgen05 version: the image is staged as split fp16 inside the kernel, no im2col
+                pk = self.stem_packed_tc(c)
+                xt = C.byref(self._ct(plan, x))
+                flag = self.range_flag.data_ptr()
+                plan.add(lib.tdn_stem_conv_pool_tc, "img", None, None, n, H, W, pk["w"].data_ptr(),
+                         pk["scale"].data_ptr(), pk["bias"].data_ptr(), xt, flag, "stream", name=c.name)
+                plan.u8_op = (lib.tdn_stem_conv_pool_tc, (None, "img", self.norm_lut().data_ptr(), n, H, W,
+                                                           pk["w"].data_ptr(), pk["scale"].data_ptr(),
+                                                           pk["bias"].data_ptr(), xt, flag, "stream"))
+            else:
+                plan.add(lib.tdn_stem_conv_pool, "img", n, H, W, pk["w"].data_ptr(), pk["scale"].data_ptr(),
+                         pk["bias"].data_ptr(), C.byref(self._ct(plan, x)), "stream", name=c.name)
+                # alternative first op: uint8 HWC frame + normalisation table (forward_u8)
+                plan.u8_op = (lib.tdn_stem_conv_pool_u8, ("img", self.norm_lut().data_ptr(), n, H, W,
+                                                           pk["w"].data_ptr(), pk["scale"].data_ptr(),
+                                                           pk["bias"].data_ptr(), plan.ops[-1][1][7], "stream"))
         else:
             # deep stem (ResNet-50) or unfused path: NCHW image -> NHWC(4) -> conv(s) -> maxpool
             img = self.buf(n, H, W, 4, split=False)

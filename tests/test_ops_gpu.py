@@ -454,6 +454,59 @@ def test_fused_stem_conv_bn_relu_maxpool(env, h, w, split):
     assert max_abs(out.torch().permute(0, 3, 1, 2).cpu(), ref) < 1e-5
 
 
+@pytest.mark.parametrize("h,w,split,u8", [(64, 96, True, False), (97, 161, False, False), (130, 70, True, True),
+                                          (257, 530, True, False), (9, 9, True, False)])
+def test_tc_stem_conv_bn_relu_maxpool(env, h, w, split, u8):
+    """tdn_stem_conv_pool_tc (tcgen05, exact mode) vs conv2d(7,2,3) -> BN(eval) -> ReLU -> max_pool2d(3,2,1) in fp64
+    (resnet.py:205-208); several strips / bands, ragged edges, and the uint8 HWC ingest (dataloader.py:66-71)."""
+    from tdnet_b200.engine import pack_stem_tc
+    lib, cabi, View, dev = env
+    g = torch.Generator().manual_seed(h * 7 + w)
+    wt = torch.randn(64, 3, 7, 7, generator=g) / 12
+    sc, bi = torch.rand(64, generator=g) + 0.5, torch.randn(64, generator=g) * 0.3
+    if u8:
+        frame = torch.randint(0, 256, (2, h, w, 3), generator=g, dtype=torch.uint8)
+        mean = torch.tensor([.485, .456, .406], dtype=torch.float64)
+        std = torch.tensor([.229, .224, .225], dtype=torch.float64)
+        img = ((frame.double() / 255.0 - mean) / std).float().permute(0, 3, 1, 2).contiguous()
+        lut = ((torch.arange(256, dtype=torch.float64)[None] / 255.0 - mean[:, None]) / std[:, None]).float().cuda()
+    else:
+        img = torch.randn(2, 3, h, w, generator=g)
+    ref = F.max_pool2d(F.relu(F.conv2d(img.double(), wt.double(), None, 2, 3) * sc.double().view(1, -1, 1, 1)
+                              + bi.double().view(1, -1, 1, 1)), 3, 2, 1)
+    hp, wp = ref.shape[2:]
+    out = View.alloc(2, hp, wp, 64, dev, split=split)
+    wk, inv = pack_stem_tc(wt.cuda())
+    scd, bid = (sc.cuda() * inv).contiguous(), bi.cuda()
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    t = out.ct()
+    if u8:
+        fd = frame.cuda()
+        rc = lib.tdn_stem_conv_pool_tc(None, fd.data_ptr(), lut.data_ptr(), 2, h, w, wk.data_ptr(), scd.data_ptr(),
+                                       bid.data_ptr(), C.byref(t), flag.data_ptr(), None)
+    else:
+        imgd = img.cuda()
+        rc = lib.tdn_stem_conv_pool_tc(imgd.data_ptr(), None, None, 2, h, w, wk.data_ptr(), scd.data_ptr(),
+                                       bid.data_ptr(), C.byref(t), flag.data_ptr(), None)
+    cabi.check(rc, "stem_tc")
+    torch.cuda.synchronize()
+    got = out.torch().permute(0, 3, 1, 2).cpu()
+    assert got.shape == ref.shape
+    assert max_abs(got, ref) < 3e-6 * max(1.0, float(ref.abs().max()))
+    assert int(flag.item()) == 0
+
+
+def test_tc_stem_rejects_bad_arguments(env):
+    lib, cabi, View, dev = env
+    out = View.alloc(1, 16, 24, 64, dev, split=True)
+    t = out.ct()
+    x = torch.zeros(16, device=dev)
+    assert lib.tdn_stem_conv_pool_tc(None, None, None, 1, 64, 96, x.data_ptr(), x.data_ptr(), x.data_ptr(),
+                                     C.byref(t), None, None) == -1
+    assert lib.tdn_stem_conv_pool_tc(x.data_ptr(), None, None, 1, 64, 100, x.data_ptr(), x.data_ptr(), x.data_ptr(),
+                                     C.byref(t), None, None) == -1
+
+
 @pytest.mark.parametrize("h,w,split", [(13, 21, False), (16, 32, True)])
 def test_psp_concat_matches_interpolate_and_cat(env, h, w, split):
     lib, cabi, View, dev = env

@@ -198,6 +198,46 @@ def experiment(name):
             torch.cuda.synchronize()
             res[f"ms_per_launch_{reps}"] = e0.elapsed_time(e1) / reps
         return res
+    if name in ("stem_tc_perf", "stem_tc_small"):
+        from tdnet_b200.engine import pack_stem_tc, View
+        from tdnet_b200 import _cabi as cabi
+        import torch.nn.functional as F
+        lib = cabi.load()
+        h, w = (1024, 2048) if name == "stem_tc_perf" else (70, 300)
+        img = torch.randn(1, 3, h, w, device=dev)
+        wt = torch.randn(64, 3, 7, 7, device=dev) / 12
+        sc, bi = torch.rand(64, device=dev) + 0.5, torch.randn(64, device=dev) * 0.3
+        ref = F.max_pool2d(F.relu(F.conv2d(img.double(), wt.double(), None, 2, 3) * sc.double().view(1, -1, 1, 1)
+                                  + bi.double().view(1, -1, 1, 1)), 3, 2, 1).permute(0, 2, 3, 1)
+        hp, wp = ref.shape[1:3]
+        wk, inv = pack_stem_tc(wt)
+        scd = (sc * inv).contiguous()
+        out = View.alloc(1, hp, wp, 64, dev, split=True)
+        t = out.ct()
+        def run():
+            cabi.check(lib.tdn_stem_conv_pool_tc(img.data_ptr(), None, None, 1, h, w, wk.data_ptr(), scd.data_ptr(),
+                                                 bi.data_ptr(), C.byref(t), None, None), "stem_tc")
+        run(); torch.cuda.synchronize()
+        st = stats(out.torch(), ref)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10): run()
+        e1.record(); torch.cuda.synchronize()
+        st["ms"] = e0.elapsed_time(e1) / 10
+        # the fp32 CUDA-core stem on the same input
+        out2 = View.alloc(1, hp, wp, 64, dev, split=True)
+        t2 = out2.ct()
+        wk2 = wt.permute(1, 2, 3, 0).reshape(147, 64).contiguous()
+        def run2():
+            cabi.check(lib.tdn_stem_conv_pool(img.data_ptr(), 1, h, w, wk2.data_ptr(), sc.data_ptr(), bi.data_ptr(),
+                                              C.byref(t2), None), "stem")
+        run2(); torch.cuda.synchronize()
+        e0.record()
+        for _ in range(10): run2()
+        e1.record(); torch.cuda.synchronize()
+        st["simt_ms"] = e0.elapsed_time(e1) / 10
+        st["simt_max_abs"] = float((out2.torch().double() - ref).abs().max())
+        return st
     if name == "halo_ragged":
         x = torch.randn(2, 23, 30, 64, device=dev)
         w = torch.randn(40, 3, 3, 64, device=dev) / 24
@@ -304,11 +344,12 @@ def attention_experiment(name):
     return st
 
 
-EXPERIMENTS = ["layout_debug", "conv3x3_d2_ragged", "layer1_perf", "layer4_perf", "attention_big"]
+EXPERIMENTS = ["stem_tc_small", "stem_tc_perf"]
 # (experiment, TDNET_TC_CHUNK_KB) pairs run after the default set
 CHUNK_SWEEP = []
 # (experiment, extra environment) pairs: the halo-region variant of the 3x3 kernel against the per-tap one
-ENV_SWEEP = [("halo_ragged", {"TDNET_TC_HALO": "1"}), ("halo_epilogue", {"TDNET_TC_HALO": "1"}),
+ENV_SWEEP = []
+_HALO_SWEEP = [("halo_ragged", {"TDNET_TC_HALO": "1"}), ("halo_epilogue", {"TDNET_TC_HALO": "1"}),
              ("conv3x3_d2_ragged", {"TDNET_TC_HALO": "1"}),
              ("layer1_perf", {"TDNET_TC_HALO": "1"}), ("layer2_perf", {"TDNET_TC_HALO": "0"}),
              ("layer2_perf", {"TDNET_TC_HALO": "1"}), ("layer3_perf", {"TDNET_TC_HALO": "0"}),
