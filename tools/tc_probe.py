@@ -348,9 +348,9 @@ EXPERIMENTS = ["stem_tc_small", "stem_tc_perf"]
 # (experiment, TDNET_TC_CHUNK_KB) pairs run after the default set
 CHUNK_SWEEP = []
 # (experiment, extra environment) pairs: the halo-region variant of the 3x3 kernel against the per-tap one
-ENV_SWEEP = []
+ENV_SWEEP = []   # e.g. = _HALO_SWEEP
 _HALO_SWEEP = [("halo_ragged", {"TDNET_TC_HALO": "1"}), ("halo_epilogue", {"TDNET_TC_HALO": "1"}),
-             ("conv3x3_d2_ragged", {"TDNET_TC_HALO": "1"}),
+             ("conv3x3_d2_ragged", {"TDNET_TC_HALO": "1"}), ("layer1_perf", {"TDNET_TC_HALO": "0"}),
              ("layer1_perf", {"TDNET_TC_HALO": "1"}), ("layer2_perf", {"TDNET_TC_HALO": "0"}),
              ("layer2_perf", {"TDNET_TC_HALO": "1"}), ("layer3_perf", {"TDNET_TC_HALO": "0"}),
              ("layer3_perf", {"TDNET_TC_HALO": "1"})]
@@ -361,7 +361,8 @@ if __name__ == "__main__":
         sys.exit(0)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     lines = []
-    todo = [(n, None) for n in (sys.argv[1:] or EXPERIMENTS)] + ([] if sys.argv[1:] else CHUNK_SWEEP + ENV_SWEEP)
+    sweep = _HALO_SWEEP if os.environ.get("TDNET_PROBE_HALO_SWEEP") else ENV_SWEEP
+    todo = [(n, None) for n in (sys.argv[1:] or EXPERIMENTS)] + ([] if sys.argv[1:] else CHUNK_SWEEP + sweep)
     for name, chunk in todo:
         t0 = time.time()
         env = dict(os.environ)
