@@ -244,16 +244,9 @@ def run_ours(args, rank, world):
             dev_in[slot].copy_(host_frames[i % N_DISTINCT_FRAMES], non_blocking=True)
             ev_in[slot].record(copy_s)
 
-    barrier()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record(stream)
-    copy_s.wait_event(e2)
-    d2h_s.wait_event(e2)
-    prefetch(step, 0, first=True)
-
-    def e2e_loop(use_label_kernel):
+    def e2e_loop(use_label_kernel, steps):
         nonlocal step
-        for i in range(args.steps):
+        for i in range(steps):
             slot = i % 2
             stream.wait_event(ev_in[slot])
             if use_label_kernel:
@@ -263,7 +256,7 @@ def run_ours(args, rank, world):
                 labels = out.max(1)[1]                          # Testing/test.py:61
             ev_consumed[slot].record(stream)
             ev_done[slot].record(stream)
-            if i + 1 < args.steps:
+            if i + 1 < steps:
                 prefetch(step + 1, slot ^ 1, first=(i == 0))
             with torch.cuda.stream(d2h_s):
                 d2h_s.wait_event(ev_done[slot])
@@ -273,19 +266,39 @@ def run_ours(args, rank, world):
             step += 1
         stream.wait_stream(d2h_s)
 
-    e2e_loop(False)
+    def e2e_warmup(use_label_kernel):
+        # untimed pass through the same loop: the caching allocator gets the label / arg-max blocks it will
+        # reuse (a first-use cudaMalloc synchronises the device) and the copy streams are created
+        ev = torch.cuda.Event()
+        ev.record(stream)
+        copy_s.wait_event(ev)
+        d2h_s.wait_event(ev)
+        prefetch(step, 0, first=True)
+        e2e_loop(use_label_kernel, 4)
+
+    e2e_warmup(False)
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record(stream)
+    copy_s.wait_event(e2)
+    d2h_s.wait_event(e2)
+    prefetch(step, 0, first=True)
+
+
+    e2e_loop(False, args.steps)
     e3.record(stream)
     barrier()
     ms_e2e = e2.elapsed_time(e3)
 
     # variant: labels straight from the fused upsample+arg-max kernel, uint8 D2H
+    e2e_warmup(True)
     barrier()
     e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e4.record(stream)
     copy_s.wait_event(e4)
     d2h_s.wait_event(e4)
     prefetch(step, 0, first=True)
-    e2e_loop(True)
+    e2e_loop(True, args.steps)
     e5.record(stream)
     barrier()
     ms_e2e_labels = e4.elapsed_time(e5)

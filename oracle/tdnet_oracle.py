@@ -4,7 +4,7 @@ This file is the checker, not the product: only tests/, __graft_entry__.smoke() 
 cpu_baseline / --impl reference legs of bench.py may import it.  tdnet_b200/ never does.
 
 It restates, as stateless functions over a flat state-dict, what the reference computes in
-/root/reference/Testing/model/pspnet/{td4_psp18,td2_psp50,resnet,transformer}.py.  Every numeric
+/root/reference/Testing/model/pspnet/{td4_psp18,td2_psp50,pspnet,resnet,transformer}.py.  Every numeric
 primitive of the reference is a PyTorch library call ("third-party arithmetic"), so
 the restatement issues the *same* fp32 torch CPU primitives in the same order (conv2d ->
 batch_norm -> relu, bmm -> div -> softmax -> bmm, layer_norm, interpolate); nothing is folded or
@@ -29,6 +29,7 @@ _BACKBONES = {
     "resnet18": ("basic", (2, 2, 2, 2)),
     "resnet34": ("basic", (3, 4, 6, 3)),
     "resnet50": ("bottleneck", (3, 4, 6, 3)),
+    "resnet101": ("bottleneck", (3, 4, 23, 3)),
 }
 
 
@@ -261,19 +262,7 @@ class TDOracle:
     __call__ = forward
 
 
-def state_dict_template(arch, backbone=None, nclass=19, ln_shape=(97, 193)):
-    """Key -> zero tensor of the right shape for the reference model's state_dict (strict=True load,
-    td4_psp18.py:236-237), derived from the architecture alone so that the GPU box (which has no
-    /root/reference) can synthesise weights.  Checked against the real reference in make_golden.py."""
-    paths = 4 if arch == "td4_psp18" else 2
-    backbone = backbone or ("resnet18" if arch == "td4_psp18" else "resnet50")
-    kind, plan = stage_plan(backbone)
-    exp = 4 if kind == "bottleneck" else 1
-    c4 = 512 * exp
-    d_v = c4 if arch == "td4_psp18" else c4 // 4
-    inter = d_v // (4 if arch == "td4_psp18" else 2)
-    sd = {}
-
+def _template_helpers(sd):
     def conv(p, co, ci, k, bias=False):
         sd[p + ".weight"] = torch.zeros(co, ci, k, k)
         if bias:
@@ -284,31 +273,55 @@ def state_dict_template(arch, backbone=None, nclass=19, ln_shape=(97, 193)):
         sd[p + ".running_mean"], sd[p + ".running_var"] = torch.zeros(c), torch.zeros(c)
         sd[p + ".num_batches_tracked"] = torch.zeros((), dtype=torch.long)
 
+    return conv, bn
+
+
+def _backbone_template(sd, p, backbone):
+    """State-dict entries of one ResNet (resnet.py:116-168) under prefix `p`; returns c4 channels."""
+    conv, bn = _template_helpers(sd)
+    kind, plan = stage_plan(backbone)
+    exp = 4 if kind == "bottleneck" else 1
+    if kind == "bottleneck":
+        conv(p + ".conv1.0", 64, 3, 3), bn(p + ".conv1.1", 64)
+        conv(p + ".conv1.3", 64, 64, 3), bn(p + ".conv1.4", 64)
+        conv(p + ".conv1.6", 128, 64, 3), bn(p + ".bn1", 128)
+        inpl = 128
+    else:
+        conv(p + ".conv1", 64, 3, 7), bn(p + ".bn1", 64)
+        inpl = 64
+    for si, blocks in enumerate(plan):
+        planes = (64, 128, 256, 512)[si]
+        for bi, b in enumerate(blocks):
+            q = f"{p}.layer{si + 1}.{bi}"
+            if kind == "bottleneck":
+                conv(q + ".conv1", planes, inpl, 1), bn(q + ".bn1", planes)
+                conv(q + ".conv2", planes, planes, 3), bn(q + ".bn2", planes)
+                conv(q + ".conv3", planes * 4, planes, 1), bn(q + ".bn3", planes * 4)
+            else:
+                conv(q + ".conv1", planes, inpl, 3), bn(q + ".bn1", planes)
+                conv(q + ".conv2", planes, planes, 3), bn(q + ".bn2", planes)
+            if b["downsample"]:
+                conv(q + ".downsample.0", planes * exp, inpl, 1), bn(q + ".downsample.1", planes * exp)
+            inpl = planes * exp
+    c4 = 512 * exp
+    sd[p + ".fc.weight"], sd[p + ".fc.bias"] = torch.zeros(1000, c4), torch.zeros(1000)
+    return c4
+
+
+def state_dict_template(arch, backbone=None, nclass=19, ln_shape=(97, 193)):
+    """Key -> zero tensor of the right shape for the reference model's state_dict (strict=True load,
+    td4_psp18.py:236-237), derived from the architecture alone so that the GPU box (which has no
+    /root/reference) can synthesise weights.  Checked against the real reference in make_golden.py."""
+    if arch == "pspnet":
+        return pspnet_state_dict_template(backbone or "resnet101", nclass)
+    paths = 4 if arch == "td4_psp18" else 2
+    backbone = backbone or ("resnet18" if arch == "td4_psp18" else "resnet50")
+    sd = {}
+    conv, bn = _template_helpers(sd)
     for path in range(1, paths + 1):
-        p = f"pretrained{path}"
-        if kind == "bottleneck":
-            conv(p + ".conv1.0", 64, 3, 3), bn(p + ".conv1.1", 64)
-            conv(p + ".conv1.3", 64, 64, 3), bn(p + ".conv1.4", 64)
-            conv(p + ".conv1.6", 128, 64, 3), bn(p + ".bn1", 128)
-            inpl = 128
-        else:
-            conv(p + ".conv1", 64, 3, 7), bn(p + ".bn1", 64)
-            inpl = 64
-        for si, blocks in enumerate(plan):
-            planes = (64, 128, 256, 512)[si]
-            for bi, b in enumerate(blocks):
-                q = f"{p}.layer{si + 1}.{bi}"
-                if kind == "bottleneck":
-                    conv(q + ".conv1", planes, inpl, 1), bn(q + ".bn1", planes)
-                    conv(q + ".conv2", planes, planes, 3), bn(q + ".bn2", planes)
-                    conv(q + ".conv3", planes * 4, planes, 1), bn(q + ".bn3", planes * 4)
-                else:
-                    conv(q + ".conv1", planes, inpl, 3), bn(q + ".bn1", planes)
-                    conv(q + ".conv2", planes, planes, 3), bn(q + ".bn2", planes)
-                if b["downsample"]:
-                    conv(q + ".downsample.0", planes * exp, inpl, 1), bn(q + ".downsample.1", planes * exp)
-                inpl = planes * exp
-        sd[p + ".fc.weight"], sd[p + ".fc.bias"] = torch.zeros(1000, c4), torch.zeros(1000)
+        c4 = _backbone_template(sd, f"pretrained{path}", backbone)
+    d_v = c4 if arch == "td4_psp18" else c4 // 4
+    inter = d_v // (4 if arch == "td4_psp18" else 2)
     for path in range(1, paths + 1):
         for i in range(1, 5):
             conv(f"psp{path}.conv{i}.0", c4 // 4, c4, 1), bn(f"psp{path}.conv{i}.1", c4 // 4)
@@ -328,4 +341,60 @@ def state_dict_template(arch, backbone=None, nclass=19, ln_shape=(97, 193)):
     for path in range(1, paths + 1):
         conv(f"head{path}.conv5.0", inter, d_v, 3), bn(f"head{path}.conv5.1", inter)
         conv(f"head{path}.conv5.4", nclass, inter, 1, True)
+    return sd
+
+
+# ------------------------------------------------------------------------------------------------
+# Single-path PSPNet comparison model: Testing/model/pspnet/pspnet.py
+# ------------------------------------------------------------------------------------------------
+def psp_head(sd, p, c4):
+    """PSPHead.forward pspnet.py:102-115 = conv5 Sequential: PyramidPooling (:118-157, all channels of
+    the four pooled branches, concatenated behind c4) -> conv3x3 2*C4 -> C4/4 (no bias) -> BN -> ReLU ->
+    Dropout2d (identity in eval) -> conv1x1 -> nclass (+bias)."""
+    n, c, h, w = c4.shape
+    feats = [c4]
+    for i, bins in enumerate((1, 2, 3, 6)):
+        f = F.adaptive_avg_pool2d(c4, bins)
+        f = _bn(sd, f"{p}.conv5.0.conv{i + 1}.1", _conv(sd, f"{p}.conv5.0.conv{i + 1}.0", f), "relu")
+        feats.append(F.interpolate(f, (h, w), mode="bilinear", align_corners=True))
+    z = torch.cat(feats, 1)
+    y = _bn(sd, p + ".conv5.2", _conv(sd, p + ".conv5.1", z, padding=1), "relu")
+    return z, _conv(sd, p + ".conv5.5", y)
+
+
+class PSPNetOracle:
+    """Restates pspnet.forward (pspnet.py:73-89): only the LAST image of the batch is segmented
+    (`x = x[-1:]`), `pos_id` is accepted and ignored; backbone -> PSPHead -> bilinear upsample
+    (align_corners=True) to the input size.  Stateless between frames."""
+    paths, depth = 1, 0
+
+    def __init__(self, state_dict, backbone="resnet101", nclass=19):
+        assert backbone in _BACKBONES
+        self.sd, self.backbone, self.nclass = state_dict, backbone, nclass
+        self.taps = {}
+
+    @torch.no_grad()
+    def forward(self, img, pos_id=None):
+        x = img[-1:]
+        h, w = x.shape[2:]
+        t = {}
+        c4 = resnet_c4(self.sd, "pretrained", x, self.backbone, t)
+        z, low = psp_head(self.sd, "head", c4)
+        t.update(c4=c4, z=z, head=low)
+        self.taps = t
+        return F.interpolate(low, (h, w), mode="bilinear", align_corners=True)
+
+    __call__ = forward
+
+
+def pspnet_state_dict_template(backbone="resnet101", nclass=19):
+    """State-dict layout of pspnet.pspnet (pspnet.py:31-71): `pretrained.*`, `head.conv5.0.conv{1..4}.{0,1}`
+    (PyramidPooling), `head.conv5.1` (3x3), `head.conv5.2` (BN), `head.conv5.5` (classifier)."""
+    sd = {}
+    conv, bn = _template_helpers(sd)
+    c4 = _backbone_template(sd, "pretrained", backbone)
+    for i in range(1, 5):
+        conv(f"head.conv5.0.conv{i}.0", c4 // 4, c4, 1), bn(f"head.conv5.0.conv{i}.1", c4 // 4)
+    conv("head.conv5.1", c4 // 4, 2 * c4, 3), bn("head.conv5.2", c4 // 4)
+    conv("head.conv5.5", nclass, c4 // 4, 1, True)
     return sd

@@ -341,13 +341,19 @@ int conv2d_tc(const tdn_tc_conv_desc* d, cudaStream_t stream) {
   p.range_flag = d->range_flag;
 
   {
-    // 3x3 / stride 1 / dilation <= 2: one halo-region load per channel block instead of nine tap loads
-    static int halo = -1;
-    if (halo < 0) {
+    // 3x3 / stride 1 / dilation <= 2: one halo-region load per channel block instead of nine tap loads.
+    // Measured on B200 (profiles/r01_tc_probe_stem_halo.txt): the region variant wins where the per-tap kernel
+    // is L2->SM bound with two channel blocks (layer 2: 128 -> 128, 0.048 -> 0.039 ms) and loses on layer 1
+    // (64 -> 64: one block per tile, its 16-byte-row TMA boxes cost more than they save) and on layer 3
+    // (dilation 2 regions are 2x the tile).  TDNET_TC_HALO = 0 / 1 forces it off / on wherever it applies.
+    static int halo = -2;
+    if (halo == -2) {
       const char* e = getenv("TDNET_TC_HALO");
-      halo = e ? atoi(e) : 0;
+      halo = e ? atoi(e) : -1;
     }
-    if (halo && d->kh == 3 && d->kw == 3 && cs == 1 && d->dilation <= 2 && !d->weight_batched && in.w >= 8)
+    const bool halo_ok = d->kh == 3 && d->kw == 3 && cs == 1 && d->dilation <= 2 && !d->weight_batched && in.w >= 8;
+    const bool halo_auto = d->dilation == 1 && in.c == 128 && d->cout <= 128;
+    if (halo_ok && (halo > 0 || (halo < 0 && halo_auto)))
       return conv2d_tc_halo(d, p, g_num_sms, p.chunk_kb, stream);
   }
 

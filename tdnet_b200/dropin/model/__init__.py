@@ -15,16 +15,4 @@ _repo = _os.path.dirname(_os.path.dirname(_os.path.dirname(_os.path.dirname(_os.
 if _repo not in _sys.path:
     _sys.path.insert(0, _repo)
 
-from tdnet_b200.model import td2_psp50, td4_psp18  # noqa: E402,F401
-
-
-class _PspnetNotOnHotPath:
-    """Testing/model/pspnet/pspnet.py (single-path PSPNet-101 comparison model) is outside the
-    accelerated hot path."""
-
-    def pspnet(self, *a, **k):
-        raise NotImplementedError("pspnet (PSPNet-101 comparison model) is not part of the tdnet_b200 hot path; "
-                                  "use the reference implementation for it")
-
-
-pspnet = _PspnetNotOnHotPath()
+from tdnet_b200.model import pspnet, td2_psp50, td4_psp18  # noqa: E402,F401

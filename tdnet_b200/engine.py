@@ -216,12 +216,12 @@ class Engine:
         self.fused_attn = os.environ.get("TDNET_B200_FUSED_ATTN", "1") != "0"
         self.tc_stride2 = os.environ.get("TDNET_B200_TC_STRIDE2", "1") != "0"
         self.fused_stem = os.environ.get("TDNET_B200_FUSED_STEM", "1") != "0"
-        self.tc_stem = os.environ.get("TDNET_B200_TC_STEM", "0") != "0"
+        self.tc_stem = os.environ.get("TDNET_B200_TC_STEM", "1") != "0"   # tcgen05 stem (0.10 ms vs 0.39 ms on the fp32 pipe)
         use_side = os.environ.get("TDNET_B200_SIDE_STREAM", "1") != "0"
         self.side_stream = torch.cuda.Stream(device) if (use_side and device.type == "cuda") else None
         self.m, self.n, self.H, self.W, self.device = arch, n, H, W, device
         self.h8, self.w8 = A.feature_hw(H, W)
-        if tuple(ln_shape) != (self.h8, self.w8):
+        if arch.arch != "pspnet" and tuple(ln_shape) != (self.h8, self.w8):
             # same failure the reference has at any input but 769x1537 (td4_psp18.py:107-110)
             raise RuntimeError(f"Given normalized_shape={list(ln_shape)}, expected input with shape "
                                f"[*, {ln_shape[0]}, {ln_shape[1]}], but got feature map "
@@ -242,10 +242,11 @@ class Engine:
         self.v_slots = [View.alloc(n, 1, self.pk, m.d_v, dev, zero=True, split=self.tc) for _ in range(m.depth)]
         self.range_flag = torch.zeros(1, dtype=torch.int32, device=dev)
         self._consts: Dict[tuple, torch.Tensor] = {}
+        ln_paths = range(1, m.paths + 1) if m.arch != "pspnet" else ()
         self.ln_gamma = {p: state_dict[f"layer_norm{p}.ln.weight"].detach().float().reshape(-1).contiguous().to(dev)
-                         for p in range(1, m.paths + 1)}
+                         for p in ln_paths}
         self.ln_beta = {p: state_dict[f"layer_norm{p}.ln.bias"].detach().float().reshape(-1).contiguous().to(dev)
-                        for p in range(1, m.paths + 1)}
+                        for p in ln_paths}
 
     # ------------------------------------------------------------------ helpers
     def packed(self, spec: A.Conv, row_slice=None) -> PackedConv:
@@ -462,6 +463,8 @@ class Engine:
             x = t
         c4 = x
         assert (c4.h, c4.w, c4.c) == (h8, w8, m.c4), (c4.h, c4.w, c4.c)
+        if m.arch == "pspnet":
+            return self._build_pspnet_tail(plan, c4)
 
         # --- pyramid pooling slice -> z  (channels: [c4 slice | 4 x upsampled branch slice])
         pid = m.psp_pid(path)
@@ -546,6 +549,40 @@ class Engine:
         # alternative last op: fused upsample + arg-max -> uint8 labels (forward_labels)
         plan.labels_op = (lib.tdn_upsample_argmax, (C.byref(self._ct(plan, low)), "out", H, W, "stream"))
         plan.taps = dict(c4=c4, z=z, q_cur=q_cur, v_cur=v_cur, fused=fused, normed=normed, head=low)
+        return plan
+
+    def _build_pspnet_tail(self, plan: FramePlan, c4: View) -> FramePlan:
+        """PSPHead of the single-path comparison model (pspnet.py:102-157): the full pyramid (every channel of
+        the four pooled branches) concatenated behind c4, conv3x3 2*C4 -> C4/4 + BN + ReLU, classifier, x8
+        upsample.  Same kernels as the TD paths, no FIFO / attention / LayerNorm."""
+        m, n, lib = self.m, self.n, self.lib
+        H, W, h8, w8 = self.H, self.W, self.h8, self.w8
+        quarter = m.c4 // 4
+        z = self.buf(n, h8, w8, 2 * m.c4)
+        pooled = self.buf(n, 1, 50, m.c4, split=False)
+        ws_bytes = int(lib.tdn_psp_pool_workspace_bytes(n, h8, m.c4))
+        ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=self.device)
+        plan.add(lib.tdn_psp_pool, C.byref(self._ct(plan, c4)), C.byref(self._ct(plan, pooled)), ws.data_ptr(),
+                 ws_bytes, "stream", launches=2)
+        plan.keep.append(ws)
+        pcs = [self.packed(c) for c in A.psp_convs(m, 1)]
+        smalls = [self.buf(n, bins, bins, quarter, split=False) for bins in PSP_BINS]
+        arr = lambda xs: (C.c_void_p * 4)(*xs)  # noqa: E731
+        wp, sp, bp = arr([p_.weight.data_ptr() for p_ in pcs]), arr([p_.scale.data_ptr() for p_ in pcs]), \
+            arr([p_.bias.data_ptr() for p_ in pcs])
+        op = arr([sm.ptr for sm in smalls])
+        plan.add(lib.tdn_psp_branch_convs, C.byref(self._ct(plan, pooled)), wp, sp, bp, quarter, op, "stream")
+        ptrs = arr([sm.ptr for sm in smalls])
+        plan.add(lib.tdn_psp_concat, C.byref(self._ct(plan, c4)), ptrs, quarter, C.byref(self._ct(plan, z)), "stream")
+        plan.keep.append((wp, sp, bp, op, pcs, ptrs, smalls))
+        hc = A.head_convs(m, 1)
+        mid = self.buf(n, h8, w8, m.head_mid)
+        self._conv(plan, self.packed(hc[0]), z, mid)
+        low = self.buf(n, h8, w8, m.nclass, split=False)
+        self._conv(plan, self.packed(hc[1]), mid, low)
+        plan.add(lib.tdn_upsample_logits, C.byref(self._ct(plan, low)), "out", H, W, "stream")
+        plan.labels_op = (lib.tdn_upsample_argmax, (C.byref(self._ct(plan, low)), "out", H, W, "stream"))
+        plan.taps = dict(c4=c4, z=z, head=low)
         return plan
 
     def _grid_view(self, slot: View) -> View:

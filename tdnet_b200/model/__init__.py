@@ -1,3 +1,3 @@
-"""Same surface as Testing/model/__init__.py:1-3: the *modules* td4_psp18 and td2_psp50
-(classes are model.td4_psp18.td4_psp18 / model.td2_psp50.td2_psp50)."""
-from . import td2_psp50, td4_psp18  # noqa: F401
+"""Same surface as Testing/model/__init__.py:1-3: the *modules* td4_psp18, td2_psp50 and pspnet
+(classes are model.td4_psp18.td4_psp18 / model.td2_psp50.td2_psp50 / model.pspnet.pspnet)."""
+from . import pspnet, td2_psp50, td4_psp18  # noqa: F401

@@ -55,13 +55,15 @@ def _default_init_(module: nn.Module, seed=0):
 
 
 class TDModel(nn.Module):
-    ARCH = None          # 'td4_psp18' | 'td2_psp50'
+    ARCH = None          # 'td4_psp18' | 'td2_psp50' | 'pspnet'
     PATHS = None
+    BACKBONES = ("resnet50", "resnet34", "resnet18")
 
     def __init__(self, nclass=21, norm_layer=None, backbone=None, dilated=True, aux=True, multi_grid=True,
                  path_num=None, model_path=None, ln_shape=(97, 193)):
         super().__init__()
-        assert backbone in ("resnet50", "resnet34", "resnet18")
+        if backbone not in self.BACKBONES:
+            raise RuntimeError("unknown backbone: {}".format(backbone))   # td4_psp18.py:68 / pspnet.py:67-68
         assert path_num == self.PATHS
         if not (dilated and multi_grid):
             raise RuntimeError("tdnet_b200 implements the dilated, multi-grid backbone the reference tests ship")

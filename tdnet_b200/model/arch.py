@@ -1,7 +1,8 @@
-"""Architecture tables of the two temporally-distributed models (product side).
+"""Architecture tables of the two temporally-distributed models and of the single-path PSPNet
+comparison model (product side).
 
 A declarative description of what the reference builds imperatively in
-Testing/model/pspnet/td4_psp18.py:29-121, td2_psp50.py:29-96 and resnet.py:114-202: which
+Testing/model/pspnet/td4_psp18.py:29-121, td2_psp50.py:29-96, pspnet.py:31-157 and resnet.py:114-202: which
 convolutions exist, their geometry, and which state-dict entries hold their parameters.  The
 engine (tdnet_b200/engine.py) turns these tables into C-ABI calls; `parameter_table` gives the flat
 state-dict (name -> shape) that checkpoints of the reference are loaded against with strict=True.
@@ -12,7 +13,7 @@ from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Tuple
 
 BLOCKS = {"resnet18": ("basic", (2, 2, 2, 2)), "resnet34": ("basic", (3, 4, 6, 3)),
-          "resnet50": ("bottleneck", (3, 4, 6, 3))}
+          "resnet50": ("bottleneck", (3, 4, 6, 3)), "resnet101": ("bottleneck", (3, 4, 23, 3))}
 STAGE_PLANES = (64, 128, 256, 512)
 MULTI_GRID = (4, 8, 16)  # resnet.py:181 `multi_dilations`
 
@@ -56,6 +57,11 @@ class ModelArch:
     nclass: int
     stems: Dict[int, List[Conv]] = field(default_factory=dict)
     stages: Dict[int, List[Block]] = field(default_factory=dict)
+
+    def prefix(self, path: int) -> str:
+        """State-dict prefix of the path's backbone: `pretrained{path}` for the TD models, plain `pretrained`
+        for pspnet (pspnet.py:49-66)."""
+        return "pretrained" if self.arch == "pspnet" else f"pretrained{path}"
 
     def hop_modules(self, path: int) -> List[str]:
         """Attention modules a path walks through, oldest key frame first
@@ -107,7 +113,15 @@ def _backbone(prefix: str, backbone: str):
 
 
 def build_arch(arch: str, backbone: str, nclass: int) -> ModelArch:
-    if backbone not in BLOCKS:
+    if arch == "pspnet":
+        if backbone not in BLOCKS:
+            raise RuntimeError("unknown backbone: {}".format(backbone))      # pspnet.py:67-68
+        c4 = 512 * (4 if BLOCKS[backbone][0] == "bottleneck" else 1)
+        # one path, no FIFO, no attention: d_k / d_v unused; head_mid = PSPHead inter_channels (pspnet.py:105)
+        m = ModelArch(arch, backbone, 1, 0, c4, 0, c4, c4 // 4, nclass)
+        m.stems[1], m.stages[1], _ = _backbone("pretrained", backbone)
+        return m
+    if backbone not in BLOCKS or backbone == "resnet101":
         raise RuntimeError("Four branch model only support ResNet18 amd ResNet34")  # td4_psp18.py:68
     paths = 4 if arch == "td4_psp18" else 2
     exp = 4 if BLOCKS[backbone][0] == "bottleneck" else 1
@@ -145,8 +159,12 @@ def parameter_table(m: ModelArch, ln_shape=(97, 193)):
                 conv(c)
             if b.downsample:
                 conv(b.downsample)
-        t[f"pretrained{path}.fc.weight"] = ((1000, m.c4), "param")  # resnet.py:160, never used by forward
-        t[f"pretrained{path}.fc.bias"] = ((1000,), "param")
+        t[f"{m.prefix(path)}.fc.weight"] = ((1000, m.c4), "param")  # resnet.py:160, never used by forward
+        t[f"{m.prefix(path)}.fc.bias"] = ((1000,), "param")
+    if m.arch == "pspnet":
+        for c in psp_convs(m, 1) + head_convs(m, 1):
+            conv(c)
+        return t
     for path in range(1, m.paths + 1):
         for c in psp_convs(m, path, full=True):
             conv(c)
@@ -163,9 +181,10 @@ def parameter_table(m: ModelArch, ln_shape=(97, 193)):
 
 
 def psp_convs(m: ModelArch, path: int, full=False) -> List[Conv]:
-    """PyramidPooling conv1..4 (td4_psp18.py:255-266): 1x1, c4 -> c4/4, BN, ReLU."""
-    return [Conv(f"psp{path}.conv{i}.0", m.c4, m.c4 // 4, 1, bn=f"psp{path}.conv{i}.1", act="relu")
-            for i in range(1, 5)]
+    """PyramidPooling conv1..4 (td4_psp18.py:255-266; pspnet.py:131-142, where the module is element 0 of
+    PSPHead.conv5): 1x1, c4 -> c4/4, BN, ReLU."""
+    p = "head.conv5.0" if m.arch == "pspnet" else f"psp{path}"
+    return [Conv(f"{p}.conv{i}.0", m.c4, m.c4 // 4, 1, bn=f"{p}.conv{i}.1", act="relu") for i in range(1, 5)]
 
 
 def encoding_convs(m: ModelArch, path: int) -> Dict[str, List[Conv]]:
@@ -186,7 +205,11 @@ def fc_conv(m: ModelArch, module: str) -> Conv:
 
 
 def head_convs(m: ModelArch, path: int) -> List[Conv]:
-    """FCNHead.conv5 (td4_psp18.py:295-299)."""
+    """FCNHead.conv5 (td4_psp18.py:295-299); for pspnet the rest of PSPHead.conv5 behind the pyramid
+    (pspnet.py:108-113): conv3x3 2*C4 -> C4/4, BN, ReLU, Dropout2d, conv1x1 -> nclass."""
+    if m.arch == "pspnet":
+        return [Conv("head.conv5.1", 2 * m.c4, m.head_mid, 3, bn="head.conv5.2", act="relu"),
+                Conv("head.conv5.5", m.head_mid, m.nclass, 1, bias=True)]
     h = f"head{path}.conv5"
     return [Conv(f"{h}.0", m.d_v, m.head_mid, 3, bn=f"{h}.1", act="relu"),
             Conv(f"{h}.4", m.head_mid, m.nclass, 1, bias=True)]

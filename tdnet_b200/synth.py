@@ -19,7 +19,7 @@ import re
 import torch
 
 
-_RESIDUAL_TAIL_BN = re.compile(r"pretrained\d+\.layer\d+\.\d+\.(bn2|bn3)\.weight$")
+_RESIDUAL_TAIL_BN = re.compile(r"pretrained\d*\.layer\d+\.\d+\.(bn2|bn3)\.weight$")
 
 
 def _gen_for(key: str, seed: int) -> torch.Generator:

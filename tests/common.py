@@ -4,7 +4,7 @@ import os
 import numpy as np
 import torch
 
-from oracle.tdnet_oracle import TDOracle, state_dict_template
+from oracle.tdnet_oracle import PSPNetOracle, TDOracle, state_dict_template
 from tdnet_b200.synth import synth_clip, synth_state_dict
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -19,6 +19,8 @@ GOLDEN_CASES = {
     "td4_r50_64x64_n2": ("td4_psp18", "resnet50"),
     "td4_r18_769x1537_chk": ("td4_psp18", "resnet18"),
 }
+# single-path PSPNet comparison model (Testing/model/pspnet/pspnet.py): name -> backbone
+PSPNET_GOLDEN_CASES = {"psp_r101_64x96_n2": "resnet101", "psp_r18_97x161": "resnet18"}
 
 
 def load_golden(name):
@@ -41,6 +43,11 @@ def make_oracle(arch, backbone, H, W, seed=0):
     h8, w8 = feat_hw(H, W)
     sd = make_weights(arch, backbone, h8, w8, seed)
     return TDOracle(arch, sd, backbone), sd
+
+
+def make_pspnet_oracle(backbone, seed=0):
+    sd = synth_state_dict(state_dict_template("pspnet", backbone), seed=seed)
+    return PSPNetOracle(sd, backbone), sd
 
 
 def max_abs(a, b):

@@ -21,7 +21,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, "/root/reference/Testing")
 
-from model import td2_psp50, td4_psp18  # noqa: E402  (the reference)
+from model import pspnet, td2_psp50, td4_psp18  # noqa: E402  (the reference)
 
 from oracle.tdnet_oracle import state_dict_template  # noqa: E402  (key/shape check only)
 from tdnet_b200.synth import synth_clip, synth_state_dict  # noqa: E402
@@ -34,6 +34,9 @@ CASES = [
     ("td2_r34_80x112", "td2_psp50", "resnet34", 80, 112, 1, 3, (2,)),      # 'bise34' stand-in, 10x14
     ("td4_r50_64x64_n2", "td4_psp18", "resnet50", 64, 64, 2, 5, (4,)),     # batch 2 streams
     ("td4_r18_769x1537_chk", "td4_psp18", "resnet18", 769, 1537, 1, 5, ()),  # reference-native size
+    # single-path PSPNet comparison model (pspnet.py); batch 2: only x[-1:] is segmented
+    ("psp_r101_64x96_n2", "pspnet", "resnet101", 64, 96, 2, 2, (0, 1)),
+    ("psp_r18_97x161", "pspnet", "resnet18", 97, 161, 1, 2, (1,)),
 ]
 
 
@@ -46,7 +49,43 @@ def feat_hw(h, w):
     return h, w
 
 
+def run_pspnet_case(name, backbone, H, W, batch, n_frames, keep):
+    """pspnet.pspnet(nclass=19, backbone=...) (pspnet.py:31-89): stateless, segments x[-1:] only."""
+    torch.manual_seed(0)
+    net = pspnet.pspnet(nclass=19, backbone=backbone).eval()
+    ref_sd = net.state_dict()
+    tmpl = state_dict_template("pspnet", backbone)
+    assert set(tmpl) == set(ref_sd), sorted(set(tmpl) ^ set(ref_sd))[:8]
+    for k in ref_sd:
+        assert tuple(tmpl[k].shape) == tuple(ref_sd[k].shape) and tmpl[k].dtype == ref_sd[k].dtype, k
+    net.load_state_dict(synth_state_dict(tmpl, seed=0), strict=True)
+    cur = {}
+    net.head.conv5[0].register_forward_hook(lambda m, i, o: cur.__setitem__("z", o))
+    net.head.register_forward_hook(lambda m, i, o: cur.__setitem__("head", o))
+    rec = {}
+    with torch.no_grad():
+        for i, f in enumerate(synth_clip(n_frames, H, W, batch=batch, clip_id=0)):
+            cur.clear()
+            # pspnet.forward runs the backbone piecewise (no pretrained.forward hook fires): tap layer4 instead
+            hk = net.pretrained.layer4.register_forward_hook(lambda m, i_, o: cur.__setitem__("c4", o))
+            out = net(f, pos_id=i % 4)
+            hk.remove()
+            rec[f"head_{i}"] = cur["head"].numpy().copy()
+            if i in keep:
+                rec[f"logits_{i}"] = out.numpy().copy()
+            if i == n_frames - 1:
+                rec["tap_c4"] = cur["c4"][:, ::CH_STRIDE].numpy().copy()
+                rec["tap_z"] = cur["z"][:, ::CH_STRIDE].numpy().copy()
+    h8, w8 = feat_hw(H, W)
+    rec["meta"] = np.array([H, W, batch, n_frames, h8, w8], dtype=np.int64)
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **rec)
+    print(f"{name}: {os.path.getsize(path) / 1e6:.2f} MB, {len(rec)} arrays")
+
+
 def run_case(name, arch, backbone, H, W, batch, n_frames, keep):
+    if arch == "pspnet":
+        return run_pspnet_case(name, backbone, H, W, batch, n_frames, keep)
     torch.manual_seed(0)
     mod = td4_psp18.td4_psp18 if arch == "td4_psp18" else td2_psp50.td2_psp50
     paths = 4 if arch == "td4_psp18" else 2

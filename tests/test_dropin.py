@@ -21,8 +21,10 @@ def test_dropin_import_surface():
         assert len(net.state_dict()) == 728
         net2 = model.td2_psp50.td2_psp50(nclass=19, path_num=2)
         assert len(net2.state_dict()) == 776 and net2.Q_queue == []
-        with pytest.raises(NotImplementedError):
-            model.pspnet.pspnet(nclass=19)
+        net3 = model.pspnet.pspnet(nclass=19)                      # PSPNet-101 comparison model (test.py:29-31)
+        assert len(net3.state_dict()) == 670 and net3.backbone == "resnet101"
+        with pytest.raises(RuntimeError, match="unknown backbone"):
+            model.pspnet.pspnet(nclass=19, backbone="resnet152")
     finally:
         sys.path.pop(0)
         sys.modules.pop("model", None)

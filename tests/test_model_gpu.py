@@ -11,8 +11,8 @@ import numpy as np
 import pytest
 import torch
 
-from common import (CH_STRIDE, GOLDEN_CASES, argmax_report, load_golden, make_oracle, make_weights, max_abs,
-                    record, rel_l2)
+from common import (CH_STRIDE, GOLDEN_CASES, PSPNET_GOLDEN_CASES, argmax_report, load_golden, make_oracle,
+                    make_pspnet_oracle, make_weights, max_abs, record, rel_l2)
 from tdnet_b200.synth import synth_clip
 
 pytestmark = pytest.mark.gpu
@@ -224,3 +224,74 @@ def test_forward_u8_is_bit_identical_to_normalised_fp32_input():
         assert torch.equal(out_ref, out_u8), i
     lab = b.forward_u8(torch.from_numpy(u8).cuda(), pos_id=0, labels=True)
     assert lab.dtype == torch.uint8 and lab.shape == (1, H, W)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Single-path PSPNet comparison model (Testing/model/pspnet/pspnet.py).  Its synthetic-
+# weight logits are larger (std 6-9, |max| 18-35) than the TD models', so the gate is stated relative to the
+# largest reference logit: max-abs error <= PSP_REL_TOL * max|ref| (the TD gate 2e-4 at |max| ~ 8 is 2.5e-5).
+# ---------------------------------------------------------------------------------------------------------
+PSP_REL_TOL = 2.5e-5
+
+
+def build_pspnet(backbone, sd, mode="tc"):
+    from tdnet_b200.model import pspnet
+    net = pspnet.pspnet(nclass=19, backbone=backbone)
+    net.load_state_dict(sd, strict=True)
+    net.engine_mode = mode
+    return net.eval().to("cuda:0")
+
+
+@pytest.mark.parametrize("mode", ["tc", "simt"])
+@pytest.mark.parametrize("name", sorted(PSPNET_GOLDEN_CASES))
+def test_pspnet_matches_reference_golden(name, mode):
+    """pspnet.forward(x, pos_id) vs what the unmodified reference produced; the batch-2 case checks that only
+    x[-1:] is segmented (pspnet.py:74); frames repeat through the CUDA-graph replay path."""
+    backbone = PSPNET_GOLDEN_CASES[name]
+    g, m = load_golden(name)
+    _, sd = make_pspnet_oracle(backbone)
+    net = build_pspnet(backbone, sd, mode)
+    frames = synth_clip(m["n_frames"], m["H"], m["W"], batch=m["batch"], clip_id=0)
+    for rep_i in range(2):                      # second pass replays the captured graph
+        for i, f in enumerate(frames):
+            out = net(f.cuda(), pos_id=i % 4)
+            torch.cuda.synchronize()
+            assert out.shape == (1, 19, m["H"], m["W"]) and out.dtype == torch.float32 and out.is_cuda
+            scale = float(np.abs(g[f"head_{i}"]).max())
+            err = max_abs(tap(net._last[1].taps["head"]), g[f"head_{i}"])
+            assert err <= PSP_REL_TOL * scale, (name, i, err, scale)
+            if f"logits_{i}" in g:
+                ref = torch.from_numpy(g[f"logits_{i}"])
+                e = max_abs(out.cpu(), ref)
+                assert e <= PSP_REL_TOL * scale, (name, i, e, scale)
+                rep = argmax_report(out.cpu(), ref, max(e, 1e-6))
+                record(f"golden/{name}/{mode}/frame{i}", max_abs=e, rel_l2=rel_l2(out.cpu(), ref), ref_absmax=scale,
+                       **rep)
+                assert rep["mismatch_decided"] == 0, rep
+                assert rep["near_ties"] <= 0.001 * rep["pixels"] + 2, rep
+            assert net.Q_queue == [] and net.K_queue == [] and net.V_queue == []
+    t = net._last[1].taps
+    assert max_abs(tap(t["c4"])[:, ::CH_STRIDE], g["tap_c4"]) <= TAP_TOL
+    assert max_abs(tap(t["z"])[:, ::CH_STRIDE], g["tap_z"]) <= TAP_TOL
+    net.check_numeric_range()
+
+
+def test_pspnet101_512x1024_against_oracle():
+    """PSPNet-101 at a realistic size (64x128 map, 4096-channel pyramid, K = 36 864 head conv) vs the oracle on
+    the host CPU; also forward_labels == argmax of the logits."""
+    H, W = 512, 1024
+    oracle, sd = make_pspnet_oracle("resnet101")
+    net = build_pspnet("resnet101", sd)
+    f = synth_clip(1, H, W, clip_id=3)[0]
+    ref = oracle(f)
+    out = net(f.cuda()).cpu()
+    scale = float(ref.abs().max())
+    e = max_abs(out, ref)
+    rep = argmax_report(out, ref, max(e, 1e-6))
+    record("pspnet101/512x1024", max_abs=e, rel_l2=rel_l2(out, ref), ref_absmax=scale, **rep)
+    assert e <= PSP_REL_TOL * scale, (e, scale)
+    assert rep["mismatch_decided"] == 0 and rep["near_ties"] <= 0.001 * rep["pixels"], rep
+    labels = net.forward_labels(f.cuda())
+    out2 = net(f.cuda())
+    assert torch.equal(labels.long(), out2.max(1)[1])
+    net.check_numeric_range()

@@ -3,7 +3,8 @@ import numpy as np
 import pytest
 import torch
 
-from common import CH_STRIDE, GOLDEN_CASES, load_golden, make_oracle, max_abs
+from common import (CH_STRIDE, GOLDEN_CASES, PSPNET_GOLDEN_CASES, load_golden, make_oracle, make_pspnet_oracle,
+                    max_abs)
 from oracle.tdnet_oracle import stage_plan, state_dict_template
 from tdnet_b200.synth import synth_clip
 
@@ -42,6 +43,26 @@ def test_oracle_matches_reference_outputs(name):
         assert max_abs(t["v3"], g["tap_hop1"]) <= 5 * TOL
     # FIFO semantics of buffer_contral (td4_psp18.py:123-134 / td2_psp50.py:98-109)
     assert len(oracle.Q_queue) == len(oracle.K_queue) == len(oracle.V_queue) == oracle.depth
+
+
+@pytest.mark.parametrize("name", sorted(PSPNET_GOLDEN_CASES))
+def test_pspnet_oracle_matches_reference_outputs(name):
+    """PSPNetOracle vs the unmodified pspnet.pspnet (pspnet.py:31-89) run on CPU; the batch-2 case pins
+    `x = x[-1:]` (only the last image of the batch is segmented, :74)."""
+    g, m = load_golden(name)
+    oracle, _ = make_pspnet_oracle(PSPNET_GOLDEN_CASES[name])
+    frames = synth_clip(m["n_frames"], m["H"], m["W"], batch=m["batch"], clip_id=0)
+    scale = 1.0
+    for i, f in enumerate(frames):
+        out = oracle(f, pos_id=i % 4)
+        scale = max(1.0, float(np.abs(g[f"head_{i}"]).max()))
+        assert max_abs(oracle.taps["head"], g[f"head_{i}"]) <= TOL * scale, (name, i)
+        if f"logits_{i}" in g:
+            assert out.shape == g[f"logits_{i}"].shape == (1, 19, m["H"], m["W"])
+            assert max_abs(out, g[f"logits_{i}"]) <= TOL * scale
+    s = CH_STRIDE
+    assert max_abs(oracle.taps["c4"][:, ::s], g["tap_c4"]) <= 5 * TOL * scale
+    assert max_abs(oracle.taps["z"][:, ::s], g["tap_z"]) <= 5 * TOL * scale
 
 
 def test_oracle_native_size_checksums():
@@ -90,3 +111,5 @@ def test_state_dict_template_sizes():
     assert len(sd) == 728 and abs(sum(v.numel() for v in sd.values()) / 1e6 - 54.9) < 0.1
     sd = state_dict_template("td2_psp50")
     assert len(sd) == 776 and abs(sum(v.numel() for v in sd.values()) / 1e6 - 65.5) < 0.1
+    sd = state_dict_template("pspnet")   # PSPNet-101: 670 tensors / 67.9 M (checked against the reference in make_golden.py)
+    assert len(sd) == 670 and abs(sum(v.numel() for v in sd.values()) / 1e6 - 67.9) < 0.1
