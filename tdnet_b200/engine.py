@@ -440,7 +440,7 @@ class Engine:
         # --- attention prelude on the side stream: the FIFO hops and the fc of the last hop depend only on the
         #     FIFO (td4_psp18.py:145-146), so they overlap the backbone instead of serialising behind it
         pre = None
-        if steady and self.tc and self.fused_attn and self.side_stream is not None:
+        if steady and m.depth > 0 and self.tc and self.fused_attn and self.side_stream is not None:
             plan.mark("fork")
             plan.side = True
             pre = self._attention_chain_tc(plan, path, None, None, stage="prelude")

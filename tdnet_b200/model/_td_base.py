@@ -62,8 +62,11 @@ class TDModel(nn.Module):
     def __init__(self, nclass=21, norm_layer=None, backbone=None, dilated=True, aux=True, multi_grid=True,
                  path_num=None, model_path=None, ln_shape=(97, 193)):
         super().__init__()
-        if backbone not in self.BACKBONES:
-            raise RuntimeError("unknown backbone: {}".format(backbone))   # td4_psp18.py:68 / pspnet.py:67-68
+        if self.ARCH == "pspnet":
+            if backbone not in self.BACKBONES:
+                raise RuntimeError("unknown backbone: {}".format(backbone))   # pspnet.py:67-68
+        else:
+            assert backbone in self.BACKBONES                                # td4_psp18.py:52 / td2_psp50.py:52
         assert path_num == self.PATHS
         if not (dilated and multi_grid):
             raise RuntimeError("tdnet_b200 implements the dilated, multi-grid backbone the reference tests ship")
