@@ -137,7 +137,17 @@ typedef struct tdn_tc_conv_desc {
   float leaky_slope;
   int32_t* range_flag;
   int32_t stride; /* 0 or 1: stride 1; 2: stride-2 conv (TMA element strides), out = ceil(in / 2) */
+  int32_t variant; /* TDN_TC_AUTO (0): the library picks the kernel; otherwise force one (tests / tuning;
+                      TDN_ERR_UNSUPPORTED if the geometry does not fit it).  All variants compute the same
+                      products in the same order and are bit-identical. */
 } tdn_tc_conv_desc;
+
+enum {
+  TDN_TC_AUTO = 0,
+  TDN_TC_BASE = 1, /* one CTA per 128-pixel x 64/128-channel tile, one A box per filter tap */
+  TDN_TC_HALO = 2, /* 3x3 stride-1 dilation<=2: one halo-region load per channel block */
+  TDN_TC_PAIR = 3  /* cout % 128 == 0, shared weights: 2-CTA clusters (tcgen05 cta_group::2), M 256 x N 256/128 */
+};
 
 int tdn_conv2d_tc(const tdn_tc_conv_desc* desc, void* stream);
 

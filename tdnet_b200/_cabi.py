@@ -40,7 +40,10 @@ class TcConvDesc(C.Structure):
                 ("scale", C.c_void_p), ("bias", C.c_void_p),
                 ("cout", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32), ("dilation", C.c_int32),
                 ("act", C.c_int32), ("leaky_slope", C.c_float), ("range_flag", C.c_void_p),
-                ("stride", C.c_int32)]
+                ("stride", C.c_int32), ("variant", C.c_int32)]
+
+
+TC_AUTO, TC_BASE, TC_HALO, TC_PAIR = 0, 1, 2, 3   # tdn_tc_conv_desc.variant
 
 
 class AttentionDesc(C.Structure):

@@ -48,7 +48,10 @@ __device__ __forceinline__ float tc_act(float v, int act, float slope) {
 
 // Epilogue role of warps 2..9 for a persistent CTA that walks tiles `blockIdx.x + i * gridDim.x`; `num_kb` K
 // blocks per tile arrive in chunks of p.chunk_kb through the TMEM accumulator ring.
-template <int BLOCK_N, int NUM_ACC>
+// PAIR = true (tc_conv_pair.cu): the CTA is one half of a two-CTA cluster that walks PAIR tiles
+// `cluster + i * clusters` (two adjacent 128-pixel M tiles x BLOCK_N columns); this CTA owns M tile
+// 2 * pair_m + rank, and a drained accumulator is handed back on the LEADER CTA's barrier, one arrival per warp.
+template <int BLOCK_N, int NUM_ACC, bool PAIR = false>
 __device__ __forceinline__ void tc_epilogue_role(const TcParams& p, uint32_t tmem_base, uint64_t* tmem_full,
                                                  uint64_t* tmem_empty, int warp, int lane, int num_kb) {
     // Warp w may only touch TMEM lanes 32*(w%4)..+31, so the 8 epilogue warps pair up per lane quarter:
@@ -62,16 +65,19 @@ __device__ __forceinline__ void tc_epilogue_role(const TcParams& p, uint32_t tme
     int as = 0;
     uint32_t aphase = 0;
     bool out_of_range = false;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    const int tile_first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    for (int tile = tile_first; tile < p.num_tiles; tile += tile_step) {
       const int nt = tile % p.n_tiles_n;
       int mt = tile / p.n_tiles_n;
+      if (PAIR) mt = 2 * mt + (int)(blockIdx.x & 1);
       const int tx = mt % p.tiles_w;
       mt /= p.tiles_w;
       const int ty = mt % p.tiles_h;
       const int img = mt / p.tiles_h;
       const int oh = ty * p.BH + h_local;
       const int ow = tx * p.BW + w_local;
-      const bool valid = oh < p.Ho && ow < p.Wo;
+      const bool valid = oh < p.Ho && ow < p.Wo && img < p.n_img;
       const long long ooff = (long long)img * p.osn + (long long)oh * p.osh + (long long)ow * p.osw;
       const long long roff = (long long)img * p.rsn + (long long)oh * p.rsh + (long long)ow * p.rsw;
       const float bias_m = (p.bias && p.bias_along_m && valid) ? __ldg(p.bias + oh * p.Wo + ow) : 0.f;
@@ -92,7 +98,12 @@ __device__ __forceinline__ void tc_epilogue_role(const TcParams& p, uint32_t tme
           for (int j = 0; j < 32; ++j) acc[chunk * 32 + j] += __uint_as_float(r[j]);
         }
         tc_fence_before();
-        mbar_arrive(&tmem_empty[as]);
+        if (PAIR) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive_leader(&tmem_empty[as]);
+        } else {
+          mbar_arrive(&tmem_empty[as]);
+        }
         if (++as == NUM_ACC) { as = 0; aphase ^= 1; }
       }
 #pragma unroll

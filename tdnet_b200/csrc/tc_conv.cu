@@ -246,6 +246,7 @@ static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUt
 }
 
 int conv2d_tc_halo(const tdn_tc_conv_desc* d, TcParams p, int num_sms, int chunk_kb, cudaStream_t stream);
+int conv2d_tc_pair(const tdn_tc_conv_desc* d, TcParams p, int block_n, int num_sms, cudaStream_t stream);
 
 int conv2d_tc(const tdn_tc_conv_desc* d, cudaStream_t stream) {
   const tdn_tensor& in = d->in;
@@ -341,19 +342,33 @@ int conv2d_tc(const tdn_tc_conv_desc* d, cudaStream_t stream) {
   p.range_flag = d->range_flag;
 
   {
-    // 3x3 / stride 1 / dilation <= 2: one halo-region load per channel block instead of nine tap loads.
-    // Measured on B200 (profiles/r01_tc_probe_stem_halo.txt): the region variant wins where the per-tap kernel
-    // is L2->SM bound with two channel blocks (layer 2: 128 -> 128, 0.048 -> 0.039 ms) and loses on layer 1
-    // (64 -> 64: one block per tile, its 16-byte-row TMA boxes cost more than they save) and on layer 3
-    // (dilation 2 regions are 2x the tile).  TDNET_TC_HALO = 0 / 1 forces it off / on wherever it applies.
-    static int halo = -2;
-    if (halo == -2) {
-      const char* e = getenv("TDNET_TC_HALO");
-      halo = e ? atoi(e) : -1;
+    // Kernel choice.  d->variant forces one (tests / tuning); otherwise:
+    //  * CTA pairs (tc_conv_pair.cu) for wide layers: M 256 x N 256 tiles over two SMs halve the shared-memory
+    //    traffic per MMA, which is what bounds the single-CTA kernel.  TDNET_TC_PAIR = 0 / 1 forces off / on.
+    //  * halo regions (tc_conv_halo.cu) for 3x3 / stride 1 / dilation <= 2: one region load per channel block
+    //    instead of nine tap loads.  Measured on B200 (profiles/r01_tc_probe_stem_halo.txt): wins where the
+    //    per-tap kernel is L2->SM bound with two channel blocks (layer 2: 128 -> 128, 0.048 -> 0.039 ms), loses
+    //    on layer 1 (64 -> 64: one block per tile, its 16-byte-row TMA boxes cost more than they save) and on
+    //    layer 3 (dilation-2 regions are 2x the tile).  TDNET_TC_HALO = 0 / 1 forces it off / on.
+    static int pair_env = -2, halo_env = -2;
+    if (pair_env == -2) {
+      const char* e = getenv("TDNET_TC_PAIR");
+      pair_env = e ? atoi(e) : 0;
+      e = getenv("TDNET_TC_HALO");
+      halo_env = e ? atoi(e) : -1;
     }
+    const bool pair_ok = !d->weight_batched && d->cout % 128 == 0;
     const bool halo_ok = d->kh == 3 && d->kw == 3 && cs == 1 && d->dilation <= 2 && !d->weight_batched && in.w >= 8;
-    const bool halo_auto = d->dilation == 1 && in.c == 128 && d->cout <= 128;
-    if (halo_ok && (halo > 0 || (halo < 0 && halo_auto)))
+    TDN_REQUIRE(d->variant >= TDN_TC_AUTO && d->variant <= TDN_TC_PAIR, TDN_ERR_INVALID, "conv2d_tc: unknown variant");
+    TDN_REQUIRE(d->variant != TDN_TC_PAIR || pair_ok, TDN_ERR_UNSUPPORTED,
+                "conv2d_tc: the CTA-pair kernel needs cout %% 128 == 0 and shared weights");
+    TDN_REQUIRE(d->variant != TDN_TC_HALO || halo_ok, TDN_ERR_UNSUPPORTED,
+                "conv2d_tc: the halo kernel needs a 3x3 stride-1 convolution with dilation <= 2");
+    const bool pair_auto = pair_env > 0 && d->cout % 256 == 0;
+    if (d->variant == TDN_TC_PAIR || (d->variant == TDN_TC_AUTO && pair_ok && pair_auto))
+      return conv2d_tc_pair(d, p, d->cout % 256 == 0 ? 256 : 128, g_num_sms, stream);
+    const bool halo_auto = halo_env > 0 || (halo_env < 0 && d->dilation == 1 && in.c == 128 && d->cout <= 128);
+    if (d->variant == TDN_TC_HALO || (d->variant == TDN_TC_AUTO && halo_ok && halo_auto))
       return conv2d_tc_halo(d, p, g_num_sms, p.chunk_kb, stream);
   }
 

@@ -1,0 +1,246 @@
+// tcgen05 implicit-GEMM convolution on CTA PAIRS (cta_group::2): the wide-N variant of tc_conv.cu.
+//
+// Why: tc_conv_kernel<128> is bound by SHARED-MEMORY bandwidth, not by the tensor pipe.  Per K block
+// (64 channels of one tap) a CTA writes 64 KB (TMA: A hi/lo + B hi/lo) and the twelve exact-mode MMAs read
+// 12 x (4 KB A + 4 KB B) = 96 KB, i.e. 160 KB per 768 MMA cycles = 208 B/clk against the SM's 128 B/clk
+// (ncu on the layer-4 conv: 79.7 MB of shared-memory traffic per SM / 128 B/clk = 622 k cycles of the 627 k
+// elapsed; tensor pipe ~50 % active).  Here two CTAs of a cluster share one M = 256 x N = 256 tile:
+//   * each CTA stages its own 128 pixel rows of A and only HALF of the B rows (the tensor cores of the pair
+//     exchange the halves over the SM-to-SM fabric), and one tcgen05.mma.cta_group::2 drives both SMs;
+//   * per CTA and K block: 64 KB written + 12 x (4 KB A + 4 KB half-B) = 96 KB read for 1536 MMA cycles
+//     = 104 B/clk -- under the shared-memory limit, so the kernel becomes MMA-bound.
+// Protocol (both CTAs run every role; only the leader = even CTA issues MMAs):
+//   warp 0  TMA producer: own A box + own half of B per stage; every load signals the LEADER's `full` barrier
+//           (the leader expects the bytes of both CTAs); waits on its own `empty` barrier.
+//   warp 1  leader: waits `full`, issues 12 MMAs (M256 x N x K16), commits with a 2-CTA multicast to the
+//           `empty` barriers of both CTAs and, per finished chunk, to both `tmem_full` barriers.
+//   warps 2-9  epilogue on the CTA's own TMEM half (rows of its M tile), same chunked fp32 register
+//           accumulation / fused scale-bias-residual-activation-split store as tc_conv.cu; a drained
+//           accumulator is released on the leader's `tmem_empty` barrier (one arrival per warp).
+// Arithmetic is identical to tc_conv.cu (same products, same chunking), so results are bit-identical to it.
+#include "tc_common.cuh"
+
+#include <stdlib.h>
+#include <string.h>
+#include <cuda.h>
+
+namespace tdn {
+
+template <int BLOCK_N>
+struct PairCfg {
+  static constexpr int B_HALF_PLANE = (BLOCK_N / 2) * TC_BLOCK_K * 2;          // this CTA's B rows, one plane
+  static constexpr int STAGE_BYTES = 2 * TC_A_PLANE + 2 * B_HALF_PLANE;        // 64 KiB (N=256) / 48 KiB (N=128)
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;                    // 3 / 4
+  static constexpr int NUM_ACC = 512 / BLOCK_N;                                // chunk accumulators in TMEM
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 512;
+};
+
+template <int BLOCK_N>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+tc_conv_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                    const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                    const TcParams p) {
+  using Cfg = PairCfg<BLOCK_N>;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int NUM_ACC = Cfg::NUM_ACC;
+  extern __shared__ uint8_t smem_raw[];
+  // identical layout in both CTAs: descriptors and barrier offsets are shared by the pair
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + NUM_ACC;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + NUM_ACC);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int rank = (int)(blockIdx.x & 1);            // == %cluster_ctarank for cluster dims (2,1,1)
+  const bool leader = rank == 0;
+  const int cluster_id = (int)(blockIdx.x >> 1);
+  const int num_clusters = (int)(gridDim.x >> 1);
+  const int kc_per_tap = p.Cin / TC_BLOCK_K;
+  const int num_kb = p.taps_h * p.taps_w * kc_per_tap;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmA_hi);
+    prefetch_tensormap(&tmA_lo);
+    prefetch_tensormap(&tmB_hi);
+    prefetch_tensormap(&tmB_lo);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);                    // used on the leader only: its producer's expect_tx arrival
+      mbar_init(&empty_bar[s], 1);                   // multicast commit of the leader's MMA thread
+    }
+    for (int s = 0; s < NUM_ACC; ++s) {
+      mbar_init(&tmem_full[s], 1);                   // multicast commit
+      mbar_init(&tmem_empty[s], 2 * TC_EPI_WARPS);   // leader only: one arrival per epilogue warp of both CTAs
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_pair(tmem_ptr, Cfg::TMEM_COLS);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                // the peer's barriers exist before anything signals them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ======================= TMA producer (both CTAs) =======================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
+        const int nt = tile % p.n_tiles_n;
+        int mt = 2 * (tile / p.n_tiles_n) + rank;    // this CTA's 128-pixel M tile (may lie past the last image:
+        const int tx = mt % p.tiles_w;               //  TMA then zero-fills and the epilogue stores nothing)
+        mt /= p.tiles_w;
+        const int ty = mt % p.tiles_h;
+        const int img = mt / p.tiles_h;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int tap = kb / kc_per_tap;
+          const int kc = kb - tap * kc_per_tap;
+          const int ky = tap / p.taps_w;
+          const int kx = tap - ky * p.taps_w;
+          const int x0 = tx * p.BW * p.conv_stride + (kx - (p.taps_w - 1) / 2) * p.dil;
+          const int y0 = ty * p.BH * p.conv_stride + (ky - (p.taps_h - 1) / 2) * p.dil;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + 2 * TC_A_PLANE;
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+          tma_load_4d_pair(sa, &tmA_hi, &full_bar[stage], kc * TC_BLOCK_K, x0, y0, img);
+          tma_load_4d_pair(sa + TC_A_PLANE, &tmA_lo, &full_bar[stage], kc * TC_BLOCK_K, x0, y0, img);
+          const int kcol = tap * p.Cin + kc * TC_BLOCK_K;
+          const int brow = nt * BLOCK_N + rank * (BLOCK_N / 2);
+          tma_load_3d_pair(sb, &tmB_hi, &full_bar[stage], kcol, brow, 0);
+          tma_load_3d_pair(sb + Cfg::B_HALF_PLANE, &tmB_lo, &full_bar[stage], kcol, brow, 0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer (leader CTA only) =======================
+    if (leader) {
+      constexpr uint32_t idesc = umma_idesc_f16(2 * TC_BLOCK_M, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
+        for (int kb0 = 0; kb0 < num_kb; kb0 += p.chunk_kb) {
+          const int kb1 = min(kb0 + p.chunk_kb, num_kb);
+          mbar_wait(&tmem_empty[as], aphase ^ 1);
+          const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+            const uint32_t sb = sa + 2 * TC_A_PLANE;
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < TC_BLOCK_K / 16; ++k) {
+                const uint64_t a_hi = umma_desc_k_sw128(sa + k * 32);
+                const uint64_t a_lo = umma_desc_k_sw128(sa + TC_A_PLANE + k * 32);
+                const uint64_t b_hi = umma_desc_k_sw128(sb + k * 32);
+                const uint64_t b_lo = umma_desc_k_sw128(sb + Cfg::B_HALF_PLANE + k * 32);
+                umma_f16_pair(d_tmem, a_hi, b_lo, idesc, ((kb - kb0) | k) != 0);
+                umma_f16_pair(d_tmem, a_lo, b_hi, idesc, 1);
+                umma_f16_pair(d_tmem, a_hi, b_hi, idesc, 1);
+              }
+              umma_commit_pair(&empty_bar[stage], 3);
+              if (kb == kb1 - 1) umma_commit_pair(&tmem_full[as], 3);
+            }
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          if (++as == NUM_ACC) { as = 0; aphase ^= 1; }
+        }
+      }
+    }
+  } else {
+    tc_epilogue_role<BLOCK_N, NUM_ACC, true>(p, tmem_base, tmem_full, tmem_empty, warp, lane, num_kb);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                // nobody leaves (or frees TMEM) while the peer still works
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+int encode_map_f16(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                   const cuuint32_t* box, const char* what, const cuuint32_t* elem_strides, int swizzle128 = 1);
+
+template <int BLOCK_N>
+static int launch_pair(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
+                       const TcParams& p, int num_sms, cudaStream_t stream) {
+  using Cfg = PairCfg<BLOCK_N>;
+  static int max_clusters = 0;
+  if (max_clusters == 0) {
+    TDN_CUDA_OK(cudaFuncSetAttribute(tc_conv_pair_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     Cfg::SMEM_BYTES));
+    // how many 2-CTA clusters the device can keep resident (GPCs with an odd number of usable SMs leave one
+    // unpaired): a persistent kernel must not launch more, or the surplus runs as a second wave
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(num_sms & ~1, 1, 1);
+    cfg.blockDim = dim3(TC_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, tc_conv_pair_kernel<BLOCK_N>, &cfg) != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      n = num_sms / 2;
+    }
+    max_clusters = n < num_sms / 2 ? n : num_sms / 2;
+  }
+  const int clusters = p.num_tiles < max_clusters ? p.num_tiles : max_clusters;
+  tc_conv_pair_kernel<BLOCK_N><<<2 * clusters, TC_THREADS, Cfg::SMEM_BYTES, stream>>>(a_hi, a_lo, b_hi, b_lo, p);
+  TDN_LAUNCH_OK();
+  return TDN_OK;
+}
+
+// Called by conv2d_tc() with the epilogue / output / residual fields of `p` filled in and the 128-pixel tile
+// shape chosen; re-tiles into pair tiles of 2 x 128 pixels x block_n output channels.
+int conv2d_tc_pair(const tdn_tc_conv_desc* d, TcParams p, int block_n, int num_sms, cudaStream_t stream) {
+  const tdn_tensor& in = d->in;
+  const int cs = p.conv_stride;
+  const int taps = d->kh * d->kw;
+  TDN_REQUIRE(!d->weight_batched, TDN_ERR_UNSUPPORTED, "conv2d_tc_pair: per-image weights are not supported");
+  p.n_tiles_n = ceil_div(d->cout, block_n);
+  const long long m_tiles = (long long)in.n * p.tiles_h * p.tiles_w;
+  const long long num_tiles = ((m_tiles + 1) / 2) * p.n_tiles_n;
+  TDN_REQUIRE(num_tiles < (1ll << 30), TDN_ERR_UNSUPPORTED, "conv2d_tc_pair: too many tiles");
+  p.num_tiles = (int)num_tiles;
+
+  CUtensorMap a_hi, a_lo, b_hi, b_lo;
+  int rc;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)in.c, (cuuint64_t)in.w, (cuuint64_t)in.h, (cuuint64_t)in.n};
+    cuuint64_t str[3] = {(cuuint64_t)in.stride_w * 2, (cuuint64_t)in.stride_h * 2, (cuuint64_t)in.stride_n * 2};
+    cuuint32_t box[4] = {(cuuint32_t)TC_BLOCK_K, (cuuint32_t)(p.BW * cs), (cuuint32_t)(p.BH * cs), 1};
+    cuuint32_t est[4] = {1, (cuuint32_t)cs, (cuuint32_t)cs, 1};
+    if ((rc = encode_map_f16(&a_hi, in.data, 4, dims, str, box, "A.hi(pair)", est, 1))) return rc;
+    if ((rc = encode_map_f16(&a_lo, in.data_lo, 4, dims, str, box, "A.lo(pair)", est, 1))) return rc;
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)taps * in.c, (cuuint64_t)d->cout, 1};
+    cuuint64_t str[2] = {(cuuint64_t)d->weight_ld * 2, (cuuint64_t)d->weight_ld * 2 * (cuuint64_t)d->cout};
+    cuuint32_t box[3] = {(cuuint32_t)TC_BLOCK_K, (cuuint32_t)(block_n / 2), 1};   // each CTA loads half of the rows
+    if ((rc = encode_map_f16(&b_hi, d->weight_hi, 3, dims, str, box, "B.hi(pair)", nullptr, 1))) return rc;
+    if ((rc = encode_map_f16(&b_lo, d->weight_lo, 3, dims, str, box, "B.lo(pair)", nullptr, 1))) return rc;
+  }
+  if (block_n == 256) return launch_pair<256>(a_hi, a_lo, b_hi, b_lo, p, num_sms, stream);
+  return launch_pair<128>(a_hi, a_lo, b_hi, b_lo, p, num_sms, stream);
+}
+
+}  // namespace tdn

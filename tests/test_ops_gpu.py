@@ -334,6 +334,78 @@ def test_tc_conv_exact_mode(env, n, h, w, cin, cout, k, dil):
     assert err < 2e-6 * max(1.0, float(ref.abs().max())), err
 
 
+PAIR_CASES = [
+    # n, h, w, cin, cout, k, dil, stride      (cout % 128 == 0: N = 256 pair tiles when cout % 256 == 0, else 128)
+    (1, 1, 512, 64, 256, 1, 1, 1),       # plain GEMM: 4 M tiles = 2 pair tiles, one K block
+    (1, 1, 1000, 512, 256, 1, 1, 1),     # ragged M (8 M tiles), 8 K blocks: the stage ring and the chunk ring wrap
+    (1, 1, 640, 128, 512, 1, 1, 1),      # 5 M tiles (odd: the last pair has an empty half), two N tiles
+    (2, 24, 40, 64, 256, 3, 2, 1),       # 3x3 dilated, batch 2, zero padding through TMA
+    (1, 97, 193, 128, 256, 3, 4, 1),     # reference-native ragged map, 18 K blocks
+    (1, 33, 47, 64, 128, 3, 1, 1),       # N = 128 pair tiles
+    (1, 40, 56, 64, 256, 3, 1, 2),       # stride 2 (TMA element strides)
+    (3, 16, 8, 192, 384, 1, 1, 1),       # cout = 384: N = 128 tiles x 3, 3 K blocks, batch 3 (3 M tiles)
+]
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,k,dil,stride", PAIR_CASES)
+def test_tc_conv_pair_variant_is_bit_identical(env, n, h, w, cin, cout, k, dil, stride):
+    """tc_conv_pair_kernel (2-CTA clusters, tcgen05 cta_group::2) against the single-CTA kernel: the same products
+    in the same order, so the SPLIT16 planes must be bit-identical -- with BN / residual / ReLU epilogue -- and both
+    within fp32 rounding of an fp64 convolution."""
+    lib, cabi, View, dev = env
+    g = torch.Generator().manual_seed(n * h + w + cin + cout + k)
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5
+    sc, bi = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.2
+    ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
+    res = torch.randn(n, cout, ho, wo, generator=g)
+    xs = View.alloc(n, h, w, cin, dev, split=True)
+    hi, lo = split_planes(nhwc(x))
+    xs.base.copy_(hi.view(-1)); xs.lo.copy_(lo.view(-1))
+    rs = View.alloc(n, ho, wo, cout, dev, split=True)
+    hi, lo = split_planes(nhwc(res))
+    rs.base.copy_(hi.view(-1)); rs.lo.copy_(lo.view(-1))
+    wh, wl = split_planes(wt.permute(0, 2, 3, 1).reshape(cout, -1).cuda())
+    scd, bid = sc.cuda(), bi.cuda()
+    outs = {}
+    for variant in (cabi.TC_BASE, cabi.TC_PAIR):
+        out = View.alloc(n, ho, wo, cout, dev, split=True)
+        out.base.fill_(float("nan")); out.lo.fill_(float("nan"))
+        d = cabi.TcConvDesc()
+        d.in_, d.out, d.residual = xs.ct(), out.ct(), rs.ct()
+        d.weight_hi, d.weight_lo, d.weight_ld = wh.data_ptr(), wl.data_ptr(), k * k * cin
+        d.scale, d.bias = scd.data_ptr(), bid.data_ptr()
+        d.cout, d.kh, d.kw, d.dilation, d.stride, d.act = cout, k, k, dil, stride, 1
+        d.variant = variant
+        cabi.check(lib.tdn_conv2d_tc(C.byref(d), None), "conv2d_tc")
+        torch.cuda.synchronize()
+        outs[variant] = (out.base.clone(), out.lo.clone(), out.torch().permute(0, 3, 1, 2).cpu())
+    base, pair = outs[cabi.TC_BASE], outs[cabi.TC_PAIR]
+    xr = (rs.base.float() + rs.lo.float()).view(n, ho, wo, cout).permute(0, 3, 1, 2).cpu().double()
+    ref = F.relu(F.conv2d(x.double(), wt.double(), None, stride, dil * (k - 1) // 2, dil)
+                 * sc.double().view(1, -1, 1, 1) + bi.double().view(1, -1, 1, 1) + xr)
+    assert max_abs(pair[2], ref) < 3e-6 * max(1.0, float(ref.abs().max()))
+    assert torch.equal(base[0].view(torch.int16), pair[0].view(torch.int16))
+    assert torch.equal(base[1].view(torch.int16), pair[1].view(torch.int16))
+
+
+def test_tc_conv_variant_errors(env):
+    lib, cabi, View, dev = env
+    xs = View.alloc(1, 8, 16, 64, dev, split=True)
+    out = View.alloc(1, 8, 16, 40, dev, split=True)
+    w = torch.zeros(40 * 64, dtype=torch.half, device=dev)
+    d = cabi.TcConvDesc()
+    d.in_, d.out = xs.ct(), out.ct()
+    d.weight_hi, d.weight_lo, d.weight_ld = w.data_ptr(), w.data_ptr(), 64
+    d.cout, d.kh, d.kw, d.dilation = 40, 1, 1, 1
+    d.variant = cabi.TC_PAIR                    # cout % 128 != 0
+    assert lib.tdn_conv2d_tc(C.byref(d), None) == -2
+    d.variant = cabi.TC_HALO                    # not a 3x3 convolution
+    assert lib.tdn_conv2d_tc(C.byref(d), None) == -2
+    d.variant = 9
+    assert lib.tdn_conv2d_tc(C.byref(d), None) == -1
+
+
 def test_tc_conv_epilogue_and_batched_weights(env):
     lib, cabi, View, dev = env
     g = torch.Generator().manual_seed(31)

@@ -167,6 +167,22 @@ def experiment(name):
         flop = 2 * 128 * 256 * 512 * 512 * 9
         st.update(ms=ms, algorithmic_tflops=flop / ms / 1e9, executed_tflops=3 * flop / ms / 1e9)
         return st
+    if name == "wvs_perf":
+        # Encoding.w_vs / Attention.fc shape: 1x1 512 -> 512 on the 128x256 map (8 K blocks per tile)
+        x = torch.randn(1, 128, 256, 512, device=dev)
+        w = torch.randn(512, 1, 1, 512, device=dev) / 22
+        out, ms, _ = run_tc(x, w, reps=10)
+        st = stats(out, ref_conv(x, w))
+        st.update(ms=ms, algorithmic_tflops=2 * 128 * 256 * 512 * 512 / ms / 1e9)
+        return st
+    if name == "head_perf":
+        # FCNHead conv5.0: 3x3 512 -> 128 on the 128x256 map
+        x = torch.randn(1, 128, 256, 512, device=dev)
+        w = torch.randn(128, 3, 3, 512, device=dev) / 68
+        out, ms, _ = run_tc(x, w, reps=10)
+        st = stats(out, ref_conv(x, w))
+        st.update(ms=ms, algorithmic_tflops=2 * 128 * 256 * 512 * 128 * 9 / ms / 1e9)
+        return st
     if name == "layer4_sustained":
         # same conv, 300 launches back to back over 4 rotating input/output sets (268 MB each > L2 share):
         # separates the power/clock and L2-residency effects from the single-launch number
@@ -355,6 +371,10 @@ _HALO_SWEEP = [("halo_ragged", {"TDNET_TC_HALO": "1"}), ("halo_epilogue", {"TDNE
              ("layer2_perf", {"TDNET_TC_HALO": "1"}), ("layer3_perf", {"TDNET_TC_HALO": "0"}),
              ("layer3_perf", {"TDNET_TC_HALO": "1"})]
 
+_PAIR_SWEEP = [(n, {"TDNET_TC_PAIR": v}) for n in ("layer4_perf", "layer3_perf", "wvs_perf")
+               for v in ("0", "1")] + [("head_perf", {"TDNET_TC_PAIR": "0"}), ("head_perf", {"TDNET_TC_PAIR": "2"}),
+                                       ("layer2_perf", {"TDNET_TC_PAIR": "2", "TDNET_TC_HALO": "0"})]
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "--one":
         print("RESULT " + json.dumps(experiment(sys.argv[2])))
@@ -362,7 +382,11 @@ if __name__ == "__main__":
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     lines = []
     sweep = _HALO_SWEEP if os.environ.get("TDNET_PROBE_HALO_SWEEP") else ENV_SWEEP
+    if os.environ.get("TDNET_PROBE_PAIR_SWEEP"):
+        sweep = _PAIR_SWEEP
     todo = [(n, None) for n in (sys.argv[1:] or EXPERIMENTS)] + ([] if sys.argv[1:] else CHUNK_SWEEP + sweep)
+    if os.environ.get("TDNET_PROBE_PAIR_SWEEP"):
+        todo = list(_PAIR_SWEEP)
     for name, chunk in todo:
         t0 = time.time()
         env = dict(os.environ)
