@@ -353,7 +353,7 @@ int conv2d_tc(const tdn_tc_conv_desc* d, cudaStream_t stream) {
     static int pair_env = -2, halo_env = -2;
     if (pair_env == -2) {
       const char* e = getenv("TDNET_TC_PAIR");
-      pair_env = e ? atoi(e) : 0;
+      pair_env = e ? atoi(e) : -1;
       e = getenv("TDNET_TC_HALO");
       halo_env = e ? atoi(e) : -1;
     }
@@ -364,7 +364,10 @@ int conv2d_tc(const tdn_tc_conv_desc* d, cudaStream_t stream) {
                 "conv2d_tc: the CTA-pair kernel needs cout %% 128 == 0 and shared weights");
     TDN_REQUIRE(d->variant != TDN_TC_HALO || halo_ok, TDN_ERR_UNSUPPORTED,
                 "conv2d_tc: the halo kernel needs a 3x3 stride-1 convolution with dilation <= 2");
-    const bool pair_auto = pair_env > 0 && d->cout % 256 == 0;
+    // measured (profiles/r01_tc_probe_pair.txt): layer 4 0.342 -> 0.308 ms, layer 3 0.106 -> 0.092 ms; the 1x1
+    // 512 -> 512 GEMMs with only 8 K blocks per tile lose 8 % (fewer, longer tiles: 3.5 waves -> 4), N = 128
+    // pair tiles are a wash
+    const bool pair_auto = d->cout % 256 == 0 && (pair_env > 0 || (pair_env < 0 && num_kb_host >= 16));
     if (d->variant == TDN_TC_PAIR || (d->variant == TDN_TC_AUTO && pair_ok && pair_auto))
       return conv2d_tc_pair(d, p, d->cout % 256 == 0 ? 256 : 128, g_num_sms, stream);
     const bool halo_auto = halo_env > 0 || (halo_env < 0 && d->dilation == 1 && in.c == 128 && d->cout <= 128);
