@@ -38,11 +38,13 @@ using namespace ptx;
 
 constexpr int AT_BQ = 128;       // queries per item
 constexpr int AT_BK = 64;        // keys per tile (= one 128-byte swizzle row of fp16)
+constexpr int AT_BK1 = 128;      // keys per PASS-1 tile (hi planes only: two 64-key boxes fill one K stage)
 constexpr int AT_DK = 64;        // d_k (fixed by the model: Encoding(d_model, 64, d_v))
 constexpr int AT_DVH = 128;      // V'^T rows per shared-memory stage / per PV MMA (N = 128)
 constexpr int AT_THREADS = 352;  // warp 0 TMA, warp 1 S-MMA issuer, warps 2-9 softmax + epilogue, warp 10 PV-MMA issuer
 constexpr int AT_PV_WARP = 10;
 constexpr int AT_SOFTMAX_THREADS = 256;
+constexpr int AT_SOFTMAX_WARPS = AT_SOFTMAX_THREADS / 32;
 constexpr int AT_Q_PLANE = AT_BQ * AT_DK * 2;   // 16 KB
 constexpr int AT_K_PLANE = AT_BK * AT_DK * 2;   // 8 KB
 constexpr int AT_V_PLANE = AT_DVH * AT_BK * 2;  // 16 KB
@@ -62,7 +64,7 @@ __device__ __forceinline__ float fast_exp2(float x) {
 
 struct AttnParams {
   int n_img, Pq, Pk;
-  int q_tiles, dv_tiles, k_tiles, num_items;
+  int q_tiles, dv_tiles, k_tiles, k_tiles1, num_items;   // k_tiles: 64-key tiles (pass 2); k_tiles1: 128-key tiles (pass 1)
   float scale_log2;         // log2(e) / sqrt(d_k)
   __half* out_hi;
   __half* out_lo;
@@ -116,12 +118,12 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant
     for (int s = 0; s < AT_VSTAGES; ++s) { mbar_init(&bars->v_full[s], 1); mbar_init(&bars->v_empty[s], 1); }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&bars->s_full[s], 1);
-      mbar_init(&bars->s_empty[s], AT_SOFTMAX_THREADS);
-      mbar_init(&bars->p_full[s], AT_SOFTMAX_THREADS);
+      mbar_init(&bars->s_empty[s], AT_SOFTMAX_WARPS);   // one arrival per softmax warp (lane 0 after __syncwarp):
+      mbar_init(&bars->p_full[s], AT_SOFTMAX_WARPS);    // 8 instead of 256 serialised shared-memory atomics per tile
       mbar_init(&bars->p_empty[s], 1);
     }
     mbar_init(&bars->o_full, 1);
-    mbar_init(&bars->o_empty, AT_SOFTMAX_THREADS);
+    mbar_init(&bars->o_empty, AT_SOFTMAX_WARPS);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -135,6 +137,7 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant
   const uint32_t tmem_S = tmem_base;            // + buf * 64
   const uint32_t tmem_O = tmem_base + 128;
   const int T = p.k_tiles;
+  const int T1 = p.k_tiles1;
   constexpr int HALVES = DVT / AT_DVH;
 
   if (warp == 0) {
@@ -152,12 +155,14 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant
         tma_load_3d(sQ, &tmQ_hi, &bars->q_full, 0, qt * AT_BQ, img);
         tma_load_3d(sQ + AT_Q_PLANE, &tmQ_lo, &bars->q_full, 0, qt * AT_BQ, img);
         qph ^= 1;
-        // pass 1: the hi plane of the keys only (S~ = Qhi.Khi^T)
-        for (int kt = 0; kt < T; ++kt) {
+        // pass 1: the hi plane of the keys only (S~ = Qhi.Khi^T), 128 keys per stage: two 64-key boxes land
+        // back to back = one 128-row swizzled tile (a box past the last key is zero-filled)
+        for (int kt = 0; kt < T1; ++kt) {
           mbar_wait(&bars->k_empty[ks], kph ^ 1);
           uint8_t* dst = sK + ks * 2 * AT_K_PLANE;
-          mbar_expect_tx(&bars->k_full[ks], AT_K_PLANE);
-          tma_load_3d(dst, &tmK_hi, &bars->k_full[ks], 0, kt * AT_BK, img);
+          mbar_expect_tx(&bars->k_full[ks], 2 * AT_K_PLANE);
+          tma_load_3d(dst, &tmK_hi, &bars->k_full[ks], 0, kt * AT_BK1, img);
+          tma_load_3d(dst + AT_K_PLANE, &tmK_hi, &bars->k_full[ks], 0, kt * AT_BK1 + AT_BK, img);
           if (++ks == AT_KSTAGES) { ks = 0; kph ^= 1; }
         }
         // pass 2: keys (hi+lo) and the V'^T slice (hi+lo).  The key tile is fetched ONE TILE AHEAD of the
@@ -189,16 +194,41 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant
     // ================================ MMA issuer 1: S = Q.K^T (both passes) ================================
     // The whole warp runs the loop and the barrier waits so that stage indices, phases and descriptors
     // stay warp-uniform (uniform registers feed tcgen05.mma directly); one elected lane issues.
-    constexpr uint32_t idesc_s = umma_idesc_f16(AT_BQ, AT_BK);   // 128 x 64
-    int ks = 0, sb = 0;
-    uint32_t kph = 0, sph = 0, qph = 0;
+    constexpr uint32_t idesc_s = umma_idesc_f16(AT_BQ, AT_BK);    // 128 x 64  (pass 2)
+    constexpr uint32_t idesc_s1 = umma_idesc_f16(AT_BQ, AT_BK1);  // 128 x 128 (pass 1)
+    int ks = 0;
+    uint32_t kph = 0, qph = 0, oph = 0;
+    uint32_t sn = 0;                                             // S tiles issued so far: buffer sn & 1, phase (sn >> 1) & 1
     const uint32_t q_hi = smem_u32(sQ), q_lo = q_hi + AT_Q_PLANE;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       mbar_wait(&bars->q_full, qph);
-      for (int it = 0; it < 2 * T; ++it) {
-        const bool exact = it >= T;                              // pass 1: hi x hi only
+      // Pass-1 tiles are 128 keys wide: buffer 0 = the S columns, buffer 1 = the first 128 O columns, which are
+      // idle until P.V starts -- once the epilogue of the previous item has read them.
+      mbar_wait(&bars->o_empty, oph ^ 1);
+      for (int it = 0; it < T1; ++it, ++sn) {
+        const int sb = sn & 1;
         mbar_wait(&bars->k_full[ks], kph);
-        mbar_wait(&bars->s_empty[sb], sph ^ 1);
+        mbar_wait(&bars->s_empty[sb], ((sn >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t k_hi = smem_u32(sK + ks * 2 * AT_K_PLANE);
+        const uint32_t d = sb ? tmem_O : tmem_S;
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < AT_DK / 16; ++k)
+            umma_f16(d, umma_desc_k_sw128(q_hi + k * 32), umma_desc_k_sw128(k_hi + k * 32), idesc_s1, k != 0);
+          umma_commit(&bars->s_full[sb]);
+          umma_commit(&bars->k_empty[ks]);
+        }
+        __syncwarp();
+        if (++ks == AT_KSTAGES) { ks = 0; kph ^= 1; }
+      }
+      // pass 2 re-uses the S columns as two 64-column buffers: the last pass-1 tile must have been read (the one
+      // before it is covered by the regular s_empty wait of the first pass-2 tile)
+      if (T1 > 0) mbar_wait(&bars->s_empty[(sn - 1) & 1], ((sn - 1) >> 1) & 1);
+      for (int it = 0; it < T; ++it, ++sn) {
+        const int sb = sn & 1;
+        mbar_wait(&bars->k_full[ks], kph);
+        mbar_wait(&bars->s_empty[sb], ((sn >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t k_hi = smem_u32(sK + ks * 2 * AT_K_PLANE), k_lo = k_hi + AT_K_PLANE;
         const uint32_t d = tmem_S + sb * AT_BK;
@@ -206,24 +236,20 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant
 #pragma unroll
           for (int k = 0; k < AT_DK / 16; ++k) {
             const uint64_t a_h = umma_desc_k_sw128(q_hi + k * 32), b_h = umma_desc_k_sw128(k_hi + k * 32);
-            if (exact) {
-              const uint64_t a_l = umma_desc_k_sw128(q_lo + k * 32), b_l = umma_desc_k_sw128(k_lo + k * 32);
-              umma_f16(d, a_h, b_l, idesc_s, k != 0);
-              umma_f16(d, a_l, b_h, idesc_s, 1);
-              umma_f16(d, a_h, b_h, idesc_s, 1);
-            } else {
-              umma_f16(d, a_h, b_h, idesc_s, k != 0);
-            }
+            const uint64_t a_l = umma_desc_k_sw128(q_lo + k * 32), b_l = umma_desc_k_sw128(k_lo + k * 32);
+            umma_f16(d, a_h, b_l, idesc_s, k != 0);
+            umma_f16(d, a_l, b_h, idesc_s, 1);
+            umma_f16(d, a_h, b_h, idesc_s, 1);
           }
           umma_commit(&bars->s_full[sb]);
           umma_commit(&bars->k_empty[ks]);
-          if (it == 2 * T - 1) umma_commit(&bars->q_empty);      // Q tile free once the last S has retired
+          if (it == T - 1) umma_commit(&bars->q_empty);            // Q tile free once the last S has retired
         }
         __syncwarp();
         if (++ks == AT_KSTAGES) { ks = 0; kph ^= 1; }
-        if (++sb == 2) { sb = 0; sph ^= 1; }
       }
       qph ^= 1;
+      oph ^= 1;
     }
   } else if (warp == AT_PV_WARP) {
     // ================================ MMA issuer 2: O += P.V'^T ================================
@@ -271,8 +297,9 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant
     const int group = (warp - 2) >> 2;
     const int row = quarter * 32 + lane;                      // query row inside the tile = TMEM lane
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-    int sb = 0, pb = 0;
-    uint32_t sph = 0, pph = 0, oph = 0;
+    int pb = 0;
+    uint32_t pph = 0, oph = 0;
+    uint32_t sn = 0;                                            // S tiles consumed so far (same counting as MMA issuer 1)
     bool out_of_range = false;
     auto group_sync = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
@@ -283,32 +310,51 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant
       const int q_idx = qt * AT_BQ + row;
       const bool valid = q_idx < p.Pq;
 
-      // ---- pass 1: row maximum of S~ (this group's 32 key columns per tile)
+      // ---- pass 1: row maximum of S~; 128-key tiles, this group's 64 key columns of each
       float m = -INFINITY;
-      for (int kt = 0; kt < T; ++kt) {
-        mbar_wait(&bars->s_full[sb], sph);
+      for (int kt = 0; kt < T1; ++kt, ++sn) {
+        const int sb = sn & 1;
+        mbar_wait(&bars->s_full[sb], (sn >> 1) & 1);
         tc_fence_after();
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_S + lane_addr + sb * AT_BK + group * 32, r);
+        uint32_t r0[32], r1[32];
+        const uint32_t src = (sb ? tmem_O : tmem_S) + lane_addr + group * 64;
+        tmem_ld_32x32(src, r0);
+        tmem_ld_32x32(src + 32, r1);
         tmem_ld_wait();
-        const int kbase = kt * AT_BK + group * 32;
+        const int kbase = kt * AT_BK1 + group * 64;
+        if (kbase + 64 <= p.Pk) {                               // only the last key tile can be ragged
+          float m0 = m, m1 = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (kbase + j < p.Pk) m = fmaxf(m, __uint_as_float(r[j]));
+          for (int j = 0; j < 32; ++j) {
+            m0 = fmaxf(m0, __uint_as_float(r0[j]));
+            m1 = fmaxf(m1, __uint_as_float(r1[j]));
+          }
+          m = fmaxf(m0, m1);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (kbase + j < p.Pk) m = fmaxf(m, __uint_as_float(r0[j]));
+            if (kbase + 32 + j < p.Pk) m = fmaxf(m, __uint_as_float(r1[j]));
+          }
+        }
         tc_fence_before();
-        mbar_arrive(&bars->s_empty[sb]);
-        if (++sb == 2) { sb = 0; sph ^= 1; }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->s_empty[sb]);
       }
       bars->xch[group][row] = m;
       group_sync();
       m = fmaxf(m, bars->xch[group ^ 1][row]);
       group_sync();                                           // xch is reused for the row sums below
-      const float m_scaled = m * p.scale_log2;
+      // exponent offset of pass 2: the row maximum AND log2 of the 2^10 probability scale, so that one FMA + one
+      // MUFU.EX2 yield p * 2^10 directly (the row sum l is then scaled by 2^10 as well: out = O / l)
+      const float m_scaled = m * p.scale_log2 - 10.f;
+      static_assert(AT_P_SCALE == 1024.f, "the exponent offset above assumes a 2^10 probability scale");
 
       // ---- pass 2: probabilities -> shared memory (UMMA K-major, 128B swizzle), partial row sum
       float l = 0.f;
-      for (int kt = 0; kt < T; ++kt) {
-        mbar_wait(&bars->s_full[sb], sph);
+      for (int kt = 0; kt < T; ++kt, ++sn) {
+        const int sb = sn & 1;
+        mbar_wait(&bars->s_full[sb], (sn >> 1) & 1);
         tc_fence_after();
         float pr[32];
         {
@@ -317,31 +363,39 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant
           tmem_ld_wait();
           const int kbase = kt * AT_BK + group * 32;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float e = fast_exp2(fmaf(__uint_as_float(r[j]), p.scale_log2, -m_scaled));
-            e = (kbase + j < p.Pk) ? e : 0.f;
-            l += e;
-            pr[j] = e * AT_P_SCALE;
+          for (int j = 0; j < 32; ++j) pr[j] = fast_exp2(fmaf(__uint_as_float(r[j]), p.scale_log2, -m_scaled));
+          if (kbase + 32 > p.Pk) {                              // ragged last tile: keys past P' contribute nothing
+#pragma unroll
+            for (int j = 0; j < 32; ++j) pr[j] = (kbase + j < p.Pk) ? pr[j] : 0.f;
           }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) l += pr[j];
         }
         tc_fence_before();
-        mbar_arrive(&bars->s_empty[sb]);
-        if (++sb == 2) { sb = 0; sph ^= 1; }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->s_empty[sb]);
 
-        mbar_wait(&bars->p_empty[pb], pph ^ 1);
-        uint8_t* ph = sP + pb * 2 * AT_P_PLANE + row * 128;
-        uint8_t* pl = ph + AT_P_PLANE;
+        // split before waiting for the buffer: the conversions overlap the P.V MMAs that still read it
+        uint4 phv[4], plv[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           __half2 hi[4], lo[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) split_f32x2(pr[c * 8 + 2 * e], pr[c * 8 + 2 * e + 1], hi[e], lo[e]);
-          const int phys = ((group * 4 + c) ^ (row & 7)) << 4;
-          *reinterpret_cast<uint4*>(ph + phys) = *reinterpret_cast<const uint4*>(hi);
-          *reinterpret_cast<uint4*>(pl + phys) = *reinterpret_cast<const uint4*>(lo);
+          phv[c] = *reinterpret_cast<const uint4*>(hi);
+          plv[c] = *reinterpret_cast<const uint4*>(lo);
+        }
+        mbar_wait(&bars->p_empty[pb], pph ^ 1);
+        uint8_t* ph = sP + pb * 2 * AT_P_PLANE + row * 128;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int phys = ((group * 4 + c) ^ (row & 7)) << 4;   // 16-byte chunk inside the 128-byte swizzled row
+          *reinterpret_cast<uint4*>(ph + phys) = phv[c];
+          *reinterpret_cast<uint4*>(ph + AT_P_PLANE + phys) = plv[c];
         }
         fence_proxy_async_smem();
-        mbar_arrive(&bars->p_full[pb]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->p_full[pb]);
         if (++pb == 2) { pb = 0; pph ^= 1; }
       }
       bars->xch[group][row] = l;
@@ -349,17 +403,33 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant
       l += bars->xch[group ^ 1][row];
       group_sync();
 
-      // ---- epilogue: out = O / (l * 2^10) + residual; this group's half of the channel slice
-      mbar_wait(&bars->o_full, oph);
-      tc_fence_after();
-      oph ^= 1;
-      const float inv = 1.f / (l * AT_P_SCALE);
+      // ---- epilogue: out = O / l + residual; this group's half of the channel slice.  The SPLIT16 residual of
+      //      chunk c+1 is requested before chunk c is processed (and chunk 0 before O is even complete): its
+      //      global-memory latency was the longest serial piece of an item.
       constexpr int COLS = DVT / 2;
+      constexpr int NCHUNK = COLS / 32;
       const int cbase = dvt * DVT + group * COLS;
       const long long obase = (long long)img * p.o_bs + (long long)q_idx * p.o_ld + cbase;
       const long long rbase = (long long)img * p.r_bs + (long long)q_idx * p.r_ld + cbase;
-#pragma unroll 1
-      for (int chunk = 0; chunk < COLS / 32; ++chunk) {
+      const bool res16 = valid && p.res_hi != nullptr;
+      uint4 rbuf[2][8];                                        // [buffer][4 x hi | 4 x lo] = 32 channels
+      auto load_res = [&](int chunk, uint4 (&dst)[8]) {
+        if (res16) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            dst[q] = __ldg(reinterpret_cast<const uint4*>(p.res_hi + rbase + chunk * 32 + q * 8));
+            dst[4 + q] = __ldg(reinterpret_cast<const uint4*>(p.res_lo + rbase + chunk * 32 + q * 8));
+          }
+        }
+      };
+      load_res(0, rbuf[0]);
+      mbar_wait(&bars->o_full, oph);
+      tc_fence_after();
+      oph ^= 1;
+      const float inv = 1.f / l;                               // l carries the 2^10 scale of P
+#pragma unroll
+      for (int chunk = 0; chunk < NCHUNK; ++chunk) {
+        if (chunk + 1 < NCHUNK) load_res(chunk + 1, rbuf[(chunk + 1) & 1]);
         uint32_t r[32];
         tmem_ld_32x32(tmem_O + lane_addr + group * COLS + chunk * 32, r);
         tmem_ld_wait();
@@ -369,12 +439,11 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * inv;
           const int c0 = chunk * 32;
           if (p.res_hi) {
+            const uint4 (&rb)[8] = rbuf[chunk & 1];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              uint4 h4 = *reinterpret_cast<const uint4*>(p.res_hi + rbase + c0 + q * 8);
-              uint4 l4 = *reinterpret_cast<const uint4*>(p.res_lo + rbase + c0 + q * 8);
-              const __half2* hh = reinterpret_cast<const __half2*>(&h4);
-              const __half2* ll = reinterpret_cast<const __half2*>(&l4);
+              const __half2* hh = reinterpret_cast<const __half2*>(&rb[q]);
+              const __half2* ll = reinterpret_cast<const __half2*>(&rb[4 + q]);
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 float2 a = __half22float2(hh[e]), b2 = __half22float2(ll[e]);
@@ -411,7 +480,8 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant
         }
       }
       tc_fence_before();
-      mbar_arrive(&bars->o_empty);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->o_empty);
     }
     if (out_of_range && p.range_flag) atomicOr(p.range_flag, 1);
   }
@@ -458,6 +528,7 @@ int attention_tc(const tdn_attention_desc* d, cudaStream_t stream) {
   p.q_tiles = ceil_div(d->pq, AT_BQ);
   p.dv_tiles = d->d_v / dvt_size;
   p.k_tiles = ceil_div(d->pk, AT_BK);
+  p.k_tiles1 = ceil_div(d->pk, AT_BK1);
   long long items = (long long)d->n * p.q_tiles * p.dv_tiles;
   TDN_REQUIRE(items < (1ll << 31), TDN_ERR_UNSUPPORTED, "attention_tc: too many work items");
   p.num_items = (int)items;

@@ -21,6 +21,7 @@ struct TcParams {
   int Cout, Cin;
   int taps_h, taps_w, dil, conv_stride;
   int n_tiles_n, num_tiles;
+  int tile_begin;        // single-CTA kernel: first tile of this launch (tiles [tile_begin, num_tiles))
   int chunk_kb;          // K blocks accumulated inside TMEM before the fp32 register accumulation
   int w_batched;
   const float* scale;
@@ -65,7 +66,7 @@ __device__ __forceinline__ void tc_epilogue_role(const TcParams& p, uint32_t tme
     int as = 0;
     uint32_t aphase = 0;
     bool out_of_range = false;
-    const int tile_first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int tile_first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x + p.tile_begin;
     const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     for (int tile = tile_first; tile < p.num_tiles; tile += tile_step) {
       const int nt = tile % p.n_tiles_n;

@@ -95,7 +95,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x + p.tile_begin; tile < p.num_tiles; tile += gridDim.x) {
         const int nt = tile % p.n_tiles_n;
         int mt = tile / p.n_tiles_n;
         const int tx = mt % p.tiles_w;
@@ -134,7 +134,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     uint32_t phase = 0;
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x + p.tile_begin; tile < p.num_tiles; tile += gridDim.x) {
       for (int kb0 = 0; kb0 < num_kb; kb0 += p.chunk_kb) {
         const int kb1 = min(kb0 + p.chunk_kb, num_kb);
         mbar_wait(&tmem_empty[as], aphase ^ 1);
@@ -239,14 +239,17 @@ static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUt
     TDN_CUDA_OK(cudaGetDevice(&dev));
     TDN_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
+  const int todo = p.num_tiles - p.tile_begin;
+  int grid = todo < g_num_sms ? todo : g_num_sms;
   tc_conv_kernel<BLOCK_N><<<grid, TC_THREADS, Cfg::SMEM_BYTES, stream>>>(a_hi, a_lo, b_hi, b_lo, p);
   TDN_LAUNCH_OK();
   return TDN_OK;
 }
 
 int conv2d_tc_halo(const tdn_tc_conv_desc* d, TcParams p, int num_sms, int chunk_kb, cudaStream_t stream);
-int conv2d_tc_pair(const tdn_tc_conv_desc* d, TcParams p, int block_n, int num_sms, cudaStream_t stream);
+int conv2d_tc_pair(const tdn_tc_conv_desc* d, TcParams p, int block_n, int num_sms, int max_pair_tiles,
+                   cudaStream_t stream);
+int conv2d_tc_pair_clusters(int block_n, int num_sms, int* clusters);
 
 int conv2d_tc(const tdn_tc_conv_desc* d, cudaStream_t stream) {
   const tdn_tensor& in = d->in;
@@ -289,7 +292,7 @@ int conv2d_tc(const tdn_tc_conv_desc* d, cudaStream_t stream) {
   }
   const long long tiles128 = (long long)in.n * p.tiles_h * p.tiles_w * ceil_div(d->cout, 128);
   const int num_kb_host = taps * (in.c / TC_BLOCK_K);
-  const int block_n = (d->cout <= 64 || (tiles128 < 2ll * g_num_sms && num_kb_host <= 24)) ? 64 : 128;
+  int block_n = (d->cout <= 64 || (tiles128 < 2ll * g_num_sms && num_kb_host <= 24)) ? 64 : 128;
   p.n_tiles_n = ceil_div(d->cout, block_n);
   long long num_tiles = (long long)in.n * p.tiles_h * p.tiles_w * p.n_tiles_n;
   TDN_REQUIRE(num_tiles < (1ll << 31), TDN_ERR_UNSUPPORTED, "conv2d_tc: too many tiles");
@@ -368,10 +371,41 @@ int conv2d_tc(const tdn_tc_conv_desc* d, cudaStream_t stream) {
     // 512 -> 512 GEMMs with only 8 K blocks per tile lose 8 % (fewer, longer tiles: 3.5 waves -> 4), N = 128
     // pair tiles are a wash
     const bool pair_auto = d->cout % 256 == 0 && (pair_env > 0 || (pair_env < 0 && num_kb_host >= 16));
-    if (d->variant == TDN_TC_PAIR || (d->variant == TDN_TC_AUTO && pair_ok && pair_auto))
-      return conv2d_tc_pair(d, p, d->cout % 256 == 0 ? 256 : 128, g_num_sms, stream);
+    if (d->variant == TDN_TC_PAIR || (d->variant == TDN_TC_AUTO && pair_ok && pair_auto)) {
+      const int pair_n = d->cout % 256 == 0 ? 256 : 128;
+      // Wave quantisation experiment (TDNET_TC_PAIR_SPLIT=1, off by default): pair tiles are big (layer 4: 256
+      // tiles on 74 clusters = 3.46 waves).  When the ragged last wave fits ONE wave of the single-CTA kernel's
+      // 128 x 128 tiles, the pair kernel runs the full waves and the single-CTA kernel the remaining M range.
+      // Measured on B200: 0.3073 -> 0.3051 ms on the layer-4 conv, i.e. nothing -- at ~1.5 PFLOP/s executed the
+      // launch is paced by the chip's power-limited tensor rate (cuBLAS bf16 burst: 1.67 PFLOP/s), not by the
+      // number of waves, so an idle half wave costs no time.  Both kernels are bit-identical per output.
+      int clusters = 0, rc;
+      if ((rc = conv2d_tc_pair_clusters(pair_n, g_num_sms, &clusters))) return rc;
+      const int ntn_pair = ceil_div(d->cout, pair_n);
+      const long long m_tiles = (long long)in.n * p.tiles_h * p.tiles_w;
+      const long long pair_tiles = ((m_tiles + 1) / 2) * ntn_pair;
+      long long head = pair_tiles / clusters * clusters;
+      head -= head % ntn_pair;                                    // whole pair rows of M only
+      const long long m_done = head / ntn_pair * 2;
+      const long long tail_tiles = (m_tiles - m_done) * ceil_div(d->cout, 128);
+      static int split_env = -2;
+      if (split_env == -2) {
+        const char* e = getenv("TDNET_TC_PAIR_SPLIT");
+        split_env = e ? atoi(e) : 0;
+      }
+      if (split_env && d->variant == TDN_TC_AUTO && head > 0 && head < pair_tiles && tail_tiles <= g_num_sms) {
+        if ((rc = conv2d_tc_pair(d, p, pair_n, g_num_sms, (int)head, stream))) return rc;
+        block_n = 128;
+        p.n_tiles_n = ceil_div(d->cout, 128);
+        p.num_tiles = (int)(m_tiles * p.n_tiles_n);
+        p.tile_begin = (int)(m_done * p.n_tiles_n);
+        // falls through to the single-CTA launch below for tiles [tile_begin, num_tiles)
+      } else {
+        return conv2d_tc_pair(d, p, pair_n, g_num_sms, 0, stream);
+      }
+    }
     const bool halo_auto = halo_env > 0 || (halo_env < 0 && d->dilation == 1 && in.c == 128 && d->cout <= 128);
-    if (d->variant == TDN_TC_HALO || (d->variant == TDN_TC_AUTO && halo_ok && halo_auto))
+    if (d->variant == TDN_TC_HALO || (d->variant == TDN_TC_AUTO && halo_ok && halo_auto && p.tile_begin == 0))
       return conv2d_tc_halo(d, p, g_num_sms, p.chunk_kb, stream);
   }
 

@@ -20,6 +20,7 @@
 // Arithmetic is identical to tc_conv.cu (same products, same chunking), so results are bit-identical to it.
 #include "tc_common.cuh"
 
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <cuda.h>
@@ -177,8 +178,7 @@ int encode_map_f16(CUtensorMap* m, const void* base, int rank, const cuuint64_t*
                    const cuuint32_t* box, const char* what, const cuuint32_t* elem_strides, int swizzle128 = 1);
 
 template <int BLOCK_N>
-static int launch_pair(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
-                       const TcParams& p, int num_sms, cudaStream_t stream) {
+static int pair_clusters(int num_sms, int* clusters) {
   using Cfg = PairCfg<BLOCK_N>;
   static int max_clusters = 0;
   if (max_clusters == 0) {
@@ -202,7 +202,23 @@ static int launch_pair(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const C
       n = num_sms / 2;
     }
     max_clusters = n < num_sms / 2 ? n : num_sms / 2;
+    if (const char* e = getenv("TDNET_TC_PAIR_VERBOSE"))
+      if (atoi(e)) fprintf(stderr, "[tdnet_b200] tc_conv_pair_kernel<%d>: %d resident clusters of 2 CTAs\n", BLOCK_N, max_clusters);
   }
+  *clusters = max_clusters;
+  return TDN_OK;
+}
+
+int conv2d_tc_pair_clusters(int block_n, int num_sms, int* clusters) {
+  return block_n == 256 ? pair_clusters<256>(num_sms, clusters) : pair_clusters<128>(num_sms, clusters);
+}
+
+template <int BLOCK_N>
+static int launch_pair(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
+                       const TcParams& p, int num_sms, cudaStream_t stream) {
+  using Cfg = PairCfg<BLOCK_N>;
+  int max_clusters = 0, rc;
+  if ((rc = pair_clusters<BLOCK_N>(num_sms, &max_clusters))) return rc;
   const int clusters = p.num_tiles < max_clusters ? p.num_tiles : max_clusters;
   tc_conv_pair_kernel<BLOCK_N><<<2 * clusters, TC_THREADS, Cfg::SMEM_BYTES, stream>>>(a_hi, a_lo, b_hi, b_lo, p);
   TDN_LAUNCH_OK();
@@ -210,8 +226,10 @@ static int launch_pair(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const C
 }
 
 // Called by conv2d_tc() with the epilogue / output / residual fields of `p` filled in and the 128-pixel tile
-// shape chosen; re-tiles into pair tiles of 2 x 128 pixels x block_n output channels.
-int conv2d_tc_pair(const tdn_tc_conv_desc* d, TcParams p, int block_n, int num_sms, cudaStream_t stream) {
+// shape chosen; re-tiles into pair tiles of 2 x 128 pixels x block_n output channels.  max_pair_tiles > 0 limits
+// the launch to the first pair tiles (the caller finishes the remaining M range with the single-CTA kernel).
+int conv2d_tc_pair(const tdn_tc_conv_desc* d, TcParams p, int block_n, int num_sms, int max_pair_tiles,
+                   cudaStream_t stream) {
   const tdn_tensor& in = d->in;
   const int cs = p.conv_stride;
   const int taps = d->kh * d->kw;
@@ -221,6 +239,8 @@ int conv2d_tc_pair(const tdn_tc_conv_desc* d, TcParams p, int block_n, int num_s
   const long long num_tiles = ((m_tiles + 1) / 2) * p.n_tiles_n;
   TDN_REQUIRE(num_tiles < (1ll << 30), TDN_ERR_UNSUPPORTED, "conv2d_tc_pair: too many tiles");
   p.num_tiles = (int)num_tiles;
+  if (max_pair_tiles > 0 && max_pair_tiles < p.num_tiles) p.num_tiles = max_pair_tiles;
+  p.tile_begin = 0;
 
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
   int rc;

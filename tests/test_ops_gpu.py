@@ -389,6 +389,34 @@ def test_tc_conv_pair_variant_is_bit_identical(env, n, h, w, cin, cout, k, dil, 
     assert torch.equal(base[1].view(torch.int16), pair[1].view(torch.int16))
 
 
+def test_tc_conv_auto_pair_plus_tail_split_is_bit_identical(env):
+    """Layer-4-like tiling (256 M tiles x 512 channels): TDN_TC_AUTO runs the full waves on the CTA-pair kernel and
+    the ragged last wave on the single-CTA kernel (two launches); every output must equal the single-kernel run."""
+    lib, cabi, View, dev = env
+    n, h, w, cin, cout, k, dil = 1, 128, 256, 128, 512, 3, 4
+    g = torch.Generator(device="cuda").manual_seed(5)
+    xs = View.alloc(n, h, w, cin, dev, split=True)
+    x = torch.randn(n * h * w * cin, generator=g, device="cuda")
+    xs.base.copy_(x.half()); xs.lo.copy_((x - x.half().float()).half())
+    wt = torch.randn(cout, k * k * cin, generator=g, device="cuda") / (cin * k * k) ** 0.5
+    wh, wl = split_planes(wt)
+    outs = []
+    for variant in (cabi.TC_BASE, cabi.TC_AUTO, cabi.TC_PAIR):
+        out = View.alloc(n, h, w, cout, dev, split=True)
+        out.base.fill_(float("nan")); out.lo.fill_(float("nan"))
+        d = cabi.TcConvDesc()
+        d.in_, d.out = xs.ct(), out.ct()
+        d.weight_hi, d.weight_lo, d.weight_ld = wh.data_ptr(), wl.data_ptr(), k * k * cin
+        d.cout, d.kh, d.kw, d.dilation, d.variant = cout, k, k, dil, variant
+        cabi.check(lib.tdn_conv2d_tc(C.byref(d), None), "conv2d_tc")
+        torch.cuda.synchronize()
+        outs.append((out.base.clone(), out.lo.clone()))
+    assert not torch.isnan(outs[1][0].float()).any()
+    for other in outs[1:]:
+        assert torch.equal(outs[0][0].view(torch.int16), other[0].view(torch.int16))
+        assert torch.equal(outs[0][1].view(torch.int16), other[1].view(torch.int16))
+
+
 def test_tc_conv_variant_errors(env):
     lib, cabi, View, dev = env
     xs = View.alloc(1, 8, 16, 64, dev, split=True)
