@@ -55,6 +55,10 @@ int attention_tc(const tdn_attention_desc*, cudaStream_t);
 int stem_conv_pool_tc(const float*, const uint8_t*, const float*, int, int, int, const void*, const float*, const float*,
                       const tdn_tensor*, int*, cudaStream_t);
 int split16(const tdn_tensor*, const tdn_tensor*, cudaStream_t);
+int fa_context(const tdn_tensor*, const tdn_tensor*, float*, void*, size_t, cudaStream_t);
+size_t fa_context_workspace_bytes(int, int, int, int);
+int fa_apply(const tdn_tensor*, const float*, const tdn_tensor*, int*, cudaStream_t);
+int add_upsampled(const tdn_tensor*, const tdn_tensor*, const tdn_tensor*, const tdn_tensor*, cudaStream_t);
 int merge16(const tdn_tensor*, const tdn_tensor*, cudaStream_t);
 
 }  // namespace tdn
@@ -210,6 +214,24 @@ int tdn_upsample_logits(const tdn_tensor* in, float* out_nchw, int32_t out_h, in
 
 int tdn_upsample_argmax(const tdn_tensor* in, uint8_t* labels, int32_t out_h, int32_t out_w, void* stream) {
   return upsample_argmax(in, labels, out_h, out_w, (cudaStream_t)stream);
+}
+
+int tdn_fa_context(const tdn_tensor* key, const tdn_tensor* value, float* f, void* workspace,
+                   uint64_t workspace_bytes, void* stream) {
+  return fa_context(key, value, f, workspace, (size_t)workspace_bytes, (cudaStream_t)stream);
+}
+
+uint64_t tdn_fa_context_workspace_bytes(int32_t n, int32_t h, int32_t w, int32_t c) {
+  return (uint64_t)fa_context_workspace_bytes(n, h, w, c);
+}
+
+int tdn_fa_apply(const tdn_tensor* query, const float* f, const tdn_tensor* out, int32_t* range_flag, void* stream) {
+  return fa_apply(query, f, out, range_flag, (cudaStream_t)stream);
+}
+
+int tdn_add_upsampled(const tdn_tensor* a, const tdn_tensor* b, const tdn_tensor* up, const tdn_tensor* out,
+                      void* stream) {
+  return add_upsampled(a, b, up, out, (cudaStream_t)stream);
 }
 
 }  // extern "C"

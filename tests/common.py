@@ -4,6 +4,7 @@ import os
 import numpy as np
 import torch
 
+from oracle.td2fa_oracle import TD2FAOracle, fa_feature_hw, td2fa_state_dict_template
 from oracle.tdnet_oracle import PSPNetOracle, TDOracle, state_dict_template
 from tdnet_b200.synth import synth_clip, synth_state_dict
 
@@ -21,6 +22,9 @@ GOLDEN_CASES = {
 }
 # single-path PSPNet comparison model (Testing/model/pspnet/pspnet.py): name -> backbone
 PSPNET_GOLDEN_CASES = {"psp_r101_64x96_n2": "resnet101", "psp_r18_97x161": "resnet18"}
+# TD2-FANet (Training/ptsemseg/models/td2_fanet/td2_fa.py; tests/golden/make_golden_fanet.py): name -> backbone
+FANET_GOLDEN_CASES = {"td2fa_r18_128x192": "resnet18", "td2fa_r34_97x161_n2": "resnet34",
+                      "td2fa_r50_64x96": "resnet50"}
 
 
 def load_golden(name):
@@ -48,6 +52,12 @@ def make_oracle(arch, backbone, H, W, seed=0):
 def make_pspnet_oracle(backbone, seed=0):
     sd = synth_state_dict(state_dict_template("pspnet", backbone), seed=seed)
     return PSPNetOracle(sd, backbone), sd
+
+
+def make_fanet_oracle(backbone, H, W, seed=0):
+    h4, w4 = fa_feature_hw(H, W)
+    sd = synth_state_dict(td2fa_state_dict_template(backbone, ln_shape=(h4, w4)), seed=seed)
+    return TD2FAOracle(sd, backbone), sd
 
 
 def max_abs(a, b):

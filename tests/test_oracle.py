@@ -3,8 +3,8 @@ import numpy as np
 import pytest
 import torch
 
-from common import (CH_STRIDE, GOLDEN_CASES, PSPNET_GOLDEN_CASES, load_golden, make_oracle, make_pspnet_oracle,
-                    max_abs)
+from common import (CH_STRIDE, FANET_GOLDEN_CASES, GOLDEN_CASES, PSPNET_GOLDEN_CASES, load_golden, make_fanet_oracle,
+                    make_oracle, make_pspnet_oracle, max_abs)
 from oracle.tdnet_oracle import stage_plan, state_dict_template
 from tdnet_b200.synth import synth_clip
 
@@ -65,6 +65,36 @@ def test_pspnet_oracle_matches_reference_outputs(name):
     assert max_abs(oracle.taps["z"][:, ::s], g["tap_z"]) <= 5 * TOL * scale
 
 
+@pytest.mark.parametrize("name", sorted(FANET_GOLDEN_CASES))
+def test_fanet_oracle_matches_reference_outputs(name):
+    """TD2FAOracle vs the unmodified td2_fa (Training/ptsemseg/models/td2_fanet/td2_fa.py) run on CPU: call i feeds
+    the frame pair (i, i+1) with pos_id = i % 2; every FAModule output of the current frame's sub-network is pinned."""
+    g, m = load_golden(name)
+    oracle, _ = make_fanet_oracle(FANET_GOLDEN_CASES[name], m["H"], m["W"])
+    calls = m["n_frames"]
+    frames = synth_clip(calls + 1, m["H"], m["W"], batch=m["batch"], clip_id=0)
+    for i in range(calls):
+        out = oracle([frames[i], frames[i + 1]], pos_id=i % 2)
+        scale = max(1.0, float(np.abs(g[f"head_{i}"]).max()))
+        assert max_abs(oracle.taps["head"], g[f"head_{i}"]) <= TOL * scale, (name, i)
+        if f"logits_{i}" in g:
+            assert out.shape == g[f"logits_{i}"].shape == (m["batch"], 19, m["H"], m["W"])
+            assert max_abs(out, g[f"logits_{i}"]) <= TOL * scale
+    t, s = oracle.taps, CH_STRIDE
+    a = 1 if (calls - 1) % 2 == 0 else 2
+    for key, tap, stride in (("feat4", f"feat4_{a}", 1), ("feat32", f"feat32_{a}", s), ("up32", f"up32_{a}", s),
+                             ("up16", f"up16_{a}", s), ("sm16", f"sm16_{a}", 1), ("up8", f"up8_{a}", 1),
+                             ("sm4", f"sm4_{a}", 1), ("q", "q", 1), ("v", "v", s), ("k_sub", "k_sub", 1),
+                             ("v_sub", "v_sub", 1), ("atn", "atn", s), ("normed", "normed", s)):
+        ref = g["tap_" + key]
+        got = t[tap][:, ::stride] if stride > 1 else t[tap]
+        assert tuple(got.shape) == ref.shape, key
+        assert max_abs(got, ref) <= 5 * TOL * max(1.0, float(np.abs(ref).max())), key
+    # `up` is a 1x1 conv with padding 1 (td2_fa.py:348): the map it returns is 2 pixels larger than its input
+    h32, w32 = g["tap_feat32"].shape[2:]
+    assert g["tap_up32"].shape[2:] == (h32 + 2, w32 + 2)
+
+
 def test_oracle_native_size_checksums():
     """769x1537 (the only size the unpatched reference accepts, LayerNorm([97,193]))."""
     name = "td4_r18_769x1537_chk"
@@ -113,3 +143,6 @@ def test_state_dict_template_sizes():
     assert len(sd) == 776 and abs(sum(v.numel() for v in sd.values()) / 1e6 - 65.5) < 0.1
     sd = state_dict_template("pspnet")   # PSPNet-101: 670 tensors / 67.9 M (checked against the reference in make_golden.py)
     assert len(sd) == 670 and abs(sum(v.numel() for v in sd.values()) / 1e6 - 67.9) < 0.1
+    from oracle.td2fa_oracle import td2fa_state_dict_template
+    sd = td2fa_state_dict_template("resnet18")   # checked against the reference module in make_golden_fanet.py
+    assert sd["ffm_32_1.up.conv.weight"].shape == (256, 512, 1, 1) and sd["head_aux2.conv_out.weight"].shape == (19, 64, 1, 1)
