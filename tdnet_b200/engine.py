@@ -226,7 +226,8 @@ class Engine:
             raise RuntimeError(f"Given normalized_shape={list(ln_shape)}, expected input with shape "
                                f"[*, {ln_shape[0]}, {ln_shape[1]}], but got feature map "
                                f"[{n}, {arch.d_v}, {self.h8}, {self.w8}]")
-        self.hs, self.ws = (self.h8 - 1) // 4 + 1, (self.w8 - 1) // 4 + 1
+        self.key_stride = A.FA_KEY_STRIDE if arch.arch == "td2_fa" else 4   # MaxPool2d(kernel 1, stride 3 | 4)
+        self.hs, self.ws = (self.h8 - 1) // self.key_stride + 1, (self.w8 - 1) // self.key_stride + 1
         self.pk = self.hs * self.ws                       # keys per frame (P')
         self.pk_pad = (self.pk + 63) // 64 * 64 if self.tc else (self.pk + 3) // 4 * 4
         self.sd = state_dict
@@ -355,7 +356,7 @@ class Engine:
 
     def _conv_simt(self, plan: FramePlan, pc: PackedConv, x: View, out: View, residual: Optional[View] = None,
                    act=None, stride=None, batch=1, weight_ptr=None, weight_kn=0, in_bs=0, out_bs=0, res_bs=0, w_bs=0,
-                   k=None, dilation=None, cout=None, scale_ptr="auto", bias_ptr="auto"):
+                   k=None, dilation=None, cout=None, scale_ptr="auto", bias_ptr="auto", pad=None):
         spec = pc.spec if pc is not None else None
         d = Conv2dDesc()
         d.in_, d.out = x.ct(), out.ct()
@@ -372,7 +373,7 @@ class Engine:
         d.kh = d.kw = kk
         d.stride = stride if stride is not None else (spec.stride if spec else 1)
         d.dilation = dilation if dilation is not None else (spec.dilation if spec else 1)
-        d.pad = d.dilation * (kk - 1) // 2
+        d.pad = d.dilation * (kk - 1) // 2 if pad is None else pad
         d.act = _ACT[act if act is not None else (spec.act if spec else "none")]
         d.leaky_slope = 0.01
         d.weight_kn, d.batch = weight_kn, batch
@@ -393,7 +394,31 @@ class Engine:
             self._plans[key] = self._build(path, steady)
         return self._plans[key]
 
+    def _residual_blocks(self, plan: FramePlan, blocks, x: View, taps=()):
+        """Runs `blocks` (resnet.py:43-59, 91-111: the last conv of a block takes the shortcut and the closing
+        ReLU); returns the outputs of the blocks whose index is in `taps`, followed by the final output."""
+        n, outs = self.n, []
+        for bi, blk in enumerate(blocks):
+            identity = x
+            if blk.downsample is not None:
+                oh, ow = self._out_hw(x.h, x.w, blk.downsample)
+                identity = self.buf(n, oh, ow, blk.downsample.cout)
+                self._conv(plan, self.packed(blk.downsample), x, identity)
+            t = x
+            for i, c in enumerate(blk.convs):
+                oh, ow = self._out_hw(t.h, t.w, c)
+                y = self.buf(n, oh, ow, c.cout)
+                last = i == len(blk.convs) - 1
+                self._conv(plan, self.packed(c), t, y, residual=identity if last else None)
+                t = y
+            x = t
+            if bi in taps:
+                outs.append(x)
+        return outs + [x]
+
     def _build(self, path: int, steady: bool) -> FramePlan:
+        if self.m.arch == "td2_fa":
+            return self._build_fanet(path)
         m, n, lib = self.m, self.n, self.lib
         plan = FramePlan()
         self._cursor = {}
@@ -447,20 +472,7 @@ class Engine:
             plan.side = False
 
         # --- residual stages
-        for blk in m.stages[path]:
-            identity = x
-            if blk.downsample is not None:
-                oh, ow = self._out_hw(x.h, x.w, blk.downsample)
-                identity = self.buf(n, oh, ow, blk.downsample.cout)
-                self._conv(plan, self.packed(blk.downsample), x, identity)
-            t = x
-            for i, c in enumerate(blk.convs):
-                oh, ow = self._out_hw(t.h, t.w, c)
-                y = self.buf(n, oh, ow, c.cout)
-                last = i == len(blk.convs) - 1
-                self._conv(plan, self.packed(c), t, y, residual=identity if last else None)
-                t = y
-            x = t
+        x = self._residual_blocks(plan, m.stages[path], x)[-1]
         c4 = x
         assert (c4.h, c4.w, c4.c) == (h8, w8, m.c4), (c4.h, c4.w, c4.c)
         if m.arch == "pspnet":
@@ -584,6 +596,206 @@ class Engine:
         plan.labels_op = (lib.tdn_upsample_argmax, (C.byref(self._ct(plan, low)), "out", H, W, "stream"))
         plan.taps = dict(c4=c4, z=z, head=low)
         return plan
+
+    # ------------------------------------------------------------------ TD2-FANet
+    def _build_fanet(self, path: int) -> FramePlan:
+        """One call of td2_fa.forward in eval mode (Training/ptsemseg/models/td2_fanet/td2_fa.py:87-186, 200-218).
+        Sub-network `path` reads the CURRENT frame ("img") and supplies q / v; the other sub-network reads the
+        PREVIOUS frame ("img2") and supplies keys / values -- it only depends on its own image, so it runs on the
+        side stream next to the first one.  Both run on every call (the reference keeps no state between calls)."""
+        m, n, lib = self.m, self.n, self.lib
+        H, W, h4, w4 = self.H, self.W, self.h8, self.w8
+        a, b = path, 3 - path
+        plan = FramePlan()
+        self._cursor = {}
+        img_cur, img_prev = self.buf(n, H, W, 4, split=False), self.buf(n, H, W, 4, split=False)
+        plan.add(lib.tdn_image_to_nhwc, "img", n, 3, H, W, C.byref(self._ct(plan, img_cur)), "stream")
+        plan.add(lib.tdn_image_to_nhwc, "img2", n, 3, H, W, C.byref(self._ct(plan, img_prev)), "stream")
+        plan.head_ops = 2                                   # both touch per-call pointers: launched outside the graph
+        enc_a, enc_b = A.encoding_convs(m, a), A.encoding_convs(m, b)
+        fork = self.side_stream is not None
+        if fork:
+            plan.mark("fork")
+            plan.side = True
+        # --- previous frame: sub-network b -> z -> Encoding(pre=True): K and V on the stride-3 grid
+        #     (transformer.py:35-46; a 1x1 conv commutes with MaxPool2d(kernel 1, stride 3) = sub-sampling)
+        z_prev, taps_b = self._fa_subnet(plan, b, img_prev)
+        zs = z_prev.subsample(self.key_stride)
+        k_mid = self.buf(n, self.hs, self.ws, m.d_k)
+        self._conv(plan, self.packed(enc_b["w_ks"][0]), zs, k_mid)
+        k_sub = self.buf(n, self.hs, self.ws, m.d_k)
+        self._conv(plan, self.packed(enc_b["w_ks"][1]), k_mid, k_sub)
+        v_sub = self.buf(n, self.hs, self.ws, m.d_v)
+        self._conv(plan, self.packed(enc_b["w_vs"][0]), zs, v_sub)
+        k_tok, v_tok = self._token_view(k_sub), self._token_view(v_sub)
+        pre = self._fa_values(plan, a, v_tok)               # V' = fc(V): Attention.fc folded into the values
+        plan.side = False
+        # --- current frame: sub-network a -> z -> Encoding(pre=False): full-resolution Q and V
+        z_cur, taps_a = self._fa_subnet(plan, a, img_cur)
+        v_cur = self.buf(n, h4, w4, m.d_v)
+        self._conv(plan, self.packed(enc_a["w_vs"][0]), z_cur, v_cur)
+        q_mid = self.buf(n, h4, w4, m.d_k)
+        self._conv(plan, self.packed(enc_a["w_qs"][0]), z_cur, q_mid)
+        q_cur = self.buf(n, h4, w4, m.d_k)
+        self._conv(plan, self.packed(enc_a["w_qs"][1]), q_mid, q_cur)
+        if fork:
+            plan.mark("join")
+        # --- atn + v (td2_fa.py:110-111), LayerNorm, FPNOutput head, upsample
+        fused = self._fa_attention(plan, a, q_cur, v_cur, k_tok, pre)
+        mean = torch.empty(n * m.d_v, dtype=torch.float32, device=self.device)
+        rstd = torch.empty_like(mean)
+        lws_bytes = int(lib.tdn_layernorm_hw_workspace_bytes(n, h4, w4, m.d_v))
+        lws = torch.empty(lws_bytes // 4 + 4, dtype=torch.float32, device=self.device)
+        plan.add(lib.tdn_layernorm_hw_stats, C.byref(self._ct(plan, fused)), mean.data_ptr(), rstd.data_ptr(),
+                 C.c_float(_LN_EPS), lws.data_ptr(), lws_bytes, "stream", launches=2)
+        normed = self.buf(n, h4, w4, m.d_v)
+        plan.add(lib.tdn_layernorm_hw_apply, C.byref(self._ct(plan, fused)), mean.data_ptr(), rstd.data_ptr(),
+                 self.ln_gamma[a].data_ptr(), self.ln_beta[a].data_ptr(), C.byref(self._ct(plan, normed)), "stream")
+        plan.keep.append((mean, rstd, lws))
+        hc = A.fa_head_convs(m, f"head{a}", m.d_v, m.head_mid)
+        mid = self.buf(n, h4, w4, m.head_mid)
+        self._conv(plan, self.packed(hc[0]), normed, mid)
+        low = self.buf(n, h4, w4, m.nclass, split=False)
+        self._conv(plan, self.packed(hc[1]), mid, low)
+        plan.add(lib.tdn_upsample_logits, C.byref(self._ct(plan, low)), "out", H, W, "stream")
+        plan.labels_op = (lib.tdn_upsample_argmax, (C.byref(self._ct(plan, low)), "out", H, W, "stream"))
+        plan.taps = dict(taps_a, z=z_cur, z_prev=z_prev, q=q_cur, v=v_cur, k_sub=k_sub, v_sub=v_sub, fused=fused,
+                         normed=normed, head=low)
+        return plan
+
+    def _token_view(self, x: View) -> View:
+        """Dense [n,h,w,c] map as the per-image token matrices [n,1,h*w,c]."""
+        assert x.sh == x.w * x.sw and x.sw == x.c
+        return x._like(x.n, 1, x.h * x.w, x.c, x.sn, x.h * x.w * x.sw, x.sw, x.offset)
+
+    def _fa_subnet(self, plan: FramePlan, idx: int, img: View):
+        """Backbone + the four fast-attention modules top-down (td2_fa.py:95-101) -> z = cat(up(smooth_16), smooth_4)
+        (_upsample_cat :191-197): 256 channels at the feat4 resolution."""
+        m, n, lib = self.m, self.n, self.lib
+        c = m.stems[idx][0]
+        # stem: conv7x7 s2 + BN + LeakyReLU on the fp32 CUDA-core kernel (3 input channels), then the -inf padded
+        # max pool (the fused stem kernels assume ReLU: their pool pads with 0)
+        oh, ow = self._out_hw(img.h, img.w, c)
+        x = self.buf(n, oh, ow, c.cout)
+        self._conv(plan, self.packed(c), img, x)
+        y = self.buf(n, (oh - 1) // 2 + 1, (ow - 1) // 2 + 1, c.cout)
+        plan.add(lib.tdn_maxpool3x3s2, C.byref(self._ct(plan, x)), C.byref(self._ct(plan, y)), "stream")
+        feat4, feat8, feat16, feat32, _ = self._residual_blocks(plan, m.stages[idx], y, taps=m.stage_ends)
+        z = self.buf(n, feat4.h, feat4.w, 2 * A.FA_OUT)
+        up32, _ = self._fa_module(plan, 32, idx, feat32, None, True, False)
+        up16, sm16 = self._fa_module(plan, 16, idx, feat16, up32, True, True)
+        up8, _ = self._fa_module(plan, 8, idx, feat8, up16, True, False)
+        _, sm4 = self._fa_module(plan, 4, idx, feat4, up8, False, True, smooth_out=z.channels(A.FA_OUT, 2 * A.FA_OUT))
+        plan.add(lib.tdn_bilinear_nhwc, C.byref(self._ct(plan, sm16)), C.byref(self._ct(plan, z.channels(0, A.FA_OUT))),
+                 "stream")
+        return z, dict(feat4=feat4, feat32=feat32, up32=up32, up16=up16, sm16=sm16, up8=up8, sm4=sm4)
+
+    def _fa_module(self, plan: FramePlan, level: int, idx: int, feat: View, up_in: Optional[View], want_up: bool,
+                   want_smooth: bool, smooth_out: Optional[View] = None):
+        """FAModule.forward (td2_fa.py:350-395): y = qhat (khat^T v) over all pixels of the map (L2-normalised 32-channel
+        query / key), p = latlayer3(y) + feat (+ upsampled coarser level); returns (up(p) or None, smooth(p) or None).
+        ffm_32 is called with smf_flag=True but has no coarser input, so it returns `up` only (:377-384)."""
+        m, n, lib = self.m, self.n, self.lib
+        cv = A.fa_module_convs(m, level, idx)
+        h, w, c = feat.h, feat.w, feat.c
+        q = self.buf(n, h, w, A.FA_DK, split=False)
+        k = self.buf(n, h, w, A.FA_DK, split=False)
+        v = self.buf(n, h, w, c)
+        self._conv(plan, self.packed(cv["w_qs"]), feat, q)
+        self._conv(plan, self.packed(cv["w_ks"]), feat, k)
+        self._conv(plan, self.packed(cv["w_vs"]), feat, v)
+        f = torch.empty(n * A.FA_DK * c, dtype=torch.float32, device=self.device)
+        ws_bytes = int(lib.tdn_fa_context_workspace_bytes(n, h, w, c))
+        ws = torch.empty(max(ws_bytes // 4, 4), dtype=torch.float32, device=self.device)
+        plan.add(lib.tdn_fa_context, C.byref(self._ct(plan, k)), C.byref(self._ct(plan, v)), f.data_ptr(), ws.data_ptr(),
+                 ws_bytes, "stream", launches=2, name=f"ffm_{level}_{idx}.context")
+        y = self.buf(n, h, w, c)
+        plan.add(lib.tdn_fa_apply, C.byref(self._ct(plan, q)), f.data_ptr(), C.byref(self._ct(plan, y)),
+                 self.range_flag.data_ptr(), "stream", name=f"ffm_{level}_{idx}.apply")
+        plan.keep.append((f, ws))
+        wy = self.buf(n, h, w, c)
+        self._conv(plan, self.packed(cv["latlayer3"]), y, wy)
+        p_feat = self.buf(n, h, w, c)
+        plan.add(lib.tdn_add_upsampled, C.byref(self._ct(plan, wy)), C.byref(self._ct(plan, feat)),
+                 C.byref(self._ct(plan, up_in)) if up_in is not None else None, C.byref(self._ct(plan, p_feat)), "stream")
+        up = smooth = None
+        if want_up:
+            up = self._fa_up_conv(plan, self.packed(cv["up"]), p_feat)
+        if want_smooth:
+            smooth = smooth_out if smooth_out is not None else self.buf(n, h, w, A.FA_OUT)
+            self._conv(plan, self.packed(cv["smooth"]), p_feat, smooth)
+        return up, smooth
+
+    def _fa_up_conv(self, plan: FramePlan, pc: PackedConv, x: View) -> View:
+        """`up` = 1x1 conv with padding 1 + BN + LeakyReLU (td2_fa.py:348): the output is 2 pixels larger than the
+        input and its 1-pixel frame holds act(BN(0)) = act(folded bias).  The CUDA-core kernel takes the padding as
+        is; for the tensor-core kernel the frame is filled by a broadcast copy and the 1x1 conv writes the interior."""
+        n = self.n
+        out = self.buf(n, x.h + 2, x.w + 2, pc.cout)
+        tc_ok = (self.tc and x.split and x.c % 64 == 0 and n * x.h * x.w >= 64 and pc.cout % 8 == 0)
+        if not tc_ok:
+            self._conv_simt(plan, pc, x, out, pad=1)
+            return out
+        key = "frame:" + pc.spec.name
+        if key not in self._packed:
+            self._packed[key] = torch.nn.functional.leaky_relu(pc.bias, 0.01).contiguous()
+        frame = self._packed[key]
+        src = View(frame, n, out.h, out.w, pc.cout, 0, 0, 0)             # every pixel reads the same [cout] vector
+        plan.add(self.lib.tdn_copy_nhwc, C.byref(self._ct(plan, src)), C.byref(self._ct(plan, out)), "stream")
+        inner = out._like(n, x.h, x.w, pc.cout, out.sn, out.sh, out.sw, out.offset + out.sh + out.sw)
+        self._conv_tc(plan, x, inner, pc=pc)
+        return out
+
+    def _fa_values(self, plan: FramePlan, idx: int, v_tok: View):
+        """Attention.fc (transformer.py:67, 84-86) applied to the values instead of the attention output (softmax
+        rows sum to 1).  tc: V'^T [n, d_v, P' padded to 64] K-major for the fused kernel; simt: V' [n, P' pad 4, d_v]."""
+        m, n = self.m, self.n
+        fc = self.packed(A.fc_conv(m, f"atn{idx}"))
+        pk, pkp = self.pk, self.pk_pad
+        if self.tc:
+            wfc = self._fc_as_activation(fc)
+            vpt = self.buf(n, 1, m.d_v, pkp, zero=True)
+            for i in range(n):
+                self._conv_tc(plan, wfc["view"], vpt.image(i).narrow_c(pk), w_hi=v_tok.image(i).ptr,
+                              w_lo=v_tok.image(i).ptr_lo, w_ld=v_tok.sw, cout=pk,
+                              scale=self.const_vec(wfc["inv_scale"], pkp), bias=fc.bias, bias_along_m=True,
+                              name=f"atn{idx}.fc")
+            return dict(vpt=vpt)
+        vp = self.buf(n, 1, pkp, m.d_v, zero=True)
+        vp_rows = View(vp.base, n, 1, pk, m.d_v, vp.sn, vp.sh, vp.sw, vp.offset)
+        self._conv(plan, fc, v_tok, vp_rows)
+        return dict(vp=vp)
+
+    def _fa_attention(self, plan: FramePlan, idx: int, q_cur: View, v_cur: View, k_tok: View, pre) -> View:
+        """atn(k_prev, v_prev, q_cur) + v_cur (td2_fa.py:110-111 / :161-162; transformer.py:71-92, 126-139)."""
+        m, n, lib = self.m, self.n, self.lib
+        pk, pkp, pq = self.pk, self.pk_pad, self.h8 * self.w8
+        out = self.buf(n, self.h8, self.w8, m.d_v)
+        if self.tc:
+            vpt = pre["vpt"]
+            q_all, out_tok, res_tok = self._token_view(q_cur), self._token_view(out), self._token_view(v_cur)
+            d = _cabi.AttentionDesc()
+            d.q_hi, d.q_lo, d.q_ld, d.q_batch_stride = q_all.ptr, q_all.ptr_lo, q_all.sw, q_all.sn
+            d.k_hi, d.k_lo, d.k_ld, d.k_batch_stride = k_tok.ptr, k_tok.ptr_lo, k_tok.sw, k_tok.sn
+            d.vt_hi, d.vt_lo, d.vt_ld, d.vt_batch_stride = vpt.ptr, vpt.ptr_lo, pkp, vpt.sn
+            d.out, d.residual = out_tok.ct(), res_tok.ct()
+            d.n, d.pq, d.pk, d.d_k, d.d_v = n, pq, pk, m.d_k, m.d_v
+            d.range_flag = self.range_flag.data_ptr()
+            plan.add(lib.tdn_attention_tc, C.byref(d), "stream", name=f"atn{idx}.attention")
+            plan.keep.append((d, q_all, k_tok, vpt, out_tok, res_tok))
+            return out
+        vp = pre["vp"]
+        q, o_one, res_one = q_cur.tokens(), out.tokens(), v_cur.tokens()
+        s = self.buf(n, 1, pq, pkp, zero=True)
+        s_one = View(s.base, 1, 1, pq, pk, s.sn, s.sh, s.sw)
+        self._conv(plan, None, q, s_one, batch=n, weight_ptr=k_tok.ptr, k=1, cout=pk, in_bs=q_cur.sn, out_bs=s.sn,
+                   w_bs=k_tok.sn, scale_ptr=None, bias_ptr=None)
+        plan.add(lib.tdn_softmax_rows, s.ptr, n * pq, pk, pkp, C.c_float(1.0 / float(m.d_k) ** 0.5), "stream")
+        plan.keep.append(s)
+        s_in = View(s.base, 1, 1, pq, pkp, s.sn, s.sh, s.sw)
+        self._conv(plan, None, s_in, o_one, residual=res_one, batch=n, weight_ptr=vp.ptr, weight_kn=1, k=1,
+                   cout=m.d_v, in_bs=s.sn, out_bs=out.sn, res_bs=v_cur.sn, w_bs=vp.sn, scale_ptr=None, bias_ptr=None)
+        return out
 
     def _grid_view(self, slot: View) -> View:
         """FIFO slot [n,1,P',c] seen as the [n,hs,ws,c] grid it was sampled from."""
@@ -725,15 +937,17 @@ class Engine:
         return self._packed[key]
 
     # ------------------------------------------------------------------ execution
-    def run_graphed(self, plan: FramePlan, img_ptr: int, out_ptr: int, labels=False, u8=False):
+    def run_graphed(self, plan: FramePlan, img_ptr: int, out_ptr: int, labels=False, u8=False, img2_ptr=None):
         """Frame through a CUDA graph: the first and last op take the per-call image / output pointers and
         are launched directly; everything in between (static buffers only) is captured once and replayed.
         The plan must have run eagerly once before (kernel attributes, lazy packing)."""
         stream = torch.cuda.current_stream(self.device)
-        first, last = (plan.u8_op if u8 else plan.ops[0]), (plan.labels_op if labels else plan.ops[-1])
-        assert "img" in first[1] and "out" in last[1] and not any(
-            a in ("img", "out") for _, args in plan.ops[1:-1] for a in args if isinstance(a, str))
-        subst = {"img": img_ptr, "out": out_ptr, "stream": stream.cuda_stream}
+        nh = getattr(plan, "head_ops", 1)   # leading ops that take per-call pointers (td2_fa: two images)
+        heads = [plan.u8_op] if u8 else plan.ops[:nh]
+        last = plan.labels_op if labels else plan.ops[-1]
+        assert "img" in heads[0][1] and "out" in last[1] and not any(
+            a in ("img", "img2", "out") for _, args in plan.ops[nh:-1] for a in args if isinstance(a, str))
+        subst = {"img": img_ptr, "img2": img2_ptr, "out": out_ptr, "stream": stream.cuda_stream}
 
         def call(op, sub, main=None):
             fn, args = op
@@ -753,17 +967,19 @@ class Engine:
                 cap_main = torch.cuda.current_stream(self.device)
                 cap = {"stream": cap_main.cuda_stream,
                        "side": self.side_stream.cuda_stream if self.side_stream is not None else None}
-                for op in plan.ops[1:-1]:
+                for op in plan.ops[nh:-1]:
                     call(op, cap, cap_main)
             plan.graph = g
-        call(first, subst)
+        for op in heads:
+            call(op, subst)
         plan.graph.replay()
         call(last, subst)
 
-    def run(self, plan: FramePlan, img_ptr: int, out_ptr: int, stream: int, probe=None, labels=False, u8=False):
+    def run(self, plan: FramePlan, img_ptr: int, out_ptr: int, stream: int, probe=None, labels=False, u8=False,
+            img2_ptr=None):
         """Enqueue the frame.  probe = (op_name, event_before, event_after) brackets one op with CUDA
         events (bench.py times the dominant kernel live this way)."""
-        subst = {"img": img_ptr, "out": out_ptr, "stream": stream,
+        subst = {"img": img_ptr, "img2": img2_ptr, "out": out_ptr, "stream": stream,
                  "side": self.side_stream.cuda_stream if self.side_stream is not None else None}
         main = torch.cuda.current_stream(self.device) if self.side_stream is not None else None
         ops = plan.ops[:-1] + [plan.labels_op] if labels else plan.ops

@@ -1,5 +1,5 @@
-"""Architecture tables of the two temporally-distributed models and of the single-path PSPNet
-comparison model (product side).
+"""Architecture tables of the two temporally-distributed PSP models, of the single-path PSPNet
+comparison model and of TD2-FANet (product side).
 
 A declarative description of what the reference builds imperatively in
 Testing/model/pspnet/td4_psp18.py:29-121, td2_psp50.py:29-96, pspnet.py:31-157 and resnet.py:114-202: which
@@ -57,6 +57,8 @@ class ModelArch:
     nclass: int
     stems: Dict[int, List[Conv]] = field(default_factory=dict)
     stages: Dict[int, List[Block]] = field(default_factory=dict)
+    stage_ends: Tuple[int, ...] = ()   # td2_fa: index of the last block of layer1..4 (the FPN taps feat4..feat32)
+    c_exp: int = 1                     # td2_fa: block expansion (4 for the Bottleneck backbone)
 
     def prefix(self, path: int) -> str:
         """State-dict prefix of the path's backbone: `pretrained{path}` for the TD models, plain `pretrained`
@@ -112,7 +114,71 @@ def _backbone(prefix: str, backbone: str):
     return stem, blocks, 512 * exp
 
 
+FA_LEVELS = (32, 16, 8, 4)       # ffm_32 .. ffm_4 (td2_fa.py:56-63); level L reads the backbone tap feat<L>
+FA_DK = 32                       # FAModule w_qs / w_ks output channels (td2_fa.py:339-341)
+FA_OUT = 128                     # FAModule `smooth` output channels
+FA_KEY_STRIDE = 3                # Encoding.maxpool_k/v of the td2_fanet tree: MaxPool2d(kernel 1, stride 3)
+
+
+def _fa_backbone(prefix: str, backbone: str):
+    """The FANet ResNet (Training/ptsemseg/models/td2_fanet/resnet.py:113-145): 7x7 s2 stem + BN + LeakyReLU, maxpool,
+    four stages that ALL start with a stride-2 block (`[2, 2, 2, 2]`, :161-176), no dilation.  BasicBlock (:36-67):
+    conv3x3(stride) BN LeakyReLU, conv3x3 BN, + shortcut, ReLU; Bottleneck (:69-108) likewise with 1x1/3x3/1x1."""
+    kind, counts = BLOCKS[backbone]
+    exp = 4 if kind == "bottleneck" else 1
+    stem = [Conv(f"{prefix}.conv1", 3, 64, 7, stride=2, bn=f"{prefix}.bn1", act="leaky_relu")]
+    blocks: List[Block] = []
+    ends = []
+    inplanes = 64
+    for si, (planes, count) in enumerate(zip(STAGE_PLANES, counts)):
+        for bi in range(count):
+            p = f"{prefix}.layer{si + 1}.{bi}"
+            s = 2 if bi == 0 else 1
+            ds = None
+            if s != 1 or inplanes != planes * exp:
+                ds = Conv(f"{p}.downsample.0", inplanes, planes * exp, 1, stride=s, bn=f"{p}.downsample.1")
+            if kind == "basic":
+                convs = (Conv(f"{p}.conv1", inplanes, planes, 3, stride=s, bn=f"{p}.bn1", act="leaky_relu"),
+                         Conv(f"{p}.conv2", planes, planes, 3, bn=f"{p}.bn2", act="relu"))
+            else:
+                convs = (Conv(f"{p}.conv1", inplanes, planes, 1, bn=f"{p}.bn1", act="leaky_relu"),
+                         Conv(f"{p}.conv2", planes, planes, 3, stride=s, bn=f"{p}.bn2", act="leaky_relu"),
+                         Conv(f"{p}.conv3", planes, planes * 4, 1, bn=f"{p}.bn3", act="relu"))
+            blocks.append(Block(convs, ds))
+            inplanes = planes * exp
+        ends.append(len(blocks) - 1)
+    return stem, blocks, tuple(ends), exp
+
+
+def fa_module_convs(m: ModelArch, level: int, idx: int) -> Dict[str, Conv]:
+    """FAModule (td2_fa.py:334-349) of pyramid level `level` in sub-network `idx`: ConvBNReLU = conv without bias +
+    norm_layer(activation=...).  `up` is a 1x1 conv with padding 1 (:348): the engine handles the 1-pixel frame."""
+    c = STAGE_PLANES[3 - FA_LEVELS.index(level)] * (m.c_exp)
+    f = f"ffm_{level}_{idx}"
+
+    def cbr(name, cout, k=1, act="leaky_relu"):
+        return Conv(f"{f}.{name}.conv", c, cout, k, bn=f"{f}.{name}.bn", act=act)
+
+    return dict(w_qs=cbr("w_qs", FA_DK, act="none"), w_ks=cbr("w_ks", FA_DK, act="none"), w_vs=cbr("w_vs", c),
+                latlayer3=cbr("latlayer3", c), up=cbr("up", c // 2), smooth=cbr("smooth", FA_OUT, 3))
+
+
+def fa_head_convs(m: ModelArch, name: str, cin: int, mid: int) -> List[Conv]:
+    """FPNOutput (td2_fa.py:306-317): ConvBNReLU 3x3 (LeakyReLU) -> conv1x1 without bias."""
+    return [Conv(f"{name}.conv.conv", cin, mid, 3, bn=f"{name}.conv.bn", act="leaky_relu"),
+            Conv(f"{name}.conv_out", mid, m.nclass, 1)]
+
+
 def build_arch(arch: str, backbone: str, nclass: int) -> ModelArch:
+    if arch == "td2_fa":
+        if backbone not in ("resnet18", "resnet34", "resnet50"):
+            raise RuntimeError("unknown backbone: {}".format(backbone))      # td2_fa.py:48-49
+        # two sub-networks, no FIFO (both run on every call); Encoding(256, 64, 256), Attention(256, 64) (:66-69)
+        m = ModelArch(arch, backbone, 2, 0, 2 * FA_OUT, 64, 2 * FA_OUT, 2 * FA_OUT, nclass)
+        for idx in (1, 2):
+            m.stems[idx], m.stages[idx], m.stage_ends, exp = _fa_backbone(f"pretrained{idx}", backbone)
+        m.c_exp = exp
+        return m
     if arch == "pspnet":
         if backbone not in BLOCKS:
             raise RuntimeError("unknown backbone: {}".format(backbone))      # pspnet.py:67-68
@@ -151,6 +217,27 @@ def parameter_table(m: ModelArch, ln_shape=(97, 193)):
         t[p + ".running_mean"], t[p + ".running_var"] = ((ch,), "buffer"), ((ch,), "buffer")
         t[p + ".num_batches_tracked"] = ((), "long_buffer")
 
+    if m.arch == "td2_fa":   # td2_fa.py:53-79 (the FANet ResNet has no fc layer)
+        for idx in (1, 2):
+            for c in m.stems[idx]:
+                conv(c)
+            for b in m.stages[idx]:
+                for c in b.convs:
+                    conv(c)
+                if b.downsample:
+                    conv(b.downsample)
+            for level in FA_LEVELS:
+                for c in fa_module_convs(m, level, idx).values():
+                    conv(c)
+            for cs in encoding_convs(m, idx).values():
+                for c in cs:
+                    conv(c)
+            conv(fc_conv(m, f"atn{idx}"))
+            t[f"layer_norm{idx}.ln.weight"] = (tuple(ln_shape), "param")
+            t[f"layer_norm{idx}.ln.bias"] = (tuple(ln_shape), "param")
+            for c in fa_head_convs(m, f"head{idx}", m.d_v, m.head_mid) + fa_head_convs(m, f"head_aux{idx}", FA_OUT, 64):
+                conv(c)
+        return t
     for path in range(1, m.paths + 1):
         for c in m.stems[path]:
             conv(c)

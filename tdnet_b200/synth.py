@@ -20,6 +20,11 @@ import torch
 
 
 _RESIDUAL_TAIL_BN = re.compile(r"pretrained\d*\.layer\d+\.\d+\.(bn2|bn3)\.weight$")
+# TD2-FANet (td2_fa.py:334-349): the linear-attention branch sums over all pixels of the map, so its BatchNorm sees
+# inputs whose scale grows with the image; a trained network absorbs that in the running variance, the synthetic
+# one in a small gamma.  `smooth` feeds the 256-channel map the Encoding projections read.
+_FA_LATERAL_BN = re.compile(r"ffm_\d+_\d\.latlayer3\.bn\.weight$")
+_FA_SMOOTH_BN = re.compile(r"ffm_\d+_\d\.smooth\.bn\.weight$")
 
 
 def _gen_for(key: str, seed: int) -> torch.Generator:
@@ -57,6 +62,10 @@ def synth_tensor(key: str, ref: torch.Tensor, seed: int = 0) -> torch.Tensor:
             # Last BN of a residual block: keep the branch small so that the trunk does not double
             # its variance at every block (a trained network is calm; a random one is not).
             gamma = gamma * 0.3
+        elif _FA_LATERAL_BN.search(key):
+            gamma = gamma * 0.02
+        elif _FA_SMOOTH_BN.search(key):
+            gamma = gamma * 0.25
         return gamma
     if leaf == "bias":
         return torch.randn(shape, generator=g) * 0.1

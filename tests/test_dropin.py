@@ -67,3 +67,38 @@ def test_engine_plans_build_without_gpu():
         assert eng.pk == 4 * 6 and len(eng.k_slots) == 3  # P' = ceil(13/4) x ceil(21/4), FIFO depth 3
     with pytest.raises(RuntimeError, match="normalized_shape"):
         Engine(m, sd, 1, 64, 64, torch.device("cpu"), (h8, w8))
+
+
+def test_td2_fa_constructor_state_dict_and_pretrained_init(tmp_path):
+    """td2_fa (Training/ptsemseg/models/td2_fanet/td2_fa.py:16-85): constructor contract, state-dict layout, and
+    pretrained_init() (:246-274) which fills BOTH sub-networks from one single-path FANet checkpoint
+    (ptsemseg/utils.py:35-66: resnet. / ffm_*. / clslayer_8. / clslayer_32. key groups)."""
+    from tdnet_b200.model import td2_fa
+    from tdnet_b200.synth import synth_state_dict
+    net = td2_fa.td2_fa(nclass=19, backbone="resnet18", path_num=2)
+    sd = net.state_dict()
+    assert len(sd) == 616 and sd["layer_norm1.ln.weight"].shape == (96, 192)         # LayerNorm([96, 192]), :71-72
+    assert sd["ffm_32_1.up.conv.weight"].shape == (256, 512, 1, 1) and "pretrained1.fc.weight" not in sd
+    with pytest.raises(AssertionError):
+        td2_fa.td2_fa(nclass=19, backbone="resnet18", path_num=4)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        net.eval()([torch.zeros(1, 3, 64, 64)] * 2, pos_id=0)
+    # a single-path FANet checkpoint: sub-network 1 of a synthetic model, renamed to the single-path key groups
+    rename = {"pretrained1": "resnet", "ffm_32_1": "ffm_32", "ffm_16_1": "ffm_16", "ffm_8_1": "ffm_8",
+              "ffm_4_1": "ffm_4", "head1": "clslayer_8", "head_aux1": "clslayer_32"}
+    full = synth_state_dict(sd, seed=5)
+    single = {rename[k.split(".")[0]] + "." + k.split(".", 1)[1]: v for k, v in full.items() if k.split(".")[0] in rename}
+    path = tmp_path / "fanet.pth"
+    torch.save(single, path)
+    b = td2_fa.td2_fa(nclass=19, backbone="resnet18", path_num=2, mdl_path=str(path))
+    got = b.state_dict()
+    for k, v in full.items():
+        head = k.split(".")[0]
+        if head in rename:
+            twin = k.replace(head, head[:-1] + "2", 1)
+            assert torch.equal(got[k], v) and torch.equal(got[twin], v), k
+    assert not torch.equal(got["enc1.w_vs.0.conv.weight"], full["enc1.w_vs.0.conv.weight"])   # not in the checkpoint
+    del single["resnet.conv1.weight"]
+    torch.save(single, path)
+    with pytest.raises(RuntimeError, match="missing"):
+        td2_fa.td2_fa(nclass=19, backbone="resnet18", path_num=2, mdl_path=str(path))

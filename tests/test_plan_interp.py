@@ -1,0 +1,56 @@
+"""CPU: the host side of the frame engine (plan construction: op order, views, weight packing, folded BatchNorm,
+algebraic rewrites) executed by the CPU plan interpreter (tests/plan_interp.py) and compared with what the unmodified
+reference produced (tests/golden/*.npz).  No CUDA kernel runs here; kernels are checked by the -m gpu tests."""
+import numpy as np
+import pytest
+import torch
+
+from common import CH_STRIDE, FANET_GOLDEN_CASES, load_golden, max_abs
+from plan_interp import read, run_plan
+from tdnet_b200.engine import Engine
+from tdnet_b200.model import arch as A
+from tdnet_b200.synth import synth_clip, synth_state_dict
+
+
+def _nchw(view):
+    return read(view.ct()).permute(0, 3, 1, 2)
+
+
+@pytest.mark.parametrize("mode", ["tc", "simt"])
+@pytest.mark.parametrize("name", sorted(FANET_GOLDEN_CASES))
+def test_fanet_plan_matches_reference_golden(name, mode):
+    g, meta = load_golden(name)
+    H, W, n, calls = meta["H"], meta["W"], meta["batch"], meta["n_frames"]
+    m = A.build_arch("td2_fa", FANET_GOLDEN_CASES[name], 19)
+    h4, w4 = A.feature_hw(H, W)
+    tmpl = {k: torch.zeros(shape, dtype=torch.long if kind == "long_buffer" else torch.float32)
+            for k, (shape, kind) in A.parameter_table(m, (h4, w4)).items()}
+    sd = synth_state_dict(tmpl, seed=0)
+    eng = Engine(m, sd, n, H, W, torch.device("cpu"), (h4, w4), mode=mode)
+    frames = synth_clip(calls + 1, H, W, batch=n, clip_id=0)
+    tol = 2e-4
+    for i in range(calls):
+        plan = eng.plan(i % 2 + 1, True)
+        prev, cur = frames[i].contiguous(), frames[i + 1].contiguous()
+        out = torch.empty(n, 19, H, W)
+        run_plan(plan, {"img": cur.data_ptr(), "img2": prev.data_ptr(), "out": out.data_ptr()})
+        head = _nchw(plan.taps["head"])
+        assert max_abs(head, g[f"head_{i}"]) <= tol, (name, mode, i, max_abs(head, g[f"head_{i}"]))
+        if f"logits_{i}" in g:
+            assert max_abs(out, g[f"logits_{i}"]) <= tol
+    t, s = plan.taps, CH_STRIDE
+    for key, tap, stride in (("feat4", "feat4", 1), ("feat32", "feat32", s), ("up32", "up32", s), ("up16", "up16", s),
+                             ("sm16", "sm16", 1), ("up8", "up8", 1), ("sm4", "sm4", 1), ("v", "v", s),
+                             ("normed", "normed", s)):
+        got = _nchw(t[tap])[:, ::stride]
+        ref = g["tap_" + key]
+        assert tuple(got.shape) == ref.shape, key
+        assert max_abs(got, ref) <= tol * max(1.0, float(np.abs(ref).max())), (key, max_abs(got, ref))
+    q = read(t["q"].ct()).reshape(n, -1, 64)
+    assert max_abs(q, g["tap_q"]) <= tol
+    assert max_abs(read(t["k_sub"].ct()).reshape(n, -1, 64), g["tap_k_sub"]) <= tol
+    assert max_abs(read(t["v_sub"].ct()).reshape(n, -1, 256), g["tap_v_sub"]) <= tol
+    fused = _nchw(t["fused"])[:, ::s]
+    ref_fused = g["tap_atn"] + g["tap_v"]
+    assert max_abs(fused, ref_fused) <= tol * max(1.0, float(np.abs(ref_fused).max()))
+    assert int(eng.range_flag.item()) == 0
