@@ -284,9 +284,11 @@ int tdn_upsample_argmax(const tdn_tensor* in, uint8_t* labels, int32_t out_h, in
  *   (`F.normalize(key_, p=2, dim=1, eps=1e-12)`, `torch.matmul(key, value)`).  key is a [n,h,w,32] view, value
  *   [n,h,w,c]; f is dense fp32.  Two-stage fixed-order reduction (bit-reproducible); the caller provides
  *   tdn_fa_context_workspace_bytes(n,h,w,c) bytes of scratch.
- * tdn_fa_apply:  out[n][p][c] = sum_j normalize(query)[p][j] * f[n][j][c]              -- td2_fa.py:358-359, 367-371
+ * tdn_fa_apply:  out[n][p][c] = out_scale * sum_j normalize(query)[p][j] * f[n][j][c]  -- td2_fa.py:358-359, 367-371
  *   (query normalised over its 32 channels, `torch.matmul(query, f)`, permuted back to a map).  out is F32 or
- *   SPLIT16; *range_flag (optional) is OR-ed with 1 if a SPLIT16 output exceeded the fp16 range guard.
+ *   SPLIT16; *range_flag (optional) is OR-ed with 1 if a SPLIT16 output exceeded the fp16 range guard.  The sum
+ *   grows with the pixel count of the map: out_scale (a power of two, undone exactly by the caller in the scale of
+ *   the convolution that reads `out`) keeps SPLIT16 outputs in range at any image size.
  * tdn_add_upsampled: out = bilinear_align_corners(up -> out size) + (a + b)            -- td2_fa.py:373, 398-402
  *   (`p_feat = W_y + feat`, then `_upsample_add`); up may be NULL (out = a + b).  a, b, out have equal dims,
  *   up has the same n and c.
@@ -294,7 +296,8 @@ int tdn_upsample_argmax(const tdn_tensor* in, uint8_t* labels, int32_t out_h, in
 int tdn_fa_context(const tdn_tensor* key, const tdn_tensor* value, float* f, void* workspace,
                    uint64_t workspace_bytes, void* stream);
 uint64_t tdn_fa_context_workspace_bytes(int32_t n, int32_t h, int32_t w, int32_t c);
-int tdn_fa_apply(const tdn_tensor* query, const float* f, const tdn_tensor* out, int32_t* range_flag, void* stream);
+int tdn_fa_apply(const tdn_tensor* query, const float* f, const tdn_tensor* out, float out_scale, int32_t* range_flag,
+                 void* stream);
 int tdn_add_upsampled(const tdn_tensor* a, const tdn_tensor* b, const tdn_tensor* up, const tdn_tensor* out,
                       void* stream);
 

@@ -57,7 +57,7 @@ int stem_conv_pool_tc(const float*, const uint8_t*, const float*, int, int, int,
 int split16(const tdn_tensor*, const tdn_tensor*, cudaStream_t);
 int fa_context(const tdn_tensor*, const tdn_tensor*, float*, void*, size_t, cudaStream_t);
 size_t fa_context_workspace_bytes(int, int, int, int);
-int fa_apply(const tdn_tensor*, const float*, const tdn_tensor*, int*, cudaStream_t);
+int fa_apply(const tdn_tensor*, const float*, const tdn_tensor*, float, int*, cudaStream_t);
 int add_upsampled(const tdn_tensor*, const tdn_tensor*, const tdn_tensor*, const tdn_tensor*, cudaStream_t);
 int merge16(const tdn_tensor*, const tdn_tensor*, cudaStream_t);
 
@@ -225,8 +225,9 @@ uint64_t tdn_fa_context_workspace_bytes(int32_t n, int32_t h, int32_t w, int32_t
   return (uint64_t)fa_context_workspace_bytes(n, h, w, c);
 }
 
-int tdn_fa_apply(const tdn_tensor* query, const float* f, const tdn_tensor* out, int32_t* range_flag, void* stream) {
-  return fa_apply(query, f, out, range_flag, (cudaStream_t)stream);
+int tdn_fa_apply(const tdn_tensor* query, const float* f, const tdn_tensor* out, float out_scale, int32_t* range_flag,
+                 void* stream) {
+  return fa_apply(query, f, out, out_scale, range_flag, (cudaStream_t)stream);
 }
 
 int tdn_add_upsampled(const tdn_tensor* a, const tdn_tensor* b, const tdn_tensor* up, const tdn_tensor* out,

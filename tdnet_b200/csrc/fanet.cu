@@ -130,10 +130,12 @@ int fa_context(const tdn_tensor* key, const tdn_tensor* value, float* f, void* w
 
 // ---------------------------------------------------------------------------------------------
 // y[b][p][c] = sum_j qhat[b][p][j] * f[b][j][c]      (td2_fa.py:358-359, 367: query normalised over its 32
-// channels, y = matmul(query, f)); block = 64 pixels x 64 channels, 4 x 4 outputs per thread.
+// channels, y = matmul(query, f)); block = 64 pixels x 64 channels, 4 x 4 outputs per thread.  y grows with the
+// number of pixels of the map (f is an un-normalised sum over all of them): out_scale, a power of two the caller
+// undoes exactly in the scale of the convolution that follows, keeps a SPLIT16 output inside the fp16 range.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) fa_apply_kernel(View query, const float* __restrict__ f, View out,
-                                                       int* __restrict__ range_flag) {
+                                                       float out_scale, int* __restrict__ range_flag) {
   __shared__ __align__(16) float sq[FA_PX][FA_DK + 1];
   __shared__ __align__(16) float sf[FA_DK][FA_CT];
   const int p0 = blockIdx.x * FA_PX, c0 = blockIdx.y * FA_CT, b = blockIdx.z;
@@ -181,13 +183,16 @@ __global__ void __launch_bounds__(256) fa_apply_kernel(View query, const float* 
     const int p = p0 + pg + i * 16;
     if (p >= P) continue;
     const int y = p / out.w, x = p - y * out.w;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] *= out_scale;
     out_of_range |= fmaxf(fmaxf(fabsf(acc[i][0]), fabsf(acc[i][1])), fmaxf(fabsf(acc[i][2]), fabsf(acc[i][3]))) > 60000.f;
     st4(out, b * out.sn + y * out.sh + x * out.sw + c, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
   }
   if (out_of_range && out.split && range_flag) atomicOr(range_flag, 1);
 }
 
-int fa_apply(const tdn_tensor* query, const float* f, const tdn_tensor* out, int* range_flag, cudaStream_t stream) {
+int fa_apply(const tdn_tensor* query, const float* f, const tdn_tensor* out, float out_scale, int* range_flag,
+             cudaStream_t stream) {
   int rc;
   if ((rc = check_tensor(query, "fa_apply.query"))) return rc;
   if ((rc = check_tensor(out, "fa_apply.out"))) return rc;
@@ -197,9 +202,10 @@ int fa_apply(const tdn_tensor* query, const float* f, const tdn_tensor* out, int
   TDN_REQUIRE(query->n == out->n && query->h == out->h && query->w == out->w, TDN_ERR_INVALID,
               "fa_apply: query / output maps differ in size");
   TDN_REQUIRE(vec4_ok(*query) && vec4_ok(*out), TDN_ERR_INVALID, "fa_apply: float4-aligned views required");
+  TDN_REQUIRE(out_scale > 0.f, TDN_ERR_INVALID, "fa_apply: out_scale must be positive");
   const int P = query->h * query->w;
   fa_apply_kernel<<<dim3(ceil_div(P, FA_PX), ceil_div(out->c, FA_CT), query->n), 256, 0, stream>>>(
-      make_view(*query), f, make_view(*out), range_flag);
+      make_view(*query), f, make_view(*out), out_scale, range_flag);
   TDN_LAUNCH_OK();
   return TDN_OK;
 }

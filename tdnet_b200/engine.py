@@ -120,7 +120,7 @@ class PackedConv:
     per-channel (scale, bias) that folds the conv bias and the eval-mode BatchNorm:
         BN(conv(x) + b) = conv(x) * s + ((b - mean) * s + beta),  s = gamma / sqrt(var + eps)."""
 
-    def __init__(self, spec: A.Conv, sd: Dict[str, torch.Tensor], device, row_slice=None):
+    def __init__(self, spec: A.Conv, sd: Dict[str, torch.Tensor], device, row_slice=None, scale_mult=1.0):
         w = sd[spec.name + ".weight"].detach().to(torch.float32)
         cout = w.shape[0]
         bias = sd[spec.name + ".bias"].detach().float() if spec.bias else torch.zeros(cout)
@@ -131,6 +131,8 @@ class PackedConv:
             scale, shift = s, (bias - mu) * s + b
         else:
             scale, shift = None, (bias if spec.bias else None)
+        if scale_mult != 1.0:   # the input of this conv arrives pre-multiplied by 1/scale_mult (an exact power of two)
+            scale = (torch.ones(cout) if scale is None else scale) * scale_mult
         w = w.permute(0, 2, 3, 1).contiguous()  # [cout, kh, kw, cin]
         if w.shape[3] % 4:
             pad = 4 - w.shape[3] % 4
@@ -250,10 +252,12 @@ class Engine:
                         for p in ln_paths}
 
     # ------------------------------------------------------------------ helpers
-    def packed(self, spec: A.Conv, row_slice=None) -> PackedConv:
+    def packed(self, spec: A.Conv, row_slice=None, scale_mult=1.0) -> PackedConv:
         key = spec.name if row_slice is None else f"{spec.name}[{row_slice[0]}:{row_slice[1]}]"
+        if scale_mult != 1.0:
+            key += f"*{scale_mult}"
         if key not in self._packed:
-            self._packed[key] = PackedConv(spec, self.sd, self.device, row_slice)
+            self._packed[key] = PackedConv(spec, self.sd, self.device, row_slice, scale_mult)
         return self._packed[key]
 
     def stem_packed(self, spec: A.Conv):
@@ -709,12 +713,17 @@ class Engine:
         ws = torch.empty(max(ws_bytes // 4, 4), dtype=torch.float32, device=self.device)
         plan.add(lib.tdn_fa_context, C.byref(self._ct(plan, k)), C.byref(self._ct(plan, v)), f.data_ptr(), ws.data_ptr(),
                  ws_bytes, "stream", launches=2, name=f"ffm_{level}_{idx}.context")
+        # y is an un-normalised sum over all h*w pixels: stored as y * 2^-k (k from the pixel count, so that SPLIT16
+        # planes stay inside the fp16 range at any image size); latlayer3's folded scale carries the exact 2^k back
+        inv = 1
+        while inv * 64 < h * w:
+            inv *= 2
         y = self.buf(n, h, w, c)
         plan.add(lib.tdn_fa_apply, C.byref(self._ct(plan, q)), f.data_ptr(), C.byref(self._ct(plan, y)),
-                 self.range_flag.data_ptr(), "stream", name=f"ffm_{level}_{idx}.apply")
+                 C.c_float(1.0 / inv), self.range_flag.data_ptr(), "stream", name=f"ffm_{level}_{idx}.apply")
         plan.keep.append((f, ws))
         wy = self.buf(n, h, w, c)
-        self._conv(plan, self.packed(cv["latlayer3"]), y, wy)
+        self._conv(plan, self.packed(cv["latlayer3"], scale_mult=float(inv)), y, wy)
         p_feat = self.buf(n, h, w, c)
         plan.add(lib.tdn_add_upsampled, C.byref(self._ct(plan, wy)), C.byref(self._ct(plan, feat)),
                  C.byref(self._ct(plan, up_in)) if up_in is not None else None, C.byref(self._ct(plan, p_feat)), "stream")

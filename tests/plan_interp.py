@@ -182,13 +182,13 @@ def op_fa_context(key, value, f, ws, ws_bytes, stream):
     _flat(f, n * 32 * c, torch.float32).view(n, 32, c).copy_(kn.transpose(1, 2) @ v.reshape(n, h * w, c))
 
 
-def op_fa_apply(query, f, out, flag, stream):
+def op_fa_apply(query, f, out, out_scale, flag, stream):
     q = read(query._obj)
     n, h, w, _ = q.shape
     c = out._obj.c
     fm = _flat(f, n * 32 * c, torch.float32).view(n, 32, c)
     qn = F.normalize(q.reshape(n, h * w, 32), p=2, dim=2, eps=1e-12)
-    write(out._obj, (qn @ fm).reshape(n, h, w, c))
+    write(out._obj, (qn @ fm).reshape(n, h, w, c) * out_scale.value)
 
 
 def op_add_upsampled(a, b, up, out, stream):

@@ -74,7 +74,8 @@ def test_fa_linear_attention_kernels_against_torch(env, n, h, w, c, split):
     flag = torch.zeros(1, dtype=torch.int32, device="cuda")
     kt, vt, qt, yt = kv.ct(), vv.ct(), qv.ct(), yv.ct()
     cabi.check(lib.tdn_fa_context(C.byref(kt), C.byref(vt), f.data_ptr(), ws.data_ptr(), ws_bytes, None), "fa_context")
-    cabi.check(lib.tdn_fa_apply(C.byref(qt), f.data_ptr(), C.byref(yt), flag.data_ptr(), None), "fa_apply")
+    out_scale = 1.0 if h * w < 4096 else 2.0 ** -6          # an exact power of two applied to the stored output
+    cabi.check(lib.tdn_fa_apply(C.byref(qt), f.data_ptr(), C.byref(yt), out_scale, flag.data_ptr(), None), "fa_apply")
     torch.cuda.synchronize()
     kn = torch.nn.functional.normalize(k.double().reshape(n, h * w, 32), p=2, dim=2, eps=1e-12)
     qn = torch.nn.functional.normalize(q.double().reshape(n, h * w, 32), p=2, dim=2, eps=1e-12)
@@ -83,7 +84,7 @@ def test_fa_linear_attention_kernels_against_torch(env, n, h, w, c, split):
     scale = float(f_ref.abs().max())
     assert max_abs(f.cpu(), f_ref.cpu()) <= 2e-6 * scale + 1e-6, max_abs(f.cpu(), f_ref.cpu())
     yscale = float(y_ref.abs().max())
-    assert max_abs(yv.torch().cpu(), y_ref.cpu()) <= 4e-6 * yscale + 1e-6
+    assert max_abs(yv.torch().cpu() / out_scale, y_ref.cpu()) <= 4e-6 * yscale + 1e-6
     assert int(flag.item()) == 0
     # bit-reproducible: a second run gives identical sums (fixed-order reduction, no atomics)
     f2 = torch.empty_like(f)
