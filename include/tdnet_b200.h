@@ -214,6 +214,14 @@ int tdn_stem_conv_pool_tc(const float* nchw, const uint8_t* hwc_u8, const float*
                           const void* weight_tc, const float* scale, const float* bias, const tdn_tensor* out,
                           int32_t* range_flag, void* stream);
 
+/* Same kernel with the activation chosen by the caller: TDN_ACT_RELU, or TDN_ACT_LEAKY_RELU for the ResNet of the
+ * td2_fanet tree (Training/ptsemseg/models/td2_fanet/resnet.py:116-117, 136-138: conv1 -> norm_layer(64,
+ * activation='leaky_relu') -> maxpool).  With LeakyReLU the pool pads with -inf (outputs may be negative). */
+int tdn_stem_conv_pool_tc_act(const float* nchw, const uint8_t* hwc_u8, const float* lut, int32_t n, int32_t h,
+                              int32_t w, const void* weight_tc, const float* scale, const float* bias,
+                              const tdn_tensor* out, int32_t act, float leaky_slope, int32_t* range_flag,
+                              void* stream);
+
 /* F.max_pool2d(kernel 3, stride 2, padding 1) of the stem (resnet.py:137,208), NHWC fp32. */
 int tdn_maxpool3x3s2(const tdn_tensor* in, const tdn_tensor* out, void* stream);
 

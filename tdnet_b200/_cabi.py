@@ -74,6 +74,9 @@ SIGNATURES = {
                                         C.c_void_p, _TP, C.c_void_p]),
     "tdn_stem_conv_pool_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                         C.c_void_p, C.c_void_p, _TP, C.c_void_p, C.c_void_p]),
+    "tdn_stem_conv_pool_tc_act": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                            C.c_void_p, C.c_void_p, C.c_void_p, _TP, C.c_int32, C.c_float, C.c_void_p,
+                                            C.c_void_p]),
     "tdn_maxpool3x3s2": (C.c_int, [_TP, _TP, C.c_void_p]),
     "tdn_psp_pool": (C.c_int, [_TP, _TP, C.c_void_p, C.c_uint64, C.c_void_p]),
     "tdn_psp_pool_workspace_bytes": (C.c_uint64, [C.c_int32, C.c_int32, C.c_int32]),

@@ -53,7 +53,7 @@ int stem_conv_pool(const float*, const uint8_t*, const float*, int, int, int, co
                    const tdn_tensor*, cudaStream_t);
 int attention_tc(const tdn_attention_desc*, cudaStream_t);
 int stem_conv_pool_tc(const float*, const uint8_t*, const float*, int, int, int, const void*, const float*, const float*,
-                      const tdn_tensor*, int*, cudaStream_t);
+                      const tdn_tensor*, int, float, int*, cudaStream_t);
 int split16(const tdn_tensor*, const tdn_tensor*, cudaStream_t);
 int fa_context(const tdn_tensor*, const tdn_tensor*, float*, void*, size_t, cudaStream_t);
 size_t fa_context_workspace_bytes(int, int, int, int);
@@ -145,7 +145,19 @@ int tdn_stem_conv_pool_tc(const float* nchw, const uint8_t* hwc_u8, const float*
   if (arch == 0) arch = tdn_device_arch();
   if (arch < 0) return arch;
   TDN_REQUIRE(arch / 10 == 10, TDN_ERR_ARCH, "stem_conv_pool_tc: tcgen05 kernels need sm_100, device is sm_%d", arch);
-  return stem_conv_pool_tc(nchw, hwc_u8, lut, n, h, w, weight_tc, scale, bias, out, range_flag, (cudaStream_t)stream);
+  return stem_conv_pool_tc(nchw, hwc_u8, lut, n, h, w, weight_tc, scale, bias, out, TDN_ACT_RELU, 0.f, range_flag,
+                           (cudaStream_t)stream);
+}
+
+int tdn_stem_conv_pool_tc_act(const float* nchw, const uint8_t* hwc_u8, const float* lut, int32_t n, int32_t h, int32_t w,
+                              const void* weight_tc, const float* scale, const float* bias, const tdn_tensor* out,
+                              int32_t act, float leaky_slope, int32_t* range_flag, void* stream) {
+  static thread_local int arch = 0;
+  if (arch == 0) arch = tdn_device_arch();
+  if (arch < 0) return arch;
+  TDN_REQUIRE(arch / 10 == 10, TDN_ERR_ARCH, "stem_conv_pool_tc: tcgen05 kernels need sm_100, device is sm_%d", arch);
+  return stem_conv_pool_tc(nchw, hwc_u8, lut, n, h, w, weight_tc, scale, bias, out, act, leaky_slope, range_flag,
+                           (cudaStream_t)stream);
 }
 
 int tdn_stem_conv_pool_u8(const uint8_t* hwc, const float* lut, int32_t n, int32_t h, int32_t w, const float* weight,

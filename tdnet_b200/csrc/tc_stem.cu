@@ -50,6 +50,8 @@ struct TcStemParams {
   View out;               // pooled [n,Hp,Wp,64]
   int H, W, Hc, Wc, Hp, Wp;
   int PB;                 // pooled rows per CTA
+  int act;                // TDN_ACT_RELU (resnet.py:136) or TDN_ACT_LEAKY_RELU (the td2_fanet ResNet, resnet.py:117)
+  float slope;
   int* range_flag;
 };
 
@@ -71,6 +73,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_stem_kernel(const TcStemPara
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
+  const float pool_pad = p.act == TDN_ACT_RELU ? 0.f : -INFINITY;
   const int b = blockIdx.z;
   const int px0 = blockIdx.x * TS_PW, py0 = blockIdx.y * p.PB;
   const int npb = min(p.PB, p.Hp - py0);               // pooled rows of this CTA
@@ -154,12 +157,14 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_stem_kernel(const TcStemPara
       for (int q = 0; q < 16; ++q) {
         const uint32_t* v = q < 8 ? &v0[q * 4] : &v1[(q - 8) * 4];
         const int ch = q * 4;
-        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        // outside the conv map: the pool's padding.  0 cannot change a max of ReLU outputs; LeakyReLU outputs may be
+        // negative, so there the padding is -inf (every 3x3 window holds at least its centre, which is inside)
+        float4 o = make_float4(pool_pad, pool_pad, pool_pad, pool_pad);
         if (ok) {
-          o.x = fmaxf(fmaf(__uint_as_float(v[0]), s_sb[ch + 0], s_sb[64 + ch + 0]), 0.f);
-          o.y = fmaxf(fmaf(__uint_as_float(v[1]), s_sb[ch + 1], s_sb[64 + ch + 1]), 0.f);
-          o.z = fmaxf(fmaf(__uint_as_float(v[2]), s_sb[ch + 2], s_sb[64 + ch + 2]), 0.f);
-          o.w = fmaxf(fmaf(__uint_as_float(v[3]), s_sb[ch + 3], s_sb[64 + ch + 3]), 0.f);
+          o.x = tc_act(fmaf(__uint_as_float(v[0]), s_sb[ch + 0], s_sb[64 + ch + 0]), p.act, p.slope);
+          o.y = tc_act(fmaf(__uint_as_float(v[1]), s_sb[ch + 1], s_sb[64 + ch + 1]), p.act, p.slope);
+          o.z = tc_act(fmaf(__uint_as_float(v[2]), s_sb[ch + 2], s_sb[64 + ch + 2]), p.act, p.slope);
+          o.w = tc_act(fmaf(__uint_as_float(v[3]), s_sb[ch + 3], s_sb[64 + ch + 3]), p.act, p.slope);
         }
         *reinterpret_cast<float4*>(dst + ((q ^ (m & 15)) * 16)) = o;
       }
@@ -227,7 +232,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_stem_kernel(const TcStemPara
         const int pxl = item >> 4;
         const int px = px0 + pxl;
         if (px >= p.Wp) continue;
-        float4 mx = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 mx = make_float4(pool_pad, pool_pad, pool_pad, pool_pad);
 #pragma unroll
         for (int dx = 0; dx < 3; ++dx) {
           const int m = 2 * pxl + dx;
@@ -260,7 +265,9 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_stem_kernel(const TcStemPara
 
 int stem_conv_pool_tc(const float* nchw, const uint8_t* hwc_u8, const float* lut, int n, int h, int w,
                       const void* weight_tc, const float* scale, const float* bias, const tdn_tensor* out,
-                      int* range_flag, cudaStream_t stream) {
+                      int act, float slope, int* range_flag, cudaStream_t stream) {
+  TDN_REQUIRE(act == TDN_ACT_RELU || act == TDN_ACT_LEAKY_RELU, TDN_ERR_UNSUPPORTED,
+              "stem_tc: activation must be ReLU or LeakyReLU (max pooling commutes with neither 'none' padding rule)");
   TDN_REQUIRE((nchw != nullptr) != (hwc_u8 != nullptr), TDN_ERR_INVALID,
               "stem_tc: exactly one of the fp32 NCHW image and the uint8 HWC frame must be given");
   TDN_REQUIRE((nchw || lut) && weight_tc && scale && bias, TDN_ERR_INVALID, "stem_tc: null pointer");
@@ -276,6 +283,7 @@ int stem_conv_pool_tc(const float* nchw, const uint8_t* hwc_u8, const float* lut
   p.Hc = (h - 1) / 2 + 1; p.Wc = (w - 1) / 2 + 1;
   p.Hp = (p.Hc - 1) / 2 + 1; p.Wp = (p.Wc - 1) / 2 + 1;
   p.range_flag = range_flag;
+  p.act = act; p.slope = slope;
   TDN_REQUIRE(out->n == n && out->h == p.Hp && out->w == p.Wp && out->c == 64 && vec4_ok(*out), TDN_ERR_INVALID,
               "stem_tc: out must be a vector-aligned [n,%d,%d,64] view", p.Hp, p.Wp);
   static bool attr_set = false;

@@ -149,6 +149,23 @@ class PackedConv:
         self.bias = None if shift is None else shift.contiguous().to(device)
         self._tc = None
 
+    @staticmethod
+    def stacked(a: "PackedConv", b: "PackedConv", name: str) -> "PackedConv":
+        """Two convolutions that read the same input with the same geometry and activation, as one with the output
+        channels of `a` followed by those of `b` (one pass over the input instead of two)."""
+        import dataclasses
+        sa, sb = a.spec, b.spec
+        assert (sa.cin, sa.k, sa.stride, sa.dilation, sa.act) == (sb.cin, sb.k, sb.stride, sb.dilation, sb.act)
+        assert (a.scale is None) == (b.scale is None) and (a.bias is None) == (b.bias is None)
+        pc = PackedConv.__new__(PackedConv)
+        pc.spec = dataclasses.replace(sa, name=name, cout=sa.cout + sb.cout)
+        pc.cout, pc.cin = a.cout + b.cout, a.cin
+        pc.weight = torch.cat([a.weight, b.weight]).contiguous()
+        pc.scale = None if a.scale is None else torch.cat([a.scale, b.scale]).contiguous()
+        pc.bias = None if a.bias is None else torch.cat([a.bias, b.bias]).contiguous()
+        pc._tc = None
+        return pc
+
     def tc(self):
         """SPLIT16 form for the tcgen05 kernel: rows scaled by an exact power of two so that the lo
         plane stays in the normal fp16 range (max |w| of a row lands in [2^13, 2^14)), hi = fp16(w),
@@ -612,10 +629,16 @@ class Engine:
         a, b = path, 3 - path
         plan = FramePlan()
         self._cursor = {}
-        img_cur, img_prev = self.buf(n, H, W, 4, split=False), self.buf(n, H, W, 4, split=False)
-        plan.add(lib.tdn_image_to_nhwc, "img", n, 3, H, W, C.byref(self._ct(plan, img_cur)), "stream")
-        plan.add(lib.tdn_image_to_nhwc, "img2", n, 3, H, W, C.byref(self._ct(plan, img_prev)), "stream")
-        plan.head_ops = 2                                   # both touch per-call pointers: launched outside the graph
+        # the two ops that read the caller's images come first (they are launched outside the captured graph)
+        if self.tc and self.tc_stem:
+            # conv7x7 s2 + BN + LeakyReLU + maxpool fused on the tensor cores, straight from the NCHW images
+            x_cur, x_prev = self._fa_stem_tc(plan, a, "img"), self._fa_stem_tc(plan, b, "img2")
+            img_cur = img_prev = None
+        else:
+            img_cur, img_prev = self.buf(n, H, W, 4, split=False), self.buf(n, H, W, 4, split=False)
+            plan.add(lib.tdn_image_to_nhwc, "img", n, 3, H, W, C.byref(self._ct(plan, img_cur)), "stream")
+            plan.add(lib.tdn_image_to_nhwc, "img2", n, 3, H, W, C.byref(self._ct(plan, img_prev)), "stream")
+        plan.head_ops = 2
         enc_a, enc_b = A.encoding_convs(m, a), A.encoding_convs(m, b)
         fork = self.side_stream is not None
         if fork:
@@ -623,7 +646,9 @@ class Engine:
             plan.side = True
         # --- previous frame: sub-network b -> z -> Encoding(pre=True): K and V on the stride-3 grid
         #     (transformer.py:35-46; a 1x1 conv commutes with MaxPool2d(kernel 1, stride 3) = sub-sampling)
-        z_prev, taps_b = self._fa_subnet(plan, b, img_prev)
+        if img_prev is not None:
+            x_prev = self._fa_stem_simt(plan, b, img_prev)
+        z_prev, taps_b = self._fa_subnet(plan, b, x_prev)
         zs = z_prev.subsample(self.key_stride)
         k_mid = self.buf(n, self.hs, self.ws, m.d_k)
         self._conv(plan, self.packed(enc_b["w_ks"][0]), zs, k_mid)
@@ -635,7 +660,9 @@ class Engine:
         pre = self._fa_values(plan, a, v_tok)               # V' = fc(V): Attention.fc folded into the values
         plan.side = False
         # --- current frame: sub-network a -> z -> Encoding(pre=False): full-resolution Q and V
-        z_cur, taps_a = self._fa_subnet(plan, a, img_cur)
+        if img_cur is not None:
+            x_cur = self._fa_stem_simt(plan, a, img_cur)
+        z_cur, taps_a = self._fa_subnet(plan, a, x_cur)
         v_cur = self.buf(n, h4, w4, m.d_v)
         self._conv(plan, self.packed(enc_a["w_vs"][0]), z_cur, v_cur)
         q_mid = self.buf(n, h4, w4, m.d_k)
@@ -672,18 +699,32 @@ class Engine:
         assert x.sh == x.w * x.sw and x.sw == x.c
         return x._like(x.n, 1, x.h * x.w, x.c, x.sn, x.h * x.w * x.sw, x.sw, x.offset)
 
-    def _fa_subnet(self, plan: FramePlan, idx: int, img: View):
+    def _fa_stem_tc(self, plan: FramePlan, idx: int, img_key: str) -> View:
+        """Stem of sub-network idx (td2_fanet/resnet.py:116-118, 136-138) on tc_stem.cu; LeakyReLU outputs may be
+        negative, so the fused pool pads with -inf there."""
+        c = self.m.stems[idx][0]
+        oh, ow = self._out_hw(self.H, self.W, c)
+        y = self.buf(self.n, (oh - 1) // 2 + 1, (ow - 1) // 2 + 1, c.cout)
+        pk = self.stem_packed_tc(c)
+        plan.add(self.lib.tdn_stem_conv_pool_tc_act, img_key, None, None, self.n, self.H, self.W, pk["w"].data_ptr(),
+                 pk["scale"].data_ptr(), pk["bias"].data_ptr(), C.byref(self._ct(plan, y)), _ACT[c.act],
+                 C.c_float(0.01), self.range_flag.data_ptr(), "stream", name=c.name)
+        return y
+
+    def _fa_stem_simt(self, plan: FramePlan, idx: int, img: View) -> View:
+        """Same stem as the generic fp32 CUDA-core conv on the NHWC(4) image + the -inf padded max pool."""
+        c = self.m.stems[idx][0]
+        oh, ow = self._out_hw(img.h, img.w, c)
+        x = self.buf(self.n, oh, ow, c.cout)
+        self._conv(plan, self.packed(c), img, x)
+        y = self.buf(self.n, (oh - 1) // 2 + 1, (ow - 1) // 2 + 1, c.cout)
+        plan.add(self.lib.tdn_maxpool3x3s2, C.byref(self._ct(plan, x)), C.byref(self._ct(plan, y)), "stream")
+        return y
+
+    def _fa_subnet(self, plan: FramePlan, idx: int, y: View):
         """Backbone + the four fast-attention modules top-down (td2_fa.py:95-101) -> z = cat(up(smooth_16), smooth_4)
         (_upsample_cat :191-197): 256 channels at the feat4 resolution."""
         m, n, lib = self.m, self.n, self.lib
-        c = m.stems[idx][0]
-        # stem: conv7x7 s2 + BN + LeakyReLU on the fp32 CUDA-core kernel (3 input channels), then the -inf padded
-        # max pool (the fused stem kernels assume ReLU: their pool pads with 0)
-        oh, ow = self._out_hw(img.h, img.w, c)
-        x = self.buf(n, oh, ow, c.cout)
-        self._conv(plan, self.packed(c), img, x)
-        y = self.buf(n, (oh - 1) // 2 + 1, (ow - 1) // 2 + 1, c.cout)
-        plan.add(lib.tdn_maxpool3x3s2, C.byref(self._ct(plan, x)), C.byref(self._ct(plan, y)), "stream")
         feat4, feat8, feat16, feat32, _ = self._residual_blocks(plan, m.stages[idx], y, taps=m.stage_ends)
         z = self.buf(n, feat4.h, feat4.w, 2 * A.FA_OUT)
         up32, _ = self._fa_module(plan, 32, idx, feat32, None, True, False)
@@ -702,11 +743,14 @@ class Engine:
         m, n, lib = self.m, self.n, self.lib
         cv = A.fa_module_convs(m, level, idx)
         h, w, c = feat.h, feat.w, feat.c
-        q = self.buf(n, h, w, A.FA_DK, split=False)
-        k = self.buf(n, h, w, A.FA_DK, split=False)
+        # w_qs and w_ks (both 1x1 c -> 32, BN, no activation) as one 64-channel conv; q / k are channel slices
+        key = f"ffm_{level}_{idx}.w_qs+w_ks"
+        if key not in self._packed:
+            self._packed[key] = PackedConv.stacked(self.packed(cv["w_qs"]), self.packed(cv["w_ks"]), key)
+        qk = self.buf(n, h, w, 2 * A.FA_DK, split=False)
+        q, k = qk.channels(0, A.FA_DK), qk.channels(A.FA_DK, 2 * A.FA_DK)
         v = self.buf(n, h, w, c)
-        self._conv(plan, self.packed(cv["w_qs"]), feat, q)
-        self._conv(plan, self.packed(cv["w_ks"]), feat, k)
+        self._conv(plan, self._packed[key], feat, qk)
         self._conv(plan, self.packed(cv["w_vs"]), feat, v)
         f = torch.empty(n * A.FA_DK * c, dtype=torch.float32, device=self.device)
         ws_bytes = int(lib.tdn_fa_context_workspace_bytes(n, h, w, c))

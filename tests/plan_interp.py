@@ -81,6 +81,19 @@ def op_image_to_nhwc(nchw, n, c, h, w, out, stream):
     write(out._obj, o)
 
 
+def op_stem_conv_pool_tc_act(nchw, hwc_u8, lut, n, h, w, weight_tc, scale, bias, out, act, slope, flag, stream):
+    """include/tdnet_b200.h: weight_tc = fp16 [2 planes][7 ky][4 kx pairs][64 cout][2 kx][4 c] (zero for kx = 7, c = 3)."""
+    assert nchw and not hwc_u8
+    img = _flat(nchw, n * 3 * h * w, torch.float32).view(n, 3, h, w)
+    planes = _flat(weight_tc, 2 * 7 * 4 * 64 * 2 * 4, torch.float16).view(2, 7, 4, 64, 2, 4).float()
+    wt = (planes[0] + planes[1]).permute(2, 4, 0, 1, 3).reshape(64, 4, 7, 8)        # [cout][c][ky][kx]
+    assert float(wt[:, 3].abs().max()) == 0.0 and float(wt[:, :, :, 7].abs().max()) == 0.0
+    y = F.conv2d(img.double(), wt[:, :3, :, :7].double(), None, 2, 3).float()
+    y = y * _vec(scale, 64).view(1, 64, 1, 1) + _vec(bias, 64).view(1, 64, 1, 1)
+    y = _act(y, act, slope.value if hasattr(slope, "value") else slope)
+    write(out._obj, _nhwc(F.max_pool2d(y, 3, 2, 1)))
+
+
 def op_maxpool3x3s2(x, out, stream):
     write(out._obj, _nhwc(F.max_pool2d(_nchw(read(x._obj)), 3, 2, 1)))
 
@@ -224,7 +237,7 @@ def op_upsample_logits(x, out, H, W, stream):
 
 
 OPS = {
-    "tdn_image_to_nhwc": op_image_to_nhwc, "tdn_maxpool3x3s2": op_maxpool3x3s2, "tdn_conv2d": op_conv2d,
+    "tdn_image_to_nhwc": op_image_to_nhwc, "tdn_stem_conv_pool_tc_act": op_stem_conv_pool_tc_act, "tdn_maxpool3x3s2": op_maxpool3x3s2, "tdn_conv2d": op_conv2d,
     "tdn_conv2d_tc": op_conv2d_tc, "tdn_attention_tc": op_attention_tc, "tdn_softmax_rows": op_softmax_rows,
     "tdn_copy_nhwc": op_copy_nhwc, "tdn_bilinear_nhwc": op_bilinear_nhwc, "tdn_fa_context": op_fa_context,
     "tdn_fa_apply": op_fa_apply, "tdn_add_upsampled": op_add_upsampled,
