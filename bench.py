@@ -34,7 +34,7 @@ FRAME_GFLOP = 936.2            # algorithmic FLOPs of one frame 
 DOMINANT_GFLOP = 154.62        # layer4 3x3 512->512 dilated conv at 128x256
 ATTN_GFLOP = 77.31             # fused attention-propagation kernel, big hop: 2*32768*2048*(64+512)
 ATTN_EXECUTED_GFLOP = 3 * (68.72 + 2 * 8.59) + 2 * 8.59
-DOMINANT_TRAFFIC_BYTES = 110.4e6   # ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum (profiles/r01_*)
+DOMINANT_TRAFFIC_BYTES = 107.5e6   # ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum (profiles/r01_*)
 N_DISTINCT_FRAMES = 8
 
 
@@ -315,14 +315,14 @@ def run_ours(args, rank, world):
         roof = None
         if dom_ms:
             achieved = DOMINANT_GFLOP / dom_ms  # GFLOP / ms = TFLOP/s
-            roof = {"bound": "tensor", "kernel": f"tc_conv_kernel<128> ({dom_ms_name(net)}: 3x3 512->512 dilated, 128x256 map)",
+            roof = {"bound": "tensor", "kernel": f"tc_conv_pair_kernel<256> ({dom_ms_name(net)}: 3x3 512->512 dilated, 128x256 map; 2-CTA tcgen05 tiles M256xN256)",
                     "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
                     "traffic": DOMINANT_TRAFFIC_BYTES, "peak_source": peaks["source"], "ms_per_launch": dom_ms,
                     "executed_tflops": 3 * achieved, "executed_frac": 3 * achieved / peaks["tflops"],
                     "note": "achieved = algorithmic FLOPs (2*MAC of the reference conv, 154.62 GFLOP) / live CUDA-event "
                             "time of that launch inside running frames; the fp32-faithful exact mode executes 3 fp16 "
                             "tensor-core products per algorithmic product, so the ceiling of `frac` is 1/3; traffic = "
-                            "dram read+write bytes of one launch from profiles/r01_prof_conv_summary.txt"}
+                            "dram read+write bytes of one launch from profiles/r01_prof_conv_pair_summary.txt"}
         line = {
             "metric": "frames/sec at 1024x2048 (td4-psp18)", "value": fps, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": warm, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,

@@ -292,7 +292,9 @@ int conv2d_tc(const tdn_tc_conv_desc* d, cudaStream_t stream) {
   }
   const long long tiles128 = (long long)in.n * p.tiles_h * p.tiles_w * ceil_div(d->cout, 128);
   const int num_kb_host = taps * (in.c / TC_BLOCK_K);
-  int block_n = (d->cout <= 64 || (tiles128 < 2ll * g_num_sms && num_kb_host <= 24)) ? 64 : 128;
+  // Third case (TD2-FANet's stride-32/64 maps: 512-channel 3x3 convs on a few thousand pixels, 72 K blocks): when
+  // 128-wide tiles cover less than half of the SMs, N = 64 doubles the CTAs at work whatever the K length.
+  int block_n = (d->cout <= 64 || (tiles128 < 2ll * g_num_sms && num_kb_host <= 24) || 2 * tiles128 <= g_num_sms) ? 64 : 128;
   p.n_tiles_n = ceil_div(d->cout, block_n);
   long long num_tiles = (long long)in.n * p.tiles_h * p.tiles_w * p.n_tiles_n;
   TDN_REQUIRE(num_tiles < (1ll << 31), TDN_ERR_UNSUPPORTED, "conv2d_tc: too many tiles");
@@ -370,7 +372,12 @@ int conv2d_tc(const tdn_tc_conv_desc* d, cudaStream_t stream) {
     // measured (profiles/r01_tc_probe_pair.txt): layer 4 0.342 -> 0.308 ms, layer 3 0.106 -> 0.092 ms; the 1x1
     // 512 -> 512 GEMMs with only 8 K blocks per tile lose 8 % (fewer, longer tiles: 3.5 waves -> 4), N = 128
     // pair tiles are a wash
-    const bool pair_auto = d->cout % 256 == 0 && (pair_env > 0 || (pair_env < 0 && num_kb_host >= 16));
+    // ... and only when the M 256 x N 256 pair tiles fill at least one wave of the 74 clusters: on small maps
+    // (TD2-FANet layer 3 / 4 at 1024x2048: 32 / 16 pair tiles, measured 77 us per launch) the single-CTA kernel's
+    // smaller tiles keep more SMs busy.
+    const long long pair_tiles256 = ((long long)in.n * p.tiles_h * p.tiles_w + 1) / 2 * (d->cout / 256);
+    const bool pair_auto = d->cout % 256 == 0 && (pair_env > 0 || (pair_env < 0 && num_kb_host >= 16 &&
+                                                                    2 * pair_tiles256 >= g_num_sms));
     if (d->variant == TDN_TC_PAIR || (d->variant == TDN_TC_AUTO && pair_ok && pair_auto)) {
       const int pair_n = d->cout % 256 == 0 ? 256 : 128;
       // Wave quantisation experiment (TDNET_TC_PAIR_SPLIT=1, off by default): pair tiles are big (layer 4: 256
