@@ -174,6 +174,35 @@ def test_full_size_1024x2048_properties():
         assert torch.equal(again, outs[i]), i
 
 
+def test_baseline_config5_td4_resnet50_batch4_1024x2048_stream_independence():
+    """BASELINE configs[4] ('td4-psp50 1024x2048 batch=4 streams/GPU' = td4_psp18(backbone='resnet50'))
+    at full size, where the oracle would need minutes per frame: the size-independent property is that the lock-step
+    streams of a batch are independent -- stream s of the n=4 run must equal the same clip run alone (n=1), through
+    warm-up into steady state (FIFO depth 3, d_v = 2048, P' = 2048 keys, 13 TFLOP per batched frame)."""
+    H, W, n = 1024, 2048, 4
+    sd = make_weights("td4_psp18", "resnet50", 128, 256)
+    net = build_model("td4_psp18", "resnet50", 128, 256, sd)
+    frames = synth_clip(5, H, W, batch=n, clip_id=21)
+    for i, f in enumerate(frames):
+        out4 = net(f.cuda(), pos_id=i % 4)
+    torch.cuda.synchronize()
+    assert out4.shape == (n, 19, H, W) and torch.isfinite(out4).all()
+    assert net.V_queue[0].shape == (n, 2048, 2048) and len(net.K_queue) == 3
+    labels4 = net.forward_labels(frames[4].cuda(), pos_id=0)      # FIFO already advanced: only shape / dtype here
+    assert labels4.shape == (n, H, W) and labels4.dtype == torch.uint8
+    net.check_numeric_range()
+    worst = 0.0
+    for s_ in (0, 3):
+        net.reset()
+        for i, f in enumerate(frames):
+            out1 = net(f[s_:s_ + 1].contiguous().cuda(), pos_id=i % 4)
+        e = float((out1[0] - out4[s_]).abs().max())
+        worst = max(worst, e)
+        assert e <= LOGIT_TOL / 4, (s_, e)
+        assert (out1[0].argmax(0) != out4[s_].argmax(0)).float().mean().item() <= 1e-5
+    record("property/td4_resnet50_n4_1024x2048/stream_independence", max_abs=worst)
+
+
 def test_api_errors_match_reference_behaviour():
     from tdnet_b200.model import td4_psp18
     with pytest.raises(AssertionError):
