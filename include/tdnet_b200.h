@@ -274,6 +274,13 @@ uint64_t tdn_layernorm_hw_workspace_bytes(int32_t n, int32_t h, int32_t w, int32
 int tdn_layernorm_hw_apply(const tdn_tensor* x, const float* mean, const float* rstd,
                            const float* gamma, const float* beta, const tdn_tensor* out, void* stream);
 
+/* The nclass classifier, a 1x1 convolution to a handful of channels (td4_psp18.py:299 `nn.Conv2d(inter, out, 1)`,
+ * pspnet.py:113, td2_fa.py:316): out[p][j] = (sum_c in[p][c] * weight[j][c]) * scale[j] + bias[j] with
+ * out.c <= 32; weight is fp32 [out.c][in.c], scale / bias fp32 [out.c] or NULL.  Channels are summed in index
+ * order by one thread (bit-reproducible).  Same operator as tdn_conv2d with kh = kw = 1, without its tile waste. */
+int tdn_pointwise_linear(const tdn_tensor* in, const float* weight, const float* scale, const float* bias,
+                         const tdn_tensor* out, void* stream);
+
 /* Final F.interpolate(output, (H, W), bilinear, align_corners=True) (td4_psp18.py:227): NHWC fp32
  * low-resolution logits -> NCHW fp32 [n, c, H, W], the tensor test.py:53,61 consumes. */
 int tdn_upsample_logits(const tdn_tensor* in, float* out_nchw, int32_t out_h, int32_t out_w,

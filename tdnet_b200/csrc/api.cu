@@ -55,6 +55,7 @@ int attention_tc(const tdn_attention_desc*, cudaStream_t);
 int stem_conv_pool_tc(const float*, const uint8_t*, const float*, int, int, int, const void*, const float*, const float*,
                       const tdn_tensor*, int, float, int*, cudaStream_t);
 int split16(const tdn_tensor*, const tdn_tensor*, cudaStream_t);
+int pointwise_linear(const tdn_tensor*, const float*, const float*, const float*, const tdn_tensor*, cudaStream_t);
 int fa_context(const tdn_tensor*, const tdn_tensor*, float*, void*, size_t, cudaStream_t);
 size_t fa_context_workspace_bytes(int, int, int, int);
 int fa_apply(const tdn_tensor*, const float*, const tdn_tensor*, float, int*, cudaStream_t);
@@ -226,6 +227,11 @@ int tdn_upsample_logits(const tdn_tensor* in, float* out_nchw, int32_t out_h, in
 
 int tdn_upsample_argmax(const tdn_tensor* in, uint8_t* labels, int32_t out_h, int32_t out_w, void* stream) {
   return upsample_argmax(in, labels, out_h, out_w, (cudaStream_t)stream);
+}
+
+int tdn_pointwise_linear(const tdn_tensor* in, const float* weight, const float* scale, const float* bias,
+                         const tdn_tensor* out, void* stream) {
+  return pointwise_linear(in, weight, scale, bias, out, (cudaStream_t)stream);
 }
 
 int tdn_fa_context(const tdn_tensor* key, const tdn_tensor* value, float* f, void* workspace,

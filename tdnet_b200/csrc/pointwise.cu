@@ -586,6 +586,29 @@ __global__ void ln_partial_kernel(View x, double2* __restrict__ part, int chunks
   }
 }
 
+// Same partial sums (same order per channel, so bit-identical results), four channels per thread with 8- / 16-byte
+// loads for vector-aligned views: the scalar version issues one 2-byte load per plane and element.
+__global__ void ln_partial_vec4_kernel(View x, double2* __restrict__ part, int chunks) {
+  const int chunk = blockIdx.x, b = blockIdx.y;
+  const int P = x.h * x.w;
+  const int p0 = chunk * LN_CHUNK, p1 = min(p0 + LN_CHUNK, P);
+  for (int c = threadIdx.x * 4; c < x.c; c += blockDim.x * 4) {
+    double s[4] = {0.0, 0.0, 0.0, 0.0}, q[4] = {0.0, 0.0, 0.0, 0.0};
+    int y = p0 / x.w, xx = p0 - y * x.w;
+#pragma unroll 4
+    for (int p = p0; p < p1; ++p) {
+      const float4 v = ld4(x, b * x.sn + y * x.sh + xx * x.sw + c);
+      const double d0 = (double)v.x, d1 = (double)v.y, d2 = (double)v.z, d3 = (double)v.w;
+      s[0] += d0; q[0] += d0 * d0; s[1] += d1; q[1] += d1 * d1;
+      s[2] += d2; q[2] += d2 * d2; s[3] += d3; q[3] += d3 * d3;
+      if (++xx == x.w) { xx = 0; ++y; }
+    }
+    double2* dst = part + ((long long)b * chunks + chunk) * x.c + c;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dst[j] = make_double2(s[j], q[j]);
+  }
+}
+
 __global__ void __launch_bounds__(256) ln_final_kernel(const double2* __restrict__ part, int chunks, int C, int P,
                                                        float eps, float* __restrict__ mean,
                                                        float* __restrict__ rstd) {
@@ -624,8 +647,13 @@ int layernorm_hw_stats(const tdn_tensor* x, float* mean, float* rstd, float eps,
   size_t need = (size_t)x->n * chunks * x->c * sizeof(double2);
   TDN_REQUIRE(workspace && workspace_bytes >= need && aligned16(workspace), TDN_ERR_WORKSPACE,
               "layernorm_hw_stats: workspace %zu < %zu bytes", workspace_bytes, need);
-  int threads = x->c >= 256 ? 256 : 128;
-  ln_partial_kernel<<<dim3(chunks, x->n), threads, 0, stream>>>(make_view(*x), (double2*)workspace, chunks);
+  if (vec4_ok(*x)) {
+    int threads = x->c / 4 >= 256 ? 256 : (x->c / 4 >= 128 ? 128 : 64);
+    ln_partial_vec4_kernel<<<dim3(chunks, x->n), threads, 0, stream>>>(make_view(*x), (double2*)workspace, chunks);
+  } else {
+    int threads = x->c >= 256 ? 256 : 128;
+    ln_partial_kernel<<<dim3(chunks, x->n), threads, 0, stream>>>(make_view(*x), (double2*)workspace, chunks);
+  }
   TDN_LAUNCH_OK();
   ln_final_kernel<<<dim3(ceil_div(x->c, 32), x->n), 256, 0, stream>>>((const double2*)workspace, chunks, x->c, P,
                                                                      eps, mean, rstd);
@@ -670,6 +698,96 @@ int layernorm_hw_apply(const tdn_tensor* x, const float* mean, const float* rstd
   long long total = (long long)x->n * x->h * x->w * (x->c / 4);
   ln_apply_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(make_view(*x), make_view(*out), mean, rstd,
                                                             gamma, beta);
+  TDN_LAUNCH_OK();
+  return TDN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// 1x1 convolution to a handful of output channels (the nclass classifier, td4_psp18.py:299 / pspnet.py:113 /
+// td2_fa.py:316): out[p][j] = (sum_c in[p][c] * w[j][c]) * scale[j] + bias[j], cout <= 32.  A 128x64-tile GEMM
+// kernel wastes most of its tile on 19 columns and is latency-bound here (32 us at 128x256 pixels); this one stages
+// 64 pixels x 64 channels per step in shared memory (coalesced 16-byte loads) and gives every thread one pixel and a
+// group of ceil(cout / 4) classes, summing channels in index order (fixed order: bit-reproducible).
+// ---------------------------------------------------------------------------------------------
+constexpr int PL_PX = 64, PL_CK = 64, PL_MAXG = 8;
+
+__global__ void __launch_bounds__(256) pointwise_linear_kernel(View in, const float* __restrict__ w,
+                                                               const float* __restrict__ scale,
+                                                               const float* __restrict__ bias, View out, int cout,
+                                                               long long total_px) {
+  __shared__ float sx[PL_PX][PL_CK + 1];
+  __shared__ float sw[32][PL_CK + 1];
+  const int tid = threadIdx.x;
+  const long long p0 = (long long)blockIdx.x * PL_PX;
+  const int px = tid & (PL_PX - 1), grp = tid >> 6;           // 64 pixels x 4 class groups
+  const int cpg = (cout + 3) >> 2;                            // classes per group (<= 8)
+  const int j0 = grp * cpg;
+  float acc[PL_MAXG];
+#pragma unroll
+  for (int j = 0; j < PL_MAXG; ++j) acc[j] = 0.f;
+  const int hw = in.h * in.w;
+  for (int c0 = 0; c0 < in.c; c0 += PL_CK) {
+    // stage: 64 px x 16 float4 -> four rounds; weights: cout x 16 float4
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int idx = tid + r * 256;
+      const int sp = idx >> 4, q = idx & 15;
+      const long long p = p0 + sp;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p < total_px && c0 + q * 4 < in.c) {
+        const int b = (int)(p / hw);
+        const int rem = (int)(p - (long long)b * hw);
+        const int y = rem / in.w, x = rem - y * in.w;
+        v = ld4(in, b * in.sn + y * in.sh + x * in.sw + c0 + q * 4);
+      }
+      sx[sp][q * 4 + 0] = v.x; sx[sp][q * 4 + 1] = v.y; sx[sp][q * 4 + 2] = v.z; sx[sp][q * 4 + 3] = v.w;
+    }
+    for (int idx = tid; idx < cout * 16; idx += 256) {
+      const int j = idx >> 4, q = idx & 15;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c0 + q * 4 < in.c) v = *reinterpret_cast<const float4*>(w + (long long)j * in.c + c0 + q * 4);
+      sw[j][q * 4 + 0] = v.x; sw[j][q * 4 + 1] = v.y; sw[j][q * 4 + 2] = v.z; sw[j][q * 4 + 3] = v.w;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int c = 0; c < PL_CK; ++c) {
+      const float xv = sx[px][c];
+#pragma unroll
+      for (int j = 0; j < PL_MAXG; ++j)
+        if (j < cpg && j0 + j < cout) acc[j] = fmaf(xv, sw[j0 + j][c], acc[j]);
+    }
+    __syncthreads();
+  }
+  const long long p = p0 + px;
+  if (p >= total_px) return;
+  const int b = (int)(p / hw);
+  const int rem = (int)(p - (long long)b * hw);
+  const int y = rem / out.w, x = rem - y * out.w;
+  const long long o = b * out.sn + y * out.sh + x * out.sw;
+#pragma unroll
+  for (int j = 0; j < PL_MAXG; ++j) {
+    const int jj = j0 + j;
+    if (j < cpg && jj < cout) {
+      float v = acc[j];
+      if (scale) v *= scale[jj];
+      if (bias) v += bias[jj];
+      st1(out, o + jj, v);
+    }
+  }
+}
+
+int pointwise_linear(const tdn_tensor* in, const float* weight, const float* scale, const float* bias,
+                     const tdn_tensor* out, cudaStream_t stream) {
+  int rc;
+  if ((rc = check_tensor(in, "pointwise_linear.in"))) return rc;
+  if ((rc = check_tensor(out, "pointwise_linear.out"))) return rc;
+  TDN_REQUIRE(weight != nullptr && aligned16(weight), TDN_ERR_INVALID, "pointwise_linear: weight must be 16-byte aligned");
+  TDN_REQUIRE(out->c >= 1 && out->c <= 32, TDN_ERR_UNSUPPORTED, "pointwise_linear: 1..32 output channels, got %d", out->c);
+  TDN_REQUIRE(in->n == out->n && in->h == out->h && in->w == out->w, TDN_ERR_INVALID, "pointwise_linear: map size mismatch");
+  TDN_REQUIRE(vec4_ok(*in), TDN_ERR_INVALID, "pointwise_linear: float4-aligned input view required");
+  const long long total_px = (long long)in->n * in->h * in->w;
+  pointwise_linear_kernel<<<ceil_div(total_px, PL_PX), 256, 0, stream>>>(make_view(*in), weight, scale, bias,
+                                                                         make_view(*out), out->c, total_px);
   TDN_LAUNCH_OK();
   return TDN_OK;
 }

@@ -235,6 +235,8 @@ class Engine:
         self.fused_attn = os.environ.get("TDNET_B200_FUSED_ATTN", "1") != "0"
         self.tc_stride2 = os.environ.get("TDNET_B200_TC_STRIDE2", "1") != "0"
         self.fused_stem = os.environ.get("TDNET_B200_FUSED_STEM", "1") != "0"
+        self.fifo_overlap = os.environ.get("TDNET_B200_FIFO_OVERLAP", "1") != "0"   # FIFO push next to LN / head
+        self.small_linear = os.environ.get("TDNET_B200_SMALL_LINEAR", "1") != "0"   # classifier on tdn_pointwise_linear
         self.tc_stem = os.environ.get("TDNET_B200_TC_STEM", "1") != "0"   # tcgen05 stem (0.10 ms vs 0.39 ms on the fp32 pipe)
         use_side = os.environ.get("TDNET_B200_SIDE_STREAM", "1") != "0"
         self.side_stream = torch.cuda.Stream(device) if (use_side and device.type == "cuda") else None
@@ -337,6 +339,15 @@ class Engine:
         the geometry fits it (stride 1, cin % 64 == 0, SPLIT16 input); the fp32 CUDA-core kernel otherwise
         (3-channel stem, stride-2 convs, pooled PSP convs, the 19-class classifier)."""
         spec = pc.spec if pc is not None else None
+        if (self.small_linear and spec is not None and not kw and residual is None and spec.k == 1 and spec.stride == 1
+                and spec.act == "none" and pc.cout <= 32 and pc.cout % 8 != 0 and pc.cin == x.c and not out.split):
+            # the nclass classifier: a dedicated kernel instead of a 128x64-tile GEMM with 19 useful columns
+            plan.add(self.lib.tdn_pointwise_linear, C.byref(self._ct(plan, x)), pc.weight.data_ptr(),
+                     pc.scale.data_ptr() if pc.scale is not None else None,
+                     pc.bias.data_ptr() if pc.bias is not None else None, C.byref(self._ct(plan, out)), "stream",
+                     name=spec.name)
+            plan.keep.append(pc)
+            return
         if (self.tc and spec is not None and not kw and spec.stride in (1, 2) and x.split and x.c % 64 == 0
                 and (spec.stride == 1 or self.tc_stride2) and x.n * x.h * x.w >= 64 and out.sw % (8 if out.split else 4) == 0 and pc.cout % 8 == 0):
             return self._conv_tc(plan, x, out, pc=pc, residual=residual)
@@ -544,6 +555,31 @@ class Engine:
         else:
             fused = v_cur  # td4_psp18.py:142-143: head(layer_norm(v_cur)) while the FIFO fills
 
+        # --- Encoding(pre=True) on the stride-4 grid and FIFO push.  Every reader of the FIFO in this frame (the
+        #     prelude hops, the big hop) has been enqueued by now, and nothing below reads it: the push (a dozen tiny
+        #     launches) runs on the side stream next to LayerNorm / head and is joined before the final upsample, so
+        #     that the next frame's prelude (which forks after this frame's last op) sees the new entry.
+        push_fork = self.side_stream is not None and self.fifo_overlap
+        if push_fork:
+            plan.mark("fork")
+            plan.side = True
+        # (oldest slot is overwritten by shifting)
+        zs = z.subsample(4)
+        k_mid = self.buf(n, self.hs, self.ws, m.d_k)
+        self._conv(plan, self.packed(enc["w_ks"][0]), zs, k_mid)
+        for j in range(m.depth - 1):  # shift: slot j <- slot j+1
+            for slots in (self.q_slots, self.k_slots, self.v_slots):
+                plan.add(lib.tdn_copy_nhwc, C.byref(self._ct(plan, slots[j + 1])), C.byref(self._ct(plan, slots[j])),
+                         "stream")
+        last = m.depth - 1
+        k_new = self._grid_view(self.k_slots[last])
+        self._conv(plan, self.packed(enc["w_ks"][1]), k_mid, k_new)
+        plan.add(lib.tdn_copy_nhwc, C.byref(self._ct(plan, v_cur.subsample(4))),
+                 C.byref(self._ct(plan, self._grid_view(self.v_slots[last]))), "stream")
+        plan.add(lib.tdn_copy_nhwc, C.byref(self._ct(plan, q_cur.subsample(4))),
+                 C.byref(self._ct(plan, self._grid_view(self.q_slots[last]))), "stream")
+        plan.side = False
+
         # --- LayerNorm over (H8, W8) + FCN head
         mean = torch.empty(n * m.d_v, dtype=torch.float32, device=self.device)
         rstd = torch.empty_like(mean)
@@ -561,21 +597,8 @@ class Engine:
         self._conv(plan, self.packed(hc[0]), normed, mid)
         low = self.buf(n, h8, w8, m.nclass, split=False)
         self._conv(plan, self.packed(hc[1]), mid, low)
-        # --- Encoding(pre=True) on the stride-4 grid and FIFO push (oldest slot is overwritten by shifting)
-        zs = z.subsample(4)
-        k_mid = self.buf(n, self.hs, self.ws, m.d_k)
-        self._conv(plan, self.packed(enc["w_ks"][0]), zs, k_mid)
-        for j in range(m.depth - 1):  # shift: slot j <- slot j+1
-            for slots in (self.q_slots, self.k_slots, self.v_slots):
-                plan.add(lib.tdn_copy_nhwc, C.byref(self._ct(plan, slots[j + 1])), C.byref(self._ct(plan, slots[j])),
-                         "stream")
-        last = m.depth - 1
-        k_new = self._grid_view(self.k_slots[last])
-        self._conv(plan, self.packed(enc["w_ks"][1]), k_mid, k_new)
-        plan.add(lib.tdn_copy_nhwc, C.byref(self._ct(plan, v_cur.subsample(4))),
-                 C.byref(self._ct(plan, self._grid_view(self.v_slots[last]))), "stream")
-        plan.add(lib.tdn_copy_nhwc, C.byref(self._ct(plan, q_cur.subsample(4))),
-                 C.byref(self._ct(plan, self._grid_view(self.q_slots[last]))), "stream")
+        if push_fork:
+            plan.mark("join")
         # --- final x8 bilinear upsample into the caller's output tensor (last op: it is the only one besides
         #     the first that touches a per-call pointer, which keeps everything in between graph-capturable)
         plan.add(lib.tdn_upsample_logits, C.byref(self._ct(plan, low)), "out", H, W, "stream")

@@ -94,6 +94,50 @@ def op_stem_conv_pool_tc_act(nchw, hwc_u8, lut, n, h, w, weight_tc, scale, bias,
     write(out._obj, _nhwc(F.max_pool2d(y, 3, 2, 1)))
 
 
+def op_stem_conv_pool_tc(nchw, hwc_u8, lut, n, h, w, weight_tc, scale, bias, out, flag, stream):
+    op_stem_conv_pool_tc_act(nchw, hwc_u8, lut, n, h, w, weight_tc, scale, bias, out, _cabi.ACT_RELU, 0.0, flag, stream)
+
+
+def op_stem_conv_pool(nchw, n, h, w, weight, scale, bias, out, stream):
+    """fp32 CUDA-core stem: weight fp32 [147][64] with k = (c*7 + ky)*7 + kx; conv7x7 s2 p3 + BN + ReLU + maxpool."""
+    img = _flat(nchw, n * 3 * h * w, torch.float32).view(n, 3, h, w)
+    wt = _flat(weight, 147 * 64, torch.float32).view(3, 7, 7, 64).permute(3, 0, 1, 2)
+    y = F.conv2d(img, wt, None, 2, 3) * _vec(scale, 64).view(1, 64, 1, 1) + _vec(bias, 64).view(1, 64, 1, 1)
+    write(out._obj, _nhwc(F.max_pool2d(F.relu(y), 3, 2, 1)))
+
+
+PSP_BINS = (1, 2, 3, 6)
+
+
+def op_psp_pool(x, out, ws, ws_bytes, stream):
+    v = _nchw(read(x._obj))
+    n, c, h, _ = v.shape
+    assert ws_bytes >= n * h * 12 * c * 4
+    rows = [F.adaptive_avg_pool2d(v, b).permute(0, 2, 3, 1).reshape(n, b * b, c) for b in PSP_BINS]
+    write(out._obj, torch.cat(rows, 1).reshape(n, 1, 50, c))
+
+
+def op_psp_branch_convs(pooled, w, scale, bias, eighth, out, stream):
+    p = read(pooled._obj)                                  # [n,1,50,c4]
+    n, c4 = p.shape[0], p.shape[3]
+    off = 0
+    for i, b in enumerate(PSP_BINS):
+        wt = _flat(w[i], eighth * c4, torch.float32).view(eighth, c4)
+        y = p[:, 0, off:off + b * b] @ wt.t() * _vec(scale[i], eighth) + _vec(bias[i], eighth)
+        _flat(out[i], n * b * b * eighth, torch.float32).view(n, b * b, eighth).copy_(F.relu(y))
+        off += b * b
+
+
+def op_psp_concat(x, small, eighth, z, stream):
+    xv = read(x._obj)
+    n, h, w, cx = xv.shape
+    parts = [xv]
+    for i, b in enumerate(PSP_BINS):
+        sm = _flat(small[i], n * b * b * eighth, torch.float32).view(n, b, b, eighth)
+        parts.append(_bilinear(sm, h, w))
+    write(z._obj, torch.cat(parts, 3))
+
+
 def op_maxpool3x3s2(x, out, stream):
     write(out._obj, _nhwc(F.max_pool2d(_nchw(read(x._obj)), 3, 2, 1)))
 
@@ -173,6 +217,18 @@ def op_attention_tc(dref, stream):
     write(d.out, out.reshape(d.out.n, d.out.h, d.out.w, d.out.c))
 
 
+def op_pointwise_linear(x, weight, scale, bias, out, stream):
+    v = read(x._obj)
+    cout, cin = out._obj.c, x._obj.c
+    w = _flat(weight, cout * cin, torch.float32).view(cout, cin)
+    y = v @ w.t()
+    if scale:
+        y = y * _vec(scale, cout)
+    if bias:
+        y = y + _vec(bias, cout)
+    write(out._obj, y)
+
+
 def op_softmax_rows(s, rows, cols, ld, scale, stream):
     flat = _flat(s, (rows - 1) * ld + cols, torch.float32)
     m = torch.as_strided(flat, (rows, cols), (ld, 1))
@@ -237,9 +293,11 @@ def op_upsample_logits(x, out, H, W, stream):
 
 
 OPS = {
-    "tdn_image_to_nhwc": op_image_to_nhwc, "tdn_stem_conv_pool_tc_act": op_stem_conv_pool_tc_act, "tdn_maxpool3x3s2": op_maxpool3x3s2, "tdn_conv2d": op_conv2d,
+    "tdn_image_to_nhwc": op_image_to_nhwc, "tdn_stem_conv_pool_tc": op_stem_conv_pool_tc,
+    "tdn_stem_conv_pool": op_stem_conv_pool, "tdn_psp_pool": op_psp_pool, "tdn_psp_branch_convs": op_psp_branch_convs,
+    "tdn_psp_concat": op_psp_concat, "tdn_stem_conv_pool_tc_act": op_stem_conv_pool_tc_act, "tdn_maxpool3x3s2": op_maxpool3x3s2, "tdn_conv2d": op_conv2d,
     "tdn_conv2d_tc": op_conv2d_tc, "tdn_attention_tc": op_attention_tc, "tdn_softmax_rows": op_softmax_rows,
-    "tdn_copy_nhwc": op_copy_nhwc, "tdn_bilinear_nhwc": op_bilinear_nhwc, "tdn_fa_context": op_fa_context,
+    "tdn_copy_nhwc": op_copy_nhwc, "tdn_pointwise_linear": op_pointwise_linear, "tdn_bilinear_nhwc": op_bilinear_nhwc, "tdn_fa_context": op_fa_context,
     "tdn_fa_apply": op_fa_apply, "tdn_add_upsampled": op_add_upsampled,
     "tdn_layernorm_hw_stats": op_layernorm_hw_stats, "tdn_layernorm_hw_apply": op_layernorm_hw_apply,
     "tdn_upsample_logits": op_upsample_logits,

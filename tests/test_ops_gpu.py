@@ -651,3 +651,37 @@ def test_psp_branch_convs_one_launch(env):
         ref = F.relu(pooled[:, off:off + b * b] @ ws[i].t() * scs[i] + bis[i])
         assert max_abs(outs[i].cpu(), ref) < 5e-6
         off += b * b
+
+
+@pytest.mark.parametrize("split", [False, True])
+@pytest.mark.parametrize("n,h,w,cin,cout,affine", [(1, 13, 21, 128, 19, "bias"), (2, 16, 32, 256, 19, "none"),
+                                                   (1, 7, 9, 512, 21, "both"), (1, 128, 256, 128, 19, "bias"),
+                                                   (1, 5, 5, 64, 3, "bias")])
+def test_pointwise_linear_classifier_against_torch(env, n, h, w, cin, cout, affine, split):
+    """tdn_pointwise_linear == the nclass 1x1 classifier conv (td4_psp18.py:299, pspnet.py:113, td2_fa.py:316)."""
+    lib, cabi, View, dev = env
+    g = torch.Generator(device="cuda").manual_seed(cin + cout)
+    x = torch.randn(n, h, w, cin, generator=g, device="cuda") * 3
+    wt = torch.randn(cout, cin, generator=g, device="cuda") / cin ** 0.5
+    scale = torch.rand(cout, generator=g, device="cuda") + 0.5 if affine == "both" else None
+    bias = torch.randn(cout, generator=g, device="cuda") if affine in ("bias", "both") else None
+    xv = View.alloc(n, h, w, cin, dev, split=split)
+    if split:
+        xv.base.copy_(x.reshape(-1).half()); xv.lo.copy_((x.reshape(-1) - xv.base.float()).half())
+        x = xv.torch()
+    else:
+        xv.base.copy_(x.reshape(-1))
+    ov = View.alloc(n, h, w, cout, dev)
+    ov.base.fill_(float("nan"))
+    xt, ot = xv.ct(), ov.ct()
+    cabi.check(lib.tdn_pointwise_linear(C.byref(xt), wt.data_ptr(), scale.data_ptr() if scale is not None else None,
+                                        bias.data_ptr() if bias is not None else None, C.byref(ot), None), "linear")
+    torch.cuda.synchronize()
+    ref = x.double() @ wt.double().t()
+    if scale is not None:
+        ref = ref * scale.double()
+    if bias is not None:
+        ref = ref + bias.double()
+    assert max_abs(ov.torch().cpu(), ref.cpu()) <= 2e-6 * float(ref.abs().max()) + 1e-6
+    big = View.alloc(n, h, w, 64, dev).ct()
+    assert lib.tdn_pointwise_linear(C.byref(xt), wt.data_ptr(), None, None, C.byref(big), None) == -2   # cout > 32

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from common import CH_STRIDE, FANET_GOLDEN_CASES, load_golden, max_abs
+from common import CH_STRIDE, FANET_GOLDEN_CASES, GOLDEN_CASES, PSPNET_GOLDEN_CASES, load_golden, max_abs
 from plan_interp import read, run_plan
 from tdnet_b200.engine import Engine
 from tdnet_b200.model import arch as A
@@ -54,3 +54,54 @@ def test_fanet_plan_matches_reference_golden(name, mode):
     ref_fused = g["tap_atn"] + g["tap_v"]
     assert max_abs(fused, ref_fused) <= tol * max(1.0, float(np.abs(ref_fused).max()))
     assert int(eng.range_flag.item()) == 0
+
+
+def _synth_weights(m, ln_shape):
+    tmpl = {k: torch.zeros(shape, dtype=torch.long if kind == "long_buffer" else torch.float32)
+            for k, (shape, kind) in A.parameter_table(m, ln_shape).items()}
+    return synth_state_dict(tmpl, seed=0)
+
+
+@pytest.mark.parametrize("mode", ["tc", "simt"])
+@pytest.mark.parametrize("name", ["td4_r18_97x161", "td2_r50_64x128", "td4_r50_64x64_n2"])
+def test_td_plans_match_reference_golden(name, mode):
+    """Warm-up and steady plans of the TD models frame by frame, FIFO included (push order, shifts, slot views)."""
+    arch, backbone = GOLDEN_CASES[name]
+    g, meta = load_golden(name)
+    H, W, n = meta["H"], meta["W"], meta["batch"]
+    m = A.build_arch(arch, backbone, 19)
+    ln = (meta["h8"], meta["w8"])
+    eng = Engine(m, _synth_weights(m, ln), n, H, W, torch.device("cpu"), ln, mode=mode)
+    frames = synth_clip(meta["n_frames"], H, W, batch=n, clip_id=0)
+    for i, f in enumerate(frames):
+        plan = eng.plan(i % m.paths + 1, i >= m.depth)
+        img, out = f.contiguous(), torch.empty(n, 19, H, W)
+        run_plan(plan, {"img": img.data_ptr(), "out": out.data_ptr()})
+        err = max_abs(_nchw(plan.taps["head"]), g[f"head_{i}"])
+        assert err <= 2e-4, (name, mode, i, err)
+        if f"logits_{i}" in g:
+            assert max_abs(out, g[f"logits_{i}"]) <= 2e-4
+    s = CH_STRIDE
+    assert max_abs(_nchw(plan.taps["z"])[:, ::s], g["tap_z"]) <= 1e-3
+    assert max_abs(_nchw(plan.taps["normed"])[:, ::s], g["tap_normed"]) <= 1e-3
+    # the newest FIFO entry is what the reference queued (Encoding(pre=True), transformer.py:34-50)
+    assert max_abs(read(eng.k_slots[-1].ct()).reshape(n, -1, 64), g["tap_k_sub"]) <= 1e-3
+    assert max_abs(read(eng.v_slots[-1].ct()).reshape(n, -1, m.d_v), g["tap_v_sub"]) <= 1e-3
+    assert max_abs(read(eng.q_slots[-1].ct()).reshape(n, -1, 64), g["tap_q_sub"]) <= 1e-3
+    assert int(eng.range_flag.item()) == 0
+
+
+@pytest.mark.parametrize("name", sorted(PSPNET_GOLDEN_CASES))
+def test_pspnet_plan_matches_reference_golden(name):
+    g, meta = load_golden(name)
+    H, W, n = meta["H"], meta["W"], meta["batch"]
+    m = A.build_arch("pspnet", PSPNET_GOLDEN_CASES[name], 19)
+    eng = Engine(m, _synth_weights(m, (0, 0)), 1, H, W, torch.device("cpu"), (0, 0), mode="tc")
+    plan = eng.plan(1, True)
+    for i, f in enumerate(synth_clip(meta["n_frames"], H, W, batch=n, clip_id=0)):
+        img, out = f[-1:].contiguous(), torch.empty(1, 19, H, W)      # pspnet.py:74 `x = x[-1:]`
+        run_plan(plan, {"img": img.data_ptr(), "out": out.data_ptr()})
+        scale = max(1.0, float(np.abs(g[f"head_{i}"]).max()))
+        assert max_abs(_nchw(plan.taps["head"]), g[f"head_{i}"]) <= 2e-4 * scale
+        if f"logits_{i}" in g:
+            assert max_abs(out, g[f"logits_{i}"]) <= 2e-4 * scale

@@ -19,6 +19,10 @@ CONFIGS = [  # label, arch, backbone, H, W, batch
     ("configs[4] td4-psp50 1024x2048 n=2", "td4_psp18", "resnet50", 1024, 2048, 2),
     ("configs[4] td4-psp50 1024x2048 n=4", "td4_psp18", "resnet50", 1024, 2048, 4),
     ("pspnet-101 1024x2048 (comparison model, TEST_README.md:31)", "pspnet", "resnet101", 1024, 2048, 1),
+    # the size of the reference's published table (Testing/TEST_README.md:31-33, Titan Xp: 360 / 180 / 85 ms per frame)
+    ("published-table size: td4-psp18 769x1537", "td4_psp18", "resnet18", 769, 1537, 1),
+    ("published-table size: td2-psp50 769x1537", "td2_psp50", "resnet50", 769, 1537, 1),
+    ("published-table size: pspnet-101 769x1537", "pspnet", "resnet101", 769, 1537, 1),
 ]
 
 
