@@ -339,7 +339,7 @@ def run_ours(args, rank, world):
                            "api": "model.forward_labels(image, pos_id): fused upsample+arg-max, uint8 label map"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof,
             "roofline_attention": {
-                "bound": "tensor", "kernel": "tc_attn_kernel<256> (big hop: 32768 queries x 2048 keys, d_k 64, d_v 512)",
+                "bound": "tensor", "kernel": "tc_attn_kernel<256> + <128> tail launch (big hop: 32768 queries x 2048 keys, d_k 64, d_v 512; one tdn_attention_tc call)",
                 "achieved": ATTN_GFLOP / attn_ms, "peak": peaks["tflops"], "unit": "TFLOP/s",
                 "frac": ATTN_GFLOP / attn_ms / peaks["tflops"], "ms_per_launch": attn_ms,
                 "executed_tflops": ATTN_EXECUTED_GFLOP / attn_ms,

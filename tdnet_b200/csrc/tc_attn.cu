@@ -65,6 +65,7 @@ __device__ __forceinline__ float fast_exp2(float x) {
 struct AttnParams {
   int n_img, Pq, Pk;
   int q_tiles, dv_tiles, k_tiles, k_tiles1, num_items;   // k_tiles: 64-key tiles (pass 2); k_tiles1: 128-key tiles (pass 1)
+  int qt_begin;             // first query tile of this launch (q_tiles counts the tiles of the launch)
   float scale_log2;         // log2(e) / sqrt(d_k)
   __half* out_hi;
   __half* out_lo;
@@ -148,7 +149,7 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
         const int dvt = item % p.dv_tiles;
         int t = item / p.dv_tiles;
-        const int qt = t % p.q_tiles;
+        const int qt = p.qt_begin + t % p.q_tiles;
         const int img = t / p.q_tiles;
         mbar_wait(&bars->q_empty, qph ^ 1);
         mbar_expect_tx(&bars->q_full, 2 * AT_Q_PLANE);
@@ -305,7 +306,7 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       const int dvt = item % p.dv_tiles;
       int t = item / p.dv_tiles;
-      const int qt = t % p.q_tiles;
+      const int qt = p.qt_begin + t % p.q_tiles;
       const int img = t / p.q_tiles;
       const int q_idx = qt * AT_BQ + row;
       const bool valid = q_idx < p.Pq;
@@ -596,6 +597,38 @@ int attention_tc(const tdn_attention_desc* d, cudaStream_t stream) {
     int dev = 0;
     TDN_CUDA_OK(cudaGetDevice(&dev));
     TDN_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  // Wave quantisation: the persistent grid walks the items in rounds of one per SM, and a ragged last round
+  // costs a full item time (big hop at 1024x2048: 512 items on 148 SMs = 3.46 rounds -> 4).  When the item count
+  // is not a multiple of the SM count, the query tiles of the full rounds run as 256-wide items and the
+  // remaining query tiles as 128-wide ones (twice as many items of ~0.63x the work: QK^T and the softmax are
+  // recomputed per slice, P.V halves) in a second launch -- here 3 + 0.63 rounds instead of 4.  Both kernels
+  // compute every output element with the same products in the same order, so results do not depend on the
+  // split.  TDNET_ATTN_TAIL=0 disables it.
+  static int tail_env = -1;
+  if (tail_env < 0) {
+    const char* e = getenv("TDNET_ATTN_TAIL");
+    tail_env = e ? atoi(e) : 1;
+  }
+  if (dvt_size == 256 && tail_env && p.num_items > num_sms && p.num_items % num_sms != 0) {
+    const int per_qt = d->n * p.dv_tiles;                                   // 256-wide items per query tile
+    const int q1 = (p.num_items / num_sms) * num_sms / per_qt;              // query tiles of the full rounds
+    const int q2 = p.q_tiles - q1;
+    const long long items1 = (long long)q1 * per_qt, items2 = (long long)q2 * d->n * (d->d_v / 128);
+    const double cost_plain = (double)ceil_div(p.num_items, num_sms);
+    const double cost_split = (double)ceil_div(items1, num_sms) + 0.63 * (double)ceil_div(items2, num_sms) + 0.1;
+    if (q1 > 0 && q2 > 0 && cost_split < cost_plain) {
+      AttnParams p1 = p, p2 = p;
+      p1.q_tiles = q1; p1.num_items = (int)items1;
+      p2.qt_begin = q1; p2.q_tiles = q2; p2.dv_tiles = d->d_v / 128; p2.num_items = (int)items2;
+      const int g1 = p1.num_items < num_sms ? p1.num_items : num_sms;
+      const int g2 = p2.num_items < num_sms ? p2.num_items : num_sms;
+      tc_attn_kernel<256><<<g1, AT_THREADS, AT_SMEM_BYTES, stream>>>(mq_h, mq_l, mk_h, mk_l, mv_h, mv_l, p1);
+      TDN_LAUNCH_OK();
+      tc_attn_kernel<128><<<g2, AT_THREADS, AT_SMEM_BYTES, stream>>>(mq_h, mq_l, mk_h, mk_l, mv_h, mv_l, p2);
+      TDN_LAUNCH_OK();
+      return TDN_OK;
+    }
   }
   int grid = p.num_items < num_sms ? p.num_items : num_sms;
   if (dvt_size == 256)

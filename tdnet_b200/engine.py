@@ -857,7 +857,8 @@ class Engine:
             d.out, d.residual = out_tok.ct(), res_tok.ct()
             d.n, d.pq, d.pk, d.d_k, d.d_v = n, pq, pk, m.d_k, m.d_v
             d.range_flag = self.range_flag.data_ptr()
-            plan.add(lib.tdn_attention_tc, C.byref(d), "stream", name=f"atn{idx}.attention")
+            plan.add(lib.tdn_attention_tc, C.byref(d), "stream", name=f"atn{idx}.attention",
+                     launches=self._attention_launches(n, pq, m.d_v))
             plan.keep.append((d, q_all, k_tok, vpt, out_tok, res_tok))
             return out
         vp = pre["vp"]
@@ -977,7 +978,8 @@ class Engine:
                 d.out, d.residual = out_tok.ct(), res_tok.ct()
                 d.n, d.pq, d.pk, d.d_k, d.d_v = n, pq, pk, m.d_k, m.d_v
                 d.range_flag = self.range_flag.data_ptr()
-                plan.add(lib.tdn_attention_tc, C.byref(d), "stream", name=name + ".attention")
+                plan.add(lib.tdn_attention_tc, C.byref(d), "stream", name=name + ".attention",
+                         launches=self._attention_launches(n, pq, m.d_v))
                 plan.keep.append((d, q_all, k_slot, vpt, out_tok, res_tok))
                 carry = out
                 continue
@@ -995,6 +997,23 @@ class Engine:
                           name=name + ".pv")
             carry = out
         return carry
+
+    def _attention_launches(self, n: int, pq: int, d_v: int) -> int:
+        """Kernels one tdn_attention_tc call launches (bench.py's gpu_launches): 2 when the library runs the ragged
+        last round of 256-channel items as a second launch of 128-channel items (tc_attn.cu, attention_tc())."""
+        import os
+        sms = torch.cuda.get_device_properties(self.device).multi_processor_count if self.device.type == "cuda" else 148
+        if d_v % 256 or os.environ.get("TDNET_ATTN_TAIL", "1") == "0":
+            return 1
+        q_tiles, per_qt = (pq + 127) // 128, n * (d_v // 256)
+        items = q_tiles * per_qt
+        if items <= sms or items % sms == 0:
+            return 1
+        q1 = items // sms * sms // per_qt
+        q2 = q_tiles - q1
+        rounds = lambda x: (x + sms - 1) // sms  # noqa: E731
+        split = rounds(q1 * per_qt) + 0.63 * rounds(q2 * n * (d_v // 128)) + 0.1
+        return 2 if (q1 > 0 and q2 > 0 and split < rounds(items)) else 1
 
     def _fc_as_activation(self, fc: PackedConv):
         """Attention.fc weight [d_v, d_v] as a SPLIT16 'activation' [1,1,d_v,d_v] (A operand of the
