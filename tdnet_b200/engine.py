@@ -1012,7 +1012,7 @@ class Engine:
         q1 = items // sms * sms // per_qt
         q2 = q_tiles - q1
         rounds = lambda x: (x + sms - 1) // sms  # noqa: E731
-        split = rounds(q1 * per_qt) + 0.63 * rounds(q2 * n * (d_v // 128)) + 0.1
+        split = rounds(q1 * per_qt) + 0.8 * rounds(q2 * n * (d_v // 128))
         return 2 if (q1 > 0 and q2 > 0 and split < rounds(items)) else 1
 
     def _fc_as_activation(self, fc: PackedConv):
