@@ -27,7 +27,7 @@
 // TMEM: S double-buffered 2 x 64 columns, O DVT columns.  Shared memory: Q 32 KB, K ring 2 x 16 KB,
 // V ring 3 x 32 KB (128-row halves of the V'^T tile), P double buffer 2 x 32 KB (hi+lo planes each).
 #include "common.cuh"
-#include "tc_ptx.cuh"
+#include "tc_common.cuh"   // tc_launch / tc_pdl_sync (programmatic dependent launch); pulls in tc_ptx.cuh
 
 #include <string.h>
 #include <cuda.h>
@@ -135,6 +135,7 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_ptr;
+  tc_pdl_sync();
   const uint32_t tmem_S = tmem_base;            // + buf * 64
   const uint32_t tmem_O = tmem_base + 128;
   const int T = p.k_tiles;
@@ -624,19 +625,16 @@ int attention_tc(const tdn_attention_desc* d, cudaStream_t stream) {
       p2.qt_begin = q1; p2.q_tiles = q2; p2.dv_tiles = d->d_v / 128; p2.num_items = (int)items2;
       const int g1 = p1.num_items < num_sms ? p1.num_items : num_sms;
       const int g2 = p2.num_items < num_sms ? p2.num_items : num_sms;
-      tc_attn_kernel<256><<<g1, AT_THREADS, AT_SMEM_BYTES, stream>>>(mq_h, mq_l, mk_h, mk_l, mv_h, mv_l, p1);
-      TDN_LAUNCH_OK();
-      tc_attn_kernel<128><<<g2, AT_THREADS, AT_SMEM_BYTES, stream>>>(mq_h, mq_l, mk_h, mk_l, mv_h, mv_l, p2);
-      TDN_LAUNCH_OK();
+      TDN_CUDA_OK(tc_launch(tc_attn_kernel<256>, g1, AT_THREADS, AT_SMEM_BYTES, stream, mq_h, mq_l, mk_h, mk_l, mv_h, mv_l, p1));
+      TDN_CUDA_OK(tc_launch(tc_attn_kernel<128>, g2, AT_THREADS, AT_SMEM_BYTES, stream, mq_h, mq_l, mk_h, mk_l, mv_h, mv_l, p2));
       return TDN_OK;
     }
   }
   int grid = p.num_items < num_sms ? p.num_items : num_sms;
   if (dvt_size == 256)
-    tc_attn_kernel<256><<<grid, AT_THREADS, AT_SMEM_BYTES, stream>>>(mq_h, mq_l, mk_h, mk_l, mv_h, mv_l, p);
+    TDN_CUDA_OK(tc_launch(tc_attn_kernel<256>, grid, AT_THREADS, AT_SMEM_BYTES, stream, mq_h, mq_l, mk_h, mk_l, mv_h, mv_l, p));
   else
-    tc_attn_kernel<128><<<grid, AT_THREADS, AT_SMEM_BYTES, stream>>>(mq_h, mq_l, mk_h, mk_l, mv_h, mv_l, p);
-  TDN_LAUNCH_OK();
+    TDN_CUDA_OK(tc_launch(tc_attn_kernel<128>, grid, AT_THREADS, AT_SMEM_BYTES, stream, mq_h, mq_l, mk_h, mk_l, mv_h, mv_l, p));
   return TDN_OK;
 }
 

@@ -5,6 +5,8 @@
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
+#include <stdlib.h>
+
 namespace tdn {
 
 using namespace ptx;
@@ -39,6 +41,41 @@ struct TcParams {
   long long rsn, rsh, rsw;
   int* range_flag;
 };
+
+// Launch of a persistent tcgen05 kernel with programmatic dependent launch (TDNET_PDL=0 turns it off): the kernel's
+// setup overlaps the tail of the previous kernel in the stream; every such kernel calls tc_pdl_sync() after its setup
+// and before it touches global memory.  Safe next to any predecessor: a kernel that never triggers its dependents
+// early releases them when it completes, which is the ordinary stream order.
+inline bool tc_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TDNET_PDL");
+    v = e ? (atoi(e) != 0) : 1;
+  }
+  return v != 0;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t tc_launch(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream,
+                             Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = tc_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<Args&&>(args)...);
+}
+
+// After the kernel's setup: wait for the producers of our inputs, then let the next kernel begin its own setup.
+__device__ __forceinline__ void tc_pdl_sync() {
+  griddep_wait();
+  griddep_launch_dependents();
+}
 
 __device__ __forceinline__ float tc_act(float v, int act, float slope) {
   if (act == TDN_ACT_RELU) return fmaxf(v, 0.f);

@@ -89,6 +89,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  tc_pdl_sync();
 
   if (warp == 0) {
     // ======================= TMA producer =======================
@@ -241,8 +242,7 @@ static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUt
   }
   const int todo = p.num_tiles - p.tile_begin;
   int grid = todo < g_num_sms ? todo : g_num_sms;
-  tc_conv_kernel<BLOCK_N><<<grid, TC_THREADS, Cfg::SMEM_BYTES, stream>>>(a_hi, a_lo, b_hi, b_lo, p);
-  TDN_LAUNCH_OK();
+  TDN_CUDA_OK(tc_launch(tc_conv_kernel<BLOCK_N>, grid, TC_THREADS, Cfg::SMEM_BYTES, stream, a_hi, a_lo, b_hi, b_lo, p));
   return TDN_OK;
 }
 

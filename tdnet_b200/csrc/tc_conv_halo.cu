@@ -81,6 +81,7 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  tc_pdl_sync();
 
   if (warp == 0) {
     // ======================= TMA producer =======================
@@ -192,7 +193,7 @@ static int launch_halo(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const C
     attr_smem = 232448;
   }
   int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
-  tc_conv_halo_kernel<BLOCK_N><<<grid, TC_THREADS, smem, stream>>>(a_hi, a_lo, b_hi, b_lo, p, g);
+  TDN_CUDA_OK(tc_launch(tc_conv_halo_kernel<BLOCK_N>, grid, TC_THREADS, smem, stream, a_hi, a_lo, b_hi, b_lo, p, g));
   TDN_LAUNCH_OK();
   return TDN_OK;
 }

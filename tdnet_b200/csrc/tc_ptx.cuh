@@ -252,5 +252,13 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
          | ((uint32_t)(M >> 4) << 24);  // m_dim
 }
 
+// Programmatic dependent launch.  `griddep_wait` blocks until every grid this one depends on has completed and its
+// memory is visible (returns at once when the kernel was launched without a programmatic dependency);
+// `griddep_launch_dependents` lets the next kernel of the stream -- if it was launched with the programmatic-
+// serialisation attribute -- start its CTAs as soon as SMs free up, so that its prologue (barrier init, TMEM
+// allocation, tensor-map prefetch) overlaps this kernel's tail instead of following it.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 }  // namespace ptx
 }  // namespace tdn
