@@ -625,16 +625,16 @@ int attention_tc(const tdn_attention_desc* d, cudaStream_t stream) {
       p2.qt_begin = q1; p2.q_tiles = q2; p2.dv_tiles = d->d_v / 128; p2.num_items = (int)items2;
       const int g1 = p1.num_items < num_sms ? p1.num_items : num_sms;
       const int g2 = p2.num_items < num_sms ? p2.num_items : num_sms;
-      TDN_CUDA_OK(tc_launch(tc_attn_kernel<256>, g1, AT_THREADS, AT_SMEM_BYTES, stream, mq_h, mq_l, mk_h, mk_l, mv_h, mv_l, p1));
-      TDN_CUDA_OK(tc_launch(tc_attn_kernel<128>, g2, AT_THREADS, AT_SMEM_BYTES, stream, mq_h, mq_l, mk_h, mk_l, mv_h, mv_l, p2));
+      TDN_CUDA_OK(tc_launch(tc_attn_kernel<256>, g1, AT_THREADS, AT_SMEM_BYTES, stream, p1.num_items <= 2 * g1, mq_h, mq_l, mk_h, mk_l, mv_h, mv_l, p1));
+      TDN_CUDA_OK(tc_launch(tc_attn_kernel<128>, g2, AT_THREADS, AT_SMEM_BYTES, stream, p2.num_items <= 2 * g2, mq_h, mq_l, mk_h, mk_l, mv_h, mv_l, p2));
       return TDN_OK;
     }
   }
   int grid = p.num_items < num_sms ? p.num_items : num_sms;
   if (dvt_size == 256)
-    TDN_CUDA_OK(tc_launch(tc_attn_kernel<256>, grid, AT_THREADS, AT_SMEM_BYTES, stream, mq_h, mq_l, mk_h, mk_l, mv_h, mv_l, p));
+    TDN_CUDA_OK(tc_launch(tc_attn_kernel<256>, grid, AT_THREADS, AT_SMEM_BYTES, stream, p.num_items <= 2 * grid, mq_h, mq_l, mk_h, mk_l, mv_h, mv_l, p));
   else
-    TDN_CUDA_OK(tc_launch(tc_attn_kernel<128>, grid, AT_THREADS, AT_SMEM_BYTES, stream, mq_h, mq_l, mk_h, mk_l, mv_h, mv_l, p));
+    TDN_CUDA_OK(tc_launch(tc_attn_kernel<128>, grid, AT_THREADS, AT_SMEM_BYTES, stream, p.num_items <= 2 * grid, mq_h, mq_l, mk_h, mk_l, mv_h, mv_l, p));
   return TDN_OK;
 }
 

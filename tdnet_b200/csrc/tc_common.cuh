@@ -42,22 +42,25 @@ struct TcParams {
   int* range_flag;
 };
 
-// Launch of a persistent tcgen05 kernel with programmatic dependent launch (TDNET_PDL=0 turns it off): the kernel's
-// setup overlaps the tail of the previous kernel in the stream; every such kernel calls tc_pdl_sync() after its setup
-// and before it touches global memory.  Safe next to any predecessor: a kernel that never triggers its dependents
-// early releases them when it completes, which is the ordinary stream order.
-inline bool tc_pdl_enabled() {
+// Launch of a persistent tcgen05 kernel, optionally with programmatic dependent launch: the kernel's setup (barrier
+// init, TMEM allocation, tensor-map prefetch) overlaps the tail of the previous kernel in the stream; every such kernel
+// calls tc_pdl_sync() after its setup and before it touches global memory.  Safe next to any predecessor: a kernel
+// that never triggers its dependents early releases them when it completes, which is the ordinary stream order.
+// Measured on B200: launches of a few tiles per CTA gain (TD2-FANet call 1.874 -> 1.823 ms), the long launches of the
+// td4-psp18 frame do not (323.8 vs 319.1 frames/s, within run-to-run noise but not a gain), so by default only
+// `short_launch` launches (<= 2 work items per CTA) ask for it.  TDNET_PDL = 0: never, 1: short launches, 2: always.
+inline int tc_pdl_mode() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("TDNET_PDL");
-    v = e ? (atoi(e) != 0) : 1;
+    v = e ? atoi(e) : 1;
   }
-  return v != 0;
+  return v;
 }
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t tc_launch(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream,
-                             Args&&... args) {
+                             bool short_launch, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(block);
@@ -67,7 +70,7 @@ inline cudaError_t tc_launch(void (*kernel)(KArgs...), int grid, int block, size
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = tc_pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = (tc_pdl_mode() >= 2 || (tc_pdl_mode() == 1 && short_launch)) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<Args&&>(args)...);
 }
 

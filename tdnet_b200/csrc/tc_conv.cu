@@ -242,7 +242,7 @@ static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUt
   }
   const int todo = p.num_tiles - p.tile_begin;
   int grid = todo < g_num_sms ? todo : g_num_sms;
-  TDN_CUDA_OK(tc_launch(tc_conv_kernel<BLOCK_N>, grid, TC_THREADS, Cfg::SMEM_BYTES, stream, a_hi, a_lo, b_hi, b_lo, p));
+  TDN_CUDA_OK(tc_launch(tc_conv_kernel<BLOCK_N>, grid, TC_THREADS, Cfg::SMEM_BYTES, stream, todo <= 2 * grid, a_hi, a_lo, b_hi, b_lo, p));
   return TDN_OK;
 }
 

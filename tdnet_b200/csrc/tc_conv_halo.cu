@@ -193,7 +193,7 @@ static int launch_halo(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const C
     attr_smem = 232448;
   }
   int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
-  TDN_CUDA_OK(tc_launch(tc_conv_halo_kernel<BLOCK_N>, grid, TC_THREADS, smem, stream, a_hi, a_lo, b_hi, b_lo, p, g));
+  TDN_CUDA_OK(tc_launch(tc_conv_halo_kernel<BLOCK_N>, grid, TC_THREADS, smem, stream, p.num_tiles <= 2 * grid, a_hi, a_lo, b_hi, b_lo, p, g));
   TDN_LAUNCH_OK();
   return TDN_OK;
 }

@@ -221,7 +221,7 @@ static int launch_pair(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const C
   int max_clusters = 0, rc;
   if ((rc = pair_clusters<BLOCK_N>(num_sms, &max_clusters))) return rc;
   const int clusters = p.num_tiles < max_clusters ? p.num_tiles : max_clusters;
-  TDN_CUDA_OK(tc_launch(tc_conv_pair_kernel<BLOCK_N>, 2 * clusters, TC_THREADS, Cfg::SMEM_BYTES, stream, a_hi, a_lo, b_hi, b_lo, p));
+  TDN_CUDA_OK(tc_launch(tc_conv_pair_kernel<BLOCK_N>, 2 * clusters, TC_THREADS, Cfg::SMEM_BYTES, stream, p.num_tiles <= 2 * clusters, a_hi, a_lo, b_hi, b_lo, p));
   TDN_LAUNCH_OK();
   return TDN_OK;
 }
