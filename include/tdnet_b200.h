@@ -291,6 +291,21 @@ int tdn_upsample_logits(const tdn_tensor* in, float* out_nchw, int32_t out_h, in
  * tdn_upsample_logits (labels == argmax of the logits that call would write).  SURVEY.md 8f rank 1. */
 int tdn_upsample_argmax(const tdn_tensor* in, uint8_t* labels, int32_t out_h, int32_t out_w, void* stream);
 
+/* What Testing/test.py:61-64 keeps of a frame: `output.max(1)[1]` resized with cv2.INTER_NEAREST to (W/4, H/4).
+ * Nearest resampling selects full-resolution pixels; labels[n][oy][ox] = arg-max over classes of the logits
+ * interpolated (bilinear, align_corners=True, to full_h x full_w) at pixel (ys[oy], xs[ox]).  ys / xs are device
+ * int32 tables of out_h / out_w full-resolution coordinates (OpenCV resizeNN: min(floor(d * src / dst), src - 1));
+ * bit-consistent with tdn_upsample_argmax at those pixels, 1/16 of its work for the quarter-size map. */
+int tdn_upsample_argmax_sampled(const tdn_tensor* in, uint8_t* labels, int32_t full_h, int32_t full_w,
+                                const int32_t* ys, const int32_t* xs, int32_t out_h, int32_t out_w, void* stream);
+
+/* cv2.resize(frame, (out_w, out_h)) of uint8 HWC RGB frames [n,h,w,3] -> [n,out_h,out_w,3] (Testing/dataloader.py:63;
+ * OpenCV INTER_LINEAR, 8-bit fixed-point path), bit-exact.  x_taps / y_taps are device int32 tables with four entries
+ * per output column / row: {source offset 0, source offset 1, weight 0, weight 1} (11-bit weights, 16-byte aligned);
+ * OpenCV derives them in float / double on the host, so does the caller (tdnet_b200/ingest.py). */
+int tdn_resize_linear_u8(const uint8_t* src, int32_t n, int32_t h, int32_t w, const int32_t* x_taps,
+                         const int32_t* y_taps, uint8_t* dst, int32_t out_h, int32_t out_w, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * TD2-FANet widening: the non-convolution pieces of FAModule.forward
  * (Training/ptsemseg/models/td2_fanet/td2_fa.py:350-395).

@@ -93,6 +93,10 @@ SIGNATURES = {
     "tdn_layernorm_hw_apply": (C.c_int, [_TP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _TP, C.c_void_p]),
     "tdn_upsample_argmax": (C.c_int, [_TP, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "tdn_upsample_logits": (C.c_int, [_TP, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "tdn_upsample_argmax_sampled": (C.c_int, [_TP, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+                                              C.c_int32, C.c_void_p]),
+    "tdn_resize_linear_u8": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_int32, C.c_int32, C.c_void_p]),
     "tdn_pointwise_linear": (C.c_int, [_TP, C.c_void_p, C.c_void_p, C.c_void_p, _TP, C.c_void_p]),
     "tdn_fa_context": (C.c_int, [_TP, _TP, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "tdn_fa_context_workspace_bytes": (C.c_uint64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),

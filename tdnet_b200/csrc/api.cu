@@ -56,6 +56,8 @@ int stem_conv_pool_tc(const float*, const uint8_t*, const float*, int, int, int,
                       const tdn_tensor*, int, float, int*, cudaStream_t);
 int split16(const tdn_tensor*, const tdn_tensor*, cudaStream_t);
 int pointwise_linear(const tdn_tensor*, const float*, const float*, const float*, const tdn_tensor*, cudaStream_t);
+int upsample_argmax_sampled(const tdn_tensor*, uint8_t*, int, int, const int*, const int*, int, int, cudaStream_t);
+int resize_linear_u8(const uint8_t*, int, int, int, const int*, const int*, uint8_t*, int, int, cudaStream_t);
 int fa_context(const tdn_tensor*, const tdn_tensor*, float*, void*, size_t, cudaStream_t);
 size_t fa_context_workspace_bytes(int, int, int, int);
 int fa_apply(const tdn_tensor*, const float*, const tdn_tensor*, float, int*, cudaStream_t);
@@ -227,6 +229,16 @@ int tdn_upsample_logits(const tdn_tensor* in, float* out_nchw, int32_t out_h, in
 
 int tdn_upsample_argmax(const tdn_tensor* in, uint8_t* labels, int32_t out_h, int32_t out_w, void* stream) {
   return upsample_argmax(in, labels, out_h, out_w, (cudaStream_t)stream);
+}
+
+int tdn_upsample_argmax_sampled(const tdn_tensor* in, uint8_t* labels, int32_t full_h, int32_t full_w, const int32_t* ys,
+                                const int32_t* xs, int32_t out_h, int32_t out_w, void* stream) {
+  return upsample_argmax_sampled(in, labels, full_h, full_w, ys, xs, out_h, out_w, (cudaStream_t)stream);
+}
+
+int tdn_resize_linear_u8(const uint8_t* src, int32_t n, int32_t h, int32_t w, const int32_t* x_taps, const int32_t* y_taps,
+                         uint8_t* dst, int32_t out_h, int32_t out_w, void* stream) {
+  return resize_linear_u8(src, n, h, w, x_taps, y_taps, dst, out_h, out_w, (cudaStream_t)stream);
 }
 
 int tdn_pointwise_linear(const tdn_tensor* in, const float* weight, const float* scale, const float* bias,

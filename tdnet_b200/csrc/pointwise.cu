@@ -915,6 +915,89 @@ int upsample_argmax(const tdn_tensor* in, uint8_t* labels, int out_h, int out_w,
   return TDN_OK;
 }
 
+// The labels test.py actually keeps (Testing/test.py:61-64): arg-max, then cv2.resize(..., INTER_NEAREST) to a quarter
+// of the frame.  Nearest resampling picks full-resolution pixels (ys[oy], xs[ox]); only those are interpolated and
+// arg-maxed here (1/16 of the work of the full label map), with the same bilerp as the two kernels above.
+__global__ void __launch_bounds__(256) upsample_argmax_sampled_kernel(View in, uint8_t* __restrict__ labels, float sy,
+                                                                      float sx, const int* __restrict__ ys,
+                                                                      const int* __restrict__ xs, int Ho, int Wo) {
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long total = (long long)in.n * Ho * Wo;
+  if (idx >= total) return;
+  const int ox = (int)(idx % Wo);
+  long long t = idx / Wo;
+  const int oy = (int)(t % Ho);
+  const int b = (int)(t / Ho);
+  int y0, y1, x0, x1; float ly, lx;
+  src_index(__ldg(ys + oy), sy, in.h, y0, y1, ly);
+  src_index(__ldg(xs + ox), sx, in.w, x0, x1, lx);
+  const float* r0 = in.p + b * in.sn + y0 * in.sh;
+  const float* r1 = in.p + b * in.sn + y1 * in.sh;
+  float best = -INFINITY;
+  int arg = 0;
+  for (int c = 0; c < in.c; ++c) {
+    const float v = bilerp(r0[x0 * in.sw + c], r0[x1 * in.sw + c], r1[x0 * in.sw + c], r1[x1 * in.sw + c], lx, ly);
+    if (v > best) { best = v; arg = c; }
+  }
+  labels[idx] = (uint8_t)arg;
+}
+
+int upsample_argmax_sampled(const tdn_tensor* in, uint8_t* labels, int full_h, int full_w, const int* ys, const int* xs,
+                            int out_h, int out_w, cudaStream_t stream) {
+  int rc;
+  if ((rc = check_f32_tensor(in, "upsample_argmax_sampled.in"))) return rc;
+  TDN_REQUIRE(labels && ys && xs && out_h > 0 && out_w > 0 && full_h > 0 && full_w > 0 && in->c <= 256, TDN_ERR_INVALID,
+              "upsample_argmax_sampled: bad output / tables / > 256 classes");
+  long long total = (long long)in->n * out_h * out_w;
+  upsample_argmax_sampled_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(
+      make_view(*in), labels, ac_scale(in->h, full_h), ac_scale(in->w, full_w), ys, xs, out_h, out_w);
+  TDN_LAUNCH_OK();
+  return TDN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// cv2.resize(frame, (W, H)) of the uint8 RGB camera frame (Testing/dataloader.py:63; INTER_LINEAR, OpenCV's 8-bit
+// fixed-point path): integer arithmetic only, bit-exact.  The per-column / per-row taps (source offsets and 11-bit
+// weights, which OpenCV derives with float / double arithmetic) come from the host as int4 tables
+// {offset0, offset1, weight0, weight1}; a thread produces the three channels of one output pixel:
+//   t_r = S[row_r][x0] * a0 + S[row_r][x1] * a1            (r = 0, 1; values scaled by 2048)
+//   out = (((b0 * (t_0 >> 4)) >> 16) + ((b1 * (t_1 >> 4)) >> 16) + 2) >> 2
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) resize_linear_u8_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
+                                                               const int4* __restrict__ xt, const int4* __restrict__ yt,
+                                                               int n, int h, int w, int H, int W) {
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long total = (long long)n * H * W;
+  if (idx >= total) return;
+  const int x = (int)(idx % W);
+  long long t = idx / W;
+  const int y = (int)(t % H);
+  const int b = (int)(t / H);
+  const int4 xc = __ldg(xt + x), yc = __ldg(yt + y);
+  const uint8_t* r0 = src + ((long long)b * h + yc.x) * w * 3;
+  const uint8_t* r1 = src + ((long long)b * h + yc.y) * w * 3;
+  uint8_t* o = dst + idx * 3;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int t0 = (int)__ldg(r0 + xc.x * 3 + c) * xc.z + (int)__ldg(r0 + xc.y * 3 + c) * xc.w;
+    const int t1 = (int)__ldg(r1 + xc.x * 3 + c) * xc.z + (int)__ldg(r1 + xc.y * 3 + c) * xc.w;
+    int v = (((yc.z * (t0 >> 4)) >> 16) + ((yc.w * (t1 >> 4)) >> 16) + 2) >> 2;
+    o[c] = (uint8_t)min(max(v, 0), 255);
+  }
+}
+
+int resize_linear_u8(const uint8_t* src, int n, int h, int w, const int* xt, const int* yt, uint8_t* dst, int H, int W,
+                     cudaStream_t stream) {
+  TDN_REQUIRE(src && dst && xt && yt, TDN_ERR_INVALID, "resize_linear_u8: null pointer");
+  TDN_REQUIRE(n > 0 && h > 0 && w > 0 && H > 0 && W > 0, TDN_ERR_INVALID, "resize_linear_u8: empty image");
+  TDN_REQUIRE(aligned16(xt) && aligned16(yt), TDN_ERR_INVALID, "resize_linear_u8: tap tables must be 16-byte aligned");
+  long long total = (long long)n * H * W;
+  resize_linear_u8_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(src, dst, reinterpret_cast<const int4*>(xt),
+                                                                    reinterpret_cast<const int4*>(yt), n, h, w, H, W);
+  TDN_LAUNCH_OK();
+  return TDN_OK;
+}
+
 int upsample_logits(const tdn_tensor* in, float* out_nchw, int out_h, int out_w, cudaStream_t stream) {
   int rc;
   if ((rc = check_f32_tensor(in, "upsample.in"))) return rc;

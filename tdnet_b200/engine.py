@@ -1032,14 +1032,32 @@ class Engine:
         return self._packed[key]
 
     # ------------------------------------------------------------------ execution
-    def run_graphed(self, plan: FramePlan, img_ptr: int, out_ptr: int, labels=False, u8=False, img2_ptr=None):
+    def preview_op(self, plan: FramePlan, out_h: int, out_w: int):
+        """Last op that writes what Testing/test.py:61-64 keeps: arg-max labels resized (cv2.INTER_NEAREST) to
+        out_h x out_w.  Only the sampled full-resolution pixels are interpolated and arg-maxed."""
+        key = ("preview", out_h, out_w)
+        if key not in self._consts:
+            from .ingest import nearest_coords
+            self._consts[key] = (torch.from_numpy(nearest_coords(self.H, out_h)).to(self.device),
+                                 torch.from_numpy(nearest_coords(self.W, out_w)).to(self.device))
+        ys, xs = self._consts[key]
+        cache = plan.__dict__.setdefault("preview_ops", {})
+        if (out_h, out_w) not in cache:
+            low = self._ct(plan, plan.taps["head"])
+            cache[(out_h, out_w)] = (self.lib.tdn_upsample_argmax_sampled,
+                                     (C.byref(low), "out", self.H, self.W, ys.data_ptr(), xs.data_ptr(), out_h, out_w,
+                                      "stream"))
+        return cache[(out_h, out_w)]
+
+    def run_graphed(self, plan: FramePlan, img_ptr: int, out_ptr: int, labels=False, u8=False, img2_ptr=None,
+                    last_op=None):
         """Frame through a CUDA graph: the first and last op take the per-call image / output pointers and
         are launched directly; everything in between (static buffers only) is captured once and replayed.
         The plan must have run eagerly once before (kernel attributes, lazy packing)."""
         stream = torch.cuda.current_stream(self.device)
         nh = getattr(plan, "head_ops", 1)   # leading ops that take per-call pointers (td2_fa: two images)
         heads = [plan.u8_op] if u8 else plan.ops[:nh]
-        last = plan.labels_op if labels else plan.ops[-1]
+        last = last_op if last_op is not None else (plan.labels_op if labels else plan.ops[-1])
         assert "img" in heads[0][1] and "out" in last[1] and not any(
             a in ("img", "img2", "out") for _, args in plan.ops[nh:-1] for a in args if isinstance(a, str))
         subst = {"img": img_ptr, "img2": img2_ptr, "out": out_ptr, "stream": stream.cuda_stream}
@@ -1071,13 +1089,15 @@ class Engine:
         call(last, subst)
 
     def run(self, plan: FramePlan, img_ptr: int, out_ptr: int, stream: int, probe=None, labels=False, u8=False,
-            img2_ptr=None):
+            img2_ptr=None, last_op=None):
         """Enqueue the frame.  probe = (op_name, event_before, event_after) brackets one op with CUDA
         events (bench.py times the dominant kernel live this way)."""
         subst = {"img": img_ptr, "img2": img2_ptr, "out": out_ptr, "stream": stream,
                  "side": self.side_stream.cuda_stream if self.side_stream is not None else None}
         main = torch.cuda.current_stream(self.device) if self.side_stream is not None else None
         ops = plan.ops[:-1] + [plan.labels_op] if labels else plan.ops
+        if last_op is not None:
+            ops = list(plan.ops[:-1]) + [last_op]
         if u8:
             ops = [plan.u8_op] + list(ops[1:])
         for i, (fn, args) in enumerate(ops):

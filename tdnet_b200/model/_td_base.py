@@ -172,6 +172,13 @@ class TDModel(nn.Module):
         the 159 MB fp32 logits tensor is never written."""
         return self.forward(img, pos_id, _labels=True)
 
+    def forward_preview(self, img, pos_id=0, out_hw=None, u8=False):
+        """What Testing/test.py:61-64 keeps of a frame: `output.max(1)[1]` as int8, resized with cv2.INTER_NEAREST to
+        (W//4, H//4) -- returned as uint8 [n, H//4, W//4] (or `out_hw`).  Nearest resampling only selects pixels, so the
+        final upsample + arg-max runs on those pixels alone (tdn_upsample_argmax_sampled), bit-consistent with
+        forward_labels at the sampled positions."""
+        return self.forward(img, pos_id, _u8=u8, _preview=out_hw or "quarter")
+
     def forward_u8(self, frame_u8, pos_id=0, labels=False):
         """Device-side frame ingest: `frame_u8` is the RGB camera frame as uint8 HWC
         [n,H,W,3] on the GPU; (x/255 - mean)/std of Testing/dataloader.py:52-53,66-67 is applied inside the
@@ -187,7 +194,7 @@ class TDModel(nn.Module):
                                    "engine_mode='simt' (fp32 planes) for this checkpoint")
 
     @torch.no_grad()
-    def forward(self, img, pos_id=0, _probe=None, _labels=False, _u8=False):
+    def forward(self, img, pos_id=0, _probe=None, _labels=False, _u8=False, _preview=None):
         if not img.is_cuda:
             raise RuntimeError("tdnet_b200 runs on a CUDA (sm_100) device only; there is no CPU path. "
                                "Move the model and the input with .to('cuda').")
@@ -206,16 +213,21 @@ class TDModel(nn.Module):
         eng = self._engine(img, (n, 3, h, w))
         steady = len(self.Q_queue) >= self.arch.depth
         plan = eng.plan(pos_id + 1, steady)
-        if _labels:
+        last_op = None
+        if _preview is not None:
+            ph, pw = (h // 4, w // 4) if _preview == "quarter" else _preview
+            out = torch.empty((n, ph, pw), dtype=torch.uint8, device=img.device)
+            last_op = eng.preview_op(plan, ph, pw)
+        elif _labels:
             out = torch.empty((n, h, w), dtype=torch.uint8, device=img.device)
         else:
             out = torch.empty((n, self.nclass, h, w), dtype=torch.float32, device=img.device)
         plan.uses = getattr(plan, "uses", 0) + 1
         if self.use_cuda_graph and _probe is None and plan.uses > 1:
-            eng.run_graphed(plan, img.data_ptr(), out.data_ptr(), labels=_labels, u8=_u8)
+            eng.run_graphed(plan, img.data_ptr(), out.data_ptr(), labels=_labels, u8=_u8, last_op=last_op)
         else:
             eng.run(plan, img.data_ptr(), out.data_ptr(), torch.cuda.current_stream(img.device).cuda_stream, _probe,
-                    labels=_labels, u8=_u8)
+                    labels=_labels, u8=_u8, last_op=last_op)
         # FIFO bookkeeping mirrors buffer_contral; the tensors are views of the engine's device slots
         # (slot j = j-th oldest frame once the FIFO is full).
         depth = self.arch.depth

@@ -24,6 +24,9 @@ class pspnet(TDModel):  # noqa: N801
     def forward_labels(self, x, pos_id=None):
         return super().forward(x[-1:], 0, _labels=True)
 
+    def forward_preview(self, x, pos_id=None, out_hw=None, u8=False):
+        return super().forward(x[-1:], 0, _u8=u8, _preview=out_hw or "quarter")
+
     def forward_u8(self, frame_u8, pos_id=None, labels=False):
         return super().forward(frame_u8[-1:], 0, _labels=labels, _u8=True)
 

@@ -82,11 +82,15 @@ class td2_fa(TDModel):  # noqa: N801
         """uint8 label map [n, H, W] = forward(f_img, pos_id=pos_id).max(1)[1], fused upsample + arg-max."""
         return self.forward(f_img, pos_id=pos_id, _labels=True)
 
+    def forward_preview(self, f_img, pos_id=0, out_hw=None):
+        """uint8 [n, H//4, W//4]: the arg-max labels resized with cv2.INTER_NEAREST, only the sampled pixels computed."""
+        return self.forward(f_img, pos_id=pos_id, _preview=out_hw or "quarter")
+
     def forward_u8(self, *a, **k):
         raise NotImplementedError("forward_u8 needs the fused ReLU stem; the FANet stem ends in LeakyReLU")
 
     @torch.no_grad()
-    def forward(self, f2_img, lbl=None, pos_id=None, _probe=None, _labels=False):
+    def forward(self, f2_img, lbl=None, pos_id=None, _probe=None, _labels=False, _preview=None):
         if self.training:
             raise RuntimeError("tdnet_b200.td2_fa implements the inference path only: call .eval() first "
                                "(the training branch, td2_fa.py:116-129, is out of scope)")
@@ -105,15 +109,21 @@ class td2_fa(TDModel):  # noqa: N801
         n, _, h, w = cur.shape
         eng = self._engine(cur, (n, 3, h, w))
         plan = eng.plan(pos_id + 1, True)
-        if _labels:
+        last_op = None
+        if _preview is not None:
+            ph, pw = (h // 4, w // 4) if _preview == "quarter" else _preview
+            out = torch.empty((n, ph, pw), dtype=torch.uint8, device=cur.device)
+            last_op = eng.preview_op(plan, ph, pw)
+        elif _labels:
             out = torch.empty((n, h, w), dtype=torch.uint8, device=cur.device)
         else:
             out = torch.empty((n, self.nclass, h, w), dtype=torch.float32, device=cur.device)
         plan.uses = getattr(plan, "uses", 0) + 1
         if self.use_cuda_graph and _probe is None and plan.uses > 1:
-            eng.run_graphed(plan, cur.data_ptr(), out.data_ptr(), labels=_labels, img2_ptr=prev.data_ptr())
+            eng.run_graphed(plan, cur.data_ptr(), out.data_ptr(), labels=_labels, img2_ptr=prev.data_ptr(),
+                            last_op=last_op)
         else:
             eng.run(plan, cur.data_ptr(), out.data_ptr(), torch.cuda.current_stream(cur.device).cuda_stream, _probe,
-                    labels=_labels, img2_ptr=prev.data_ptr())
+                    labels=_labels, img2_ptr=prev.data_ptr(), last_op=last_op)
         self._last = (eng, plan)
         return out
