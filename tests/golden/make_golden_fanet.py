@@ -58,7 +58,36 @@ CASES = [
     ("td2fa_r34_97x161_n2", "resnet34", 97, 161, 2, 2),    # ragged maps 13x21 / 7x11 / 4x6 / 2x3, batch 2
     ("td2fa_r50_64x96", "resnet50", 64, 96, 1, 2),         # Bottleneck backbone, 2048-channel feat32
 ]
+# the only size the UNPATCHED reference accepts: LayerNorm([96, 192]) (td2_fa.py:71-72) = a 768x1536 input; checksums only
+NATIVE = ("td2fa_r18_768x1536_chk", "resnet18", 768, 1536, 1, 2)
 CH_STRIDE = 4
+
+
+def run_native(td2_fa, norm_layer, name, backbone, H, W, batch, calls):
+    """No patch at all: the hard-coded LayerNorm([96, 192]) is used as constructed."""
+    torch.manual_seed(0)
+    net = td2_fa(nclass=19, backbone=backbone, norm_layer=norm_layer, path_num=2).eval()
+    assert fa_feature_hw(H, W) == (96, 192)
+    net.load_state_dict(synth_state_dict(td2fa_state_dict_template(backbone), seed=0), strict=True)
+    cur = {}
+    for idx in (1, 2):
+        getattr(net, f"head{idx}").register_forward_hook(
+            lambda _m, _i, out, k=f"head{idx}": cur.setdefault(k, []).append(out))
+    frames = synth_clip(calls + 1, H, W, batch=batch, clip_id=0)
+    rec = {}
+    with torch.no_grad():
+        for i in range(calls):
+            cur.clear()
+            out = net([frames[i], frames[i + 1]], pos_id=i % 2)
+            head = cur[f"head{i % 2 + 1}"][0]
+            rec[f"head_mean_{i}"] = np.float64(head.double().mean().item())
+            rec[f"head_absmean_{i}"] = np.float64(head.double().abs().mean().item())
+            rec[f"head_sub_{i}"] = head[:, :, ::8, ::16].numpy().copy()
+            rec[f"logits_sub_{i}"] = out[:, :, ::64, ::128].numpy().copy()
+    rec["meta"] = np.array([H, W, batch, calls, 96, 192], dtype=np.int64)
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **rec)
+    print(f"{name}: {os.path.getsize(path) / 1e6:.2f} MB, {len(rec)} arrays")
 
 
 def run_case(td2_fa, norm_layer, name, backbone, H, W, batch, calls):
@@ -124,3 +153,5 @@ if __name__ == "__main__":
     for case in CASES:
         if not only or case[0] in only:
             run_case(td2_fa, norm_layer, *case)
+    if not only or NATIVE[0] in only:
+        run_native(td2_fa, norm_layer, *NATIVE)

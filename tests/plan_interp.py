@@ -292,6 +292,22 @@ def op_upsample_logits(x, out, H, W, stream):
         F.interpolate(_nchw(v), (H, W), mode="bilinear", align_corners=True))
 
 
+def _full_res_logits(x, H, W):
+    return F.interpolate(_nchw(read(x._obj)), (H, W), mode="bilinear", align_corners=True)
+
+
+def op_upsample_argmax(x, out, H, W, stream):
+    lab = _full_res_logits(x, H, W).argmax(1).to(torch.uint8)
+    _flat(out, lab.numel(), torch.uint8).view(lab.shape).copy_(lab)
+
+
+def op_upsample_argmax_sampled(x, out, H, W, ys, xs, Ho, Wo, stream):
+    yi = _flat(ys, Ho, torch.int32).long()
+    xi = _flat(xs, Wo, torch.int32).long()
+    lab = _full_res_logits(x, H, W).argmax(1)[:, yi][:, :, xi].to(torch.uint8)
+    _flat(out, lab.numel(), torch.uint8).view(lab.shape).copy_(lab)
+
+
 OPS = {
     "tdn_image_to_nhwc": op_image_to_nhwc, "tdn_stem_conv_pool_tc": op_stem_conv_pool_tc,
     "tdn_stem_conv_pool": op_stem_conv_pool, "tdn_psp_pool": op_psp_pool, "tdn_psp_branch_convs": op_psp_branch_convs,
@@ -300,14 +316,17 @@ OPS = {
     "tdn_copy_nhwc": op_copy_nhwc, "tdn_pointwise_linear": op_pointwise_linear, "tdn_bilinear_nhwc": op_bilinear_nhwc, "tdn_fa_context": op_fa_context,
     "tdn_fa_apply": op_fa_apply, "tdn_add_upsampled": op_add_upsampled,
     "tdn_layernorm_hw_stats": op_layernorm_hw_stats, "tdn_layernorm_hw_apply": op_layernorm_hw_apply,
-    "tdn_upsample_logits": op_upsample_logits,
+    "tdn_upsample_logits": op_upsample_logits, "tdn_upsample_argmax": op_upsample_argmax,
+    "tdn_upsample_argmax_sampled": op_upsample_argmax_sampled,
 }
 
 
-def run_plan(plan, subst):
+def run_plan(plan, subst, last_op=None):
     """Execute every op of `plan` in order; `subst` maps the symbolic arguments ("img", "img2", "out") to host
-    addresses.  Stream arguments and fork / join marks are ignored (sequential execution is one valid schedule)."""
-    for fn, args in plan.ops:
+    addresses.  Stream arguments and fork / join marks are ignored (sequential execution is one valid schedule).
+    `last_op` replaces the plan's last op (the labels / preview variants of the output stage)."""
+    ops = plan.ops if last_op is None else list(plan.ops[:-1]) + [last_op]
+    for fn, args in ops:
         if fn in ("fork", "join"):
             continue
         impl = OPS.get(fn.__name__)

@@ -191,6 +191,28 @@ def test_fanet_against_oracle(backbone, H, W, n):
     net.check_numeric_range()
 
 
+def test_fanet_native_size_768x1536_against_reference_checksums():
+    """The reference's own size (LayerNorm([96, 192]) untouched, default ln_shape) against what the unmodified module
+    produced there: sub-sampled head / logits and the head mean."""
+    from common import load_golden
+    g, m = load_golden("td2fa_r18_768x1536_chk")
+    _, sd = make_fanet_oracle("resnet18", m["H"], m["W"])
+    from tdnet_b200.model import td2_fa
+    net = td2_fa.td2_fa(nclass=19, backbone="resnet18", path_num=2)            # default ln_shape = (96, 192)
+    net.load_state_dict(sd, strict=True)
+    net.eval().to("cuda:0")
+    frames = [f.cuda() for f in synth_clip(m["n_frames"] + 1, m["H"], m["W"], clip_id=0)]
+    for i in range(m["n_frames"]):
+        out = net([frames[i], frames[i + 1]], pos_id=i % 2)
+        e = max_abs(out[:, :, ::64, ::128].cpu(), g[f"logits_sub_{i}"])
+        record(f"golden/td2fa_r18_768x1536_chk/call{i}", max_abs=e)
+        assert e <= LOGIT_TOL, (i, e)
+        head = tap(net._last[1].taps["head"])
+        assert max_abs(head[:, :, ::8, ::16], g[f"head_sub_{i}"]) <= LOGIT_TOL
+        assert abs(head.double().mean().item() - float(g[f"head_mean_{i}"])) <= 1e-5
+    net.check_numeric_range()
+
+
 def test_fanet_full_size_1024x2048_properties():
     """Cityscapes-sized frame pair: runs, finite, deterministic run to run, labels == arg-max of the logits."""
     from tdnet_b200.model.arch import feature_hw

@@ -95,6 +95,22 @@ def test_fanet_oracle_matches_reference_outputs(name):
     assert g["tap_up32"].shape[2:] == (h32 + 2, w32 + 2)
 
 
+def test_fanet_oracle_native_size_checksums():
+    """768x1536: the only size the unpatched td2_fa accepts (hard-coded LayerNorm([96, 192]), td2_fa.py:71-72); the
+    fixture was produced without touching the module at all."""
+    g, m = load_golden("td2fa_r18_768x1536_chk")
+    assert (m["h8"], m["w8"]) == (96, 192)
+    oracle, _ = make_fanet_oracle("resnet18", m["H"], m["W"])
+    frames = synth_clip(m["n_frames"] + 1, m["H"], m["W"], batch=m["batch"], clip_id=0)
+    for i in range(m["n_frames"]):
+        out = oracle([frames[i], frames[i + 1]], pos_id=i % 2)
+        head = oracle.taps["head"]
+        assert max_abs(head[:, :, ::8, ::16], g[f"head_sub_{i}"]) <= 2 * TOL
+        assert max_abs(out[:, :, ::64, ::128], g[f"logits_sub_{i}"]) <= 2 * TOL
+        assert abs(head.double().mean().item() - float(g[f"head_mean_{i}"])) <= 1e-6
+    assert oracle.taps["k_sub"].shape == (1, 32 * 64, 64)          # stride-3 keys of a 96x192 map
+
+
 def test_oracle_native_size_checksums():
     """769x1537 (the only size the unpatched reference accepts, LayerNorm([97,193]))."""
     name = "td4_r18_769x1537_chk"

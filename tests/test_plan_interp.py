@@ -105,3 +105,27 @@ def test_pspnet_plan_matches_reference_golden(name):
         assert max_abs(_nchw(plan.taps["head"]), g[f"head_{i}"]) <= 2e-4 * scale
         if f"logits_{i}" in g:
             assert max_abs(out, g[f"logits_{i}"]) <= 2e-4 * scale
+
+
+def test_label_and_preview_output_stages():
+    """forward_labels / forward_preview variants of the last op: labels == arg-max of the logits; the preview equals the
+    cv2.INTER_NEAREST resize of that label map (Testing/test.py:61-64) -- host-built coordinate tables included."""
+    from oracle import cv2_resize_oracle as O
+    name = "td4_r18_97x161"
+    arch, backbone = GOLDEN_CASES[name]
+    g, meta = load_golden(name)
+    H, W = meta["H"], meta["W"]
+    m = A.build_arch(arch, backbone, 19)
+    ln = (meta["h8"], meta["w8"])
+    eng = Engine(m, _synth_weights(m, ln), 1, H, W, torch.device("cpu"), ln, mode="tc")
+    plan = eng.plan(1, False)
+    img = synth_clip(1, H, W)[0].contiguous()
+    logits, labels = torch.empty(1, 19, H, W), torch.empty(1, H, W, dtype=torch.uint8)
+    run_plan(plan, {"img": img.data_ptr(), "out": logits.data_ptr()})
+    run_plan(plan, {"img": img.data_ptr(), "out": labels.data_ptr()}, last_op=plan.labels_op)
+    assert torch.equal(labels.long(), logits.argmax(1))
+    for ph, pw in ((H // 4, W // 4), (37, 53)):
+        prev = torch.empty(1, ph, pw, dtype=torch.uint8)
+        run_plan(plan, {"img": img.data_ptr(), "out": prev.data_ptr()}, last_op=eng.preview_op(plan, ph, pw))
+        want = O.resize_nearest(labels[0].numpy().astype(np.int8), pw, ph)
+        assert np.array_equal(prev[0].numpy().astype(np.int8), want)
