@@ -58,3 +58,31 @@ def test_vertical_border_rows_are_not_plain_copies():
     assert ty[0, 0] == ty[0, 1] == 0 and ty[0, 2] != 2048          # both taps read row 0, weights (w0, w1) kept
     tx = ingest.linear_taps(37, 97, "x")
     assert tx[0, 0] == 0 and tx[0, 2] == 2048 and tx[0, 3] == 0     # columns: border pixel copied
+
+
+def test_oracle_matches_installed_cv2_on_random_shapes():
+    """Sixty random (source, destination) shape pairs between 2 and 90 pixels per side, up- and down-scaling mixed per
+    axis: the restatement must agree with cv2 bit for bit on every one of them."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(99)
+    for _ in range(60):
+        h, w, H, W = (int(v) for v in rng.integers(2, 91, 4))
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        assert np.array_equal(O.resize_linear_u8(img, W, H), cv2.resize(img, (W, H))), (h, w, H, W)
+        lab = rng.integers(0, 19, (h, w), dtype=np.int8)
+        assert np.array_equal(O.resize_nearest(lab, W, H), cv2.resize(lab, (W, H), interpolation=cv2.INTER_NEAREST))
+
+
+def test_header_is_valid_c(tmp_path):
+    """include/tdnet_b200.h is a C header (the boundary is a C ABI): it must compile as C99, not only as C++."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "abi.c"
+    src.write_text('#include "tdnet_b200.h"\n'
+                   "int main(void) { tdn_tensor t; tdn_attention_desc d; (void)t; (void)d; return TDN_ABI_VERSION - 1; }\n")
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(root, "include"),
+                           "-c", str(src), "-o", str(tmp_path / "abi.o")])
