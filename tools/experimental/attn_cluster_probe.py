@@ -1,0 +1,81 @@
+"""Probe for the EXPERIMENTAL 2-CTA-cluster attention kernel (tools/experimental/tc_attn_cluster.cu) -- run on a B200:
+
+    bash tools/experimental/build.sh && timeout 120 python tools/experimental/attn_cluster_probe.py
+
+For each shape: output of tdnx_attention_tc_cluster against the product tdn_attention_tc (expected bit-identical: same
+probabilities, same accumulation order per output element) and against an fp64 reference, then both timed (CUDA events,
+20 launches after 3 warm-up).  Wrap in `timeout`: a protocol bug in an unvalidated kernel can hang until the 2 s
+mbarrier watchdog of every CTA fires."""
+import ctypes as C
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from tdnet_b200 import _cabi  # noqa: E402
+
+SHAPES = [(1, 300, 100, 512), (2, 1000, 690, 512), (1, 2048, 64, 512), (1, 4096, 2048, 1024), (1, 32768, 2048, 512)]
+
+
+def split(t):
+    hi = t.half()
+    return hi.contiguous(), (t - hi.float()).half().contiguous()
+
+
+def main():
+    lib = C.CDLL(os.path.join(ROOT, "tools", "experimental", "build", "libtdnet_b200_x.so"))
+    lib.tdnx_attention_tc_cluster.restype = C.c_int
+    lib.tdnx_attention_tc_cluster.argtypes = [C.POINTER(_cabi.AttentionDesc), C.c_void_p]
+    lib.tdn_attention_tc.restype = C.c_int
+    lib.tdn_attention_tc.argtypes = [C.POINTER(_cabi.AttentionDesc), C.c_void_p]
+    lib.tdn_last_error.restype = C.c_char_p
+    for n, pq, pk, dv in SHAPES:
+        g = torch.Generator().manual_seed(pq + pk)
+        q, k = torch.randn(n, pq, 64, generator=g) * 1.3, torch.randn(n, pk, 64, generator=g) * 1.4
+        v, r = torch.randn(n, pk, dv, generator=g) * 3, torch.randn(n, pq, dv, generator=g)
+        pkp = (pk + 63) // 64 * 64
+        vt = torch.zeros(n, dv, pkp)
+        vt[:, :, :pk] = v.transpose(1, 2)
+        pl = {name: split(t.cuda()) for name, t in (("q", q), ("k", k), ("vt", vt), ("r", r))}
+        outs = {}
+        for which, fn in (("product", lib.tdn_attention_tc), ("cluster", lib.tdnx_attention_tc_cluster)):
+            out = torch.full((n, pq, dv), float("nan"), device="cuda")
+            d = _cabi.AttentionDesc()
+            d.q_hi, d.q_lo, d.q_ld, d.q_batch_stride = pl["q"][0].data_ptr(), pl["q"][1].data_ptr(), 64, pq * 64
+            d.k_hi, d.k_lo, d.k_ld, d.k_batch_stride = pl["k"][0].data_ptr(), pl["k"][1].data_ptr(), 64, pk * 64
+            d.vt_hi, d.vt_lo, d.vt_ld, d.vt_batch_stride = pl["vt"][0].data_ptr(), pl["vt"][1].data_ptr(), pkp, dv * pkp
+            d.out = _cabi.Tensor(out.data_ptr(), None, 0, n, 1, pq, dv, pq * dv, pq * dv, dv)
+            d.residual = _cabi.Tensor(pl["r"][0].data_ptr(), pl["r"][1].data_ptr(), 1, n, 1, pq, dv, pq * dv, pq * dv, dv)
+            d.n, d.pq, d.pk, d.d_k, d.d_v = n, pq, pk, 64, dv
+            rc = fn(C.byref(d), None)
+            if rc:
+                print(which, "rc", rc, lib.tdn_last_error().decode())
+                continue
+            torch.cuda.synchronize()
+            for _ in range(3):
+                fn(C.byref(d), None)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(20):
+                fn(C.byref(d), None)
+            e1.record()
+            torch.cuda.synchronize()
+            outs[which] = (out, e0.elapsed_time(e1) / 20)
+        res = {"shape": [n, pq, pk, dv]}
+        if len(outs) == 2:
+            a = torch.softmax(torch.bmm(q.double(), k.double().transpose(1, 2)) / 8.0, dim=2) if pq * pk <= 8e7 else None
+            res.update(bit_identical=bool(torch.equal(outs["product"][0], outs["cluster"][0])),
+                       max_diff=float((outs["product"][0] - outs["cluster"][0]).abs().max()),
+                       ms_product=round(outs["product"][1], 4), ms_cluster=round(outs["cluster"][1], 4))
+            if a is not None:
+                ref = torch.bmm(a, v.double()) + r.double()
+                res["max_abs_vs_fp64"] = float((outs["cluster"][0].cpu().double() - ref).abs().max())
+        print(json.dumps(res), flush=True)
+
+
+if __name__ == "__main__":
+    main()
