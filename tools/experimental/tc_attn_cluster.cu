@@ -1,7 +1,7 @@
 // EXPERIMENTAL, NOT PART OF THE PRODUCT LIBRARY (not under tdnet_b200/csrc, not built by __graft_entry__.build()).
-// Written at the end of round 1 without GPU time left to run it: it compiles for sm_100a (tools/experimental/build.sh),
-// it has NOT been executed.  tools/experimental/attn_cluster_probe.py checks it against an fp64 reference and times it
-// next to tdn_attention_tc -- run that first.
+// Written at the end of round 1; one probe run on B200 (tools/experimental/attn_cluster_probe.py): results are correct
+// (within 4e-6 of tdn_attention_tc, <= 7e-5 of fp64 on all shapes) but the big hop takes 0.407 ms against 0.260 ms for
+// the product kernel -- see tools/experimental/README.md for the suspects and the next step.
 //
 // What it is: tc_attn.cu's fused attention-propagation kernel on 2-CTA CLUSTERS, the next step DESIGN.md section 9
 // derives from the ncu stall analysis (pass 2 is tensor-pipe bound; the per-slice QK^T recompute is 20 % of an item's
@@ -16,7 +16,7 @@
 // warp arrivals each) -- no cluster-wide barrier inside the item loop, so the TMA / MMA warps keep running ahead.
 // Per CTA and item the tensor pipe then runs 32 P.V tiles + 16 S tiles (+ 8 pass-1 tiles) instead of 32 + 32 (+ 16).
 //
-// To validate first (the parts that cannot be checked without the hardware):
+// Mechanisms this draft relies on (all three worked on the first run):
 //   * generic-proxy st.shared::cluster writes of P followed by `fence.proxy.async` + a `.release.cluster` remote
 //     mbarrier arrive, consumed by the peer's tcgen05.mma (async proxy) after an `.acquire.cluster` try_wait;
 //   * tcgen05.commit.cta_group::1 ... multicast::cluster arriving on the same barrier offset in both CTAs;
