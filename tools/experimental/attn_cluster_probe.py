@@ -1,6 +1,7 @@
 """Probe for the EXPERIMENTAL 2-CTA-cluster attention kernel (tools/experimental/tc_attn_cluster.cu) -- run on a B200:
 
     bash tools/experimental/build.sh && timeout 120 python tools/experimental/attn_cluster_probe.py
+    SUFFIX=_bulk bash tools/experimental/build.sh -DATC_BULK_HANDOFF=1 && timeout 120 python tools/experimental/attn_cluster_probe.py _bulk
 
 For each shape: output of tdnx_attention_tc_cluster against the product tdn_attention_tc (expected bit-identical: same
 probabilities, same accumulation order per output element) and against an fp64 reference, then both timed (CUDA events,
@@ -27,7 +28,9 @@ def split(t):
 
 
 def main():
-    lib = C.CDLL(os.path.join(ROOT, "tools", "experimental", "build", "libtdnet_b200_x.so"))
+    suffix = sys.argv[1] if len(sys.argv) > 1 else ""        # e.g. "_bulk" for the library built with SUFFIX=_bulk
+    lib = C.CDLL(os.path.join(ROOT, "tools", "experimental", "build", f"libtdnet_b200_x{suffix}.so"))
+    print(f"library: libtdnet_b200_x{suffix}.so", flush=True)
     lib.tdnx_attention_tc_cluster.restype = C.c_int
     lib.tdnx_attention_tc_cluster.argtypes = [C.POINTER(_cabi.AttentionDesc), C.c_void_p]
     lib.tdn_attention_tc.restype = C.c_int

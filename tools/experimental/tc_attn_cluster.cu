@@ -33,7 +33,25 @@ namespace experimental {
 
 using namespace ptx;
 
+// Hand-off of a finished P tile to the peer CTA:
+//   ATC_BULK_HANDOFF = 0 (the variant that ran on B200): every softmax thread writes its 8 x 16 bytes into both CTAs
+//     (st.shared + st.shared::cluster), fences at cluster scope and the warp arrives on both p_full barriers.
+//   ATC_BULK_HANDOFF = 1 (NEVER EXECUTED): the tile is written locally only; once the 8 warps have arrived on the local
+//     p_full, one thread forwards the 32 KB tile with a single cp.async.bulk.shared::cluster whose complete_tx lands on
+//     the peer's p_full (armed with expect_tx by the peer's P.V issuer) -- asynchronous, no generic-proxy fence at
+//     cluster scope, no per-thread DSMEM stores.
+#ifndef ATC_BULK_HANDOFF
+#define ATC_BULK_HANDOFF 0
+#endif
+
 // ---- cluster helpers local to this file
+// shared::cta -> shared::cluster bulk copy; completion is signalled as transaction bytes on the REMOTE mbarrier
+__device__ __forceinline__ void bulk_copy_to_cluster(uint32_t dst_cluster_addr, const void* src_local, uint32_t bytes,
+                                                     uint32_t mbar_cluster_addr) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst_cluster_addr), "r"(smem_u32(src_local)), "r"(bytes), "r"(mbar_cluster_addr)
+               : "memory");
+}
 __device__ __forceinline__ uint32_t map_to_cta(const void* smem_ptr, uint32_t cta) {   // shared::cluster address of the
   uint32_t r;                                                                          // same offset in CTA `cta`
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(smem_ptr)), "r"(cta));
@@ -176,7 +194,12 @@ tc_attn_cluster_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_
     for (int s = 0; s < 2; ++s) {
       mbar_init(&bars->s_full[s], 1);
       mbar_init(&bars->s_empty[s], AT_SOFTMAX_WARPS);   // one arrival per softmax warp (lane 0 after __syncwarp):
+#if ATC_BULK_HANDOFF
+      // own buffer: the 8 local softmax warps; the peer's buffer: this CTA's expect_tx arrive + the bulk copy's bytes
+      mbar_init(&bars->p_full[s], s == (int)rank ? AT_SOFTMAX_WARPS : 1);
+#else
       mbar_init(&bars->p_full[s], AT_SOFTMAX_WARPS);    // buffer s is filled by the 8 softmax warps of CTA s
+#endif
       mbar_init(&bars->p_empty[s], 2);                  // ... and released by the P.V issuers of both CTAs
     }
     mbar_init(&bars->o_full, 1);
@@ -323,11 +346,21 @@ tc_attn_cluster_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_
     int vs = 0;
     uint32_t vph = 0, oph = 0;
     uint32_t pmask = 0;                                          // bit b: phase of p_full[b] expected next
+#if ATC_BULK_HANDOFF
+    if (elect_one()) mbar_expect_tx(&bars->p_full[peer], 2 * AT_P_PLANE);   // arm the first tile the peer will forward
+    __syncwarp();
+#endif
     for (int item = cluster_id; item < p.num_items; item += num_clusters) {
       mbar_wait(&bars->o_empty, oph ^ 1);                        // epilogue of the previous item has read O
       for (int kt = 0; kt < T; ++kt) {
         const int pb = kt & 1;                                   // buffer = rank of the CTA that produced tile kt
         mbar_wait_cluster(&bars->p_full[pb], (pmask >> pb) & 1u);   // ... written locally or by the peer (DSMEM)
+#if ATC_BULK_HANDOFF
+        if (pb == (int)peer) {                                   // re-arm for the next tile the peer forwards
+          if (elect_one()) mbar_expect_tx(&bars->p_full[pb], 2 * AT_P_PLANE);
+          __syncwarp();
+        }
+#endif
         const uint32_t p_hi = smem_u32(sP + pb * 2 * AT_P_PLANE), p_lo = p_hi + AT_P_PLANE;
         for (int h = 0; h < HALVES; ++h) {
           mbar_wait(&bars->v_full[vs], vph);
@@ -474,9 +507,25 @@ tc_attn_cluster_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_
           const int phys = ((group * 4 + c) ^ (row & 7)) << 4;   // 16-byte chunk inside the 128-byte swizzled row
           *reinterpret_cast<uint4*>(ph + phys) = phv[c];
           *reinterpret_cast<uint4*>(ph + AT_P_PLANE + phys) = plv[c];
+#if !ATC_BULK_HANDOFF
           st_cluster_v4(ph_peer + phys, phv[c]);
           st_cluster_v4(ph_peer + AT_P_PLANE + phys, plv[c]);
+#endif
         }
+#if ATC_BULK_HANDOFF
+        (void)ph_peer;
+        fence_proxy_async_smem();                              // local writes -> async proxy (UMMA and the bulk copy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->p_full[pb]);
+        if (warp == 2 && lane == 0) {
+          // forwarder: when all 8 warps have written the tile, one asynchronous 32 KB copy into the peer's buffer;
+          // its completion is what the peer's P.V issuer waits for.  The local buffer is not rewritten before both
+          // P.V issuers have released it (p_empty), which the peer only does after the copy has landed.
+          mbar_wait(&bars->p_full[pb], pph);
+          bulk_copy_to_cluster(peer_sP, sP + pb * 2 * AT_P_PLANE, 2 * AT_P_PLANE, peer_p_full);
+        }
+        __syncwarp();
+#else
         fence_cluster();
         fence_proxy_async_all();
         __syncwarp();
@@ -484,6 +533,7 @@ tc_attn_cluster_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_
           mbar_arrive(&bars->p_full[pb]);
           mbar_arrive_cluster(peer_p_full);
         }
+#endif
         pph ^= 1;                                              // the same buffer every time: its phase flips per tile
       }
       bars->xch[group][row] = l;
