@@ -31,8 +31,12 @@ def main():
     suffix = sys.argv[1] if len(sys.argv) > 1 else ""        # e.g. "_bulk" for the library built with SUFFIX=_bulk
     lib = C.CDLL(os.path.join(ROOT, "tools", "experimental", "build", f"libtdnet_b200_x{suffix}.so"))
     print(f"library: libtdnet_b200_x{suffix}.so", flush=True)
-    lib.tdnx_attention_tc_cluster.restype = C.c_int
-    lib.tdnx_attention_tc_cluster.argtypes = [C.POINTER(_cabi.AttentionDesc), C.c_void_p]
+    variants = [("product", lib.tdn_attention_tc)]
+    for name in ("tdnx_attention_tc_cluster", "tdnx_attention_tc_cluster3"):
+        if hasattr(lib, name):
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = C.c_int, [C.POINTER(_cabi.AttentionDesc), C.c_void_p]
+            variants.append((name.replace("tdnx_attention_tc_", ""), fn))
     lib.tdn_attention_tc.restype = C.c_int
     lib.tdn_attention_tc.argtypes = [C.POINTER(_cabi.AttentionDesc), C.c_void_p]
     lib.tdn_last_error.restype = C.c_char_p
@@ -45,7 +49,7 @@ def main():
         vt[:, :, :pk] = v.transpose(1, 2)
         pl = {name: split(t.cuda()) for name, t in (("q", q), ("k", k), ("vt", vt), ("r", r))}
         outs = {}
-        for which, fn in (("product", lib.tdn_attention_tc), ("cluster", lib.tdnx_attention_tc_cluster)):
+        for which, fn in variants:
             out = torch.full((n, pq, dv), float("nan"), device="cuda")
             d = _cabi.AttentionDesc()
             d.q_hi, d.q_lo, d.q_ld, d.q_batch_stride = pl["q"][0].data_ptr(), pl["q"][1].data_ptr(), 64, pq * 64
@@ -69,14 +73,14 @@ def main():
             torch.cuda.synchronize()
             outs[which] = (out, e0.elapsed_time(e1) / 20)
         res = {"shape": [n, pq, pk, dv]}
-        if len(outs) == 2:
-            a = torch.softmax(torch.bmm(q.double(), k.double().transpose(1, 2)) / 8.0, dim=2) if pq * pk <= 8e7 else None
-            res.update(bit_identical=bool(torch.equal(outs["product"][0], outs["cluster"][0])),
-                       max_diff=float((outs["product"][0] - outs["cluster"][0]).abs().max()),
-                       ms_product=round(outs["product"][1], 4), ms_cluster=round(outs["cluster"][1], 4))
-            if a is not None:
-                ref = torch.bmm(a, v.double()) + r.double()
-                res["max_abs_vs_fp64"] = float((outs["cluster"][0].cpu().double() - ref).abs().max())
+        a = torch.softmax(torch.bmm(q.double(), k.double().transpose(1, 2)) / 8.0, dim=2) if pq * pk <= 8e7 else None
+        ref = torch.bmm(a, v.double()) + r.double() if a is not None else None
+        for which, (out, ms) in outs.items():
+            res[f"ms_{which}"] = round(ms, 4)
+            if which != "product" and "product" in outs:
+                res[f"max_diff_{which}"] = float((outs["product"][0] - out).abs().max())
+            if ref is not None:
+                res[f"max_abs_vs_fp64_{which}"] = float((out.cpu().double() - ref).abs().max())
         print(json.dumps(res), flush=True)
 
 
