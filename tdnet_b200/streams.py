@@ -8,7 +8,7 @@ Backend 'nccl' on the GPU box, 'gloo' in the CPU tests.
 """
 from __future__ import annotations
 
-from typing import List, Sequence
+from typing import List
 
 
 def clips_for_rank(rank: int, world: int, n_clips: int) -> List[int]:

@@ -6,7 +6,7 @@ import torch
 
 from oracle.td2fa_oracle import TD2FAOracle, fa_feature_hw, td2fa_state_dict_template
 from oracle.tdnet_oracle import PSPNetOracle, TDOracle, state_dict_template
-from tdnet_b200.synth import synth_clip, synth_state_dict
+from tdnet_b200.synth import synth_state_dict
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CH_STRIDE = 4  # tests/golden/make_golden.py stores every 4th channel of the wide taps

@@ -6,7 +6,6 @@ identical on every pixel whose reference top-1/top-2 margin exceeds twice the me
 """
 import ctypes as C
 
-import numpy as np
 import pytest
 import torch
 

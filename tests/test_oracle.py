@@ -1,7 +1,6 @@
 """CPU: the oracle restatement vs. what the unmodified reference produced (tests/golden/*.npz)."""
 import numpy as np
 import pytest
-import torch
 
 from common import (CH_STRIDE, FANET_GOLDEN_CASES, GOLDEN_CASES, PSPNET_GOLDEN_CASES, load_golden, make_fanet_oracle,
                     make_oracle, make_pspnet_oracle, max_abs)
