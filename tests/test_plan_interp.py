@@ -63,7 +63,7 @@ def _synth_weights(m, ln_shape):
 
 
 @pytest.mark.parametrize("mode", ["tc", "simt"])
-@pytest.mark.parametrize("name", ["td4_r18_97x161", "td2_r50_64x128", "td4_r50_64x64_n2"])
+@pytest.mark.parametrize("name", ["td4_r18_97x161", "td4_r18_128x256", "td2_r50_64x128", "td2_r34_80x112", "td4_r50_64x64_n2"])
 def test_td_plans_match_reference_golden(name, mode):
     """Warm-up and steady plans of the TD models frame by frame, FIFO included (push order, shifts, slot views)."""
     arch, backbone = GOLDEN_CASES[name]
