@@ -129,3 +129,35 @@ def test_label_and_preview_output_stages():
         run_plan(plan, {"img": img.data_ptr(), "out": prev.data_ptr()}, last_op=eng.preview_op(plan, ph, pw))
         want = O.resize_nearest(labels[0].numpy().astype(np.int8), pw, ph)
         assert np.array_equal(prev[0].numpy().astype(np.int8), want)
+
+
+@pytest.mark.parametrize("arch,backbone,H,W", [
+    ("td4_psp18", "resnet18", 65, 97), ("td4_psp18", "resnet18", 120, 200), ("td2_psp50", "resnet34", 72, 136),
+    ("td2_fa", "resnet18", 96, 160), ("td2_fa", "resnet18", 130, 210), ("pspnet", "resnet18", 70, 110)])
+def test_plans_at_sizes_without_fixtures_match_the_oracle(arch, backbone, H, W):
+    """Odd input sizes that no fixture covers (ragged maps, key grids that do not divide, `up` frames of FANet): the
+    interpreted plan against the CPU oracle on the same synthetic weights, warm-up into steady state."""
+    from common import make_fanet_oracle, make_oracle, make_pspnet_oracle
+    m = A.build_arch(arch, backbone, 19)
+    ln = A.feature_hw(H, W) if arch != "pspnet" else (0, 0)
+    if arch == "td2_fa":
+        oracle, sd = make_fanet_oracle(backbone, H, W)
+    elif arch == "pspnet":
+        oracle, sd = make_pspnet_oracle(backbone)
+    else:
+        oracle, sd = make_oracle(arch, backbone, H, W)
+    eng = Engine(m, sd, 1, H, W, torch.device("cpu"), ln, mode="tc")
+    frames = synth_clip(m.depth + 3, H, W, clip_id=6)
+    for i in range(m.depth + 2):
+        cur = frames[i + 1].contiguous()
+        out = torch.empty(1, 19, H, W)
+        if arch == "td2_fa":
+            prev = frames[i].contiguous()
+            ref = oracle([prev, cur], pos_id=i % 2)
+            run_plan(eng.plan(i % 2 + 1, True), {"img": cur.data_ptr(), "img2": prev.data_ptr(), "out": out.data_ptr()})
+        else:
+            ref = oracle(cur, pos_id=i % m.paths)
+            run_plan(eng.plan(i % m.paths + 1, i >= m.depth), {"img": cur.data_ptr(), "out": out.data_ptr()})
+        scale = max(1.0, float(ref.abs().max()))
+        assert max_abs(out, ref) <= 2e-4 * scale, (arch, H, W, i, max_abs(out, ref))
+    assert int(eng.range_flag.item()) == 0
