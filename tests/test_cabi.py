@@ -49,3 +49,20 @@ def test_struct_layout_matches_header(lib):
     # tdn_tensor: 2 pointers, 5 int32 (+pad), 3 int64
     assert ctypes.sizeof(_cabi.Tensor) == 8 + 8 + 4 * 5 + 4 + 8 * 3
     assert _cabi.Conv2dDesc.weight.offset == 3 * ctypes.sizeof(_cabi.Tensor)
+
+
+def test_plain_c_consumer_links_and_runs(lib, tmp_path):
+    """examples/abi_smoke.c: a C99 program linked against the library (no Python, no torch in the boundary); the GPU-less
+    build checks version / error strings / workspace sizing and the argument validation done before any CUDA call."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    exe = tmp_path / "abi_smoke"
+    libdir = os.path.dirname(_cabi.LIB_PATH)
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "abi_smoke.c"), "-L", libdir, "-ltdnet_b200",
+                           f"-Wl,-rpath,{libdir}", "-o", str(exe)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and "abi_smoke: ok" in out.stdout, out.stderr
