@@ -34,6 +34,7 @@ FRAME_GFLOP = 936.2            # algorithmic FLOPs of one frame 
 DOMINANT_GFLOP = 154.62        # layer4 3x3 512->512 dilated conv at 128x256
 ATTN_GFLOP = 77.31             # fused attention-propagation kernel, big hop: 2*32768*2048*(64+512)
 ATTN_EXECUTED_GFLOP = 3 * (68.72 + 2 * 8.59) + 2 * 8.59
+ATTN_TRAFFIC_BYTES = 100.8e6       # same capture for the attention op: (70.3 + 15.6) + (14.8 + 0.0) MB over its two launches
 DOMINANT_TRAFFIC_BYTES = 107.5e6   # ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum (profiles/r01_*)
 N_DISTINCT_FRAMES = 8
 
@@ -353,10 +354,13 @@ def run_ours(args, rank, world):
                 "bound": "tensor", "kernel": "tc_attn_kernel<256> + <128> tail launch (big hop: 32768 queries x 2048 keys, d_k 64, d_v 512; one tdn_attention_tc call)",
                 "achieved": ATTN_GFLOP / attn_ms, "peak": peaks["tflops"], "unit": "TFLOP/s",
                 "frac": ATTN_GFLOP / attn_ms / peaks["tflops"], "ms_per_launch": attn_ms,
+                "traffic": ATTN_TRAFFIC_BYTES,
                 "executed_tflops": ATTN_EXECUTED_GFLOP / attn_ms,
                 "executed_frac": ATTN_EXECUTED_GFLOP / attn_ms / peaks["tflops"],
                 "note": "algorithmic = 2*Pq*P'*(d_k+d_v) = 77.31 GFLOP (SURVEY.md 8d); executed = 3 products x "
-                        "(PV + 2 d_v-slices x QK^T) + the single-product max pass = 275 GFLOP"},
+                        "(PV + 2 d_v-slices x QK^T) + the single-product max pass = 275 GFLOP; traffic = dram "
+                        "read+write bytes of the op's two launches from profiles/r01_prof_attn_split_summary.txt "
+                        "(algorithmic: Q 8 MB + out 67 MB + residual 67 MB, K / V'^T stay in L2)"},
             "cpu_baseline": cpu_baseline() if (world == 1 and not args.no_cpu_baseline) else None,
         }
         print(json.dumps(line), flush=True)
