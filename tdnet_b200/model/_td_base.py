@@ -166,6 +166,28 @@ class TDModel(nn.Module):
             total += e0.elapsed_time(e1)
         return total / reps
 
+    # forward_path1..4 of the reference (td4_psp18.py:137-212, td2_psp50.py:112-143) return the LOW-resolution logits
+    # [n, nclass, H/8, W/8] of one path; forward() adds the bilinear upsample (:227).  Same here: the frame runs through
+    # the engine (FIFO advanced exactly as by forward()) and the head map is returned as a new NCHW tensor.
+    def _forward_path(self, k, img):
+        if not (1 <= k <= self.PATHS):
+            raise AttributeError(f"{type(self).__name__} has no forward_path{k} (path_num = {self.PATHS})")
+        self.forward(img, pos_id=k - 1)
+        _, plan = self._last
+        return plan.taps["head"].torch().permute(0, 3, 1, 2).contiguous()
+
+    def forward_path1(self, img):
+        return self._forward_path(1, img)
+
+    def forward_path2(self, img):
+        return self._forward_path(2, img)
+
+    def forward_path3(self, img):
+        return self._forward_path(3, img)
+
+    def forward_path4(self, img):
+        return self._forward_path(4, img)
+
     def forward_labels(self, img, pos_id=0):
         """Same frame step as forward(), but returns the uint8 label map [n, H, W] =
         forward(img, pos_id).max(1)[1] (Testing/test.py:61) computed by a fused upsample + arg-max kernel:

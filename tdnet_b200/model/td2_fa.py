@@ -78,6 +78,19 @@ class td2_fa(TDModel):  # noqa: N801
     def reset(self):
         pass
 
+    def forward_path1(self, f_img):
+        """td2_fa.py:87-131: sub-network 1 on the current frame; full-resolution logits (the reference interpolates
+        inside forward_path1/2 for this model)."""
+        return self.forward(f_img, pos_id=0)
+
+    def forward_path2(self, f_img):
+        return self.forward(f_img, pos_id=1)
+
+    def forward_path3(self, f_img):
+        raise AttributeError("td2_fa has two paths")
+
+    forward_path4 = forward_path3
+
     def forward_labels(self, f_img, pos_id=0):
         """uint8 label map [n, H, W] = forward(f_img, pos_id=pos_id).max(1)[1], fused upsample + arg-max."""
         return self.forward(f_img, pos_id=pos_id, _labels=True)

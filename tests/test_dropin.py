@@ -102,3 +102,24 @@ def test_td2_fa_constructor_state_dict_and_pretrained_init(tmp_path):
     torch.save(single, path)
     with pytest.raises(RuntimeError, match="missing"):
         td2_fa.td2_fa(nclass=19, backbone="resnet18", path_num=2, mdl_path=str(path))
+
+
+def test_forward_path_methods_mirror_the_reference_surface():
+    """forward_path1..4 (td4_psp18.py:137-212) / forward_path1..2 (td2_psp50.py:112-143, td2_fa.py:87-186) exist with the
+    reference's arity; like everything else they refuse CPU tensors instead of falling back."""
+    from tdnet_b200.model import td2_fa, td2_psp50, td4_psp18
+    x = torch.zeros(1, 3, 32, 32)
+    td4 = td4_psp18.td4_psp18(nclass=19, path_num=4).eval()
+    for k in range(1, 5):
+        with pytest.raises(RuntimeError, match="no CPU path"):
+            getattr(td4, f"forward_path{k}")(x)
+    td2 = td2_psp50.td2_psp50(nclass=19, path_num=2, backbone="resnet18").eval()
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        td2.forward_path2(x)
+    with pytest.raises(AttributeError):
+        td2.forward_path3(x)
+    fa = td2_fa.td2_fa(nclass=19, backbone="resnet18", path_num=2).eval()
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        fa.forward_path1([x, x])
+    with pytest.raises(AttributeError):
+        fa.forward_path3([x, x])
