@@ -26,57 +26,11 @@
 // (row max / sum exchanged through shared memory).
 // TMEM: S double-buffered 2 x 64 columns, O DVT columns.  Shared memory: Q 32 KB, K ring 2 x 16 KB,
 // V ring 3 x 32 KB (128-row halves of the V'^T tile), P double buffer 2 x 32 KB (hi+lo planes each).
-#include "common.cuh"
-#include "tc_common.cuh"   // tc_launch / tc_pdl_sync (programmatic dependent launch); pulls in tc_ptx.cuh
+#include "tc_attn.cuh"
 
 #include <string.h>
-#include <cuda.h>
 
 namespace tdn {
-
-using namespace ptx;
-
-constexpr int AT_BQ = 128;       // queries per item
-constexpr int AT_BK = 64;        // keys per tile (= one 128-byte swizzle row of fp16)
-constexpr int AT_BK1 = 128;      // keys per PASS-1 tile (hi planes only: two 64-key boxes fill one K stage)
-constexpr int AT_DK = 64;        // d_k (fixed by the model: Encoding(d_model, 64, d_v))
-constexpr int AT_DVH = 128;      // V'^T rows per shared-memory stage / per PV MMA (N = 128)
-constexpr int AT_THREADS = 352;  // warp 0 TMA, warp 1 S-MMA issuer, warps 2-9 softmax + epilogue, warp 10 PV-MMA issuer
-constexpr int AT_PV_WARP = 10;
-constexpr int AT_SOFTMAX_THREADS = 256;
-constexpr int AT_SOFTMAX_WARPS = AT_SOFTMAX_THREADS / 32;
-constexpr int AT_Q_PLANE = AT_BQ * AT_DK * 2;   // 16 KB
-constexpr int AT_K_PLANE = AT_BK * AT_DK * 2;   // 8 KB
-constexpr int AT_V_PLANE = AT_DVH * AT_BK * 2;  // 16 KB
-constexpr int AT_P_PLANE = AT_BQ * AT_BK * 2;   // 16 KB
-constexpr int AT_KSTAGES = 2, AT_VSTAGES = 3;
-constexpr int AT_SMEM_DATA = 2 * AT_Q_PLANE + AT_KSTAGES * 2 * AT_K_PLANE + AT_VSTAGES * 2 * AT_V_PLANE + 2 * 2 * AT_P_PLANE;
-constexpr int AT_TMEM_COLS = 512;   // S: 2 x 64 columns, O: up to 256 columns
-constexpr float AT_P_SCALE = 1024.f;
-
-// 2^x through one MUFU.EX2 (2 ulp; results below the normal range flush to zero, which is what a
-// probability that small should do).  The libm exp2f spends ~6 more instructions on range handling.
-__device__ __forceinline__ float fast_exp2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-struct AttnParams {
-  int n_img, Pq, Pk;
-  int q_tiles, dv_tiles, k_tiles, k_tiles1, num_items;   // k_tiles: 64-key tiles (pass 2); k_tiles1: 128-key tiles (pass 1)
-  int qt_begin;             // first query tile of this launch (q_tiles counts the tiles of the launch)
-  float scale_log2;         // log2(e) / sqrt(d_k)
-  __half* out_hi;
-  __half* out_lo;
-  float* out_f32;
-  long long o_bs, o_ld;     // batch stride / row pitch (elements)
-  const __half* res_hi;
-  const __half* res_lo;
-  const float* res_f32;
-  long long r_bs, r_ld;
-  int* range_flag;
-};
 
 struct AttnBars {
   uint64_t q_full, q_empty;
@@ -508,12 +462,18 @@ int attention_tc(const tdn_attention_desc* d, cudaStream_t stream) {
   TDN_REQUIRE(d->d_v % AT_DVH == 0, TDN_ERR_UNSUPPORTED, "attention_tc: d_v=%d must be a multiple of 128", d->d_v);
   // 256-wide slices halve the QK^T / softmax recompute; small problems (the FIFO hops with P' queries) would
   // not fill the SMs with them, so they take 128-wide slices = twice as many work items.
-  static int num_sms_cached = 0;
-  if (num_sms_cached == 0) {
-    int dev = 0;
-    TDN_CUDA_OK(cudaGetDevice(&dev));
-    TDN_CUDA_OK(cudaDeviceGetAttribute(&num_sms_cached, cudaDevAttrMultiProcessorCount, dev));
+  int dev = 0, num_sms = 0;
+  TDN_CUDA_OK(cudaGetDevice(&dev));
+  {
+    static int sms_of[64] = {};                      // per device ordinal (a process may drive several GPUs)
+    if (dev < 0 || dev >= 64 || sms_of[dev] == 0) {
+      TDN_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+      if (dev >= 0 && dev < 64) sms_of[dev] = num_sms;
+    } else {
+      num_sms = sms_of[dev];
+    }
   }
+  const int num_sms_cached = num_sms;
   const long long items256 = (long long)d->n * ceil_div(d->pq, AT_BQ) * (d->d_v / 256);
   const int dvt_size = (d->d_v % 256 == 0 && items256 >= num_sms_cached) ? 256 : 128;
   TDN_REQUIRE(d->n > 0 && d->pq > 0 && d->pk > 0, TDN_ERR_INVALID, "attention_tc: empty problem");
@@ -561,6 +521,7 @@ int attention_tc(const tdn_attention_desc* d, cudaStream_t stream) {
     p.r_bs = r.stride_n; p.r_ld = r.stride_w;
   }
   p.range_flag = d->range_flag;
+  { const char* e = getenv("TDNET_ATTN_DEBUG"); p.debug = e ? atoi(e) : 0; }
 
   CUtensorMap mq_h, mq_l, mk_h, mk_l, mv_h, mv_l;
   int rc;
@@ -587,18 +548,26 @@ int attention_tc(const tdn_attention_desc* d, cudaStream_t stream) {
     if ((rc = encode_map_f16(&mv_h, d->vt_hi, 3, dims, str, box, "Vt.hi", nullptr))) return rc;
     if ((rc = encode_map_f16(&mv_l, d->vt_lo, 3, dims, str, box, "Vt.lo", nullptr))) return rc;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    TDN_CUDA_OK(cudaFuncSetAttribute(tc_attn_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES));
-    TDN_CUDA_OK(cudaFuncSetAttribute(tc_attn_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES));
-    attr_set = true;
+  // Kernel family: 1 (default) = tc_attn_ts.cu, probabilities handed to the P.V' MMAs through tensor memory;
+  // 0 = the kernels of this file (P through shared memory), kept as the yardstick.  TDNET_ATTN_TS selects.
+  // (read on every call: the probes and tests flip it inside one process)
+  const char* ts_env = getenv("TDNET_ATTN_TS");
+  const bool use_ts = ts_env ? atoi(ts_env) != 0 : true;
+  {
+    static bool attr_set[64] = {};                   // the > 48 KB shared-memory opt-in is per device
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+      TDN_CUDA_OK(cudaFuncSetAttribute(tc_attn_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES));
+      TDN_CUDA_OK(cudaFuncSetAttribute(tc_attn_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES));
+      if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
   }
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    TDN_CUDA_OK(cudaGetDevice(&dev));
-    TDN_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  auto launch = [&](int dvt, int grid, const AttnParams& pp) -> cudaError_t {
+    const bool short_launch = pp.num_items <= 2 * grid;
+    if (use_ts) return attention_ts_launch(dvt, grid, stream, short_launch, mq_h, mq_l, mk_h, mk_l, mv_h, mv_l, pp);
+    if (dvt == 256)
+      return tc_launch(tc_attn_kernel<256>, grid, AT_THREADS, AT_SMEM_BYTES, stream, short_launch, mq_h, mq_l, mk_h, mk_l, mv_h, mv_l, pp);
+    return tc_launch(tc_attn_kernel<128>, grid, AT_THREADS, AT_SMEM_BYTES, stream, short_launch, mq_h, mq_l, mk_h, mk_l, mv_h, mv_l, pp);
+  };
   // Wave quantisation: the persistent grid walks the items in rounds of one per SM, and a ragged last round
   // costs a full item time (big hop at 1024x2048: 512 items on 148 SMs = 3.46 rounds -> 4).  When the item count
   // is not a multiple of the SM count, the query tiles of the full rounds run as 256-wide items and the
@@ -625,16 +594,13 @@ int attention_tc(const tdn_attention_desc* d, cudaStream_t stream) {
       p2.qt_begin = q1; p2.q_tiles = q2; p2.dv_tiles = d->d_v / 128; p2.num_items = (int)items2;
       const int g1 = p1.num_items < num_sms ? p1.num_items : num_sms;
       const int g2 = p2.num_items < num_sms ? p2.num_items : num_sms;
-      TDN_CUDA_OK(tc_launch(tc_attn_kernel<256>, g1, AT_THREADS, AT_SMEM_BYTES, stream, p1.num_items <= 2 * g1, mq_h, mq_l, mk_h, mk_l, mv_h, mv_l, p1));
-      TDN_CUDA_OK(tc_launch(tc_attn_kernel<128>, g2, AT_THREADS, AT_SMEM_BYTES, stream, p2.num_items <= 2 * g2, mq_h, mq_l, mk_h, mk_l, mv_h, mv_l, p2));
+      TDN_CUDA_OK(launch(256, g1, p1));
+      TDN_CUDA_OK(launch(128, g2, p2));
       return TDN_OK;
     }
   }
   int grid = p.num_items < num_sms ? p.num_items : num_sms;
-  if (dvt_size == 256)
-    TDN_CUDA_OK(tc_launch(tc_attn_kernel<256>, grid, AT_THREADS, AT_SMEM_BYTES, stream, p.num_items <= 2 * grid, mq_h, mq_l, mk_h, mk_l, mv_h, mv_l, p));
-  else
-    TDN_CUDA_OK(tc_launch(tc_attn_kernel<128>, grid, AT_THREADS, AT_SMEM_BYTES, stream, p.num_items <= 2 * grid, mq_h, mq_l, mk_h, mk_l, mv_h, mv_l, p));
+  TDN_CUDA_OK(launch(dvt_size, grid, p));
   return TDN_OK;
 }
 

@@ -1,0 +1,62 @@
+// Shared pieces of the fused attention-propagation kernels (tc_attn.cu: P through shared memory;
+// tc_attn_ts.cu: P through tensor memory): tile constants, the parameter block and the exp2 helper.
+#pragma once
+#include "common.cuh"
+#include "tc_common.cuh"   // tc_launch / tc_pdl_sync (programmatic dependent launch); pulls in tc_ptx.cuh
+
+#include <cuda.h>
+
+namespace tdn {
+
+using namespace ptx;
+
+constexpr int AT_BQ = 128;       // queries per item
+constexpr int AT_BK = 64;        // keys per tile (= one 128-byte swizzle row of fp16)
+constexpr int AT_BK1 = 128;      // keys per PASS-1 tile (hi planes only: two 64-key boxes fill one K stage)
+constexpr int AT_DK = 64;        // d_k (fixed by the model: Encoding(d_model, 64, d_v))
+constexpr int AT_DVH = 128;      // V'^T rows per shared-memory stage / per PV MMA (N = 128)
+constexpr int AT_THREADS = 352;  // warp 0 TMA, warp 1 S-MMA issuer, warps 2-9 softmax + epilogue, warp 10 PV-MMA issuer
+constexpr int AT_PV_WARP = 10;
+constexpr int AT_SOFTMAX_THREADS = 256;
+constexpr int AT_SOFTMAX_WARPS = AT_SOFTMAX_THREADS / 32;
+constexpr int AT_Q_PLANE = AT_BQ * AT_DK * 2;   // 16 KB
+constexpr int AT_K_PLANE = AT_BK * AT_DK * 2;   // 8 KB
+constexpr int AT_V_PLANE = AT_DVH * AT_BK * 2;  // 16 KB
+constexpr int AT_P_PLANE = AT_BQ * AT_BK * 2;   // 16 KB
+constexpr int AT_KSTAGES = 2, AT_VSTAGES = 3;
+constexpr int AT_SMEM_DATA = 2 * AT_Q_PLANE + AT_KSTAGES * 2 * AT_K_PLANE + AT_VSTAGES * 2 * AT_V_PLANE + 2 * 2 * AT_P_PLANE;
+constexpr int AT_TMEM_COLS = 512;   // S: 2 x 64 columns, O: up to 256 columns
+constexpr float AT_P_SCALE = 1024.f;
+
+// 2^x through one MUFU.EX2 (2 ulp; results below the normal range flush to zero, which is what a
+// probability that small should do).  The libm exp2f spends ~6 more instructions on range handling.
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+struct AttnParams {
+  int n_img, Pq, Pk;
+  int q_tiles, dv_tiles, k_tiles, k_tiles1, num_items;   // k_tiles: 64-key tiles (pass 2); k_tiles1: 128-key tiles (pass 1)
+  int qt_begin;             // first query tile of this launch (q_tiles counts the tiles of the launch)
+  float scale_log2;         // log2(e) / sqrt(d_k)
+  __half* out_hi;
+  __half* out_lo;
+  float* out_f32;
+  long long o_bs, o_ld;     // batch stride / row pitch (elements)
+  const __half* res_hi;
+  const __half* res_lo;
+  const float* res_f32;
+  long long r_bs, r_ld;
+  int* range_flag;
+  int debug;                // energy-attribution experiments (TDNET_ATTN_DEBUG bit mask, tc_attn_ts.cu only); 0 in production
+};
+
+
+// tc_attn_ts.cu: launch of the TMEM-operand kernel family (dvt = 128 or 256 output channels per work item).
+cudaError_t attention_ts_launch(int dvt, int grid, cudaStream_t stream, bool short_launch, const CUtensorMap& mq_h,
+                                const CUtensorMap& mq_l, const CUtensorMap& mk_h, const CUtensorMap& mk_l,
+                                const CUtensorMap& mv_h, const CUtensorMap& mv_l, const AttnParams& p);
+
+}  // namespace tdn

@@ -150,6 +150,29 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem desc]: the A operand (M = 128 rows = TMEM lanes, K-major, two fp16 per 32-bit
+// column, i.e. 8 columns per K16 step) is read from tensor memory instead of shared memory.
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 16 consecutive 32-bit columns, registers -> tensor memory (thread t writes lane base_lane + t).
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ----------------------------------------------------------------------------- CTA pairs (cta_group::2)
 // A thread-block cluster of two CTAs drives ONE tcgen05.mma over both SMs (M = 256: rows 0-127 accumulate in
@@ -250,6 +273,16 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
          | (0u << 15) | (0u << 16)      // a_major = b_major = K
          | ((uint32_t)(N >> 3) << 17)   // n_dim
          | ((uint32_t)(M >> 4) << 24);  // m_dim
+}
+
+// Same with an fp16 accumulator (c_format = F16): two N elements per 32-bit TMEM column, i.e. an N-wide tile
+// occupies N / 2 columns.  Used where only a coarse result is needed (row maxima of the attention scores).
+__host__ __device__ constexpr uint32_t umma_idesc_f16_acc16(int M, int N) {
+  return (0u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
 // Programmatic dependent launch.  `griddep_wait` blocks until every grid this one depends on has completed and its
