@@ -521,7 +521,6 @@ int attention_tc(const tdn_attention_desc* d, cudaStream_t stream) {
     p.r_bs = r.stride_n; p.r_ld = r.stride_w;
   }
   p.range_flag = d->range_flag;
-  { const char* e = getenv("TDNET_ATTN_DEBUG"); p.debug = e ? atoi(e) : 0; }
 
   CUtensorMap mq_h, mq_l, mk_h, mk_l, mv_h, mv_l;
   int rc;

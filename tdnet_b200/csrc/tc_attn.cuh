@@ -50,7 +50,6 @@ struct AttnParams {
   const float* res_f32;
   long long r_bs, r_ld;
   int* range_flag;
-  int debug;                // energy-attribution experiments (TDNET_ATTN_DEBUG bit mask, tc_attn_ts.cu only); 0 in production
 };
 
 

@@ -18,10 +18,13 @@
 // 2 x 32 KB P double buffer becomes a fourth V'^T stage and a third K stage, and the generic->async proxy fence per
 // tile is gone.  With four S/P buffers the S issuer runs up to three key tiles ahead of P.V'.
 //
-// Warp roles (384 threads): warp 0 TMA producer for Q and K; warp 11 TMA producer for V'^T (a full V ring must not
-// hold back the key tiles S needs); warp 1 issues S = Q.K^T (both passes); warp 10 issues O += P.V'^T;
-// warps 2-9 softmax + epilogue, two per TMEM lane quarter (group g owns key columns [32g, 32g+32) of a tile and
-// output channels [g*DVT/2, (g+1)*DVT/2)).
+// Warp roles (512 threads): warp 0 TMA producer for Q and K; warp 3 TMA producer for V'^T (a full V ring must not
+// hold back the key tiles S needs); warp 1 issues S = Q.K^T (both passes); warp 2 issues O += P.V'^T;
+// warps 4-11 softmax, two per TMEM lane quarter (group g owns key columns [32g, 32g+32) of a tile);
+// warps 12-15 epilogue, one per lane quarter (out = O / l + residual for all DVT channels of 32 query rows).
+// The epilogue of item i runs NEXT TO pass 1 and the first softmax tiles of item i+1: ncu of the previous layout
+// (the softmax warps also ran the epilogue) showed 22 % of an item in the epilogue and 13 % in pass 1 with the P.V'
+// pipe idle in both; the row sums reach the epilogue warps through shared memory.
 // TMEM (512 columns): O = columns [0, DVT); S/P buffer b = columns [256 + 64 b, 256 + 64 b + 64).  Pass 1 (row maxima of
 // S~ = Qhi.Khi^T, 128-key tiles) uses the buffers pairwise as two 128-column tiles.
 // Shared memory: Q 32 KB, K ring 3 x 16 KB, V'^T ring 4 x 32 KB (128-row halves of a key tile).
@@ -29,12 +32,17 @@
 
 namespace tdn {
 
-constexpr int ATS_THREADS = 384;
-constexpr int ATS_PV_WARP = 10;
-constexpr int ATS_V_WARP = 11;
+constexpr int ATS_THREADS = 512;
+constexpr int ATS_PV_WARP = 2;
+constexpr int ATS_V_WARP = 3;
+constexpr int ATS_SOFTMAX_WARP0 = 4;      // warps 4-11
+constexpr int ATS_EPI_WARP0 = 12;         // warps 12-15
+constexpr int ATS_EPI_WARPS = 4;
 constexpr int ATS_KSTAGES = 3, ATS_VSTAGES = 4;
 constexpr int ATS_SP = 4;                          // S/P buffers of 64 TMEM columns
-constexpr int ATS_SMEM_DATA = 2 * AT_Q_PLANE + ATS_KSTAGES * 2 * AT_K_PLANE + ATS_VSTAGES * 2 * AT_V_PLANE;
+constexpr int ATS_EPI_STAGE = 4096;                // per epilogue warp: 32 rows x 128 B turn-around block
+constexpr int ATS_SMEM_DATA = 2 * AT_Q_PLANE + ATS_KSTAGES * 2 * AT_K_PLANE + ATS_VSTAGES * 2 * AT_V_PLANE +
+                              ATS_EPI_WARPS * ATS_EPI_STAGE;
 
 struct AttnTsBars {
   uint64_t q_full, q_empty;
@@ -43,8 +51,10 @@ struct AttnTsBars {
   uint64_t s1_full[2], s1_empty[2];                // pass 1: S~ tile ready / read by the softmax warps
   uint64_t s_full[ATS_SP], p_full[ATS_SP], sp_empty[ATS_SP];   // pass 2: S ready / P written / P consumed by P.V'
   uint64_t o_full, o_empty;
+  uint64_t l_full, l_empty;                        // row sums of an item written / read by the epilogue warps
   uint32_t tmem_ptr;
-  float xch[2][AT_BQ];     // row max / row sum exchange between the two softmax warp groups
+  float xch[2][AT_BQ];     // row max exchange between the two softmax warp groups, then their partial row sums
+                           // for the epilogue warps (rewritten only after l_empty of the previous item)
 };
 
 constexpr int ATS_SMEM_BYTES = ATS_SMEM_DATA + 1024 /*alignment slack*/ + ((int)sizeof(AttnTsBars) + 127) / 128 * 128;
@@ -61,7 +71,8 @@ tc_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_const
   uint8_t* sQ = smem;                                            // hi | lo
   uint8_t* sK = sQ + 2 * AT_Q_PLANE;                             // stages x (hi | lo)
   uint8_t* sV = sK + ATS_KSTAGES * 2 * AT_K_PLANE;               // stages x (hi | lo)
-  AttnTsBars* bars = reinterpret_cast<AttnTsBars*>(sV + ATS_VSTAGES * 2 * AT_V_PLANE);
+  uint8_t* sE = sV + ATS_VSTAGES * 2 * AT_V_PLANE;               // epilogue turn-around blocks
+  AttnTsBars* bars = reinterpret_cast<AttnTsBars*>(sE + ATS_EPI_WARPS * ATS_EPI_STAGE);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -84,7 +95,9 @@ tc_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_const
       mbar_init(&bars->sp_empty[s], 1);
     }
     mbar_init(&bars->o_full, 1);
-    mbar_init(&bars->o_empty, AT_SOFTMAX_WARPS);
+    mbar_init(&bars->o_empty, ATS_EPI_WARPS);
+    mbar_init(&bars->l_full, AT_SOFTMAX_WARPS);
+    mbar_init(&bars->l_empty, ATS_EPI_WARPS);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -99,7 +112,7 @@ tc_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_const
   const uint32_t tmem_O = tmem_base;
   const uint32_t tmem_SP = tmem_base + 256;      // + b * 64
   const int T = p.k_tiles;
-  const int T1 = (p.debug & 1) ? 0 : p.k_tiles1;
+  const int T1 = p.k_tiles1;
   constexpr int HALVES = DVT / AT_DVH;
 
   if (warp == 0) {
@@ -207,7 +220,6 @@ tc_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_const
           for (int k = 0; k < AT_DK / 16; ++k) {
             const uint64_t a_h = umma_desc_k_sw128(q_hi + k * 32), b_h = umma_desc_k_sw128(k_hi + k * 32);
             const uint64_t a_l = umma_desc_k_sw128(q_lo + k * 32), b_l = umma_desc_k_sw128(k_lo + k * 32);
-            if (p.debug & 2) { umma_f16(d, a_h, b_h, idesc_s, k != 0); continue; }
             umma_f16(d, a_h, b_l, idesc_s, k != 0);
             umma_f16(d, a_l, b_h, idesc_s, 1);
             umma_f16(d, a_h, b_h, idesc_s, 1);
@@ -245,7 +257,6 @@ tc_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_const
               // lo pairs 16 columns further
               const uint32_t a_h = p_base + (k >> 1) * 32 + (k & 1) * 8, a_l = a_h + 16;
               const uint64_t b_h = umma_desc_k_sw128(v_hi + k * 32), b_l = umma_desc_k_sw128(v_lo + k * 32);
-              if (p.debug & 4) { umma_f16_ts(d, a_h, b_h, idesc_o, (kt | k) != 0); continue; }
               umma_f16_ts(d, a_h, b_l, idesc_o, (kt | k) != 0);
               umma_f16_ts(d, a_l, b_h, idesc_o, 1);
               umma_f16_ts(d, a_h, b_h, idesc_o, 1);
@@ -262,26 +273,18 @@ tc_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_const
       }
       oph ^= 1;
     }
-  } else {
-    // ================================ softmax + epilogue warps ================================
+  } else if (warp < ATS_EPI_WARP0) {
+    // ================================ softmax warps ================================
     const int quarter = warp & 3;
-    const int group = (warp - 2) >> 2;
+    const int group = (warp - ATS_SOFTMAX_WARP0) >> 2;
     const int row = quarter * 32 + lane;                      // query row inside the tile = TMEM lane
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-    uint32_t oph = 0;
     uint32_t n1 = 0, n2 = 0;                                  // same counting as MMA issuer 1
-    bool out_of_range = false;
+    uint32_t items_done = 0;
     auto group_sync = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };
-    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-      const int dvt = item % p.dv_tiles;
-      int t = item / p.dv_tiles;
-      const int qt = p.qt_begin + t % p.q_tiles;
-      const int img = t / p.q_tiles;
-      const int q_idx = qt * AT_BQ + row;
-      const bool valid = q_idx < p.Pq;
-
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++items_done) {
       // ---- pass 1: row maximum of S~; 128-key tiles, this group's 64 key columns of each
-      float m = (p.debug & 1) ? 40.f : -INFINITY;
+      float m = -INFINITY;
       for (int kt = 0; kt < T1; ++kt, ++n1) {
         const int pair = n1 & 1;
         mbar_wait(&bars->s1_full[pair], (n1 >> 1) & 1);
@@ -289,12 +292,8 @@ tc_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_const
         uint32_t r0[32], r1[32];
         const uint32_t src = tmem_SP + pair * AT_BK1 + lane_addr + group * 64;
         tmem_ld_32x32(src, r0);
-        if (!(p.debug & 16)) tmem_ld_32x32(src + 32, r1);
+        tmem_ld_32x32(src + 32, r1);
         tmem_ld_wait();
-        if (p.debug & 16) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) r1[j] = r0[j];
-        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->s1_empty[pair]);      // the tile is in registers: hand the buffer back first
@@ -315,30 +314,16 @@ tc_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_const
           }
         }
       }
+      mbar_wait(&bars->l_empty, (items_done & 1) ^ 1);         // the row sums of the previous item have been read
       bars->xch[group][row] = m;
       group_sync();
       m = fmaxf(m, bars->xch[group ^ 1][row]);
-      group_sync();                                           // xch is reused for the row sums below
+      group_sync();                                           // xch carries the row sums next
       // exponent offset of pass 2: the row maximum AND log2 of the 2^10 probability scale, so that one FMA + one
       // MUFU.EX2 yield p * 2^10 directly (the row sum l is then scaled by 2^10 as well: out = O / l)
       const float m_scaled = m * p.scale_log2 - 10.f;
       static_assert(AT_P_SCALE == 1024.f, "the exponent offset above assumes a 2^10 probability scale");
 
-      // the residual rows this thread adds in the epilogue come from HBM: pull them into L2 now
-      {
-        constexpr int COLS_ = DVT / 2;
-        const long long rb_ = (long long)img * p.r_bs + (long long)q_idx * p.r_ld + dvt * DVT + group * COLS_;
-        if (valid && p.res_hi) {
-#pragma unroll
-          for (int c = 0; c < COLS_ * 2; c += 128) {
-            prefetch_l2(reinterpret_cast<const char*>(p.res_hi + rb_) + c);
-            prefetch_l2(reinterpret_cast<const char*>(p.res_lo + rb_) + c);
-          }
-        } else if (valid && p.res_f32) {
-#pragma unroll
-          for (int c = 0; c < COLS_ * 4; c += 128) prefetch_l2(reinterpret_cast<const char*>(p.res_f32 + rb_) + c);
-        }
-      }
       // ---- pass 2: S -> probabilities, written back over S as packed fp16 hi / lo pairs; partial row sum
       float l = 0.f;
       for (int kt = 0; kt < T; ++kt, ++n2) {
@@ -353,9 +338,7 @@ tc_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_const
           tmem_ld_wait();
           const int kbase = kt * AT_BK + group * 32;
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            pr[j] = (p.debug & 8) ? fmaf(__uint_as_float(r[j]), p.scale_log2, 40.f)
-                                  : fast_exp2(fmaf(__uint_as_float(r[j]), p.scale_log2, -m_scaled));
+          for (int j = 0; j < 32; ++j) pr[j] = fast_exp2(fmaf(__uint_as_float(r[j]), p.scale_log2, -m_scaled));
           if (kbase + 32 > p.Pk) {                              // ragged last tile: keys past P' contribute nothing
 #pragma unroll
             for (int j = 0; j < 32; ++j) pr[j] = (kbase + j < p.Pk) ? pr[j] : 0.f;
@@ -367,8 +350,6 @@ tc_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_const
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
           __half2 hi, lo;
-          if (p.debug & 8) { hi = __floats2half2_rn(pr[2 * e], pr[2 * e + 1]); lo = hi; }
-          else
           split_f32x2(pr[2 * e], pr[2 * e + 1], hi, lo);        // key 2e in the low half, key 2e+1 in the high half
           ph[e] = *reinterpret_cast<const uint32_t*>(&hi);
           pl[e] = *reinterpret_cast<const uint32_t*>(&lo);
@@ -380,85 +361,154 @@ tc_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_const
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->p_full[sb]);
       }
+      // ---- hand the partial row sum to the epilogue warps (they add the two groups in a fixed order)
       bars->xch[group][row] = l;
-      group_sync();
-      l += bars->xch[group ^ 1][row];
-      group_sync();
-
-      // ---- epilogue: out = O / l + residual; this group's half of the channel slice.  The SPLIT16 residual of
-      //      chunk c+1 is requested before chunk c is processed (and chunk 0 before O is even complete).
-      constexpr int COLS = DVT / 2;
-      constexpr int NCHUNK = COLS / 32;
-      const int cbase = dvt * DVT + group * COLS;
-      const long long obase = (long long)img * p.o_bs + (long long)q_idx * p.o_ld + cbase;
-      const long long rbase = (long long)img * p.r_bs + (long long)q_idx * p.r_ld + cbase;
-      const bool res16 = valid && p.res_hi != nullptr;
-      uint4 rbuf[2][8];                                        // [buffer][4 x hi | 4 x lo] = 32 channels
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->l_full);               // release: orders the stores above
+    }
+  } else {
+    // ================================ epilogue warps ================================
+    // out = O / l + residual for the 32 query rows of this warp's TMEM lane quarter, all DVT channels, 32 at a time.
+    // O arrives with one query row per thread (TMEM lane = row), but a warp-wide 16-byte access with one ROW per
+    // thread touches 32 cache lines (ncu: the epilogue was bound by the L1 tag stage, stall_lg + long scoreboard).
+    // So global memory is accessed with 4 (fp16 planes: 64-byte row pieces) or 8 (fp32: 128-byte row pieces)
+    // consecutive lanes per row -- 8 or 4 lines per instruction -- and a 4 KB shared-memory block per warp turns
+    // between the two arrangements: residual global -> regs (one chunk ahead) -> block -> row per thread; result
+    // row per thread -> block -> global.  16-byte pieces are XOR-swizzled so that both arrangements are conflict-free.
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    uint8_t* stg = sE + (warp - ATS_EPI_WARP0) * ATS_EPI_STAGE;
+    // fp16 plane (32 rows x 64 B): lanes 4r'..4r'+3 cover a row piece; fp32 (32 rows x 128 B): lanes 8r'..8r'+7
+    const int rA = lane >> 2, cA = lane & 3, rB = lane >> 3, cB = lane & 7;
+    auto offA = [](int r, int c) { return r * 64 + ((c ^ ((r >> 1) & 3)) << 4); };
+    auto offB = [](int r, int c) { return r * 128 + ((c ^ (r & 7)) << 4); };
+    uint32_t iph = 0;
+    bool out_of_range = false;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      const int dvt = item % p.dv_tiles;
+      int t = item / p.dv_tiles;
+      const int qt = p.qt_begin + t % p.q_tiles;
+      const int img = t / p.q_tiles;
+      const int q0 = qt * AT_BQ + quarter * 32;                // first query row of this warp
+      constexpr int NCHUNK = DVT / 32;
+      const int cbase = dvt * DVT;
+      const long long obase = (long long)img * p.o_bs + cbase;
+      const long long rbase = (long long)img * p.r_bs + cbase;
+      uint4 rbuf[8] = {};          // residual of one chunk: [hi k'=0..3 | lo k'=0..3] or fp32 k'=0..7
       auto load_res = [&](int chunk, uint4 (&dst)[8]) {
-        if (res16) {
+        if (p.res_hi) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            dst[q] = __ldg(reinterpret_cast<const uint4*>(p.res_hi + rbase + chunk * 32 + q * 8));
-            dst[4 + q] = __ldg(reinterpret_cast<const uint4*>(p.res_lo + rbase + chunk * 32 + q * 8));
+          for (int k = 0; k < 4; ++k) {
+            const int q = q0 + 8 * k + rA;
+            if (q < p.Pq) {
+              const long long off = rbase + (long long)q * p.r_ld + chunk * 32 + cA * 8;
+              dst[k] = __ldg(reinterpret_cast<const uint4*>(p.res_hi + off));
+              dst[4 + k] = __ldg(reinterpret_cast<const uint4*>(p.res_lo + off));
+            }
+          }
+        } else if (p.res_f32) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int q = q0 + 4 * k + rB;
+            if (q < p.Pq)
+              dst[k] = __ldg(reinterpret_cast<const uint4*>(p.res_f32 + rbase + (long long)q * p.r_ld + chunk * 32 + cB * 4));
           }
         }
       };
-      load_res(0, rbuf[0]);
-      mbar_wait(&bars->o_full, oph);
-      tc_fence_after();
-      oph ^= 1;
+      load_res(0, rbuf);
+      mbar_wait(&bars->l_full, iph);
+      const float l = bars->xch[0][row] + bars->xch[1][row];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->l_empty);
       const float inv = 1.f / l;                               // l carries the 2^10 scale of P
-#pragma unroll
+      mbar_wait(&bars->o_full, iph);
+      tc_fence_after();
+      iph ^= 1;
+#pragma unroll 1
       for (int chunk = 0; chunk < NCHUNK; ++chunk) {
-        if (chunk + 1 < NCHUNK) load_res(chunk + 1, rbuf[(chunk + 1) & 1]);
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_O + lane_addr + group * COLS + chunk * 32, r);
-        tmem_ld_wait();
-        if (valid) {
-          float v[32];
+        // residual of this chunk -> block; its registers then take the loads of the next chunk, which stay in
+        // flight while this chunk is processed
+        const uint4 (&rb)[8] = rbuf;
+        if (p.res_hi) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            *reinterpret_cast<uint4*>(stg + offA(8 * k + rA, cA)) = rb[k];
+            *reinterpret_cast<uint4*>(stg + 2048 + offA(8 * k + rA, cA)) = rb[4 + k];
+          }
+        } else if (p.res_f32) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) *reinterpret_cast<uint4*>(stg + offB(4 * k + rB, cB)) = rb[k];
+        }
+        __syncwarp();
+        if (chunk + 1 < NCHUNK) load_res(chunk + 1, rbuf);
+        float v[32];
+        {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_O + lane_addr + chunk * 32, r);
+          tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * inv;
-          const int c0 = chunk * 32;
-          if (p.res_hi) {
-            const uint4 (&rb)[8] = rbuf[chunk & 1];
+        }
+        if (p.res_hi) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const __half2* hh = reinterpret_cast<const __half2*>(&rb[q]);
-              const __half2* ll = reinterpret_cast<const __half2*>(&rb[4 + q]);
+          for (int q = 0; q < 4; ++q) {
+            const uint4 h4 = *reinterpret_cast<const uint4*>(stg + offA(lane, q));
+            const uint4 l4 = *reinterpret_cast<const uint4*>(stg + 2048 + offA(lane, q));
+            const __half2* hh = reinterpret_cast<const __half2*>(&h4);
+            const __half2* ll = reinterpret_cast<const __half2*>(&l4);
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float2 a = __half22float2(hh[e]), b2 = __half22float2(ll[e]);
-                v[q * 8 + e * 2 + 0] += a.x + b2.x;
-                v[q * 8 + e * 2 + 1] += a.y + b2.y;
-              }
-            }
-          } else if (p.res_f32) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              float4 f = *reinterpret_cast<const float4*>(p.res_f32 + rbase + c0 + q * 4);
-              v[q * 4 + 0] += f.x; v[q * 4 + 1] += f.y; v[q * 4 + 2] += f.z; v[q * 4 + 3] += f.w;
+            for (int e = 0; e < 4; ++e) {
+              float2 a = __half22float2(hh[e]), b2 = __half22float2(ll[e]);
+              v[q * 8 + e * 2 + 0] += a.x + b2.x;
+              v[q * 8 + e * 2 + 1] += a.y + b2.y;
             }
           }
-          if (p.out_f32) {
+        } else if (p.res_f32) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q)
-              *reinterpret_cast<float4*>(p.out_f32 + obase + c0 + q * 4) =
-                  make_float4(v[q * 4 + 0], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-          }
-          if (p.out_hi) {
-            __half2 hi[16], lo[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              out_of_range |= fmaxf(fabsf(v[2 * j]), fabsf(v[2 * j + 1])) > 60000.f;
-              split_f32x2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              *reinterpret_cast<uint4*>(p.out_hi + obase + c0 + q * 8) = *reinterpret_cast<const uint4*>(&hi[q * 4]);
-              *reinterpret_cast<uint4*>(p.out_lo + obase + c0 + q * 8) = *reinterpret_cast<const uint4*>(&lo[q * 4]);
-            }
+          for (int q = 0; q < 8; ++q) {
+            const float4 f = *reinterpret_cast<const float4*>(stg + offB(lane, q));
+            v[q * 4 + 0] += f.x; v[q * 4 + 1] += f.y; v[q * 4 + 2] += f.z; v[q * 4 + 3] += f.w;
           }
         }
+        __syncwarp();                                          // every lane has read its residual row
+        // result row -> block, then out with 4 / 8 lanes per row
+        if (p.out_hi) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            __half2 hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              out_of_range |= fmaxf(fabsf(v[q * 8 + 2 * e]), fabsf(v[q * 8 + 2 * e + 1])) > 60000.f;
+              split_f32x2(v[q * 8 + 2 * e], v[q * 8 + 2 * e + 1], hi[e], lo[e]);
+            }
+            *reinterpret_cast<uint4*>(stg + offA(lane, q)) = *reinterpret_cast<const uint4*>(hi);
+            *reinterpret_cast<uint4*>(stg + 2048 + offA(lane, q)) = *reinterpret_cast<const uint4*>(lo);
+          }
+          __syncwarp();
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int q = q0 + 8 * k + rA;
+            if (q < p.Pq) {
+              const long long off = obase + (long long)q * p.o_ld + chunk * 32 + cA * 8;
+              *reinterpret_cast<uint4*>(p.out_hi + off) = *reinterpret_cast<const uint4*>(stg + offA(8 * k + rA, cA));
+              *reinterpret_cast<uint4*>(p.out_lo + off) = *reinterpret_cast<const uint4*>(stg + 2048 + offA(8 * k + rA, cA));
+            }
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(stg + offB(lane, q)) = make_float4(v[q * 4 + 0], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int q = q0 + 4 * k + rB;
+            if (q < p.Pq)
+              *reinterpret_cast<uint4*>(p.out_f32 + obase + (long long)q * p.o_ld + chunk * 32 + cB * 4) =
+                  *reinterpret_cast<const uint4*>(stg + offB(4 * k + rB, cB));
+          }
+        }
+        __syncwarp();                                          // the block is rewritten by the next chunk
       }
       tc_fence_before();
       __syncwarp();

@@ -27,6 +27,53 @@ def split(t):
     return hi.contiguous(), (t - hi.float()).half().contiguous()
 
 
+def formats(lib):
+    """Every out / residual format pair on two ragged shapes: TS against SS (bit-identical expected) and fp64."""
+    for n, pq, pk, dv in ((2, 1000, 690, 512), (1, 300, 100, 256), (1, 32768, 200, 512)):
+        g = torch.Generator().manual_seed(pq + pk)
+        q, k = torch.randn(n, pq, 64, generator=g) * 1.3, torch.randn(n, pk, 64, generator=g) * 1.4
+        v, r = torch.randn(n, pk, dv, generator=g) * 3, torch.randn(n, pq, dv, generator=g)
+        pkp = (pk + 63) // 64 * 64
+        vt = torch.zeros(n, dv, pkp)
+        vt[:, :, :pk] = v.transpose(1, 2)
+        pl = {name: split(t.cuda()) for name, t in (("q", q), ("k", k), ("vt", vt), ("r", r))}
+        rf = r.cuda().contiguous()
+        a = torch.softmax(torch.bmm(q.double(), k.double().transpose(1, 2)) / 8.0, dim=2)
+        base = torch.bmm(a, v.double())
+        for out_fmt in ("f32", "split"):
+            for res_fmt in ("split", "f32", "none"):
+                got = {}
+                for which in ("ss", "ts"):
+                    os.environ["TDNET_ATTN_TS"] = "1" if which == "ts" else "0"
+                    of = torch.full((n, pq, dv), float("nan"), device="cuda")
+                    oh = torch.full((n, pq, dv), float("nan"), device="cuda", dtype=torch.half)
+                    ol = torch.full((n, pq, dv), float("nan"), device="cuda", dtype=torch.half)
+                    d = _cabi.AttentionDesc()
+                    d.q_hi, d.q_lo, d.q_ld, d.q_batch_stride = pl["q"][0].data_ptr(), pl["q"][1].data_ptr(), 64, pq * 64
+                    d.k_hi, d.k_lo, d.k_ld, d.k_batch_stride = pl["k"][0].data_ptr(), pl["k"][1].data_ptr(), 64, pk * 64
+                    d.vt_hi, d.vt_lo, d.vt_ld, d.vt_batch_stride = pl["vt"][0].data_ptr(), pl["vt"][1].data_ptr(), pkp, dv * pkp
+                    if out_fmt == "f32":
+                        d.out = _cabi.Tensor(of.data_ptr(), None, 0, n, 1, pq, dv, pq * dv, pq * dv, dv)
+                    else:
+                        d.out = _cabi.Tensor(oh.data_ptr(), ol.data_ptr(), 1, n, 1, pq, dv, pq * dv, pq * dv, dv)
+                    if res_fmt == "split":
+                        d.residual = _cabi.Tensor(pl["r"][0].data_ptr(), pl["r"][1].data_ptr(), 1, n, 1, pq, dv, pq * dv, pq * dv, dv)
+                    elif res_fmt == "f32":
+                        d.residual = _cabi.Tensor(rf.data_ptr(), None, 0, n, 1, pq, dv, pq * dv, pq * dv, dv)
+                    d.n, d.pq, d.pk, d.d_k, d.d_v = n, pq, pk, 64, dv
+                    rc = lib.tdn_attention_tc(C.byref(d), None)
+                    if rc:
+                        print(which, "rc", rc, lib.tdn_last_error().decode(), flush=True)
+                        continue
+                    torch.cuda.synchronize()
+                    got[which] = of if out_fmt == "f32" else oh.float() + ol.float()
+                ref = base + (r.double() if res_fmt != "none" else 0)
+                print(json.dumps({"shape": [n, pq, pk, dv], "out": out_fmt, "res": res_fmt,
+                                  "max_diff_ts_vs_ss": float((got["ss"] - got["ts"]).abs().max()),
+                                  "nan_ts": int(torch.isnan(got["ts"]).sum()),
+                                  "max_abs_vs_fp64_ts": float((got["ts"].cpu().double() - ref).abs().max())}), flush=True)
+
+
 def main():
     # --profile: one launch per kernel family of the big hop only (for ncu)
     profile = "--profile" in sys.argv
@@ -34,6 +81,8 @@ def main():
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
     out_path = args[0] if args else None
     lib = _cabi.load()
+    if "--formats" in sys.argv:
+        return formats(lib)
     lines = []
     for n, pq, pk, dv in (SHAPES[-1:] if profile or sustain else SHAPES):
         g = torch.Generator().manual_seed(pq + pk)
