@@ -285,6 +285,16 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
+// 16-byte shared-memory accesses by 32-bit shared address (no generic-address resolution in the hot loops)
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 // Programmatic dependent launch.  `griddep_wait` blocks until every grid this one depends on has completed and its
 // memory is visible (returns at once when the kernel was launched without a programmatic dependency);
 // `griddep_launch_dependents` lets the next kernel of the stream -- if it was launched with the programmatic-

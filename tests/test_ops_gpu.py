@@ -510,6 +510,84 @@ def test_fused_attention_tc(env, n, pq, pk, dv):
     assert float((out.cpu().double() - ref).norm() / ref.norm()) < 5e-6
 
 
+def _attention_case(cabi, lib, dev, n, pq, pk, dv, out_fmt="f32", res_fmt="split", seed=None):
+    """One tdn_attention_tc call on seeded operands; returns (out fp32 [n,pq,dv] on the device, q, k, v, r on the host)."""
+    g = torch.Generator().manual_seed(pq + pk if seed is None else seed)
+    q, k = torch.randn(n, pq, 64, generator=g) * 1.3, torch.randn(n, pk, 64, generator=g) * 1.4
+    v, r = torch.randn(n, pk, dv, generator=g) * 3, torch.randn(n, pq, dv, generator=g)
+    pkp = (pk + 63) // 64 * 64
+    vt = torch.zeros(n, dv, pkp)
+    vt[:, :, :pk] = v.transpose(1, 2)
+    pl = {name: split_planes(t.cuda()) for name, t in (("q", q), ("k", k), ("vt", vt), ("r", r))}
+    rf = r.cuda().contiguous()
+    of = torch.full((n, pq, dv), float("nan"), device=dev)
+    oh = torch.full((n, pq, dv), float("nan"), device=dev, dtype=torch.half)
+    ol = torch.full((n, pq, dv), float("nan"), device=dev, dtype=torch.half)
+    d = cabi.AttentionDesc()
+    d.q_hi, d.q_lo, d.q_ld, d.q_batch_stride = pl["q"][0].data_ptr(), pl["q"][1].data_ptr(), 64, pq * 64
+    d.k_hi, d.k_lo, d.k_ld, d.k_batch_stride = pl["k"][0].data_ptr(), pl["k"][1].data_ptr(), 64, pk * 64
+    d.vt_hi, d.vt_lo, d.vt_ld, d.vt_batch_stride = pl["vt"][0].data_ptr(), pl["vt"][1].data_ptr(), pkp, dv * pkp
+    if out_fmt == "f32":
+        d.out = cabi.Tensor(of.data_ptr(), None, 0, n, 1, pq, dv, pq * dv, pq * dv, dv)
+    else:
+        d.out = cabi.Tensor(oh.data_ptr(), ol.data_ptr(), 1, n, 1, pq, dv, pq * dv, pq * dv, dv)
+    if res_fmt == "split":
+        d.residual = cabi.Tensor(pl["r"][0].data_ptr(), pl["r"][1].data_ptr(), 1, n, 1, pq, dv, pq * dv, pq * dv, dv)
+    elif res_fmt == "f32":
+        d.residual = cabi.Tensor(rf.data_ptr(), None, 0, n, 1, pq, dv, pq * dv, pq * dv, dv)
+    d.n, d.pq, d.pk, d.d_k, d.d_v = n, pq, pk, 64, dv
+    cabi.check(lib.tdn_attention_tc(C.byref(d), None), "attention_tc")
+    torch.cuda.synchronize()
+    return (of if out_fmt == "f32" else oh.float() + ol.float()), q, k, v, r
+
+
+@pytest.fixture
+def attn_family():
+    """Restores TDNET_ATTN_TS (the library reads it on every call) after a test that flips kernel families."""
+    import os
+    old = os.environ.get("TDNET_ATTN_TS")
+    yield lambda ts: os.environ.__setitem__("TDNET_ATTN_TS", "1" if ts else "0")
+    if old is None:
+        os.environ.pop("TDNET_ATTN_TS", None)
+    else:
+        os.environ["TDNET_ATTN_TS"] = old
+
+
+@pytest.mark.parametrize("out_fmt", ["f32", "split"])
+@pytest.mark.parametrize("res_fmt", ["split", "f32", "none"])
+@pytest.mark.parametrize("n,pq,pk,dv", [(2, 1000, 690, 512), (1, 300, 100, 256), (1, 20000, 200, 512)])
+def test_attention_kernel_families_bit_identical(env, attn_family, n, pq, pk, dv, out_fmt, res_fmt):
+    """The tensor-memory-operand kernels (tc_attn_ts.cu, default) and the shared-memory-operand kernels (tc_attn.cu)
+    issue the same products in the same order per output element: equal bit for bit in every out / residual format,
+    including the split into 256- and 128-channel launches (20000 queries: 314 items on 148 SMs) and ragged tiles."""
+    lib, cabi, View, dev = env
+    got = {}
+    for ts in (False, True):
+        attn_family(ts)
+        got[ts] = _attention_case(cabi, lib, dev, n, pq, pk, dv, out_fmt, res_fmt)[0]
+    assert not torch.isnan(got[True]).any()
+    assert torch.equal(got[False], got[True])
+
+
+@pytest.mark.parametrize("n,pq,pk,dv", [(1, 32768, 2048, 512), (1, 32768, 1225, 512), (1, 4096, 2048, 1024)])
+def test_fused_attention_tc_big_hop(env, attn_family, n, pq, pk, dv):
+    """The big hop of td4-psp18 at 1024x2048 (32768 queries x 2048 keys, d_v 512), the 769x1537 key count (P' = 1225)
+    and a ResNet-50 d_v: both kernel families bit-identical, and rows sampled across the map against the fp64
+    softmax(q k^T / 8) v + residual of transformer.py:126-139 (the full fp64 matrix would not fit the test budget)."""
+    lib, cabi, View, dev = env
+    got = {}
+    for ts in (False, True):
+        attn_family(ts)
+        got[ts], q, k, v, r = _attention_case(cabi, lib, dev, n, pq, pk, dv, "split", "split")
+    assert torch.equal(got[False], got[True])
+    rows = torch.arange(0, pq, 61)
+    a = torch.softmax(q[:, rows].double() @ k.double().transpose(1, 2) / 8.0, dim=2)
+    ref = a @ v.double() + r[:, rows].double()
+    out = got[True][:, rows.to(dev)].cpu().double()
+    assert max_abs(out, ref) < 1.5e-5 * float(ref.abs().max())
+    assert float((out - ref).norm() / ref.norm()) < 5e-6
+
+
 @pytest.mark.parametrize("n,h,w,cin,cout,k", [(1, 64, 96, 64, 128, 3), (2, 25, 41, 64, 128, 3), (1, 193, 385, 64, 64, 3),
                                                (1, 25, 41, 128, 256, 1)])
 def test_tc_conv_stride2(env, n, h, w, cin, cout, k):
