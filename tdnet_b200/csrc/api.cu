@@ -64,6 +64,19 @@ int fa_apply(const tdn_tensor*, const float*, const tdn_tensor*, float, int*, cu
 int add_upsampled(const tdn_tensor*, const tdn_tensor*, const tdn_tensor*, const tdn_tensor*, cudaStream_t);
 int merge16(const tdn_tensor*, const tdn_tensor*, cudaStream_t);
 
+int device_sm_count() {
+  static PerDeviceInt cache;
+  const int slot = current_device_slot();
+  int n = cache.get(slot);
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    cache.set(slot, n);
+  }
+  return n;
+}
+
 }  // namespace tdn
 
 using namespace tdn;
@@ -94,6 +107,18 @@ int tdn_device_arch(void) {
   return major * 10 + minor;
 }
 
+// Compute capability of the current device, cached per device ordinal (negative: a tdn_status error).
+static int cached_device_arch() {
+  static tdn::PerDeviceInt cache;
+  const int slot = tdn::current_device_slot();
+  int arch = cache.get(slot);
+  if (arch == 0) {
+    arch = tdn_device_arch();
+    if (arch > 0) cache.set(slot, arch);
+  }
+  return arch;
+}
+
 int tdn_conv2d(const tdn_conv2d_desc* d, void* stream) {
   TDN_REQUIRE(d != nullptr, TDN_ERR_INVALID, "conv2d: null descriptor");
   TDN_REQUIRE(d->in.data && d->out.data && d->weight, TDN_ERR_INVALID, "conv2d: null data pointer");
@@ -106,8 +131,7 @@ int tdn_conv2d(const tdn_conv2d_desc* d, void* stream) {
 
 int tdn_conv2d_tc(const tdn_tc_conv_desc* d, void* stream) {
   TDN_REQUIRE(d != nullptr, TDN_ERR_INVALID, "conv2d_tc: null descriptor");
-  static thread_local int arch = 0;
-  if (arch == 0) arch = tdn_device_arch();
+  const int arch = cached_device_arch();
   if (arch < 0) return arch;
   TDN_REQUIRE(arch / 10 == 10, TDN_ERR_ARCH, "conv2d_tc: tcgen05 kernels need sm_100, device is sm_%d", arch);
   TDN_REQUIRE(d->cout > 0 && d->kh > 0 && d->kw > 0 && d->dilation > 0, TDN_ERR_INVALID, "conv2d_tc: bad geometry");
@@ -116,8 +140,7 @@ int tdn_conv2d_tc(const tdn_tc_conv_desc* d, void* stream) {
 
 int tdn_attention_tc(const tdn_attention_desc* d, void* stream) {
   TDN_REQUIRE(d != nullptr, TDN_ERR_INVALID, "attention_tc: null descriptor");
-  static thread_local int arch = 0;
-  if (arch == 0) arch = tdn_device_arch();
+  const int arch = cached_device_arch();
   if (arch < 0) return arch;
   TDN_REQUIRE(arch / 10 == 10, TDN_ERR_ARCH, "attention_tc: tcgen05 kernels need sm_100, device is sm_%d", arch);
   return attention_tc(d, (cudaStream_t)stream);
@@ -144,8 +167,7 @@ int tdn_stem_conv_pool(const float* nchw, int32_t n, int32_t h, int32_t w, const
 int tdn_stem_conv_pool_tc(const float* nchw, const uint8_t* hwc_u8, const float* lut, int32_t n, int32_t h, int32_t w,
                           const void* weight_tc, const float* scale, const float* bias, const tdn_tensor* out,
                           int32_t* range_flag, void* stream) {
-  static thread_local int arch = 0;
-  if (arch == 0) arch = tdn_device_arch();
+  const int arch = cached_device_arch();
   if (arch < 0) return arch;
   TDN_REQUIRE(arch / 10 == 10, TDN_ERR_ARCH, "stem_conv_pool_tc: tcgen05 kernels need sm_100, device is sm_%d", arch);
   return stem_conv_pool_tc(nchw, hwc_u8, lut, n, h, w, weight_tc, scale, bias, out, TDN_ACT_RELU, 0.f, range_flag,
@@ -155,8 +177,7 @@ int tdn_stem_conv_pool_tc(const float* nchw, const uint8_t* hwc_u8, const float*
 int tdn_stem_conv_pool_tc_act(const float* nchw, const uint8_t* hwc_u8, const float* lut, int32_t n, int32_t h, int32_t w,
                               const void* weight_tc, const float* scale, const float* bias, const tdn_tensor* out,
                               int32_t act, float leaky_slope, int32_t* range_flag, void* stream) {
-  static thread_local int arch = 0;
-  if (arch == 0) arch = tdn_device_arch();
+  const int arch = cached_device_arch();
   if (arch < 0) return arch;
   TDN_REQUIRE(arch / 10 == 10, TDN_ERR_ARCH, "stem_conv_pool_tc: tcgen05 kernels need sm_100, device is sm_%d", arch);
   return stem_conv_pool_tc(nchw, hwc_u8, lut, n, h, w, weight_tc, scale, bias, out, act, leaky_slope, range_flag,

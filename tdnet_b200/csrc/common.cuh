@@ -37,6 +37,28 @@ const char* get_error();
 
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// One process may drive several GPUs (model.to('cuda:1')): the > 48 KB dynamic shared-memory opt-in of a kernel
+// (cudaFuncSetAttribute), the SM count and the compute capability are properties of the CURRENT device, so every
+// "done once" cache in the library is kept per device ordinal.
+constexpr int TDN_MAX_DEVICES = 64;
+static inline int current_device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= TDN_MAX_DEVICES) return -1;   // -1: never cached
+  return dev;
+}
+struct PerDeviceFlag {
+  bool done[TDN_MAX_DEVICES] = {};
+  bool is_set(int slot) const { return slot >= 0 && done[slot]; }
+  void set(int slot) { if (slot >= 0) done[slot] = true; }
+};
+struct PerDeviceInt {
+  int v[TDN_MAX_DEVICES] = {};
+  int get(int slot) const { return slot >= 0 ? v[slot] : 0; }
+  void set(int slot, int x) { if (slot >= 0) v[slot] = x; }
+};
+// SM count of the current device (cached per device); 0 on failure.
+int device_sm_count();
+
 // Device-side NHWC view: one fp32 plane (p) or two fp16 planes hi/lo with value = hi + lo
 // (TDN_SPLIT16).  Every layout kernel goes through ld4/st4/ld1/st1, so it accepts either format.
 struct View {

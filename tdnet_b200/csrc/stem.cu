@@ -166,11 +166,12 @@ int stem_conv_pool(const float* nchw, const uint8_t* hwc_u8, const float* lut, i
   TDN_REQUIRE(out->n == n && out->h == p.Hp && out->w == p.Wp && out->c == 64 && vec4_ok(*out), TDN_ERR_INVALID,
               "stem: out must be a vector-aligned [n,%d,%d,64] view", p.Hp, p.Wp);
   const int smem = ST_SMEM_FLOATS * (int)sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceFlag attr_set;
+  const int slot = current_device_slot();
+  if (!attr_set.is_set(slot)) {
     TDN_CUDA_OK(cudaFuncSetAttribute(stem_conv_pool_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     TDN_CUDA_OK(cudaFuncSetAttribute(stem_conv_pool_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
+    attr_set.set(slot);
   }
   dim3 grid(ceil_div(p.Wp, ST_P), ceil_div(p.Hp, ST_P), n);
   if (nchw) stem_conv_pool_kernel<false><<<grid, ST_THREADS, smem, stream>>>(p);

@@ -462,17 +462,8 @@ int attention_tc(const tdn_attention_desc* d, cudaStream_t stream) {
   TDN_REQUIRE(d->d_v % AT_DVH == 0, TDN_ERR_UNSUPPORTED, "attention_tc: d_v=%d must be a multiple of 128", d->d_v);
   // 256-wide slices halve the QK^T / softmax recompute; small problems (the FIFO hops with P' queries) would
   // not fill the SMs with them, so they take 128-wide slices = twice as many work items.
-  int dev = 0, num_sms = 0;
-  TDN_CUDA_OK(cudaGetDevice(&dev));
-  {
-    static int sms_of[64] = {};                      // per device ordinal (a process may drive several GPUs)
-    if (dev < 0 || dev >= 64 || sms_of[dev] == 0) {
-      TDN_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-      if (dev >= 0 && dev < 64) sms_of[dev] = num_sms;
-    } else {
-      num_sms = sms_of[dev];
-    }
-  }
+  const int num_sms = device_sm_count();
+  TDN_REQUIRE(num_sms > 0, TDN_ERR_CUDA, "attention_tc: cannot query the SM count");
   const int num_sms_cached = num_sms;
   const long long items256 = (long long)d->n * ceil_div(d->pq, AT_BQ) * (d->d_v / 256);
   const int dvt_size = (d->d_v % 256 == 0 && items256 >= num_sms_cached) ? 256 : 128;
@@ -553,11 +544,12 @@ int attention_tc(const tdn_attention_desc* d, cudaStream_t stream) {
   const char* ts_env = getenv("TDNET_ATTN_TS");
   const bool use_ts = ts_env ? atoi(ts_env) != 0 : true;
   {
-    static bool attr_set[64] = {};                   // the > 48 KB shared-memory opt-in is per device
-    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    static PerDeviceFlag attr_set;                   // the > 48 KB shared-memory opt-in is per device
+    const int slot = current_device_slot();
+    if (!attr_set.is_set(slot)) {
       TDN_CUDA_OK(cudaFuncSetAttribute(tc_attn_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES));
       TDN_CUDA_OK(cudaFuncSetAttribute(tc_attn_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES));
-      if (dev >= 0 && dev < 64) attr_set[dev] = true;
+      attr_set.set(slot);
     }
   }
   auto launch = [&](int dvt, int grid, const AttnParams& pp) -> cudaError_t {

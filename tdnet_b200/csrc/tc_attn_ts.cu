@@ -628,16 +628,14 @@ cudaError_t attention_ts_launch(int dvt, int grid, cudaStream_t stream, bool sho
                                 const CUtensorMap& mq_l, const CUtensorMap& mk_h, const CUtensorMap& mk_l,
                                 const CUtensorMap& mv_h, const CUtensorMap& mv_l, const AttnParams& p) {
   // the > 48 KB dynamic shared-memory opt-in is a per-device function attribute: set it once per device
-  static bool attr_set[64] = {};
-  int dev = 0;
-  cudaError_t e = cudaGetDevice(&dev);
-  if (e != cudaSuccess) return e;
-  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    e = cudaFuncSetAttribute(tc_attn_ts_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATS_SMEM_BYTES);
+  static PerDeviceFlag attr_set;
+  const int slot = current_device_slot();
+  if (!attr_set.is_set(slot)) {
+    cudaError_t e = cudaFuncSetAttribute(tc_attn_ts_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATS_SMEM_BYTES);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(tc_attn_ts_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATS_SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    attr_set.set(slot);
   }
   if (dvt == 256)
     return tc_launch(tc_attn_ts_kernel<256>, grid, ATS_THREADS, ATS_SMEM_BYTES, stream, short_launch, mq_h, mq_l, mk_h,

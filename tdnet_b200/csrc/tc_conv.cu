@@ -223,23 +223,20 @@ static void pick_tile(int H, int W, int* BH, int* BW) {
   }
 }
 
-static int g_num_sms = 0;
 
 template <int BLOCK_N>
 static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
                      const CUtensorMap& b_lo, const TcParams& p, cudaStream_t stream) {
   using Cfg = TcCfg<BLOCK_N>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceFlag attr_set;
+  const int slot = current_device_slot();
+  if (!attr_set.is_set(slot)) {
     TDN_CUDA_OK(cudaFuncSetAttribute(tc_conv_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      Cfg::SMEM_BYTES));
-    attr_set = true;
+    attr_set.set(slot);
   }
-  if (g_num_sms == 0) {
-    int dev = 0;
-    TDN_CUDA_OK(cudaGetDevice(&dev));
-    TDN_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  const int g_num_sms = device_sm_count();
+  TDN_REQUIRE(g_num_sms > 0, TDN_ERR_CUDA, "conv2d_tc: cannot query the SM count");
   const int todo = p.num_tiles - p.tile_begin;
   int grid = todo < g_num_sms ? todo : g_num_sms;
   TDN_CUDA_OK(tc_launch(tc_conv_kernel<BLOCK_N>, grid, TC_THREADS, Cfg::SMEM_BYTES, stream, todo <= 2 * grid, a_hi, a_lo, b_hi, b_lo, p));
@@ -285,11 +282,8 @@ int conv2d_tc(const tdn_tc_conv_desc* d, cudaStream_t stream) {
   // N tile: 128 columns unless the problem is so small that 128-wide tiles would leave the 148 SMs with fewer
   // than two waves of work AND the K loop is short (measured: the fc GEMMs with 8 K blocks gain 25 % from
   // N = 64, the head conv with 72 K blocks loses 35 % because the A tile is then fetched twice as often).
-  if (g_num_sms == 0) {
-    int dev = 0;
-    TDN_CUDA_OK(cudaGetDevice(&dev));
-    TDN_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  const int g_num_sms = device_sm_count();
+  TDN_REQUIRE(g_num_sms > 0, TDN_ERR_CUDA, "conv2d_tc: cannot query the SM count");
   const long long tiles128 = (long long)in.n * p.tiles_h * p.tiles_w * ceil_div(d->cout, 128);
   const int num_kb_host = taps * (in.c / TC_BLOCK_K);
   // Third case (TD2-FANet's stride-32/64 maps: 512-channel 3x3 convs on a few thousand pixels, 72 K blocks): when

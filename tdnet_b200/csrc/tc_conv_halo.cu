@@ -187,10 +187,11 @@ static int launch_halo(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const C
   using Cfg = HaloCfg<BLOCK_N>;
   const int smem = Cfg::B_STAGES * Cfg::B_STAGE + HL_A_STAGES * g.a_stage + 1024 + 512;
   TDN_REQUIRE(smem <= 232448, TDN_ERR_UNSUPPORTED, "conv2d_tc_halo: %d bytes of shared memory", smem);
-  static int attr_smem = 0;
-  if (smem > attr_smem) {
+  static PerDeviceFlag attr_set;
+  const int slot = current_device_slot();
+  if (!attr_set.is_set(slot)) {
     TDN_CUDA_OK(cudaFuncSetAttribute(tc_conv_halo_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    attr_smem = 232448;
+    attr_set.set(slot);
   }
   int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
   TDN_CUDA_OK(tc_launch(tc_conv_halo_kernel<BLOCK_N>, grid, TC_THREADS, smem, stream, p.num_tiles <= 2 * grid, a_hi, a_lo, b_hi, b_lo, p, g));

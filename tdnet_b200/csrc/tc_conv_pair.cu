@@ -181,7 +181,9 @@ int encode_map_f16(CUtensorMap* m, const void* base, int rank, const cuuint64_t*
 template <int BLOCK_N>
 static int pair_clusters(int num_sms, int* clusters) {
   using Cfg = PairCfg<BLOCK_N>;
-  static int max_clusters = 0;
+  static PerDeviceInt cache;
+  const int slot = current_device_slot();
+  int max_clusters = cache.get(slot);
   if (max_clusters == 0) {
     TDN_CUDA_OK(cudaFuncSetAttribute(tc_conv_pair_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      Cfg::SMEM_BYTES));
@@ -205,6 +207,7 @@ static int pair_clusters(int num_sms, int* clusters) {
     max_clusters = n < num_sms / 2 ? n : num_sms / 2;
     if (const char* e = getenv("TDNET_TC_PAIR_VERBOSE"))
       if (atoi(e)) fprintf(stderr, "[tdnet_b200] tc_conv_pair_kernel<%d>: %d resident clusters of 2 CTAs\n", BLOCK_N, max_clusters);
+    cache.set(slot, max_clusters);
   }
   *clusters = max_clusters;
   return TDN_OK;

@@ -286,21 +286,18 @@ int stem_conv_pool_tc(const float* nchw, const uint8_t* hwc_u8, const float* lut
   p.act = act; p.slope = slope;
   TDN_REQUIRE(out->n == n && out->h == p.Hp && out->w == p.Wp && out->c == 64 && vec4_ok(*out), TDN_ERR_INVALID,
               "stem_tc: out must be a vector-aligned [n,%d,%d,64] view", p.Hp, p.Wp);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceFlag attr_set;
+  const int slot = current_device_slot();
+  if (!attr_set.is_set(slot)) {
     TDN_CUDA_OK(cudaFuncSetAttribute(tc_stem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES));
     TDN_CUDA_OK(cudaFuncSetAttribute(tc_stem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES));
-    attr_set = true;
+    attr_set.set(slot);
   }
   // Pooled rows per CTA: every CTA pays ~6 row-times of prologue (weights, pipeline fill) and one halo conv
   // row, and the grid runs in waves of one CTA per SM -- pick the band height with the shortest critical path.
   const int strips = ceil_div(p.Wp, TS_PW);
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    TDN_CUDA_OK(cudaGetDevice(&dev));
-    TDN_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  const int sms = device_sm_count();
+  TDN_REQUIRE(sms > 0, TDN_ERR_CUDA, "stem_tc: cannot query the SM count");
   int best_pb = 1;
   long long best_cost = -1;
   for (int pb = 1; pb <= 64 && pb <= p.Hp; ++pb) {

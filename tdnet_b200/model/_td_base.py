@@ -70,6 +70,12 @@ class TDModel(nn.Module):
         assert path_num == self.PATHS
         if not (dilated and multi_grid):
             raise RuntimeError("tdnet_b200 implements the dilated, multi-grid backbone the reference tests ship")
+        # BatchNorm is folded into the convolution epilogues (eval mode, running statistics + affine, with the
+        # activation of the reference's BatchNorm2d wrapper): any other normalisation layer would silently compute
+        # something else, so only the reference's own default (or None) is accepted.
+        if norm_layer is not None and getattr(norm_layer, "__name__", "") != "BatchNorm2d":
+            raise RuntimeError("tdnet_b200 folds eval-mode BatchNorm2d into its kernels; norm_layer={!r} is not "
+                               "supported".format(norm_layer))
         self.psp_path = model_path
         self.path_num = path_num
         self.nclass = nclass
@@ -86,8 +92,13 @@ class TDModel(nn.Module):
         self.Q_queue, self.K_queue, self.V_queue = [], [], []
         # 'tc': tcgen05 exact-mode kernels (product path on B200); 'simt': fp32 CUDA-core kernels only.
         self.engine_mode = os.environ.get("TDNET_B200_ENGINE", "tc")
-        # Replay each static frame plan through a CUDA graph from its second use on (removes ~60 launch gaps).
+        # Replay each static frame plan through a CUDA graph (removes ~60 launch gaps).  All plans of a model are
+        # built, run once on a scratch frame and captured when the engine is created (first forward of a new input
+        # shape, or prepare()), never inside a later frame.
         self.use_cuda_graph = os.environ.get("TDNET_B200_CUDA_GRAPH", "1") != "0"
+        # SPLIT16 range guard (|x| > 6e4 overflows an fp16 plane): the device flag is copied to pinned host memory
+        # after every frame without blocking and examined at the next call.
+        self._range_host = None
 
     # ---- reference API ---------------------------------------------------------------------
     def pretrained_mp_load(self):
@@ -138,7 +149,39 @@ class TDModel(nn.Module):
             sd = {k: v.detach().cpu() for k, v in self.state_dict().items()}
             eng = Engine(self.arch, sd, n, h, w, img.device, self.ln_shape, mode=self.engine_mode)
             self._engines[key] = eng
+            self._range_host = None
+            if self.use_cuda_graph:
+                eng.prepare_graphs()
         return eng
+
+    def prepare(self, n, h, w, device=None):
+        """Build the engine for [n,3,h,w] inputs now: weight packing, all frame plans, their CUDA graphs.  forward()
+        does the same on the first frame of a new shape; call this to keep it out of the first frame's latency.
+        Starts a new clip."""
+        device = torch.device(device) if device is not None else next(self.parameters()).device
+        if device.type != "cuda":
+            raise RuntimeError("tdnet_b200 runs on a CUDA (sm_100) device only; move the model with .to('cuda') first")
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        with torch.cuda.device(device):
+            self._engine(torch.empty(0, device=device), (n, 3, h, w))
+        self.reset()
+        return self
+
+    def _poll_range_flag(self, eng):
+        """Non-blocking range guard: raise if the flag copied after an EARLIER frame was set, then queue the copy of
+        the current flag behind this frame.  An overflow is therefore reported at most one call late (or at once by
+        check_numeric_range()); it is never silent."""
+        if self._range_host is None:
+            self._range_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        elif int(self._range_host[0]) != 0:
+            self._range_host.zero_()
+            eng.range_flag.zero_()
+            raise RuntimeError(self._RANGE_MSG)
+        self._range_host.copy_(eng.range_flag, non_blocking=True)
+
+    _RANGE_MSG = ("tdnet_b200: an activation exceeded the SPLIT16 range (|x| > 6e4) in an earlier frame, its logits "
+                  "are invalid; use engine_mode='simt' (fp32 planes) for this checkpoint")
 
     def time_attention_op(self, frames, step, reps=8):
         """Average device time (ms) of the fused attention-propagation kernel of the big hop (the last hop of
@@ -212,8 +255,10 @@ class TDModel(nn.Module):
         engine was created.  Synchronises; meant for validation runs, not the frame loop."""
         for eng in self._engines.values():
             if int(eng.range_flag.item()) != 0:
-                raise RuntimeError("tdnet_b200: an activation exceeded the SPLIT16 range (|x| > 6e4); use "
-                                   "engine_mode='simt' (fp32 planes) for this checkpoint")
+                eng.range_flag.zero_()
+                if self._range_host is not None:
+                    self._range_host.zero_()
+                raise RuntimeError(self._RANGE_MSG)
 
     @torch.no_grad()
     def forward(self, img, pos_id=0, _probe=None, _labels=False, _u8=False, _preview=None):
@@ -232,6 +277,11 @@ class TDModel(nn.Module):
             raise RuntimeError(f"pos_id must be in [0,{self.PATHS})")
         img = img.contiguous()
         n, _, h, w = shape_nchw if _u8 else img.shape
+        # the library launches on the CURRENT device: make the input's device current for the whole frame
+        with torch.cuda.device(img.device):
+            return self._forward_on_device(img, pos_id, n, h, w, _probe, _labels, _u8, _preview)
+
+    def _forward_on_device(self, img, pos_id, n, h, w, _probe, _labels, _u8, _preview):
         eng = self._engine(img, (n, 3, h, w))
         steady = len(self.Q_queue) >= self.arch.depth
         plan = eng.plan(pos_id + 1, steady)
@@ -245,7 +295,7 @@ class TDModel(nn.Module):
         else:
             out = torch.empty((n, self.nclass, h, w), dtype=torch.float32, device=img.device)
         plan.uses = getattr(plan, "uses", 0) + 1
-        if self.use_cuda_graph and _probe is None and plan.uses > 1:
+        if self.use_cuda_graph and _probe is None and getattr(plan, "graph", None) is not None:
             eng.run_graphed(plan, img.data_ptr(), out.data_ptr(), labels=_labels, u8=_u8, last_op=last_op)
         else:
             eng.run(plan, img.data_ptr(), out.data_ptr(), torch.cuda.current_stream(img.device).cuda_stream, _probe,
@@ -258,4 +308,6 @@ class TDModel(nn.Module):
         self.K_queue = [eng.k_slots[depth - fill + j].torch().view(n, -1, self.arch.d_k) for j in range(fill)]
         self.V_queue = [eng.v_slots[depth - fill + j].torch().view(n, -1, self.arch.d_v) for j in range(fill)]
         self._last = (eng, plan)
+        if eng.tc:
+            self._poll_range_flag(eng)
         return out

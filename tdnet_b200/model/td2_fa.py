@@ -45,6 +45,7 @@ class td2_fa(TDModel):  # noqa: N801
         self.Q_queue, self.K_queue, self.V_queue = [], [], []   # no FIFO in this model; kept empty for the shared base
         self.engine_mode = os.environ.get("TDNET_B200_ENGINE", "tc")
         self.use_cuda_graph = os.environ.get("TDNET_B200_CUDA_GRAPH", "1") != "0"
+        self._range_host = None
         self.pretrained_init()
 
     def pretrained_init(self):
@@ -120,6 +121,10 @@ class td2_fa(TDModel):  # noqa: N801
             raise RuntimeError("the two frames of the pair must have the same shape and device")
         prev, cur = prev.contiguous(), cur.contiguous()
         n, _, h, w = cur.shape
+        with torch.cuda.device(cur.device):      # the library launches on the current device
+            return self._forward_on_device(prev, cur, pos_id, n, h, w, _probe, _labels, _preview)
+
+    def _forward_on_device(self, prev, cur, pos_id, n, h, w, _probe, _labels, _preview):
         eng = self._engine(cur, (n, 3, h, w))
         plan = eng.plan(pos_id + 1, True)
         last_op = None
@@ -139,4 +144,6 @@ class td2_fa(TDModel):  # noqa: N801
             eng.run(plan, cur.data_ptr(), out.data_ptr(), torch.cuda.current_stream(cur.device).cuda_stream, _probe,
                     labels=_labels, img2_ptr=prev.data_ptr(), last_op=last_op)
         self._last = (eng, plan)
+        if eng.tc:
+            self._poll_range_flag(eng)
         return out

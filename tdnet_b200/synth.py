@@ -34,8 +34,10 @@ def _gen_for(key: str, seed: int) -> torch.Generator:
     return g
 
 
-def synth_tensor(key: str, ref: torch.Tensor, seed: int = 0) -> torch.Tensor:
-    """Value for state-dict entry `key` (same shape/dtype as `ref`)."""
+def synth_tensor(key: str, ref: torch.Tensor, seed: int = 0, tame: bool = True) -> torch.Tensor:
+    """Value for state-dict entry `key` (same shape/dtype as `ref`).  tame=False drops the two adjustments that keep a
+    random network as calm as a trained one (small residual-tail gammas, 0.25 gain on the second Q/K projection):
+    activations then grow block by block and the softmax turns one-hot -- the stress case of the range guard."""
     g = _gen_for(key, seed)
     shape = tuple(ref.shape)
     leaf = key.rsplit(".", 1)[-1]
@@ -47,7 +49,7 @@ def synth_tensor(key: str, ref: torch.Tensor, seed: int = 0) -> torch.Tensor:
         return torch.rand(shape, generator=g) + 0.5
     if ref.dim() == 4:  # conv weight [cout, cin, kh, kw]
         fan_in = shape[1] * shape[2] * shape[3]
-        if ".w_qs.1." in key or ".w_ks.1." in key:
+        if (".w_qs.1." in key or ".w_ks.1." in key) and tame:
             gain = 0.25  # keeps q.k/8 at a few units so the softmax is neither flat nor one-hot
         elif ".w_qs." in key or ".w_ks." in key or ".w_vs." in key or ".fc." in key:
             gain = 1.0
@@ -58,7 +60,9 @@ def synth_tensor(key: str, ref: torch.Tensor, seed: int = 0) -> torch.Tensor:
         return torch.randn(shape, generator=g) * math.sqrt(1.0 / shape[1])
     if leaf == "weight":  # BN gamma [C] or LN gamma [H8, W8]
         gamma = torch.rand(shape, generator=g) + 0.5
-        if _RESIDUAL_TAIL_BN.search(key):
+        if not tame:
+            pass
+        elif _RESIDUAL_TAIL_BN.search(key):
             # Last BN of a residual block: keep the branch small so that the trunk does not double
             # its variance at every block (a trained network is calm; a random one is not).
             gamma = gamma * 0.3
@@ -72,9 +76,9 @@ def synth_tensor(key: str, ref: torch.Tensor, seed: int = 0) -> torch.Tensor:
     raise KeyError(f"synth_tensor: unclassified state-dict key {key!r} shape {shape}")
 
 
-def synth_state_dict(template: dict, seed: int = 0) -> dict:
+def synth_state_dict(template: dict, seed: int = 0, tame: bool = True) -> dict:
     """Fill every entry of a state-dict template (key -> tensor) deterministically."""
-    return {k: synth_tensor(k, v, seed).to(v.dtype) for k, v in template.items()}
+    return {k: synth_tensor(k, v, seed, tame).to(v.dtype) for k, v in template.items()}
 
 
 _MEAN = torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1)

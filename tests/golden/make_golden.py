@@ -128,6 +128,12 @@ def run_case(name, arch, backbone, H, W, batch, n_frames, keep):
                 rec[f"head_absmean_{i}"] = np.float64(head.double().abs().mean().item())
                 rec[f"head_sub_{i}"] = head[:, :, ::8, ::16].numpy().copy()
                 rec[f"logits_sub_{i}"] = out[:, :, ::64, ::128].numpy().copy()
+                if i == n_frames - 1:
+                    # the reference's arg-max label map of the last (steady-state) frame at its native size
+                    # (Testing/test.py:61) and the pixels whose top-1 / top-2 margin is below 1e-3 (near-ties), bit-packed
+                    top2 = out.topk(2, dim=1).values
+                    rec["argmax_last"] = out.argmax(1).to(torch.uint8).numpy().copy()
+                    rec["near_tie_last"] = np.packbits(((top2[:, 0] - top2[:, 1]) < 1e-3).numpy())
                 continue
             rec[f"head_{i}"] = head.numpy().copy()
             if i in keep:

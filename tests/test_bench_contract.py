@@ -1,4 +1,4 @@
-"""CPU: bench.py's reference arm (the CPU oracle port timed on the host cores) prints one JSON line that
+"""CPU: bench.py's reference arm (the reference -- oracle/_ref when present, else the oracle port -- timed on the host cores) prints one JSON line that
 carries the contract keys.  Uses the real 1024x2048 workload with a single timed frame."""
 import json
 import os
@@ -19,7 +19,10 @@ def test_reference_arm_json_line():
     assert d["metric"].startswith("frames/sec at 1024x2048") and d["dtype"] == "f32" and d["data"] == "synthetic"
     assert d["value"] > 0 and d["steps"] == 1 and d["vs_baseline"] is None and d["scaling"] == "weak"
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "1024x2048" in cb["sample"]
+    have_ref = os.path.isfile(os.path.join(ROOT, "oracle", "_ref", "Testing", "model", "pspnet", "td4_psp18.py"))
+    assert cb["kind"] == ("reference" if have_ref else "port")      # the reference's own package when oracle/_ref exists
+    assert cb["cores"] >= 1 and cb["value"] == d["value"] and "1024x2048" in cb["sample"]
+    assert d["warmup"] == 3 and d["config"]["config_id"] == 1
     assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "td4-psp18 1024x2048" in d["config"]["workload"]
 

@@ -123,3 +123,19 @@ def test_forward_path_methods_mirror_the_reference_surface():
         fa.forward_path1([x, x])
     with pytest.raises(AttributeError):
         fa.forward_path3([x, x])
+
+
+def test_foreign_norm_layer_is_refused_not_ignored():
+    """BatchNorm2d (eval) is folded into the convolution epilogues; a user-supplied normalisation layer of another kind
+    would silently compute something else, so the constructor raises (the reference's own default and torch's
+    BatchNorm2d are accepted; td4_psp18.py:11-24,52-53)."""
+    import torch.nn as nn
+    from tdnet_b200.model import td2_psp50, td4_psp18
+    td4_psp18.td4_psp18(nclass=19, path_num=4)                                   # the reference's default
+    td4_psp18.td4_psp18(nclass=19, path_num=4, norm_layer=nn.BatchNorm2d)
+    td4_psp18.td4_psp18(nclass=19, path_num=4, norm_layer=None)
+    for cls, kw in ((td4_psp18.td4_psp18, dict(path_num=4)), (td2_psp50.td2_psp50, dict(path_num=2))):
+        with pytest.raises(RuntimeError, match="norm_layer"):
+            cls(nclass=19, norm_layer=nn.GroupNorm, **kw)
+        with pytest.raises(RuntimeError, match="norm_layer"):
+            cls(nclass=19, norm_layer=nn.InstanceNorm2d, **kw)

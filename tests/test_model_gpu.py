@@ -86,6 +86,15 @@ def test_native_size_769x1537_against_reference_checksums():
         assert max_abs(out[:, :, ::64, ::128].cpu(), g[f"logits_sub_{i}"]) <= LOGIT_TOL
         head = tap(net._last[1].taps["head"])
         assert abs(head.double().mean().item() - float(g[f"head_mean_{i}"])) <= 1e-5
+    # the reference's arg-max label map of the last (steady-state) frame, every pixel of the 769x1537 image
+    # (Testing/test.py:61): equal outside the reference's near-tie pixels (top-1 / top-2 margin < 1e-3, stored bit-packed)
+    labels = out.argmax(1).to(torch.uint8).cpu().numpy()
+    near = np.unpackbits(g["near_tie_last"])[:labels.size].reshape(labels.shape).astype(bool)
+    diff = labels != g["argmax_last"]
+    record("golden/td4_r18_769x1537_chk/argmax", mismatch_total=int(diff.sum()), mismatch_decided=int((diff & ~near).sum()),
+           near_ties=int(near.sum()), pixels=int(labels.size))
+    assert int((diff & ~near).sum()) == 0 and near.mean() < 5e-3
+    assert np.array_equal(net.forward_labels(frames[0].cuda(), pos_id=(i + 1) % 4).shape, (1, 769, 1537))
     assert net.K_queue[0].shape == (1, 1225, 64)
 
 
@@ -323,4 +332,102 @@ def test_pspnet101_512x1024_against_oracle():
     labels = net.forward_labels(f.cuda())
     out2 = net(f.cuda())
     assert torch.equal(labels.long(), out2.max(1)[1])
+    net.check_numeric_range()
+
+
+def test_untamed_weights_pass_or_raise_never_silently_wrong():
+    """Synthetic weights WITHOUT the calming adjustments of tdnet_b200/synth.py (residual-tail gammas x0.3, 0.25 gain
+    on the second Q/K projection): activations grow block by block, attention scores reach the hundreds and the
+    softmax is close to one-hot.  That problem is ill-conditioned for EVERY fp32 implementation -- the reference's own
+    fp32 result moves by up to 7e-4 against its fp64 evaluation on these frames -- so the yardstick is the fp64
+    evaluation of the oracle: the product path (22-bit SPLIT16 operands) must stay within LOGIT_TOL x logit scale or a
+    small multiple of the reference's own fp32 error, or raise through the SPLIT16 range guard.  Never NaN / Inf, never
+    silently wrong (td4_psp18.py:11-24,52-53; DESIGN.md 'exact mode')."""
+    from oracle.tdnet_oracle import TDOracle, state_dict_template
+    from tdnet_b200.synth import synth_state_dict
+    H, W = 128, 256
+    sd = synth_state_dict(state_dict_template("td4_psp18", "resnet18", ln_shape=(16, 32)), seed=5, tame=False)
+    oracle = TDOracle("td4_psp18", sd, "resnet18")
+    oracle64 = TDOracle("td4_psp18", {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}, "resnet18")
+    net = build_model("td4_psp18", "resnet18", 16, 32, sd)
+    raised = False
+    for i, f in enumerate(synth_clip(6, H, W, clip_id=11)):
+        ref, truth = oracle(f, pos_id=i % 4), oracle64(f.double(), pos_id=i % 4)
+        try:
+            out = net(f.cuda(), pos_id=i % 4).cpu()
+            net.check_numeric_range()
+        except RuntimeError as e:
+            assert "SPLIT16 range" in str(e)
+            raised = True
+            break
+        scale = max(1.0, float(truth.abs().max()))
+        e_ref, e_ours = max_abs(ref, truth), max_abs(out, truth)
+        record(f"untamed/td4_128x256/frame{i}", max_abs_vs_fp64=e_ours, reference_fp32_vs_fp64=e_ref, logit_absmax=scale,
+               argmax_agreement_vs_fp64=float((out.argmax(1) == truth.argmax(1)).float().mean()))
+        assert torch.isfinite(out).all()
+        assert e_ours <= max(LOGIT_TOL * scale, 8.0 * e_ref), (i, e_ours, e_ref, scale)
+    record("untamed/td4_128x256/outcome", raised=raised)
+
+
+def test_range_guard_raises_on_the_next_call_without_being_asked():
+    """An activation beyond the fp16 range of a SPLIT16 plane must not go unnoticed in the plain forward() loop (the
+    drop-in Testing/test.py flow never calls check_numeric_range): the device flag is copied to pinned memory after
+    each frame and the NEXT call raises."""
+    sd = make_weights("td4_psp18", "resnet18", 8, 12)
+    net = build_model("td4_psp18", "resnet18", 8, 12, sd)
+    f = synth_clip(1, 64, 96)[0].cuda()
+    net(f, pos_id=0)
+    net(f * 3e4, pos_id=1)           # |x| ~ 6e4 at the input already
+    torch.cuda.synchronize()
+    with pytest.raises(RuntimeError, match="SPLIT16 range"):
+        net(f, pos_id=2)
+    net(f, pos_id=2)                 # the guard re-arms: a clean frame runs again
+
+
+def test_prepare_builds_every_plan_and_graph_up_front():
+    """prepare() (and the first forward of a new shape) builds all path x {warm-up, steady} plans and captures their
+    CUDA graphs, so no later frame pays for a capture (Testing/test.py times frames 6+); results equal the eager path."""
+    sd = make_weights("td4_psp18", "resnet18", 8, 12)
+    net = build_model("td4_psp18", "resnet18", 8, 12, sd)
+    net.prepare(1, 64, 96)
+    eng = next(iter(net._engines.values()))
+    assert len(eng._plans) == 8 and all(getattr(p, "graph", None) is not None for p in eng._plans.values())
+    eager = build_model("td4_psp18", "resnet18", 8, 12, sd)
+    eager.use_cuda_graph = False
+    for i, f in enumerate(synth_clip(7, 64, 96, clip_id=2)):
+        a, b = net(f.cuda(), pos_id=i % 4), eager(f.cuda(), pos_id=i % 4)
+        assert torch.equal(a, b), i
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_model_on_second_gpu_while_first_is_current():
+    """model.to('cuda:1') with cuda:0 current: the frame must run on the input's device (per-device kernel
+    attributes and SM counts in the library, device guard in forward)."""
+    sd = make_weights("td4_psp18", "resnet18", 8, 12)
+    net0 = build_model("td4_psp18", "resnet18", 8, 12, sd)
+    from tdnet_b200.model import td4_psp18
+    net1 = td4_psp18.td4_psp18(nclass=19, path_num=4, backbone="resnet18", ln_shape=(8, 12))
+    net1.load_state_dict(sd, strict=True)
+    net1 = net1.eval().to("cuda:1")
+    torch.cuda.set_device(0)
+    for i, f in enumerate(synth_clip(5, 64, 96, clip_id=4)):
+        a = net0(f.to("cuda:0"), pos_id=i % 4)
+        b = net1(f.to("cuda:1"), pos_id=i % 4)
+        assert b.device.index == 1 and torch.equal(a.cpu(), b.cpu()), i
+
+
+def test_baseline_config5_td4_resnet50_1024x2048_single_stream_against_oracle():
+    """BASELINE configs[4] at its full size against the ORACLE (the batch-4 test above is a stream-independence
+    property): td4_psp18(backbone='resnet50'), one stream, 1024x2048 -- three warm-up frames and the first steady-state
+    frame (d_v = 2048 attention, deep stem, Bottleneck layers at 128x256)."""
+    H, W = 1024, 2048
+    oracle, sd = make_oracle("td4_psp18", "resnet50", H, W)
+    net = build_model("td4_psp18", "resnet50", 128, 256, sd)
+    for i, f in enumerate(synth_clip(4, H, W, clip_id=9)):
+        ref = oracle(f, pos_id=i % 4)
+        out = net(f.cuda(), pos_id=i % 4).cpu()
+        e = max_abs(out, ref)
+        rep = argmax_report(out, ref, max(e, 1e-6))
+        record(f"oracle/td4r50_1024x2048/frame{i}", max_abs=e, rel_l2=rel_l2(out, ref), **rep)
+        assert e <= LOGIT_TOL and rep["mismatch_decided"] == 0, (i, e, rep)
     net.check_numeric_range()

@@ -161,3 +161,19 @@ def test_state_dict_template_sizes():
     from oracle.td2fa_oracle import td2fa_state_dict_template
     sd = td2fa_state_dict_template("resnet18")   # checked against the reference module in make_golden_fanet.py
     assert sd["ffm_32_1.up.conv.weight"].shape == (256, 512, 1, 1) and sd["head_aux2.conv_out.weight"].shape == (19, 64, 1, 1)
+
+
+def test_oracle_ref_is_a_byte_identical_copy_of_the_reference_tree():
+    """oracle/_ref/Testing (oracle/make_ref.py) must be the reference's Testing/ tree byte for byte: the manifest
+    written at copy time is re-derived from the copy, and from /root/reference when that exists here."""
+    import json
+    import os
+    from oracle import make_ref
+    man = os.path.join(os.path.dirname(make_ref.DST), "MANIFEST.json")
+    if not os.path.isfile(man):
+        pytest.skip("oracle/_ref absent")
+    files = json.load(open(man))["files"]
+    assert "test.py" in files and "dataloader.py" in files and "model/pspnet/td4_psp18.py" in files
+    assert make_ref.manifest(make_ref.DST) == files
+    if os.path.isdir(make_ref.SRC):
+        assert make_ref.manifest(make_ref.SRC) == files
