@@ -123,7 +123,7 @@ __global__ void psp_rowsum_kernel(View in, float* __restrict__ rowsum) {
     cur[l] = j;
     nend[l] = bin_end(j, lv_o[l], W);
   }
-  constexpr int UN = 8;   // loads issued ahead of the (serial) range bookkeeping
+  constexpr int UN = 8;   // loads issued ahead of the (serial) range bookkeeping (32 was measured 2.8x slower: registers)
   for (int x0 = x_lo; x0 < x_hi; x0 += UN) {
     float vbuf[UN];
 #pragma unroll
@@ -661,6 +661,42 @@ int layernorm_hw_stats(const tdn_tensor* x, float* mean, float* rstd, float eps,
   return TDN_OK;
 }
 
+// SPLIT16 in and out, c % 8 == 0: 8 channels per thread with 16-byte accesses on every plane (same arithmetic).
+__global__ void ln_apply_split8_kernel(View x, View out, const float* __restrict__ mean,
+                                       const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                       const float* __restrict__ beta) {
+  const int c8 = x.c >> 3;
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long total = (long long)x.n * x.h * x.w * c8;
+  if (idx >= total) return;
+  const int c = (idx % c8) * 8;
+  long long t = idx / c8;
+  const int xx = t % x.w; t /= x.w;
+  const int y = t % x.h;
+  const int b = t / x.h;
+  const float g = gamma[y * x.w + xx], be = beta[y * x.w + xx];
+  const long long ioff = b * x.sn + y * x.sh + xx * x.sw + c;
+  const uint4 hv = *reinterpret_cast<const uint4*>(x.hi + ioff);
+  const uint4 lv = *reinterpret_cast<const uint4*>(x.lo + ioff);
+  const __half2* h = reinterpret_cast<const __half2*>(&hv);
+  const __half2* l = reinterpret_cast<const __half2*>(&lv);
+  float mu[8], rs[8];
+  *reinterpret_cast<float4*>(mu) = *reinterpret_cast<const float4*>(mean + b * x.c + c);
+  *reinterpret_cast<float4*>(mu + 4) = *reinterpret_cast<const float4*>(mean + b * x.c + c + 4);
+  *reinterpret_cast<float4*>(rs) = *reinterpret_cast<const float4*>(rstd + b * x.c + c);
+  *reinterpret_cast<float4*>(rs + 4) = *reinterpret_cast<const float4*>(rstd + b * x.c + c + 4);
+  __half2 oh[4], ol[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 a = __half22float2(h[e]), d = __half22float2(l[e]);
+    const float v0 = a.x + d.x, v1 = a.y + d.y;
+    split_f32x2((v0 - mu[2 * e]) * rs[2 * e] * g + be, (v1 - mu[2 * e + 1]) * rs[2 * e + 1] * g + be, oh[e], ol[e]);
+  }
+  const long long ooff = b * out.sn + y * out.sh + xx * out.sw + c;
+  *reinterpret_cast<uint4*>(out.hi + ooff) = *reinterpret_cast<const uint4*>(oh);
+  *reinterpret_cast<uint4*>(out.lo + ooff) = *reinterpret_cast<const uint4*>(ol);
+}
+
 __global__ void ln_apply_kernel(View x, View out, const float* __restrict__ mean,
                                 const float* __restrict__ rstd, const float* __restrict__ gamma,
                                 const float* __restrict__ beta) {
@@ -696,8 +732,16 @@ int layernorm_hw_apply(const tdn_tensor* x, const float* mean, const float* rstd
   TDN_REQUIRE(x->n == out->n && x->h == out->h && x->w == out->w && x->c == out->c, TDN_ERR_INVALID,
               "layernorm_hw_apply: dims mismatch");
   long long total = (long long)x->n * x->h * x->w * (x->c / 4);
-  ln_apply_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(make_view(*x), make_view(*out), mean, rstd,
-                                                            gamma, beta);
+  const bool split8 = x->dtype == TDN_SPLIT16 && out->dtype == TDN_SPLIT16 && x->c % 8 == 0 && aligned16(x->data) &&
+                      aligned16(x->data_lo) && aligned16(out->data) && aligned16(out->data_lo) &&
+                      x->stride_n % 8 == 0 && x->stride_h % 8 == 0 && x->stride_w % 8 == 0 &&
+                      out->stride_n % 8 == 0 && out->stride_h % 8 == 0 && out->stride_w % 8 == 0;
+  if (split8)
+    ln_apply_split8_kernel<<<ceil_div(total / 2, 256), 256, 0, stream>>>(make_view(*x), make_view(*out), mean, rstd,
+                                                                        gamma, beta);
+  else
+    ln_apply_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(make_view(*x), make_view(*out), mean, rstd,
+                                                              gamma, beta);
   TDN_LAUNCH_OK();
   return TDN_OK;
 }
