@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TDN_ABI_VERSION 1
+#define TDN_ABI_VERSION 2 /* 2: `flags` appended to tdn_tc_conv_desc and tdn_attention_desc */
 
 typedef enum tdn_status {
   TDN_OK = 0,
@@ -140,7 +140,13 @@ typedef struct tdn_tc_conv_desc {
   int32_t variant; /* TDN_TC_AUTO (0): the library picks the kernel; otherwise force one (tests / tuning;
                       TDN_ERR_UNSUPPORTED if the geometry does not fit it).  All variants compute the same
                       products in the same order and are bit-identical. */
+  int32_t flags;   /* TDN_TC_FLAG_* (0 = exact mode) */
 } tdn_tc_conv_desc;
+
+/* Opt-in FAST mode: one fp16 tensor-core product per K step (the hi planes only) instead of the three exact-mode
+ * products -- roughly bf16/fp16-GEMM accuracy (11-bit operands), NOT the reference's fp32 arithmetic.  Never the parity
+ * gate; bench.py reports its speed next to its measured arg-max mismatch rate. */
+enum { TDN_TC_FLAG_FAST = 1 };
 
 enum {
   TDN_TC_AUTO = 0,
@@ -178,6 +184,7 @@ typedef struct tdn_attention_desc {
   tdn_tensor residual; /* residual.data == NULL -> none */
   int32_t n, pq, pk, d_k, d_v;
   int32_t* range_flag;
+  int32_t flags; /* TDN_TC_FLAG_* (0 = exact mode); FAST: Qhi.Khi^T and Phi.V'hi^T only */
 } tdn_attention_desc;
 
 int tdn_attention_tc(const tdn_attention_desc* desc, void* stream);

@@ -40,7 +40,7 @@ class TcConvDesc(C.Structure):
                 ("scale", C.c_void_p), ("bias", C.c_void_p),
                 ("cout", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32), ("dilation", C.c_int32),
                 ("act", C.c_int32), ("leaky_slope", C.c_float), ("range_flag", C.c_void_p),
-                ("stride", C.c_int32), ("variant", C.c_int32)]
+                ("stride", C.c_int32), ("variant", C.c_int32), ("flags", C.c_int32)]
 
 
 TC_AUTO, TC_BASE, TC_HALO, TC_PAIR = 0, 1, 2, 3   # tdn_tc_conv_desc.variant
@@ -52,8 +52,10 @@ class AttentionDesc(C.Structure):
                 ("vt_hi", C.c_void_p), ("vt_lo", C.c_void_p), ("vt_ld", C.c_int64), ("vt_batch_stride", C.c_int64),
                 ("out", Tensor), ("residual", Tensor),
                 ("n", C.c_int32), ("pq", C.c_int32), ("pk", C.c_int32), ("d_k", C.c_int32), ("d_v", C.c_int32),
-                ("range_flag", C.c_void_p)]
+                ("range_flag", C.c_void_p), ("flags", C.c_int32)]
 
+
+TC_FLAG_FAST = 1   # tdn_tc_conv_desc.flags / tdn_attention_desc.flags: one fp16 product per K step (opt-in, not fp32-faithful)
 
 # symbol -> (restype, argtypes); tests/test_cabi.py checks this list against include/tdnet_b200.h
 _TP = C.POINTER(Tensor)
@@ -121,7 +123,7 @@ def load():
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError here = header/library drift
         fn.restype, fn.argtypes = res, args
-    if lib.tdn_abi_version() != 1:
+    if lib.tdn_abi_version() != 2:
         raise RuntimeError("tdnet_b200: ABI version mismatch between _cabi.py and the library")
     _lib = lib
     return lib

@@ -193,9 +193,13 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant
           for (int k = 0; k < AT_DK / 16; ++k) {
             const uint64_t a_h = umma_desc_k_sw128(q_hi + k * 32), b_h = umma_desc_k_sw128(k_hi + k * 32);
             const uint64_t a_l = umma_desc_k_sw128(q_lo + k * 32), b_l = umma_desc_k_sw128(k_lo + k * 32);
-            umma_f16(d, a_h, b_l, idesc_s, k != 0);
-            umma_f16(d, a_l, b_h, idesc_s, 1);
-            umma_f16(d, a_h, b_h, idesc_s, 1);
+            if (p.fast) {
+              umma_f16(d, a_h, b_h, idesc_s, k != 0);
+            } else {
+              umma_f16(d, a_h, b_l, idesc_s, k != 0);
+              umma_f16(d, a_l, b_h, idesc_s, 1);
+              umma_f16(d, a_h, b_h, idesc_s, 1);
+            }
           }
           umma_commit(&bars->s_full[sb]);
           umma_commit(&bars->k_empty[ks]);
@@ -227,9 +231,13 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant
             for (int k = 0; k < AT_BK / 16; ++k) {
               const uint64_t a_h = umma_desc_k_sw128(p_hi + k * 32), a_l = umma_desc_k_sw128(p_lo + k * 32);
               const uint64_t b_h = umma_desc_k_sw128(v_hi + k * 32), b_l = umma_desc_k_sw128(v_lo + k * 32);
-              umma_f16(d, a_h, b_l, idesc_o, (kt | k) != 0);
-              umma_f16(d, a_l, b_h, idesc_o, 1);
-              umma_f16(d, a_h, b_h, idesc_o, 1);
+              if (p.fast) {
+                umma_f16(d, a_h, b_h, idesc_o, (kt | k) != 0);
+              } else {
+                umma_f16(d, a_h, b_l, idesc_o, (kt | k) != 0);
+                umma_f16(d, a_l, b_h, idesc_o, 1);
+                umma_f16(d, a_h, b_h, idesc_o, 1);
+              }
             }
             umma_commit(&bars->v_empty[vs]);
             if (h == HALVES - 1) {
@@ -512,6 +520,7 @@ int attention_tc(const tdn_attention_desc* d, cudaStream_t stream) {
     p.r_bs = r.stride_n; p.r_ld = r.stride_w;
   }
   p.range_flag = d->range_flag;
+  p.fast = (d->flags & TDN_TC_FLAG_FAST) ? 1 : 0;
 
   CUtensorMap mq_h, mq_l, mk_h, mk_l, mv_h, mv_l;
   int rc;

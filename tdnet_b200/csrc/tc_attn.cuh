@@ -50,6 +50,7 @@ struct AttnParams {
   const float* res_f32;
   long long r_bs, r_ld;
   int* range_flag;
+  int fast;                 // TDN_TC_FLAG_FAST: Qhi.Khi^T and Phi.V'hi^T only (opt-in, not fp32-faithful)
 };
 
 

@@ -427,9 +427,13 @@ tc_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_const
           for (int k = 0; k < AT_DK / 16; ++k) {
             const uint64_t a_h = umma_desc_k_sw128(q_hi + k * 32), b_h = umma_desc_k_sw128(k_hi + k * 32);
             const uint64_t a_l = umma_desc_k_sw128(q_lo + k * 32), b_l = umma_desc_k_sw128(k_lo + k * 32);
-            umma_f16(d, a_h, b_l, idesc_s, k != 0);
-            umma_f16(d, a_l, b_h, idesc_s, 1);
-            umma_f16(d, a_h, b_h, idesc_s, 1);
+            if (p.fast) {
+              umma_f16(d, a_h, b_h, idesc_s, k != 0);
+            } else {
+              umma_f16(d, a_h, b_l, idesc_s, k != 0);
+              umma_f16(d, a_l, b_h, idesc_s, 1);
+              umma_f16(d, a_h, b_h, idesc_s, 1);
+            }
           }
           umma_commit(&bars->s_full[sb]);
           umma_commit(&bars->k_empty[ks]);
@@ -464,9 +468,13 @@ tc_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_const
               // lo pairs 16 columns further
               const uint32_t a_h = p_base + (k >> 1) * 32 + (k & 1) * 8, a_l = a_h + 16;
               const uint64_t b_h = umma_desc_k_sw128(v_hi + k * 32), b_l = umma_desc_k_sw128(v_lo + k * 32);
-              umma_f16_ts(d, a_h, b_l, idesc_o, (kt | k) != 0);
-              umma_f16_ts(d, a_l, b_h, idesc_o, 1);
-              umma_f16_ts(d, a_h, b_h, idesc_o, 1);
+              if (p.fast) {
+                umma_f16_ts(d, a_h, b_h, idesc_o, (kt | k) != 0);
+              } else {
+                umma_f16_ts(d, a_h, b_l, idesc_o, (kt | k) != 0);
+                umma_f16_ts(d, a_l, b_h, idesc_o, 1);
+                umma_f16_ts(d, a_h, b_h, idesc_o, 1);
+              }
             }
             umma_commit(&bars->v_empty[vs]);
             if (h == HALVES - 1) {

@@ -40,6 +40,7 @@ struct TcParams {
   const float* res_f32;
   long long rsn, rsh, rsw;
   int* range_flag;
+  int fast;              // TDN_TC_FLAG_FAST: issue only the hi x hi product of every K step
 };
 
 // Launch of a persistent tcgen05 kernel, optionally with programmatic dependent launch: the kernel's setup (barrier

@@ -152,9 +152,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               const uint64_t a_lo = umma_desc_k_sw128(sa + TC_A_PLANE + k * 32);
               const uint64_t b_hi = umma_desc_k_sw128(sb + k * 32);
               const uint64_t b_lo = umma_desc_k_sw128(sb + Cfg::B_PLANE + k * 32);
-              umma_f16(d_tmem, a_hi, b_lo, idesc, ((kb - kb0) | k) != 0);
-              umma_f16(d_tmem, a_lo, b_hi, idesc, 1);
-              umma_f16(d_tmem, a_hi, b_hi, idesc, 1);
+              if (p.fast) {
+                umma_f16(d_tmem, a_hi, b_hi, idesc, ((kb - kb0) | k) != 0);
+              } else {
+                umma_f16(d_tmem, a_hi, b_lo, idesc, ((kb - kb0) | k) != 0);
+                umma_f16(d_tmem, a_lo, b_hi, idesc, 1);
+                umma_f16(d_tmem, a_hi, b_hi, idesc, 1);
+              }
             }
             umma_commit(&empty_bar[stage]);
             if (kb == kb1 - 1) umma_commit(&tmem_full[as]);
@@ -339,6 +343,7 @@ int conv2d_tc(const tdn_tc_conv_desc* d, cudaStream_t stream) {
     p.rsn = r.stride_n; p.rsh = r.stride_h; p.rsw = r.stride_w;
   }
   p.range_flag = d->range_flag;
+  p.fast = (d->flags & TDN_TC_FLAG_FAST) ? 1 : 0;
 
   {
     // Kernel choice.  d->variant forces one (tests / tuning); otherwise:

@@ -148,9 +148,13 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
               const uint64_t a_lo = umma_desc_k_noswz(a_lo_addr, lbo, sbo);
               const uint64_t b_hi = umma_desc_k_sw128(sb + k * 32);
               const uint64_t b_lo = umma_desc_k_sw128(sb + Cfg::B_PLANE + k * 32);
-              umma_f16(d_tmem, a_hi, b_lo, idesc, (in_chunk | k) != 0);
-              umma_f16(d_tmem, a_lo, b_hi, idesc, 1);
-              umma_f16(d_tmem, a_hi, b_hi, idesc, 1);
+              if (p.fast) {
+                umma_f16(d_tmem, a_hi, b_hi, idesc, (in_chunk | k) != 0);
+              } else {
+                umma_f16(d_tmem, a_hi, b_lo, idesc, (in_chunk | k) != 0);
+                umma_f16(d_tmem, a_lo, b_hi, idesc, 1);
+                umma_f16(d_tmem, a_hi, b_hi, idesc, 1);
+              }
             }
             umma_commit(&b_empty[bs]);
             if (tap == 8) umma_commit(&a_empty[as_]);

@@ -147,9 +147,13 @@ tc_conv_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                 const uint64_t a_lo = umma_desc_k_sw128(sa + TC_A_PLANE + k * 32);
                 const uint64_t b_hi = umma_desc_k_sw128(sb + k * 32);
                 const uint64_t b_lo = umma_desc_k_sw128(sb + Cfg::B_HALF_PLANE + k * 32);
-                umma_f16_pair(d_tmem, a_hi, b_lo, idesc, ((kb - kb0) | k) != 0);
-                umma_f16_pair(d_tmem, a_lo, b_hi, idesc, 1);
-                umma_f16_pair(d_tmem, a_hi, b_hi, idesc, 1);
+                if (p.fast) {
+                  umma_f16_pair(d_tmem, a_hi, b_hi, idesc, ((kb - kb0) | k) != 0);
+                } else {
+                  umma_f16_pair(d_tmem, a_hi, b_lo, idesc, ((kb - kb0) | k) != 0);
+                  umma_f16_pair(d_tmem, a_lo, b_hi, idesc, 1);
+                  umma_f16_pair(d_tmem, a_hi, b_hi, idesc, 1);
+                }
               }
               umma_commit_pair(&empty_bar[stage], 3);
               if (kb == kb1 - 1) umma_commit_pair(&tmem_full[as], 3);

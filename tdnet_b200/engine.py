@@ -227,10 +227,13 @@ class Engine:
 
     def __init__(self, arch: A.ModelArch, state_dict, n, H, W, device, ln_shape, mode="tc"):
         """mode 'tc': tcgen05 exact-mode kernels on SPLIT16 activations wherever the shape allows (the
-        product path on B200); mode 'simt': everything on the fp32 CUDA-core kernels (yardstick)."""
-        assert mode in ("tc", "simt")
+        product path on B200); mode 'simt': everything on the fp32 CUDA-core kernels (yardstick); mode 'tc_fast': the
+        'tc' plans with TDN_TC_FLAG_FAST on every tensor-core conv / attention call -- one fp16 product per K step
+        instead of three, NOT fp32-faithful (opt-in; bench.py reports its arg-max mismatch rate)."""
+        assert mode in ("tc", "simt", "tc_fast")
         self.lib = _cabi.load()
-        self.tc = mode == "tc"
+        self.tc = mode in ("tc", "tc_fast")
+        self.tc_flags = _cabi.TC_FLAG_FAST if mode == "tc_fast" else 0
         import os
         self.fused_attn = os.environ.get("TDNET_B200_FUSED_ATTN", "1") != "0"
         self.tc_stride2 = os.environ.get("TDNET_B200_TC_STRIDE2", "1") != "0"
@@ -383,6 +386,7 @@ class Engine:
             d.cout, d.kh, d.kw, d.dilation, d.act = cout, k, k, dilation, _ACT[act]
         d.leaky_slope = 0.01
         d.range_flag = self.range_flag.data_ptr()
+        d.flags = self.tc_flags
         plan.add(self.lib.tdn_conv2d_tc, C.byref(d), "stream", name=name)
         plan.keep.append((d, pc, x, out, residual, scale, bias))
 
@@ -857,6 +861,7 @@ class Engine:
             d.out, d.residual = out_tok.ct(), res_tok.ct()
             d.n, d.pq, d.pk, d.d_k, d.d_v = n, pq, pk, m.d_k, m.d_v
             d.range_flag = self.range_flag.data_ptr()
+            d.flags = self.tc_flags
             plan.add(lib.tdn_attention_tc, C.byref(d), "stream", name=f"atn{idx}.attention",
                      launches=self._attention_launches(n, pq, m.d_v))
             plan.keep.append((d, q_all, k_tok, vpt, out_tok, res_tok))
@@ -978,6 +983,7 @@ class Engine:
                 d.out, d.residual = out_tok.ct(), res_tok.ct()
                 d.n, d.pq, d.pk, d.d_k, d.d_v = n, pq, pk, m.d_k, m.d_v
                 d.range_flag = self.range_flag.data_ptr()
+                d.flags = self.tc_flags
                 plan.add(lib.tdn_attention_tc, C.byref(d), "stream", name=name + ".attention",
                          launches=self._attention_launches(n, pq, m.d_v))
                 plan.keep.append((d, q_all, k_slot, vpt, out_tok, res_tok))

@@ -18,18 +18,30 @@ from . import arch as A
 
 
 class _Group(nn.Module):
-    """Pure parameter container; never called."""
+    """Pure parameter container; never called.  Loading a state dict into a sub-module (the reference's own idiom in
+    td2_fa.pretrained_init, or `model.pretrained1.load_state_dict(...)`) invalidates the packed device weights of the
+    model it belongs to."""
 
     def forward(self, *a, **k):  # pragma: no cover
         raise RuntimeError("parameter container; the computation runs in the CUDA engine")
 
+    def _load_from_state_dict(self, *a, **k):
+        out = super()._load_from_state_dict(*a, **k)
+        root = getattr(self, "_td_root", None)
+        if root is not None and root() is not None:
+            root().invalidate()
+        return out
+
 
 def _attach(root: nn.Module, key: str, shape, kind: str):
+    import weakref
     *parents, leaf = key.split(".")
     mod = root
     for p in parents:
         if not hasattr(mod, p):
-            mod.add_module(p, _Group())
+            g = _Group()
+            object.__setattr__(g, "_td_root", weakref.ref(root))     # plain attribute: not a sub-module, no cycle
+            mod.add_module(p, g)
         mod = getattr(mod, p)
     if kind == "param":
         t = torch.zeros(shape)
@@ -57,6 +69,7 @@ def _default_init_(module: nn.Module, seed=0):
 class TDModel(nn.Module):
     ARCH = None          # 'td4_psp18' | 'td2_psp50' | 'pspnet'
     PATHS = None
+    MAX_ENGINES = 2      # engines (packed weights + plans + scratch) kept alive, keyed by (n, H, W, device, mode)
     BACKBONES = ("resnet50", "resnet34", "resnet18")
 
     def __init__(self, nclass=21, norm_layer=None, backbone=None, dilated=True, aux=True, multi_grid=True,
@@ -90,7 +103,8 @@ class TDModel(nn.Module):
         self._engines: Dict[tuple, object] = {}
         self.pretrained_mp_load()
         self.Q_queue, self.K_queue, self.V_queue = [], [], []
-        # 'tc': tcgen05 exact-mode kernels (product path on B200); 'simt': fp32 CUDA-core kernels only.
+        # 'tc': tcgen05 exact-mode kernels (product path on B200); 'simt': fp32 CUDA-core kernels only;
+        # 'tc_fast': opt-in single-product tensor-core mode (NOT fp32-faithful, never the parity gate).
         self.engine_mode = os.environ.get("TDNET_B200_ENGINE", "tc")
         # Replay each static frame plan through a CUDA graph (removes ~60 launch gaps).  All plans of a model are
         # built, run once on a scratch frame and captured when the engine is created (first forward of a new input
@@ -109,20 +123,36 @@ class TDModel(nn.Module):
             else:
                 print("No pretrained found at '{}'".format(self.psp_path))
 
+    def invalidate(self):
+        """Drop the packed device weights, frame plans and CUDA graphs; they are rebuilt from the current parameters at
+        the next forward.  Called automatically by load_state_dict() (of the model or any sub-module), .to() / .half() /
+        .float(), set_ln_shape(); call it yourself after editing parameters in place (`p.data.copy_(...)`)."""
+        self._engines.clear()
+        self._range_host = None
+
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        if getattr(self, "_engines", None):
+            self.invalidate()
+        return out
+
     def set_ln_shape(self, h8, w8):
         """Re-create the LayerNorm affine for another feature-map size (the reference hard-codes
-        [97,193], td4_psp18.py:107-110, i.e. 769x1537 inputs; tests patch it the same way)."""
+        [97,193], td4_psp18.py:107-110, i.e. 769x1537 inputs; tests patch it the same way).  A no-op when the shape
+        already matches (loaded affine weights are kept)."""
+        if tuple(self.ln_shape) == (h8, w8):
+            return
         self.ln_shape = (h8, w8)
         dev = next(self.parameters()).device
         for p in range(1, self.PATHS + 1):
             ln = getattr(self, f"layer_norm{p}").ln
             ln.weight = nn.Parameter(torch.ones(h8, w8, device=dev), requires_grad=False)
             ln.bias = nn.Parameter(torch.zeros(h8, w8, device=dev), requires_grad=False)
-        self._engines.clear()
+        self.invalidate()
 
     def load_state_dict(self, state_dict, strict=True, **kw):
         out = super().load_state_dict(state_dict, strict=strict, **kw)
-        self._engines.clear()  # packed device weights are rebuilt lazily
+        self.invalidate()  # packed device weights are rebuilt lazily
         return out
 
     def reset(self):
@@ -143,15 +173,19 @@ class TDModel(nn.Module):
         key = (n, h, w, img.device.index, self.engine_mode)
         eng = self._engines.get(key)
         if eng is None:
-            if self._engines:  # a different input shape starts a new clip: the FIFO lives in the engine
-                self._engines.clear()
-                self.reset()
             sd = {k: v.detach().cpu() for k, v in self.state_dict().items()}
             eng = Engine(self.arch, sd, n, h, w, img.device, self.ln_shape, mode=self.engine_mode)
+            while len(self._engines) >= self.MAX_ENGINES:          # small LRU: alternating two input shapes does not
+                self._engines.pop(next(iter(self._engines)))       # re-pack every weight on each switch
             self._engines[key] = eng
             self._range_host = None
             if self.use_cuda_graph:
                 eng.prepare_graphs()
+            self.reset()       # a different input shape starts a new clip: the FIFO lives in the engine
+        elif key != getattr(self, "_active_key", key):
+            self._engines[key] = self._engines.pop(key)            # most recently used last
+            self.reset()
+        self._active_key = key
         return eng
 
     def prepare(self, n, h, w, device=None):

@@ -36,7 +36,7 @@ def test_every_declared_symbol_is_exported(lib):
 
 
 def test_info_calls_without_gpu(lib):
-    assert lib.tdn_abi_version() == 1
+    assert lib.tdn_abi_version() == 2
     assert lib.tdn_strerror(0) == b"ok"
     assert b"sm_100" in lib.tdn_strerror(-4)
     assert lib.tdn_psp_pool_workspace_bytes(1, 128, 512) == 128 * 12 * 512 * 4

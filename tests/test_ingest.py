@@ -83,6 +83,6 @@ def test_header_is_valid_c(tmp_path):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     src = tmp_path / "abi.c"
     src.write_text('#include "tdnet_b200.h"\n'
-                   "int main(void) { tdn_tensor t; tdn_attention_desc d; (void)t; (void)d; return TDN_ABI_VERSION - 1; }\n")
+                   "int main(void) { tdn_tensor t; tdn_attention_desc d; (void)t; (void)d; return TDN_ABI_VERSION - 2; }\n")
     subprocess.check_call([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(root, "include"),
                            "-c", str(src), "-o", str(tmp_path / "abi.o")])
