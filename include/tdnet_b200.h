@@ -189,6 +189,10 @@ typedef struct tdn_attention_desc {
 
 int tdn_attention_tc(const tdn_attention_desc* desc, void* stream);
 
+/* Number of kernels tdn_attention_tc(desc) launches on the current device (1, or 2 when the shared-memory-operand kernel
+ * family runs the ragged last round as a second launch); same validation and decisions, nothing is launched. */
+int tdn_attention_tc_launches(const tdn_attention_desc* desc, int32_t* launches);
+
 /* fp32 plane <-> SPLIT16 planes (hi = fp16(x), lo = fp16(x - hi)); views must have equal dims. */
 int tdn_split16(const tdn_tensor* in_f32, const tdn_tensor* out_split16, void* stream);
 int tdn_merge16(const tdn_tensor* in_split16, const tdn_tensor* out_f32, void* stream);

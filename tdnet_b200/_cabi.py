@@ -67,6 +67,7 @@ SIGNATURES = {
     "tdn_conv2d": (C.c_int, [C.POINTER(Conv2dDesc), C.c_void_p]),
     "tdn_conv2d_tc": (C.c_int, [C.POINTER(TcConvDesc), C.c_void_p]),
     "tdn_attention_tc": (C.c_int, [C.POINTER(AttentionDesc), C.c_void_p]),
+    "tdn_attention_tc_launches": (C.c_int, [C.POINTER(AttentionDesc), C.POINTER(C.c_int32)]),
     "tdn_split16": (C.c_int, [_TP, _TP, C.c_void_p]),
     "tdn_merge16": (C.c_int, [_TP, _TP, C.c_void_p]),
     "tdn_image_to_nhwc": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _TP, C.c_void_p]),

@@ -51,7 +51,7 @@ int upsample_argmax(const tdn_tensor*, uint8_t*, int, int, cudaStream_t);
 int conv2d_tc(const tdn_tc_conv_desc*, cudaStream_t);
 int stem_conv_pool(const float*, const uint8_t*, const float*, int, int, int, const float*, const float*, const float*,
                    const tdn_tensor*, cudaStream_t);
-int attention_tc(const tdn_attention_desc*, cudaStream_t);
+int attention_tc(const tdn_attention_desc*, cudaStream_t, int* count_only);
 int stem_conv_pool_tc(const float*, const uint8_t*, const float*, int, int, int, const void*, const float*, const float*,
                       const tdn_tensor*, int, float, int*, cudaStream_t);
 int split16(const tdn_tensor*, const tdn_tensor*, cudaStream_t);
@@ -143,7 +143,15 @@ int tdn_attention_tc(const tdn_attention_desc* d, void* stream) {
   const int arch = cached_device_arch();
   if (arch < 0) return arch;
   TDN_REQUIRE(arch / 10 == 10, TDN_ERR_ARCH, "attention_tc: tcgen05 kernels need sm_100, device is sm_%d", arch);
-  return attention_tc(d, (cudaStream_t)stream);
+  return attention_tc(d, (cudaStream_t)stream, nullptr);
+}
+
+int tdn_attention_tc_launches(const tdn_attention_desc* d, int32_t* launches) {
+  TDN_REQUIRE(d != nullptr && launches != nullptr, TDN_ERR_INVALID, "attention_tc_launches: null argument");
+  int n = 0;
+  const int rc = attention_tc(d, nullptr, &n);
+  *launches = n;
+  return rc;
 }
 
 int tdn_split16(const tdn_tensor* in, const tdn_tensor* out, void* stream) {

@@ -463,7 +463,9 @@ int encode_map_f16(CUtensorMap* m, const void* base, int rank, const cuuint64_t*
                    const cuuint64_t* strides_bytes, const cuuint32_t* box, const char* what,
                    const cuuint32_t* elem_strides, int swizzle128 = 1);
 
-int attention_tc(const tdn_attention_desc* d, cudaStream_t stream) {
+// count_only != nullptr: validate, make the same kernel-selection decisions, and report how many kernels the call
+// would launch instead of launching them (tdn_attention_tc_launches).
+int attention_tc(const tdn_attention_desc* d, cudaStream_t stream, int* count_only) {
   TDN_REQUIRE(d->q_hi && d->q_lo && d->k_hi && d->k_lo && d->vt_hi && d->vt_lo, TDN_ERR_INVALID,
               "attention_tc: null operand");
   TDN_REQUIRE(d->d_k == AT_DK, TDN_ERR_UNSUPPORTED, "attention_tc: d_k must be 64 (got %d)", d->d_k);
@@ -493,6 +495,7 @@ int attention_tc(const tdn_attention_desc* d, cudaStream_t stream) {
   long long items = (long long)d->n * p.q_tiles * p.dv_tiles;
   TDN_REQUIRE(items < (1ll << 31), TDN_ERR_UNSUPPORTED, "attention_tc: too many work items");
   p.num_items = (int)items;
+  p.items_a = p.num_items;   // no mixed-width tail unless the split below says so
   p.scale_log2 = 1.4426950408889634f / sqrtf((float)d->d_k);
   if (out.dtype == TDN_SPLIT16) {
     TDN_REQUIRE(out.data_lo && aligned16(out.data) && aligned16(out.data_lo) && out.stride_w % 8 == 0 &&
@@ -562,6 +565,7 @@ int attention_tc(const tdn_attention_desc* d, cudaStream_t stream) {
     }
   }
   auto launch = [&](int dvt, int grid, const AttnParams& pp) -> cudaError_t {
+    if (count_only) { ++*count_only; return cudaSuccess; }
     const bool short_launch = pp.num_items <= 2 * grid;
     if (use_ts) return attention_ts_launch(dvt, grid, stream, short_launch, mq_h, mq_l, mk_h, mk_l, mv_h, mv_l, pp);
     if (dvt == 256)
@@ -592,6 +596,17 @@ int attention_tc(const tdn_attention_desc* d, cudaStream_t stream) {
       AttnParams p1 = p, p2 = p;
       p1.q_tiles = q1; p1.num_items = (int)items1;
       p2.qt_begin = q1; p2.q_tiles = q2; p2.dv_tiles = d->d_v / 128; p2.num_items = (int)items2;
+      if (use_ts) {
+        // one launch: every CTA walks its 256-wide items and then (at most) one 128-wide tail item -- no kernel boundary,
+        // and the tail item's pass 1 / prologue overlap the previous item's epilogue like any other item
+        AttnParams pm = p1;
+        pm.items_a = p1.num_items;
+        pm.num_items = p1.num_items + p2.num_items;
+        pm.dv_tiles_b = p2.dv_tiles; pm.qt_begin_b = p2.qt_begin; pm.q_tiles_b = p2.q_tiles;
+        TDN_CUDA_OK(launch(256, num_sms, pm));
+        return TDN_OK;
+      }
+      p1.items_a = p1.num_items; p2.items_a = p2.num_items;
       const int g1 = p1.num_items < num_sms ? p1.num_items : num_sms;
       const int g2 = p2.num_items < num_sms ? p2.num_items : num_sms;
       TDN_CUDA_OK(launch(256, g1, p1));

@@ -40,6 +40,10 @@ struct AttnParams {
   int n_img, Pq, Pk;
   int q_tiles, dv_tiles, k_tiles, k_tiles1, num_items;   // k_tiles: 64-key tiles (pass 2); k_tiles1: 128-key tiles (pass 1)
   int qt_begin;             // first query tile of this launch (q_tiles counts the tiles of the launch)
+  // tc_attn_ts.cu only: a launch may end with 128-channel-wide "tail" items (the ragged last round of a 256-wide
+  // launch): items [0, items_a) are decoded with (dv_tiles, qt_begin, q_tiles) and are DVT wide, items
+  // [items_a, num_items) with (dv_tiles_b, qt_begin_b, q_tiles_b) and are 128 wide.  items_a == num_items: no tail.
+  int items_a, dv_tiles_b, qt_begin_b, q_tiles_b;
   float scale_log2;         // log2(e) / sqrt(d_k)
   __half* out_hi;
   __half* out_lo;
@@ -53,6 +57,28 @@ struct AttnParams {
   int fast;                 // TDN_TC_FLAG_FAST: Qhi.Khi^T and Phi.V'hi^T only (opt-in, not fp32-faithful)
 };
 
+
+// One work item of a (possibly mixed-width) launch.
+struct AttnItem { int qt, img, dv0, halves; };
+template <int DVT>
+__device__ __forceinline__ AttnItem attn_item(const AttnParams& p, int item) {
+  AttnItem it;
+  if (item < p.items_a) {
+    const int t = item / p.dv_tiles;
+    it.dv0 = (item - t * p.dv_tiles) * DVT;
+    it.img = t / p.q_tiles;
+    it.qt = p.qt_begin + (t - it.img * p.q_tiles);
+    it.halves = DVT / AT_DVH;
+  } else {
+    const int j = item - p.items_a;
+    const int t = j / p.dv_tiles_b;
+    it.dv0 = (j - t * p.dv_tiles_b) * AT_DVH;
+    it.img = t / p.q_tiles_b;
+    it.qt = p.qt_begin_b + (t - it.img * p.q_tiles_b);
+    it.halves = 1;
+  }
+  return it;
+}
 
 // tc_attn_ts.cu: launch of the TMEM-operand kernel family (dvt = 128 or 256 output channels per work item).
 cudaError_t attention_ts_launch(int dvt, int grid, cudaStream_t stream, bool short_launch, const CUtensorMap& mq_h,

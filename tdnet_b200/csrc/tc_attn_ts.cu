@@ -70,9 +70,10 @@ static_assert(ATS_SMEM_BYTES <= 232448, "attention kernel exceeds the 227 KB sha
 // registers (one chunk ahead) -> block -> row per thread; result row per thread -> block -> global.  The 16-byte
 // pieces are XOR-swizzled so that both arrangements are free of bank conflicts.
 // RES: 0 none, 1 SPLIT16, 2 fp32.  OUT16: SPLIT16 output, else fp32.  q0: first query row of the warp.
-template <int RES, bool OUT16, int NCHUNK>
+template <int RES, bool OUT16>
 __device__ __forceinline__ void attn_epilogue_item(const AttnParams& p, uint32_t tmem_o, uint32_t stg, int lane, int q0,
-                                                   long long rbase, long long obase, float inv, bool& out_of_range) {
+                                                   long long rbase, long long obase, float inv, int NCHUNK,
+                                                   bool& out_of_range) {
   // "piece" arrangement: fp16 plane = 32 rows x 64 B, lanes 4r..4r+3 per row; fp32 = 32 rows x 128 B, lanes 8r..8r+7
   const int rA = lane >> 2, cA = lane & 3, rB = lane >> 3, cB = lane & 7;
   const uint32_t pieceA = stg + rA * 64 + ((cA ^ ((rA >> 1) & 3)) << 4);      // row 8k + rA: + 512 k   (lo plane + 2048)
@@ -320,7 +321,6 @@ tc_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_const
   const uint32_t tmem_SP = tmem_base + 256;      // + b * 64
   const int T = p.k_tiles;
   const int T1 = p.k_tiles1;
-  constexpr int HALVES = DVT / AT_DVH;
 
   if (warp == 0) {
     // ================================ TMA producer: Q tile and key tiles ================================
@@ -328,9 +328,8 @@ tc_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_const
       int ks = 0;
       uint32_t kph = 0, qph = 0;
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-        int t = item / p.dv_tiles;
-        const int qt = p.qt_begin + t % p.q_tiles;
-        const int img = t / p.q_tiles;
+        const AttnItem w = attn_item<DVT>(p, item);
+        const int qt = w.qt, img = w.img;
         mbar_wait(&bars->q_empty, qph ^ 1);
         mbar_expect_tx(&bars->q_full, 2 * AT_Q_PLANE);
         tma_load_3d(sQ, &tmQ_hi, &bars->q_full, 0, qt * AT_BQ, img);
@@ -363,15 +362,15 @@ tc_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_const
       int vs = 0;
       uint32_t vph = 0;
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-        const int dvt = item % p.dv_tiles;
-        const int img = (item / p.dv_tiles) / p.q_tiles;
+        const AttnItem w = attn_item<DVT>(p, item);
+        const int img = w.img;
         for (int kt = 0; kt < T; ++kt) {
-          for (int h = 0; h < HALVES; ++h) {
+          for (int h = 0; h < w.halves; ++h) {
             mbar_wait(&bars->v_empty[vs], vph ^ 1);
             uint8_t* dv = sV + vs * 2 * AT_V_PLANE;
             mbar_expect_tx(&bars->v_full[vs], 2 * AT_V_PLANE);
-            tma_load_3d(dv, &tmV_hi, &bars->v_full[vs], kt * AT_BK, dvt * DVT + h * AT_DVH, img);
-            tma_load_3d(dv + AT_V_PLANE, &tmV_lo, &bars->v_full[vs], kt * AT_BK, dvt * DVT + h * AT_DVH, img);
+            tma_load_3d(dv, &tmV_hi, &bars->v_full[vs], kt * AT_BK, w.dv0 + h * AT_DVH, img);
+            tma_load_3d(dv + AT_V_PLANE, &tmV_lo, &bars->v_full[vs], kt * AT_BK, w.dv0 + h * AT_DVH, img);
             if (++vs == ATS_VSTAGES) { vs = 0; vph ^= 1; }
           }
         }
@@ -451,12 +450,13 @@ tc_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_const
     uint32_t vph = 0, oph = 0;
     uint32_t n2 = 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      const int halves = attn_item<DVT>(p, item).halves;
       mbar_wait(&bars->o_empty, oph ^ 1);                        // epilogue of the previous item has read O
       for (int kt = 0; kt < T; ++kt, ++n2) {
         const int sb = n2 & (ATS_SP - 1);
         mbar_wait(&bars->p_full[sb], (n2 / ATS_SP) & 1);
         const uint32_t p_base = tmem_SP + sb * AT_BK;
-        for (int h = 0; h < HALVES; ++h) {
+        for (int h = 0; h < halves; ++h) {
           mbar_wait(&bars->v_full[vs], vph);
           tc_fence_after();
           const uint32_t v_hi = smem_u32(sV + vs * 2 * AT_V_PLANE), v_lo = v_hi + AT_V_PLANE;
@@ -477,7 +477,7 @@ tc_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_const
               }
             }
             umma_commit(&bars->v_empty[vs]);
-            if (h == HALVES - 1) {
+            if (h == halves - 1) {
               umma_commit(&bars->sp_empty[sb]);
               if (kt == T - 1) umma_commit(&bars->o_full);
             }
@@ -593,14 +593,11 @@ tc_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_const
     uint32_t iph = 0;
     bool out_of_range = false;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-      const int dvt = item % p.dv_tiles;
-      int t = item / p.dv_tiles;
-      const int qt = p.qt_begin + t % p.q_tiles;
-      const int img = t / p.q_tiles;
-      const int q0 = qt * AT_BQ + quarter * 32;                // first query row of this warp
-      constexpr int NCHUNK = DVT / 32;
-      const long long obase = (long long)img * p.o_bs + dvt * DVT;
-      const long long rbase = (long long)img * p.r_bs + dvt * DVT;
+      const AttnItem w = attn_item<DVT>(p, item);
+      const int q0 = w.qt * AT_BQ + quarter * 32;              // first query row of this warp
+      const int NCHUNK = w.halves * (AT_DVH / 32);
+      const long long obase = (long long)w.img * p.o_bs + w.dv0;
+      const long long rbase = (long long)w.img * p.r_bs + w.dv0;
       mbar_wait(&bars->l_full, iph);
       const float l = bars->xch[0][row] + bars->xch[1][row];
       __syncwarp();
@@ -610,12 +607,12 @@ tc_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_const
       tc_fence_after();
       iph ^= 1;
       switch (fmt) {
-        case 0: attn_epilogue_item<0, false, NCHUNK>(p, tmem_o, stg, lane, q0, rbase, obase, inv, out_of_range); break;
-        case 1: attn_epilogue_item<0, true, NCHUNK>(p, tmem_o, stg, lane, q0, rbase, obase, inv, out_of_range); break;
-        case 2: attn_epilogue_item<1, false, NCHUNK>(p, tmem_o, stg, lane, q0, rbase, obase, inv, out_of_range); break;
-        case 3: attn_epilogue_item<1, true, NCHUNK>(p, tmem_o, stg, lane, q0, rbase, obase, inv, out_of_range); break;
-        case 4: attn_epilogue_item<2, false, NCHUNK>(p, tmem_o, stg, lane, q0, rbase, obase, inv, out_of_range); break;
-        default: attn_epilogue_item<2, true, NCHUNK>(p, tmem_o, stg, lane, q0, rbase, obase, inv, out_of_range); break;
+        case 0: attn_epilogue_item<0, false>(p, tmem_o, stg, lane, q0, rbase, obase, inv, NCHUNK, out_of_range); break;
+        case 1: attn_epilogue_item<0, true>(p, tmem_o, stg, lane, q0, rbase, obase, inv, NCHUNK, out_of_range); break;
+        case 2: attn_epilogue_item<1, false>(p, tmem_o, stg, lane, q0, rbase, obase, inv, NCHUNK, out_of_range); break;
+        case 3: attn_epilogue_item<1, true>(p, tmem_o, stg, lane, q0, rbase, obase, inv, NCHUNK, out_of_range); break;
+        case 4: attn_epilogue_item<2, false>(p, tmem_o, stg, lane, q0, rbase, obase, inv, NCHUNK, out_of_range); break;
+        default: attn_epilogue_item<2, true>(p, tmem_o, stg, lane, q0, rbase, obase, inv, NCHUNK, out_of_range); break;
       }
       tc_fence_before();
       __syncwarp();

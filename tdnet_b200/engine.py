@@ -863,7 +863,7 @@ class Engine:
             d.range_flag = self.range_flag.data_ptr()
             d.flags = self.tc_flags
             plan.add(lib.tdn_attention_tc, C.byref(d), "stream", name=f"atn{idx}.attention",
-                     launches=self._attention_launches(n, pq, m.d_v))
+                     launches=self._attention_launches(d))
             plan.keep.append((d, q_all, k_tok, vpt, out_tok, res_tok))
             return out
         vp = pre["vp"]
@@ -985,7 +985,7 @@ class Engine:
                 d.range_flag = self.range_flag.data_ptr()
                 d.flags = self.tc_flags
                 plan.add(lib.tdn_attention_tc, C.byref(d), "stream", name=name + ".attention",
-                         launches=self._attention_launches(n, pq, m.d_v))
+                         launches=self._attention_launches(d))
                 plan.keep.append((d, q_all, k_slot, vpt, out_tok, res_tok))
                 carry = out
                 continue
@@ -1004,22 +1004,15 @@ class Engine:
             carry = out
         return carry
 
-    def _attention_launches(self, n: int, pq: int, d_v: int) -> int:
-        """Kernels one tdn_attention_tc call launches (bench.py's gpu_launches): 2 when the library runs the ragged
-        last round of 256-channel items as a second launch of 128-channel items (tc_attn.cu, attention_tc())."""
-        import os
-        sms = torch.cuda.get_device_properties(self.device).multi_processor_count if self.device.type == "cuda" else 148
-        if d_v % 256 or os.environ.get("TDNET_ATTN_TAIL", "1") == "0":
+    def _attention_launches(self, d) -> int:
+        """Kernels one tdn_attention_tc call launches (bench.py's gpu_launches), asked from the library itself
+        (tdn_attention_tc_launches makes the same decisions as the call); 1 on the CPU plan interpreter."""
+        if self.device.type != "cuda":
             return 1
-        q_tiles, per_qt = (pq + 127) // 128, n * (d_v // 256)
-        items = q_tiles * per_qt
-        if items <= sms or items % sms == 0:
-            return 1
-        q1 = items // sms * sms // per_qt
-        q2 = q_tiles - q1
-        rounds = lambda x: (x + sms - 1) // sms  # noqa: E731
-        split = rounds(q1 * per_qt) + 0.8 * rounds(q2 * n * (d_v // 128))
-        return 2 if (q1 > 0 and q2 > 0 and split < rounds(items)) else 1
+        k = C.c_int32(0)
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.tdn_attention_tc_launches(C.byref(d), C.byref(k)), "attention_tc_launches")
+        return int(k.value)
 
     def _fc_as_activation(self, fc: PackedConv):
         """Attention.fc weight [d_v, d_v] as a SPLIT16 'activation' [1,1,d_v,d_v] (A operand of the
