@@ -475,8 +475,8 @@ def run_ours(args, rank, world):
             "of the tensor peak doing necessary work; traffic = dram read+write bytes of one launch from "
             "profiles/r01_prof_conv_pair_summary.txt")
         roof_attn = tensor_roofline(
-            "tc_attn_ts_kernel<256> + <128> tail launch (big hop: 32768 queries x 2048 keys, d_k 64, d_v 512; one "
-            "tdn_attention_tc call; P handed to the P.V' MMAs through tensor memory)",
+            "tc_attn_ts_kernel<256>, one launch: 444 items of 256 channels + 136 tail items of 128 channels (big hop: 32768 "
+            "queries x 2048 keys, d_k 64, d_v 512; P handed to the P.V' MMAs through tensor memory)",
             ATTN_GFLOP, ATTN_NECESSARY_GFLOP, ATTN_EXECUTED_GFLOP, attn_ms,
             sustained and sustained["attention_ms_per_launch"], ATTN_TRAFFIC_BYTES,
             "algorithmic = 2*Pq*P'*(d_k+d_v) = 77.31 GFLOP (SURVEY.md 8d); necessary = 3 x algorithmic (exact mode, one QK^T "
