@@ -617,6 +617,8 @@ def main():
     ap.add_argument("--no-fast-mode", action="store_true", help="skip the extra `fast_mode` key (N = 1, configs[1])")
     ap.add_argument("--config", type=int, default=1, choices=sorted(CONFIGS),
                     help="BASELINE.json configs index (default 1 = the configuration the metric is quoted on; 2 = 1 with --gpus 8)")
+    ap.add_argument("--streams", type=int, default=0,
+                    help="lock-step streams per GPU (batch); 0 = the configuration's own (4 for --config 4, else 1)")
     ap.add_argument("--sustain-seconds", type=float, default=5.0,
                     help="length of the back-to-back sustained loop (0 disables it)")
     args = ap.parse_args()
@@ -624,6 +626,9 @@ def main():
     c = CONFIGS[args.config]
     H, W, BATCH, ARCH, BACKBONE, PATHS, WORKLOAD, CONFIG_ID = (c["H"], c["W"], c["batch"], c["arch"], c["backbone"],
                                                                c["paths"], c["workload"], args.config)
+    if args.streams > 0 and args.streams != BATCH:
+        BATCH = args.streams
+        WORKLOAD += f" [--streams {BATCH}]"
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     if args.impl == "reference":
