@@ -43,8 +43,9 @@ def formats(lib):
         for out_fmt in ("f32", "split"):
             for res_fmt in ("split", "f32", "none"):
                 got = {}
-                for which in ("ss", "ts"):
-                    os.environ["TDNET_ATTN_TS"] = "1" if which == "ts" else "0"
+                fams = tuple(os.environ.get("ATTN_PROBE_FAMILIES", "ss,ts").split(","))
+                for which in fams:
+                    os.environ["TDNET_ATTN_TS"] = {"ss": "0", "ts2": "2"}.get(which, "1")
                     of = torch.full((n, pq, dv), float("nan"), device="cuda")
                     oh = torch.full((n, pq, dv), float("nan"), device="cuda", dtype=torch.half)
                     ol = torch.full((n, pq, dv), float("nan"), device="cuda", dtype=torch.half)
@@ -68,10 +69,11 @@ def formats(lib):
                     torch.cuda.synchronize()
                     got[which] = of if out_fmt == "f32" else oh.float() + ol.float()
                 ref = base + (r.double() if res_fmt != "none" else 0)
+                last = fams[-1]
                 print(json.dumps({"shape": [n, pq, pk, dv], "out": out_fmt, "res": res_fmt,
-                                  "max_diff_ts_vs_ss": float((got["ss"] - got["ts"]).abs().max()),
-                                  "nan_ts": int(torch.isnan(got["ts"]).sum()),
-                                  "max_abs_vs_fp64_ts": float((got["ts"].cpu().double() - ref).abs().max())}), flush=True)
+                                  "max_diff_ts_vs_ss": float((got["ss"] - got[last]).abs().max()),
+                                  "nan_ts": int(torch.isnan(got[last]).sum()),
+                                  "max_abs_vs_fp64_ts": float((got[last].cpu().double() - ref).abs().max())}), flush=True)
 
 
 def main():
@@ -93,13 +95,13 @@ def main():
         vt[:, :, :pk] = v.transpose(1, 2)
         pl = {name: split(t.cuda()) for name, t in (("q", q), ("k", k), ("vt", vt), ("r", r))}
         outs = {}
-        variants = ("ss", "ts")
+        variants = tuple(os.environ.get("ATTN_PROBE_FAMILIES", "ss,ts").split(","))
         if profile and os.environ.get("ATTN_PROBE_VARIANTS"):
             variants = tuple(os.environ["ATTN_PROBE_VARIANTS"].split(","))
         if sustain and "--debug" in sys.argv:
             variants = tuple(os.environ.get("ATTN_PROBE_VARIANTS", "ts,ts_dbg1,ts_dbg2,ts_dbg4,ts_dbg8,ts_dbg15").split(","))
         for which in variants:
-            os.environ["TDNET_ATTN_TS"] = "0" if which == "ss" else "1"
+            os.environ["TDNET_ATTN_TS"] = {"ss": "0", "ts2": "2"}.get(which.split("_")[0], "1")
             os.environ["TDNET_ATTN_DEBUG"] = which.split("dbg")[1] if "dbg" in which else "0"
             out = torch.full((n, pq, dv), float("nan"), device="cuda")
             d = _cabi.AttentionDesc()
@@ -170,6 +172,8 @@ def main():
                 res[f"max_abs_vs_fp64_{which}"] = float((out.cpu().double() - ref).abs().max())
         if "ss" in outs and "ts" in outs:
             res["max_diff_ts_vs_ss"] = float((outs["ss"][0] - outs["ts"][0]).abs().max())
+        if "ss" in outs and "ts2" in outs:
+            res["max_diff_ts2_vs_ss"] = float((outs["ss"][0] - outs["ts2"][0]).abs().max())
         print(json.dumps(res), flush=True)
         lines.append(json.dumps(res))
     if out_path:
