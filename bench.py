@@ -50,7 +50,7 @@ DOMINANT_GFLOP = 154.62        # layer4 3x3 512->512 dilated conv at 128x256 (SU
 ATTN_GFLOP = 77.31             # fused attention-propagation kernel, big hop: 2*32768*2048*(64+512)
 ATTN_NECESSARY_GFLOP = 3 * ATTN_GFLOP   # the fp32-faithful exact mode needs 3 fp16 products per algorithmic product
 ATTN_EXECUTED_GFLOP = 3 * (68.72 + 2 * 8.59) + 2 * 8.59   # + QK^T once per 256-channel slice + the single-product max pass
-ATTN_TRAFFIC_BYTES = 100.8e6       # ncu, dram read+write of the op's two launches (profiles/r01_prof_attn_split_summary.txt; the r02 TMEM-operand kernels move the same bytes)
+ATTN_TRAFFIC_BYTES = 107.3e6       # ncu --set full of the r02 TMEM-operand kernels, dram read+write: (70.3 + 22.1) + (14.8 + 0.0) MB (profiles/r02_prof_attn_ts_c_summary.txt)
 DOMINANT_TRAFFIC_BYTES = 107.5e6   # ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum (profiles/r01_*)
 N_DISTINCT_FRAMES = 8
 

@@ -626,17 +626,19 @@ __global__ void ln_partial_vec4_kernel(View x, double2* __restrict__ part, int c
   }
 }
 
-__global__ void __launch_bounds__(256) ln_final_kernel(const double2* __restrict__ part, int chunks, int C, int P,
-                                                       float eps, float* __restrict__ mean,
-                                                       float* __restrict__ rstd) {
-  // block = 32 channels x 8 chunk groups; fixed summation order -> bit-reproducible
-  __shared__ double ss[8][32], sq[8][32];
+constexpr int LN_FINAL_GROUPS = 32;   // chunk groups per block: the kernel is a chain of dependent loads per thread, so
+                                      // more (shorter) chains finish sooner; the order of the additions is fixed
+__global__ void __launch_bounds__(32 * LN_FINAL_GROUPS) ln_final_kernel(const double2* __restrict__ part, int chunks, int C,
+                                                                        int P, float eps, float* __restrict__ mean,
+                                                                        float* __restrict__ rstd) {
+  // block = 32 channels x LN_FINAL_GROUPS chunk groups; fixed summation order -> bit-reproducible
+  __shared__ double ss[LN_FINAL_GROUPS][32], sq[LN_FINAL_GROUPS][32];
   const int b = blockIdx.y;
   const int cl = threadIdx.x & 31, grp = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
   double s = 0.0, q = 0.0;
   if (c < C) {
-    for (int k = grp; k < chunks; k += 8) {
+    for (int k = grp; k < chunks; k += LN_FINAL_GROUPS) {
       double2 v = part[((long long)b * chunks + k) * C + c];
       s += v.x; q += v.y;
     }
@@ -645,7 +647,7 @@ __global__ void __launch_bounds__(256) ln_final_kernel(const double2* __restrict
   __syncthreads();
   if (grp == 0 && c < C) {
 #pragma unroll
-    for (int g = 1; g < 8; ++g) { s += ss[g][cl]; q += sq[g][cl]; }
+    for (int g = 1; g < LN_FINAL_GROUPS; ++g) { s += ss[g][cl]; q += sq[g][cl]; }
     double mu = s / P;
     double var = q / P - mu * mu;
     if (var < 0.0) var = 0.0;
@@ -672,7 +674,7 @@ int layernorm_hw_stats(const tdn_tensor* x, float* mean, float* rstd, float eps,
     ln_partial_kernel<<<dim3(chunks, x->n), threads, 0, stream>>>(make_view(*x), (double2*)workspace, chunks);
   }
   TDN_LAUNCH_OK();
-  ln_final_kernel<<<dim3(ceil_div(x->c, 32), x->n), 256, 0, stream>>>((const double2*)workspace, chunks, x->c, P,
+  ln_final_kernel<<<dim3(ceil_div(x->c, 32), x->n), 32 * LN_FINAL_GROUPS, 0, stream>>>((const double2*)workspace, chunks, x->c, P,
                                                                      eps, mean, rstd);
   TDN_LAUNCH_OK();
   return TDN_OK;
