@@ -567,7 +567,11 @@ int attention_tc(const tdn_attention_desc* d, cudaStream_t stream, int* count_on
   auto launch = [&](int dvt, int grid, const AttnParams& pp) -> cudaError_t {
     if (count_only) { ++*count_only; return cudaSuccess; }
     const bool short_launch = pp.num_items <= 2 * grid;
-    if (use_ts) return attention_ts_launch(dvt, grid, stream, short_launch, mq_h, mq_l, mk_h, mk_l, mv_h, mv_l, pp);
+    if (use_ts) {
+      AttnParams q = pp;
+      q.per_cta = ceil_div(q.items_a, grid);     // contiguous blocks: the d_v slices of a query tile meet on one CTA
+      return attention_ts_launch(dvt, grid, stream, short_launch, mq_h, mq_l, mk_h, mk_l, mv_h, mv_l, q);
+    }
     if (dvt == 256)
       return tc_launch(tc_attn_kernel<256>, grid, AT_THREADS, AT_SMEM_BYTES, stream, short_launch, mq_h, mq_l, mk_h, mk_l, mv_h, mv_l, pp);
     return tc_launch(tc_attn_kernel<128>, grid, AT_THREADS, AT_SMEM_BYTES, stream, short_launch, mq_h, mq_l, mk_h, mk_l, mv_h, mv_l, pp);

@@ -44,6 +44,10 @@ struct AttnParams {
   // launch): items [0, items_a) are decoded with (dv_tiles, qt_begin, q_tiles) and are DVT wide, items
   // [items_a, num_items) with (dv_tiles_b, qt_begin_b, q_tiles_b) and are 128 wide.  items_a == num_items: no tail.
   int items_a, dv_tiles_b, qt_begin_b, q_tiles_b;
+  // tc_attn_ts.cu: the items [0, items_a) are dealt out in contiguous blocks of per_cta items per CTA, so that consecutive
+  // items of a CTA are the d_v slices of the same query tile whenever possible and share its row maxima (pass 1 runs once
+  // per query tile and CTA instead of once per item); tail items go one per CTA and round.  0: strided walk (tc_attn.cu).
+  int per_cta;
   float scale_log2;         // log2(e) / sqrt(d_k)
   __half* out_hi;
   __half* out_lo;
@@ -78,6 +82,21 @@ __device__ __forceinline__ AttnItem attn_item(const AttnParams& p, int item) {
     it.halves = 1;
   }
   return it;
+}
+
+// k-th work item of this CTA in the blocked walk described at AttnParams::per_cta (-1: no more items).
+__device__ __forceinline__ int attn_walk(const AttnParams& p, int k) {
+  const int c = (int)blockIdx.x, G = (int)gridDim.x;
+  const int base = c * p.per_cta;
+  int n_main = p.items_a - base;
+  n_main = n_main < 0 ? 0 : (n_main > p.per_cta ? p.per_cta : n_main);
+  if (k < n_main) return base + k;
+  const int t = p.items_a + c + (k - n_main) * G;
+  return t < p.num_items ? t : -1;
+}
+// Item `item` may reuse the row maxima of the item this CTA processed just before it: same image and query tile.
+__device__ __forceinline__ bool attn_shares_rowmax(const AttnParams& p, int item, int prev) {
+  return prev >= 0 && item < p.items_a && prev < p.items_a && item / p.dv_tiles == prev / p.dv_tiles;
 }
 
 // tc_attn_ts.cu: launch of the TMEM-operand kernel family (dvt = 128 or 256 output channels per work item).

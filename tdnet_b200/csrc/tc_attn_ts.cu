@@ -119,7 +119,7 @@ tc_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_const
     if (lane == 0) {
       int ks = 0;
       uint32_t kph = 0, qph = 0;
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      for (int k = 0, item, prev = -1; (item = attn_walk(p, k)) >= 0; prev = item, ++k) {
         const AttnItem w = attn_item<DVT>(p, item);
         const int qt = w.qt, img = w.img;
         mbar_wait(&bars->q_empty, qph ^ 1);
@@ -127,9 +127,11 @@ tc_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_const
         tma_load_3d(sQ, &tmQ_hi, &bars->q_full, 0, qt * AT_BQ, img);
         tma_load_3d(sQ + AT_Q_PLANE, &tmQ_lo, &bars->q_full, 0, qt * AT_BQ, img);
         qph ^= 1;
-        // pass 1: the hi plane of the keys only (S~ = Qhi.Khi^T), 128 keys per stage: two 64-key boxes land
-        // back to back = one 128-row swizzled tile (a box past the last key is zero-filled)
-        for (int kt = 0; kt < T1; ++kt) {
+        // pass 1 (skipped when this CTA has just computed the row maxima of the same query tile): the hi plane of the
+        // keys only (S~ = Qhi.Khi^T), 128 keys per stage: two 64-key boxes land back to back = one 128-row swizzled tile
+        // (a box past the last key is zero-filled)
+        const int t1 = attn_shares_rowmax(p, item, prev) ? 0 : T1;
+        for (int kt = 0; kt < t1; ++kt) {
           mbar_wait(&bars->k_empty[ks], kph ^ 1);
           uint8_t* dst = sK + ks * 2 * AT_K_PLANE;
           mbar_expect_tx(&bars->k_full[ks], 2 * AT_K_PLANE);
@@ -153,7 +155,7 @@ tc_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_const
     if (lane == 0) {
       int vs = 0;
       uint32_t vph = 0;
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      for (int k = 0, item; (item = attn_walk(p, k)) >= 0; ++k) {
         const AttnItem w = attn_item<DVT>(p, item);
         const int img = w.img;
         for (int kt = 0; kt < T; ++kt) {
@@ -180,11 +182,14 @@ tc_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_const
     uint32_t n2 = 0;      // pass-2 tiles issued so far: buffer n2 & 3, use n2 >> 2
     uint32_t items_done = 0;
     const uint32_t q_hi = smem_u32(sQ), q_lo = q_hi + AT_Q_PLANE;
-    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++items_done) {
+    for (int k = 0, item, prev = -1; (item = attn_walk(p, k)) >= 0; prev = item, ++k, ++items_done) {
+      const bool reuse = attn_shares_rowmax(p, item, prev);   // the row maxima of this query tile are known already
       mbar_wait(&bars->q_full, qph);
-      // the S/P buffers still hold probabilities of the previous item until its last P.V' MMA has retired
-      if (items_done > 0) mbar_wait(&bars->o_full, (items_done - 1) & 1);
-      for (int it = 0; it < T1; ++it, ++n1) {
+      // pass 1 writes whole S/P buffer pairs, which still hold probabilities of the previous item until its last P.V'
+      // MMA has retired; with the row maxima reused there is no pass 1 and the per-buffer sp_empty waits of pass 2 suffice
+      const int t1 = reuse ? 0 : T1;
+      if (!reuse && items_done > 0) mbar_wait(&bars->o_full, (items_done - 1) & 1);
+      for (int it = 0; it < t1; ++it, ++n1) {
         const int pair = n1 & 1;
         mbar_wait(&bars->k_full[ks], kph);
         mbar_wait(&bars->s1_empty[pair], ((n1 >> 1) & 1) ^ 1);
@@ -202,7 +207,7 @@ tc_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_const
         if (++ks == ATS_KSTAGES) { ks = 0; kph ^= 1; }
       }
       // pass 2 overwrites the pass-1 tiles: the softmax warps must have read the last two of them
-      for (uint32_t j = 1; j <= 2 && j <= (uint32_t)T1; ++j) {
+      for (uint32_t j = 1; j <= 2 && j <= (uint32_t)t1; ++j) {
         const uint32_t t = n1 - j;
         mbar_wait(&bars->s1_empty[t & 1], (t >> 1) & 1);
       }
@@ -241,7 +246,7 @@ tc_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_const
     int vs = 0;
     uint32_t vph = 0, oph = 0;
     uint32_t n2 = 0;
-    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+    for (int k = 0, item; (item = attn_walk(p, k)) >= 0; ++k) {
       const int halves = attn_item<DVT>(p, item).halves;
       mbar_wait(&bars->o_empty, oph ^ 1);                        // epilogue of the previous item has read O
       for (int kt = 0; kt < T; ++kt, ++n2) {
@@ -289,9 +294,12 @@ tc_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_const
     uint32_t n1 = 0, n2 = 0;                                  // same counting as MMA issuer 1
     uint32_t items_done = 0;
     auto group_sync = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };
-    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++items_done) {
+    float m = -INFINITY;                                      // row maximum; survives to the next item of the same query tile
+    for (int k = 0, item, prev = -1; (item = attn_walk(p, k)) >= 0; prev = item, ++k, ++items_done) {
       // ---- pass 1: row maximum of S~; 128-key tiles, this group's 64 key columns of each
-      float m = -INFINITY;
+      const bool reuse = attn_shares_rowmax(p, item, prev);
+      if (!reuse) {
+      m = -INFINITY;
       for (int kt = 0; kt < T1; ++kt, ++n1) {
         const int pair = n1 & 1;
         mbar_wait(&bars->s1_full[pair], (n1 >> 1) & 1);
@@ -326,6 +334,9 @@ tc_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_const
       group_sync();
       m = fmaxf(m, bars->xch[group ^ 1][row]);
       group_sync();                                           // xch carries the row sums next
+      } else {
+        mbar_wait(&bars->l_empty, (items_done & 1) ^ 1);       // (the row sums below reuse xch)
+      }
       // exponent offset of pass 2: the row maximum AND log2 of the 2^10 probability scale, so that one FMA + one
       // MUFU.EX2 yield p * 2^10 directly (the row sum l is then scaled by 2^10 as well: out = O / l)
       const float m_scaled = m * p.scale_log2 - 10.f;
@@ -384,7 +395,7 @@ tc_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_const
     const int fmt = attn_epilogue_fmt(p);
     uint32_t iph = 0;
     bool out_of_range = false;
-    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+    for (int k = 0, item; (item = attn_walk(p, k)) >= 0; ++k) {
       const AttnItem w = attn_item<DVT>(p, item);
       const int q0 = w.qt * AT_BQ + quarter * 32;              // first query row of this warp
       const int NCHUNK = w.halves * (AT_DVH / 32);
