@@ -30,7 +30,7 @@ MAX_MISMATCH_PER_FRAME = 8
 
 def run_script(package, ckpt, out_dir, model="td4-psp18"):
     os.makedirs(out_dir, exist_ok=True)
-    key = {"td4-psp18": "--_td4_psp18_path", "td2-psp50": "--_td2_psp50_path"}[model]
+    key = {"td4-psp18": "--_td4_psp18_path", "td2-psp50": "--_td2_psp50_path", "psp101": "--_psp101_path"}[model]
     cmd = [sys.executable, os.path.join(ROOT, "oracle", "run_reference_script.py"), "--package", package, "--",
            "--model", model, "--output_path", out_dir + os.sep, key, ckpt]
     env = dict(os.environ)
@@ -46,11 +46,17 @@ def run_script(package, ckpt, out_dir, model="td4-psp18"):
 
 @pytest.mark.skipif(not (os.path.isfile(os.path.join(REF, "test.py")) and os.path.isdir(os.path.join(REF, "data", "vid1"))),
                     reason="oracle/_ref/Testing absent (python oracle/make_ref.py needs /root/reference)")
-@pytest.mark.parametrize("model,arch,backbone", [("td4-psp18", "td4_psp18", "resnet18")])
+@pytest.mark.parametrize("model,arch,backbone", [("td4-psp18", "td4_psp18", "resnet18"), ("td2-psp50", "td2_psp50", "resnet50"),
+                                                 ("psp101", "pspnet", "resnet101")])
 def test_unmodified_reference_script_on_dropin_matches_reference_package(tmp_path, model, arch, backbone):
+    """All three `--model` choices of Testing/test.py:21-38 (td4-psp18, td2-psp50, psp101)."""
     import cv2
     ckpt = str(tmp_path / "ckpt.pkl")
-    torch.save(make_weights(arch, backbone, 97, 193), ckpt)       # LayerNorm([97,193]) as the reference constructs it
+    if arch == "pspnet":
+        from common import make_pspnet_oracle
+        torch.save(make_pspnet_oracle(backbone)[1], ckpt)
+    else:
+        torch.save(make_weights(arch, backbone, 97, 193), ckpt)   # LayerNorm([97,193]) as the reference constructs it
     lat_ref, frames_ref = run_script("reference", ckpt, str(tmp_path / "reference"), model)
     lat_ours, frames_ours = run_script("dropin", ckpt, str(tmp_path / "dropin"), model)
     names = sorted(os.listdir(tmp_path / "reference" / "vid1"))
@@ -67,8 +73,8 @@ def test_unmodified_reference_script_on_dropin_matches_reference_package(tmp_pat
            "per_frame_s_dropin": frames_ours, "per_frame_s_reference": frames_ref}
     try:
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-        with open(os.path.join(ROOT, "gpurun_out", "reference_script_run.json"), "w") as f:
-            json.dump(rec, f)
+        with open(os.path.join(ROOT, "gpurun_out", "reference_script_run.jsonl"), "a") as f:
+            f.write(json.dumps(rec) + "\n")
     except OSError:
         pass
     print(rec)
