@@ -452,7 +452,15 @@ class Engine:
                 outs.append(x)
         return outs + [x]
 
-    def _build(self, path: int, steady: bool) -> FramePlan:
+    def backbone_plan(self, path: int) -> FramePlan:
+        """Only the sub-network of `path` (stem + residual stages, resnet.py:204-215): image -> c4.  What
+        `model.pretrainedK(img)` runs (the reference's sub-network plugin surface, td4_psp18.py:70-77)."""
+        key = ("backbone", path)
+        if key not in self._plans:
+            self._plans[key] = self._build(path, False, backbone_only=True)
+        return self._plans[key]
+
+    def _build(self, path: int, steady: bool, backbone_only: bool = False) -> FramePlan:
         if self.m.arch == "td2_fa":
             return self._build_fanet(path)
         m, n, lib = self.m, self.n, self.lib
@@ -501,7 +509,7 @@ class Engine:
         # --- attention prelude on the side stream: the FIFO hops and the fc of the last hop depend only on the
         #     FIFO (td4_psp18.py:145-146), so they overlap the backbone instead of serialising behind it
         pre = None
-        if steady and m.depth > 0 and self.tc and self.fused_attn and self.side_stream is not None:
+        if steady and m.depth > 0 and self.tc and self.fused_attn and self.side_stream is not None and not backbone_only:
             plan.mark("fork")
             plan.side = True
             pre = self._attention_chain_tc(plan, path, None, None, stage="prelude")
@@ -511,6 +519,9 @@ class Engine:
         x = self._residual_blocks(plan, m.stages[path], x)[-1]
         c4 = x
         assert (c4.h, c4.w, c4.c) == (h8, w8, m.c4), (c4.h, c4.w, c4.c)
+        if backbone_only:
+            plan.taps = dict(c4=c4)
+            return plan
         if m.arch == "pspnet":
             return self._build_pspnet_tail(plan, c4)
 

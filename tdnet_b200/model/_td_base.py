@@ -22,7 +22,14 @@ class _Group(nn.Module):
     td2_fa.pretrained_init, or `model.pretrained1.load_state_dict(...)`) invalidates the packed device weights of the
     model it belongs to."""
 
-    def forward(self, *a, **k):  # pragma: no cover
+    def forward(self, *a, **k):
+        # The sub-networks are callable like the reference's (`model.pretrained1(img)` -> c4, td4_psp18.py:70-77,
+        # resnet.py:204-215); every other group is a pure parameter container.
+        root = getattr(self, "_td_root", None)
+        root = root() if root is not None else None
+        name = getattr(self, "_td_name", "")
+        if root is not None and name.startswith("pretrained") and len(a) == 1 and not k:
+            return root._subnetwork(name, a[0])
         raise RuntimeError("parameter container; the computation runs in the CUDA engine")
 
     def _load_from_state_dict(self, *a, **k):
@@ -41,6 +48,7 @@ def _attach(root: nn.Module, key: str, shape, kind: str):
         if not hasattr(mod, p):
             g = _Group()
             object.__setattr__(g, "_td_root", weakref.ref(root))     # plain attribute: not a sub-module, no cycle
+            object.__setattr__(g, "_td_name", p if mod is root else "")
             mod.add_module(p, g)
         mod = getattr(mod, p)
     if kind == "param":
@@ -216,6 +224,30 @@ class TDModel(nn.Module):
 
     _RANGE_MSG = ("tdnet_b200: an activation exceeded the SPLIT16 range (|x| > 6e4) in an earlier frame, its logits "
                   "are invalid; use engine_mode='simt' (fp32 planes) for this checkpoint")
+
+    @torch.no_grad()
+    def _subnetwork(self, name, img):
+        """`model.pretrainedK(img)` of the reference (the sub-network of path K: dilated ResNet, image -> c4 feature map
+        [n, C4, H/8, W/8], resnet.py:204-215) on the engine's kernels.  Does not touch the FIFO."""
+        k = int(name[len("pretrained"):] or 1)
+        if not img.is_cuda:
+            raise RuntimeError("tdnet_b200 runs on a CUDA (sm_100) device only; there is no CPU path. "
+                               "Move the model and the input with .to('cuda').")
+        if img.dtype != torch.float32 or img.dim() != 4 or img.shape[1] != 3:
+            raise RuntimeError("expected an fp32 NCHW image batch [n,3,H,W] (Testing/dataloader.py:69-71)")
+        img = img.contiguous()
+        n, _, h, w = img.shape
+        with torch.cuda.device(img.device):
+            queues = (self.Q_queue, self.K_queue, self.V_queue)
+            eng = self._engine(img, (n, 3, h, w))
+            if getattr(self, "_active_key", None) is not None:
+                self.Q_queue, self.K_queue, self.V_queue = queues      # a sub-network call is not a clip boundary
+            plan = eng.backbone_plan(k)
+            eng.run(plan, img.data_ptr(), 0, torch.cuda.current_stream(img.device).cuda_stream)
+            out = plan.taps["c4"].torch().permute(0, 3, 1, 2).contiguous()
+            if eng.tc:
+                self._poll_range_flag(eng)
+        return out
 
     def time_attention_op(self, frames, step, reps=8):
         """Average device time (ms) of the fused attention-propagation kernel of the big hop (the last hop of

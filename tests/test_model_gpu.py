@@ -475,3 +475,20 @@ def test_fast_mode_is_opt_in_close_and_not_exact():
     record("fast_mode/td4_128x256", max_abs_fast=worst_fast, max_abs_exact=worst_exact, argmax_agreement_fast=min(agree))
     assert worst_exact <= LOGIT_TOL
     assert LOGIT_TOL < worst_fast < 0.25 and min(agree) > 0.97
+
+
+def test_subnetworks_are_callable_like_the_reference():
+    """`model.pretrainedK(img)` (the sub-network plugin surface, td4_psp18.py:70-77 / resnet.py:204-215) returns the c4
+    feature map of path K, computed by the same kernels as forward(): equal to forward's own c4 tap (which the golden
+    tests pin on the reference) and without touching the FIFO."""
+    sd = make_weights("td4_psp18", "resnet18", 8, 12)
+    net = build_model("td4_psp18", "resnet18", 8, 12, sd)
+    frames = [f.cuda() for f in synth_clip(5, 64, 96, clip_id=8)]
+    for i, f in enumerate(frames):
+        net(f, pos_id=i % 4)
+        want = tap(net._last[1].taps["c4"])
+        fifo = len(net.Q_queue)
+        got = getattr(net, f"pretrained{i % 4 + 1}")(f)
+        assert got.shape == (1, 512, 8, 12) and torch.equal(got.cpu(), want) and len(net.Q_queue) == fifo
+    with pytest.raises(RuntimeError, match="parameter container"):
+        net.head1(frames[0])
