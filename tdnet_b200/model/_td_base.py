@@ -110,7 +110,8 @@ class TDModel(nn.Module):
         _default_init_(self)
         self._engines: Dict[tuple, object] = {}
         self.pretrained_mp_load()
-        self.Q_queue, self.K_queue, self.V_queue = [], [], []
+        self._fifo_fill = 0            # frames in the FIFO (the tensors live in the engine's device slots)
+        self._fifo_manual = None       # lists handed in through buffer_contral() / assignment (reference API)
         # 'tc': tcgen05 exact-mode kernels (product path on B200); 'simt': fp32 CUDA-core kernels only;
         # 'tc_fast': opt-in single-product tensor-core mode (NOT fp32-faithful, never the parity gate).
         self.engine_mode = os.environ.get("TDNET_B200_ENGINE", "tc")
@@ -165,14 +166,45 @@ class TDModel(nn.Module):
 
     def reset(self):
         """Start a new clip (the reference needs a new model instance for that)."""
-        self.Q_queue, self.K_queue, self.V_queue = [], [], []
+        self._fifo_fill = 0
+        self._fifo_manual = None
+
+    # The observable FIFO of the reference (`Q_queue / K_queue / V_queue`, td4_psp18.py:118-134).  The entries live in the
+    # engine's device slots (SPLIT16 planes); the lists are materialised ON ACCESS as new fp32 tensors [n, P', d] -- oldest
+    # first, like the reference's -- so a caller holding them is not affected by later frames, and the frame loop itself
+    # launches nothing for them.
+    def _fifo_list(self, which):
+        if self._fifo_manual is not None:
+            return self._fifo_manual[which]
+        eng = self._engines.get(getattr(self, "_active_key", None))
+        if eng is None or self._fifo_fill == 0:
+            return []
+        depth, fill = self.arch.depth, self._fifo_fill
+        slots = (eng.q_slots, eng.k_slots, eng.v_slots)[which]
+        d = self.arch.d_v if which == 2 else self.arch.d_k
+        return [slots[depth - fill + j].torch().reshape(eng.n, -1, d).clone() for j in range(fill)]
+
+    def _fifo_assign(self, which, value):
+        if self._fifo_manual is None:
+            self._fifo_manual = [self._fifo_list(0), self._fifo_list(1), self._fifo_list(2)]
+        self._fifo_manual[which] = list(value)
+        if not any(self._fifo_manual):
+            self._fifo_manual, self._fifo_fill = None, 0
+
+    Q_queue = property(lambda self: self._fifo_list(0), lambda self, v: self._fifo_assign(0, v))
+    K_queue = property(lambda self: self._fifo_list(1), lambda self, v: self._fifo_assign(1, v))
+    V_queue = property(lambda self: self._fifo_list(2), lambda self, v: self._fifo_assign(2, v))
 
     def buffer_contral(self, q, k, v):
-        assert len(self.Q_queue) == len(self.V_queue)
-        assert len(self.Q_queue) == len(self.K_queue)
-        self.Q_queue.append(q), self.V_queue.append(v), self.K_queue.append(k)
-        if len(self.Q_queue) > self.arch.depth:
-            self.Q_queue.pop(0), self.V_queue.pop(0), self.K_queue.pop(0)
+        """td4_psp18.py:123-134, kept for API parity: appends to the observable lists.  The engine pushes its own
+        FIFO inside forward(); lists edited by hand are only reported back, they do not feed the kernels."""
+        qs, ks, vs = self.Q_queue, self.K_queue, self.V_queue
+        assert len(qs) == len(vs)
+        assert len(qs) == len(ks)
+        qs.append(q), vs.append(v), ks.append(k)
+        if len(qs) > self.arch.depth:
+            qs.pop(0), vs.pop(0), ks.pop(0)
+        self._fifo_manual = [qs, ks, vs]
 
     # ---- engine ----------------------------------------------------------------------------
     def _engine(self, img: torch.Tensor, shape):
@@ -238,10 +270,10 @@ class TDModel(nn.Module):
         img = img.contiguous()
         n, _, h, w = img.shape
         with torch.cuda.device(img.device):
-            queues = (self.Q_queue, self.K_queue, self.V_queue)
+            fill, key = self._fifo_fill, getattr(self, "_active_key", None)
             eng = self._engine(img, (n, 3, h, w))
-            if getattr(self, "_active_key", None) is not None:
-                self.Q_queue, self.K_queue, self.V_queue = queues      # a sub-network call is not a clip boundary
+            if key is not None and key == self._active_key:
+                self._fifo_fill = fill                                 # a sub-network call is not a clip boundary
             plan = eng.backbone_plan(k)
             eng.run(plan, img.data_ptr(), 0, torch.cuda.current_stream(img.device).cuda_stream)
             out = plan.taps["c4"].torch().permute(0, 3, 1, 2).contiguous()
@@ -349,7 +381,7 @@ class TDModel(nn.Module):
 
     def _forward_on_device(self, img, pos_id, n, h, w, _probe, _labels, _u8, _preview):
         eng = self._engine(img, (n, 3, h, w))
-        steady = len(self.Q_queue) >= self.arch.depth
+        steady = self._fifo_fill >= self.arch.depth
         plan = eng.plan(pos_id + 1, steady)
         last_op = None
         if _preview is not None:
@@ -366,13 +398,10 @@ class TDModel(nn.Module):
         else:
             eng.run(plan, img.data_ptr(), out.data_ptr(), torch.cuda.current_stream(img.device).cuda_stream, _probe,
                     labels=_labels, u8=_u8, last_op=last_op)
-        # FIFO bookkeeping mirrors buffer_contral; the tensors are views of the engine's device slots
-        # (slot j = j-th oldest frame once the FIFO is full).
-        depth = self.arch.depth
-        fill = min(len(self.Q_queue) + 1, depth)
-        self.Q_queue = [eng.q_slots[depth - fill + j].torch().view(n, -1, self.arch.d_k) for j in range(fill)]
-        self.K_queue = [eng.k_slots[depth - fill + j].torch().view(n, -1, self.arch.d_k) for j in range(fill)]
-        self.V_queue = [eng.v_slots[depth - fill + j].torch().view(n, -1, self.arch.d_v) for j in range(fill)]
+        # FIFO bookkeeping mirrors buffer_contral (slot j = j-th oldest frame once the FIFO is full); the observable
+        # lists are materialised on access (Q_queue / K_queue / V_queue properties), not here in the frame loop
+        self._fifo_fill = min(self._fifo_fill + 1, self.arch.depth)
+        self._fifo_manual = None
         self._last = (eng, plan)
         if eng.tc:
             self._poll_range_flag(eng)

@@ -42,7 +42,7 @@ class td2_fa(TDModel):  # noqa: N801
             _attach(self, key, shape, kind)
         _default_init_(self)
         self._engines = {}
-        self.Q_queue, self.K_queue, self.V_queue = [], [], []   # no FIFO in this model; kept empty for the shared base
+        self._fifo_fill, self._fifo_manual = 0, None             # no FIFO in this model; the shared base reports empty lists
         self.engine_mode = os.environ.get("TDNET_B200_ENGINE", "tc")
         self.use_cuda_graph = os.environ.get("TDNET_B200_CUDA_GRAPH", "1") != "0"
         self._range_host = None
