@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(256) fa_apply_kernel(View query, const float* 
     out_of_range |= fmaxf(fmaxf(fabsf(acc[i][0]), fabsf(acc[i][1])), fmaxf(fabsf(acc[i][2]), fabsf(acc[i][3]))) > 60000.f;
     st4(out, b * out.sn + y * out.sh + x * out.sw + c, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
   }
-  if (out_of_range && out.split && range_flag) atomicOr(range_flag, 1);
+  if (out_of_range && out.split && range_flag) *reinterpret_cast<volatile int*>(range_flag) = 1;
 }
 
 int fa_apply(const tdn_tensor* query, const float* f, const tdn_tensor* out, float out_scale, int* range_flag,

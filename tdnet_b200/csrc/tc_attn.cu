@@ -447,7 +447,7 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->o_empty);
     }
-    if (out_of_range && p.range_flag) atomicOr(p.range_flag, 1);
+    if (out_of_range && p.range_flag) *reinterpret_cast<volatile int*>(p.range_flag) = 1;   // idempotent store: the flag may live in host-mapped memory
   }
 
   tc_fence_before();

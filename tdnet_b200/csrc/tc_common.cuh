@@ -247,7 +247,7 @@ __device__ __forceinline__ void tc_epilogue_role(const TcParams& p, uint32_t tme
         }
       }
     }
-    if (out_of_range && p.range_flag) atomicOr(p.range_flag, 1);
+    if (out_of_range && p.range_flag) *reinterpret_cast<volatile int*>(p.range_flag) = 1;   // idempotent store: the flag may live in host-mapped memory
 }
 
 }  // namespace tdn

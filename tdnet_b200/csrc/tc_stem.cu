@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_stem_kernel(const TcStemPara
       fence_proxy_async_smem();
       mbar_arrive(&img_full[slot]);
     }
-    if (out_of_range && p.range_flag) atomicOr(p.range_flag, 1);
+    if (out_of_range && p.range_flag) *reinterpret_cast<volatile int*>(p.range_flag) = 1;   // idempotent store: the flag may live in host-mapped memory
   } else {
     // ======================= pool: 3x3 stride-2 max over three conv rows =======================
     const int tp = tid - TS_POOL_WARP0 * 32;

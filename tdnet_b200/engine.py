@@ -265,7 +265,11 @@ class Engine:
         self.q_slots = [View.alloc(n, 1, self.pk, m.d_k, dev, zero=True, split=self.tc) for _ in range(m.depth)]
         self.k_slots = [View.alloc(n, 1, self.pk, m.d_k, dev, zero=True, split=self.tc) for _ in range(m.depth)]
         self.v_slots = [View.alloc(n, 1, self.pk, m.d_v, dev, zero=True, split=self.tc) for _ in range(m.depth)]
-        self.range_flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        # SPLIT16 range guard: one int the kernels set to 1 (plain store) when an output exceeds the fp16 range.  It lives in
+        # pinned, device-mapped HOST memory, so the host examines it without any copy or synchronisation in the frame loop.
+        self.range_flag = torch.zeros(1, dtype=torch.int32)
+        if dev.type == "cuda":
+            self.range_flag = self.range_flag.pin_memory()
         self._consts: Dict[tuple, torch.Tensor] = {}
         ln_paths = range(1, m.paths + 1) if m.arch != "pspnet" else ()
         self.ln_gamma = {p: state_dict[f"layer_norm{p}.ln.weight"].detach().float().reshape(-1).contiguous().to(dev)

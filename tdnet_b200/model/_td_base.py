@@ -119,9 +119,8 @@ class TDModel(nn.Module):
         # built, run once on a scratch frame and captured when the engine is created (first forward of a new input
         # shape, or prepare()), never inside a later frame.
         self.use_cuda_graph = os.environ.get("TDNET_B200_CUDA_GRAPH", "1") != "0"
-        # SPLIT16 range guard (|x| > 6e4 overflows an fp16 plane): the device flag is copied to pinned host memory
-        # after every frame without blocking and examined at the next call.
-        self._range_host = None
+        # SPLIT16 range guard (|x| > 6e4 overflows an fp16 plane): the kernels raise a flag in host-mapped pinned memory
+        # that forward() examines after every frame without a copy or a synchronisation (_poll_range_flag).
 
     # ---- reference API ---------------------------------------------------------------------
     def pretrained_mp_load(self):
@@ -137,7 +136,6 @@ class TDModel(nn.Module):
         the next forward.  Called automatically by load_state_dict() (of the model or any sub-module), .to() / .half() /
         .float(), set_ln_shape(); call it yourself after editing parameters in place (`p.data.copy_(...)`)."""
         self._engines.clear()
-        self._range_host = None
 
     def _apply(self, fn, *a, **k):
         out = super()._apply(fn, *a, **k)
@@ -218,7 +216,6 @@ class TDModel(nn.Module):
             while len(self._engines) >= self.MAX_ENGINES:          # small LRU: alternating two input shapes does not
                 self._engines.pop(next(iter(self._engines)))       # re-pack every weight on each switch
             self._engines[key] = eng
-            self._range_host = None
             if self.use_cuda_graph:
                 eng.prepare_graphs()
             self.reset()       # a different input shape starts a new clip: the FIFO lives in the engine
@@ -243,16 +240,13 @@ class TDModel(nn.Module):
         return self
 
     def _poll_range_flag(self, eng):
-        """Non-blocking range guard: raise if the flag copied after an EARLIER frame was set, then queue the copy of
-        the current flag behind this frame.  An overflow is therefore reported at most one call late (or at once by
-        check_numeric_range()); it is never silent."""
-        if self._range_host is None:
-            self._range_host = torch.zeros(1, dtype=torch.int32).pin_memory()
-        elif int(self._range_host[0]) != 0:
-            self._range_host.zero_()
+        """Non-blocking range guard: the kernels set eng.range_flag (pinned, device-mapped host memory) when a SPLIT16
+        output overflows; the host looks at it after every frame without a copy or a synchronisation, so an overflow
+        raises as soon as a frame that saw it has finished -- at the latest on the call after -- never silently."""
+        if int(eng.range_flag[0]) != 0:
+            torch.cuda.synchronize(eng.device)     # let the offending frame finish before the flag is re-armed
             eng.range_flag.zero_()
             raise RuntimeError(self._RANGE_MSG)
-        self._range_host.copy_(eng.range_flag, non_blocking=True)
 
     _RANGE_MSG = ("tdnet_b200: an activation exceeded the SPLIT16 range (|x| > 6e4) in an earlier frame, its logits "
                   "are invalid; use engine_mode='simt' (fp32 planes) for this checkpoint")
@@ -352,10 +346,9 @@ class TDModel(nn.Module):
         """Raise if any SPLIT16 activation ever exceeded the fp16 range guard (|x| > 6e4) since the
         engine was created.  Synchronises; meant for validation runs, not the frame loop."""
         for eng in self._engines.values():
-            if int(eng.range_flag.item()) != 0:
+            torch.cuda.synchronize(eng.device)
+            if int(eng.range_flag[0]) != 0:
                 eng.range_flag.zero_()
-                if self._range_host is not None:
-                    self._range_host.zero_()
                 raise RuntimeError(self._RANGE_MSG)
 
     @torch.no_grad()

@@ -45,7 +45,6 @@ class td2_fa(TDModel):  # noqa: N801
         self._fifo_fill, self._fifo_manual = 0, None             # no FIFO in this model; the shared base reports empty lists
         self.engine_mode = os.environ.get("TDNET_B200_ENGINE", "tc")
         self.use_cuda_graph = os.environ.get("TDNET_B200_CUDA_GRAPH", "1") != "0"
-        self._range_host = None
         self.pretrained_init()
 
     def pretrained_init(self):
