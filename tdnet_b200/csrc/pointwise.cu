@@ -95,77 +95,59 @@ int maxpool3x3s2(const tdn_tensor* in, const tdn_tensor* out, cudaStream_t strea
 __device__ __forceinline__ int bin_start(int i, int o, int len) { return (i * len) / o; }
 __device__ __forceinline__ int bin_end(int i, int o, int len) { return ((i + 1) * len + o - 1) / o; }
 
-constexpr int PSP_PARTS = 1;   // x-segments per row in the WORKSPACE (tdn_psp_pool_workspace_bytes assumes 1)
-constexpr int PSP_SEGS = 4;    // x-segments per row inside a block: the pass is latency-bound (one serial walk per
-                               // thread), so four walks per channel run side by side and their partial range sums are
-                               // combined through shared memory in segment order (fixed order: bit-reproducible)
+constexpr int PSP_PARTS = 1;   // x-segments per row (tdn_psp_pool_workspace_bytes assumes 1); splitting rows into 4 was
+                               // measured slower: it only adds pass-2 reads, the pass is not occupancy-bound
 
-__global__ void __launch_bounds__(128 * PSP_SEGS) psp_rowsum_kernel(View in, float* __restrict__ rowsum) {
+__global__ void psp_rowsum_kernel(View in, float* __restrict__ rowsum) {
   // One pass over a quarter of the row: every pyramid level keeps the running sum of its current column
   // range.  Adjacent ranges of a level overlap by at most one column (ceil vs floor), which seeds the next
   // sum.  Ranges cut by the segment boundary leave partial sums; untouched ranges stay zero.
-  __shared__ float part_sum[PSP_SEGS][12][128];
   const int y = blockIdx.x;
-  const int b = blockIdx.z;
-  const int ct = threadIdx.x & 127, part = threadIdx.x >> 7;
-  const int c = blockIdx.y * 128 + ct;
-  const bool live = c < in.c;
+  const int part = blockIdx.z % PSP_PARTS, b = blockIdx.z / PSP_PARTS;
+  const int c = blockIdx.y * blockDim.x + threadIdx.x;
+  if (c >= in.c) return;
   const long long row = b * in.sn + y * in.sh + c;
+  float* dst = rowsum + (((long long)(b * in.h + y) * PSP_PARTS + part) * 12) * in.c + c;
   const int W = in.w;
-  const int x_lo = (part * W) / PSP_SEGS, x_hi = ((part + 1) * W) / PSP_SEGS;
+  const int x_lo = (part * W) / PSP_PARTS, x_hi = ((part + 1) * W) / PSP_PARTS;
   const int lv_o[4] = {1, 2, 3, 6};
   const int lv_off[4] = {0, 1, 3, 6};
 #pragma unroll
-  for (int r = 0; r < 12; ++r) part_sum[part][r][ct] = 0.f;
-  if (live) {
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    int cur[4], nend[4];
+  for (int r = 0; r < 12; ++r) dst[(long long)r * in.c] = 0.f;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  int cur[4], nend[4];
 #pragma unroll
-    for (int l = 0; l < 4; ++l) {
-      int j = 0;
-      while (j < lv_o[l] && bin_end(j, lv_o[l], W) <= x_lo) ++j;   // first range that reaches into the segment
-      cur[l] = j;
-      nend[l] = bin_end(j, lv_o[l], W);
-      // a range that started in an earlier segment and overlaps the previous range's last column does not re-seed
-    }
-    constexpr int UN = 8;   // loads issued ahead of the (serial) range bookkeeping
-    for (int x0 = x_lo; x0 < x_hi; x0 += UN) {
-      float vbuf[UN];
+  for (int l = 0; l < 4; ++l) {
+    int j = 0;
+    while (j < lv_o[l] && bin_end(j, lv_o[l], W) <= x_lo) ++j;   // first range that reaches into the segment
+    cur[l] = j;
+    nend[l] = bin_end(j, lv_o[l], W);
+  }
+  constexpr int UN = 8;   // loads issued ahead of the (serial) range bookkeeping
+  for (int x0 = x_lo; x0 < x_hi; x0 += UN) {
+    float vbuf[UN];
 #pragma unroll
-      for (int u = 0; u < UN; ++u) vbuf[u] = (x0 + u < x_hi) ? ld1(in, row + (long long)(x0 + u) * in.sw) : 0.f;
+    for (int u = 0; u < UN; ++u) vbuf[u] = (x0 + u < x_hi) ? ld1(in, row + (long long)(x0 + u) * in.sw) : 0.f;
 #pragma unroll
-      for (int u = 0; u < UN; ++u) {
-        const int x = x0 + u;
-        if (x >= x_hi) break;
-        const float v = vbuf[u];
+    for (int u = 0; u < UN; ++u) {
+      const int x = x0 + u;
+      if (x >= x_hi) break;
+      const float v = vbuf[u];
 #pragma unroll
-        for (int l = 0; l < 4; ++l) {
-          acc[l] += v;
-          if (x + 1 == nend[l]) {
-            part_sum[part][lv_off[l] + cur[l]][ct] = acc[l];
-            ++cur[l];
-            nend[l] = bin_end(cur[l], lv_o[l], W);
-            acc[l] = (cur[l] < lv_o[l] && bin_start(cur[l], lv_o[l], W) <= x) ? v : 0.f;
-          }
+      for (int l = 0; l < 4; ++l) {
+        acc[l] += v;
+        if (x + 1 == nend[l]) {
+          dst[(long long)(lv_off[l] + cur[l]) * in.c] = acc[l];
+          ++cur[l];
+          nend[l] = bin_end(cur[l], lv_o[l], W);
+          acc[l] = (cur[l] < lv_o[l] && bin_start(cur[l], lv_o[l], W) <= x) ? v : 0.f;
         }
       }
     }
-#pragma unroll
-    for (int l = 0; l < 4; ++l)      // ranges still open at the segment end keep their partial sum
-      if (cur[l] < lv_o[l] && bin_start(cur[l], lv_o[l], W) < x_hi) part_sum[part][lv_off[l] + cur[l]][ct] = acc[l];
   }
-  __syncthreads();
-  // combine: 12 ranges x 128 channels by the 512 threads, segments added in index order
-  float* dst = rowsum + ((long long)(b * in.h + y) * 12) * in.c + blockIdx.y * 128;
-  for (int i = threadIdx.x; i < 12 * 128; i += 128 * PSP_SEGS) {
-    const int r = i >> 7, cc = i & 127;
-    if (blockIdx.y * 128 + cc < in.c) {
-      float sum = part_sum[0][r][cc];
 #pragma unroll
-      for (int sgm = 1; sgm < PSP_SEGS; ++sgm) sum += part_sum[sgm][r][cc];
-      dst[(long long)r * in.c + cc] = sum;
-    }
-  }
+  for (int l = 0; l < 4; ++l)      // ranges still open at the segment end keep their partial sum
+    if (cur[l] < lv_o[l] && bin_start(cur[l], lv_o[l], W) < x_hi) dst[(long long)(lv_off[l] + cur[l]) * in.c] = acc[l];
 }
 
 // Generic fallback (any width, re-reads the row once per level): used when the map is narrower than the
@@ -223,7 +205,8 @@ int psp_pool(const tdn_tensor* in, const tdn_tensor* out, float* workspace, size
               "psp_pool: workspace %zu < %zu bytes", workspace_bytes, need);
   int threads = in->c >= 512 ? 512 : (in->c >= 256 ? 256 : 128);
   if (in->w >= 6) {
-    psp_rowsum_kernel<<<dim3(in->h, ceil_div(in->c, 128), in->n), 128 * PSP_SEGS, 0, stream>>>(make_view(*in), workspace);
+    psp_rowsum_kernel<<<dim3(in->h, ceil_div(in->c, 128), in->n * PSP_PARTS), 128, 0, stream>>>(make_view(*in),
+                                                                                              workspace);
   } else {
     psp_rowsum_generic_kernel<<<dim3(in->h, in->n), threads, 0, stream>>>(make_view(*in), workspace);
   }
