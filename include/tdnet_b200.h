@@ -255,6 +255,29 @@ int tdn_bilinear_nhwc(const tdn_tensor* in, const tdn_tensor* out, void* stream)
 int tdn_psp_branch_convs(const tdn_tensor* pooled, const float* const* w, const float* const* scale,
                          const float* const* bias, int32_t eighth, float* const* out, void* stream);
 
+/* tdn_psp_branch_convs plus the projection of the pyramid features into the weight matrices of the 1x1 convolutions
+ * that consume z = cat(c4 slice, up(b1), up(b2), up(b3), up(b6)) (td4_psp18.py:278-284 feeding Encoding.w_qs / w_ks /
+ * w_vs, transformer.py:53-55): a 1x1 convolution commutes with the bilinear resize, so with the interpolation weights
+ * of the 50 bins as 64 extra input channels of every pixel (constant per map size) neither the resized branch maps
+ * nor z are ever written.  For projection q and image i the call stores, as SPLIT16,
+ *     dst[i * batch_stride + o * ld + bin] = sum_c w[lv(bin) * eighth + c][o] * b_lv[i][bin][c]      (bin = 0..49)
+ * i.e. column `bin` of the dynamic K block of the consumer's K-major weight matrix (columns 50..63 of that block stay
+ * as the caller initialised them: zero).  `w` must carry the same per-row scale as the consumer's static weights.
+ * range_flag (may be NULL) is set to 1 when a stored value exceeds the fp16 range of a SPLIT16 plane. */
+#define TDN_PSP_MAX_PROJECTIONS 4
+typedef struct tdn_psp_projection {
+  const float* w;       /* fp32 [4 * eighth][cout]: input-channel major, so that the kernel's loads coalesce over o */
+  void* dst_hi;         /* fp16 planes: element (row 0, first dynamic column) of image 0 */
+  void* dst_lo;
+  int64_t ld;           /* row pitch of dst, elements */
+  int64_t batch_stride; /* per-image stride of dst, elements (ignored for n = 1) */
+  int32_t cout;
+  int32_t reserved;
+} tdn_psp_projection;
+int tdn_psp_branch_project(const tdn_tensor* pooled, const float* const* w, const float* const* scale,
+                           const float* const* bias, int32_t eighth, float* const* out,
+                           const tdn_psp_projection* proj, int32_t n_proj, int32_t* range_flag, void* stream);
+
 /* The whole PyramidPooling output in one pass (td4_psp18.py:273-284): z = cat(x, up(b1), up(b2), up(b3), up(b6))
  * where x is the (already sliced) channel view of c4 and small[i] are the four branch maps, dense fp32
  * [n, bins_i, bins_i, eighth] with bins = 1, 2, 3, 6, resized bilinearly (align_corners=True) on the fly. */

@@ -55,6 +55,13 @@ class AttentionDesc(C.Structure):
                 ("range_flag", C.c_void_p), ("flags", C.c_int32)]
 
 
+class PspProjection(C.Structure):
+    """tdn_psp_projection (include/tdnet_b200.h)."""
+    _fields_ = [("w", C.c_void_p), ("dst_hi", C.c_void_p), ("dst_lo", C.c_void_p), ("ld", C.c_int64),
+                ("batch_stride", C.c_int64), ("cout", C.c_int32), ("reserved", C.c_int32)]
+
+
+PSP_MAX_PROJECTIONS = 4
 TC_FLAG_FAST = 1   # tdn_tc_conv_desc.flags / tdn_attention_desc.flags: one fp16 product per K step (opt-in, not fp32-faithful)
 
 # symbol -> (restype, argtypes); tests/test_cabi.py checks this list against include/tdnet_b200.h
@@ -86,6 +93,8 @@ SIGNATURES = {
     "tdn_bilinear_nhwc": (C.c_int, [_TP, _TP, C.c_void_p]),
     "tdn_psp_branch_convs": (C.c_int, [_TP, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                        C.c_int32, C.POINTER(C.c_void_p), C.c_void_p]),
+    "tdn_psp_branch_project": (C.c_int, [_TP, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                         C.c_int32, C.POINTER(C.c_void_p), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "tdn_psp_concat": (C.c_int, [_TP, C.POINTER(C.c_void_p), C.c_int32, _TP, C.c_void_p]),
     "tdn_copy_nhwc": (C.c_int, [_TP, _TP, C.c_void_p]),
     "tdn_softmax_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_float, C.c_void_p]),

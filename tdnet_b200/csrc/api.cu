@@ -41,6 +41,8 @@ int copy_nhwc(const tdn_tensor*, const tdn_tensor*, cudaStream_t);
 int psp_concat(const tdn_tensor*, const float* const*, int, const tdn_tensor*, cudaStream_t);
 int psp_branch_convs(const tdn_tensor*, const float* const*, const float* const*, const float* const*, int, float* const*,
                      cudaStream_t);
+int psp_branch_project(const tdn_tensor*, const float* const*, const float* const*, const float* const*, int, float* const*,
+                       const tdn_psp_projection*, int, int*, cudaStream_t);
 int softmax_rows(float*, long long, int, long long, float, cudaStream_t);
 int softmax_rows_split16(const float*, long long, int, long long, float, void*, void*, long long, float, cudaStream_t);
 int layernorm_hw_stats(const tdn_tensor*, float*, float*, float, void*, size_t, cudaStream_t);
@@ -218,6 +220,12 @@ int tdn_bilinear_nhwc(const tdn_tensor* in, const tdn_tensor* out, void* stream)
 int tdn_psp_branch_convs(const tdn_tensor* pooled, const float* const* w, const float* const* scale,
                          const float* const* bias, int32_t eighth, float* const* out, void* stream) {
   return psp_branch_convs(pooled, w, scale, bias, eighth, out, (cudaStream_t)stream);
+}
+
+int tdn_psp_branch_project(const tdn_tensor* pooled, const float* const* w, const float* const* scale,
+                           const float* const* bias, int32_t eighth, float* const* out,
+                           const tdn_psp_projection* proj, int32_t n_proj, int32_t* range_flag, void* stream) {
+  return psp_branch_project(pooled, w, scale, bias, eighth, out, proj, n_proj, range_flag, (cudaStream_t)stream);
 }
 
 int tdn_psp_concat(const tdn_tensor* x, const float* const* small, int32_t eighth, const tdn_tensor* z, void* stream) {

@@ -150,6 +150,117 @@ __global__ void psp_rowsum_kernel(View in, float* __restrict__ rowsum) {
     if (cur[l] < lv_o[l] && bin_start(cur[l], lv_o[l], W) < x_hi) dst[(long long)(lv_off[l] + cur[l]) * in.c] = acc[l];
 }
 
+// Vectorised pass 1 (c % 8 == 0, 16-byte aligned planes, rows wide enough): a thread owns 8 channels (one 16-byte load
+// per plane and pixel) and one of RS_SEG x-segments of the row, so 16x more loads are in flight than with one serial
+// walk per channel (that version: 65 us for the 67 MB map of a 1024x2048 frame, latency-bound).  A segment is shorter
+// than the narrowest column range minus one (host check: 6 (seg_len + 1) <= W), so per pyramid level it meets at most
+// two ranges: the first one reaching into it ("A") and the next ("B"; the two may share one column).  The partial sums
+// go to shared memory and are added per range in segment order (fixed order: bit-reproducible).
+constexpr int RS_SEG = 16;                           // x-segments per row
+constexpr int RS_CB = 64;                            // channels per block (8 lanes x 8 channels)
+constexpr int RS_SLOTS = 7;                          // level 0: A; levels 1..3: A and B
+constexpr int RS_PITCH = RS_SLOTS * RS_CB + 8;       // floats per segment (+8: the 4 segments of a warp use different banks)
+
+__device__ __forceinline__ int first_range(int o, int W, int x_lo) {   // first range of level o that ends behind x_lo
+  int j = 0;
+  while (j < o - 1 && bin_end(j, o, W) <= x_lo) ++j;
+  return j;
+}
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(RS_SEG * RS_CB / 8) psp_rowsum_vec8_kernel(View in, float* __restrict__ rowsum, int seg_len) {
+  __shared__ __align__(16) float part[RS_SEG * RS_PITCH];
+  __shared__ int first[RS_SEG][4];                   // first range of level l that reaches into segment s
+  const int y = blockIdx.x, b = blockIdx.z;
+  const int g = threadIdx.x & 7, s = threadIdx.x >> 3;
+  const int c0 = blockIdx.y * RS_CB + g * 8;
+  const int W = in.w;
+  const int x_lo = min(s * seg_len, W), x_hi = min(x_lo + seg_len, W);
+  if (threadIdx.x < RS_SEG * 4) {
+    const int s2 = threadIdx.x >> 2, l = threadIdx.x & 3;
+    first[s2][l] = first_range(l == 0 ? 1 : l == 1 ? 2 : l == 2 ? 3 : 6, W, min(s2 * seg_len, W));
+  }
+  __syncthreads();
+  int endA[4], startB[4];
+#pragma unroll
+  for (int l = 0; l < 4; ++l) {
+    const int o = l == 0 ? 1 : l == 1 ? 2 : l == 2 ? 3 : 6;
+    const int j = first[s][l];
+    endA[l] = bin_end(j, o, W);
+    startB[l] = j + 1 < o ? bin_start(j + 1, o, W) : 0x7fffffff;
+  }
+  float acc[RS_SLOTS][8];
+#pragma unroll
+  for (int k = 0; k < RS_SLOTS; ++k)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[k][e] = 0.f;
+  if (c0 < in.c) {
+    const long long base = b * in.sn + y * in.sh + c0;
+    constexpr int UN = 4;                              // pixels whose loads are issued together
+    for (int x0 = x_lo; x0 < x_hi; x0 += UN) {
+      float v[UN][8];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const long long off = base + (long long)min(x0 + u, x_hi - 1) * in.sw;
+        if (SPLIT) {
+          const uint4 hv = *reinterpret_cast<const uint4*>(in.hi + off);
+          const uint4 lv = *reinterpret_cast<const uint4*>(in.lo + off);
+          const __half2* h = reinterpret_cast<const __half2*>(&hv);
+          const __half2* lo = reinterpret_cast<const __half2*>(&lv);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 a = __half22float2(h[e]), d = __half22float2(lo[e]);
+            v[u][2 * e] = a.x + d.x;
+            v[u][2 * e + 1] = a.y + d.y;
+          }
+        } else {
+          *reinterpret_cast<float4*>(&v[u][0]) = *reinterpret_cast<const float4*>(in.p + off);
+          *reinterpret_cast<float4*>(&v[u][4]) = *reinterpret_cast<const float4*>(in.p + off + 4);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int x = x0 + u;
+        if (x < x_hi) {
+#pragma unroll
+          for (int l = 0; l < 4; ++l) {
+            if (x < endA[l]) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) acc[l == 0 ? 0 : 2 * l - 1][e] += v[u][e];
+            }
+            if (l > 0 && x >= startB[l]) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) acc[2 * l][e] += v[u][e];
+            }
+          }
+        }
+      }
+    }
+  }
+  float* mine = part + s * RS_PITCH + g * 8;
+#pragma unroll
+  for (int k = 0; k < RS_SLOTS; ++k) {
+    *reinterpret_cast<float4*>(mine + k * RS_CB) = make_float4(acc[k][0], acc[k][1], acc[k][2], acc[k][3]);
+    *reinterpret_cast<float4*>(mine + k * RS_CB + 4) = make_float4(acc[k][4], acc[k][5], acc[k][6], acc[k][7]);
+  }
+  __syncthreads();
+  // 12 ranges x RS_CB channels: every segment that meets the range adds its A or B slot, in segment order
+  float* dst = rowsum + ((long long)(b * in.h + y) * 12) * in.c + blockIdx.y * RS_CB;
+  for (int i = threadIdx.x; i < 12 * RS_CB; i += RS_SEG * RS_CB / 8) {
+    const int r = i / RS_CB, cc = i - r * RS_CB;
+    int l, j;
+    if (r < 1) { l = 0; j = 0; } else if (r < 3) { l = 1; j = r - 1; } else if (r < 6) { l = 2; j = r - 3; } else { l = 3; j = r - 6; }
+    float sum = 0.f;
+    for (int s2 = 0; s2 < RS_SEG; ++s2) {
+      if (s2 * seg_len >= W) break;
+      const int j0 = first[s2][l];
+      if (j == j0) sum += part[s2 * RS_PITCH + (l == 0 ? 0 : 2 * l - 1) * RS_CB + cc];
+      else if (l > 0 && j == j0 + 1) sum += part[s2 * RS_PITCH + 2 * l * RS_CB + cc];
+    }
+    if (blockIdx.y * RS_CB + cc < in.c) dst[(long long)r * in.c + cc] = sum;
+  }
+}
+
 // Generic fallback (any width, re-reads the row once per level): used when the map is narrower than the
 // finest pyramid level, where ranges overlap by more than one column.
 __global__ void psp_rowsum_generic_kernel(View in, float* __restrict__ rowsum) {
@@ -204,7 +315,17 @@ int psp_pool(const tdn_tensor* in, const tdn_tensor* out, float* workspace, size
   TDN_REQUIRE(workspace && workspace_bytes >= need, TDN_ERR_WORKSPACE,
               "psp_pool: workspace %zu < %zu bytes", workspace_bytes, need);
   int threads = in->c >= 512 ? 512 : (in->c >= 256 ? 256 : 128);
-  if (in->w >= 6) {
+  const int seg_len = ceil_div(in->w, RS_SEG);
+  const bool split = in->dtype == TDN_SPLIT16;
+  const bool vec8 = in->c % 8 == 0 && 6 * (seg_len + 1) <= in->w &&
+                    (split ? (aligned16(in->data) && aligned16(in->data_lo) && in->stride_n % 8 == 0 &&
+                              in->stride_h % 8 == 0 && in->stride_w % 8 == 0)
+                           : vec4_ok(*in));
+  if (vec8) {
+    const dim3 grid(in->h, ceil_div(in->c, RS_CB), in->n);
+    if (split) psp_rowsum_vec8_kernel<true><<<grid, RS_SEG * RS_CB / 8, 0, stream>>>(make_view(*in), workspace, seg_len);
+    else psp_rowsum_vec8_kernel<false><<<grid, RS_SEG * RS_CB / 8, 0, stream>>>(make_view(*in), workspace, seg_len);
+  } else if (in->w >= 6) {
     psp_rowsum_kernel<<<dim3(in->h, ceil_div(in->c, 128), in->n * PSP_PARTS), 128, 0, stream>>>(make_view(*in),
                                                                                               workspace);
   } else {
@@ -308,9 +429,29 @@ struct PspBranch {
   float* out[4];          // [n, bins, bins, eighth]
 };
 
+// Optional second stage (tdn_psp_branch_project): the consumers of z = cat(c4 slice, up(b1), .., up(b6)) are 1x1
+// convolutions, and a 1x1 convolution commutes with the bilinear resize: W . up(b_i) = up(W_i . b_i).  With the
+// interpolation weights of the 50 bins as 64 extra input channels of every pixel (constant per map size, written once
+// by the host), the resized branch maps never have to exist: this stage writes T[bin][o] = sum_c W[o][lv*eighth + c] *
+// b_lv[bin][c] into column `bin` of the consumer's K-major SPLIT16 weight matrix, and the consumer reads
+// [c4 slice | 64 interpolation channels] as its input (td4_psp18.py:273-284 + transformer.py:53-55 in one GEMM).
+struct PspProjection {
+  const float* w;         // [4 * eighth][cout] fp32 (already carrying the row scale of the consumer's static weights)
+  __half* hi;
+  __half* lo;
+  long long ld, bs;       // row pitch / per-image stride of the destination (elements)
+  int cout;
+};
+struct PspProjections {
+  PspProjection p[TDN_PSP_MAX_PROJECTIONS];
+  int n;
+  int* range_flag;
+};
+
 __global__ void __launch_bounds__(256) psp_branch_kernel(const float* __restrict__ pooled, int c4, int eighth,
-                                                         PspBranch br) {
-  extern __shared__ float xs[];
+                                                         PspBranch br, PspProjections pj) {
+  extern __shared__ float xs[];         // pooled vector [c4] | branch output of this bin [eighth]
+  float* ys = xs + c4;
   const int bin = blockIdx.x, b = blockIdx.y;
   int lv, local, bins;
   if (bin < 1) { lv = 0; local = bin; bins = 1; }
@@ -333,26 +474,84 @@ __global__ void __launch_bounds__(256) psp_branch_kernel(const float* __restrict
       acc = fmaf(wv.z, xv.z, acc); acc = fmaf(wv.w, xv.w, acc);
     }
     acc = warp_sum_f(acc);
-    if (lane == 0) out[co] = fmaxf(fmaf(acc, br.scale[lv][co], br.bias[lv][co]), 0.f);
+    if (lane == 0) {
+      const float v = fmaxf(fmaf(acc, br.scale[lv][co], br.bias[lv][co]), 0.f);
+      out[co] = v;
+      ys[co] = v;
+    }
   }
+  if (pj.n == 0) return;
+  __syncthreads();
+  bool out_of_range = false;
+  for (int q = 0; q < pj.n; ++q) {
+    const PspProjection& P = pj.p[q];
+    __half* dh = P.hi + (long long)b * P.bs + bin;
+    __half* dl = P.lo + (long long)b * P.bs + bin;
+    // one output channel per thread: the loads of a warp are one coalesced line per input channel and all independent
+    // (a warp per output with a shuffle reduction measured 100 us here: 80 dependent round trips to L2 per warp)
+    for (int o = threadIdx.x; o < P.cout; o += 256) {
+      const float* wc = P.w + (long long)lv * eighth * P.cout + o;
+      float acc = 0.f;
+#pragma unroll 8
+      for (int k = 0; k < eighth; ++k) acc = fmaf(__ldg(wc + (long long)k * P.cout), ys[k], acc);   // index order: fixed
+      __half h, l;
+      split_f32(acc, h, l);
+      dh[(long long)o * P.ld] = h;
+      dl[(long long)o * P.ld] = l;
+      out_of_range |= fabsf(acc) > 60000.f;
+    }
+  }
+  if (out_of_range && pj.range_flag) *reinterpret_cast<volatile int*>(pj.range_flag) = 1;
 }
 
-int psp_branch_convs(const tdn_tensor* pooled, const float* const* w, const float* const* scale,
-                     const float* const* bias, int eighth, float* const* out, cudaStream_t stream) {
+static int psp_branch_launch(const tdn_tensor* pooled, const float* const* w, const float* const* scale,
+                             const float* const* bias, int eighth, float* const* out, const PspProjections& pj,
+                             cudaStream_t stream) {
   int rc;
   if ((rc = check_f32_tensor(pooled, "psp_branch.pooled"))) return rc;
   TDN_REQUIRE(pooled->h == 1 && pooled->w == 50 && pooled->stride_w == pooled->c && pooled->stride_n == 50ll * pooled->c &&
                   pooled->c % 4 == 0 && aligned16(pooled->data), TDN_ERR_INVALID, "psp_branch: pooled must be dense [n,1,50,c4]");
+  TDN_REQUIRE(eighth > 0, TDN_ERR_INVALID, "psp_branch: eighth must be positive");
   PspBranch br;
   for (int i = 0; i < 4; ++i) {
     TDN_REQUIRE(w && scale && bias && out && w[i] && scale[i] && bias[i] && out[i] && aligned16(w[i]), TDN_ERR_INVALID,
                 "psp_branch: null or misaligned branch %d", i);
     br.w[i] = w[i]; br.scale[i] = scale[i]; br.bias[i] = bias[i]; br.out[i] = out[i];
   }
-  psp_branch_kernel<<<dim3(50, pooled->n), 256, pooled->c * sizeof(float), stream>>>((const float*)pooled->data,
-                                                                                     pooled->c, eighth, br);
+  psp_branch_kernel<<<dim3(50, pooled->n), 256, (pooled->c + eighth) * sizeof(float), stream>>>(
+      (const float*)pooled->data, pooled->c, eighth, br, pj);
   TDN_LAUNCH_OK();
   return TDN_OK;
+}
+
+int psp_branch_convs(const tdn_tensor* pooled, const float* const* w, const float* const* scale,
+                     const float* const* bias, int eighth, float* const* out, cudaStream_t stream) {
+  PspProjections pj;
+  pj.n = 0;
+  pj.range_flag = nullptr;
+  return psp_branch_launch(pooled, w, scale, bias, eighth, out, pj, stream);
+}
+
+int psp_branch_project(const tdn_tensor* pooled, const float* const* w, const float* const* scale,
+                       const float* const* bias, int eighth, float* const* out, const tdn_psp_projection* proj,
+                       int n_proj, int* range_flag, cudaStream_t stream) {
+  TDN_REQUIRE(proj && n_proj >= 1 && n_proj <= TDN_PSP_MAX_PROJECTIONS, TDN_ERR_INVALID,
+              "psp_branch_project: 1..%d projections expected", TDN_PSP_MAX_PROJECTIONS);
+  PspProjections pj;
+  pj.n = n_proj;
+  pj.range_flag = range_flag;
+  for (int q = 0; q < n_proj; ++q) {
+    const tdn_psp_projection& s = proj[q];
+    TDN_REQUIRE(s.w && s.dst_hi && s.dst_lo && s.cout > 0 && s.ld >= 50 && (pooled == nullptr || pooled->n == 1 || s.batch_stride > 0),
+                TDN_ERR_INVALID, "psp_branch_project: bad projection %d", q);
+    pj.p[q].w = s.w;
+    pj.p[q].hi = (__half*)s.dst_hi;
+    pj.p[q].lo = (__half*)s.dst_lo;
+    pj.p[q].ld = s.ld;
+    pj.p[q].bs = s.batch_stride;
+    pj.p[q].cout = s.cout;
+  }
+  return psp_branch_launch(pooled, w, scale, bias, eighth, out, pj, stream);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -609,6 +808,61 @@ __global__ void ln_partial_vec4_kernel(View x, double2* __restrict__ part, int c
   }
 }
 
+// SPLIT16 maps with c % 8 == 0: 8 channels per thread (one 16-byte load per plane and pixel) and four pixel sub-groups
+// per chunk, i.e. 4x the warps and 2x the bytes per load of the float4 version (31 us for the 67 MB map of a 1024x2048
+// frame: latency-bound).  The sub-group sums are added in index order through shared memory (fixed order per channel:
+// bit-reproducible run to run).
+constexpr int LN_SUB = 4;
+__global__ void __launch_bounds__(64 * LN_SUB) ln_partial_split8_kernel(View x, double2* __restrict__ part, int chunks) {
+  __shared__ double2 sm[LN_SUB - 1][512];
+  const int chunk = blockIdx.x, b = blockIdx.y;
+  const int P = x.h * x.w;
+  const int sub = threadIdx.x >> 6, lane_g = threadIdx.x & 63;
+  constexpr int PER = LN_CHUNK / LN_SUB;
+  const int p0 = min(chunk * LN_CHUNK + sub * PER, P), p1 = min(p0 + PER, P);
+  for (int cb = 0; cb < x.c; cb += 512) {
+    const int c = cb + lane_g * 8;
+    double s[8], q[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { s[e] = 0.0; q[e] = 0.0; }
+    if (c < x.c) {
+      int y = p0 / x.w, xx = p0 - y * x.w;
+#pragma unroll 4
+      for (int p = p0; p < p1; ++p) {
+        const long long off = b * x.sn + y * x.sh + xx * x.sw + c;
+        const uint4 hv = *reinterpret_cast<const uint4*>(x.hi + off);
+        const uint4 lv = *reinterpret_cast<const uint4*>(x.lo + off);
+        const __half2* h = reinterpret_cast<const __half2*>(&hv);
+        const __half2* l = reinterpret_cast<const __half2*>(&lv);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 a = __half22float2(h[e]), d = __half22float2(l[e]);
+          const double d0 = (double)(a.x + d.x), d1 = (double)(a.y + d.y);
+          s[2 * e] += d0; q[2 * e] += d0 * d0;
+          s[2 * e + 1] += d1; q[2 * e + 1] += d1 * d1;
+        }
+        if (++xx == x.w) { xx = 0; ++y; }
+      }
+    }
+    if (sub > 0) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) sm[sub - 1][lane_g * 8 + e] = make_double2(s[e], q[e]);
+    }
+    __syncthreads();
+    if (sub == 0 && c < x.c) {
+      double2* dst = part + ((long long)b * chunks + chunk) * x.c + c;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        double ss = s[e], qq = q[e];
+#pragma unroll
+        for (int g = 0; g < LN_SUB - 1; ++g) { ss += sm[g][lane_g * 8 + e].x; qq += sm[g][lane_g * 8 + e].y; }
+        dst[e] = make_double2(ss, qq);
+      }
+    }
+    __syncthreads();
+  }
+}
+
 constexpr int LN_FINAL_GROUPS = 32;   // chunk groups per block: the kernel is a chain of dependent loads per thread, so
                                       // more (shorter) chains finish sooner; the order of the additions is fixed
 __global__ void __launch_bounds__(32 * LN_FINAL_GROUPS) ln_final_kernel(const double2* __restrict__ part, int chunks, int C,
@@ -649,7 +903,11 @@ int layernorm_hw_stats(const tdn_tensor* x, float* mean, float* rstd, float eps,
   size_t need = (size_t)x->n * chunks * x->c * sizeof(double2);
   TDN_REQUIRE(workspace && workspace_bytes >= need && aligned16(workspace), TDN_ERR_WORKSPACE,
               "layernorm_hw_stats: workspace %zu < %zu bytes", workspace_bytes, need);
-  if (vec4_ok(*x)) {
+  const bool split8 = x->dtype == TDN_SPLIT16 && x->c % 8 == 0 && x->c >= 256 && aligned16(x->data) && aligned16(x->data_lo) &&
+                      x->stride_n % 8 == 0 && x->stride_h % 8 == 0 && x->stride_w % 8 == 0;
+  if (split8) {
+    ln_partial_split8_kernel<<<dim3(chunks, x->n), 64 * LN_SUB, 0, stream>>>(make_view(*x), (double2*)workspace, chunks);
+  } else if (vec4_ok(*x)) {
     int threads = x->c / 4 >= 256 ? 256 : (x->c / 4 >= 128 ? 128 : 64);
     ln_partial_vec4_kernel<<<dim3(chunks, x->n), threads, 0, stream>>>(make_view(*x), (double2*)workspace, chunks);
   } else {
@@ -908,6 +1166,52 @@ __global__ void __launch_bounds__(256) upsample_logits_kernel(View in, float* __
   }
 }
 
+// Same outputs (same bilerp, same operands) for the common >= 3x upsample of a dense map: a block produces ONE output row and
+// first stages the two low-resolution rows it needs in shared memory, transposed to [class][x].  In the kernel above a warp's
+// scalar loads of one class touch ~11 cache lines (19-float pixel pitch): 20 M L1 wavefronts per 1024x2048 frame, 53 us for a
+// 159 MB write that HBM takes in 25 us.  Here the loads are conflict-free shared-memory reads of ~17 consecutive words.
+__global__ void __launch_bounds__(256) upsample_logits_row_kernel(View in, float* __restrict__ out, int H, int W, float sy,
+                                                                  float sx) {
+  extern __shared__ float srow[];                    // [2][C][in.w + 1]
+  const int C = in.c, pitch = in.w + 1;
+  const int y = blockIdx.x, b = blockIdx.y;
+  int y0, y1; float ly;
+  src_index(y, sy, in.h, y0, y1, ly);
+  const float* g0 = in.p + b * in.sn + y0 * in.sh;
+  const float* g1 = in.p + b * in.sn + y1 * in.sh;
+  const int row_elems = in.w * C;
+  for (int i = threadIdx.x; i < row_elems; i += 256) {
+    const int x = i / C, c = i - x * C;
+    srow[c * pitch + x] = g0[x * in.sw + c];
+    srow[(C + c) * pitch + x] = g1[x * in.sw + c];
+  }
+  __syncthreads();
+  const int W4 = W >> 2;
+  const long long plane = (long long)H * W;
+  for (int xq = threadIdx.x; xq < W4; xq += 256) {
+    int x0[4], x1[4]; float lx[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) src_index(xq * 4 + j, sx, in.w, x0[j], x1[j], lx[j]);
+    const int xa = x0[0], xb = min(xa + 1, in.w - 1), xc = min(xa + 2, in.w - 1);
+    float* o = out + (long long)b * C * plane + (long long)y * W + xq * 4;
+    for (int c = 0; c < C; ++c) {
+      const float* t = srow + c * pitch;
+      const float* u = srow + (C + c) * pitch;
+      const float t0 = t[xa], t1 = t[xb], t2 = t[xc];
+      const float u0 = u[xa], u1 = u[xb], u2 = u[xc];
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int d0 = x0[j] - xa, d1 = x1[j] - xa;            // 0..1 and 0..2
+        const float ta = d0 == 0 ? t0 : t1, tb = d1 == 0 ? t0 : (d1 == 1 ? t1 : t2);
+        const float ua = d0 == 0 ? u0 : u1, ub = d1 == 0 ? u0 : (d1 == 1 ? u1 : u2);
+        v[j] = bilerp(ta, tb, ua, ub, lx[j], ly);
+      }
+      __stcs(reinterpret_cast<float4*>(o + c * plane), make_float4(v[0], v[1], v[2], v[3]));
+    }
+  }
+}
+
 // Same interpolation, but only the arg-max class leaves the chip: uint8 label map [n, H, W]
 // (Testing/test.py:61 takes output.max(1)[1] right after the forward; lowest index wins ties, like torch).
 // Saves the 159 MB fp32 logits write and turns a 16.8 MB int64 D2H into 2 MB.
@@ -1049,6 +1353,20 @@ int upsample_logits(const tdn_tensor* in, float* out_nchw, int out_h, int out_w,
   if ((rc = check_f32_tensor(in, "upsample.in"))) return rc;
   TDN_REQUIRE(out_nchw && out_h > 0 && out_w > 0, TDN_ERR_INVALID, "upsample_logits: bad output");
   TDN_REQUIRE(aligned16(out_nchw), TDN_ERR_INVALID, "upsample_logits: output must be 16-byte aligned");
+  const float sx = ac_scale(in->w, out_w);
+  const size_t row_smem = (size_t)2 * in->c * (in->w + 1) * sizeof(float);
+  if (sx <= 1.f / 3.f && (out_w & 3) == 0 && row_smem <= 96 * 1024 && out_h >= 128) {
+    static PerDeviceFlag attr_set;
+    const int slot = current_device_slot();
+    if (!attr_set.is_set(slot)) {
+      TDN_CUDA_OK(cudaFuncSetAttribute(upsample_logits_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      attr_set.set(slot);
+    }
+    upsample_logits_row_kernel<<<dim3(out_h, in->n), 256, row_smem, stream>>>(make_view(*in), out_nchw, out_h, out_w,
+                                                                             ac_scale(in->h, out_h), sx);
+    TDN_LAUNCH_OK();
+    return TDN_OK;
+  }
   long long total = (long long)in->n * out_h * ((out_w + 3) / 4);
   upsample_logits_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(
       make_view(*in), out_nchw, out_h, out_w, ac_scale(in->h, out_h), ac_scale(in->w, out_w));

@@ -553,8 +553,10 @@ int attention_tc(const tdn_attention_desc* d, cudaStream_t stream, int* count_on
   // Kernel family: 1 (default) = tc_attn_ts.cu, probabilities handed to the P.V' MMAs through tensor memory;
   // 0 = the kernels of this file (P through shared memory), kept as the yardstick.  TDNET_ATTN_TS selects.
   // (read on every call: the probes and tests flip it inside one process)
+  // TDNET_ATTN_TS = 3: the TS kernels with the Q tile in tensor memory as well (tc_attn_ts.cu, "QT").
   const char* ts_env = getenv("TDNET_ATTN_TS");
-  const bool use_ts = ts_env ? atoi(ts_env) != 0 : true;
+  const int ts_variant = ts_env ? atoi(ts_env) : ATTN_DEFAULT_VARIANT;
+  const bool use_ts = ts_variant != 0;
   {
     static PerDeviceFlag attr_set;                   // the > 48 KB shared-memory opt-in is per device
     const int slot = current_device_slot();
@@ -570,7 +572,7 @@ int attention_tc(const tdn_attention_desc* d, cudaStream_t stream, int* count_on
     if (use_ts) {
       AttnParams q = pp;
       q.per_cta = ceil_div(q.items_a, grid);     // contiguous blocks: the d_v slices of a query tile meet on one CTA
-      return attention_ts_launch(dvt, grid, stream, short_launch, mq_h, mq_l, mk_h, mk_l, mv_h, mv_l, q);
+      return attention_ts_launch(dvt, ts_variant == 3, grid, stream, short_launch, mq_h, mq_l, mk_h, mk_l, mv_h, mv_l, q);
     }
     if (dvt == 256)
       return tc_launch(tc_attn_kernel<256>, grid, AT_THREADS, AT_SMEM_BYTES, stream, short_launch, mq_h, mq_l, mk_h, mk_l, mv_h, mv_l, pp);

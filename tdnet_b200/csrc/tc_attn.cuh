@@ -27,6 +27,7 @@ constexpr int AT_KSTAGES = 2, AT_VSTAGES = 3;
 constexpr int AT_SMEM_DATA = 2 * AT_Q_PLANE + AT_KSTAGES * 2 * AT_K_PLANE + AT_VSTAGES * 2 * AT_V_PLANE + 2 * 2 * AT_P_PLANE;
 constexpr int AT_TMEM_COLS = 512;   // S: 2 x 64 columns, O: up to 256 columns
 constexpr float AT_P_SCALE = 1024.f;
+constexpr int ATTN_DEFAULT_VARIANT = 1;   // TDNET_ATTN_TS default: 0 tc_attn.cu, 1 tc_attn_ts.cu, 3 tc_attn_ts.cu with Q in TMEM
 
 // 2^x through one MUFU.EX2 (2 ulp; results below the normal range flush to zero, which is what a
 // probability that small should do).  The libm exp2f spends ~6 more instructions on range handling.
@@ -100,7 +101,7 @@ __device__ __forceinline__ bool attn_shares_rowmax(const AttnParams& p, int item
 }
 
 // tc_attn_ts.cu: launch of the TMEM-operand kernel family (dvt = 128 or 256 output channels per work item).
-cudaError_t attention_ts_launch(int dvt, int grid, cudaStream_t stream, bool short_launch, const CUtensorMap& mq_h,
+cudaError_t attention_ts_launch(int dvt, bool qt, int grid, cudaStream_t stream, bool short_launch, const CUtensorMap& mq_h,
                                 const CUtensorMap& mq_l, const CUtensorMap& mk_h, const CUtensorMap& mk_l,
                                 const CUtensorMap& mv_h, const CUtensorMap& mv_l, const AttnParams& p);
 

@@ -39,7 +39,8 @@ constexpr int ATS_SOFTMAX_WARP0 = 4;      // warps 4-11
 constexpr int ATS_EPI_WARP0 = 12;         // warps 12-15
 constexpr int ATS_EPI_WARPS = 4;
 constexpr int ATS_KSTAGES = 3, ATS_VSTAGES = 4;
-constexpr int ATS_SP = 4;                          // S/P buffers of 64 TMEM columns
+constexpr int ATS_SP = 4;                          // S/P buffers of 64 TMEM columns (three in the QT variant)
+constexpr int ATS_QT_COL = 448;                    // QT variant: Q hi pairs in TMEM columns [448, 480), lo pairs [480, 512)
 constexpr int ATS_SMEM_DATA = 2 * AT_Q_PLANE + ATS_KSTAGES * 2 * AT_K_PLANE + ATS_VSTAGES * 2 * AT_V_PLANE +
                               ATS_EPI_WARPS * ATS_EPI_STAGE;
 
@@ -51,6 +52,7 @@ struct AttnTsBars {
   uint64_t s_full[ATS_SP], p_full[ATS_SP], sp_empty[ATS_SP];   // pass 2: S ready / P written / P consumed by P.V'
   uint64_t o_full, o_empty;
   uint64_t l_full, l_empty;                        // row sums of an item written / read by the epilogue warps
+  uint64_t qt_full;                                // QT variant: the Q tile has been copied into tensor memory
   uint32_t tmem_ptr;
   float xch[2][AT_BQ];     // row max exchange between the two softmax warp groups, then their partial row sums
                            // for the epilogue warps (rewritten only after l_empty of the previous item)
@@ -60,7 +62,13 @@ constexpr int ATS_SMEM_BYTES = ATS_SMEM_DATA + 1024 /*alignment slack*/ + ((int)
 static_assert(ATS_SMEM_BYTES <= 232448, "attention kernel exceeds the 227 KB shared-memory limit");
 
 
-template <int DVT>   // d_v slice per work item: 128 or 256 (one or two 128-row V'^T halves per key tile)
+// QT ("Q in tensor memory"): the pass-2 S MMAs are M128 x N64 x K16 -- 32 tensor cycles, but 4 KB of A plus 2 KB of B from
+// shared memory at 128 B/clk = 48 cycles (measured 52), i.e. 29 % of a key tile's tensor time is spent at 0.6 of the MMA
+// rate.  Q is the A operand of every one of them and is constant for the whole item, so the softmax warps copy the tile
+// (hi and lo planes, 64 + 64 fp16 per row = 64 TMEM columns) into tensor memory once per query tile, after pass 1, and
+// the S MMAs take A from there (B only from shared memory: 16 cycles).  The columns come from the S/P ring, which
+// shrinks from four to three buffers; pass 1 still uses [256, 512) as two 128-column tiles (the copy follows it).
+template <int DVT, bool QT>   // d_v slice per work item: 128 or 256 (one or two 128-row V'^T halves per key tile)
 __global__ void __launch_bounds__(ATS_THREADS, 1)
 tc_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ CUtensorMap tmQ_lo,
                   const __grid_constant__ CUtensorMap tmK_hi, const __grid_constant__ CUtensorMap tmK_lo,
@@ -98,6 +106,7 @@ tc_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_const
     mbar_init(&bars->o_empty, ATS_EPI_WARPS);
     mbar_init(&bars->l_full, AT_SOFTMAX_WARPS);
     mbar_init(&bars->l_empty, ATS_EPI_WARPS);
+    mbar_init(&bars->qt_full, AT_SOFTMAX_WARPS);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -111,6 +120,7 @@ tc_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_const
   tc_pdl_sync();
   const uint32_t tmem_O = tmem_base;
   const uint32_t tmem_SP = tmem_base + 256;      // + b * 64
+  constexpr uint32_t SP = QT ? 3 : ATS_SP;       // S/P ring depth
   const int T = p.k_tiles;
   const int T1 = p.k_tiles1;
 
@@ -179,7 +189,8 @@ tc_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_const
     int ks = 0;
     uint32_t kph = 0, qph = 0;
     uint32_t n1 = 0;      // pass-1 tiles issued so far: buffer pair n1 & 1, use n1 >> 1
-    uint32_t n2 = 0;      // pass-2 tiles issued so far: buffer n2 & 3, use n2 >> 2
+    uint32_t n2 = 0;      // pass-2 tiles issued so far: buffer n2 % SP, use n2 / SP
+    uint32_t nq = 0;      // QT: query tiles copied into tensor memory so far
     uint32_t items_done = 0;
     const uint32_t q_hi = smem_u32(sQ), q_lo = q_hi + AT_Q_PLANE;
     for (int k = 0, item, prev = -1; (item = attn_walk(p, k)) >= 0; prev = item, ++k, ++items_done) {
@@ -211,10 +222,14 @@ tc_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_const
         const uint32_t t = n1 - j;
         mbar_wait(&bars->s1_empty[t & 1], (t >> 1) & 1);
       }
+      if (QT && !reuse) {                                           // the softmax warps have put this Q tile into TMEM
+        mbar_wait(&bars->qt_full, nq & 1);
+        ++nq;
+      }
       for (int it = 0; it < T; ++it, ++n2) {
-        const int sb = n2 & (ATS_SP - 1);
+        const int sb = n2 % SP;
         mbar_wait(&bars->k_full[ks], kph);
-        mbar_wait(&bars->sp_empty[sb], ((n2 / ATS_SP) & 1) ^ 1);
+        mbar_wait(&bars->sp_empty[sb], ((n2 / SP) & 1) ^ 1);
         tc_fence_after();
         const uint32_t k_hi = smem_u32(sK + ks * 2 * AT_K_PLANE), k_lo = k_hi + AT_K_PLANE;
         const uint32_t d = tmem_SP + sb * AT_BK;
@@ -223,7 +238,16 @@ tc_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_const
           for (int k = 0; k < AT_DK / 16; ++k) {
             const uint64_t a_h = umma_desc_k_sw128(q_hi + k * 32), b_h = umma_desc_k_sw128(k_hi + k * 32);
             const uint64_t a_l = umma_desc_k_sw128(q_lo + k * 32), b_l = umma_desc_k_sw128(k_lo + k * 32);
-            if (p.fast) {
+            if (QT) {
+              const uint32_t t_h = tmem_base + ATS_QT_COL + k * 8, t_l = t_h + 32;   // 8 columns of fp16 pairs per K16 step
+              if (p.fast) {
+                umma_f16_ts(d, t_h, b_h, idesc_s, k != 0);
+              } else {
+                umma_f16_ts(d, t_h, b_l, idesc_s, k != 0);
+                umma_f16_ts(d, t_l, b_h, idesc_s, 1);
+                umma_f16_ts(d, t_h, b_h, idesc_s, 1);
+              }
+            } else if (p.fast) {
               umma_f16(d, a_h, b_h, idesc_s, k != 0);
             } else {
               umma_f16(d, a_h, b_l, idesc_s, k != 0);
@@ -250,8 +274,8 @@ tc_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_const
       const int halves = attn_item<DVT>(p, item).halves;
       mbar_wait(&bars->o_empty, oph ^ 1);                        // epilogue of the previous item has read O
       for (int kt = 0; kt < T; ++kt, ++n2) {
-        const int sb = n2 & (ATS_SP - 1);
-        mbar_wait(&bars->p_full[sb], (n2 / ATS_SP) & 1);
+        const int sb = n2 % SP;
+        mbar_wait(&bars->p_full[sb], (n2 / SP) & 1);
         const uint32_t p_base = tmem_SP + sb * AT_BK;
         for (int h = 0; h < halves; ++h) {
           mbar_wait(&bars->v_full[vs], vph);
@@ -334,6 +358,27 @@ tc_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_const
       group_sync();
       m = fmaxf(m, bars->xch[group ^ 1][row]);
       group_sync();                                           // xch carries the row sums next
+      if (QT) {
+        // Q tile -> tensor memory (group 0: hi plane, group 1: lo plane; one row per thread).  Every softmax warp is past
+        // its last pass-1 tile here (the syncs above), so the columns [448, 512) of the second pass-1 buffer are free.
+        mbar_wait(&bars->q_full, items_done & 1);             // TMA-written shared memory: observe the barrier ourselves
+        const uint32_t qrow = smem_u32(sQ) + group * AT_Q_PLANE + row * 128;
+        uint32_t w0[16], w1[16];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {                           // 128-byte swizzle: 16-byte piece c of row r sits at c ^ (r & 7)
+          const uint4 a = lds128(qrow + ((c ^ (row & 7)) << 4));
+          const uint4 b2 = lds128(qrow + (((c + 4) ^ (row & 7)) << 4));
+          w0[4 * c] = a.x; w0[4 * c + 1] = a.y; w0[4 * c + 2] = a.z; w0[4 * c + 3] = a.w;
+          w1[4 * c] = b2.x; w1[4 * c + 1] = b2.y; w1[4 * c + 2] = b2.z; w1[4 * c + 3] = b2.w;
+        }
+        const uint32_t qdst = tmem_base + ATS_QT_COL + group * 32 + lane_addr;
+        tmem_st_32x16(qdst, w0);
+        tmem_st_32x16(qdst + 16, w1);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->qt_full);
+      }
       } else {
         mbar_wait(&bars->l_empty, (items_done & 1) ^ 1);       // (the row sums below reuse xch)
       }
@@ -345,9 +390,9 @@ tc_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_const
       // ---- pass 2: S -> probabilities, written back over S as packed fp16 hi / lo pairs; partial row sum
       float l = 0.f;
       for (int kt = 0; kt < T; ++kt, ++n2) {
-        const int sb = n2 & (ATS_SP - 1);
+        const int sb = n2 % SP;
         const uint32_t taddr = tmem_SP + sb * AT_BK + lane_addr + group * 32;
-        mbar_wait(&bars->s_full[sb], (n2 / ATS_SP) & 1);
+        mbar_wait(&bars->s_full[sb], (n2 / SP) & 1);
         tc_fence_after();
         float pr[32];
         {
@@ -425,24 +470,27 @@ tc_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_const
   }
 }
 
-cudaError_t attention_ts_launch(int dvt, int grid, cudaStream_t stream, bool short_launch, const CUtensorMap& mq_h,
+cudaError_t attention_ts_launch(int dvt, bool qt, int grid, cudaStream_t stream, bool short_launch, const CUtensorMap& mq_h,
                                 const CUtensorMap& mq_l, const CUtensorMap& mk_h, const CUtensorMap& mk_l,
                                 const CUtensorMap& mv_h, const CUtensorMap& mv_l, const AttnParams& p) {
   // the > 48 KB dynamic shared-memory opt-in is a per-device function attribute: set it once per device
   static PerDeviceFlag attr_set;
   const int slot = current_device_slot();
   if (!attr_set.is_set(slot)) {
-    cudaError_t e = cudaFuncSetAttribute(tc_attn_ts_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATS_SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(tc_attn_ts_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATS_SMEM_BYTES);
-    if (e != cudaSuccess) return e;
+    cudaError_t e;
+#define ATS_OPT_IN(K) \
+    if ((e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, ATS_SMEM_BYTES)) != cudaSuccess) return e
+    ATS_OPT_IN((tc_attn_ts_kernel<128, false>));
+    ATS_OPT_IN((tc_attn_ts_kernel<256, false>));
+    ATS_OPT_IN((tc_attn_ts_kernel<128, true>));
+    ATS_OPT_IN((tc_attn_ts_kernel<256, true>));
+#undef ATS_OPT_IN
     attr_set.set(slot);
   }
-  if (dvt == 256)
-    return tc_launch(tc_attn_ts_kernel<256>, grid, ATS_THREADS, ATS_SMEM_BYTES, stream, short_launch, mq_h, mq_l, mk_h,
-                     mk_l, mv_h, mv_l, p);
-  return tc_launch(tc_attn_ts_kernel<128>, grid, ATS_THREADS, ATS_SMEM_BYTES, stream, short_launch, mq_h, mq_l, mk_h,
-                   mk_l, mv_h, mv_l, p);
+#define ATS_LAUNCH(K) tc_launch(K, grid, ATS_THREADS, ATS_SMEM_BYTES, stream, short_launch, mq_h, mq_l, mk_h, mk_l, mv_h, mv_l, p)
+  if (qt) return dvt == 256 ? ATS_LAUNCH((tc_attn_ts_kernel<256, true>)) : ATS_LAUNCH((tc_attn_ts_kernel<128, true>));
+  return dvt == 256 ? ATS_LAUNCH((tc_attn_ts_kernel<256, false>)) : ATS_LAUNCH((tc_attn_ts_kernel<128, false>));
+#undef ATS_LAUNCH
 }
 
 }  // namespace tdn

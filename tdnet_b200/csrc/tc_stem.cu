@@ -173,45 +173,90 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_stem_kernel(const TcStemPara
     }
   } else if (warp < TS_POOL_WARP0) {
     // ======================= loader: image rows -> split fp16, 4 channels per pixel =======================
+    // Software-pipelined: all 18 global loads of row pair u+1 (2 rows x 3 pixels per thread x 3 channels) are issued
+    // before row pair u is converted and stored, so a thread always has one row pair of loads in flight.  (With the
+    // loads issued pixel by pixel the loader was one DRAM round trip per pixel and row: 6 dependent trips = ~5 K
+    // cycles per conv row, the bound of the whole kernel at 128 us per 1024x2048 frame.)
     const int tl = tid - TS_LOAD_WARP0 * 32;
     const int NP = NR + 3;
     const float* img = p.img + (long long)b * 3 * p.H * p.W;
     const uint8_t* img8 = p.img_u8 + (long long)b * 3 * p.H * p.W;
     const long long plane = (long long)p.H * p.W;
+    constexpr int PXI = (TS_IPX + TS_LOAD_THREADS - 1) / TS_LOAD_THREADS;     // pixels per thread and row (3)
     bool out_of_range = false;
-    for (int u = 0; u < NP; ++u) {
-      const int slot = u % TS_DP;
-      mbar_wait(&img_empty[slot], ((u / TS_DP) & 1) ^ 1);
+    // raw[rr][it][c]: the fp32 bit pattern (NCHW image) or the byte value (uint8 frame) of channel c
+    auto issue = [&](int u, uint32_t (&raw)[2][PXI][3], uint32_t& okmask) {
+      okmask = 0;
 #pragma unroll
       for (int rr = 0; rr < 2; ++rr) {
         const int iy = iy0 + 2 * u + rr;
         const bool rowok = iy >= 0 && iy < p.H;
-        uint8_t* dst_hi = s_ring + (slot * 2 + rr) * TS_ROW_BYTES;
-        uint8_t* dst_lo = dst_hi + TS_RING_PLANE;
-        for (int px = tl; px < TS_IPX; px += TS_LOAD_THREADS) {
+#pragma unroll
+        for (int it = 0; it < PXI; ++it) {
+          const int px = tl + it * TS_LOAD_THREADS;
           const int ix = ix0 + px;
-          float c0 = 0.f, c1 = 0.f, c2 = 0.f;          // zero padding applies to the normalised tensor
-          if (rowok && ix >= 0 && ix < p.W && px < TS_IPX_USED) {
+          const bool ok = rowok && ix >= 0 && ix < p.W && px < TS_IPX_USED;
+          raw[rr][it][0] = raw[rr][it][1] = raw[rr][it][2] = 0u;
+          if (ok) {
+            okmask |= 1u << (rr * PXI + it);
             if (U8) {
               const uint8_t* q = img8 + ((long long)iy * p.W + ix) * 3;
-              c0 = __ldg(p.lut + __ldg(q));
-              c1 = __ldg(p.lut + 256 + __ldg(q + 1));
-              c2 = __ldg(p.lut + 512 + __ldg(q + 2));
+              raw[rr][it][0] = __ldg(q); raw[rr][it][1] = __ldg(q + 1); raw[rr][it][2] = __ldg(q + 2);
             } else {
               const float* q = img + (long long)iy * p.W + ix;
-              c0 = __ldg(q); c1 = __ldg(q + plane); c2 = __ldg(q + 2 * plane);
+              raw[rr][it][0] = __float_as_uint(__ldg(q));
+              raw[rr][it][1] = __float_as_uint(__ldg(q + plane));
+              raw[rr][it][2] = __float_as_uint(__ldg(q + 2 * plane));
             }
-            out_of_range |= fmaxf(fabsf(c0), fmaxf(fabsf(c1), fabsf(c2))) > 60000.f;
           }
-          __half2 h[2], l[2];
-          split_f32x2(c0, c1, h[0], l[0]);
-          split_f32x2(c2, 0.f, h[1], l[1]);
-          *reinterpret_cast<uint2*>(dst_hi + px * 8) = *reinterpret_cast<const uint2*>(h);
-          *reinterpret_cast<uint2*>(dst_lo + px * 8) = *reinterpret_cast<const uint2*>(l);
+        }
+      }
+    };
+    uint32_t cur[2][PXI][3], nxt[2][PXI][3];
+    uint32_t cur_ok = 0, nxt_ok = 0;
+    issue(0, cur, cur_ok);
+    for (int u = 0; u < NP; ++u) {
+      const int slot = u % TS_DP;
+      if (u + 1 < NP) issue(u + 1, nxt, nxt_ok);
+      mbar_wait(&img_empty[slot], ((u / TS_DP) & 1) ^ 1);
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        uint8_t* dst_hi = s_ring + (slot * 2 + rr) * TS_ROW_BYTES;
+        uint8_t* dst_lo = dst_hi + TS_RING_PLANE;
+#pragma unroll
+        for (int it = 0; it < PXI; ++it) {
+          const int px = tl + it * TS_LOAD_THREADS;
+          if (px < TS_IPX) {
+            float c0 = 0.f, c1 = 0.f, c2 = 0.f;        // zero padding applies to the normalised tensor
+            if (cur_ok >> (rr * PXI + it) & 1) {
+              if (U8) {
+                c0 = __ldg(p.lut + cur[rr][it][0]);
+                c1 = __ldg(p.lut + 256 + cur[rr][it][1]);
+                c2 = __ldg(p.lut + 512 + cur[rr][it][2]);
+              } else {
+                c0 = __uint_as_float(cur[rr][it][0]);
+                c1 = __uint_as_float(cur[rr][it][1]);
+                c2 = __uint_as_float(cur[rr][it][2]);
+              }
+              out_of_range |= fmaxf(fabsf(c0), fmaxf(fabsf(c1), fabsf(c2))) > 60000.f;
+            }
+            __half2 h[2], l[2];
+            split_f32x2(c0, c1, h[0], l[0]);
+            split_f32x2(c2, 0.f, h[1], l[1]);
+            *reinterpret_cast<uint2*>(dst_hi + px * 8) = *reinterpret_cast<const uint2*>(h);
+            *reinterpret_cast<uint2*>(dst_lo + px * 8) = *reinterpret_cast<const uint2*>(l);
+          }
         }
       }
       fence_proxy_async_smem();
       mbar_arrive(&img_full[slot]);
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+        for (int it = 0; it < PXI; ++it)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) cur[rr][it][c] = nxt[rr][it][c];
+      cur_ok = nxt_ok;
     }
     if (out_of_range && p.range_flag) *reinterpret_cast<volatile int*>(p.range_flag) = 1;   // idempotent store: the flag may live in host-mapped memory
   } else {

@@ -128,6 +128,29 @@ def op_psp_branch_convs(pooled, w, scale, bias, eighth, out, stream):
         off += b * b
 
 
+def op_psp_branch_project(pooled, w, scale, bias, eighth, out, proj, n_proj, flag, stream):
+    """include/tdnet_b200.h: the branch convs, then dst[i][o][bin] = sum_c w[lv(bin) * eighth + c][o] * b_lv[i][bin][c]
+    stored as SPLIT16 into column `bin` of each projection's destination."""
+    op_psp_branch_convs(pooled, w, scale, bias, eighth, out, stream)
+    n = pooled._obj.n
+    for q in range(n_proj):
+        pr = proj[q]
+        wq = _flat(pr.w, pr.cout * 4 * eighth, torch.float32).view(4, eighth, pr.cout).permute(2, 0, 1)
+        off = 0
+        for lv, b in enumerate(PSP_BINS):
+            feat = _flat(out[lv], n * b * b * eighth, torch.float32).view(n, b * b, eighth)
+            t = torch.einsum("oc,nbc->nob", wq[:, lv].double(), feat.double()).float()      # [n, cout, bins^2]
+            for i in range(n):
+                ext = (pr.cout - 1) * pr.ld + b * b
+                base = i * pr.batch_stride + off
+                hi = torch.as_strided(_flat(pr.dst_hi + 2 * base, ext, torch.float16), (pr.cout, b * b), (pr.ld, 1))
+                lo = torch.as_strided(_flat(pr.dst_lo + 2 * base, ext, torch.float16), (pr.cout, b * b), (pr.ld, 1))
+                h = t[i].half()
+                hi.copy_(h)
+                lo.copy_((t[i] - h.float()).half())
+            off += b * b
+
+
 def op_psp_concat(x, small, eighth, z, stream):
     xv = read(x._obj)
     n, h, w, cx = xv.shape
@@ -311,7 +334,7 @@ def op_upsample_argmax_sampled(x, out, H, W, ys, xs, Ho, Wo, stream):
 OPS = {
     "tdn_image_to_nhwc": op_image_to_nhwc, "tdn_stem_conv_pool_tc": op_stem_conv_pool_tc,
     "tdn_stem_conv_pool": op_stem_conv_pool, "tdn_psp_pool": op_psp_pool, "tdn_psp_branch_convs": op_psp_branch_convs,
-    "tdn_psp_concat": op_psp_concat, "tdn_stem_conv_pool_tc_act": op_stem_conv_pool_tc_act, "tdn_maxpool3x3s2": op_maxpool3x3s2, "tdn_conv2d": op_conv2d,
+    "tdn_psp_concat": op_psp_concat, "tdn_psp_branch_project": op_psp_branch_project, "tdn_stem_conv_pool_tc_act": op_stem_conv_pool_tc_act, "tdn_maxpool3x3s2": op_maxpool3x3s2, "tdn_conv2d": op_conv2d,
     "tdn_conv2d_tc": op_conv2d_tc, "tdn_attention_tc": op_attention_tc, "tdn_softmax_rows": op_softmax_rows,
     "tdn_copy_nhwc": op_copy_nhwc, "tdn_pointwise_linear": op_pointwise_linear, "tdn_bilinear_nhwc": op_bilinear_nhwc, "tdn_fa_context": op_fa_context,
     "tdn_fa_apply": op_fa_apply, "tdn_add_upsampled": op_add_upsampled,

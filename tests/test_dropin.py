@@ -57,7 +57,10 @@ def test_engine_plans_build_without_gpu():
     for k in sd:
         if k.endswith("running_var"):
             sd[k].fill_(1.0)
-    for mode, tc_ops in (("simt", 0), ("tc", 26)):  # 26 = every conv but the 3-ch stem, the PSP branch convs and the classifier
+    # 28 = every conv but the 3-ch stem and the PSP branch convs (with the pyramid fold the first key projection is a
+    # tensor-core GEMM over [c4 slice | interpolation channels] even on the 4 x 6 key grid; the 19-class classifier runs
+    # as a GEMM with 24 output channels)
+    for mode, tc_ops in (("simt", 0), ("tc", 28)):
         eng = Engine(m, sd, 1, 97, 161, torch.device("cpu"), (h8, w8), mode=mode)
         warm, steady = eng.plan(1, False), eng.plan(1, True)
         c = Counter(fn.__name__ for fn, _ in steady.ops)

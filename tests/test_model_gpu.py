@@ -36,9 +36,14 @@ def tap(view):  # engine NHWC view -> NCHW cpu tensor
     return view.torch().permute(0, 3, 1, 2).contiguous().cpu()
 
 
-@pytest.mark.parametrize("mode", ["tc", "simt"])
+@pytest.mark.parametrize("mode", ["tc", "tc_nofold", "simt"])
 @pytest.mark.parametrize("name", [n for n in GOLDEN_CASES if not n.endswith("_chk")])
-def test_model_matches_reference_golden(name, mode):
+def test_model_matches_reference_golden(name, mode, monkeypatch):
+    """'tc' is the product path (pyramid fold: the Encoding convs read [c4 slice | interpolation channels], z is never
+    written); 'tc_nofold' the same kernels with the materialised z of td4_psp18.py:278-284 (and its tap)."""
+    if mode == "tc_nofold":
+        monkeypatch.setenv("TDNET_B200_PSP_FOLD", "0")
+        mode = "tc"
     arch, backbone = GOLDEN_CASES[name]
     g, m = load_golden(name)
     sd = make_weights(arch, backbone, m["h8"], m["w8"])
@@ -64,7 +69,9 @@ def test_model_matches_reference_golden(name, mode):
     s = CH_STRIDE
     t = plan.taps
     assert max_abs(tap(t["c4"])[:, ::s], g["tap_c4"]) <= TAP_TOL
-    assert max_abs(tap(t["z"])[:, ::s], g["tap_z"]) <= TAP_TOL
+    assert ("z" in t) == (not eng.psp_fold)
+    if "z" in t:
+        assert max_abs(tap(t["z"])[:, ::s], g["tap_z"]) <= TAP_TOL
     assert max_abs(tap(t["v_cur"])[:, ::s], g["tap_v_cur"]) <= TAP_TOL
     assert max_abs(t["q_cur"].torch().reshape(m["batch"], -1, 64).cpu(), g["tap_q_cur"]) <= TAP_TOL
     assert max_abs(tap(t["normed"])[:, ::s], g["tap_normed"]) <= TAP_TOL

@@ -171,6 +171,30 @@ def test_psp_pool_matches_adaptive_avg_pool(env, h, w):
         off += bins * bins
 
 
+@pytest.mark.parametrize("h,w,c", [(128, 256, 512), (97, 193, 512), (16, 32, 256), (13, 21, 64), (33, 40, 72)])
+def test_psp_pool_split16_channel_slice_view(env, h, w, c):
+    """The vectorised row pass (8 channels per thread, 16 x-segments) on a SPLIT16 map that is a channel range of a wider
+    buffer -- the c4 view of the pyramid fold -- against adaptive_avg_pool2d of the merged values."""
+    lib, cabi, View, dev = env
+    g = torch.Generator(device="cuda").manual_seed(h * w + c)
+    big = View.alloc(1, h, w, c + 128, dev, split=True)
+    x = torch.randn(1, h, w, c + 128, generator=g, device="cuda") * 2 + 0.5
+    big.base.copy_(x.reshape(-1).half()); big.lo.copy_((x.reshape(-1) - big.base.float()).half())
+    v = big.channels(64, 64 + c)
+    out = torch.full((1, 50, c), float("nan"), device=dev)
+    nbytes = int(lib.tdn_psp_pool_workspace_bytes(1, h, c))
+    ws = torch.empty(nbytes // 4, device=dev)
+    ti, to = v.ct(), View(out.view(-1), 1, 1, 50, c).ct()
+    cabi.check(lib.tdn_psp_pool(C.byref(ti), C.byref(to), ws.data_ptr(), nbytes, None))
+    torch.cuda.synchronize()
+    ref_in = v.torch().permute(0, 3, 1, 2).double().cpu()
+    off = 0
+    for bins in (1, 2, 3, 6):
+        ref = F.adaptive_avg_pool2d(ref_in, bins).permute(0, 2, 3, 1).reshape(1, bins * bins, c)
+        assert max_abs(out[:, off:off + bins * bins].cpu(), ref) < 3e-6
+        off += bins * bins
+
+
 @pytest.mark.parametrize("hs,ws", [(1, 1), (2, 2), (3, 3), (6, 6)])
 def test_bilinear_align_corners_into_channel_slice(env, hs, ws):
     lib, cabi, View, dev = env
@@ -209,7 +233,30 @@ def test_layernorm_hw(env):
     assert max_abs(y.permute(0, 3, 1, 2).cpu(), ref) < 5e-6
 
 
-@pytest.mark.parametrize("h,w,H,W", [(13, 21, 97, 161), (16, 32, 128, 256), (8, 8, 64, 64)])
+def test_layernorm_hw_split16_wide(env):
+    """SPLIT16 map with 512 channels (the 8-channel-per-thread partial-sum kernel) on a ragged number of pixels."""
+    lib, cabi, View, dev = env
+    g = torch.Generator(device="cuda").manual_seed(5)
+    n, h, w, c = 2, 37, 53, 512
+    x = torch.randn(n, h, w, c, generator=g, device="cuda") * 3 + 1.5
+    xv = View.alloc(n, h, w, c, dev, split=True)
+    xv.base.copy_(x.reshape(-1).half()); xv.lo.copy_((x.reshape(-1) - xv.base.float()).half())
+    xm = xv.torch()
+    mean, rstd = torch.empty(n * c, device=dev), torch.empty(n * c, device=dev)
+    nbytes = int(lib.tdn_layernorm_hw_workspace_bytes(n, h, w, c))
+    ws = torch.empty(nbytes // 4, device=dev)
+    tx = xv.ct()
+    cabi.check(lib.tdn_layernorm_hw_stats(C.byref(tx), mean.data_ptr(), rstd.data_ptr(), C.c_float(1e-5),
+                                          ws.data_ptr(), nbytes, None))
+    torch.cuda.synchronize()
+    xd = xm.double()
+    mu, var = xd.mean(dim=(1, 2)), xd.var(dim=(1, 2), unbiased=False)
+    assert max_abs(mean.cpu(), mu.reshape(-1).cpu()) < 1e-6
+    assert max_abs(rstd.cpu(), (1.0 / torch.sqrt(var + 1e-5)).reshape(-1).cpu()) < 1e-6
+
+
+@pytest.mark.parametrize("h,w,H,W", [(13, 21, 97, 161), (16, 32, 128, 256), (8, 8, 64, 64), (128, 256, 1024, 2048),
+                                     (64, 128, 512, 1024), (45, 60, 360, 480)])
 def test_upsample_logits_nchw(env, h, w, H, W):
     lib, cabi, View, dev = env
     g = torch.Generator().manual_seed(H)
@@ -546,7 +593,7 @@ def attn_family():
     """Restores TDNET_ATTN_TS (the library reads it on every call) after a test that flips kernel families."""
     import os
     old = os.environ.get("TDNET_ATTN_TS")
-    yield lambda ts: os.environ.__setitem__("TDNET_ATTN_TS", "1" if ts else "0")
+    yield lambda ts: os.environ.__setitem__("TDNET_ATTN_TS", str(int(ts)))   # 0 SS, 1 TS, 3 TS with Q in tensor memory
     if old is None:
         os.environ.pop("TDNET_ATTN_TS", None)
     else:
@@ -562,11 +609,12 @@ def test_attention_kernel_families_bit_identical(env, attn_family, n, pq, pk, dv
     including the split into 256- and 128-channel launches (20000 queries: 314 items on 148 SMs) and ragged tiles."""
     lib, cabi, View, dev = env
     got = {}
-    for ts in (False, True):
+    for ts in (0, 1, 3):
         attn_family(ts)
         got[ts] = _attention_case(cabi, lib, dev, n, pq, pk, dv, out_fmt, res_fmt)[0]
-    assert not torch.isnan(got[True]).any()
-    assert torch.equal(got[False], got[True])
+    assert not torch.isnan(got[1]).any()
+    assert torch.equal(got[0], got[1])
+    assert torch.equal(got[0], got[3])         # Q as a tensor-memory operand: same products, same order
 
 
 @pytest.mark.parametrize("n,pq,pk,dv", [(1, 32768, 2048, 512), (1, 32768, 1225, 512), (1, 4096, 2048, 1024)])
@@ -576,14 +624,15 @@ def test_fused_attention_tc_big_hop(env, attn_family, n, pq, pk, dv):
     softmax(q k^T / 8) v + residual of transformer.py:126-139 (the full fp64 matrix would not fit the test budget)."""
     lib, cabi, View, dev = env
     got = {}
-    for ts in (False, True):
+    for ts in (0, 1, 3):
         attn_family(ts)
         got[ts], q, k, v, r = _attention_case(cabi, lib, dev, n, pq, pk, dv, "split", "split")
-    assert torch.equal(got[False], got[True])
+    assert torch.equal(got[0], got[1])
+    assert torch.equal(got[0], got[3])
     rows = torch.arange(0, pq, 61)
     a = torch.softmax(q[:, rows].double() @ k.double().transpose(1, 2) / 8.0, dim=2)
     ref = a @ v.double() + r[:, rows].double()
-    out = got[True][:, rows.to(dev)].cpu().double()
+    out = got[1][:, rows.to(dev)].cpu().double()
     assert max_abs(out, ref) < 1.5e-5 * float(ref.abs().max())
     assert float((out - ref).norm() / ref.norm()) < 5e-6
 
@@ -732,6 +781,55 @@ def test_psp_branch_convs_one_launch(env):
         ref = F.relu(pooled[:, off:off + b * b] @ ws[i].t() * scs[i] + bis[i])
         assert max_abs(outs[i].cpu(), ref) < 5e-6
         off += b * b
+
+
+@pytest.mark.parametrize("n,c4,couts", [(1, 512, (512, 64, 64)), (2, 2048, (256, 64))])
+def test_psp_branch_project_writes_projected_features(env, n, c4, couts):
+    """tdn_psp_branch_project: the branch maps of tdn_psp_branch_convs plus, per projection, dst[i][o][bin] =
+    sum_c w[lv * eighth + c][o] * b_lv[i][bin][c] as SPLIT16 in the dynamic columns of a wider weight matrix whose other
+    columns must stay untouched."""
+    lib, cabi, View, dev = env
+    g = torch.Generator().manual_seed(c4 + n)
+    eighth = c4 // 8
+    pooled = torch.randn(n, 50, c4, generator=g)
+    ws = [torch.randn(eighth, c4, generator=g) / c4 ** 0.5 for _ in range(4)]
+    scs = [torch.rand(eighth, generator=g) + 0.5 for _ in range(4)]
+    bis = [torch.randn(eighth, generator=g) * 0.2 for _ in range(4)]
+    pd = pooled.cuda()
+    wd, sd_, bd = [w.cuda() for w in ws], [s.cuda() for s in scs], [b.cuda() for b in bis]
+    outs = [torch.empty(n, b * b, eighth, device=dev) for b in (1, 2, 3, 6)]
+    arr = lambda xs: (C.c_void_p * 4)(*[t.data_ptr() for t in xs])  # noqa: E731
+    K, dyn = 64 + 128, 128
+    projs, pw, dst = (cabi.PspProjection * len(couts))(), [], []
+    for q, cout in enumerate(couts):
+        w = (torch.randn(4 * eighth, cout, generator=g) * 3).cuda()
+        hi = torch.full((n, cout, K), 7.0, dtype=torch.float16, device=dev)
+        lo = torch.full((n, cout, K), -3.0, dtype=torch.float16, device=dev)
+        pw.append(w); dst.append((hi, lo))
+        projs[q].w, projs[q].dst_hi, projs[q].dst_lo = w.data_ptr(), hi.data_ptr() + 2 * dyn, lo.data_ptr() + 2 * dyn
+        projs[q].ld, projs[q].batch_stride, projs[q].cout = K, cout * K, cout
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    t = View(pd.view(-1), n, 1, 50, c4).ct()
+    cabi.check(lib.tdn_psp_branch_project(C.byref(t), arr(wd), arr(sd_), arr(bd), eighth, arr(outs), projs, len(couts),
+                                          flag.data_ptr(), None), "psp_branch_project")
+    torch.cuda.synchronize()
+    off, feats = 0, []
+    for i, b in enumerate((1, 2, 3, 6)):
+        ref = F.relu(pooled[:, off:off + b * b] @ ws[i].t() * scs[i] + bis[i])
+        assert max_abs(outs[i].cpu(), ref) < 5e-6
+        feats.append(outs[i].double().cpu())
+        off += b * b
+    for q, cout in enumerate(couts):
+        hi, lo = dst[q]
+        got = hi.float().cpu() + lo.float().cpu()
+        w = pw[q].double().cpu().view(4, eighth, cout)
+        want = torch.cat([torch.einsum("co,nbc->nob", w[lv], feats[lv]) for lv in range(4)], 2)        # [n, cout, 50]
+        scale = float(want.abs().max())
+        assert max_abs(got[:, :, dyn:dyn + 50], want) <= 2e-6 * scale
+        assert float((hi[:, :, :dyn] - 7).abs().max()) == 0 and float((hi[:, :, dyn + 50:] - 7).abs().max()) == 0
+        assert float((lo[:, :, :dyn] + 3).abs().max()) == 0 and float((lo[:, :, dyn + 50:] + 3).abs().max()) == 0
+    assert int(flag.item()) == 0
+    assert lib.tdn_psp_branch_project(C.byref(t), arr(wd), arr(sd_), arr(bd), eighth, arr(outs), projs, 0, None, None) == -1
 
 
 @pytest.mark.parametrize("split", [False, True])

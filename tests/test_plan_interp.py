@@ -62,10 +62,14 @@ def _synth_weights(m, ln_shape):
     return synth_state_dict(tmpl, seed=0)
 
 
-@pytest.mark.parametrize("mode", ["tc", "simt"])
+@pytest.mark.parametrize("mode", ["tc", "tc_nofold", "simt"])
 @pytest.mark.parametrize("name", ["td4_r18_97x161", "td4_r18_128x256", "td2_r50_64x128", "td2_r34_80x112", "td4_r50_64x64_n2"])
-def test_td_plans_match_reference_golden(name, mode):
-    """Warm-up and steady plans of the TD models frame by frame, FIFO included (push order, shifts, slot views)."""
+def test_td_plans_match_reference_golden(name, mode, monkeypatch):
+    """Warm-up and steady plans of the TD models frame by frame, FIFO included (push order, shifts, slot views).  'tc' runs
+    the pyramid fold (Encoding convs over [c4 slice | interpolation channels], no z); 'tc_nofold' the materialised z."""
+    if mode == "tc_nofold":
+        monkeypatch.setenv("TDNET_B200_PSP_FOLD", "0")
+        mode = "tc"
     arch, backbone = GOLDEN_CASES[name]
     g, meta = load_golden(name)
     H, W, n = meta["H"], meta["W"], meta["batch"]
@@ -82,7 +86,9 @@ def test_td_plans_match_reference_golden(name, mode):
         if f"logits_{i}" in g:
             assert max_abs(out, g[f"logits_{i}"]) <= 2e-4
     s = CH_STRIDE
-    assert max_abs(_nchw(plan.taps["z"])[:, ::s], g["tap_z"]) <= 1e-3
+    assert ("z" in plan.taps) == (not eng.psp_fold)
+    if "z" in plan.taps:
+        assert max_abs(_nchw(plan.taps["z"])[:, ::s], g["tap_z"]) <= 1e-3
     assert max_abs(_nchw(plan.taps["normed"])[:, ::s], g["tap_normed"]) <= 1e-3
     # the newest FIFO entry is what the reference queued (Encoding(pre=True), transformer.py:34-50)
     assert max_abs(read(eng.k_slots[-1].ct()).reshape(n, -1, 64), g["tap_k_sub"]) <= 1e-3

@@ -45,7 +45,7 @@ def formats(lib):
                 got = {}
                 fams = tuple(os.environ.get("ATTN_PROBE_FAMILIES", "ss,ts").split(","))
                 for which in fams:
-                    os.environ["TDNET_ATTN_TS"] = {"ss": "0", "ts2": "2"}.get(which, "1")
+                    os.environ["TDNET_ATTN_TS"] = {"ss": "0", "ts2": "2", "tq": "3"}.get(which, "1")
                     of = torch.full((n, pq, dv), float("nan"), device="cuda")
                     oh = torch.full((n, pq, dv), float("nan"), device="cuda", dtype=torch.half)
                     ol = torch.full((n, pq, dv), float("nan"), device="cuda", dtype=torch.half)
@@ -101,7 +101,7 @@ def main():
         if sustain and "--debug" in sys.argv:
             variants = tuple(os.environ.get("ATTN_PROBE_VARIANTS", "ts,ts_dbg1,ts_dbg2,ts_dbg4,ts_dbg8,ts_dbg15").split(","))
         for which in variants:
-            os.environ["TDNET_ATTN_TS"] = {"ss": "0", "ts2": "2"}.get(which.split("_")[0], "1")
+            os.environ["TDNET_ATTN_TS"] = {"ss": "0", "ts2": "2", "tq": "3"}.get(which.split("_")[0], "1")
             os.environ["TDNET_ATTN_DEBUG"] = which.split("dbg")[1] if "dbg" in which else "0"
             out = torch.full((n, pq, dv), float("nan"), device="cuda")
             d = _cabi.AttentionDesc()
@@ -172,8 +172,8 @@ def main():
                 res[f"max_abs_vs_fp64_{which}"] = float((out.cpu().double() - ref).abs().max())
         if "ss" in outs and "ts" in outs:
             res["max_diff_ts_vs_ss"] = float((outs["ss"][0] - outs["ts"][0]).abs().max())
-        if "ss" in outs and "ts2" in outs:
-            res["max_diff_ts2_vs_ss"] = float((outs["ss"][0] - outs["ts2"][0]).abs().max())
+        if "ss" in outs and "tq" in outs:
+            res["max_diff_tq_vs_ss"] = float((outs["ss"][0] - outs["tq"][0]).abs().max())
         print(json.dumps(res), flush=True)
         lines.append(json.dumps(res))
     if out_path:
