@@ -1,7 +1,7 @@
 #!/bin/bash
 # One B200 session: the driver's GPU test command, smoke, the attention probe (kernel families), bench (default line) with
 # either attention variant, the unfiltered launch list of steady frames.  Usage: bash tools/gpu_session.sh [tag] [steps...]
-# steps: tests smoke probe bench bench_tq launches reference (default: all but reference)
+# steps: tests smoke probe bench bench_tq launches reference ncu:<kernel regex> (default: the first six)
 cd "$(dirname "$0")/.."
 TAG=${1:-r02}
 shift
@@ -24,4 +24,14 @@ if has launches; then
   echo "== launch list"; timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/${TAG}_frame_all.csv python tools/frame_launches.py > gpurun_out/${TAG}_frame_all.log 2>&1
   python tools/launch_summary.py gpurun_out/${TAG}_frame_all.csv | head -24
 fi
+# ncu:<regex> -- one full-set capture (source-level stall samples included) of the first matching launch inside steady frames
+for st in $STEPS; do
+  if [[ $st == ncu:* ]]; then
+    K=${st#ncu:}
+    echo "== ncu --set full of $K"
+    timeout 600 ncu --set full --import-source on --clock-control none --profile-from-start off --kernel-name regex:$K --launch-count 1 \
+      -f -o gpurun_out/${TAG}_prof_${K} python tools/frame_launches.py > gpurun_out/${TAG}_prof_${K}.log 2>&1
+    tail -2 gpurun_out/${TAG}_prof_${K}.log
+  fi
+done
 if has reference; then echo "== reference arm"; timeout 600 python bench.py --impl reference --steps 20 --warmup 5 2>&1 | tail -1 | tee gpurun_out/${TAG}_bench_reference.json | cut -c1-400; fi
