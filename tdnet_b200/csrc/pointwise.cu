@@ -1257,14 +1257,75 @@ __global__ void __launch_bounds__(256) upsample_argmax_kernel(View in, uint8_t* 
   }
 }
 
+// Shared-memory version of the arg-max upsampler, built like upsample_logits_row_kernel (one output row per block, the two
+// low-resolution rows staged as [class][x]) with the identical bilerp on identical operands: labels == arg-max of the logits
+// either logits kernel writes.  No 159 MB logits write, and the per-class loads are conflict-free shared-memory reads instead
+// of 16 scattered 4-byte global loads per class and thread.
+__global__ void __launch_bounds__(256) upsample_argmax_row_kernel(View in, uint8_t* __restrict__ labels, int H, int W,
+                                                                  float sy, float sx) {
+  extern __shared__ float srow[];                    // [2][C][in.w + 1]
+  const int C = in.c, pitch = in.w + 1;
+  const int y = blockIdx.x, b = blockIdx.y;
+  int y0, y1; float ly;
+  src_index(y, sy, in.h, y0, y1, ly);
+  const float* g0 = in.p + b * in.sn + y0 * in.sh;
+  const float* g1 = in.p + b * in.sn + y1 * in.sh;
+  const int row_elems = in.w * C;
+  for (int i = threadIdx.x; i < row_elems; i += 256) {
+    const int x = i / C, c = i - x * C;
+    srow[c * pitch + x] = g0[x * in.sw + c];
+    srow[(C + c) * pitch + x] = g1[x * in.sw + c];
+  }
+  __syncthreads();
+  const int W4 = W >> 2;
+  for (int xq = threadIdx.x; xq < W4; xq += 256) {
+    int x0[4], x1[4]; float lx[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) src_index(xq * 4 + j, sx, in.w, x0[j], x1[j], lx[j]);
+    const int xa = x0[0], xb = min(xa + 1, in.w - 1), xc = min(xa + 2, in.w - 1);
+    float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    int arg[4] = {0, 0, 0, 0};
+    for (int c = 0; c < C; ++c) {
+      const float* t = srow + c * pitch;
+      const float* u = srow + (C + c) * pitch;
+      const float t0 = t[xa], t1 = t[xb], t2 = t[xc];
+      const float u0 = u[xa], u1 = u[xb], u2 = u[xc];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int d0 = x0[j] - xa, d1 = x1[j] - xa;            // 0..1 and 0..2
+        const float ta = d0 == 0 ? t0 : t1, tb = d1 == 0 ? t0 : (d1 == 1 ? t1 : t2);
+        const float ua = d0 == 0 ? u0 : u1, ub = d1 == 0 ? u0 : (d1 == 1 ? u1 : u2);
+        const float v = bilerp(ta, tb, ua, ub, lx[j], ly);
+        if (v > best[j]) { best[j] = v; arg[j] = c; }
+      }
+    }
+    *reinterpret_cast<uchar4*>(labels + ((long long)b * H + y) * W + xq * 4) =
+        make_uchar4((uint8_t)arg[0], (uint8_t)arg[1], (uint8_t)arg[2], (uint8_t)arg[3]);
+  }
+}
+
 int upsample_argmax(const tdn_tensor* in, uint8_t* labels, int out_h, int out_w, cudaStream_t stream) {
   int rc;
   if ((rc = check_f32_tensor(in, "upsample_argmax.in"))) return rc;
   TDN_REQUIRE(labels && out_h > 0 && out_w > 0 && in->c <= 256, TDN_ERR_INVALID, "upsample_argmax: bad output / > 256 classes");
   TDN_REQUIRE((((uintptr_t)labels) & 3u) == 0, TDN_ERR_INVALID, "upsample_argmax: labels must be 4-byte aligned");
+  const float sx = ac_scale(in->w, out_w);
+  const size_t row_smem = (size_t)2 * in->c * (in->w + 1) * sizeof(float);
+  if (sx <= 1.f / 3.f && (out_w & 3) == 0 && row_smem <= 96 * 1024 && out_h >= 128) {
+    static PerDeviceFlag attr_set;
+    const int slot = current_device_slot();
+    if (!attr_set.is_set(slot)) {
+      TDN_CUDA_OK(cudaFuncSetAttribute(upsample_argmax_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      attr_set.set(slot);
+    }
+    upsample_argmax_row_kernel<<<dim3(out_h, in->n), 256, row_smem, stream>>>(make_view(*in), labels, out_h, out_w,
+                                                                             ac_scale(in->h, out_h), sx);
+    TDN_LAUNCH_OK();
+    return TDN_OK;
+  }
   long long total = (long long)in->n * out_h * ((out_w + 3) / 4);
   upsample_argmax_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(make_view(*in), labels, out_h, out_w,
-                                                                   ac_scale(in->h, out_h), ac_scale(in->w, out_w));
+                                                                   ac_scale(in->h, out_h), sx);
   TDN_LAUNCH_OK();
   return TDN_OK;
 }

@@ -13,12 +13,17 @@
 // The weights sit in shared memory for the whole kernel as [chunk 28][cout 64][8] fp16 per plane.
 //
 // One CTA walks down a strip of 126 conv columns (63 pooled columns) for 2*PB+1 conv rows (PB pooled rows):
-//   warps 5-8  loader   image rows (2 per conv row) -> split fp16 -> ring of 6 row pairs
-//   warp  0    MMA      42 MMAs per conv row into one of two 64-column TMEM accumulators
-//   warps 1-4  epilogue TMEM -> BN + ReLU (0 outside the conv map: cannot change a max of ReLU outputs)
-//                       -> ring of 3 fp32 conv rows in shared memory (16-byte quads XOR-swizzled by column)
-//   warps 9-12 pool     3x3/2 max over three conv rows -> pooled row in global memory (F32 or SPLIT16)
+//   warps 9-12  loader   image rows (2 per conv row) -> split fp16 -> ring of 5 row pairs (the next pair's global
+//                        loads are in flight in registers while the current one is converted)
+//   warp  0     MMA      42 MMAs per conv row into one of two 64-column TMEM accumulators
+//   warps 1-8   epilogue TMEM -> BN + ReLU (0 outside the conv map: cannot change a max of ReLU outputs)
+//                        -> ring of 4 fp32 conv rows in shared memory (16-byte quads XOR-swizzled by column);
+//                        two warps per TMEM lane quarter, 32 channels each
+//   warps 13-16 pool     3x3/2 max over three conv rows -> pooled row in global memory (F32 or SPLIT16)
 // all hand-offs through mbarriers; the 512x1024x64 pre-pool map never leaves the SM.
+// ncu of the round-1 layout (4 epilogue warps of 64 channels, 3 conv-row slots, loads issued pixel by pixel): 5.4 K
+// cycles per conv row against 2.0 K of MMA time -- first the loader (one DRAM round trip per pixel), then the epilogue
+// warps (700 instructions per row on one warp per scheduler, and blocked while the pool holds all three row slots).
 #include "tc_common.cuh"
 
 namespace tdn {
@@ -28,17 +33,19 @@ constexpr int TS_PW = 63;                              // pooled columns per str
 constexpr int TS_IPX_USED = 2 * TS_M + 6;              // 262 image pixels feed 128 conv columns (kx 0..7)
 constexpr int TS_IPX = 264;                            // staged row pitch in pixels
 constexpr int TS_ROW_BYTES = TS_IPX * 8;               // 2112 (multiple of 16)
-constexpr int TS_DP = 6;                               // image ring depth in row pairs (4 in use + 2 ahead)
+constexpr int TS_DP = 5;                               // image ring depth in row pairs (4 in use + 1 ahead)
 constexpr int TS_RING_PLANE = TS_DP * 2 * TS_ROW_BYTES;
 constexpr int TS_W_CHUNKS = 28;                        // 7 filter rows x 4 column pairs
 constexpr int TS_W_PLANE = TS_W_CHUNKS * 64 * 16;      // 28 KiB per plane
 constexpr int TS_CROW_BYTES = TS_M * 64 * 4;           // one conv row, fp32
-constexpr int TS_CROWS = 3;
-constexpr int TS_LOAD_WARP0 = 5, TS_POOL_WARP0 = 9;     // warp 0 MMA, warps 1-4 epilogue
+constexpr int TS_CROWS = 4;                            // three feed a pooled row, the fourth is being written
+constexpr int TS_EPI_WARPS = 8;                        // warps 1-8
+constexpr int TS_LOAD_WARP0 = 9, TS_POOL_WARP0 = 13;   // warp 0 MMA, warps 1-8 epilogue
 constexpr int TS_LOAD_THREADS = 128, TS_POOL_THREADS = 128;
-constexpr int TS_THREADS = 32 * 13;
+constexpr int TS_THREADS = 32 * 17;
 constexpr int TS_TMEM_COLS = 128;
 constexpr int TS_SMEM_BYTES = 2 * TS_W_PLANE + 2 * TS_RING_PLANE + TS_CROWS * TS_CROW_BYTES + 512 + 256 + 128;
+static_assert(TS_SMEM_BYTES <= 232448, "stem kernel exceeds the 227 KB shared-memory limit");
 
 struct TcStemParams {
   const float* img;       // [n,3,H,W] fp32 NCHW ...
@@ -55,7 +62,7 @@ struct TcStemParams {
   int* range_flag;
 };
 
-template <bool U8>
+template <bool U8, bool LEAKY>
 __global__ void __launch_bounds__(TS_THREADS, 1) tc_stem_kernel(const TcStemParams p) {
   extern __shared__ uint8_t ts_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ts_smem_raw) + 127) & ~(uintptr_t)127);
@@ -73,7 +80,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_stem_kernel(const TcStemPara
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  const float pool_pad = p.act == TDN_ACT_RELU ? 0.f : -INFINITY;
+  const float pool_pad = LEAKY ? -INFINITY : 0.f;
   const int b = blockIdx.z;
   const int px0 = blockIdx.x * TS_PW, py0 = blockIdx.y * p.PB;
   const int npb = min(p.PB, p.Hp - py0);               // pooled rows of this CTA
@@ -83,8 +90,8 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_stem_kernel(const TcStemPara
 
   if (tid == 0) {
     for (int s = 0; s < TS_DP; ++s) { mbar_init(&img_full[s], TS_LOAD_THREADS); mbar_init(&img_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
-    for (int s = 0; s < TS_CROWS; ++s) { mbar_init(&row_full[s], 4); mbar_init(&row_empty[s], TS_POOL_THREADS / 32); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], TS_EPI_WARPS); }
+    for (int s = 0; s < TS_CROWS; ++s) { mbar_init(&row_full[s], TS_EPI_WARPS); mbar_init(&row_empty[s], TS_POOL_THREADS / 32); }
     fence_mbar_init();
   }
   if (warp == 0) {
@@ -134,9 +141,12 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_stem_kernel(const TcStemPara
   } else if (warp < TS_LOAD_WARP0) {
     // ======================= epilogue: TMEM -> BN + ReLU -> conv-row ring =======================
     const int quarter = warp & 3;                      // TMEM lanes 32*quarter .. +31
+    const int chalf = (warp - 1) >> 2;                 // channels 32*chalf .. +31
     const int m = quarter * 32 + lane;                 // conv column of the strip
     const int cx = cx0 + m;
     const bool colok = cx >= 0 && cx < p.Wc;
+    const float4* sc4 = reinterpret_cast<const float4*>(s_sb + chalf * 32);
+    const float4* bi4 = reinterpret_cast<const float4*>(s_sb + 64 + chalf * 32);
     for (int r = 0; r < NR; ++r) {
       const int slot = r % TS_CROWS;
       mbar_wait(&acc_full[r & 1], (r >> 1) & 1);
@@ -145,28 +155,32 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_stem_kernel(const TcStemPara
       const int cy = cy0 + r;
       const bool ok = colok && cy >= 0 && cy < p.Hc;
       uint8_t* dst = s_rows + slot * TS_CROW_BYTES + m * 256;
-      uint32_t v0[32], v1[32];
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (r & 1) * 64;
-      tmem_ld_32x32(taddr, v0);
-      tmem_ld_32x32(taddr + 32, v1);
+      uint32_t v[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (r & 1) * 64 + chalf * 32;
+      tmem_ld_32x32(taddr, v);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[r & 1]);
 #pragma unroll
-      for (int q = 0; q < 16; ++q) {
-        const uint32_t* v = q < 8 ? &v0[q * 4] : &v1[(q - 8) * 4];
-        const int ch = q * 4;
+      for (int q = 0; q < 8; ++q) {
         // outside the conv map: the pool's padding.  0 cannot change a max of ReLU outputs; LeakyReLU outputs may be
         // negative, so there the padding is -inf (every 3x3 window holds at least its centre, which is inside)
         float4 o = make_float4(pool_pad, pool_pad, pool_pad, pool_pad);
         if (ok) {
-          o.x = tc_act(fmaf(__uint_as_float(v[0]), s_sb[ch + 0], s_sb[64 + ch + 0]), p.act, p.slope);
-          o.y = tc_act(fmaf(__uint_as_float(v[1]), s_sb[ch + 1], s_sb[64 + ch + 1]), p.act, p.slope);
-          o.z = tc_act(fmaf(__uint_as_float(v[2]), s_sb[ch + 2], s_sb[64 + ch + 2]), p.act, p.slope);
-          o.w = tc_act(fmaf(__uint_as_float(v[3]), s_sb[ch + 3], s_sb[64 + ch + 3]), p.act, p.slope);
+          const float4 sc = sc4[q], bi = bi4[q];
+          o.x = fmaf(__uint_as_float(v[q * 4 + 0]), sc.x, bi.x);
+          o.y = fmaf(__uint_as_float(v[q * 4 + 1]), sc.y, bi.y);
+          o.z = fmaf(__uint_as_float(v[q * 4 + 2]), sc.z, bi.z);
+          o.w = fmaf(__uint_as_float(v[q * 4 + 3]), sc.w, bi.w);
+          if (LEAKY) {
+            o.x = o.x > 0.f ? o.x : o.x * p.slope; o.y = o.y > 0.f ? o.y : o.y * p.slope;
+            o.z = o.z > 0.f ? o.z : o.z * p.slope; o.w = o.w > 0.f ? o.w : o.w * p.slope;
+          } else {
+            o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+          }
         }
-        *reinterpret_cast<float4*>(dst + ((q ^ (m & 15)) * 16)) = o;
+        *reinterpret_cast<float4*>(dst + (((chalf * 8 + q) ^ (m & 15)) * 16)) = o;
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&row_full[slot]);
@@ -334,8 +348,10 @@ int stem_conv_pool_tc(const float* nchw, const uint8_t* hwc_u8, const float* lut
   static PerDeviceFlag attr_set;
   const int slot = current_device_slot();
   if (!attr_set.is_set(slot)) {
-    TDN_CUDA_OK(cudaFuncSetAttribute(tc_stem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES));
-    TDN_CUDA_OK(cudaFuncSetAttribute(tc_stem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES));
+    TDN_CUDA_OK(cudaFuncSetAttribute(tc_stem_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES));
+    TDN_CUDA_OK(cudaFuncSetAttribute(tc_stem_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES));
+    TDN_CUDA_OK(cudaFuncSetAttribute(tc_stem_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES));
+    TDN_CUDA_OK(cudaFuncSetAttribute(tc_stem_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES));
     attr_set.set(slot);
   }
   // Pooled rows per CTA: every CTA pays ~6 row-times of prologue (weights, pipeline fill) and one halo conv
@@ -352,8 +368,14 @@ int stem_conv_pool_tc(const float* nchw, const uint8_t* hwc_u8, const float* lut
   }
   p.PB = best_pb;
   dim3 grid(strips, ceil_div(p.Hp, p.PB), n);
-  if (nchw) tc_stem_kernel<false><<<grid, TS_THREADS, TS_SMEM_BYTES, stream>>>(p);
-  else tc_stem_kernel<true><<<grid, TS_THREADS, TS_SMEM_BYTES, stream>>>(p);
+  const bool leaky = act == TDN_ACT_LEAKY_RELU;
+  if (nchw) {
+    if (leaky) tc_stem_kernel<false, true><<<grid, TS_THREADS, TS_SMEM_BYTES, stream>>>(p);
+    else tc_stem_kernel<false, false><<<grid, TS_THREADS, TS_SMEM_BYTES, stream>>>(p);
+  } else {
+    if (leaky) tc_stem_kernel<true, true><<<grid, TS_THREADS, TS_SMEM_BYTES, stream>>>(p);
+    else tc_stem_kernel<true, false><<<grid, TS_THREADS, TS_SMEM_BYTES, stream>>>(p);
+  }
   TDN_LAUNCH_OK();
   return TDN_OK;
 }

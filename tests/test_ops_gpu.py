@@ -270,6 +270,24 @@ def test_upsample_logits_nchw(env, h, w, H, W):
     assert max_abs(out.cpu(), ref) < 2e-6
 
 
+@pytest.mark.parametrize("h,w,H,W", [(13, 21, 97, 161), (128, 256, 1024, 2048), (97, 193, 769, 1537), (24, 40, 192, 320)])
+def test_upsample_argmax_equals_argmax_of_upsampled_logits(env, h, w, H, W):
+    """tdn_upsample_argmax (Testing/test.py:61 fused into the final interpolation) == arg-max over the classes of what
+    tdn_upsample_logits writes, bit for bit: both kernel pairs (per-thread loads / shared-memory rows) share one bilerp."""
+    lib, cabi, View, dev = env
+    g = torch.Generator(device="cuda").manual_seed(H + w)
+    pad = torch.randn(1, h, w, 24, generator=g, device="cuda")          # 19 classes at a 24-float pixel pitch
+    t = View(pad.view(-1), 1, h, w, 24).narrow_c(19).ct()
+    out = torch.empty(1, 19, H, W, device=dev)
+    lab = torch.full((1, H, W), 255, dtype=torch.uint8, device=dev)
+    cabi.check(lib.tdn_upsample_logits(C.byref(t), out.data_ptr(), H, W, None))
+    cabi.check(lib.tdn_upsample_argmax(C.byref(t), lab.data_ptr(), H, W, None))
+    torch.cuda.synchronize()
+    ref = F.interpolate(pad[..., :19].permute(0, 3, 1, 2).cpu(), (H, W), mode="bilinear", align_corners=True)
+    assert max_abs(out.cpu(), ref) < 2e-6
+    assert torch.equal(lab.long(), out.max(1)[1])
+
+
 def test_errors_are_reported_not_swallowed(env):
     lib, cabi, View, dev = env
     x = torch.zeros(1, 5, 5, 6, device=dev)
