@@ -171,6 +171,7 @@ template <bool SPLIT>
 __global__ void __launch_bounds__(RS_SEG * RS_CB / 8) psp_rowsum_vec8_kernel(View in, float* __restrict__ rowsum, int seg_len) {
   __shared__ __align__(16) float part[RS_SEG * RS_PITCH];
   __shared__ int first[RS_SEG][4];                   // first range of level l that reaches into segment s
+  __shared__ int seg_lo[12], seg_hi[12];             // segments that meet range r
   const int y = blockIdx.x, b = blockIdx.z;
   const int g = threadIdx.x & 7, s = threadIdx.x >> 3;
   const int c0 = blockIdx.y * RS_CB + g * 8;
@@ -179,6 +180,13 @@ __global__ void __launch_bounds__(RS_SEG * RS_CB / 8) psp_rowsum_vec8_kernel(Vie
   if (threadIdx.x < RS_SEG * 4) {
     const int s2 = threadIdx.x >> 2, l = threadIdx.x & 3;
     first[s2][l] = first_range(l == 0 ? 1 : l == 1 ? 2 : l == 2 ? 3 : 6, W, min(s2 * seg_len, W));
+  } else if (threadIdx.x < RS_SEG * 4 + 12) {
+    const int r = threadIdx.x - RS_SEG * 4;
+    const int l = r < 1 ? 0 : r < 3 ? 1 : r < 6 ? 2 : 3;
+    const int o = l == 0 ? 1 : l == 1 ? 2 : l == 2 ? 3 : 6;
+    const int j = r - (l == 0 ? 0 : l == 1 ? 1 : l == 2 ? 3 : 6);
+    seg_lo[r] = bin_start(j, o, W) / seg_len;
+    seg_hi[r] = min((bin_end(j, o, W) - 1) / seg_len, RS_SEG - 1);
   }
   __syncthreads();
   int endA[4], startB[4];
@@ -251,8 +259,7 @@ __global__ void __launch_bounds__(RS_SEG * RS_CB / 8) psp_rowsum_vec8_kernel(Vie
     int l, j;
     if (r < 1) { l = 0; j = 0; } else if (r < 3) { l = 1; j = r - 1; } else if (r < 6) { l = 2; j = r - 3; } else { l = 3; j = r - 6; }
     float sum = 0.f;
-    for (int s2 = 0; s2 < RS_SEG; ++s2) {
-      if (s2 * seg_len >= W) break;
+    for (int s2 = seg_lo[r]; s2 <= seg_hi[r]; ++s2) {
       const int j0 = first[s2][l];
       if (j == j0) sum += part[s2 * RS_PITCH + (l == 0 ? 0 : 2 * l - 1) * RS_CB + cc];
       else if (l > 0 && j == j0 + 1) sum += part[s2 * RS_PITCH + 2 * l * RS_CB + cc];
@@ -1170,46 +1177,53 @@ __global__ void __launch_bounds__(256) upsample_logits_kernel(View in, float* __
   }
 }
 
-// Same outputs (same bilerp, same operands) for the common >= 3x upsample of a dense map: a block produces ONE output row and
-// first stages the two low-resolution rows it needs in shared memory, transposed to [class][x].  In the kernel above a warp's
-// scalar loads of one class touch ~11 cache lines (19-float pixel pitch): 20 M L1 wavefronts per 1024x2048 frame, 53 us for a
-// 159 MB write that HBM takes in 25 us.  Here the loads are conflict-free shared-memory reads of ~17 consecutive words.
+// Same outputs (same bilerp, same operands) for the common >= 3x upsample: a block produces ONE output row and first
+// stages the two low-resolution rows it needs in shared memory as [class][x][row] (the column behind the last one
+// repeats it, so x + 1 is always readable; its weight is 0 there).  A thread then needs two 8-byte shared-memory loads
+// per class and output pixel -- (top, bottom) at x0 and at x0 + 1 -- and no index arithmetic inside the class loop.
+// History: per-thread global loads (19-float pixel pitch, ~11 cache lines per warp load: 20 M L1 wavefronts per
+// 1024x2048 frame) 53 us; rows staged as [class][x] with three loads per row and register selects 47 us, issue-bound
+// (ncu: 88 % issue slots busy, the selects); HBM needs 25 us for the 159 MB write.
+__device__ __forceinline__ void upsample_stage_rows(const View& in, float2* srow, int pitch, int b, int y0, int y1) {
+  const int C = in.c;
+  const float* g0 = in.p + b * in.sn + y0 * in.sh;
+  const float* g1 = in.p + b * in.sn + y1 * in.sh;
+  const int row_elems = in.w * C;
+  for (int i = threadIdx.x; i < row_elems; i += blockDim.x) {
+    const int x = i / C, c = i - x * C;
+    const float2 v = make_float2(g0[x * in.sw + c], g1[x * in.sw + c]);
+    srow[c * pitch + x] = v;
+    if (x == in.w - 1) srow[c * pitch + x + 1] = v;
+  }
+}
+
 __global__ void __launch_bounds__(256) upsample_logits_row_kernel(View in, float* __restrict__ out, int H, int W, float sy,
                                                                   float sx) {
-  extern __shared__ float srow[];                    // [2][C][in.w + 1]
+  extern __shared__ float2 srow2[];                  // [C][in.w + 1] (top, bottom)
   const int C = in.c, pitch = in.w + 1;
   const int y = blockIdx.x, b = blockIdx.y;
   int y0, y1; float ly;
   src_index(y, sy, in.h, y0, y1, ly);
-  const float* g0 = in.p + b * in.sn + y0 * in.sh;
-  const float* g1 = in.p + b * in.sn + y1 * in.sh;
-  const int row_elems = in.w * C;
-  for (int i = threadIdx.x; i < row_elems; i += 256) {
-    const int x = i / C, c = i - x * C;
-    srow[c * pitch + x] = g0[x * in.sw + c];
-    srow[(C + c) * pitch + x] = g1[x * in.sw + c];
-  }
+  upsample_stage_rows(in, srow2, pitch, b, y0, y1);
   __syncthreads();
   const int W4 = W >> 2;
   const long long plane = (long long)H * W;
   for (int xq = threadIdx.x; xq < W4; xq += 256) {
-    int x0[4], x1[4]; float lx[4];
+    const float2* p[4]; float lx[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) src_index(xq * 4 + j, sx, in.w, x0[j], x1[j], lx[j]);
-    const int xa = x0[0], xb = min(xa + 1, in.w - 1), xc = min(xa + 2, in.w - 1);
+    for (int j = 0; j < 4; ++j) {
+      int x0, x1;
+      src_index(xq * 4 + j, sx, in.w, x0, x1, lx[j]);
+      p[j] = srow2 + x0;
+    }
     float* o = out + (long long)b * C * plane + (long long)y * W + xq * 4;
     for (int c = 0; c < C; ++c) {
-      const float* t = srow + c * pitch;
-      const float* u = srow + (C + c) * pitch;
-      const float t0 = t[xa], t1 = t[xb], t2 = t[xc];
-      const float u0 = u[xa], u1 = u[xb], u2 = u[xc];
       float v[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int d0 = x0[j] - xa, d1 = x1[j] - xa;            // 0..1 and 0..2
-        const float ta = d0 == 0 ? t0 : t1, tb = d1 == 0 ? t0 : (d1 == 1 ? t1 : t2);
-        const float ua = d0 == 0 ? u0 : u1, ub = d1 == 0 ? u0 : (d1 == 1 ? u1 : u2);
-        v[j] = bilerp(ta, tb, ua, ub, lx[j], ly);
+        const float2 a = p[j][0], d = p[j][1];       // (top, bottom) at x0 and at x0 + 1 (= x1, or weight 0)
+        v[j] = bilerp(a.x, d.x, a.y, d.y, lx[j], ly);
+        p[j] += pitch;
       }
       __stcs(reinterpret_cast<float4*>(o + c * plane), make_float4(v[0], v[1], v[2], v[3]));
     }
@@ -1258,45 +1272,35 @@ __global__ void __launch_bounds__(256) upsample_argmax_kernel(View in, uint8_t* 
 }
 
 // Shared-memory version of the arg-max upsampler, built like upsample_logits_row_kernel (one output row per block, the two
-// low-resolution rows staged as [class][x]) with the identical bilerp on identical operands: labels == arg-max of the logits
-// either logits kernel writes.  No 159 MB logits write, and the per-class loads are conflict-free shared-memory reads instead
-// of 16 scattered 4-byte global loads per class and thread.
+// low-resolution rows staged as [class][x][row]) with the identical bilerp on identical operands: labels == arg-max of the
+// logits either logits kernel writes.  No 159 MB logits write.
 __global__ void __launch_bounds__(256) upsample_argmax_row_kernel(View in, uint8_t* __restrict__ labels, int H, int W,
                                                                   float sy, float sx) {
-  extern __shared__ float srow[];                    // [2][C][in.w + 1]
+  extern __shared__ float2 srow2[];                  // [C][in.w + 1] (top, bottom)
   const int C = in.c, pitch = in.w + 1;
   const int y = blockIdx.x, b = blockIdx.y;
   int y0, y1; float ly;
   src_index(y, sy, in.h, y0, y1, ly);
-  const float* g0 = in.p + b * in.sn + y0 * in.sh;
-  const float* g1 = in.p + b * in.sn + y1 * in.sh;
-  const int row_elems = in.w * C;
-  for (int i = threadIdx.x; i < row_elems; i += 256) {
-    const int x = i / C, c = i - x * C;
-    srow[c * pitch + x] = g0[x * in.sw + c];
-    srow[(C + c) * pitch + x] = g1[x * in.sw + c];
-  }
+  upsample_stage_rows(in, srow2, pitch, b, y0, y1);
   __syncthreads();
   const int W4 = W >> 2;
   for (int xq = threadIdx.x; xq < W4; xq += 256) {
-    int x0[4], x1[4]; float lx[4];
+    const float2* p[4]; float lx[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) src_index(xq * 4 + j, sx, in.w, x0[j], x1[j], lx[j]);
-    const int xa = x0[0], xb = min(xa + 1, in.w - 1), xc = min(xa + 2, in.w - 1);
+    for (int j = 0; j < 4; ++j) {
+      int x0, x1;
+      src_index(xq * 4 + j, sx, in.w, x0, x1, lx[j]);
+      p[j] = srow2 + x0;
+    }
     float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
     int arg[4] = {0, 0, 0, 0};
     for (int c = 0; c < C; ++c) {
-      const float* t = srow + c * pitch;
-      const float* u = srow + (C + c) * pitch;
-      const float t0 = t[xa], t1 = t[xb], t2 = t[xc];
-      const float u0 = u[xa], u1 = u[xb], u2 = u[xc];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int d0 = x0[j] - xa, d1 = x1[j] - xa;            // 0..1 and 0..2
-        const float ta = d0 == 0 ? t0 : t1, tb = d1 == 0 ? t0 : (d1 == 1 ? t1 : t2);
-        const float ua = d0 == 0 ? u0 : u1, ub = d1 == 0 ? u0 : (d1 == 1 ? u1 : u2);
-        const float v = bilerp(ta, tb, ua, ub, lx[j], ly);
+        const float2 a = p[j][0], d = p[j][1];
+        const float v = bilerp(a.x, d.x, a.y, d.y, lx[j], ly);
         if (v > best[j]) { best[j] = v; arg[j] = c; }
+        p[j] += pitch;
       }
     }
     *reinterpret_cast<uchar4*>(labels + ((long long)b * H + y) * W + xq * 4) =

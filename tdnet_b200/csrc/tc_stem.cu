@@ -19,11 +19,12 @@
 //   warps 1-8   epilogue TMEM -> BN + ReLU (0 outside the conv map: cannot change a max of ReLU outputs)
 //                        -> ring of 4 fp32 conv rows in shared memory (16-byte quads XOR-swizzled by column);
 //                        two warps per TMEM lane quarter, 32 channels each
-//   warps 13-16 pool     3x3/2 max over three conv rows -> pooled row in global memory (F32 or SPLIT16)
+//   warps 13-20 pool     3x3/2 max over three conv rows -> pooled row in global memory (F32 or SPLIT16)
 // all hand-offs through mbarriers; the 512x1024x64 pre-pool map never leaves the SM.
 // ncu of the round-1 layout (4 epilogue warps of 64 channels, 3 conv-row slots, loads issued pixel by pixel): 5.4 K
 // cycles per conv row against 2.0 K of MMA time -- first the loader (one DRAM round trip per pixel), then the epilogue
-// warps (700 instructions per row on one warp per scheduler, and blocked while the pool holds all three row slots).
+// warps (700 instructions per row on one warp per scheduler, and blocked while the pool holds all three row slots),
+// then the four pool warps (busy 84 % of the time): eight now.
 #include "tc_common.cuh"
 
 namespace tdn {
@@ -41,8 +42,8 @@ constexpr int TS_CROW_BYTES = TS_M * 64 * 4;           // one conv row, fp32
 constexpr int TS_CROWS = 4;                            // three feed a pooled row, the fourth is being written
 constexpr int TS_EPI_WARPS = 8;                        // warps 1-8
 constexpr int TS_LOAD_WARP0 = 9, TS_POOL_WARP0 = 13;   // warp 0 MMA, warps 1-8 epilogue
-constexpr int TS_LOAD_THREADS = 128, TS_POOL_THREADS = 128;
-constexpr int TS_THREADS = 32 * 17;
+constexpr int TS_LOAD_THREADS = 128, TS_POOL_THREADS = 256;
+constexpr int TS_THREADS = 32 * 21;
 constexpr int TS_TMEM_COLS = 128;
 constexpr int TS_SMEM_BYTES = 2 * TS_W_PLANE + 2 * TS_RING_PLANE + TS_CROWS * TS_CROW_BYTES + 512 + 256 + 128;
 static_assert(TS_SMEM_BYTES <= 232448, "stem kernel exceeds the 227 KB shared-memory limit");
