@@ -1189,11 +1189,28 @@ __device__ __forceinline__ void upsample_stage_rows(const View& in, float2* srow
   const float* g0 = in.p + b * in.sn + y0 * in.sh;
   const float* g1 = in.p + b * in.sn + y1 * in.sh;
   const int row_elems = in.w * C;
-  for (int i = threadIdx.x; i < row_elems; i += blockDim.x) {
-    const int x = i / C, c = i - x * C;
-    const float2 v = make_float2(g0[x * in.sw + c], g1[x * in.sw + c]);
-    srow[c * pitch + x] = v;
-    if (x == in.w - 1) srow[c * pitch + x + 1] = v;
+  constexpr int UN = 4;                                // elements whose (two) loads are issued before the first store
+  for (int i0 = threadIdx.x; i0 < row_elems; i0 += blockDim.x * UN) {
+    float2 v[UN];
+    int dst[UN];
+#pragma unroll
+    for (int k = 0; k < UN; ++k) {
+      const int i = i0 + k * blockDim.x;
+      dst[k] = -1;
+      if (i < row_elems) {
+        const int x = i / C, c = i - x * C;
+        v[k] = make_float2(__ldg(g0 + x * in.sw + c), __ldg(g1 + x * in.sw + c));
+        dst[k] = (c * pitch + x) | (x == in.w - 1 ? 0x40000000 : 0);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < UN; ++k) {
+      if (dst[k] >= 0) {
+        const int d = dst[k] & 0x3fffffff;
+        srow[d] = v[k];
+        if (dst[k] & 0x40000000) srow[d + 1] = v[k];
+      }
+    }
   }
 }
 

@@ -13,18 +13,19 @@
 // The weights sit in shared memory for the whole kernel as [chunk 28][cout 64][8] fp16 per plane.
 //
 // One CTA walks down a strip of 126 conv columns (63 pooled columns) for 2*PB+1 conv rows (PB pooled rows):
-//   warps 9-12  loader   image rows (2 per conv row) -> split fp16 -> ring of 5 row pairs (the next pair's global
+//   warps 9-16  loader   image rows (2 per conv row) -> split fp16 -> ring of 5 row pairs (the next pair's global
 //                        loads are in flight in registers while the current one is converted)
 //   warp  0     MMA      42 MMAs per conv row into one of two 64-column TMEM accumulators
 //   warps 1-8   epilogue TMEM -> BN + ReLU (0 outside the conv map: cannot change a max of ReLU outputs)
 //                        -> ring of 4 fp32 conv rows in shared memory (16-byte quads XOR-swizzled by column);
 //                        two warps per TMEM lane quarter, 32 channels each
-//   warps 13-20 pool     3x3/2 max over three conv rows -> pooled row in global memory (F32 or SPLIT16)
+//   warps 17-24 pool     3x3/2 max over three conv rows -> pooled row in global memory (F32 or SPLIT16)
 // all hand-offs through mbarriers; the 512x1024x64 pre-pool map never leaves the SM.
 // ncu of the round-1 layout (4 epilogue warps of 64 channels, 3 conv-row slots, loads issued pixel by pixel): 5.4 K
 // cycles per conv row against 2.0 K of MMA time -- first the loader (one DRAM round trip per pixel), then the epilogue
 // warps (700 instructions per row on one warp per scheduler, and blocked while the pool holds all three row slots),
-// then the four pool warps (busy 84 % of the time): eight now.
+// then the four pool warps (busy 84 % of the time) and the four loader warps (400 instructions per row pair at one warp
+// per scheduler): eight of each now, 25 warps in all.
 #include "tc_common.cuh"
 
 namespace tdn {
@@ -41,9 +42,9 @@ constexpr int TS_W_PLANE = TS_W_CHUNKS * 64 * 16;      // 28 KiB per plane
 constexpr int TS_CROW_BYTES = TS_M * 64 * 4;           // one conv row, fp32
 constexpr int TS_CROWS = 4;                            // three feed a pooled row, the fourth is being written
 constexpr int TS_EPI_WARPS = 8;                        // warps 1-8
-constexpr int TS_LOAD_WARP0 = 9, TS_POOL_WARP0 = 13;   // warp 0 MMA, warps 1-8 epilogue
-constexpr int TS_LOAD_THREADS = 128, TS_POOL_THREADS = 256;
-constexpr int TS_THREADS = 32 * 21;
+constexpr int TS_LOAD_WARP0 = 9, TS_POOL_WARP0 = 17;   // warp 0 MMA, warps 1-8 epilogue, 9-16 loader, 17-24 pool
+constexpr int TS_LOAD_THREADS = 256, TS_POOL_THREADS = 256;
+constexpr int TS_THREADS = 32 * 25;
 constexpr int TS_TMEM_COLS = 128;
 constexpr int TS_SMEM_BYTES = 2 * TS_W_PLANE + 2 * TS_RING_PLANE + TS_CROWS * TS_CROW_BYTES + 512 + 256 + 128;
 static_assert(TS_SMEM_BYTES <= 232448, "stem kernel exceeds the 227 KB shared-memory limit");
@@ -192,86 +193,82 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_stem_kernel(const TcStemPara
     // before row pair u is converted and stored, so a thread always has one row pair of loads in flight.  (With the
     // loads issued pixel by pixel the loader was one DRAM round trip per pixel and row: 6 dependent trips = ~5 K
     // cycles per conv row, the bound of the whole kernel at 128 us per 1024x2048 frame.)
+    // 256 threads: thread (rr, pl) owns pixels pl, pl + 128, pl + 256 of row rr of every row pair.
     const int tl = tid - TS_LOAD_WARP0 * 32;
+    const int rr = tl >> 7, pl = tl & 127;
     const int NP = NR + 3;
     const float* img = p.img + (long long)b * 3 * p.H * p.W;
     const uint8_t* img8 = p.img_u8 + (long long)b * 3 * p.H * p.W;
-    const long long plane = (long long)p.H * p.W;
-    constexpr int PXI = (TS_IPX + TS_LOAD_THREADS - 1) / TS_LOAD_THREADS;     // pixels per thread and row (3)
+    const int plane = p.H * p.W;                        // < 2^31 / 3 for any image this kernel is given (host check)
+    constexpr int PXI = (TS_IPX + 127) / 128;           // pixels per thread and row (3)
+    constexpr uint32_t PAD = 0xffffffffu;               // uint8 frames: "outside the image" (byte values are <= 255)
     bool out_of_range = false;
-    // raw[rr][it][c]: the fp32 bit pattern (NCHW image) or the byte value (uint8 frame) of channel c
-    auto issue = [&](int u, uint32_t (&raw)[2][PXI][3], uint32_t& okmask) {
-      okmask = 0;
+    // everything that does not depend on the row pair: image column of this thread's pixels
+    int ixs[PXI];
+    bool colok[PXI];
 #pragma unroll
-      for (int rr = 0; rr < 2; ++rr) {
-        const int iy = iy0 + 2 * u + rr;
-        const bool rowok = iy >= 0 && iy < p.H;
+    for (int it = 0; it < PXI; ++it) {
+      const int px = pl + it * 128;
+      ixs[it] = ix0 + px;
+      colok[it] = ixs[it] >= 0 && ixs[it] < p.W && px < TS_IPX_USED;
+    }
+    // raw[it][c]: the fp32 bit pattern (NCHW image; 0 = the zero padding) or the byte value (uint8 frame; PAD = padding)
+    auto issue = [&](int u, uint32_t (&raw)[PXI][3]) {
+      const int iy = iy0 + 2 * u + rr;
+      const bool rowok = iy >= 0 && iy < p.H;
+      const int rowoff = iy * p.W;
 #pragma unroll
-        for (int it = 0; it < PXI; ++it) {
-          const int px = tl + it * TS_LOAD_THREADS;
-          const int ix = ix0 + px;
-          const bool ok = rowok && ix >= 0 && ix < p.W && px < TS_IPX_USED;
-          raw[rr][it][0] = raw[rr][it][1] = raw[rr][it][2] = 0u;
-          if (ok) {
-            okmask |= 1u << (rr * PXI + it);
-            if (U8) {
-              const uint8_t* q = img8 + ((long long)iy * p.W + ix) * 3;
-              raw[rr][it][0] = __ldg(q); raw[rr][it][1] = __ldg(q + 1); raw[rr][it][2] = __ldg(q + 2);
-            } else {
-              const float* q = img + (long long)iy * p.W + ix;
-              raw[rr][it][0] = __float_as_uint(__ldg(q));
-              raw[rr][it][1] = __float_as_uint(__ldg(q + plane));
-              raw[rr][it][2] = __float_as_uint(__ldg(q + 2 * plane));
-            }
+      for (int it = 0; it < PXI; ++it) {
+        raw[it][0] = raw[it][1] = raw[it][2] = U8 ? PAD : 0u;
+        if (rowok && colok[it]) {
+          const int idx = rowoff + ixs[it];
+          if (U8) {
+            const uint8_t* q = img8 + (long long)idx * 3;
+            raw[it][0] = __ldg(q); raw[it][1] = __ldg(q + 1); raw[it][2] = __ldg(q + 2);
+          } else {
+            raw[it][0] = __float_as_uint(__ldg(img + idx));
+            raw[it][1] = __float_as_uint(__ldg(img + idx + plane));
+            raw[it][2] = __float_as_uint(__ldg(img + idx + 2 * plane));
           }
         }
       }
     };
-    uint32_t cur[2][PXI][3], nxt[2][PXI][3];
-    uint32_t cur_ok = 0, nxt_ok = 0;
-    issue(0, cur, cur_ok);
+    uint32_t cur[PXI][3], nxt[PXI][3];
+    issue(0, cur);
     for (int u = 0; u < NP; ++u) {
       const int slot = u % TS_DP;
-      if (u + 1 < NP) issue(u + 1, nxt, nxt_ok);
+      if (u + 1 < NP) issue(u + 1, nxt);
       mbar_wait(&img_empty[slot], ((u / TS_DP) & 1) ^ 1);
+      uint8_t* dst_hi = s_ring + (slot * 2 + rr) * TS_ROW_BYTES + pl * 8;
+      uint8_t* dst_lo = dst_hi + TS_RING_PLANE;
 #pragma unroll
-      for (int rr = 0; rr < 2; ++rr) {
-        uint8_t* dst_hi = s_ring + (slot * 2 + rr) * TS_ROW_BYTES;
-        uint8_t* dst_lo = dst_hi + TS_RING_PLANE;
-#pragma unroll
-        for (int it = 0; it < PXI; ++it) {
-          const int px = tl + it * TS_LOAD_THREADS;
-          if (px < TS_IPX) {
-            float c0 = 0.f, c1 = 0.f, c2 = 0.f;        // zero padding applies to the normalised tensor
-            if (cur_ok >> (rr * PXI + it) & 1) {
-              if (U8) {
-                c0 = __ldg(p.lut + cur[rr][it][0]);
-                c1 = __ldg(p.lut + 256 + cur[rr][it][1]);
-                c2 = __ldg(p.lut + 512 + cur[rr][it][2]);
-              } else {
-                c0 = __uint_as_float(cur[rr][it][0]);
-                c1 = __uint_as_float(cur[rr][it][1]);
-                c2 = __uint_as_float(cur[rr][it][2]);
-              }
-              out_of_range |= fmaxf(fabsf(c0), fmaxf(fabsf(c1), fabsf(c2))) > 60000.f;
-            }
-            __half2 h[2], l[2];
-            split_f32x2(c0, c1, h[0], l[0]);
-            split_f32x2(c2, 0.f, h[1], l[1]);
-            *reinterpret_cast<uint2*>(dst_hi + px * 8) = *reinterpret_cast<const uint2*>(h);
-            *reinterpret_cast<uint2*>(dst_lo + px * 8) = *reinterpret_cast<const uint2*>(l);
+      for (int it = 0; it < PXI; ++it) {
+        if (pl + it * 128 < TS_IPX) {
+          float c0, c1, c2;                              // zero padding applies to the normalised tensor
+          if (U8) {
+            const bool in = cur[it][0] != PAD;
+            c0 = in ? __ldg(p.lut + cur[it][0]) : 0.f;
+            c1 = in ? __ldg(p.lut + 256 + cur[it][1]) : 0.f;
+            c2 = in ? __ldg(p.lut + 512 + cur[it][2]) : 0.f;
+          } else {
+            c0 = __uint_as_float(cur[it][0]);
+            c1 = __uint_as_float(cur[it][1]);
+            c2 = __uint_as_float(cur[it][2]);
           }
+          out_of_range |= fmaxf(fabsf(c0), fmaxf(fabsf(c1), fabsf(c2))) > 60000.f;
+          __half2 h[2], l[2];
+          split_f32x2(c0, c1, h[0], l[0]);
+          split_f32x2(c2, 0.f, h[1], l[1]);
+          *reinterpret_cast<uint2*>(dst_hi + it * 128 * 8) = *reinterpret_cast<const uint2*>(h);
+          *reinterpret_cast<uint2*>(dst_lo + it * 128 * 8) = *reinterpret_cast<const uint2*>(l);
         }
       }
       fence_proxy_async_smem();
       mbar_arrive(&img_full[slot]);
 #pragma unroll
-      for (int rr = 0; rr < 2; ++rr)
+      for (int it = 0; it < PXI; ++it)
 #pragma unroll
-        for (int it = 0; it < PXI; ++it)
-#pragma unroll
-          for (int c = 0; c < 3; ++c) cur[rr][it][c] = nxt[rr][it][c];
-      cur_ok = nxt_ok;
+        for (int c = 0; c < 3; ++c) cur[it][c] = nxt[it][c];
     }
     if (out_of_range && p.range_flag) *reinterpret_cast<volatile int*>(p.range_flag) = 1;   // idempotent store: the flag may live in host-mapped memory
   } else {
@@ -332,6 +329,7 @@ int stem_conv_pool_tc(const float* nchw, const uint8_t* hwc_u8, const float* lut
               "stem_tc: exactly one of the fp32 NCHW image and the uint8 HWC frame must be given");
   TDN_REQUIRE((nchw || lut) && weight_tc && scale && bias, TDN_ERR_INVALID, "stem_tc: null pointer");
   TDN_REQUIRE(n >= 1 && h >= 1 && w >= 1, TDN_ERR_INVALID, "stem_tc: empty image");
+  TDN_REQUIRE((long long)h * w * 3 < (1ll << 31), TDN_ERR_UNSUPPORTED, "stem_tc: image planes beyond 32-bit indexing");
   TDN_REQUIRE((reinterpret_cast<uintptr_t>(weight_tc) & 15) == 0, TDN_ERR_INVALID, "stem_tc: weights must be 16-byte aligned");
   int rc;
   if ((rc = check_tensor(out, "stem_tc.out"))) return rc;
