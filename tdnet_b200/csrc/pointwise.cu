@@ -290,7 +290,11 @@ __global__ void psp_rowsum_generic_kernel(View in, float* __restrict__ rowsum) {
   }
 }
 
+// Pass 2.  A block per bin; BS_GROUPS thread groups walk interleaved rows of the bin (the 1x1 bin sums all H rows: one
+// serial walk per channel was 14 us of pure load latency) and their partial sums are added in group order (fixed order).
+constexpr int BS_GROUPS = 4;
 __global__ void psp_binsum_kernel(const float* __restrict__ rowsum, View out, int H, int W) {
+  extern __shared__ float bs_part[];                 // [BS_GROUPS - 1][C]
   const int bin = blockIdx.x, b = blockIdx.y;
   int o, local, roff;
   if (bin < 1) { o = 1; local = bin; roff = 0; }
@@ -301,13 +305,25 @@ __global__ void psp_binsum_kernel(const float* __restrict__ rowsum, View out, in
   const int y0 = bin_start(i, o, H), y1 = bin_end(i, o, H);
   const int x0 = bin_start(j, o, W), x1 = bin_end(j, o, W);
   const float inv = 1.f / (float)((y1 - y0) * (x1 - x0));
-  for (int c = threadIdx.x; c < out.c; c += blockDim.x) {
+  const int C = out.c;
+  const int per = blockDim.x / BS_GROUPS;            // threads per group
+  const int grp = threadIdx.x / per, t = threadIdx.x - grp * per;
+  for (int c0 = 0; c0 < C; c0 += per) {
+    const int c = c0 + t;
     float s = 0.f;
-    for (int y = y0; y < y1; ++y)
+    if (c < C) {
+#pragma unroll 4
+      for (int y = y0 + grp; y < y1; y += BS_GROUPS)
+        s += rowsum[(((long long)(b * H + y) * PSP_PARTS) * 12 + roff + j) * C + c];
+      if (grp > 0) bs_part[(grp - 1) * C + c] = s;
+    }
+    __syncthreads();
+    if (grp == 0 && c < C) {
 #pragma unroll
-      for (int part = 0; part < PSP_PARTS; ++part)
-        s += rowsum[(((long long)(b * H + y) * PSP_PARTS + part) * 12 + roff + j) * out.c + c];
-    out.p[b * out.sn + bin * out.sw + c] = s * inv;
+      for (int g2 = 0; g2 < BS_GROUPS - 1; ++g2) s += bs_part[g2 * C + c];
+      out.p[b * out.sn + bin * out.sw + c] = s * inv;
+    }
+    __syncthreads();
   }
 }
 
@@ -339,7 +355,8 @@ int psp_pool(const tdn_tensor* in, const tdn_tensor* out, float* workspace, size
     psp_rowsum_generic_kernel<<<dim3(in->h, in->n), threads, 0, stream>>>(make_view(*in), workspace);
   }
   TDN_LAUNCH_OK();
-  psp_binsum_kernel<<<dim3(50, in->n), threads, 0, stream>>>(workspace, make_view(*out), in->h, in->w);
+  psp_binsum_kernel<<<dim3(50, in->n), 512, (BS_GROUPS - 1) * in->c * sizeof(float), stream>>>(workspace, make_view(*out),
+                                                                                              in->h, in->w);
   TDN_LAUNCH_OK();
   return TDN_OK;
 }
