@@ -152,7 +152,11 @@ enum {
   TDN_TC_AUTO = 0,
   TDN_TC_BASE = 1, /* one CTA per 128-pixel x 64/128-channel tile, one A box per filter tap */
   TDN_TC_HALO = 2, /* 3x3 stride-1 dilation<=2: one halo-region load per channel block */
-  TDN_TC_PAIR = 3  /* cout % 128 == 0, shared weights: 2-CTA clusters (tcgen05 cta_group::2), M 256 x N 256/128 */
+  TDN_TC_PAIR = 3, /* cout % 128 == 0, shared weights: 2-CTA clusters (tcgen05 cta_group::2), M 256 x N 256/128 */
+  /* Two measured alternatives of the pair kernel (cout % 256 == 0), bit-identical to it, never picked by TDN_TC_AUTO
+     (both leave the frame rate unchanged): */
+  TDN_TC_PAIR_TAIL = 4, /* full rounds as N = 256 pair tiles, the ragged last round as N = 128 pair tiles (second launch) */
+  TDN_TC_PAIR_QUAD = 5  /* clusters of two pairs that share the weight tile by TMA multicast */
 };
 
 int tdn_conv2d_tc(const tdn_tc_conv_desc* desc, void* stream);

@@ -523,7 +523,8 @@ int attention_tc(const tdn_attention_desc* d, cudaStream_t stream, int* count_on
     p.r_bs = r.stride_n; p.r_ld = r.stride_w;
   }
   p.range_flag = d->range_flag;
-  p.fast = (d->flags & TDN_TC_FLAG_FAST) ? 1 : 0;
+  p.fast = (d->flags & TDN_TC_FLAG_FAST) ? 3 : 0;   // bit 0: single-product S, bit 1: single-product P.V' (the TS kernels test them separately)
+  if (const char* dbg = getenv("TDNET_ATTN_DEBUG")) p.fast |= atoi(dbg) & 3;   // probes only: ablation of either product group
 
   CUtensorMap mq_h, mq_l, mk_h, mk_l, mv_h, mv_l;
   int rc;
@@ -554,6 +555,7 @@ int attention_tc(const tdn_attention_desc* d, cudaStream_t stream, int* count_on
   // 0 = the kernels of this file (P through shared memory), kept as the yardstick.  TDNET_ATTN_TS selects.
   // (read on every call: the probes and tests flip it inside one process)
   // TDNET_ATTN_TS = 3: the TS kernels with the Q tile in tensor memory as well (tc_attn_ts.cu, "QT").
+  // TDNET_ATTN_TS = 4: tc_attn_s128.cu -- the TS kernel with 128-key S MMAs in pass 2 (one S buffer, two P slots).
   const char* ts_env = getenv("TDNET_ATTN_TS");
   const int ts_variant = ts_env ? atoi(ts_env) : ATTN_DEFAULT_VARIANT;
   const bool use_ts = ts_variant != 0;
@@ -572,6 +574,7 @@ int attention_tc(const tdn_attention_desc* d, cudaStream_t stream, int* count_on
     if (use_ts) {
       AttnParams q = pp;
       q.per_cta = ceil_div(q.items_a, grid);     // contiguous blocks: the d_v slices of a query tile meet on one CTA
+      if (ts_variant == 4) return attention_s128_launch(dvt, grid, stream, short_launch, mq_h, mq_l, mk_h, mk_l, mv_h, mv_l, q);
       return attention_ts_launch(dvt, ts_variant == 3, grid, stream, short_launch, mq_h, mq_l, mk_h, mk_l, mv_h, mv_l, q);
     }
     if (dvt == 256)

@@ -59,7 +59,7 @@ struct AttnParams {
   const float* res_f32;
   long long r_bs, r_ld;
   int* range_flag;
-  int fast;                 // TDN_TC_FLAG_FAST: Qhi.Khi^T and Phi.V'hi^T only (opt-in, not fp32-faithful)
+  int fast;                 // TDN_TC_FLAG_FAST (3): bit 0 Qhi.Khi^T only, bit 1 Phi.V'hi^T only (opt-in, not fp32-faithful)
 };
 
 
@@ -104,5 +104,10 @@ __device__ __forceinline__ bool attn_shares_rowmax(const AttnParams& p, int item
 cudaError_t attention_ts_launch(int dvt, bool qt, int grid, cudaStream_t stream, bool short_launch, const CUtensorMap& mq_h,
                                 const CUtensorMap& mq_l, const CUtensorMap& mk_h, const CUtensorMap& mk_l,
                                 const CUtensorMap& mv_h, const CUtensorMap& mv_l, const AttnParams& p);
+
+// tc_attn_s128.cu: the TS kernel with 128-key S MMAs in pass 2 (one S buffer of 128 TMEM columns, two P slots).
+cudaError_t attention_s128_launch(int dvt, int grid, cudaStream_t stream, bool short_launch, const CUtensorMap& mq_h,
+                                  const CUtensorMap& mq_l, const CUtensorMap& mk_h, const CUtensorMap& mk_l,
+                                  const CUtensorMap& mv_h, const CUtensorMap& mv_l, const AttnParams& p);
 
 }  // namespace tdn

@@ -240,14 +240,14 @@ tc_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_const
             const uint64_t a_l = umma_desc_k_sw128(q_lo + k * 32), b_l = umma_desc_k_sw128(k_lo + k * 32);
             if (QT) {
               const uint32_t t_h = tmem_base + ATS_QT_COL + k * 8, t_l = t_h + 32;   // 8 columns of fp16 pairs per K16 step
-              if (p.fast) {
+              if (p.fast & 1) {
                 umma_f16_ts(d, t_h, b_h, idesc_s, k != 0);
               } else {
                 umma_f16_ts(d, t_h, b_l, idesc_s, k != 0);
                 umma_f16_ts(d, t_l, b_h, idesc_s, 1);
                 umma_f16_ts(d, t_h, b_h, idesc_s, 1);
               }
-            } else if (p.fast) {
+            } else if (p.fast & 1) {
               umma_f16(d, a_h, b_h, idesc_s, k != 0);
             } else {
               umma_f16(d, a_h, b_l, idesc_s, k != 0);
@@ -289,7 +289,7 @@ tc_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_const
               // lo pairs 16 columns further
               const uint32_t a_h = p_base + (k >> 1) * 32 + (k & 1) * 8, a_l = a_h + 16;
               const uint64_t b_h = umma_desc_k_sw128(v_hi + k * 32), b_l = umma_desc_k_sw128(v_lo + k * 32);
-              if (p.fast) {
+              if (p.fast & 2) {
                 umma_f16_ts(d, a_h, b_h, idesc_o, (kt | k) != 0);
               } else {
                 umma_f16_ts(d, a_h, b_l, idesc_o, (kt | k) != 0);

@@ -23,7 +23,7 @@ struct TcParams {
   int Cout, Cin;
   int taps_h, taps_w, dil, conv_stride;
   int n_tiles_n, num_tiles;
-  int tile_begin;        // single-CTA kernel: first tile of this launch (tiles [tile_begin, num_tiles))
+  int tile_begin;        // first tile of this launch (tiles [tile_begin, num_tiles))
   int chunk_kb;          // K blocks accumulated inside TMEM before the fp32 register accumulation
   int w_batched;
   const float* scale;
@@ -41,7 +41,22 @@ struct TcParams {
   long long rsn, rsh, rsw;
   int* range_flag;
   int fast;              // TDN_TC_FLAG_FAST: issue only the hi x hi product of every K step
+  int quad;              // tc_conv_pair.cu: clusters of TWO pairs that share the weight tile (see pair_tile_coords)
 };
+
+// Pair tile index -> (output-channel tile, row of pair tiles = 256 pixels).  Plain pair launch: the channel tiles of a row
+// are consecutive.  Quad launch (clusters of two pairs, p.quad): consecutive indices 2s, 2s+1 are the two pairs of a
+// cluster working on "super tile" s -- the SAME channel tile of two consecutive rows, so that they can share its weights.
+__device__ __forceinline__ void pair_tile_coords(const TcParams& p, int tile, int& nt, int& mrow) {
+  if (p.quad) {
+    const int st = tile >> 1;
+    nt = st % p.n_tiles_n;
+    mrow = 2 * (st / p.n_tiles_n) + (tile & 1);
+  } else {
+    nt = tile % p.n_tiles_n;
+    mrow = tile / p.n_tiles_n;
+  }
+}
 
 // Launch of a persistent tcgen05 kernel, optionally with programmatic dependent launch: the kernel's setup (barrier
 // init, TMEM allocation, tensor-map prefetch) overlaps the tail of the previous kernel in the stream; every such kernel
@@ -107,12 +122,15 @@ __device__ __forceinline__ void tc_epilogue_role(const TcParams& p, uint32_t tme
     int as = 0;
     uint32_t aphase = 0;
     bool out_of_range = false;
-    const int tile_first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x + p.tile_begin;
+    const int tile_first = (PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x) + p.tile_begin;
     const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     for (int tile = tile_first; tile < p.num_tiles; tile += tile_step) {
-      const int nt = tile % p.n_tiles_n;
+      int nt = tile % p.n_tiles_n;
       int mt = tile / p.n_tiles_n;
-      if (PAIR) mt = 2 * mt + (int)(blockIdx.x & 1);
+      if (PAIR) {
+        pair_tile_coords(p, tile, nt, mt);
+        mt = 2 * mt + (int)(blockIdx.x & 1);
+      }
       const int tx = mt % p.tiles_w;
       mt /= p.tiles_w;
       const int ty = mt % p.tiles_h;

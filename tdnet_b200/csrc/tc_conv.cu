@@ -249,8 +249,9 @@ static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUt
 
 int conv2d_tc_halo(const tdn_tc_conv_desc* d, TcParams p, int num_sms, int chunk_kb, cudaStream_t stream);
 int conv2d_tc_pair(const tdn_tc_conv_desc* d, TcParams p, int block_n, int num_sms, int max_pair_tiles,
-                   cudaStream_t stream);
+                   cudaStream_t stream, int first_pair_row = 0, bool quad = false);
 int conv2d_tc_pair_clusters(int block_n, int num_sms, int* clusters);
+int conv2d_tc_quad_clusters(int num_sms, int* clusters);
 
 int conv2d_tc(const tdn_tc_conv_desc* d, cudaStream_t stream) {
   const tdn_tensor& in = d->in;
@@ -363,8 +364,11 @@ int conv2d_tc(const tdn_tc_conv_desc* d, cudaStream_t stream) {
     }
     const bool pair_ok = !d->weight_batched && d->cout % 128 == 0;
     const bool halo_ok = d->kh == 3 && d->kw == 3 && cs == 1 && d->dilation <= 2 && !d->weight_batched && in.w >= 8;
-    TDN_REQUIRE(d->variant >= TDN_TC_AUTO && d->variant <= TDN_TC_PAIR, TDN_ERR_INVALID, "conv2d_tc: unknown variant");
-    TDN_REQUIRE(d->variant != TDN_TC_PAIR || pair_ok, TDN_ERR_UNSUPPORTED,
+    TDN_REQUIRE(d->variant >= TDN_TC_AUTO && d->variant <= TDN_TC_PAIR_QUAD, TDN_ERR_INVALID, "conv2d_tc: unknown variant");
+    const bool pair_forced = d->variant == TDN_TC_PAIR || d->variant == TDN_TC_PAIR_TAIL || d->variant == TDN_TC_PAIR_QUAD;
+    TDN_REQUIRE(d->variant < TDN_TC_PAIR_TAIL || (pair_ok && d->cout % 256 == 0), TDN_ERR_UNSUPPORTED,
+                "conv2d_tc: the tail / quad variants of the CTA-pair kernel need cout %% 256 == 0 and shared weights");
+    TDN_REQUIRE(!pair_forced || pair_ok, TDN_ERR_UNSUPPORTED,
                 "conv2d_tc: the CTA-pair kernel needs cout %% 128 == 0 and shared weights");
     TDN_REQUIRE(d->variant != TDN_TC_HALO || halo_ok, TDN_ERR_UNSUPPORTED,
                 "conv2d_tc: the halo kernel needs a 3x3 stride-1 convolution with dilation <= 2");
@@ -377,38 +381,50 @@ int conv2d_tc(const tdn_tc_conv_desc* d, cudaStream_t stream) {
     const long long pair_tiles256 = ((long long)in.n * p.tiles_h * p.tiles_w + 1) / 2 * (d->cout / 256);
     const bool pair_auto = d->cout % 256 == 0 && (pair_env > 0 || (pair_env < 0 && num_kb_host >= 16 &&
                                                                     2 * pair_tiles256 >= g_num_sms));
-    if (d->variant == TDN_TC_PAIR || (d->variant == TDN_TC_AUTO && pair_ok && pair_auto)) {
+    if (pair_forced || (d->variant == TDN_TC_AUTO && pair_ok && pair_auto)) {
       const int pair_n = d->cout % 256 == 0 ? 256 : 128;
-      // Wave quantisation experiment (TDNET_TC_PAIR_SPLIT=1, off by default): pair tiles are big (layer 4: 256
-      // tiles on 74 clusters = 3.46 waves).  When the ragged last wave fits ONE wave of the single-CTA kernel's
-      // 128 x 128 tiles, the pair kernel runs the full waves and the single-CTA kernel the remaining M range.
-      // Measured on B200: 0.3073 -> 0.3051 ms on the layer-4 conv, i.e. nothing -- at ~1.5 PFLOP/s executed the
-      // launch is paced by the chip's power-limited tensor rate (cuBLAS bf16 burst: 1.67 PFLOP/s), not by the
-      // number of waves, so an idle half wave costs no time.  Both kernels are bit-identical per output.
+      // Two alternatives were built, are bit-identical (same products in the same order per output element) and are kept
+      // as explicit variants because neither moves the frame rate:
+      //  * TDN_TC_PAIR_TAIL -- wave quantisation: pair tiles are big (layer 4 at 1024x2048: 256 tiles on 74 clusters = 3.46
+      //    rounds) and the launch time follows the ROUNDS, not the work (tools/quant_probe.py: 208 / 224 / 256 / 288 / 304
+      //    tiles take 0.259 / 0.328 / 0.334 / 0.352 / 0.416 ms).  The full rounds run as N = 256 tiles and the remaining
+      //    rows of pair tiles as N = 128 tiles in a second launch.  But an N = 128 pair tile is shared-memory bound (6 KB of
+      //    operands per 64 tensor cycles) and costs ~0.7 of a full one: 0.341 -> 0.331 ms standalone, nothing in frames.
+      //  * TDN_TC_PAIR_QUAD -- clusters of two pairs share the weight tile by TMA multicast (half the L2 reads of B): 33
+      //    resident clusters of four instead of 74 of two, tile time 0.0836 -> 0.0823 ms: the kernel is not L2-bound.
+      //  (Earlier: the ragged round on the SINGLE-CTA kernel gained nothing either.)  TDNET_TC_PAIR_MODE=tail|quad
+      //  applies them to TDN_TC_AUTO for A/B runs.
+      static int mode_env = -1;
+      if (mode_env < 0) {
+        const char* e = getenv("TDNET_TC_PAIR_MODE");
+        mode_env = !e ? 0 : !strcmp(e, "tail") ? 1 : !strcmp(e, "quad") ? 2 : 0;
+      }
+      const int mode = d->variant == TDN_TC_PAIR_TAIL ? 1 : d->variant == TDN_TC_PAIR_QUAD ? 2
+                       : (d->variant == TDN_TC_AUTO && pair_n == 256) ? mode_env : 0;
       int clusters = 0, rc;
+      if (mode == 2) {
+        int quads = 0;
+        if ((rc = conv2d_tc_quad_clusters(g_num_sms, &quads))) return rc;
+        TDN_REQUIRE(quads > 0 || d->variant == TDN_TC_AUTO, TDN_ERR_UNSUPPORTED, "conv2d_tc: no resident 4-CTA clusters");
+        if (quads > 0) return conv2d_tc_pair(d, p, 256, g_num_sms, 0, stream, 0, true);
+      }
       if ((rc = conv2d_tc_pair_clusters(pair_n, g_num_sms, &clusters))) return rc;
-      const int ntn_pair = ceil_div(d->cout, pair_n);
-      const long long m_tiles = (long long)in.n * p.tiles_h * p.tiles_w;
-      const long long pair_tiles = ((m_tiles + 1) / 2) * ntn_pair;
-      long long head = pair_tiles / clusters * clusters;
-      head -= head % ntn_pair;                                    // whole pair rows of M only
-      const long long m_done = head / ntn_pair * 2;
-      const long long tail_tiles = (m_tiles - m_done) * ceil_div(d->cout, 128);
-      static int split_env = -2;
-      if (split_env == -2) {
-        const char* e = getenv("TDNET_TC_PAIR_SPLIT");
-        split_env = e ? atoi(e) : 0;
+      if (mode == 1) {
+        const int ntn_pair = ceil_div(d->cout, pair_n);
+        const long long m_tiles = (long long)in.n * p.tiles_h * p.tiles_w;
+        const long long pair_rows = (m_tiles + 1) / 2;
+        const long long pair_tiles = pair_rows * ntn_pair;
+        long long head = pair_tiles / clusters * clusters;
+        head -= head % ntn_pair;                                    // whole rows of pair tiles only
+        const long long tail_tiles = (pair_rows - head / ntn_pair) * (d->cout / 128);
+        const double cost_plain = (double)ceil_div((int)pair_tiles, clusters);
+        const double cost_split = (double)(head / clusters) + 0.7 * (double)ceil_div((int)tail_tiles, clusters) + 0.05;
+        if (head > 0 && head < pair_tiles && (cost_split < cost_plain || d->variant == TDN_TC_PAIR_TAIL)) {
+          if ((rc = conv2d_tc_pair(d, p, 256, g_num_sms, (int)head, stream, 0))) return rc;
+          return conv2d_tc_pair(d, p, 128, g_num_sms, 0, stream, (int)(head / ntn_pair));
+        }
       }
-      if (split_env && d->variant == TDN_TC_AUTO && head > 0 && head < pair_tiles && tail_tiles <= g_num_sms) {
-        if ((rc = conv2d_tc_pair(d, p, pair_n, g_num_sms, (int)head, stream))) return rc;
-        block_n = 128;
-        p.n_tiles_n = ceil_div(d->cout, 128);
-        p.num_tiles = (int)(m_tiles * p.n_tiles_n);
-        p.tile_begin = (int)(m_done * p.n_tiles_n);
-        // falls through to the single-CTA launch below for tiles [tile_begin, num_tiles)
-      } else {
-        return conv2d_tc_pair(d, p, pair_n, g_num_sms, 0, stream);
-      }
+      return conv2d_tc_pair(d, p, pair_n, g_num_sms, 0, stream);
     }
     const bool halo_auto = halo_env > 0 || (halo_env < 0 && d->dilation == 1 && in.c == 128 && d->cout <= 128);
     if (d->variant == TDN_TC_HALO || (d->variant == TDN_TC_AUTO && halo_ok && halo_auto && p.tile_begin == 0))

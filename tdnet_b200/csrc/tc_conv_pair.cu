@@ -37,8 +37,15 @@ struct PairCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 512;
 };
 
-template <int BLOCK_N>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+// QUAD: clusters of FOUR CTAs = two pairs that work on the same output-channel tile of two consecutive rows of pair tiles
+// and share its weights: each CTA fetches ONE plane (pair 0: hi, pair 1: lo) of its half of the B rows and multicasts it to
+// the CTA of the same parity in the other pair.  Why: the pair kernel is paced by the L2 -> SM path, not by the MMAs
+// (tools/quant_probe.py: an N = 128 pair tile with half the MMA work takes as long as an N = 256 tile; ~33 B/clk per SM
+// arrive in both cases against ~42 B/clk chip-wide TMA throughput); the weights are half of those bytes and identical for
+// every cluster.  The stage ring couples the two pairs: a stage is free when the MMAs of BOTH pairs that read it have
+// retired (two multicast commits per `empty` barrier).
+template <int BLOCK_N, bool QUAD>
+__global__ void __cluster_dims__(QUAD ? 4 : 2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 tc_conv_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                     const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                     const TcParams p) {
@@ -56,8 +63,9 @@ tc_conv_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int rank = (int)(blockIdx.x & 1);            // == %cluster_ctarank for cluster dims (2,1,1)
+  const int rank = (int)(blockIdx.x & 1);            // parity inside the pair (== %cluster_ctarank & 1)
   const bool leader = rank == 0;
+  const int pair_in_cluster = QUAD ? (int)((blockIdx.x >> 1) & 1) : 0;
   const int cluster_id = (int)(blockIdx.x >> 1);
   const int num_clusters = (int)(gridDim.x >> 1);
   const int kc_per_tap = p.Cin / TC_BLOCK_K;
@@ -70,7 +78,7 @@ tc_conv_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     prefetch_tensormap(&tmB_lo);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);                    // used on the leader only: its producer's expect_tx arrival
-      mbar_init(&empty_bar[s], 1);                   // multicast commit of the leader's MMA thread
+      mbar_init(&empty_bar[s], QUAD ? 2 : 1);        // multicast commit of the MMA thread of every pair of the cluster
     }
     for (int s = 0; s < NUM_ACC; ++s) {
       mbar_init(&tmem_full[s], 1);                   // multicast commit
@@ -94,9 +102,11 @@ tc_conv_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
-        const int nt = tile % p.n_tiles_n;
-        int mt = 2 * (tile / p.n_tiles_n) + rank;    // this CTA's 128-pixel M tile (may lie past the last image:
+      const uint16_t mc_mask = (uint16_t)(5u << rank);   // QUAD: this CTA and the CTA of the same parity in the other pair
+      for (int tile = p.tile_begin + cluster_id; tile < p.num_tiles; tile += num_clusters) {
+        int nt, mt;
+        pair_tile_coords(p, tile, nt, mt);
+        mt = 2 * mt + rank;                          // this CTA's 128-pixel M tile (may lie past the last image:
         const int tx = mt % p.tiles_w;               //  TMA then zero-fills and the epilogue stores nothing)
         mt /= p.tiles_w;
         const int ty = mt % p.tiles_h;
@@ -116,8 +126,14 @@ tc_conv_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
           tma_load_4d_pair(sa + TC_A_PLANE, &tmA_lo, &full_bar[stage], kc * TC_BLOCK_K, x0, y0, img);
           const int kcol = tap * p.Cin + kc * TC_BLOCK_K;
           const int brow = nt * BLOCK_N + rank * (BLOCK_N / 2);
-          tma_load_3d_pair(sb, &tmB_hi, &full_bar[stage], kcol, brow, 0);
-          tma_load_3d_pair(sb + Cfg::B_HALF_PLANE, &tmB_lo, &full_bar[stage], kcol, brow, 0);
+          if (!QUAD) {
+            tma_load_3d_pair(sb, &tmB_hi, &full_bar[stage], kcol, brow, 0);
+            tma_load_3d_pair(sb + Cfg::B_HALF_PLANE, &tmB_lo, &full_bar[stage], kcol, brow, 0);
+          } else if (pair_in_cluster == 0) {
+            tma_load_3d_pair_mc(sb, &tmB_hi, &full_bar[stage], mc_mask, kcol, brow, 0);
+          } else {
+            tma_load_3d_pair_mc(sb + Cfg::B_HALF_PLANE, &tmB_lo, &full_bar[stage], mc_mask, kcol, brow, 0);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -130,7 +146,7 @@ tc_conv_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
+      for (int tile = p.tile_begin + cluster_id; tile < p.num_tiles; tile += num_clusters) {
         for (int kb0 = 0; kb0 < num_kb; kb0 += p.chunk_kb) {
           const int kb1 = min(kb0 + p.chunk_kb, num_kb);
           mbar_wait(&tmem_empty[as], aphase ^ 1);
@@ -155,8 +171,8 @@ tc_conv_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                   umma_f16_pair(d_tmem, a_hi, b_hi, idesc, 1);
                 }
               }
-              umma_commit_pair(&empty_bar[stage], 3);
-              if (kb == kb1 - 1) umma_commit_pair(&tmem_full[as], 3);
+              umma_commit_pair(&empty_bar[stage], QUAD ? 0xF : 3);
+              if (kb == kb1 - 1) umma_commit_pair(&tmem_full[as], (uint16_t)(3u << (2 * pair_in_cluster)));
             }
             __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -182,62 +198,71 @@ tc_conv_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
 int encode_map_f16(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
                    const cuuint32_t* box, const char* what, const cuuint32_t* elem_strides, int swizzle128 = 1);
 
-template <int BLOCK_N>
+// Resident clusters of CSIZE CTAs (2: one pair, 4: two pairs) the device can hold.
+template <int BLOCK_N, bool QUAD>
 static int pair_clusters(int num_sms, int* clusters) {
   using Cfg = PairCfg<BLOCK_N>;
+  constexpr int CSIZE = QUAD ? 4 : 2;
   static PerDeviceInt cache;
   const int slot = current_device_slot();
   int max_clusters = cache.get(slot);
   if (max_clusters == 0) {
-    TDN_CUDA_OK(cudaFuncSetAttribute(tc_conv_pair_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    TDN_CUDA_OK(cudaFuncSetAttribute(tc_conv_pair_kernel<BLOCK_N, QUAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      Cfg::SMEM_BYTES));
-    // how many 2-CTA clusters the device can keep resident (GPCs with an odd number of usable SMs leave one
-    // unpaired): a persistent kernel must not launch more, or the surplus runs as a second wave
+    // how many clusters the device can keep resident (GPCs whose usable SM count is not a multiple of the cluster size
+    // leave SMs unused): a persistent kernel must not launch more, or the surplus runs as a second wave
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(num_sms & ~1, 1, 1);
+    cfg.gridDim = dim3(num_sms / CSIZE * CSIZE, 1, 1);
     cfg.blockDim = dim3(TC_THREADS, 1, 1);
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cudaLaunchAttribute attr;
     attr.id = cudaLaunchAttributeClusterDimension;
-    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    attr.val.clusterDim.x = CSIZE; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
     cfg.attrs = &attr;
     cfg.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, tc_conv_pair_kernel<BLOCK_N>, &cfg) != cudaSuccess || n <= 0) {
+    if (cudaOccupancyMaxActiveClusters(&n, tc_conv_pair_kernel<BLOCK_N, QUAD>, &cfg) != cudaSuccess || n <= 0) {
       cudaGetLastError();
-      n = num_sms / 2;
+      n = QUAD ? 0 : num_sms / CSIZE;                // quad: unknown -> not used
     }
-    max_clusters = n < num_sms / 2 ? n : num_sms / 2;
+    max_clusters = n < num_sms / CSIZE ? n : num_sms / CSIZE;
     if (const char* e = getenv("TDNET_TC_PAIR_VERBOSE"))
-      if (atoi(e)) fprintf(stderr, "[tdnet_b200] tc_conv_pair_kernel<%d>: %d resident clusters of 2 CTAs\n", BLOCK_N, max_clusters);
-    cache.set(slot, max_clusters);
+      if (atoi(e)) fprintf(stderr, "[tdnet_b200] tc_conv_pair_kernel<%d>: %d resident clusters of %d CTAs\n", BLOCK_N, max_clusters, CSIZE);
+    cache.set(slot, max_clusters > 0 ? max_clusters : -1);
   }
-  *clusters = max_clusters;
+  *clusters = max_clusters > 0 ? max_clusters : 0;
   return TDN_OK;
 }
 
 int conv2d_tc_pair_clusters(int block_n, int num_sms, int* clusters) {
-  return block_n == 256 ? pair_clusters<256>(num_sms, clusters) : pair_clusters<128>(num_sms, clusters);
+  return block_n == 256 ? pair_clusters<256, false>(num_sms, clusters) : pair_clusters<128, false>(num_sms, clusters);
 }
+int conv2d_tc_quad_clusters(int num_sms, int* clusters) { return pair_clusters<256, true>(num_sms, clusters); }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool QUAD>
 static int launch_pair(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
                        const TcParams& p, int num_sms, cudaStream_t stream) {
   using Cfg = PairCfg<BLOCK_N>;
+  constexpr int PAIRS = QUAD ? 2 : 1;                // pairs per cluster; p.num_tiles counts pair tiles
   int max_clusters = 0, rc;
-  if ((rc = pair_clusters<BLOCK_N>(num_sms, &max_clusters))) return rc;
-  const int clusters = p.num_tiles < max_clusters ? p.num_tiles : max_clusters;
-  TDN_CUDA_OK(tc_launch(tc_conv_pair_kernel<BLOCK_N>, 2 * clusters, TC_THREADS, Cfg::SMEM_BYTES, stream, p.num_tiles <= 2 * clusters, a_hi, a_lo, b_hi, b_lo, p));
+  if ((rc = pair_clusters<BLOCK_N, QUAD>(num_sms, &max_clusters))) return rc;
+  TDN_REQUIRE(max_clusters > 0, TDN_ERR_UNSUPPORTED, "conv2d_tc_pair: no resident clusters for this variant");
+  const int todo = (p.num_tiles - p.tile_begin + PAIRS - 1) / PAIRS;
+  const int clusters = todo < max_clusters ? todo : max_clusters;
+  TDN_CUDA_OK(tc_launch(tc_conv_pair_kernel<BLOCK_N, QUAD>, 2 * PAIRS * clusters, TC_THREADS, Cfg::SMEM_BYTES, stream,
+                        todo <= 2 * clusters, a_hi, a_lo, b_hi, b_lo, p));
   TDN_LAUNCH_OK();
   return TDN_OK;
 }
 
 // Called by conv2d_tc() with the epilogue / output / residual fields of `p` filled in and the 128-pixel tile
 // shape chosen; re-tiles into pair tiles of 2 x 128 pixels x block_n output channels.  max_pair_tiles > 0 limits
-// the launch to the first pair tiles (the caller finishes the remaining M range with the single-CTA kernel).
+// the launch to the first pair tiles; first_pair_row > 0 starts it at that row of pair tiles (256 pixels each, all
+// output-channel tiles) -- together they let the caller run the full rounds and the ragged last round as two launches.
+// quad: clusters of two pairs that share the weight tile (block_n 256 only; tile indices then follow pair_tile_coords).
 int conv2d_tc_pair(const tdn_tc_conv_desc* d, TcParams p, int block_n, int num_sms, int max_pair_tiles,
-                   cudaStream_t stream) {
+                   cudaStream_t stream, int first_pair_row, bool quad) {
   const tdn_tensor& in = d->in;
   const int cs = p.conv_stride;
   const int taps = d->kh * d->kw;
@@ -248,7 +273,14 @@ int conv2d_tc_pair(const tdn_tc_conv_desc* d, TcParams p, int block_n, int num_s
   TDN_REQUIRE(num_tiles < (1ll << 30), TDN_ERR_UNSUPPORTED, "conv2d_tc_pair: too many tiles");
   p.num_tiles = (int)num_tiles;
   if (max_pair_tiles > 0 && max_pair_tiles < p.num_tiles) p.num_tiles = max_pair_tiles;
-  p.tile_begin = 0;
+  p.tile_begin = first_pair_row * p.n_tiles_n;
+  p.quad = 0;
+  if (quad) {
+    TDN_REQUIRE(block_n == 256 && max_pair_tiles <= 0 && first_pair_row == 0, TDN_ERR_INVALID,
+                "conv2d_tc_pair: the quad variant runs whole launches of N = 256 tiles");
+    p.quad = 1;
+    p.num_tiles = (int)(((m_tiles + 3) / 4) * 2 * p.n_tiles_n);   // both pairs of a cluster walk the same number of tiles
+  }
 
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
   int rc;
@@ -267,8 +299,9 @@ int conv2d_tc_pair(const tdn_tc_conv_desc* d, TcParams p, int block_n, int num_s
     if ((rc = encode_map_f16(&b_hi, d->weight_hi, 3, dims, str, box, "B.hi(pair)", nullptr, 1))) return rc;
     if ((rc = encode_map_f16(&b_lo, d->weight_lo, 3, dims, str, box, "B.lo(pair)", nullptr, 1))) return rc;
   }
-  if (block_n == 256) return launch_pair<256>(a_hi, a_lo, b_hi, b_lo, p, num_sms, stream);
-  return launch_pair<128>(a_hi, a_lo, b_hi, b_lo, p, num_sms, stream);
+  if (quad) return launch_pair<256, true>(a_hi, a_lo, b_hi, b_lo, p, num_sms, stream);
+  if (block_n == 256) return launch_pair<256, false>(a_hi, a_lo, b_hi, b_lo, p, num_sms, stream);
+  return launch_pair<128, false>(a_hi, a_lo, b_hi, b_lo, p, num_sms, stream);
 }
 
 }  // namespace tdn

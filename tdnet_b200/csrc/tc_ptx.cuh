@@ -211,6 +211,17 @@ __device__ __forceinline__ void tma_load_3d_pair(void* smem_dst, const void* tma
       "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// The same load delivered to this offset in every CTA of `cta_mask` (cluster ranks); each destination's bytes are counted
+// on the barrier at `leader_bar`'s offset in the leader of THAT destination's pair (the CUTLASS 2-SM multicast form).
+__device__ __forceinline__ void tma_load_3d_pair_mc(void* smem_dst, const void* tmap, uint64_t* leader_bar, uint16_t cta_mask,
+                                                    int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], "
+      "[%1, {%4, %5, %6}], [%2], %3;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(leader_bar) & PEER_BIT_MASK),
+      "h"(cta_mask), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_result, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
                "r"(ncols)

@@ -455,8 +455,10 @@ def test_tc_conv_pair_variant_is_bit_identical(env, n, h, w, cin, cout, k, dil, 
 
 
 def test_tc_conv_auto_pair_plus_tail_split_is_bit_identical(env):
-    """Layer-4-like tiling (256 M tiles x 512 channels): TDN_TC_AUTO runs the full waves on the CTA-pair kernel and
-    the ragged last wave on the single-CTA kernel (two launches); every output must equal the single-kernel run."""
+    """Layer-4-like tiling (256 M tiles x 512 channels = 256 pair tiles on 74 clusters): the single-CTA kernel, the library's
+    choice, the CTA-pair kernel, its tail variant (full rounds as N = 256 pair tiles + the ragged last round as N = 128 pair
+    tiles in a second launch) and its quad variant (clusters of two pairs sharing the weight tile by TMA multicast) must
+    agree bit for bit."""
     lib, cabi, View, dev = env
     n, h, w, cin, cout, k, dil = 1, 128, 256, 128, 512, 3, 4
     g = torch.Generator(device="cuda").manual_seed(5)
@@ -466,7 +468,7 @@ def test_tc_conv_auto_pair_plus_tail_split_is_bit_identical(env):
     wt = torch.randn(cout, k * k * cin, generator=g, device="cuda") / (cin * k * k) ** 0.5
     wh, wl = split_planes(wt)
     outs = []
-    for variant in (cabi.TC_BASE, cabi.TC_AUTO, cabi.TC_PAIR):
+    for variant in (cabi.TC_BASE, cabi.TC_AUTO, cabi.TC_PAIR, cabi.TC_PAIR_TAIL, cabi.TC_PAIR_QUAD):
         out = View.alloc(n, h, w, cout, dev, split=True)
         out.base.fill_(float("nan")); out.lo.fill_(float("nan"))
         d = cabi.TcConvDesc()
@@ -611,7 +613,7 @@ def attn_family():
     """Restores TDNET_ATTN_TS (the library reads it on every call) after a test that flips kernel families."""
     import os
     old = os.environ.get("TDNET_ATTN_TS")
-    yield lambda ts: os.environ.__setitem__("TDNET_ATTN_TS", str(int(ts)))   # 0 SS, 1 TS, 3 TS with Q in tensor memory
+    yield lambda ts: os.environ.__setitem__("TDNET_ATTN_TS", str(int(ts)))   # 0 SS, 1 TS, 3 TS with Q in tensor memory, 4 TS with 128-key S tiles
     if old is None:
         os.environ.pop("TDNET_ATTN_TS", None)
     else:
@@ -627,12 +629,13 @@ def test_attention_kernel_families_bit_identical(env, attn_family, n, pq, pk, dv
     including the split into 256- and 128-channel launches (20000 queries: 314 items on 148 SMs) and ragged tiles."""
     lib, cabi, View, dev = env
     got = {}
-    for ts in (0, 1, 3):
+    for ts in (0, 1, 3, 4):
         attn_family(ts)
         got[ts] = _attention_case(cabi, lib, dev, n, pq, pk, dv, out_fmt, res_fmt)[0]
     assert not torch.isnan(got[1]).any()
     assert torch.equal(got[0], got[1])
     assert torch.equal(got[0], got[3])         # Q as a tensor-memory operand: same products, same order
+    assert torch.equal(got[0], got[4])         # 128-key S MMAs (tc_attn_s128.cu): same products, same order
 
 
 @pytest.mark.parametrize("n,pq,pk,dv", [(1, 32768, 2048, 512), (1, 32768, 1225, 512), (1, 4096, 2048, 1024)])
@@ -642,11 +645,12 @@ def test_fused_attention_tc_big_hop(env, attn_family, n, pq, pk, dv):
     softmax(q k^T / 8) v + residual of transformer.py:126-139 (the full fp64 matrix would not fit the test budget)."""
     lib, cabi, View, dev = env
     got = {}
-    for ts in (0, 1, 3):
+    for ts in (0, 1, 3, 4):
         attn_family(ts)
         got[ts], q, k, v, r = _attention_case(cabi, lib, dev, n, pq, pk, dv, "split", "split")
     assert torch.equal(got[0], got[1])
     assert torch.equal(got[0], got[3])
+    assert torch.equal(got[0], got[4])
     rows = torch.arange(0, pq, 61)
     a = torch.softmax(q[:, rows].double() @ k.double().transpose(1, 2) / 8.0, dim=2)
     ref = a @ v.double() + r[:, rows].double()

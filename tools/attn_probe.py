@@ -45,7 +45,7 @@ def formats(lib):
                 got = {}
                 fams = tuple(os.environ.get("ATTN_PROBE_FAMILIES", "ss,ts").split(","))
                 for which in fams:
-                    os.environ["TDNET_ATTN_TS"] = {"ss": "0", "ts2": "2", "tq": "3"}.get(which, "1")
+                    os.environ["TDNET_ATTN_TS"] = {"ss": "0", "ts2": "2", "tq": "3", "s128": "4"}.get(which, "1")
                     of = torch.full((n, pq, dv), float("nan"), device="cuda")
                     oh = torch.full((n, pq, dv), float("nan"), device="cuda", dtype=torch.half)
                     ol = torch.full((n, pq, dv), float("nan"), device="cuda", dtype=torch.half)
@@ -86,7 +86,7 @@ def main():
     if "--formats" in sys.argv:
         return formats(lib)
     lines = []
-    for n, pq, pk, dv in (SHAPES[-1:] if profile or sustain else SHAPES):
+    for n, pq, pk, dv in (SHAPES[-1:] if profile or sustain or "--bighop" in sys.argv else SHAPES):
         g = torch.Generator().manual_seed(pq + pk)
         q, k = torch.randn(n, pq, 64, generator=g) * 1.3, torch.randn(n, pk, 64, generator=g) * 1.4
         v, r = torch.randn(n, pk, dv, generator=g) * 3, torch.randn(n, pq, dv, generator=g)
@@ -101,7 +101,7 @@ def main():
         if sustain and "--debug" in sys.argv:
             variants = tuple(os.environ.get("ATTN_PROBE_VARIANTS", "ts,ts_dbg1,ts_dbg2,ts_dbg4,ts_dbg8,ts_dbg15").split(","))
         for which in variants:
-            os.environ["TDNET_ATTN_TS"] = {"ss": "0", "ts2": "2", "tq": "3"}.get(which.split("_")[0], "1")
+            os.environ["TDNET_ATTN_TS"] = {"ss": "0", "ts2": "2", "tq": "3", "s128": "4"}.get(which.split("_")[0], "1")
             os.environ["TDNET_ATTN_DEBUG"] = which.split("dbg")[1] if "dbg" in which else "0"
             out = torch.full((n, pq, dv), float("nan"), device="cuda")
             d = _cabi.AttentionDesc()
