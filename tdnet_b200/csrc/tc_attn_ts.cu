@@ -199,7 +199,10 @@ tc_attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_const
       // pass 1 writes whole S/P buffer pairs, which still hold probabilities of the previous item until its last P.V'
       // MMA has retired; with the row maxima reused there is no pass 1 and the per-buffer sp_empty waits of pass 2 suffice
       const int t1 = reuse ? 0 : T1;
-      if (!reuse && items_done > 0) mbar_wait(&bars->o_full, (items_done - 1) & 1);
+      // (waited for on EVERY item, also when there is no pass 1: a parity wait that skips a phase passes at once when the
+      //  barrier is still two phases back -- with few key tiles per item this warp gets that far ahead -- and P.V' cannot
+      //  restart before the epilogue has drained O anyway, so the wait costs nothing)
+      if (items_done > 0) mbar_wait(&bars->o_full, (items_done - 1) & 1);
       for (int it = 0; it < t1; ++it, ++n1) {
         const int pair = n1 & 1;
         mbar_wait(&bars->k_full[ks], kph);
