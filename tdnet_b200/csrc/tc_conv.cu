@@ -248,6 +248,7 @@ static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUt
 }
 
 int conv2d_tc_halo(const tdn_tc_conv_desc* d, TcParams p, int num_sms, int chunk_kb, cudaStream_t stream);
+int conv2d_tc_halo_sw(const tdn_tc_conv_desc* d, TcParams p, int num_sms, int chunk_kb, cudaStream_t stream);
 int conv2d_tc_pair(const tdn_tc_conv_desc* d, TcParams p, int block_n, int num_sms, int max_pair_tiles,
                    cudaStream_t stream, int first_pair_row = 0, bool quad = false);
 int conv2d_tc_pair_clusters(int block_n, int num_sms, int* clusters);
@@ -364,9 +365,11 @@ int conv2d_tc(const tdn_tc_conv_desc* d, cudaStream_t stream) {
     }
     const bool pair_ok = !d->weight_batched && d->cout % 128 == 0;
     const bool halo_ok = d->kh == 3 && d->kw == 3 && cs == 1 && d->dilation <= 2 && !d->weight_batched && in.w >= 8;
-    TDN_REQUIRE(d->variant >= TDN_TC_AUTO && d->variant <= TDN_TC_PAIR_QUAD, TDN_ERR_INVALID, "conv2d_tc: unknown variant");
+    TDN_REQUIRE(d->variant >= TDN_TC_AUTO && d->variant <= TDN_TC_HALO_SW, TDN_ERR_INVALID, "conv2d_tc: unknown variant");
     const bool pair_forced = d->variant == TDN_TC_PAIR || d->variant == TDN_TC_PAIR_TAIL || d->variant == TDN_TC_PAIR_QUAD;
-    TDN_REQUIRE(d->variant < TDN_TC_PAIR_TAIL || (pair_ok && d->cout % 256 == 0), TDN_ERR_UNSUPPORTED,
+    TDN_REQUIRE(d->variant != TDN_TC_HALO_SW || halo_ok, TDN_ERR_UNSUPPORTED,
+                "conv2d_tc: the swizzled halo kernel needs a 3x3 stride-1 convolution with dilation <= 2, width >= 8");
+    TDN_REQUIRE((d->variant != TDN_TC_PAIR_TAIL && d->variant != TDN_TC_PAIR_QUAD) || (pair_ok && d->cout % 256 == 0), TDN_ERR_UNSUPPORTED,
                 "conv2d_tc: the tail / quad variants of the CTA-pair kernel need cout %% 256 == 0 and shared weights");
     TDN_REQUIRE(!pair_forced || pair_ok, TDN_ERR_UNSUPPORTED,
                 "conv2d_tc: the CTA-pair kernel needs cout %% 128 == 0 and shared weights");
@@ -427,6 +430,15 @@ int conv2d_tc(const tdn_tc_conv_desc* d, cudaStream_t stream) {
       return conv2d_tc_pair(d, p, pair_n, g_num_sms, 0, stream);
     }
     const bool halo_auto = halo_env > 0 || (halo_env < 0 && d->dilation == 1 && in.c == 128 && d->cout <= 128);
+    // the 128-byte-swizzled halo kernel (tc_conv_halo_sw.cu): TDNET_TC_HALO_SW = 0 never, 1 wherever it fits, default: see below
+    static int halo_sw_env = -2;
+    if (halo_sw_env == -2) {
+      const char* e = getenv("TDNET_TC_HALO_SW");
+      halo_sw_env = e ? atoi(e) : -1;
+    }
+    const bool halo_sw_auto = halo_sw_env > 0 || (halo_sw_env < 0 && false);
+    if (d->variant == TDN_TC_HALO_SW || (d->variant == TDN_TC_AUTO && halo_ok && halo_sw_auto && d->cout <= 128))
+      return conv2d_tc_halo_sw(d, p, g_num_sms, p.chunk_kb, stream);
     if (d->variant == TDN_TC_HALO || (d->variant == TDN_TC_AUTO && halo_ok && halo_auto && p.tile_begin == 0))
       return conv2d_tc_halo(d, p, g_num_sms, p.chunk_kb, stream);
   }

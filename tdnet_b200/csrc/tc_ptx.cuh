@@ -265,6 +265,19 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                           // layout type SWIZZLE_128B, bits [61,64)
   return d;
 }
+// The same layout with an explicit stride between the 8-row groups (16-byte units) and a start address that is 128-byte but
+// not 1024-byte aligned (tc_conv_halo_sw.cu: a filter tap is a row offset into a swizzled halo region).  Measured on B200: every
+// row keeps the swizzle phase of its ABSOLUTE shared-memory address -- the phase TMA wrote it with -- and the descriptor's
+// base-offset field (bits [49,52)) must stay 0; (address >> 7) & 7 there gives wrong results.
+__device__ __forceinline__ uint64_t umma_desc_k_sw128_at(uint32_t smem_addr, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(sbo & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 // K-major operand without swizzle ("interleave"): 8-row x 16-byte core matrices stored contiguously (128 B);
 // lbo = distance between the two 8-element K chunks of a K16 step, sbo = distance between consecutive 8-row
 // groups, both in 16-byte units.  The start address only needs 16-byte alignment, which is what lets a filter

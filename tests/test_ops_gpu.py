@@ -484,6 +484,37 @@ def test_tc_conv_auto_pair_plus_tail_split_is_bit_identical(env):
         assert torch.equal(outs[0][1].view(torch.int16), other[1].view(torch.int16))
 
 
+@pytest.mark.parametrize("n,h,w,cin,cout,dil", [(1, 64, 96, 64, 64, 1), (2, 45, 77, 128, 128, 2), (1, 33, 40, 64, 128, 1)])
+def test_tc_conv_swizzled_halo_variant_is_bit_identical_to_halo(env, n, h, w, cin, cout, dil):
+    """tc_conv_halo_sw.cu (the halo region in the 128-byte-swizzled layout, a filter tap = a row offset into it, descriptor
+    base offset 0) against tc_conv_halo.cu (no-swizzle region): same products in the same order; ragged map sizes exercise
+    the zero fill of the 16-pixel-wide region boxes; and both against the fp64 convolution."""
+    lib, cabi, View, dev = env
+    g = torch.Generator().manual_seed(h * w + cin)
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5
+    xs = View.alloc(n, h, w, cin, dev, split=True)
+    hi, lo = split_planes(nhwc(x))
+    xs.base.copy_(hi.view(-1)); xs.lo.copy_(lo.view(-1))
+    wh, wl = split_planes(wt.permute(0, 2, 3, 1).reshape(cout, -1).cuda())
+    outs = {}
+    for variant in (cabi.TC_HALO, cabi.TC_HALO_SW):
+        out = View.alloc(n, h, w, cout, dev, split=True)
+        out.base.fill_(float("nan")); out.lo.fill_(float("nan"))
+        d = cabi.TcConvDesc()
+        d.in_, d.out = xs.ct(), out.ct()
+        d.weight_hi, d.weight_lo, d.weight_ld = wh.data_ptr(), wl.data_ptr(), 9 * cin
+        d.cout, d.kh, d.kw, d.dilation, d.variant = cout, 3, 3, dil, variant
+        cabi.check(lib.tdn_conv2d_tc(C.byref(d), None), "conv2d_tc")
+        torch.cuda.synchronize()
+        outs[variant] = (out.base.clone(), out.lo.clone(), out.torch().permute(0, 3, 1, 2).cpu())
+    a, b = outs[cabi.TC_HALO], outs[cabi.TC_HALO_SW]
+    assert torch.equal(a[0].view(torch.int16), b[0].view(torch.int16))
+    assert torch.equal(a[1].view(torch.int16), b[1].view(torch.int16))
+    ref = F.conv2d(x.double(), wt.double(), None, 1, dil, dil)
+    assert max_abs(b[2], ref) < 2e-6 * max(1.0, float(ref.abs().max()))
+
+
 def test_tc_conv_variant_errors(env):
     lib, cabi, View, dev = env
     xs = View.alloc(1, 8, 16, 64, dev, split=True)
