@@ -32,7 +32,14 @@
 
 namespace tdn {
 
-template <int BLOCK_N>
+// TSA ("A through tensor memory"): the MMA warp copies the A tile of every K block from shared memory into one of two
+// 64-column TMEM buffers (tcgen05.cp, 8 slabs of 128 rows x 32 bytes: hi plane then lo plane) and the twelve exact-mode MMAs
+// take A from there (tcgen05.mma [d], [a_tmem], b_desc): shared memory is then read once per K block for A (32 KB) instead of
+// twelve times 4 KB, and the MMAs fetch only B.  Why: MMAs with both operands in shared memory and N <= 128 retire at about half
+// their tensor rate in every kernel of this library, the tensor-memory-operand MMAs of the attention
+// kernel at their full rate.  The ring of chunk accumulators shrinks from 512 to 384 columns.  Same products in the same
+// order: bit-identical.
+template <int BLOCK_N, bool TSA = false>
 struct TcCfg {
   static constexpr int B_PLANE = BLOCK_N * TC_BLOCK_K * 2;
   static constexpr int STAGE_BYTES = 2 * TC_A_PLANE + 2 * B_PLANE;
@@ -40,17 +47,18 @@ struct TcCfg {
   // All 512 TMEM columns as a ring of chunk accumulators (4 x 128 or 8 x 64 columns): the MMA warp can
   // run several chunks ahead of the warps that drain them, so the per-tile store phase of the epilogue
   // (scale/bias/residual/split/store) overlaps the MMAs of the next tile instead of stalling them.
-  static constexpr int NUM_ACC = 512 / BLOCK_N;
+  static constexpr int NUM_ACC = (TSA ? 384 : 512) / BLOCK_N;
+  static constexpr int A_TMEM_COL = 384;             // TSA: A buffer b = columns [384 + 64 b, 448 + 64 b): hi pairs | lo pairs
   static constexpr int TMEM_COLS = 512;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool TSA>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                const TcParams p) {
-  using Cfg = TcCfg<BLOCK_N>;
+  using Cfg = TcCfg<BLOCK_N, TSA>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -135,6 +143,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     uint32_t phase = 0;
     int as = 0;
     uint32_t aphase = 0;
+    uint32_t kbc = 0;                                  // K blocks issued so far (TSA: A buffer kbc & 1)
     for (int tile = blockIdx.x + p.tile_begin; tile < p.num_tiles; tile += gridDim.x) {
       for (int kb0 = 0; kb0 < num_kb; kb0 += p.chunk_kb) {
         const int kb1 = min(kb0 + p.chunk_kb, num_kb);
@@ -146,6 +155,27 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint32_t sb = sa + 2 * TC_A_PLANE;
           if (elect_one()) {
+            if (TSA) {
+              const uint32_t a_t = tmem_base + Cfg::A_TMEM_COL + (kbc & 1) * 64;
+#pragma unroll
+              for (int k = 0; k < TC_BLOCK_K / 16; ++k) {
+                tmem_cp_128x256b(a_t + k * 8, umma_desc_k_sw128(sa + k * 32));
+                tmem_cp_128x256b(a_t + 32 + k * 8, umma_desc_k_sw128(sa + TC_A_PLANE + k * 32));
+              }
+#pragma unroll
+              for (int k = 0; k < TC_BLOCK_K / 16; ++k) {
+                const uint32_t a_hi = a_t + k * 8, a_lo = a_hi + 32;
+                const uint64_t b_hi = umma_desc_k_sw128(sb + k * 32);
+                const uint64_t b_lo = umma_desc_k_sw128(sb + Cfg::B_PLANE + k * 32);
+                if (p.fast) {
+                  umma_f16_ts(d_tmem, a_hi, b_hi, idesc, ((kb - kb0) | k) != 0);
+                } else {
+                  umma_f16_ts(d_tmem, a_hi, b_lo, idesc, ((kb - kb0) | k) != 0);
+                  umma_f16_ts(d_tmem, a_lo, b_hi, idesc, 1);
+                  umma_f16_ts(d_tmem, a_hi, b_hi, idesc, 1);
+                }
+              }
+            } else {
 #pragma unroll
             for (int k = 0; k < TC_BLOCK_K / 16; ++k) {
               const uint64_t a_hi = umma_desc_k_sw128(sa + k * 32);
@@ -160,11 +190,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 umma_f16(d_tmem, a_hi, b_hi, idesc, 1);
               }
             }
+            }
             umma_commit(&empty_bar[stage]);
             if (kb == kb1 - 1) umma_commit(&tmem_full[as]);
           }
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          ++kbc;
         }
         if (++as == NUM_ACC) { as = 0; aphase ^= 1; }
       }
@@ -228,14 +260,14 @@ static void pick_tile(int H, int W, int* BH, int* BW) {
 }
 
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool TSA>
 static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
                      const CUtensorMap& b_lo, const TcParams& p, cudaStream_t stream) {
-  using Cfg = TcCfg<BLOCK_N>;
+  using Cfg = TcCfg<BLOCK_N, TSA>;
   static PerDeviceFlag attr_set;
   const int slot = current_device_slot();
   if (!attr_set.is_set(slot)) {
-    TDN_CUDA_OK(cudaFuncSetAttribute(tc_conv_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    TDN_CUDA_OK(cudaFuncSetAttribute(tc_conv_kernel<BLOCK_N, TSA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      Cfg::SMEM_BYTES));
     attr_set.set(slot);
   }
@@ -243,7 +275,7 @@ static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUt
   TDN_REQUIRE(g_num_sms > 0, TDN_ERR_CUDA, "conv2d_tc: cannot query the SM count");
   const int todo = p.num_tiles - p.tile_begin;
   int grid = todo < g_num_sms ? todo : g_num_sms;
-  TDN_CUDA_OK(tc_launch(tc_conv_kernel<BLOCK_N>, grid, TC_THREADS, Cfg::SMEM_BYTES, stream, todo <= 2 * grid, a_hi, a_lo, b_hi, b_lo, p));
+  TDN_CUDA_OK(tc_launch(tc_conv_kernel<BLOCK_N, TSA>, grid, TC_THREADS, Cfg::SMEM_BYTES, stream, todo <= 2 * grid, a_hi, a_lo, b_hi, b_lo, p));
   return TDN_OK;
 }
 
@@ -365,7 +397,7 @@ int conv2d_tc(const tdn_tc_conv_desc* d, cudaStream_t stream) {
     }
     const bool pair_ok = !d->weight_batched && d->cout % 128 == 0;
     const bool halo_ok = d->kh == 3 && d->kw == 3 && cs == 1 && d->dilation <= 2 && !d->weight_batched && in.w >= 8;
-    TDN_REQUIRE(d->variant >= TDN_TC_AUTO && d->variant <= TDN_TC_HALO_SW, TDN_ERR_INVALID, "conv2d_tc: unknown variant");
+    TDN_REQUIRE(d->variant >= TDN_TC_AUTO && d->variant <= TDN_TC_BASE_TS, TDN_ERR_INVALID, "conv2d_tc: unknown variant");
     const bool pair_forced = d->variant == TDN_TC_PAIR || d->variant == TDN_TC_PAIR_TAIL || d->variant == TDN_TC_PAIR_QUAD;
     TDN_REQUIRE(d->variant != TDN_TC_HALO_SW || halo_ok, TDN_ERR_UNSUPPORTED,
                 "conv2d_tc: the swizzled halo kernel needs a 3x3 stride-1 convolution with dilation <= 2, width >= 8");
@@ -466,8 +498,19 @@ int conv2d_tc(const tdn_tc_conv_desc* d, cudaStream_t stream) {
     if ((rc = encode_map_f16(&b_hi, d->weight_hi, 3, dims, str, box, "B.hi", nullptr, 1))) return rc;
     if ((rc = encode_map_f16(&b_lo, d->weight_lo, 3, dims, str, box, "B.lo", nullptr, 1))) return rc;
   }
-  if (block_n == 64) return launch_tc<64>(a_hi, a_lo, b_hi, b_lo, p, stream);
-  return launch_tc<128>(a_hi, a_lo, b_hi, b_lo, p, stream);
+  // A through tensor memory (TSA, see TcCfg): TDN_TC_BASE_TS forces it, TDNET_TC_TSA = 0 / 1 switches it for TDN_TC_AUTO / TDN_TC_BASE
+  static int tsa_env = -2;
+  if (tsa_env == -2) {
+    const char* e = getenv("TDNET_TC_TSA");
+    tsa_env = e ? atoi(e) : 0;
+  }
+  const bool tsa = d->variant == TDN_TC_BASE_TS || (d->variant != TDN_TC_BASE && tsa_env > 0);
+  if (tsa) {
+    if (block_n == 64) return launch_tc<64, true>(a_hi, a_lo, b_hi, b_lo, p, stream);
+    return launch_tc<128, true>(a_hi, a_lo, b_hi, b_lo, p, stream);
+  }
+  if (block_n == 64) return launch_tc<64, false>(a_hi, a_lo, b_hi, b_lo, p, stream);
+  return launch_tc<128, false>(a_hi, a_lo, b_hi, b_lo, p, stream);
 }
 
 }  // namespace tdn

@@ -172,6 +172,12 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r
         "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
+// Asynchronous copy shared memory -> tensor memory of a 128-row x 32-byte slab (one K16 step of an fp16 A operand: row i ->
+// lane i, 8 columns), the source described like an MMA operand.  Executes in issue order with the tcgen05.mma of the same
+// thread, so an MMA issued after it may name the destination columns as its A operand without further synchronisation.
+__device__ __forceinline__ void tmem_cp_128x256b(uint32_t taddr, uint64_t desc) {
+  asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(desc) : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ----------------------------------------------------------------------------- CTA pairs (cta_group::2)

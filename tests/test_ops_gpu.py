@@ -433,7 +433,7 @@ def test_tc_conv_pair_variant_is_bit_identical(env, n, h, w, cin, cout, k, dil, 
     wh, wl = split_planes(wt.permute(0, 2, 3, 1).reshape(cout, -1).cuda())
     scd, bid = sc.cuda(), bi.cuda()
     outs = {}
-    for variant in (cabi.TC_BASE, cabi.TC_PAIR):
+    for variant in (cabi.TC_BASE, cabi.TC_PAIR, cabi.TC_BASE_TS):
         out = View.alloc(n, ho, wo, cout, dev, split=True)
         out.base.fill_(float("nan")); out.lo.fill_(float("nan"))
         d = cabi.TcConvDesc()
@@ -452,6 +452,9 @@ def test_tc_conv_pair_variant_is_bit_identical(env, n, h, w, cin, cout, k, dil, 
     assert max_abs(pair[2], ref) < 3e-6 * max(1.0, float(ref.abs().max()))
     assert torch.equal(base[0].view(torch.int16), pair[0].view(torch.int16))
     assert torch.equal(base[1].view(torch.int16), pair[1].view(torch.int16))
+    ts = outs[cabi.TC_BASE_TS]       # the single-CTA kernel with the A tile copied to tensor memory per K block (tcgen05.cp)
+    assert torch.equal(base[0].view(torch.int16), ts[0].view(torch.int16))
+    assert torch.equal(base[1].view(torch.int16), ts[1].view(torch.int16))
 
 
 def test_tc_conv_auto_pair_plus_tail_split_is_bit_identical(env):

@@ -17,7 +17,7 @@ from tdnet_b200 import _cabi as cabi  # noqa: E402
 def main():
     lib = cabi.load()
     shapes = [(1, 256, 512, 64, 64, 1), (1, 128, 256, 128, 128, 1), (1, 128, 256, 128, 128, 2), (2, 45, 77, 64, 128, 2),
-              (1, 128, 256, 256, 256, 2)]
+              (1, 128, 256, 256, 256, 2), (1, 128, 256, 512, 128, 1)]
     g = torch.Generator().manual_seed(3)
     for n, h, w, cin, cout, dil in shapes:
         wt = (torch.randn(cout, 9 * cin, generator=g) / (9 * cin) ** 0.5).cuda()
@@ -28,7 +28,7 @@ def main():
         xl = (x - xh.float()).half().contiguous()
         res = {"shape": [n, h, w, cin, cout, dil]}
         ref = None
-        for name, variant in (("base", cabi.TC_BASE), ("halo", cabi.TC_HALO), ("halo_sw", cabi.TC_HALO_SW)):
+        for name, variant in (("base", cabi.TC_BASE), ("base_ts", cabi.TC_BASE_TS), ("halo", cabi.TC_HALO), ("halo_sw", cabi.TC_HALO_SW)):
             oh = torch.full((n, h, w, cout), float("nan"), dtype=torch.half, device="cuda")
             ol = torch.full((n, h, w, cout), float("nan"), dtype=torch.half, device="cuda")
             d = cabi.TcConvDesc()
