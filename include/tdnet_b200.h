@@ -158,7 +158,8 @@ enum {
   TDN_TC_PAIR_TAIL = 4, /* full rounds as N = 256 pair tiles, the ragged last round as N = 128 pair tiles (second launch) */
   TDN_TC_PAIR_QUAD = 5, /* clusters of two pairs that share the weight tile by TMA multicast */
   TDN_TC_HALO_SW = 6,   /* 3x3 stride-1 dilation<=2: one 128-byte-swizzled halo-region load per channel block */
-  TDN_TC_BASE_TS = 7    /* TDN_TC_BASE with the A tile copied to tensor memory per K block (tcgen05.cp) and read from there */
+  TDN_TC_BASE_TS = 7,   /* TDN_TC_BASE with the A tile copied to tensor memory per K block (tcgen05.cp) and read from there */
+  TDN_TC_PAIR_BAND = 8  /* 3x3 stride-1 dilation<=4 cout%256==0 on CTA pairs: one activation band per channel block and filter row */
 };
 
 int tdn_conv2d_tc(const tdn_tc_conv_desc* desc, void* stream);

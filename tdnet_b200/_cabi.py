@@ -43,7 +43,7 @@ class TcConvDesc(C.Structure):
                 ("stride", C.c_int32), ("variant", C.c_int32), ("flags", C.c_int32)]
 
 
-TC_AUTO, TC_BASE, TC_HALO, TC_PAIR, TC_PAIR_TAIL, TC_PAIR_QUAD, TC_HALO_SW, TC_BASE_TS = 0, 1, 2, 3, 4, 5, 6, 7   # tdn_tc_conv_desc.variant
+TC_AUTO, TC_BASE, TC_HALO, TC_PAIR, TC_PAIR_TAIL, TC_PAIR_QUAD, TC_HALO_SW, TC_BASE_TS, TC_PAIR_BAND = range(9)   # tdn_tc_conv_desc.variant
 
 
 class AttentionDesc(C.Structure):

@@ -285,6 +285,7 @@ int conv2d_tc_pair(const tdn_tc_conv_desc* d, TcParams p, int block_n, int num_s
                    cudaStream_t stream, int first_pair_row = 0, bool quad = false);
 int conv2d_tc_pair_clusters(int block_n, int num_sms, int* clusters);
 int conv2d_tc_quad_clusters(int num_sms, int* clusters);
+int conv2d_tc_pair_band(const tdn_tc_conv_desc* d, TcParams p, int num_sms, cudaStream_t stream);
 
 int conv2d_tc(const tdn_tc_conv_desc* d, cudaStream_t stream) {
   const tdn_tensor& in = d->in;
@@ -397,7 +398,12 @@ int conv2d_tc(const tdn_tc_conv_desc* d, cudaStream_t stream) {
     }
     const bool pair_ok = !d->weight_batched && d->cout % 128 == 0;
     const bool halo_ok = d->kh == 3 && d->kw == 3 && cs == 1 && d->dilation <= 2 && !d->weight_batched && in.w >= 8;
-    TDN_REQUIRE(d->variant >= TDN_TC_AUTO && d->variant <= TDN_TC_BASE_TS, TDN_ERR_INVALID, "conv2d_tc: unknown variant");
+    TDN_REQUIRE(d->variant >= TDN_TC_AUTO && d->variant <= TDN_TC_PAIR_BAND, TDN_ERR_INVALID, "conv2d_tc: unknown variant");
+    const bool band_ok = d->kh == 3 && d->kw == 3 && cs == 1 && d->dilation >= 1 && d->dilation <= 4 && !d->weight_batched &&
+                         d->cout % 256 == 0 && in.w >= 8;
+    TDN_REQUIRE(d->variant != TDN_TC_PAIR_BAND || band_ok, TDN_ERR_UNSUPPORTED,
+                "conv2d_tc: the band kernel needs a 3x3 stride-1 convolution with dilation <= 4, cout %% 256 == 0, shared weights");
+    if (d->variant == TDN_TC_PAIR_BAND) return conv2d_tc_pair_band(d, p, g_num_sms, stream);
     const bool pair_forced = d->variant == TDN_TC_PAIR || d->variant == TDN_TC_PAIR_TAIL || d->variant == TDN_TC_PAIR_QUAD;
     TDN_REQUIRE(d->variant != TDN_TC_HALO_SW || halo_ok, TDN_ERR_UNSUPPORTED,
                 "conv2d_tc: the swizzled halo kernel needs a 3x3 stride-1 convolution with dilation <= 2, width >= 8");
@@ -432,11 +438,12 @@ int conv2d_tc(const tdn_tc_conv_desc* d, cudaStream_t stream) {
       static int mode_env = -1;
       if (mode_env < 0) {
         const char* e = getenv("TDNET_TC_PAIR_MODE");
-        mode_env = !e ? 0 : !strcmp(e, "tail") ? 1 : !strcmp(e, "quad") ? 2 : 0;
+        mode_env = !e ? 0 : !strcmp(e, "tail") ? 1 : !strcmp(e, "quad") ? 2 : !strcmp(e, "band") ? 3 : 0;
       }
       const int mode = d->variant == TDN_TC_PAIR_TAIL ? 1 : d->variant == TDN_TC_PAIR_QUAD ? 2
                        : (d->variant == TDN_TC_AUTO && pair_n == 256) ? mode_env : 0;
       int clusters = 0, rc;
+      if (mode == 3 && band_ok) return conv2d_tc_pair_band(d, p, g_num_sms, stream);
       if (mode == 2) {
         int quads = 0;
         if ((rc = conv2d_tc_quad_clusters(g_num_sms, &quads))) return rc;

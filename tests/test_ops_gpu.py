@@ -518,6 +518,52 @@ def test_tc_conv_swizzled_halo_variant_is_bit_identical_to_halo(env, n, h, w, ci
     assert max_abs(b[2], ref) < 2e-6 * max(1.0, float(ref.abs().max()))
 
 
+@pytest.mark.parametrize("n,h,w,cin,cout,dil", [(1, 64, 96, 64, 256, 2), (2, 45, 77, 128, 256, 1), (1, 40, 56, 64, 512, 4),
+                                                (1, 33, 24, 128, 256, 3)])
+def test_tc_conv_pair_band_variant(env, n, h, w, cin, cout, dil):
+    """tc_conv_pair_band.cu (CTA pairs, one activation band per channel block and filter row, taps = row offsets into the
+    swizzled band): bit-identical to tc_conv_halo.cu where that applies (same (channel block, tap) order), within fp32
+    rounding of the tap-major pair kernel and of the fp64 convolution everywhere (dilation 3 / 4, ragged maps, BN + residual +
+    ReLU epilogue)."""
+    lib, cabi, View, dev = env
+    g = torch.Generator().manual_seed(h * w + cin + dil)
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5
+    sc, bi = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.2
+    res = torch.randn(n, cout, h, w, generator=g)
+    xs = View.alloc(n, h, w, cin, dev, split=True)
+    hi, lo = split_planes(nhwc(x))
+    xs.base.copy_(hi.view(-1)); xs.lo.copy_(lo.view(-1))
+    rs = View.alloc(n, h, w, cout, dev, split=True)
+    hi, lo = split_planes(nhwc(res))
+    rs.base.copy_(hi.view(-1)); rs.lo.copy_(lo.view(-1))
+    wh, wl = split_planes(wt.permute(0, 2, 3, 1).reshape(cout, -1).cuda())
+    scd, bid = sc.cuda(), bi.cuda()
+    outs = {}
+    for variant in (cabi.TC_PAIR, cabi.TC_PAIR_BAND) + ((cabi.TC_HALO,) if dil <= 2 else ()):
+        out = View.alloc(n, h, w, cout, dev, split=True)
+        out.base.fill_(float("nan")); out.lo.fill_(float("nan"))
+        d = cabi.TcConvDesc()
+        d.in_, d.out, d.residual = xs.ct(), out.ct(), rs.ct()
+        d.weight_hi, d.weight_lo, d.weight_ld = wh.data_ptr(), wl.data_ptr(), 9 * cin
+        d.scale, d.bias = scd.data_ptr(), bid.data_ptr()
+        d.cout, d.kh, d.kw, d.dilation, d.act, d.variant = cout, 3, 3, dil, 1, variant
+        cabi.check(lib.tdn_conv2d_tc(C.byref(d), None), "conv2d_tc")
+        torch.cuda.synchronize()
+        outs[variant] = (out.base.clone(), out.lo.clone(), out.torch().permute(0, 3, 1, 2).cpu())
+    band = outs[cabi.TC_PAIR_BAND]
+    assert not torch.isnan(band[2]).any()
+    if dil <= 2:
+        halo = outs[cabi.TC_HALO]
+        assert torch.equal(halo[0].view(torch.int16), band[0].view(torch.int16))
+        assert torch.equal(halo[1].view(torch.int16), band[1].view(torch.int16))
+    xr = (rs.base.float() + rs.lo.float()).view(n, h, w, cout).permute(0, 3, 1, 2).cpu().double()
+    ref = F.relu(F.conv2d(x.double(), wt.double(), None, 1, dil, dil) * sc.double().view(1, -1, 1, 1)
+                 + bi.double().view(1, -1, 1, 1) + xr)
+    assert max_abs(band[2], ref) < 3e-6 * max(1.0, float(ref.abs().max()))
+    assert max_abs(band[2], outs[cabi.TC_PAIR][2]) < 3e-6 * max(1.0, float(ref.abs().max()))
+
+
 def test_tc_conv_variant_errors(env):
     lib, cabi, View, dev = env
     xs = View.alloc(1, 8, 16, 64, dev, split=True)

@@ -17,7 +17,10 @@ from tdnet_b200 import _cabi as cabi  # noqa: E402
 def main():
     lib = cabi.load()
     shapes = [(1, 256, 512, 64, 64, 1), (1, 128, 256, 128, 128, 1), (1, 128, 256, 128, 128, 2), (2, 45, 77, 64, 128, 2),
-              (1, 128, 256, 256, 256, 2), (1, 128, 256, 512, 128, 1)]
+              (1, 128, 256, 256, 256, 2), (1, 128, 256, 512, 128, 1), (1, 128, 256, 512, 512, 4), (1, 128, 256, 256, 512, 2),
+              (1, 128, 256, 512, 512, 2), (2, 45, 77, 64, 256, 3)]
+    if len(sys.argv) > 1:
+        shapes = [s for s in shapes if s[4] % 256 == 0]
     g = torch.Generator().manual_seed(3)
     for n, h, w, cin, cout, dil in shapes:
         wt = (torch.randn(cout, 9 * cin, generator=g) / (9 * cin) ** 0.5).cuda()
@@ -28,7 +31,7 @@ def main():
         xl = (x - xh.float()).half().contiguous()
         res = {"shape": [n, h, w, cin, cout, dil]}
         ref = None
-        for name, variant in (("base", cabi.TC_BASE), ("base_ts", cabi.TC_BASE_TS), ("halo", cabi.TC_HALO), ("halo_sw", cabi.TC_HALO_SW)):
+        for name, variant in (("base", cabi.TC_BASE), ("base_ts", cabi.TC_BASE_TS), ("halo", cabi.TC_HALO), ("halo_sw", cabi.TC_HALO_SW), ("pair", cabi.TC_PAIR), ("band", cabi.TC_PAIR_BAND)):
             oh = torch.full((n, h, w, cout), float("nan"), dtype=torch.half, device="cuda")
             ol = torch.full((n, h, w, cout), float("nan"), dtype=torch.half, device="cuda")
             d = cabi.TcConvDesc()
@@ -44,6 +47,10 @@ def main():
             out = oh.float() + ol.float()
             if ref is None:
                 ref = out
+            if name == "halo":
+                ref_halo = out
+            if name == "band" and dil <= 2:
+                res["band_mismatch_vs_halo"] = int((out != ref_halo).sum())
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             for _ in range(3):
                 lib.tdn_conv2d_tc(C.byref(d), None)
