@@ -372,6 +372,13 @@ int tdn_fa_apply(const tdn_tensor* query, const float* f, const tdn_tensor* out,
 int tdn_add_upsampled(const tdn_tensor* a, const tdn_tensor* b, const tdn_tensor* up, const tdn_tensor* out,
                       void* stream);
 
+/* Diagnostics: the SM clock the chip actually runs at while other kernels are executing.  `blocks` CTAs of one warp (no
+ * shared memory, so they co-reside with the persistent tcgen05 kernels) each spin for at least min_ns nanoseconds of
+ * %globaltimer and write {elapsed %clock64 cycles, elapsed nanoseconds, SM id} to out[3 * block]: cycles / ns is that SM's
+ * clock in GHz during the interval.  NVML's clock reading lags the power management by far more than a kernel's run time
+ * (tools/clock_probe.py). */
+int tdn_sm_clock_probe(uint64_t* out, int32_t blocks, int64_t min_ns, void* stream);
+
 /* Library info / errors. */
 int tdn_abi_version(void);
 const char* tdn_strerror(int status);

@@ -114,6 +114,7 @@ SIGNATURES = {
     "tdn_fa_context_workspace_bytes": (C.c_uint64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "tdn_fa_apply": (C.c_int, [_TP, C.c_void_p, _TP, C.c_float, C.c_void_p, C.c_void_p]),
     "tdn_add_upsampled": (C.c_int, [_TP, _TP, _TP, _TP, C.c_void_p]),
+    "tdn_sm_clock_probe": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p]),
 }
 
 _lib = None

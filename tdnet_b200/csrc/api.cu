@@ -83,9 +83,36 @@ int device_sm_count() {
 
 using namespace tdn;
 
+namespace tdn {
+// one warp per CTA; lane 0 spins on %globaltimer and reports how many SM cycles passed meanwhile
+__global__ void sm_clock_probe_kernel(unsigned long long* out, long long min_ns) {
+  if (threadIdx.x != 0) return;
+  unsigned long long t0, t1, c0, c1;
+  unsigned int smid;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  asm volatile("mov.u64 %0, %%clock64;" : "=l"(c0));
+  do {
+    __nanosleep(200);
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+  } while ((long long)(t1 - t0) < min_ns);
+  asm volatile("mov.u64 %0, %%clock64;" : "=l"(c1));
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+  out[3 * blockIdx.x + 0] = c1 - c0;
+  out[3 * blockIdx.x + 1] = t1 - t0;
+  out[3 * blockIdx.x + 2] = smid;
+}
+}  // namespace tdn
+
 extern "C" {
 
 int tdn_abi_version(void) { return TDN_ABI_VERSION; }
+
+int tdn_sm_clock_probe(uint64_t* out, int32_t blocks, int64_t min_ns, void* stream) {
+  TDN_REQUIRE(out && blocks > 0 && min_ns > 0, TDN_ERR_INVALID, "sm_clock_probe: bad arguments");
+  tdn::sm_clock_probe_kernel<<<blocks, 32, 0, (cudaStream_t)stream>>>((unsigned long long*)out, (long long)min_ns);
+  TDN_LAUNCH_OK();
+  return TDN_OK;
+}
 
 const char* tdn_strerror(int status) {
   switch (status) {
