@@ -236,6 +236,31 @@ def cpu_baseline(n_frames=8):
     return {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample}
 
 
+def _sm_clock_probe_start(dev, after_stream, span_ms):
+    """Launches tdn_sm_clock_probe on a side stream behind `after_stream`: one-warp CTAs that co-reside with the frame's
+    kernels and compare %clock64 with %globaltimer for span_ms -- the SM clock the kernels really run at (NVML / nvidia-smi
+    lag the power management by more than the length of the timed region)."""
+    import torch
+    from tdnet_b200 import _cabi
+    lib = _cabi.load()
+    side = torch.cuda.Stream(dev)
+    out = torch.zeros(3 * 148, dtype=torch.int64, device=dev)
+    side.wait_stream(after_stream)
+    with torch.cuda.stream(side):
+        _cabi.check(lib.tdn_sm_clock_probe(out.data_ptr(), 148, int(span_ms * 1e6), side.cuda_stream), "sm_clock_probe")
+    return out, side
+
+
+def _sm_clock_probe_result(handle, where):
+    import statistics
+    out, side = handle
+    side.synchronize()
+    o = out.view(-1, 3).cpu()
+    mhz = sorted((1e3 * o[:, 0].double() / o[:, 1].double().clamp(min=1)).tolist())
+    return {"median": round(statistics.median(mhz), 1), "min": round(mhz[0], 1), "max": round(mhz[-1], 1),
+            "sms_sampled": len(set(o[:, 2].tolist())), "where": where}
+
+
 def run_ours(args, rank, world):
     import torch
     import torch.distributed as dist
@@ -289,6 +314,21 @@ def run_ours(args, rank, world):
     barrier()
     ms_dev = e0.elapsed_time(e1)
     clocks = sampler.stop() if sampler else None
+    # the SM clock measured ON the SMs, in a repetition of the same loop right after the timed region (not inside it: `value`
+    # is taken without the probe's CTAs on the chip)
+    if rank == 0 and clocks is not None:
+        try:
+            for i in range(args.steps):
+                if i == args.steps // 3:
+                    handle = _sm_clock_probe_start(dev, stream, 0.5 * ms_dev)
+                net(dev_frames[step % N_DISTINCT_FRAMES], pos_id=step % PATHS)
+                step += 1
+            torch.cuda.synchronize(dev)
+            clocks["sm_mhz_on_sm"] = _sm_clock_probe_result(
+                handle, "tdn_sm_clock_probe during the middle of a repetition of the timed loop, right after it")
+        except Exception as exc:  # noqa: BLE001 -- a diagnostic must not cost the bench line
+            clocks["sm_mhz_on_sm"] = {"error": repr(exc)[:200]}
+    barrier()
 
     # ---- timed region B: end to end through the public API, the way a streaming caller drives it:
     #      pinned host frame -> H2D (copy stream, double-buffered) -> model(image, pos_id) -> argmax
@@ -389,6 +429,7 @@ def run_ours(args, rank, world):
         barrier()
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         probes = {"dom": [], "attn": []}
+        sus_probe = None
         pace = torch.cuda.Event()
         s0.record(stream)
         for i in range(n_sus):
@@ -403,6 +444,11 @@ def run_ours(args, rank, world):
             else:
                 net(dev_frames[step % N_DISTINCT_FRAMES], pos_id=pos)
             step += 1
+            if rank == 0 and i == (3 * n_sus) // 4:
+                try:
+                    sus_probe = _sm_clock_probe_start(dev, stream, 30.0)
+                except Exception:  # noqa: BLE001
+                    sus_probe = None
             if i % 64 == 63:                  # bound the launch queue without draining it
                 pace.synchronize() if i > 63 else None
                 pace.record(stream)
@@ -410,6 +456,11 @@ def run_ours(args, rank, world):
         barrier()
         ms_sus = s0.elapsed_time(s1)
         clocks2 = sampler2.stop() if sampler2 else None
+        if clocks2 is not None and sus_probe is not None:
+            try:
+                clocks2["sm_mhz_on_sm"] = _sm_clock_probe_result(sus_probe, "tdn_sm_clock_probe, 30 ms at three quarters of the loop")
+            except Exception as exc:  # noqa: BLE001
+                clocks2["sm_mhz_on_sm"] = {"error": repr(exc)[:200]}
         _, ms_sus, fps_sus = whole_job_throughput(n_sus, ms_sus, device=dev)
         mean = lambda ev: (sum(a.elapsed_time(b) for a, b in ev) / len(ev)) if ev else None  # noqa: E731
         sustained = {"seconds": ms_sus / 1e3, "frames_per_gpu": n_sus, "value": fps_sus, "unit": "frames/s",
