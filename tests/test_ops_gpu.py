@@ -564,6 +564,21 @@ def test_tc_conv_pair_band_variant(env, n, h, w, cin, cout, dil):
     assert max_abs(band[2], outs[cabi.TC_PAIR][2]) < 3e-6 * max(1.0, float(ref.abs().max()))
 
 
+def test_sm_clock_probe(env):
+    """tdn_sm_clock_probe: %clock64 cycles per %globaltimer nanosecond on a few SMs = a plausible SM clock, and the spin lasts
+    at least the requested time (the diagnostic behind bench.py's clocks.sm_mhz_on_sm)."""
+    lib, cabi, View, dev = env
+    blocks = 8
+    out = torch.zeros(3 * blocks, dtype=torch.int64, device=dev)
+    cabi.check(lib.tdn_sm_clock_probe(out.data_ptr(), blocks, 2_000_000, None), "sm_clock_probe")
+    torch.cuda.synchronize()
+    o = out.view(blocks, 3).cpu()
+    assert bool((o[:, 1] >= 2_000_000).all())
+    ghz = o[:, 0].double() / o[:, 1].double()
+    assert bool((ghz > 0.3).all()) and bool((ghz < 3.0).all()), ghz
+    assert lib.tdn_sm_clock_probe(None, blocks, 2_000_000, None) < 0      # null output: TDN_ERR_INVALID, nothing launched
+
+
 def test_tc_conv_variant_errors(env):
     lib, cabi, View, dev = env
     xs = View.alloc(1, 8, 16, 64, dev, split=True)
