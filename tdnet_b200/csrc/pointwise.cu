@@ -292,7 +292,11 @@ __global__ void psp_rowsum_generic_kernel(View in, float* __restrict__ rowsum) {
 
 // Pass 2.  A block per bin; BS_GROUPS thread groups walk interleaved rows of the bin (the 1x1 bin sums all H rows: one
 // serial walk per channel was 14 us of pure load latency) and their partial sums are added in group order (fixed order).
+// 1024 threads = 4 groups x 256 channels per pass, eight loads in flight per thread: the 1x1 bin of a 128-row map is 2 passes x
+// 4 round trips to L2.  (The first version of this kernel had 512 threads = 4 groups x 128 channels and four loads in flight:
+// 4 passes x 8 round trips, 24 us -- slower than the serial walk it replaced; found in the launch list of the third session.)
 constexpr int BS_GROUPS = 4;
+constexpr int BS_THREADS = 1024;
 __global__ void psp_binsum_kernel(const float* __restrict__ rowsum, View out, int H, int W) {
   extern __shared__ float bs_part[];                 // [BS_GROUPS - 1][C]
   const int bin = blockIdx.x, b = blockIdx.y;
@@ -312,7 +316,7 @@ __global__ void psp_binsum_kernel(const float* __restrict__ rowsum, View out, in
     const int c = c0 + t;
     float s = 0.f;
     if (c < C) {
-#pragma unroll 4
+#pragma unroll 8
       for (int y = y0 + grp; y < y1; y += BS_GROUPS)
         s += rowsum[(((long long)(b * H + y) * PSP_PARTS) * 12 + roff + j) * C + c];
       if (grp > 0) bs_part[(grp - 1) * C + c] = s;
@@ -355,7 +359,7 @@ int psp_pool(const tdn_tensor* in, const tdn_tensor* out, float* workspace, size
     psp_rowsum_generic_kernel<<<dim3(in->h, in->n), threads, 0, stream>>>(make_view(*in), workspace);
   }
   TDN_LAUNCH_OK();
-  psp_binsum_kernel<<<dim3(50, in->n), 512, (BS_GROUPS - 1) * in->c * sizeof(float), stream>>>(workspace, make_view(*out),
+  psp_binsum_kernel<<<dim3(50, in->n), BS_THREADS, (BS_GROUPS - 1) * in->c * sizeof(float), stream>>>(workspace, make_view(*out),
                                                                                               in->h, in->w);
   TDN_LAUNCH_OK();
   return TDN_OK;
