@@ -32,13 +32,14 @@
 
 namespace tdn {
 
-// TSA ("A through tensor memory"): the MMA warp copies the A tile of every K block from shared memory into one of two
-// 64-column TMEM buffers (tcgen05.cp, 8 slabs of 128 rows x 32 bytes: hi plane then lo plane) and the twelve exact-mode MMAs
-// take A from there (tcgen05.mma [d], [a_tmem], b_desc): shared memory is then read once per K block for A (32 KB) instead of
-// twelve times 4 KB, and the MMAs fetch only B.  Why: MMAs with both operands in shared memory and N <= 128 retire at about half
-// their tensor rate in every kernel of this library, the tensor-memory-operand MMAs of the attention
-// kernel at their full rate.  The ring of chunk accumulators shrinks from 512 to 384 columns.  Same products in the same
-// order: bit-identical.
+// TSA ("A through tensor memory"; TDN_TC_BASE_TS, an experiment kept as an explicit variant): the MMA warp copies the A tile of
+// every K block from shared memory into one of two 64-column TMEM buffers (tcgen05.cp.128x256b, 8 slabs of 128 rows x 32
+// bytes: hi plane then lo plane, the source named by the same SWIZZLE_128B descriptor an MMA would use) and the twelve
+// exact-mode MMAs take A from there (tcgen05.mma [d], [a_tmem], b_desc); copies and MMAs of one thread execute in issue order,
+// so nothing else synchronises them.  Shared memory is then read once per K block for A (32 KB) instead of twelve times 4 KB;
+// the ring of chunk accumulators shrinks from 512 to 384 columns.  Same products in the same order: bit-identical.
+// Hypothesis tested: the N <= 128 kernels (K blocks of 2-3x their tensor time) wait for shared-memory operand reads.
+// Result: 12-16 % SLOWER on every shape -- they do not; DESIGN.md section 10, third session.
 template <int BLOCK_N, bool TSA = false>
 struct TcCfg {
   static constexpr int B_PLANE = BLOCK_N * TC_BLOCK_K * 2;

@@ -17,8 +17,8 @@
 // Activation traffic per output tile and channel block: 16 x (16 + 2d) = 288 / 320 px instead of 9 x 128.
 // Result (tools/halo_probe.py, profiles/r02_halo_probe.txt): NOT faster than the no-swizzle region -- layer 2 39.2 vs 39.7 us,
 // dilation 2 39.2 vs 42.2 us, layer 1 54.2 vs 52.5 us (per-tap kernel: 46.5) -- so the operand layout was not what slows the
-// halo kernel's MMAs; shared-memory-operand MMAs of N <= 128 retire at about half rate in every kernel of this library
-// (DESIGN.md section 10).  Kept as an explicit variant (TDN_TC_HALO_SW), never picked by TDN_TC_AUTO.  Arithmetic (exact mode, chunked fp32 accumulation, epilogue) is identical to
+// halo kernel's K blocks (they take 2-3x their tensor time in every N <= 128 kernel of this library, whatever the layout or
+// the operand source: DESIGN.md section 10).  Kept as an explicit variant (TDN_TC_HALO_SW), never picked by TDN_TC_AUTO.  Arithmetic (exact mode, chunked fp32 accumulation, epilogue) is identical to
 // tc_conv.cu: same products in the same order, bit-identical output.
 #include "tc_common.cuh"
 

@@ -37,13 +37,13 @@ struct PairCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 512;
 };
 
-// QUAD: clusters of FOUR CTAs = two pairs that work on the same output-channel tile of two consecutive rows of pair tiles
-// and share its weights: each CTA fetches ONE plane (pair 0: hi, pair 1: lo) of its half of the B rows and multicasts it to
-// the CTA of the same parity in the other pair.  Why: the pair kernel is paced by the L2 -> SM path, not by the MMAs
-// (tools/quant_probe.py: an N = 128 pair tile with half the MMA work takes as long as an N = 256 tile; ~33 B/clk per SM
-// arrive in both cases against ~42 B/clk chip-wide TMA throughput); the weights are half of those bytes and identical for
-// every cluster.  The stage ring couples the two pairs: a stage is free when the MMAs of BOTH pairs that read it have
-// retired (two multicast commits per `empty` barrier).
+// QUAD (TDN_TC_PAIR_QUAD, an experiment kept as an explicit variant): clusters of FOUR CTAs = two pairs that work on the same
+// output-channel tile of two consecutive rows of pair tiles and share its weights: each CTA fetches ONE plane (pair 0: hi,
+// pair 1: lo) of its half of the B rows and multicasts it to the CTA of the same parity in the other pair.  The stage ring
+// couples the two pairs: a stage is free when the MMAs of BOTH pairs that read it have retired (two multicast commits per
+// `empty` barrier).  Hypothesis tested: the pair kernel is paced by L2 reads (the weights are half of its bytes and identical
+// for every cluster).  Result: half the L2 reads of B move the tile time by 1.6 % (and only 33 clusters of four are
+// resident against 74 of two) -- it is not; DESIGN.md section 10, third session.
 template <int BLOCK_N, bool QUAD>
 __global__ void __cluster_dims__(QUAD ? 4 : 2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 tc_conv_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,

@@ -1,19 +1,19 @@
 // tcgen05 3x3 convolution on CTA pairs with ONE activation load per (channel block, filter ROW): the "band" variant of
 // tc_conv_pair.cu for the wide dilated layers (ResNet layer 3 / 4: 3x3, stride 1, dilation <= 4, cout % 256 == 0).
 //
-// Why: every conv kernel of this library takes 25-35 bytes per clock into an SM, whatever its tile shape, operand layout or
-// operand source (third session), and tc_conv_pair.cu needs 64 KB per K block and CTA (32 KB of
-// activations + 32 KB of weights) for 1 536 cycles of MMAs = 42 B/clk: it runs at ~1 860 cycles per K block, paced by its
-// bytes.  The three taps of one filter row read the same pixels shifted by the dilation, so here a CTA loads, per 64-channel
-// block and filter row ky, ONE band of 16 rows x 16 pixels around its 16 x 8 pixel tile (the halo in x only) and the taps
-// kx = 0, 1, 2 read it in place:
+// Hypothesis tested (TDN_TC_PAIR_BAND, an experiment kept as an explicit variant): tc_conv_pair.cu is paced by the bytes that
+// enter the SM -- it needs 64 KB per K block and CTA (32 KB of activations + 32 KB of weights) for 1 536 cycles of MMAs and
+// takes ~2 250.  The three taps of one filter row read the same pixels shifted by the dilation, so here a CTA loads, per
+// 64-channel block and filter row ky, ONE band of 16 rows x 16 pixels around its 16 x 8 pixel tile (the halo in x only) and
+// the taps kx = 0, 1, 2 read it in place.  Result: correct on the first run, 17 % fewer bytes into the SM, and the same time
+// as tc_conv_pair.cu on every layer-3 / layer-4 shape (336.7 vs 333.4 us at 512 -> 512, dilation 4) -- it is not; DESIGN.md
+// section 10, third session.
 //   * the band lives in shared memory like every other operand: rows of 128 bytes (64 channels of a pixel), SWIZZLE_128B,
 //     one TMA box per plane; it is 16 pixels wide, so a pixel's swizzle phase is its column & 7 in every band row;
 //   * with BW = 8 an output-tile row is one 8-row swizzle group: the A descriptor of tap kx starts kx * d rows (128 B each)
 //     into the band, SBO = 2048 B; the start is not 1024-byte aligned, which needs nothing (the hardware swizzles by
 //     absolute address: tc_conv_halo_sw.cu);
-//   * activation bytes per K block: 64 KB / 3 instead of 32 KB -- 53 KB per K block and CTA with the weights, 35 B/clk at the
-//     MMA rate.
+//   * activation bytes per K block: 64 KB / 3 instead of 32 KB -- 53 KB per K block and CTA with the weights.
 // A full halo region (all nine taps) would need 16 x 24 pixels x 2 planes = 96 KB per channel block at dilation 4, which does
 // not fit twice next to a weight ring; bands of one filter row do: 2 x 64 KB of bands + 3 x 32 KB of weights.
 // K blocks run in (channel block, ky, kx) order -- the order of tc_conv_halo.cu, bit-identical to it where both apply; against
