@@ -50,7 +50,7 @@ DOMINANT_GFLOP = 154.62        # layer4 3x3 512->512 dilated conv at 128x256 (SU
 ATTN_GFLOP = 77.31             # fused attention-propagation kernel, big hop: 2*32768*2048*(64+512)
 ATTN_NECESSARY_GFLOP = 3 * ATTN_GFLOP   # the fp32-faithful exact mode needs 3 fp16 products per algorithmic product
 ATTN_EXECUTED_GFLOP = 3 * (68.72 + 2 * 8.59) + 2 * 8.59   # + QK^T once per 256-channel slice + the single-product max pass
-ATTN_TRAFFIC_BYTES = 107.3e6       # ncu --set full of the r02 TMEM-operand kernels, dram read+write: (70.3 + 22.1) + (14.8 + 0.0) MB (profiles/r02_prof_attn_ts_c_summary.txt)
+ATTN_TRAFFIC_BYTES = 114.2e6       # ncu --set full of the final single-launch TMEM-operand kernel, dram read + write: 80.8 + 33.5 MB (profiles/r02_prof_attn_s128_summary.txt, first kernel)
 DOMINANT_TRAFFIC_BYTES = 107.5e6   # ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum (profiles/r01_*)
 N_DISTINCT_FRAMES = 8
 
@@ -532,7 +532,7 @@ def run_ours(args, rank, world):
             sustained and sustained["attention_ms_per_launch"], ATTN_TRAFFIC_BYTES,
             "algorithmic = 2*Pq*P'*(d_k+d_v) = 77.31 GFLOP (SURVEY.md 8d); necessary = 3 x algorithmic (exact mode, one QK^T "
             "per query tile); executed additionally counts the second QK^T per 256-channel slice and the single-product "
-            "max pass (275 GFLOP) and is NOT progress; traffic = dram read+write bytes of the op's two launches (ncu; "
+            "max pass (275 GFLOP) and is NOT progress; traffic = dram read+write bytes of the op's single launch (ncu --set full, standalone; "
             "algorithmic: Q 8 MB + out 67 MB + residual 67 MB, K / V'^T stay in L2)")
         line = {
             "metric": _metric(), "value": fps, "unit": "frames/s", "n_gpus": world,
