@@ -105,6 +105,29 @@ def main():
     def idle_work(ms):
         return 0
 
+    if "--cublas" in sys.argv:
+        # the yardstick: cuBLAS bf16 GEMM 8192^3 (what MEASURED_PEAKS.json's bf16_tflops times), with the clock it runs at
+        n8 = 8192
+        ma = torch.randn(n8, n8, device="cuda", dtype=torch.bfloat16)
+        mb = torch.randn(n8, n8, device="cuda", dtype=torch.bfloat16)
+        mc = torch.empty(n8, n8, device="cuda", dtype=torch.bfloat16)
+        state = {"n": 0, "t0": None}
+
+        def gemm_work(ms):
+            n = int(ms / 0.66) + 1
+            for _ in range(n):
+                torch.matmul(ma, mb, out=mc)
+            return n
+        for label, warm in (("cuBLAS bf16 8192^3, back to back", 30.0), ("cuBLAS bf16 8192^3, 300 ms before the probe", 300.0)):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            probe(lib, label, gemm_work, warm_ms=warm)
+            e0.record()
+            k = gemm_work(20.0)
+            e1.record()
+            torch.cuda.synchronize()
+            print(json.dumps({"case": label + " (the 20 ms right after, no probe CTAs)", "tflops": round(k * 2 * n8 ** 3 / e0.elapsed_time(e1) / 1e9, 1)}), flush=True)
+        return
     probe(lib, "idle (probe CTAs only)", idle_work)
     probe(lib, "layer-4 pair convolution, back to back", conv_work)
     probe(lib, "layer-4 pair convolution, 300 ms before the probe", conv_work, warm_ms=300.0)
